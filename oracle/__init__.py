@@ -1,0 +1,272 @@
+"""ctypes bindings for the CPU checker.  TEST INFRASTRUCTURE ONLY.
+
+Two libraries live here:
+
+* ``liboracle.so``  -- the C restatement of the reference matcher
+  (``osfm_oracle.c``; each function cites the reference file:line it follows).
+* ``_ref/libosfm_ref.so`` -- the UNMODIFIED reference sources compiled in place
+  from ``/root/reference`` plus a thin ``extern "C"`` driver (``ref_driver.cc``).
+  It can only be (re)built where ``/root/reference`` exists; the prebuilt file
+  travels to the GPU box.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this package.  The product
+(``orthosfm_b200``) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libosfm_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the restatement and, where the reference tree exists, the reference."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    if ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "mve", "sfm")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+class NNResult(C.Structure):
+    _fields_ = [("dist_1st_best", C.c_float), ("dist_2nd_best", C.c_float),
+                ("index_1st_best", C.c_int), ("index_2nd_best", C.c_int)]
+
+    def astuple(self):
+        return (self.dist_1st_best, self.dist_2nd_best,
+                self.index_1st_best, self.index_2nd_best)
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _c(a, dtype) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+_KIND = {
+    "u8": (np.uint8, C.c_uint8, 128),
+    "s8": (np.int8, C.c_int8, 64),
+    "f32": (np.float32, C.c_float, 128),
+}
+
+
+class _Impl:
+    """Shared front-end over either library (prefix 'osfm_oracle_' or 'osfm_ref_')."""
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} missing: run `make -C oracle` (and `make -C oracle ref` "
+                f"where /root/reference exists)")
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.is_ref = prefix == "osfm_ref_"
+        f = self._f
+        f("num_threads").restype = C.c_int
+        f("count_consistent").restype = C.c_int
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def num_threads(self) -> int:
+        return int(self._f("num_threads")())
+
+    # -- NearestNeighbor<T>::find ------------------------------------
+    def nn(self, kind: str, query, elements, sse3_order: bool = True):
+        npdt, ct, _ = _KIND[kind]
+        q = _c(query, npdt)
+        e = _c(elements, npdt).reshape(-1, q.shape[-1])
+        r = NNResult()
+        args = [_ptr(q, ct), _ptr(e, ct), C.c_int(e.shape[0]), C.c_int(q.shape[-1])]
+        if kind == "f32" and not self.is_ref:
+            args.append(C.c_int(1 if sse3_order else 0))
+        self._f("nn_" + kind)(*args, C.byref(r))
+        return r.astuple()
+
+    # -- Matching::twoway_match<T> -----------------------------------
+    def twoway(self, kind: str, set_1, set_2, ratio: float, dist: float = FLT_MAX,
+               sse3_order: bool = True):
+        npdt, ct, dim = _KIND[kind]
+        a = _c(set_1, npdt)
+        b = _c(set_2, npdt)
+        if a.ndim == 2:
+            dim = a.shape[1]
+        elif b.ndim == 2:
+            dim = b.shape[1]
+        a = a.reshape(-1, dim)
+        b = b.reshape(-1, dim)
+        n1, n2 = a.shape[0], b.shape[0]
+        m12 = np.full(max(n1, 1), -7, dtype=np.int32)
+        m21 = np.full(max(n2, 1), -7, dtype=np.int32)
+        args = [_ptr(a, ct), C.c_int(n1), _ptr(b, ct), C.c_int(n2), C.c_int(dim),
+                C.c_float(ratio), C.c_float(dist)]
+        if kind == "f32" and not self.is_ref:
+            args.append(C.c_int(1 if sse3_order else 0))
+        self._f("twoway_" + kind)(*args, _ptr(m12, C.c_int), _ptr(m21, C.c_int))
+        return m12[:n1].copy(), m21[:n2].copy()
+
+    # -- filters -----------------------------------------------------
+    def remove_inconsistent(self, m12, m21):
+        a = _c(m12, np.int32).copy()
+        b = _c(m21, np.int32).copy()
+        self._f("remove_inconsistent")(_ptr(a, C.c_int), C.c_int(a.size),
+                                       _ptr(b, C.c_int), C.c_int(b.size))
+        return a, b
+
+    def count_consistent(self, m12, m21) -> int:
+        a = _c(m12, np.int32)
+        b = _c(m21, np.int32)
+        return int(self._f("count_consistent")(_ptr(a, C.c_int), C.c_int(a.size),
+                                               _ptr(b, C.c_int), C.c_int(b.size)))
+
+    def combine_results(self, sift_12, sift_21, surf_12, surf_21):
+        s12, s21 = _c(sift_12, np.int32), _c(sift_21, np.int32)
+        f12, f21 = _c(surf_12, np.int32), _c(surf_21, np.int32)
+        o12 = np.full(max(s12.size + f12.size, 1), -7, dtype=np.int32)
+        o21 = np.full(max(s21.size + f21.size, 1), -7, dtype=np.int32)
+        self._f("combine_results")(
+            _ptr(s12, C.c_int), C.c_int(s12.size), _ptr(s21, C.c_int), C.c_int(s21.size),
+            _ptr(f12, C.c_int), C.c_int(f12.size), _ptr(f21, C.c_int), C.c_int(f21.size),
+            _ptr(o12, C.c_int), _ptr(o21, C.c_int))
+        return o12[:s12.size + f12.size].copy(), o21[:s21.size + f21.size].copy()
+
+    def match_filtered(self, kind: str, set_1, set_2, ratio: float):
+        """twoway_match + remove_inconsistent_matches (the reference's timed unit)."""
+        m12, m21 = self.twoway(kind, set_1, set_2, ratio)
+        return self.remove_inconsistent(m12, m21)
+
+
+class Oracle(_Impl):
+    """The C restatement (liboracle.so)."""
+
+    def __init__(self):
+        super().__init__(_ORACLE_SO, "osfm_oracle_")
+        self.lib.osfm_oracle_pairwise_match_lowres.restype = C.c_int
+
+    def quantize_sift(self, desc) -> np.ndarray:
+        d = _c(desc, np.float32).reshape(-1, 128)
+        out = np.empty(d.shape, dtype=np.uint8)
+        self.lib.osfm_oracle_quantize_sift(_ptr(d, C.c_float), C.c_int(d.shape[0]),
+                                           _ptr(out, C.c_uint8))
+        return out
+
+    def quantize_surf(self, desc) -> np.ndarray:
+        d = _c(desc, np.float32).reshape(-1, 64)
+        out = np.empty(d.shape, dtype=np.int8)
+        self.lib.osfm_oracle_quantize_surf(_ptr(d, C.c_float), C.c_int(d.shape[0]),
+                                           _ptr(out, C.c_int8))
+        return out
+
+    @staticmethod
+    def _sets(sift_1, sift_2, surf_1, surf_2):
+        s1 = _c(sift_1, np.uint8).reshape(-1, 128)
+        s2 = _c(sift_2, np.uint8).reshape(-1, 128)
+        f1 = _c(surf_1, np.int8).reshape(-1, 64)
+        f2 = _c(surf_2, np.int8).reshape(-1, 64)
+        return s1, s2, f1, f2
+
+    def pairwise_match(self, sift_1, sift_2, surf_1, surf_2):
+        """ExhaustiveMatching::pairwise_match on already-quantised descriptors."""
+        s1, s2, f1, f2 = self._sets(sift_1, sift_2, surf_1, surf_2)
+        n12 = (s1.shape[0] if s1.shape[0] else 0) + (f1.shape[0] if f1.shape[0] else 0)
+        n21 = (s2.shape[0] if s1.shape[0] else 0) + (f2.shape[0] if f1.shape[0] else 0)
+        m12 = np.full(max(n12, 1), -7, dtype=np.int32)
+        m21 = np.full(max(n21, 1), -7, dtype=np.int32)
+        self.lib.osfm_oracle_pairwise_match(
+            _ptr(s1, C.c_uint8), C.c_int(s1.shape[0]), _ptr(s2, C.c_uint8), C.c_int(s2.shape[0]),
+            _ptr(f1, C.c_int8), C.c_int(f1.shape[0]), _ptr(f2, C.c_int8), C.c_int(f2.shape[0]),
+            _ptr(m12, C.c_int), _ptr(m21, C.c_int))
+        return m12[:n12].copy(), m21[:n21].copy()
+
+    def pairwise_match_lowres(self, sift_1, sift_2, surf_1, surf_2, num_features: int) -> int:
+        s1, s2, f1, f2 = self._sets(sift_1, sift_2, surf_1, surf_2)
+        return int(self.lib.osfm_oracle_pairwise_match_lowres(
+            _ptr(s1, C.c_uint8), C.c_int(s1.shape[0]), _ptr(s2, C.c_uint8), C.c_int(s2.shape[0]),
+            _ptr(f1, C.c_int8), C.c_int(f1.shape[0]), _ptr(f2, C.c_int8), C.c_int(f2.shape[0]),
+            C.c_int(num_features)))
+
+
+class Reference(_Impl):
+    """The reference itself, compiled from /root/reference (oracle/_ref)."""
+
+    def __init__(self):
+        super().__init__(_REF_SO, "osfm_ref_")
+        L = self.lib
+        L.osfm_ref_match_pairs_u8.restype = C.c_long
+        L.osfm_ref_exhaustive_create.restype = C.c_void_p
+        L.osfm_ref_exhaustive_pairwise_match_lowres.restype = C.c_int
+        L.osfm_ref_sift_gray8.restype = C.c_int
+
+    def match_pairs_u8(self, views, pairs, ratio: float = 0.8):
+        """twoway_match + remove_inconsistent over a pair list, OpenMP over pairs
+        (bundler_matching.cc:74).  Returns per-pair consistent-match counts."""
+        views = [_c(v, np.uint8).reshape(-1, 128) for v in views]
+        ptrs = (C.POINTER(C.c_uint8) * len(views))(*[_ptr(v, C.c_uint8) for v in views])
+        sizes = np.array([v.shape[0] for v in views], dtype=np.int32)
+        pr = _c(pairs, np.int32).reshape(-1, 2)
+        counts = np.zeros(max(pr.shape[0], 1), dtype=np.int32)
+        self.lib.osfm_ref_match_pairs_u8(ptrs, _ptr(sizes, C.c_int), C.c_int(len(views)),
+                                         _ptr(pr, C.c_int), C.c_int(pr.shape[0]),
+                                         C.c_float(ratio), _ptr(counts, C.c_int))
+        return counts[:pr.shape[0]].copy()
+
+    def exhaustive(self, views_float):
+        """views_float: list of (sift n x 128 float32, surf n x 64 float32)."""
+        return _RefExhaustive(self, views_float)
+
+    def sift_gray8(self, pixels: np.ndarray, max_desc: int = 1 << 16) -> np.ndarray:
+        img = _c(pixels, np.uint8)
+        h, w = img.shape
+        out = np.zeros((max_desc, 128), dtype=np.float32)
+        n = self.lib.osfm_ref_sift_gray8(_ptr(img, C.c_uint8), C.c_int(w), C.c_int(h),
+                                         _ptr(out, C.c_float), C.c_int(max_desc))
+        return out[:n].copy()
+
+
+class _RefExhaustive:
+    def __init__(self, ref: Reference, views_float):
+        self.L = ref.lib
+        self.sizes = []
+        self.h = C.c_void_p(self.L.osfm_ref_exhaustive_create(C.c_int(len(views_float))))
+        for v, (sift, surf) in enumerate(views_float):
+            s = _c(sift, np.float32).reshape(-1, 128)
+            f = _c(surf, np.float32).reshape(-1, 64)
+            self.sizes.append(s.shape[0] + f.shape[0])
+            self.L.osfm_ref_exhaustive_set_view(self.h, C.c_int(v),
+                                                _ptr(s, C.c_float), C.c_int(s.shape[0]),
+                                                _ptr(f, C.c_float), C.c_int(f.shape[0]))
+        self.L.osfm_ref_exhaustive_init(self.h)
+
+    def pairwise_match(self, v1: int, v2: int):
+        m12 = np.full(self.sizes[v1] + 1, -7, dtype=np.int32)
+        m21 = np.full(self.sizes[v2] + 1, -7, dtype=np.int32)
+        n12, n21 = C.c_int(0), C.c_int(0)
+        self.L.osfm_ref_exhaustive_pairwise_match(self.h, C.c_int(v1), C.c_int(v2),
+                                                  _ptr(m12, C.c_int), C.byref(n12),
+                                                  _ptr(m21, C.c_int), C.byref(n21))
+        return m12[:n12.value].copy(), m21[:n21.value].copy()
+
+    def pairwise_match_lowres(self, v1: int, v2: int, num_features: int) -> int:
+        return int(self.L.osfm_ref_exhaustive_pairwise_match_lowres(
+            self.h, C.c_int(v1), C.c_int(v2), C.c_int(num_features)))
+
+    def __del__(self):
+        try:
+            self.L.osfm_ref_exhaustive_destroy(self.h)
+        except Exception:
+            pass

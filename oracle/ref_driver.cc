@@ -1,0 +1,361 @@
+/*
+ * ref_driver.cc -- thin extern "C" driver around the UNMODIFIED reference
+ * matcher.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file contains no reference code.  It is compiled together with the
+ * reference's own sources where they lie under /root/reference (see
+ * oracle/Makefile, target _ref) into oracle/_ref/libosfm_ref.so, which is used
+ * (a) to pin the C restatement in osfm_oracle.c, (b) to generate the golden
+ * fixtures in tests/golden/, and (c) as the "reference" CPU baseline timed by
+ * bench.py.  oracle/_ref/ is git-ignored; the prebuilt .so travels to the GPU
+ * box with the gpurun snapshot.
+ *
+ * Reference entry points bound here (paths relative to /root/reference):
+ *   sfm::Matching::twoway_match<T>            src/mve/sfm/matching.h:148-159
+ *   sfm::Matching::oneway_match<T>            src/mve/sfm/matching.h:114-146
+ *   sfm::Matching::remove_inconsistent_matches src/mve/sfm/matching.cc:19-36
+ *   sfm::Matching::count_consistent_matches   src/mve/sfm/matching.cc:39-47
+ *   sfm::Matching::combine_results            src/mve/sfm/matching.cc:50-89
+ *   sfm::NearestNeighbor<T>::find             src/mve/sfm/nearest_neighbor.cc:216-289
+ *   sfm::ExhaustiveMatching::{init,pairwise_match,pairwise_match_lowres}
+ *                                             src/mve/sfm/exhaustive_matching.cc:56,115,147
+ *   sfm::Sift::process                        src/mve/sfm/sift.cc (fixture producer only)
+ */
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "sfm/bundler_common.h"
+#include "sfm/exhaustive_matching.h"
+#include "sfm/matching.h"
+#include "sfm/nearest_neighbor.h"
+#include "sfm/sift.h"
+#include "util/aligned_memory.h"
+
+namespace
+{
+    template <typename T, typename S>
+    util::AlignedMemory<T, 16>
+    widen (S const* src, std::size_t count)
+    {
+        util::AlignedMemory<T, 16> out(count + 8);
+        for (std::size_t i = 0; i < count; ++i)
+            out[i] = static_cast<T>(src[i]);
+        return out;
+    }
+
+    void
+    copy_out (std::vector<int> const& v, int* dst)
+    {
+        if (!v.empty())
+            std::memcpy(dst, v.data(), sizeof(int) * v.size());
+    }
+
+    sfm::Matching::Options
+    make_opts (int dim, float ratio, float dist)
+    {
+        sfm::Matching::Options o;
+        o.descriptor_length = dim;
+        o.lowe_ratio_threshold = ratio;
+        o.distance_threshold = dist;
+        return o;
+    }
+}
+
+extern "C" {
+
+struct osfm_ref_nn_result
+{
+    float dist_1st_best;
+    float dist_2nd_best;
+    int index_1st_best;
+    int index_2nd_best;
+};
+
+int
+osfm_ref_num_threads (void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---- NearestNeighbor<T>::find ------------------------------------- */
+
+void
+osfm_ref_nn_u8 (const uint8_t* query, const uint8_t* elements, int n, int dim,
+    osfm_ref_nn_result* out)
+{
+    auto q = widen<unsigned short>(query, dim);
+    auto e = widen<unsigned short>(elements, (std::size_t)n * dim);
+    sfm::NearestNeighbor<unsigned short> nn;
+    nn.set_elements(e.data());
+    nn.set_num_elements(n);
+    nn.set_element_dimensions(dim);
+    sfm::NearestNeighbor<unsigned short>::Result r;
+    nn.find(q.data(), &r);
+    out->dist_1st_best = static_cast<float>(r.dist_1st_best);
+    out->dist_2nd_best = static_cast<float>(r.dist_2nd_best);
+    out->index_1st_best = r.index_1st_best;
+    out->index_2nd_best = r.index_2nd_best;
+}
+
+void
+osfm_ref_nn_s8 (const int8_t* query, const int8_t* elements, int n, int dim,
+    osfm_ref_nn_result* out)
+{
+    auto q = widen<short>(query, dim);
+    auto e = widen<short>(elements, (std::size_t)n * dim);
+    sfm::NearestNeighbor<short> nn;
+    nn.set_elements(e.data());
+    nn.set_num_elements(n);
+    nn.set_element_dimensions(dim);
+    sfm::NearestNeighbor<short>::Result r;
+    nn.find(q.data(), &r);
+    out->dist_1st_best = static_cast<float>(r.dist_1st_best);
+    out->dist_2nd_best = static_cast<float>(r.dist_2nd_best);
+    out->index_1st_best = r.index_1st_best;
+    out->index_2nd_best = r.index_2nd_best;
+}
+
+void
+osfm_ref_nn_f32 (const float* query, const float* elements, int n, int dim,
+    osfm_ref_nn_result* out)
+{
+    auto q = widen<float>(query, dim);
+    auto e = widen<float>(elements, (std::size_t)n * dim);
+    sfm::NearestNeighbor<float> nn;
+    nn.set_elements(e.data());
+    nn.set_num_elements(n);
+    nn.set_element_dimensions(dim);
+    sfm::NearestNeighbor<float>::Result r;
+    nn.find(q.data(), &r);
+    out->dist_1st_best = r.dist_1st_best;
+    out->dist_2nd_best = r.dist_2nd_best;
+    out->index_1st_best = r.index_1st_best;
+    out->index_2nd_best = r.index_2nd_best;
+}
+
+/* ---- Matching::twoway_match<T> ------------------------------------ */
+
+void
+osfm_ref_twoway_u8 (const uint8_t* set_1, int n1, const uint8_t* set_2, int n2,
+    int dim, float ratio, float dist, int* m12, int* m21)
+{
+    auto a = widen<unsigned short>(set_1, (std::size_t)n1 * dim);
+    auto b = widen<unsigned short>(set_2, (std::size_t)n2 * dim);
+    sfm::Matching::Result r;
+    sfm::Matching::twoway_match(make_opts(dim, ratio, dist),
+        a.data(), n1, b.data(), n2, &r);
+    copy_out(r.matches_1_2, m12);
+    copy_out(r.matches_2_1, m21);
+}
+
+void
+osfm_ref_twoway_s8 (const int8_t* set_1, int n1, const int8_t* set_2, int n2,
+    int dim, float ratio, float dist, int* m12, int* m21)
+{
+    auto a = widen<short>(set_1, (std::size_t)n1 * dim);
+    auto b = widen<short>(set_2, (std::size_t)n2 * dim);
+    sfm::Matching::Result r;
+    sfm::Matching::twoway_match(make_opts(dim, ratio, dist),
+        a.data(), n1, b.data(), n2, &r);
+    copy_out(r.matches_1_2, m12);
+    copy_out(r.matches_2_1, m21);
+}
+
+void
+osfm_ref_twoway_f32 (const float* set_1, int n1, const float* set_2, int n2,
+    int dim, float ratio, float dist, int* m12, int* m21)
+{
+    auto a = widen<float>(set_1, (std::size_t)n1 * dim);
+    auto b = widen<float>(set_2, (std::size_t)n2 * dim);
+    sfm::Matching::Result r;
+    sfm::Matching::twoway_match(make_opts(dim, ratio, dist),
+        a.data(), n1, b.data(), n2, &r);
+    copy_out(r.matches_1_2, m12);
+    copy_out(r.matches_2_1, m21);
+}
+
+/* ---- filters ------------------------------------------------------ */
+
+void
+osfm_ref_remove_inconsistent (int* m12, int n1, int* m21, int n2)
+{
+    sfm::Matching::Result r;
+    r.matches_1_2.assign(m12, m12 + n1);
+    r.matches_2_1.assign(m21, m21 + n2);
+    sfm::Matching::remove_inconsistent_matches(&r);
+    copy_out(r.matches_1_2, m12);
+    copy_out(r.matches_2_1, m21);
+}
+
+int
+osfm_ref_count_consistent (const int* m12, int n1, const int* m21, int n2)
+{
+    sfm::Matching::Result r;
+    r.matches_1_2.assign(m12, m12 + n1);
+    r.matches_2_1.assign(m21, m21 + n2);
+    return sfm::Matching::count_consistent_matches(r);
+}
+
+void
+osfm_ref_combine_results (
+    const int* sift_1_2, int n1_sift, const int* sift_2_1, int n2_sift,
+    const int* surf_1_2, int n1_surf, const int* surf_2_1, int n2_surf,
+    int* out_1_2, int* out_2_1)
+{
+    sfm::Matching::Result a, b, c;
+    a.matches_1_2.assign(sift_1_2, sift_1_2 + n1_sift);
+    a.matches_2_1.assign(sift_2_1, sift_2_1 + n2_sift);
+    b.matches_1_2.assign(surf_1_2, surf_1_2 + n1_surf);
+    b.matches_2_1.assign(surf_2_1, surf_2_1 + n2_surf);
+    sfm::Matching::combine_results(a, b, &c);
+    copy_out(c.matches_1_2, out_1_2);
+    copy_out(c.matches_2_1, out_2_1);
+}
+
+/* ---- the reference's timed unit: twoway + remove_inconsistent over a
+ *      list of pairs, OpenMP over pairs like bundler_matching.cc:74 ---- */
+
+/* views: `num_views` pointers to n_i x 128 byte descriptors.  pairs: 2*npairs
+ * view ids.  Returns the total number of consistent matches; if counts != NULL
+ * it receives the per-pair consistent-match count. */
+long
+osfm_ref_match_pairs_u8 (const uint8_t* const* views, const int* sizes,
+    int num_views, const int* pairs, int npairs, float ratio, int* counts)
+{
+    std::vector<util::AlignedMemory<unsigned short, 16>> wide(num_views);
+    std::vector<char> used(num_views, 0);
+    for (int p = 0; p < 2 * npairs; ++p)
+        used[pairs[p]] = 1;
+    for (int v = 0; v < num_views; ++v)
+        if (used[v])
+            wide[v] = widen<unsigned short>(views[v], (std::size_t)sizes[v] * 128);
+
+    long total = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+:total)
+    for (int p = 0; p < npairs; ++p)
+    {
+        int const v1 = pairs[2 * p + 0];
+        int const v2 = pairs[2 * p + 1];
+        sfm::Matching::Result r;
+        sfm::Matching::twoway_match(make_opts(128, ratio,
+            std::numeric_limits<float>::max()),
+            wide[v1].data(), sizes[v1], wide[v2].data(), sizes[v2], &r);
+        sfm::Matching::remove_inconsistent_matches(&r);
+        int const c = sfm::Matching::count_consistent_matches(r);
+        if (counts != nullptr)
+            counts[p] = c;
+        total += c;
+    }
+    return total;
+}
+
+/* ---- ExhaustiveMatching (the MatchingBase plugin) ------------------ */
+
+struct osfm_ref_exhaustive
+{
+    sfm::ExhaustiveMatching matcher;
+    sfm::bundler::ViewportList viewports;
+};
+
+osfm_ref_exhaustive*
+osfm_ref_exhaustive_create (int num_views)
+{
+    osfm_ref_exhaustive* h = new osfm_ref_exhaustive();
+    h->viewports.resize(num_views);
+    return h;
+}
+
+/* float descriptors exactly as Sift/Surf produce them (n x 128 / n x 64) */
+void
+osfm_ref_exhaustive_set_view (osfm_ref_exhaustive* h, int view,
+    const float* sift, int n_sift, const float* surf, int n_surf)
+{
+    sfm::FeatureSet& fs = h->viewports[view].features;
+    fs.sift_descriptors.resize(n_sift);
+    for (int i = 0; i < n_sift; ++i)
+    {
+        sfm::Sift::Descriptor& d = fs.sift_descriptors[i];
+        d.x = d.y = d.scale = d.orientation = 0.0f;
+        std::copy(sift + (std::size_t)i * 128, sift + (std::size_t)(i + 1) * 128,
+            d.data.begin());
+    }
+    fs.surf_descriptors.resize(n_surf);
+    for (int i = 0; i < n_surf; ++i)
+    {
+        sfm::Surf::Descriptor& d = fs.surf_descriptors[i];
+        d.x = d.y = d.scale = d.orientation = 0.0f;
+        std::copy(surf + (std::size_t)i * 64, surf + (std::size_t)(i + 1) * 64,
+            d.data.begin());
+    }
+}
+
+void
+osfm_ref_exhaustive_init (osfm_ref_exhaustive* h)
+{
+    h->matcher.init(&h->viewports);
+}
+
+/* Returns sizes through n12/n21; buffers must hold the combined lengths. */
+void
+osfm_ref_exhaustive_pairwise_match (osfm_ref_exhaustive* h, int v1, int v2,
+    int* m12, int* n12, int* m21, int* n21)
+{
+    sfm::Matching::Result r;
+    h->matcher.pairwise_match(v1, v2, &r);
+    *n12 = (int)r.matches_1_2.size();
+    *n21 = (int)r.matches_2_1.size();
+    copy_out(r.matches_1_2, m12);
+    copy_out(r.matches_2_1, m21);
+}
+
+int
+osfm_ref_exhaustive_pairwise_match_lowres (osfm_ref_exhaustive* h,
+    int v1, int v2, int num_features)
+{
+    return h->matcher.pairwise_match_lowres(v1, v2, (std::size_t)num_features);
+}
+
+void
+osfm_ref_exhaustive_destroy (osfm_ref_exhaustive* h)
+{
+    delete h;
+}
+
+/* ---- fixture producer: the reference's own SIFT on a P5 PGM image --- */
+
+/* Runs sfm::Sift with default options on an 8-bit grey image, sorts by scale
+ * descending like FeatureSet::compute_sift (src/mve/sfm/feature_set.cc:58-78)
+ * and writes up to max_desc descriptors (128 floats each).  Returns the count. */
+int
+osfm_ref_sift_gray8 (const uint8_t* pixels, int width, int height,
+    float* out_desc, int max_desc)
+{
+    mve::ByteImage::Ptr img = mve::ByteImage::create(width, height, 1);
+    std::memcpy(img->get_data_pointer(), pixels, (std::size_t)width * height);
+    sfm::Sift::Options opts;
+    sfm::Sift sift(opts);
+    sift.set_image(img);
+    sift.process();
+    sfm::Sift::Descriptors descr = sift.get_descriptors();
+    std::sort(descr.begin(), descr.end(),
+        [] (sfm::Sift::Descriptor const& a, sfm::Sift::Descriptor const& b)
+        { return a.scale > b.scale; });
+    int const n = std::min<int>((int)descr.size(), max_desc);
+    for (int i = 0; i < n; ++i)
+        std::copy(descr[i].data.begin(), descr[i].data.end(),
+            out_desc + (std::size_t)i * 128);
+    return n;
+}
+
+} /* extern "C" */

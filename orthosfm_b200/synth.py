@@ -1,0 +1,117 @@
+"""Deterministic synthetic SIFT-like descriptor sets.
+
+Mirrors what the reference feeds its matcher: unit-norm non-negative 128-d
+vectors, clamped at 0.2 and re-normalised (src/mve/sfm/sift.cc:832-839), then
+quantised like convert_descriptor (src/mve/sfm/exhaustive_matching.cc:18-27):
+``q = floor(255 * clamp(x, 0, 1) + 0.5)`` stored as one byte.
+
+Pure noise produces no consistent matches, so a fraction of every image's
+descriptors is a +-1 LSB perturbed copy of a shared "scene" pool; those are the
+rows that survive the ratio test and the mutual filter.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SIFT_DIM = 128
+SURF_DIM = 64
+
+
+def _normalise_clamp_quantise(x: np.ndarray) -> np.ndarray:
+    x = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    x = np.minimum(x, 0.2)
+    x = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    return np.floor(255.0 * np.clip(x, 0.0, 1.0) + 0.5).astype(np.uint8)
+
+
+def scene_pool(cfg: int, size: int) -> np.ndarray:
+    """Shared pool of quantised scene descriptors for configuration ``cfg``."""
+    rng = np.random.Generator(np.random.MT19937(1000 * cfg + 999))
+    return _normalise_clamp_quantise(np.abs(rng.standard_normal((size, SIFT_DIM), dtype=np.float32)))
+
+
+def sift_view(cfg: int, view: int, n: int, pool: np.ndarray | None = None,
+              planted_fraction: float = 0.25) -> np.ndarray:
+    """``n x 128`` uint8 descriptors of image ``view`` (seed = 1000*cfg + view)."""
+    rng = np.random.Generator(np.random.MT19937(1000 * cfg + view))
+    desc = _normalise_clamp_quantise(np.abs(rng.standard_normal((n, SIFT_DIM), dtype=np.float32)))
+    if pool is not None and planted_fraction > 0 and n > 0:
+        k = min(int(n * planted_fraction), pool.shape[0])
+        rows = rng.permutation(n)[:k]
+        picks = rng.permutation(pool.shape[0])[:k]
+        noise = rng.integers(-1, 2, size=(k, SIFT_DIM), dtype=np.int16)
+        desc[rows] = np.clip(pool[picks].astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    return desc
+
+
+def sift_views(cfg: int, num_views: int, n: int, planted_fraction: float = 0.25,
+               pool_size: int | None = None) -> list[np.ndarray]:
+    pool = scene_pool(cfg, pool_size if pool_size is not None else max(n // 2, 1))
+    return [sift_view(cfg, v, n, pool, planted_fraction) for v in range(num_views)]
+
+
+def surf_view(cfg: int, view: int, n: int, pool: np.ndarray | None = None,
+              planted_fraction: float = 0.25) -> np.ndarray:
+    """``n x 64`` int8 SURF-like descriptors: signed, unit norm scaled to 127
+    (convert_descriptor, exhaustive_matching.cc:30-39)."""
+    rng = np.random.Generator(np.random.MT19937(1000 * cfg + 500 + view))
+    x = rng.standard_normal((n, SURF_DIM), dtype=np.float32)
+    x = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    v = np.clip(x, -1.0, 1.0) * 127.0
+    q = np.where(v > 0, np.floor(v + 0.5), np.ceil(v - 0.5)).astype(np.int8)
+    if pool is not None and planted_fraction > 0 and n > 0:
+        k = min(int(n * planted_fraction), pool.shape[0])
+        rows = rng.permutation(n)[:k]
+        picks = rng.permutation(pool.shape[0])[:k]
+        noise = rng.integers(-1, 2, size=(k, SURF_DIM), dtype=np.int16)
+        q[rows] = np.clip(pool[picks].astype(np.int16) + noise, -127, 127).astype(np.int8)
+    return q
+
+
+def surf_pool(cfg: int, size: int) -> np.ndarray:
+    return surf_view(cfg, 498, size)
+
+
+def all_pairs(num_views: int) -> np.ndarray:
+    """The reference's pair enumeration (src/mve/sfm/bundler_matching.cc:92-93):
+    flat index i -> (view_1, view_2) with view_1 > view_2."""
+    out = np.empty((num_views * (num_views - 1) // 2, 2), dtype=np.int32)
+    k = 0
+    for v1 in range(1, num_views):
+        for v2 in range(v1):
+            out[k] = (v1, v2)
+            k += 1
+    return out
+
+
+def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction: float = 0.25):
+    """Same distribution generated on the device with torch (for the large bench
+    configurations where 4 GB of numpy randoms would dominate start-up).  Returns
+    a ``num_views*n x 128`` uint8 tensor; seeded, but not bit-identical to the
+    numpy generator."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 * cfg + 7)
+
+    def make(rows: int) -> "torch.Tensor":
+        x = torch.randn((rows, SIFT_DIM), generator=g, device=device, dtype=torch.float32).abs_()
+        x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        x = x.clamp_max(0.2)
+        x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        return torch.floor(255.0 * x.clamp(0.0, 1.0) + 0.5).to(torch.uint8)
+
+    pool = make(max(n // 2, 1))
+    k = min(int(n * planted_fraction), pool.shape[0])
+    out = torch.empty((num_views * n, SIFT_DIM), dtype=torch.uint8, device=device)
+    chunk = max(1, (1 << 22) // max(n, 1))
+    for v0 in range(0, num_views, chunk):
+        v1 = min(num_views, v0 + chunk)
+        out[v0 * n:v1 * n] = make((v1 - v0) * n)
+    if k > 0:
+        for v in range(num_views):
+            rows = torch.randperm(n, generator=g, device=device)[:k] + v * n
+            picks = torch.randperm(pool.shape[0], generator=g, device=device)[:k]
+            noise = torch.randint(-1, 2, (k, SIFT_DIM), generator=g, device=device, dtype=torch.int16)
+            out[rows] = (pool[picks].to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+    return out
