@@ -1,0 +1,194 @@
+/*
+ * osfm_match.h -- C ABI of the B200-native exhaustive pairwise feature matcher
+ * for OrthoSfM (libosfm_match.so).
+ *
+ * This is the drop-in boundary for the one hot path this project replaces: the
+ * work done behind sfm::MatchingBase (reference: src/mve/sfm/matching_base.h:22-55)
+ * by sfm::ExhaustiveMatching (src/mve/sfm/exhaustive_matching.{h,cc}).  A C++
+ * subclass of MatchingBase that forwards to these entry points is shipped as
+ * orthosfm_b200/csrc/gpu_exhaustive_matching.h; INTEGRATION.md shows the two-line
+ * change in src/mve/sfm/bundler_matching.cc:31-41 that selects it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only, no C++ or torch types;
+ *   - every function returns 0 on success or a negative osfm_status; it never
+ *     throws and never exits the process (unlike CudaSift's safeCall,
+ *     src/cuda_sift/cudautils.h:15-21).  osfm_match_last_error() gives the text;
+ *   - a handle is internally serialised by a mutex, so the const, re-entrant
+ *     pairwise_match() contract of MatchingBase holds when the reference calls
+ *     it from its OpenMP pair loop (src/mve/sfm/bundler_matching.cc:74);
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x
+ *     osfm_match_create() fails with OSFM_ERR_NO_DEVICE.
+ *
+ * All file:line citations are relative to the reference tree (/root/reference).
+ */
+#ifndef OSFM_MATCH_H
+#define OSFM_MATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSFM_MATCH_ABI_VERSION 1
+
+typedef enum {
+    OSFM_OK = 0,
+    OSFM_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the reference  */
+    OSFM_ERR_NO_DEVICE = -2,        /* no sm_100 device / CUDA unavailable       */
+    OSFM_ERR_CUDA = -3,             /* a CUDA call failed, see last_error        */
+    OSFM_ERR_STATE = -4,            /* call order violated (e.g. match before commit) */
+    OSFM_ERR_OUT_OF_MEMORY = -5,
+    OSFM_ERR_INTERNAL = -6          /* self-check failed inside a kernel          */
+} osfm_status;
+
+/* Descriptor kinds (reference: exhaustive_matching.h:46-48). */
+typedef enum {
+    OSFM_KIND_SIFT_U8 = 0, /* 128 x unsigned byte, Matching::twoway_match<unsigned short> */
+    OSFM_KIND_SURF_S8 = 1  /*  64 x signed byte,   Matching::twoway_match<short>          */
+} osfm_kind;
+
+/* Mirrors MatchingBase::Options (matching_base.h:25-31): per feature type the
+ * Lowe ratio and the distance threshold of Matching::Options (matching.h:29-50).
+ * The descriptor lengths are fixed (128 / 64). */
+typedef struct {
+    int   device;                   /* CUDA device ordinal                      */
+    float sift_lowe_ratio;          /* 0.8f                                     */
+    float sift_distance_threshold;  /* FLT_MAX                                  */
+    float surf_lowe_ratio;          /* 0.7f                                     */
+    float surf_distance_threshold;  /* FLT_MAX                                  */
+    int   reserved[4];              /* must be zero                             */
+} osfm_match_config;
+
+typedef struct osfm_matcher osfm_matcher;
+
+/* Fills cfg with the reference defaults (matching_base.h:27-30), device 0. */
+void osfm_match_default_config(osfm_match_config* cfg);
+
+int osfm_match_abi_version(void);
+
+/* Replaces `new ExhaustiveMatching()` (bundler_matching.cc:34). */
+int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out);
+void osfm_match_destroy(osfm_matcher* m);
+const char* osfm_match_last_error(const osfm_matcher* m);
+
+/* ---- staging: replaces ExhaustiveMatching::init (exhaustive_matching.cc:56-112).
+ * The caller may free its buffers as soon as set_view returns, exactly like
+ * bundler::Matching::init frees the float descriptors right after
+ * matcher->init (bundler_matching.cc:53-55). ------------------------------------ */
+
+/* Declares the number of views (ViewportList::size()).  Resets the handle. */
+int osfm_match_begin(osfm_matcher* m, int num_views);
+
+/* Float descriptors exactly as Sift / Surf produce them; quantised on the device
+ * like convert_descriptor (exhaustive_matching.cc:18-39).  `sift` is
+ * n_sift x 128 floats, row stride sift_stride floats (>= 128; the reference's
+ * Sift::Descriptor is 132 floats, sift.h:137-149, so pass &descr[0].data[0] and
+ * stride 132).  `surf` is n_surf x 64 floats, stride >= 64 (68 for
+ * Surf::Descriptor, surf.h:83-95).  Either may be NULL with n = 0. */
+int osfm_match_set_view_f32(osfm_matcher* m, int view_id,
+    const float* sift, int n_sift, int sift_stride,
+    const float* surf, int n_surf, int surf_stride);
+
+/* Already quantised descriptors: n_sift x 128 unsigned bytes, n_surf x 64
+ * signed bytes, densely packed. */
+int osfm_match_set_view_q8(osfm_matcher* m, int view_id,
+    const uint8_t* sift, int n_sift, const int8_t* surf, int n_surf);
+
+/* Copies all staged views into one HBM-resident pool and builds the TMA
+ * descriptors.  After commit the views are immutable. */
+int osfm_match_commit(osfm_matcher* m);
+
+/* Device-resident variant for the multi-GPU path: adopts a descriptor pool that
+ * already lives in this device's memory (e.g. the target of an NCCL broadcast).
+ * sift_pool is sum(n_sift) x 128 bytes with view v at row sift_row_offset[v];
+ * it must be 128-byte aligned and followed by at least 256 readable rows of
+ * padding.  surf_pool likewise with 64-byte rows (may be NULL).  The memory
+ * stays owned by the caller and must outlive the handle. */
+int osfm_match_commit_device(osfm_matcher* m, int num_views,
+    const void* sift_pool, const int64_t* sift_row_offset, const int32_t* n_sift,
+    int64_t sift_pool_rows,
+    const void* surf_pool, const int64_t* surf_row_offset, const int32_t* n_surf,
+    int64_t surf_pool_rows);
+
+int osfm_match_num_views(const osfm_matcher* m);
+/* Number of SIFT / SURF features of a view; their sum is the length of that
+ * view's side of a Matching::Result. */
+int osfm_match_view_size(const osfm_matcher* m, int view_id, int* n_sift, int* n_surf);
+
+/* ---- matching -------------------------------------------------------------- */
+
+/* Replaces ExhaustiveMatching::pairwise_match (exhaustive_matching.cc:115-144):
+ * SIFT two-way match + remove_inconsistent_matches, the same for SURF, then
+ * combine_results.  matches_1_2 receives *len_1_2 ints (index into view_2's
+ * features or -1), matches_2_1 receives *len_2_1 ints.  The lengths follow the
+ * reference exactly (a feature type contributes only if view_1 has descriptors
+ * of it, exhaustive_matching.cc:123,134); the buffers must hold
+ * n_sift+n_surf ints of the respective view.  n_consistent (may be NULL)
+ * receives Matching::count_consistent_matches (matching.cc:39-47). */
+int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id,
+    int32_t* matches_1_2, int* len_1_2, int32_t* matches_2_1, int* len_2_1,
+    int* n_consistent);
+
+/* Replaces Matching::twoway_match<T> (matching.h:148-159) for one feature kind:
+ * both one-way results WITHOUT the mutual filter.  matches_1_2 has n1 entries
+ * of that kind, matches_2_1 n2. */
+int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_id,
+    int32_t* matches_1_2, int32_t* matches_2_1);
+
+/* Replaces ExhaustiveMatching::pairwise_match_lowres (exhaustive_matching.cc:147-180). */
+int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id,
+    size_t num_features, int* n_consistent);
+
+/* Batched form of osfm_match_pair for SIFT-only or SIFT+SURF views: all pairs in
+ * one pass of the persistent kernel.  pairs = 2*npairs view ids (view_1, view_2).
+ * Results are written densely: pair p's matches_1_2 starts at
+ * matches[offsets[2p]] and its matches_2_1 at matches[offsets[2p+1]];
+ * offsets has 2*npairs+1 entries (the last one is the total length) and is
+ * filled by the call.  `matches` (host) must hold osfm_match_pairs_result_size()
+ * ints.  n_consistent (may be NULL) gets npairs counts. */
+int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int npairs);
+int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs,
+    int32_t* matches, int64_t* offsets, int32_t* n_consistent);
+
+/* Device-resident batched form (no host<->device copies of descriptors or dense
+ * results): the filtered matches of every pair are compacted, ordered by the
+ * view_1 feature index, into (i, j) int32 pairs.  d_match_ij (device) holds
+ * capacity_ij pairs; pair p's list starts at list_offset[p] (host, npairs+1
+ * entries, filled by the call; list_offset[npairs] = total).  Returns
+ * OSFM_ERR_OUT_OF_MEMORY if capacity_ij is too small (list_offset[npairs] then
+ * holds the required capacity).  SIFT only. */
+int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs,
+    int32_t* d_match_ij, int64_t capacity_ij, int64_t* list_offset);
+
+/* ---- introspection --------------------------------------------------------- */
+
+typedef struct {
+    int64_t kernel_launches;     /* launches of this library's kernels so far      */
+    int64_t scan_items;          /* (job, 128-row block) work items processed       */
+    int64_t candidate_rows;      /* rows that needed the exact second-best refine   */
+    int64_t slow_rows;           /* rows re-evaluated with the 16-bit wrap emulation */
+    int64_t self_check_failures; /* must stay 0                                      */
+    double  last_scan_ms;        /* CUDA-event time of the last scan kernel launch(es) */
+    double  last_total_ms;       /* CUDA-event time of the last batched call, device part */
+    int64_t last_comparisons;    /* sum n1*n2 of the last batched call (unique)      */
+} osfm_match_stats;
+
+int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
+
+/* Test / profiling hooks (not part of the reference surface). */
+/* mode 0 = normal; 1 = scan kernel skips the epilogue reduction (MMA+TMA only);
+ * 2 = epilogue reads TMEM but does not reduce.  Results are invalid for != 0. */
+int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
+/* Writes the raw int32 similarity matrix of one (query view, candidate view)
+ * SIFT job as computed by the tensor-core kernel: out is n_q x ld ints,
+ * ld = 256 * ceil(n_c / 256). */
+int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int view_c,
+    int32_t* out, int64_t out_ints);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSFM_MATCH_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of libosfm_match.so (include/osfm_match.h).  Fails loudly when the
+CUDA library is missing or no B200 is present -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libosfm_match.so")
+
+OSFM_OK = 0
+ERR_NAMES = {
+    -1: "OSFM_ERR_INVALID_ARGUMENT", -2: "OSFM_ERR_NO_DEVICE", -3: "OSFM_ERR_CUDA",
+    -4: "OSFM_ERR_STATE", -5: "OSFM_ERR_OUT_OF_MEMORY", -6: "OSFM_ERR_INTERNAL",
+}
+KIND_SIFT_U8 = 0
+KIND_SURF_S8 = 1
+
+# every symbol include/osfm_match.h declares
+EXPORTS = [
+    "osfm_match_default_config", "osfm_match_abi_version", "osfm_match_create",
+    "osfm_match_destroy", "osfm_match_last_error", "osfm_match_begin",
+    "osfm_match_set_view_f32", "osfm_match_set_view_q8", "osfm_match_commit",
+    "osfm_match_commit_device", "osfm_match_num_views", "osfm_match_view_size",
+    "osfm_match_pair", "osfm_match_pair_twoway", "osfm_match_pair_lowres",
+    "osfm_match_pairs_result_size", "osfm_match_pairs", "osfm_match_pairs_compact_device",
+    "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("sift_lowe_ratio", C.c_float),
+                ("sift_distance_threshold", C.c_float), ("surf_lowe_ratio", C.c_float),
+                ("surf_distance_threshold", C.c_float), ("reserved", C.c_int * 4)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("scan_items", C.c_int64),
+                ("candidate_rows", C.c_int64), ("slow_rows", C.c_int64),
+                ("self_check_failures", C.c_int64), ("last_scan_ms", C.c_double),
+                ("last_total_ms", C.c_double), ("last_comparisons", C.c_int64)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class MatcherError(RuntimeError):
+    """Mirrors the std::runtime_error / std::invalid_argument the MVE code throws
+    (src/mve/sfm/bundler_matching.cc:40,48,62)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m orthosfm_b200.csrc.build` "
+            f"(or __graft_entry__.build()).  orthosfm_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, i32p, i64p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.osfm_match_default_config.argtypes = [C.POINTER(Config)]
+    L.osfm_match_default_config.restype = None
+    L.osfm_match_abi_version.restype = C.c_int
+    L.osfm_match_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.osfm_match_destroy.argtypes = [vp]
+    L.osfm_match_destroy.restype = None
+    L.osfm_match_last_error.argtypes = [vp]
+    L.osfm_match_last_error.restype = C.c_char_p
+    L.osfm_match_begin.argtypes = [vp, C.c_int]
+    L.osfm_match_set_view_f32.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+    L.osfm_match_set_view_q8.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int]
+    L.osfm_match_commit.argtypes = [vp]
+    L.osfm_match_commit_device.argtypes = [vp, C.c_int, vp, i64p, i32p, C.c_int64, vp, i64p, i32p, C.c_int64]
+    L.osfm_match_num_views.argtypes = [vp]
+    L.osfm_match_view_size.argtypes = [vp, C.c_int, ip, ip]
+    L.osfm_match_pair.argtypes = [vp, C.c_int, C.c_int, i32p, ip, i32p, ip, ip]
+    L.osfm_match_pair_twoway.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, i32p]
+    L.osfm_match_pair_lowres.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, ip]
+    L.osfm_match_pairs_result_size.argtypes = [vp, i32p, C.c_int]
+    L.osfm_match_pairs_result_size.restype = C.c_int64
+    L.osfm_match_pairs.argtypes = [vp, i32p, C.c_int, i32p, i64p, i32p]
+    L.osfm_match_pairs_compact_device.argtypes = [vp, i32p, C.c_int, vp, C.c_int64, i64p]
+    L.osfm_match_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
+    L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
+    _lib = L
+    return L

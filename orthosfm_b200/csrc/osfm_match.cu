@@ -1,0 +1,947 @@
+// osfm_match.cu -- host side of libosfm_match.so: the C ABI declared in
+// include/osfm_match.h over the sm_100a kernels in scan_kernel.cuh / post_kernels.cuh.
+//
+// Host-side mirror of the reference (paths relative to /root/reference):
+//   ExhaustiveMatching::init                  src/mve/sfm/exhaustive_matching.cc:56-112
+//   ExhaustiveMatching::pairwise_match        src/mve/sfm/exhaustive_matching.cc:115-144
+//   ExhaustiveMatching::pairwise_match_lowres src/mve/sfm/exhaustive_matching.cc:147-180
+//   Matching::twoway_match                    src/mve/sfm/matching.h:148-159
+//   Matching::combine_results                 src/mve/sfm/matching.cc:50-89
+//
+// There is no CPU path in this file: every result comes from the kernels.
+#include <algorithm>
+#include <cfloat>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/osfm_match.h"
+#include "post_kernels.cuh"
+#include "scan_kernel.cuh"
+
+using namespace osfm;
+
+namespace {
+
+constexpr int kPadRows = 256;                  // readable zero rows after the last view
+constexpr int64_t kMaxBatchRows = 48ll << 20;  // job rows per batch (bounds scratch memory)
+constexpr int64_t kMaxBatchDense = 1ll << 30;  // dense result ints per batch (4 GiB)
+
+struct KindPool {
+    bool is_signed = false;
+    int dim = 128;
+    uint8_t* pool = nullptr;        // rows of kRowBytes bytes
+    bool owned = false;
+    int64_t rows = 0;               // rows that belong to views
+    std::vector<int64_t> off;       // first row of each view
+    std::vector<int32_t> n;         // descriptors per view
+    std::vector<int32_t> maxnorm2;  // signed kind only
+    int32_t* d_norm2 = nullptr;     // signed kind only
+    CUtensorMap tmap;
+    std::vector<uint8_t*> staged;   // per-view device buffers before commit
+    float lowe = 0.8f, dist = FLT_MAX;
+};
+
+struct JobSpec { int q_view, q_n, c_view, c_n; };
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t const want = std::max<size_t>(count + count / 8, 1024);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// One image pair as the batched entry points see it.
+struct PairPlan {
+    int v1, v2;
+    int n1[2], n2[2];        // effective sizes per kind (0 if the kind does not contribute)
+    int64_t out12, out21;    // offsets of the combined vectors in the dense result
+    int len12, len21;
+};
+
+}  // namespace
+
+struct osfm_matcher {
+    std::mutex mu;
+    std::string err;
+    osfm_match_config cfg;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    EncodeTiledFn encode = nullptr;
+    HangReport* hang_host = nullptr;
+
+    int num_views = 0;
+    bool began = false, committed = false;
+    KindPool kind[2];
+
+    DevBuf<ScanJob> d_jobs;
+    DevBuf<int4> d_rowres;
+    DevBuf<int32_t> d_oneway;
+    DevBuf<int64_t> d_slow;
+    DevBuf<PairPart> d_parts;
+    DevBuf<int32_t> d_dense;
+    DevBuf<int32_t> d_counts;
+    DevBuf<int64_t> d_listoff;
+    DevBuf<float> d_ftmp;
+    unsigned long long* d_counters = nullptr;  // see PostParams::counters
+
+    int scan_mode = 0;
+    double scan_ms_acc = 0.0;
+    osfm_match_stats stats;
+};
+
+namespace {
+
+int fail(osfm_matcher* m, int code, const char* fmt, ...) {
+    char buf[768];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (m) m->err = buf;
+    return code;
+}
+
+int cuda_fail(osfm_matcher* m, cudaError_t e, const char* what) {
+    char extra[200] = "";
+    if (m && m->hang_host && m->hang_host->flag)
+        snprintf(extra, sizeof extra,
+                 " [kernel watchdog: wait code %u block %u thread %u parity %u aux %u]",
+                 m->hang_host->code, m->hang_host->block, m->hang_host->thread,
+                 m->hang_host->parity, m->hang_host->aux);
+    return fail(m, OSFM_ERR_CUDA, "%s: %s%s", what, cudaGetErrorString(e), extra);
+}
+
+#define CU_TRY(m, call)                                             \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail((m), e__, #call);  \
+    } while (0)
+
+#define OS_TRY(call)                  \
+    do {                              \
+        int r__ = (call);             \
+        if (r__ != OSFM_OK) return r__; \
+    } while (0)
+
+void free_kind(KindPool& k) {
+    for (uint8_t* p : k.staged) if (p) cudaFree(p);
+    k.staged.clear();
+    if (k.owned && k.pool) cudaFree(k.pool);
+    if (k.d_norm2) cudaFree(k.d_norm2);
+    k.pool = nullptr; k.owned = false; k.d_norm2 = nullptr;
+    k.rows = 0; k.off.clear(); k.n.clear(); k.maxnorm2.clear();
+}
+
+int make_tmap(osfm_matcher* m, KindPool& k) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(k.rows + kPadRows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(kRowBytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kRowBytes), static_cast<cuuint32_t>(kBlockM)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = m->encode(&k.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, k.pool, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(m, OSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return OSFM_OK;
+}
+
+// Per-row squared norms + per-view maxima for the signed kind (wrap certificate).
+int compute_norms(osfm_matcher* m, KindPool& k) {
+    k.maxnorm2.assign(k.n.size(), 0);
+    if (!k.is_signed || k.rows == 0) return OSFM_OK;
+    std::vector<int32_t> row_view(k.rows);
+    for (size_t v = 0; v < k.n.size(); ++v)
+        for (int i = 0; i < k.n[v]; ++i) row_view[k.off[v] + i] = static_cast<int32_t>(v);
+    int32_t *d_view = nullptr, *d_max = nullptr;
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_view), sizeof(int32_t) * k.rows));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_max), sizeof(int32_t) * k.n.size()));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.d_norm2), sizeof(int32_t) * (k.rows + kPadRows)));
+    CU_TRY(m, cudaMemcpyAsync(d_view, row_view.data(), sizeof(int32_t) * k.rows, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemsetAsync(d_max, 0, sizeof(int32_t) * k.n.size(), m->stream));
+    CU_TRY(m, cudaMemsetAsync(k.d_norm2, 0, sizeof(int32_t) * (k.rows + kPadRows), m->stream));
+    int const grid = static_cast<int>((k.rows + 255) / 256);
+    rownorm_kernel<<<grid, 256, 0, m->stream>>>(k.pool, k.rows, d_view, k.d_norm2, d_max);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches++;
+    CU_TRY(m, cudaMemcpyAsync(k.maxnorm2.data(), d_max, sizeof(int32_t) * k.n.size(), cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    cudaFree(d_view);
+    cudaFree(d_max);
+    return OSFM_OK;
+}
+
+template <int MODE>
+cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kScanSmemBytes);
+    if (e != cudaSuccess) return e;
+    int const grid = std::min(m->num_sms, total_items);
+    uint32_t const idesc = make_idesc_i8(kBlockM, kBlockN, k.is_signed ? 1 : 0, k.is_signed ? 1 : 0);
+    scan_kernel<MODE><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
+        k.tmap, m->d_jobs.p, total_items, m->d_rowres.p, idesc, dump, dump_ld);
+    return cudaGetLastError();
+}
+
+// Runs scan + finalize + wrap emulation for a list of jobs of one kind.  On return (in
+// stream order) m->d_oneway holds, for job i, q_n one-way results starting at out_row[i]
+// (out_row[i] = -1 if the job was not run because one side is empty).
+int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
+             std::vector<int64_t>& out_row, int32_t* dump = nullptr, int64_t dump_ld = 0) {
+    KindPool& k = m->kind[kind_id];
+    out_row.assign(specs.size(), -1);
+    std::vector<ScanJob> jobs;
+    jobs.reserve(specs.size() + 1);
+    int64_t rows = 0, items = 0;
+    for (size_t i = 0; i < specs.size(); ++i) {
+        JobSpec const& s = specs[i];
+        if (s.q_n <= 0 || s.c_n <= 0) continue;
+        ScanJob j;
+        j.q_row = static_cast<int32_t>(k.off[s.q_view]);
+        j.q_n = s.q_n;
+        j.c_row = static_cast<int32_t>(k.off[s.c_view]);
+        j.c_n = s.c_n;
+        j.out_row = rows;
+        j.item_start = static_cast<int32_t>(items);
+        j.c_maxnorm2 = k.is_signed ? k.maxnorm2[s.c_view] : 0;
+        out_row[i] = rows;
+        rows += s.q_n;
+        items += (s.q_n + kBlockM - 1) / kBlockM;
+        jobs.push_back(j);
+    }
+    if (jobs.empty()) return OSFM_OK;
+    if (items > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many work items in one batch");
+    int const njobs = static_cast<int>(jobs.size());
+    ScanJob sentinel;
+    memset(&sentinel, 0, sizeof sentinel);
+    sentinel.out_row = rows;
+    sentinel.item_start = static_cast<int32_t>(items);
+    jobs.push_back(sentinel);
+
+    CU_TRY(m, m->d_jobs.reserve(jobs.size()));
+    CU_TRY(m, m->d_rowres.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, m->d_slow.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, cudaMemcpyAsync(m->d_jobs.p, jobs.data(), sizeof(ScanJob) * jobs.size(),
+                              cudaMemcpyHostToDevice, m->stream));
+    // pageable source: the copy is staged before the call returns, `jobs` may die.
+    CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));
+
+    CU_TRY(m, cudaEventRecord(m->ev[0], m->stream));
+    cudaError_t e;
+    switch (dump ? 3 : m->scan_mode) {
+        case 1: e = launch_scan<1>(m, k, static_cast<int>(items), nullptr, 0); break;
+        case 2: e = launch_scan<2>(m, k, static_cast<int>(items), nullptr, 0); break;
+        case 3: e = launch_scan<3>(m, k, static_cast<int>(items), dump, dump_ld); break;
+        default: e = launch_scan<0>(m, k, static_cast<int>(items), nullptr, 0); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
+    CU_TRY(m, cudaEventRecord(m->ev[1], m->stream));
+    m->stats.kernel_launches++;
+    m->stats.scan_items += items;
+
+    PostParams pp;
+    pp.pool = k.pool;
+    pp.jobs = m->d_jobs.p;
+    pp.njobs = njobs;
+    pp.total_rows = rows;
+    pp.rowres = m->d_rowres.p;
+    pp.oneway = m->d_oneway.p;
+    pp.sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
+    pp.sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
+    pp.slow_list = m->d_slow.p;
+    pp.counters = m->d_counters;
+    pp.norm2 = k.d_norm2;
+    int const grid = static_cast<int>((rows + 255) / 256);
+    if (k.is_signed) finalize_kernel<true><<<grid, 256, 0, m->stream>>>(pp);
+    else             finalize_kernel<false><<<grid, 256, 0, m->stream>>>(pp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(m, e, "finalize_kernel launch");
+    int const sgrid = m->num_sms * 2;
+    if (k.is_signed) slow_rows_kernel<true><<<sgrid, 256, 0, m->stream>>>(pp);
+    else             slow_rows_kernel<false><<<sgrid, 256, 0, m->stream>>>(pp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
+    m->stats.kernel_launches += 2;
+
+    // Scan time of this launch; read after the caller's next synchronisation.
+    // (cudaEventElapsedTime needs completed events, so we synchronise on ev[1] lazily in
+    // collect_scan_time().)
+    return OSFM_OK;
+}
+
+int collect_scan_time(osfm_matcher* m) {
+    if (cudaEventQuery(m->ev[1]) == cudaErrorNotReady) CU_TRY(m, cudaEventSynchronize(m->ev[1]));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->scan_ms_acc += ms;
+    return OSFM_OK;
+}
+
+int check_view(osfm_matcher* m, int v) {
+    if (v < 0 || v >= m->num_views) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "view id %d out of range [0,%d)", v, m->num_views);
+    return OSFM_OK;
+}
+
+// Effective sizes of one pair, following exhaustive_matching.cc:123,134: a feature type
+// takes part only if view_1 has descriptors of it.
+PairPlan plan_pair(osfm_matcher* m, int v1, int v2, int limit /* <=0: none */, bool sift_only_lowres) {
+    PairPlan p;
+    p.v1 = v1; p.v2 = v2;
+    for (int kd = 0; kd < 2; ++kd) {
+        int a = m->kind[kd].n.empty() ? 0 : m->kind[kd].n[v1];
+        int b = m->kind[kd].n.empty() ? 0 : m->kind[kd].n[v2];
+        if (a <= 0) { a = 0; b = 0; }
+        if (limit > 0) { a = std::min(a, limit); b = std::min(b, limit); }
+        p.n1[kd] = a; p.n2[kd] = b;
+    }
+    if (sift_only_lowres) {
+        // pairwise_match_lowres: SIFT if view_1 has SIFT, else SURF (exhaustive_matching.cc:153-177)
+        if (p.n1[0] > 0) { p.n1[1] = 0; p.n2[1] = 0; }
+    }
+    p.len12 = p.n1[0] + p.n1[1];
+    p.len21 = p.n2[0] + p.n2[1];
+    p.out12 = p.out21 = 0;
+    return p;
+}
+
+enum OutputMode { kFiltered = 0, kTwoway = 1 };
+
+// Device part of a batch: fills m->d_dense (layout given by plans[].out12/out21, relative
+// to the batch) and m->d_counts (one per plan; only in kFiltered mode).
+int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense_ints, OutputMode mode,
+              int only_kind /* -1: both */) {
+    int const np = static_cast<int>(plans.size());
+    CU_TRY(m, m->d_dense.reserve(static_cast<size_t>(std::max<int64_t>(dense_ints, 1))));
+    CU_TRY(m, m->d_counts.reserve(static_cast<size_t>(np)));
+    CU_TRY(m, cudaMemsetAsync(m->d_counts.p, 0, sizeof(int32_t) * np, m->stream));
+
+    std::vector<JobSpec> specs;
+    std::vector<int64_t> out_row;
+    std::vector<PairPart> parts;
+    for (int kd = 0; kd < 2; ++kd) {
+        if (only_kind >= 0 && kd != only_kind) continue;
+        specs.clear();
+        bool any = false;
+        for (PairPlan const& p : plans) {
+            specs.push_back({p.v1, p.n1[kd], p.v2, p.n2[kd]});
+            specs.push_back({p.v2, p.n2[kd], p.v1, p.n1[kd]});
+            any = any || p.n1[kd] > 0 || p.n2[kd] > 0;
+        }
+        if (!any) continue;
+        OS_TRY(run_jobs(m, kd, specs, out_row));
+        parts.clear();
+        int max_n = 0;
+        for (int i = 0; i < np; ++i) {
+            PairPlan const& p = plans[i];
+            if (p.n1[kd] == 0 && p.n2[kd] == 0) continue;
+            PairPart pt;
+            pt.in12 = out_row[2 * i];
+            pt.in21 = out_row[2 * i + 1];
+            // combine_results: SURF block follows the SIFT block; indices into the other
+            // view's combined vector are shifted by that view's SIFT count (matching.cc:74-88).
+            pt.out12 = p.out12 + (kd == 1 ? p.n1[0] : 0);
+            pt.out21 = p.out21 + (kd == 1 ? p.n2[0] : 0);
+            pt.n1 = p.n1[kd];
+            pt.n2 = p.n2[kd];
+            pt.add12 = (kd == 1 && mode == kFiltered) ? p.n2[0] : 0;
+            pt.add21 = (kd == 1 && mode == kFiltered) ? p.n1[0] : 0;
+            pt.pair = i;
+            pt.pad = 0;
+            parts.push_back(pt);
+            max_n = std::max(max_n, std::max(pt.n1, pt.n2));
+        }
+        if (parts.empty()) continue;
+        CU_TRY(m, m->d_parts.reserve(parts.size()));
+        CU_TRY(m, cudaMemcpyAsync(m->d_parts.p, parts.data(), sizeof(PairPart) * parts.size(),
+                                  cudaMemcpyHostToDevice, m->stream));
+        dim3 const grid(static_cast<unsigned>(parts.size()),
+                        static_cast<unsigned>((max_n + kMutualChunk - 1) / kMutualChunk));
+        if (mode == kFiltered)
+            mutual_kernel<<<grid, 256, 0, m->stream>>>(m->d_parts.p, m->d_oneway.p, m->d_dense.p, m->d_counts.p);
+        else
+            copy_twoway_kernel<<<grid, 256, 0, m->stream>>>(m->d_parts.p, m->d_oneway.p, m->d_dense.p);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches++;
+        OS_TRY(collect_scan_time(m));  // also orders the reuse of `parts` / scratch across kinds
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    }
+    return OSFM_OK;
+}
+
+int read_counters(osfm_matcher* m) {
+    unsigned long long c[4];
+    CU_TRY(m, cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    m->stats.candidate_rows = static_cast<int64_t>(c[1]);
+    m->stats.self_check_failures = static_cast<int64_t>(c[2]);
+    m->stats.slow_rows = static_cast<int64_t>(c[3]);
+    if (c[2] != 0) return fail(m, OSFM_ERR_INTERNAL, "kernel self-check failed %llu times (scan/refine mismatch)", c[2]);
+    return OSFM_OK;
+}
+
+// Splits `plans` into batches bounded by scratch memory; calls fn(first, last, dense_ints).
+template <typename Fn>
+int for_each_batch(std::vector<PairPlan>& plans, Fn fn) {
+    size_t first = 0;
+    while (first < plans.size()) {
+        int64_t rows = 0, dense = 0;
+        size_t last = first;
+        while (last < plans.size()) {
+            PairPlan& p = plans[last];
+            int64_t const r = std::max<int64_t>(p.n1[0] + p.n2[0], p.n1[1] + p.n2[1]);
+            int64_t const d = static_cast<int64_t>(p.len12) + p.len21;
+            if (last > first && (rows + r > kMaxBatchRows || dense + d > kMaxBatchDense)) break;
+            p.out12 = dense;
+            p.out21 = dense + p.len12;
+            rows += r; dense += d;
+            ++last;
+        }
+        int r = fn(first, last, dense);
+        if (r != OSFM_OK) return r;
+        first = last;
+    }
+    return OSFM_OK;
+}
+
+int require_committed(osfm_matcher* m) {
+    if (!m->committed) return fail(m, OSFM_ERR_STATE, "matcher not committed (call osfm_match_commit first)");
+    return OSFM_OK;
+}
+
+int64_t comparisons_of(const std::vector<PairPlan>& plans) {
+    int64_t c = 0;
+    for (PairPlan const& p : plans)
+        for (int kd = 0; kd < 2; ++kd) c += static_cast<int64_t>(p.n1[kd]) * p.n2[kd];
+    return c;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+
+extern "C" {
+
+void osfm_match_default_config(osfm_match_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->sift_lowe_ratio = 0.8f;            // matching_base.h:27
+    cfg->sift_distance_threshold = FLT_MAX;
+    cfg->surf_lowe_ratio = 0.7f;            // matching_base.h:29
+    cfg->surf_distance_threshold = FLT_MAX;
+}
+
+int osfm_match_abi_version(void) { return OSFM_MATCH_ABI_VERSION; }
+
+const char* osfm_match_last_error(const osfm_matcher* m) {
+    return m ? m->err.c_str() : "null handle";
+}
+
+int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
+    if (!out) return OSFM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    osfm_matcher* m = new (std::nothrow) osfm_matcher();
+    if (!m) return OSFM_ERR_OUT_OF_MEMORY;
+    *out = m;  // returned even on failure so that last_error() is readable
+    memset(&m->stats, 0, sizeof m->stats);
+    if (cfg) m->cfg = *cfg; else osfm_match_default_config(&m->cfg);
+    m->device = m->cfg.device;
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(m, OSFM_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (m->device < 0 || m->device >= count)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", m->device, count);
+    cudaDeviceProp prop;
+    CU_TRY(m, cudaGetDeviceProperties(&prop, m->device));
+    if (prop.major != 10)
+        return fail(m, OSFM_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only",
+                    m->device, prop.major, prop.minor);
+    CU_TRY(m, cudaSetDevice(m->device));
+    m->num_sms = prop.multiProcessorCount;
+    CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 4 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMemset(m->d_counters, 0, 4 * sizeof(unsigned long long)));
+
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(m, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(m, OSFM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    m->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+    // watchdog report buffer in mapped pinned memory
+    CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&m->hang_host), sizeof(HangReport), cudaHostAllocMapped));
+    memset(m->hang_host, 0, sizeof(HangReport));
+    HangReport* dptr = nullptr;
+    CU_TRY(m, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->hang_host, 0));
+    CU_TRY(m, cudaMemcpyToSymbol(g_hang_report, &dptr, sizeof dptr));
+
+    m->kind[0].is_signed = false; m->kind[0].dim = 128;
+    m->kind[0].lowe = m->cfg.sift_lowe_ratio; m->kind[0].dist = m->cfg.sift_distance_threshold;
+    m->kind[1].is_signed = true;  m->kind[1].dim = 64;
+    m->kind[1].lowe = m->cfg.surf_lowe_ratio; m->kind[1].dist = m->cfg.surf_distance_threshold;
+    return OSFM_OK;
+}
+
+void osfm_match_destroy(osfm_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    free_kind(m->kind[0]);
+    free_kind(m->kind[1]);
+    m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release(); m->d_slow.release();
+    m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
+    m->d_ftmp.release();
+    if (m->d_counters) cudaFree(m->d_counters);
+    if (m->hang_host) {
+        HangReport* null_ptr = nullptr;
+        cudaMemcpyToSymbol(g_hang_report, &null_ptr, sizeof null_ptr);
+        cudaFreeHost(m->hang_host);
+    }
+    for (auto& ev : m->ev) if (ev) cudaEventDestroy(ev);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int osfm_match_begin(osfm_matcher* m, int num_views) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    for (int kd = 0; kd < 2; ++kd) {
+        free_kind(m->kind[kd]);
+        m->kind[kd].n.assign(num_views, 0);
+        m->kind[kd].off.assign(num_views, 0);
+        m->kind[kd].staged.assign(num_views, nullptr);
+    }
+    m->num_views = num_views;
+    m->began = true;
+    m->committed = false;
+    return OSFM_OK;
+}
+
+static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n, int stride, bool is_float) {
+    KindPool& k = m->kind[kd];
+    if (k.staged[view]) { cudaFree(k.staged[view]); k.staged[view] = nullptr; }
+    k.n[view] = 0;
+    if (n <= 0) return OSFM_OK;
+    if (!src) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null descriptor pointer with n = %d", n);
+    uint8_t* d = nullptr;
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), static_cast<size_t>(n) * kRowBytes));
+    k.staged[view] = d;
+    if (is_float) {
+        if (stride < k.dim) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "stride %d < descriptor length %d", stride, k.dim);
+        size_t const count = static_cast<size_t>(n - 1) * stride + k.dim;
+        CU_TRY(m, m->d_ftmp.reserve(count));
+        CU_TRY(m, cudaMemcpyAsync(m->d_ftmp.p, src, count * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        int64_t const total = static_cast<int64_t>(n) * kRowBytes;
+        int const grid = static_cast<int>((total + 255) / 256);
+        if (k.is_signed) quantize_kernel<true><<<grid, 256, 0, m->stream>>>(m->d_ftmp.p, n, k.dim, stride, d);
+        else             quantize_kernel<false><<<grid, 256, 0, m->stream>>>(m->d_ftmp.p, n, k.dim, stride, d);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches++;
+        CU_TRY(m, cudaStreamSynchronize(m->stream));  // caller may free src; d_ftmp is reused
+    } else if (k.dim == kRowBytes) {
+        CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    } else {
+        // 64-byte rows are zero-padded to the 128-byte pool pitch
+        CU_TRY(m, cudaMemsetAsync(d, 0, static_cast<size_t>(n) * kRowBytes, m->stream));
+        CU_TRY(m, cudaMemcpy2DAsync(d, kRowBytes, src, k.dim, k.dim, n, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    }
+    k.n[view] = n;
+    return OSFM_OK;
+}
+
+int osfm_match_set_view_f32(osfm_matcher* m, int view_id, const float* sift, int n_sift, int sift_stride,
+                            const float* surf, int n_surf, int surf_stride) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
+    OS_TRY(check_view(m, view_id));
+    CU_TRY(m, cudaSetDevice(m->device));
+    OS_TRY(stage_view(m, 0, view_id, sift, n_sift, sift_stride, true));
+    OS_TRY(stage_view(m, 1, view_id, surf, n_surf, surf_stride, true));
+    return OSFM_OK;
+}
+
+int osfm_match_set_view_q8(osfm_matcher* m, int view_id, const uint8_t* sift, int n_sift,
+                           const int8_t* surf, int n_surf) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
+    OS_TRY(check_view(m, view_id));
+    CU_TRY(m, cudaSetDevice(m->device));
+    OS_TRY(stage_view(m, 0, view_id, sift, n_sift, 128, false));
+    OS_TRY(stage_view(m, 1, view_id, surf, n_surf, 64, false));
+    return OSFM_OK;
+}
+
+int osfm_match_commit(osfm_matcher* m) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "commit outside begin/commit");
+    CU_TRY(m, cudaSetDevice(m->device));
+    for (int kd = 0; kd < 2; ++kd) {
+        KindPool& k = m->kind[kd];
+        int64_t rows = 0;
+        for (int v = 0; v < m->num_views; ++v) { k.off[v] = rows; rows += k.n[v]; }
+        if (rows + kPadRows > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "descriptor pool exceeds 2^31 rows");
+        k.rows = rows;
+        size_t const bytes = static_cast<size_t>(rows + kPadRows) * kRowBytes;
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.pool), bytes));
+        k.owned = true;
+        CU_TRY(m, cudaMemsetAsync(k.pool + static_cast<size_t>(rows) * kRowBytes, 0,
+                                  static_cast<size_t>(kPadRows) * kRowBytes, m->stream));
+        for (int v = 0; v < m->num_views; ++v)
+            if (k.n[v] > 0)
+                CU_TRY(m, cudaMemcpyAsync(k.pool + static_cast<size_t>(k.off[v]) * kRowBytes, k.staged[v],
+                                          static_cast<size_t>(k.n[v]) * kRowBytes, cudaMemcpyDeviceToDevice, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        for (uint8_t*& p : k.staged) { if (p) cudaFree(p); p = nullptr; }
+        OS_TRY(make_tmap(m, k));
+        OS_TRY(compute_norms(m, k));
+    }
+    m->committed = true;
+    return OSFM_OK;
+}
+
+int osfm_match_commit_device(osfm_matcher* m, int num_views,
+                             const void* sift_pool, const int64_t* sift_row_offset, const int32_t* n_sift,
+                             int64_t sift_pool_rows,
+                             const void* surf_pool, const int64_t* surf_row_offset, const int32_t* n_surf,
+                             int64_t surf_pool_rows) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    const void* pools[2] = {sift_pool, surf_pool};
+    const int64_t* offs[2] = {sift_row_offset, surf_row_offset};
+    const int32_t* ns[2] = {n_sift, n_surf};
+    int64_t prow[2] = {sift_pool_rows, surf_pool_rows};
+    for (int kd = 0; kd < 2; ++kd) {
+        KindPool& k = m->kind[kd];
+        free_kind(k);
+        k.n.assign(num_views, 0);
+        k.off.assign(num_views, 0);
+        k.staged.assign(num_views, nullptr);
+        if (!pools[kd]) {
+            // empty pool: still needs a valid (tiny) allocation for the tensor map
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.pool), static_cast<size_t>(kPadRows) * kRowBytes));
+            CU_TRY(m, cudaMemset(k.pool, 0, static_cast<size_t>(kPadRows) * kRowBytes));
+            k.owned = true;
+            k.rows = 0;
+        } else {
+            if ((reinterpret_cast<uintptr_t>(pools[kd]) & 127u) != 0)
+                return fail(m, OSFM_ERR_INVALID_ARGUMENT, "device pool must be 128-byte aligned");
+            if (!offs[kd] || !ns[kd]) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null offset / size array");
+            if (prow[kd] + kPadRows > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "descriptor pool exceeds 2^31 rows");
+            for (int v = 0; v < num_views; ++v) {
+                if (ns[kd][v] < 0 || offs[kd][v] < 0 || offs[kd][v] + ns[kd][v] > prow[kd])
+                    return fail(m, OSFM_ERR_INVALID_ARGUMENT, "view %d lies outside the pool", v);
+                k.n[v] = ns[kd][v];
+                k.off[v] = offs[kd][v];
+            }
+            k.pool = const_cast<uint8_t*>(static_cast<const uint8_t*>(pools[kd]));
+            k.owned = false;
+            k.rows = prow[kd];
+        }
+        OS_TRY(make_tmap(m, k));
+        OS_TRY(compute_norms(m, k));
+    }
+    m->num_views = num_views;
+    m->began = true;
+    m->committed = true;
+    return OSFM_OK;
+}
+
+int osfm_match_num_views(const osfm_matcher* m) { return m ? m->num_views : OSFM_ERR_INVALID_ARGUMENT; }
+
+int osfm_match_view_size(const osfm_matcher* m, int view_id, int* n_sift, int* n_surf) {
+    if (!m || view_id < 0 || view_id >= m->num_views) return OSFM_ERR_INVALID_ARGUMENT;
+    if (n_sift) *n_sift = m->kind[0].n[view_id];
+    if (n_surf) *n_surf = m->kind[1].n[view_id];
+    return OSFM_OK;
+}
+
+// ---- batched dense --------------------------------------------------------------------
+
+static int build_plans(osfm_matcher* m, const int32_t* pairs, int npairs, int limit, bool lowres,
+                       std::vector<PairPlan>& plans) {
+    if (npairs < 0 || (npairs > 0 && !pairs)) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad pair list");
+    plans.clear();
+    plans.reserve(npairs);
+    for (int i = 0; i < npairs; ++i) {
+        OS_TRY(check_view(m, pairs[2 * i]));
+        OS_TRY(check_view(m, pairs[2 * i + 1]));
+        plans.push_back(plan_pair(m, pairs[2 * i], pairs[2 * i + 1], limit, lowres));
+    }
+    return OSFM_OK;
+}
+
+int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int npairs) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (require_committed(m) != OSFM_OK) return OSFM_ERR_STATE;
+    std::vector<PairPlan> plans;
+    int r = build_plans(m, pairs, npairs, 0, false, plans);
+    if (r != OSFM_OK) return r;
+    int64_t total = 0;
+    for (PairPlan const& p : plans) total += static_cast<int64_t>(p.len12) + p.len21;
+    return total;
+}
+
+static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, OutputMode mode, int only_kind,
+                             int32_t* matches, int64_t* offsets, int32_t* n_consistent) {
+    CU_TRY(m, cudaSetDevice(m->device));
+    m->scan_ms_acc = 0.0;
+    CU_TRY(m, cudaEventRecord(m->ev[2], m->stream));
+    int64_t host_base = 0;
+    int r = for_each_batch(plans, [&](size_t first, size_t last, int64_t dense) -> int {
+        std::vector<PairPlan> sub(plans.begin() + first, plans.begin() + last);
+        OS_TRY(run_batch(m, sub, dense, mode, only_kind));
+        if (dense > 0 && matches)
+            CU_TRY(m, cudaMemcpyAsync(matches + host_base, m->d_dense.p, sizeof(int32_t) * dense,
+                                      cudaMemcpyDeviceToHost, m->stream));
+        if (n_consistent)
+            CU_TRY(m, cudaMemcpyAsync(n_consistent + first, m->d_counts.p, sizeof(int32_t) * (last - first),
+                                      cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        if (offsets)
+            for (size_t i = first; i < last; ++i) {
+                offsets[2 * i] = host_base + plans[i].out12;
+                offsets[2 * i + 1] = host_base + plans[i].out21;
+            }
+        host_base += dense;
+        return OSFM_OK;
+    });
+    if (r != OSFM_OK) return r;
+    if (offsets) offsets[2 * plans.size()] = host_base;
+    CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));
+    CU_TRY(m, cudaEventSynchronize(m->ev[3]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]);
+    m->stats.last_total_ms = ms;
+    m->stats.last_scan_ms = m->scan_ms_acc;
+    m->stats.last_comparisons = comparisons_of(plans);
+    return read_counters(m);
+}
+
+int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* matches, int64_t* offsets,
+                     int32_t* n_consistent) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    std::vector<PairPlan> plans;
+    OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
+    return match_pairs_dense(m, plans, kFiltered, -1, matches, offsets, n_consistent);
+}
+
+int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id, int32_t* matches_1_2, int* len_1_2,
+                    int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    int32_t pr[2] = {view_1_id, view_2_id};
+    std::vector<PairPlan> plans;
+    OS_TRY(build_plans(m, pr, 1, 0, false, plans));
+    std::vector<int32_t> buf(static_cast<size_t>(plans[0].len12) + plans[0].len21 + 1);
+    int64_t offs[3];
+    int32_t cnt = 0;
+    OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, buf.data(), offs, &cnt));
+    if (matches_1_2 && plans[0].len12 > 0) memcpy(matches_1_2, buf.data() + offs[0], sizeof(int32_t) * plans[0].len12);
+    if (matches_2_1 && plans[0].len21 > 0) memcpy(matches_2_1, buf.data() + offs[1], sizeof(int32_t) * plans[0].len21);
+    if (len_1_2) *len_1_2 = plans[0].len12;
+    if (len_2_1) *len_2_1 = plans[0].len21;
+    if (n_consistent) *n_consistent = cnt;
+    return OSFM_OK;
+}
+
+int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_id, int32_t* matches_1_2,
+                           int32_t* matches_2_1) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    if (kind != OSFM_KIND_SIFT_U8 && kind != OSFM_KIND_SURF_S8) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "unknown kind %d", kind);
+    OS_TRY(check_view(m, view_1_id));
+    OS_TRY(check_view(m, view_2_id));
+    // twoway_match itself has no "view_1 must be non-empty" rule: both vectors always
+    // have the full set sizes (matching.h:121-122).
+    PairPlan p;
+    p.v1 = view_1_id; p.v2 = view_2_id;
+    for (int kd = 0; kd < 2; ++kd) { p.n1[kd] = 0; p.n2[kd] = 0; }
+    p.n1[kind] = m->kind[kind].n[view_1_id];
+    p.n2[kind] = m->kind[kind].n[view_2_id];
+    p.len12 = p.n1[kind]; p.len21 = p.n2[kind];
+    p.out12 = p.out21 = 0;
+    std::vector<PairPlan> plans(1, p);
+    std::vector<int32_t> buf(static_cast<size_t>(p.len12) + p.len21 + 1);
+    int64_t offs[3];
+    OS_TRY(match_pairs_dense(m, plans, kTwoway, kind, buf.data(), offs, nullptr));
+    if (matches_1_2 && p.len12 > 0) memcpy(matches_1_2, buf.data() + offs[0], sizeof(int32_t) * p.len12);
+    if (matches_2_1 && p.len21 > 0) memcpy(matches_2_1, buf.data() + offs[1], sizeof(int32_t) * p.len21);
+    return OSFM_OK;
+}
+
+int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t num_features, int* n_consistent) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    if (num_features == 0 || num_features > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad num_features");
+    int32_t pr[2] = {view_1_id, view_2_id};
+    std::vector<PairPlan> plans;
+    OS_TRY(build_plans(m, pr, 1, static_cast<int>(num_features), true, plans));
+    int32_t cnt = 0;
+    // count_consistent_matches of the unfiltered two-way result equals the number of
+    // survivors of the mutual filter (matching.cc:39-47 vs :19-36).
+    OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, &cnt));
+    if (n_consistent) *n_consistent = cnt;
+    return OSFM_OK;
+}
+
+// ---- batched, device-resident, compacted ------------------------------------------------
+
+int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
+                                    int64_t capacity_ij, int64_t* list_offset) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    if (!list_offset) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "list_offset is null");
+    std::vector<PairPlan> plans;
+    OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
+    for (PairPlan& p : plans) {  // SIFT only
+        p.n1[1] = p.n2[1] = 0;
+        p.len12 = p.n1[0]; p.len21 = p.n2[0];
+    }
+    CU_TRY(m, cudaSetDevice(m->device));
+    m->scan_ms_acc = 0.0;
+    CU_TRY(m, cudaEventRecord(m->ev[2], m->stream));
+    int64_t list_base = 0;
+    bool overflow = false;
+    std::vector<int32_t> counts;
+    std::vector<int64_t> loff;
+    std::vector<PairPart> parts;
+    int r = for_each_batch(plans, [&](size_t first, size_t last, int64_t dense) -> int {
+        std::vector<PairPlan> sub(plans.begin() + first, plans.begin() + last);
+        OS_TRY(run_batch(m, sub, dense, kFiltered, 0));
+        size_t const np = last - first;
+        counts.resize(np);
+        CU_TRY(m, cudaMemcpyAsync(counts.data(), m->d_counts.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        loff.resize(np);
+        parts.clear();
+        for (size_t i = 0; i < np; ++i) {
+            list_offset[first + i] = list_base;
+            loff[i] = list_base;
+            list_base += counts[i];
+            if (counts[i] > 0) {
+                PairPart pt;
+                memset(&pt, 0, sizeof pt);
+                pt.out12 = sub[i].out12;
+                pt.n1 = sub[i].n1[0];
+                pt.pair = static_cast<int32_t>(i);
+                parts.push_back(pt);
+            }
+        }
+        if (list_base > capacity_ij || !d_match_ij) { overflow = true; return OSFM_OK; }
+        if (parts.empty()) return OSFM_OK;
+        CU_TRY(m, m->d_listoff.reserve(np));
+        CU_TRY(m, m->d_parts.reserve(parts.size()));
+        CU_TRY(m, cudaMemcpyAsync(m->d_listoff.p, loff.data(), sizeof(int64_t) * np, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(m->d_parts.p, parts.data(), sizeof(PairPart) * parts.size(), cudaMemcpyHostToDevice, m->stream));
+        compact_kernel<<<static_cast<unsigned>(parts.size()), 1024, 0, m->stream>>>(
+            m->d_parts.p, m->d_dense.p, m->d_listoff.p, reinterpret_cast<int2*>(d_match_ij));
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches++;
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        return OSFM_OK;
+    });
+    if (r != OSFM_OK) return r;
+    list_offset[plans.size()] = list_base;
+    CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));
+    CU_TRY(m, cudaEventSynchronize(m->ev[3]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]);
+    m->stats.last_total_ms = ms;
+    m->stats.last_scan_ms = m->scan_ms_acc;
+    m->stats.last_comparisons = comparisons_of(plans);
+    OS_TRY(read_counters(m));
+    if (overflow) return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
+                              (long long)list_base, (long long)capacity_ij);
+    return OSFM_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------
+
+int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
+    if (!m || !out) return OSFM_ERR_INVALID_ARGUMENT;
+    *out = m->stats;
+    return OSFM_OK;
+}
+
+int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
+    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->scan_mode = mode;
+    return OSFM_OK;
+}
+
+int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int view_c, int32_t* out, int64_t out_ints) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    if (kind != 0 && kind != 1) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "unknown kind %d", kind);
+    OS_TRY(check_view(m, view_q));
+    OS_TRY(check_view(m, view_c));
+    CU_TRY(m, cudaSetDevice(m->device));
+    int const nq = m->kind[kind].n[view_q], nc = m->kind[kind].n[view_c];
+    if (nq <= 0 || nc <= 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "empty view");
+    int64_t const ld = static_cast<int64_t>(kBlockN) * ((nc + kBlockN - 1) / kBlockN);
+    if (!out || out_ints < static_cast<int64_t>(nq) * ld) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "dump buffer too small");
+    int32_t* d = nullptr;
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int32_t) * nq * ld));
+    std::vector<JobSpec> specs(1, JobSpec{view_q, nq, view_c, nc});
+    std::vector<int64_t> out_row;
+    int r = run_jobs(m, kind, specs, out_row, d, ld);
+    if (r == OSFM_OK) {
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, sizeof(int32_t) * nq * ld, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) r = cuda_fail(m, e, "dump copy");
+    }
+    cudaFree(d);
+    return r;
+}
+
+}  // extern "C"

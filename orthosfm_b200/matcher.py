@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's matcher interface over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference
+(paths relative to /root/reference):
+
+* ``Matching.Options`` / ``Matching.Result``      src/mve/sfm/matching.h:29-62
+* ``MatchingBase.Options``                        src/mve/sfm/matching_base.h:25-31
+* ``ExhaustiveMatching.init / pairwise_match / pairwise_match_lowres``
+                                                  src/mve/sfm/exhaustive_matching.cc:56,115,147
+* ``FeatureSet`` / ``Viewport``                   src/mve/sfm/feature_set.h:70-72,
+                                                  src/mve/sfm/bundler_common.h:37-62
+
+All matching work happens in libosfm_match.so (CUDA, sm_100a).  Nothing here falls back
+to the CPU: if the library or the GPU is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import KIND_SIFT_U8, KIND_SURF_S8, MatcherError
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class Matching:
+    """sfm::Matching -- options / result types and the small list utilities."""
+
+    @dataclass
+    class Options:  # matching.h:29-50
+        descriptor_length: int
+        lowe_ratio_threshold: float
+        distance_threshold: float
+
+    @dataclass
+    class Result:  # matching.h:56-62
+        matches_1_2: np.ndarray = field(default_factory=lambda: np.empty(0, np.int32))
+        matches_2_1: np.ndarray = field(default_factory=lambda: np.empty(0, np.int32))
+
+    @staticmethod
+    def count_consistent_matches(matches: "Matching.Result") -> int:
+        """matching.cc:39-47 (host utility for callers that already hold a Result)."""
+        m12 = np.asarray(matches.matches_1_2)
+        m21 = np.asarray(matches.matches_2_1)
+        idx = np.nonzero(m12 != -1)[0]
+        if idx.size == 0:
+            return 0
+        return int(np.count_nonzero(m21[m12[idx]] == idx))
+
+
+class MatchingBase:
+    @dataclass
+    class Options:  # matching_base.h:25-31
+        sift_matching_opts: Matching.Options = field(
+            default_factory=lambda: Matching.Options(128, 0.8, FLT_MAX))
+        surf_matching_opts: Matching.Options = field(
+            default_factory=lambda: Matching.Options(64, 0.7, FLT_MAX))
+
+
+@dataclass
+class FeatureSet:
+    """The slice of sfm::FeatureSet the matcher reads (feature_set.h:64-72).
+
+    Descriptors are either float arrays as Sift/Surf produce them (n x 128 in [0,1],
+    n x 64 in [-1,1]) or already quantised (uint8 n x 128, int8 n x 64)."""
+    sift_descriptors: Optional[np.ndarray] = None
+    surf_descriptors: Optional[np.ndarray] = None
+    positions: Optional[np.ndarray] = None
+
+    def clear_descriptors(self) -> None:  # feature_set.h:58
+        self.sift_descriptors = None
+        self.surf_descriptors = None
+
+
+@dataclass
+class Viewport:  # bundler_common.h:37-62
+    features: FeatureSet = field(default_factory=FeatureSet)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
+
+
+class ExhaustiveMatching:
+    """Drop-in for sfm::ExhaustiveMatching, computing on a B200.
+
+    ``init`` stages every view's descriptors into HBM once; ``pairwise_match`` and
+    ``pairwise_match_lowres`` return exactly what the reference returns.  ``match_pairs``
+    is the batched form the pipeline should prefer (all pairs in one persistent kernel).
+    """
+
+    def __init__(self, opts: Optional[MatchingBase.Options] = None, device: int = 0):
+        self.opts = opts if opts is not None else MatchingBase.Options()
+        if self.opts.sift_matching_opts.descriptor_length != 128 or \
+                self.opts.surf_matching_opts.descriptor_length != 64:
+            raise ValueError("descriptor lengths are fixed: 128 (SIFT) and 64 (SURF)")
+        self._L = _lib.load()
+        cfg = _lib.Config()
+        self._L.osfm_match_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.sift_lowe_ratio = self.opts.sift_matching_opts.lowe_ratio_threshold
+        cfg.sift_distance_threshold = self.opts.sift_matching_opts.distance_threshold
+        cfg.surf_lowe_ratio = self.opts.surf_matching_opts.lowe_ratio_threshold
+        cfg.surf_distance_threshold = self.opts.surf_matching_opts.distance_threshold
+        self._h = C.c_void_p()
+        rc = self._L.osfm_match_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.osfm_match_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                self._L.osfm_match_destroy(self._h)
+                self._h = C.c_void_p()
+            raise MatcherError(rc, msg)
+        self._sizes: List[tuple] = []
+        self._keepalive = None
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise MatcherError(rc, self._L.osfm_match_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.osfm_match_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- ExhaustiveMatching::init ----------------------------------------------------------
+    def init(self, viewports: Sequence[Viewport]) -> None:
+        if viewports is None:
+            raise ValueError("Viewports must not be null")  # bundler_matching.cc:47-48
+        self._check(self._L.osfm_match_begin(self._h, len(viewports)))
+        self._sizes = []
+        for v, vp in enumerate(viewports):
+            fs = vp.features if hasattr(vp, "features") else vp
+            sift = None if fs.sift_descriptors is None else np.asarray(fs.sift_descriptors)
+            surf = None if fs.surf_descriptors is None else np.asarray(fs.surf_descriptors)
+            n_sift = 0 if sift is None else sift.reshape(-1, 128).shape[0]
+            n_surf = 0 if surf is None else surf.reshape(-1, 64).shape[0]
+            quantised = (sift is None or sift.dtype == np.uint8) and (surf is None or surf.dtype == np.int8)
+            if quantised:
+                s = None if sift is None else np.ascontiguousarray(sift, np.uint8).reshape(-1, 128)
+                f = None if surf is None else np.ascontiguousarray(surf, np.int8).reshape(-1, 64)
+                self._check(self._L.osfm_match_set_view_q8(self._h, v, _ptr(s), n_sift, _ptr(f), n_surf))
+            else:
+                s = None if sift is None else np.ascontiguousarray(sift, np.float32).reshape(-1, 128)
+                f = None if surf is None else np.ascontiguousarray(surf, np.float32).reshape(-1, 64)
+                self._check(self._L.osfm_match_set_view_f32(self._h, v, _ptr(s), n_sift, 128,
+                                                            _ptr(f), n_surf, 64))
+            self._sizes.append((n_sift, n_surf))
+        self._check(self._L.osfm_match_commit(self._h))
+
+    def init_device_pool(self, sift_pool, row_offsets, sizes) -> None:
+        """Adopts a SIFT descriptor pool already resident on this GPU (a torch uint8
+        tensor of shape [rows + >=256 padding rows, 128]); used by the multi-GPU path after
+        the NCCL broadcast.  ``row_offsets[v]`` / ``sizes[v]`` locate view v."""
+        off = np.ascontiguousarray(row_offsets, np.int64)
+        n = np.ascontiguousarray(sizes, np.int32)
+        rows = int(sift_pool.shape[0]) - 256
+        if rows < 0 or (off.size and int((off + n).max()) > rows):
+            raise ValueError("pool needs 256 padding rows after the last view")
+        self._check(self._L.osfm_match_commit_device(
+            self._h, int(n.size), C.c_void_p(int(sift_pool.data_ptr())),
+            off.ctypes.data_as(C.POINTER(C.c_int64)), n.ctypes.data_as(C.POINTER(C.c_int32)),
+            C.c_int64(rows), None, None, None, C.c_int64(0)))
+        self._sizes = [(int(x), 0) for x in n]
+        self._keepalive = sift_pool
+
+    @property
+    def num_views(self) -> int:
+        return len(self._sizes)
+
+    def view_size(self, view_id: int) -> tuple:
+        return self._sizes[view_id]
+
+    # -- ExhaustiveMatching::pairwise_match ------------------------------------------------
+    def pairwise_match(self, view_1_id: int, view_2_id: int,
+                       result: Optional[Matching.Result] = None) -> Matching.Result:
+        n1 = sum(self._sizes[view_1_id]) if 0 <= view_1_id < len(self._sizes) else 0
+        n2 = sum(self._sizes[view_2_id]) if 0 <= view_2_id < len(self._sizes) else 0
+        m12 = np.empty(max(n1, 1), np.int32)
+        m21 = np.empty(max(n2, 1), np.int32)
+        l12, l21, cnt = C.c_int(0), C.c_int(0), C.c_int(0)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_pair(self._h, view_1_id, view_2_id,
+                                            m12.ctypes.data_as(i32p), C.byref(l12),
+                                            m21.ctypes.data_as(i32p), C.byref(l21), C.byref(cnt)))
+        if result is None:
+            result = Matching.Result()
+        result.matches_1_2 = m12[:l12.value].copy()
+        result.matches_2_1 = m21[:l21.value].copy()
+        self.last_consistent = cnt.value
+        return result
+
+    # -- ExhaustiveMatching::pairwise_match_lowres -----------------------------------------
+    def pairwise_match_lowres(self, view_1_id: int, view_2_id: int, num_features: int) -> int:
+        cnt = C.c_int(0)
+        self._check(self._L.osfm_match_pair_lowres(self._h, view_1_id, view_2_id,
+                                                   C.c_size_t(num_features), C.byref(cnt)))
+        return cnt.value
+
+    # -- Matching::twoway_match<T> ---------------------------------------------------------
+    def twoway_match(self, kind: int, view_1_id: int, view_2_id: int) -> Matching.Result:
+        k = 0 if kind == KIND_SIFT_U8 else 1
+        n1 = self._sizes[view_1_id][k]
+        n2 = self._sizes[view_2_id][k]
+        m12 = np.empty(max(n1, 1), np.int32)
+        m21 = np.empty(max(n2, 1), np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_pair_twoway(self._h, kind, view_1_id, view_2_id,
+                                                   m12.ctypes.data_as(i32p), m21.ctypes.data_as(i32p)))
+        return Matching.Result(m12[:n1].copy(), m21[:n2].copy())
+
+    # -- batched ------------------------------------------------------------------------------
+    def match_pairs(self, pairs) -> tuple:
+        """All pairs in one pass.  Returns (results, n_consistent): a list of
+        Matching.Result (views into one dense buffer) and an int32 array of
+        count_consistent_matches per pair."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pr.shape[0]
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        total = self._L.osfm_match_pairs_result_size(self._h, pr.ctypes.data_as(i32p), npairs)
+        if total < 0:
+            self._check(int(total))
+        dense = np.empty(max(int(total), 1), np.int32)
+        offsets = np.zeros(2 * npairs + 1, np.int64)
+        counts = np.zeros(max(npairs, 1), np.int32)
+        self._check(self._L.osfm_match_pairs(self._h, pr.ctypes.data_as(i32p), npairs,
+                                             dense.ctypes.data_as(i32p), offsets.ctypes.data_as(i64p),
+                                             counts.ctypes.data_as(i32p)))
+        out = []
+        for p in range(npairs):
+            a, b, c = offsets[2 * p], offsets[2 * p + 1], offsets[2 * p + 2]
+            out.append(Matching.Result(dense[a:b], dense[b:c]))
+        return out, counts[:npairs]
+
+    def match_pairs_compact(self, pairs, out_ij) -> np.ndarray:
+        """Device-resident batched matching (SIFT): surviving (i, j) index pairs of every
+        image pair, ordered by i, written to the int32 torch tensor ``out_ij`` of shape
+        [capacity, 2] on this GPU.  Returns the int64 list offsets (npairs + 1)."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pr.shape[0]
+        loff = np.zeros(npairs + 1, np.int64)
+        rc = self._L.osfm_match_pairs_compact_device(
+            self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), npairs,
+            C.c_void_p(int(out_ij.data_ptr())), C.c_int64(int(out_ij.shape[0])),
+            loff.ctypes.data_as(C.POINTER(C.c_int64)))
+        self._check(rc)
+        return loff
+
+    # -- introspection --------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self._check(self._L.osfm_match_get_stats(self._h, C.byref(s)))
+        return s.asdict()
+
+    def debug_set_scan_mode(self, mode: int) -> None:
+        self._check(self._L.osfm_match_debug_set_scan_mode(self._h, mode))
+
+    def debug_dump_similarity(self, kind: int, view_q: int, view_c: int) -> np.ndarray:
+        k = 0 if kind == KIND_SIFT_U8 else 1
+        nq = self._sizes[view_q][k]
+        nc = self._sizes[view_c][k]
+        ld = 256 * ((nc + 255) // 256)
+        out = np.zeros((nq, ld), np.int32)
+        self._check(self._L.osfm_match_debug_dump_similarity(
+            self._h, kind, view_q, view_c, out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(out.size)))
+        return out[:, :nc]
