@@ -1,0 +1,122 @@
+"""Multi-GPU plumbing for the matcher: one process per GPU, image pairs partitioned across
+ranks, descriptor pool replicated with one broadcast, match lists gathered to rank 0.
+
+The reference has no multi-GPU or multi-process code at all; its only
+parallelism is an OpenMP loop over the flat pair index
+(src/mve/sfm/bundler_matching.cc:74-132) whose iterations are independent.  That is the
+unit sharded here.  There is no collective on the data path: the broadcast happens once
+before matching and the gather once after it.
+
+Works with NCCL (GPU tensors) and gloo (CPU tensors; used by the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def partition_pairs(pairs: np.ndarray, sizes: Sequence[int], world_size: int) -> List[np.ndarray]:
+    """Deterministic cost-balanced partition of the pair list.
+
+    Cost of a pair is n1*n2 (the matcher's work is exactly proportional to it).  Pairs are
+    visited in the reference's enumeration order and handed to the least-loaded rank
+    (ties: lowest rank), so equal-size views degenerate to round-robin.  Returns, per rank,
+    the indices into ``pairs`` it owns (ascending)."""
+    pairs = np.asarray(pairs, np.int64).reshape(-1, 2)
+    sizes = np.asarray(sizes, np.int64)
+    cost = sizes[pairs[:, 0]] * sizes[pairs[:, 1]] if pairs.size else np.zeros(0, np.int64)
+    owned: List[List[int]] = [[] for _ in range(world_size)]
+    if pairs.shape[0] == 0:
+        return [np.zeros(0, np.int64) for _ in range(world_size)]
+    if np.all(cost == cost[0]):
+        for r in range(world_size):
+            owned[r] = list(range(r, pairs.shape[0], world_size))
+    else:
+        load = np.zeros(world_size, np.int64)
+        for i in range(pairs.shape[0]):
+            r = int(np.argmin(load))
+            owned[r].append(i)
+            load[r] += cost[i]
+    return [np.asarray(o, np.int64) for o in owned]
+
+
+def broadcast_pool(pool, src: int = 0):
+    """Replicates the packed descriptor pool (uint8 tensor [rows, 128]) from ``src`` to
+    every rank (NCCL broadcast over NVLink on the GPU box)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(pool, src=src)
+    return pool
+
+
+def gather_match_lists(local_ij, local_offsets: np.ndarray, owned: np.ndarray, npairs: int,
+                       dst: int = 0) -> Tuple[object, np.ndarray]:
+    """Gathers every rank's compacted (i, j) lists to ``dst`` and orders them by global
+    pair index.
+
+    local_ij      int32 tensor [>= local_offsets[-1], 2] on this rank's device
+    local_offsets int64 array, len(owned) + 1
+    owned         global pair indices of this rank's lists (ascending)
+    Returns (ij, offsets) on ``dst`` -- ij int32 [total, 2], offsets int64 [npairs + 1] --
+    and (None, None) on the other ranks."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        total = int(local_offsets[-1])
+        offsets = np.zeros(npairs + 1, np.int64)
+        counts = np.zeros(npairs, np.int64)
+        counts[owned] = np.diff(local_offsets)
+        offsets[1:] = np.cumsum(counts)
+        return local_ij[:total], offsets
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = local_ij.device
+    # 1. every rank learns every pair's list length (one small all-reduce)
+    counts = torch.zeros(npairs, dtype=torch.int64, device=dev)
+    if len(owned):
+        counts[torch.as_tensor(owned, device=dev)] = torch.as_tensor(np.diff(local_offsets), device=dev)
+    dist.all_reduce(counts)
+    counts_h = counts.cpu().numpy()
+    offsets = np.zeros(npairs + 1, np.int64)
+    offsets[1:] = np.cumsum(counts_h)
+    # per-rank totals follow from the (deterministic) partition
+    owner = np.full(npairs, -1, np.int64)
+    all_owned: List[np.ndarray] = [None] * world  # type: ignore[list-item]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.asarray(owned, np.int64))
+    for r in range(world):
+        all_owned[r] = gathered[r]
+        owner[all_owned[r]] = r
+    totals = [int(counts_h[all_owned[r]].sum()) for r in range(world)]
+
+    # 2. payload: point-to-point into rank dst's staging buffers
+    my_total = int(local_offsets[-1])
+    if rank != dst:
+        if my_total > 0:
+            dist.send(local_ij[:my_total].contiguous(), dst=dst)
+        return None, None
+    stage = []
+    for r in range(world):
+        if r == dst:
+            stage.append(local_ij[:my_total])
+        elif totals[r] > 0:
+            buf = torch.empty((totals[r], 2), dtype=torch.int32, device=dev)
+            dist.recv(buf, src=r)
+            stage.append(buf)
+        else:
+            stage.append(torch.empty((0, 2), dtype=torch.int32, device=dev))
+    # 3. reorder rank-major lists into global pair order
+    out = torch.empty((int(offsets[-1]), 2), dtype=torch.int32, device=dev)
+    for r in range(world):
+        if totals[r] == 0:
+            continue
+        lens = counts_h[all_owned[r]]
+        src_off = np.concatenate([[0], np.cumsum(lens)])
+        dst_off = offsets[all_owned[r]]
+        # build one gather index for the whole rank
+        idx = np.concatenate([np.arange(dst_off[k], dst_off[k] + lens[k]) for k in range(len(lens))]) \
+            if len(lens) else np.zeros(0, np.int64)
+        out[torch.as_tensor(idx, device=dev)] = stage[r][:int(src_off[-1])]
+    return out, offsets

@@ -1,0 +1,291 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the CPU oracle on the same inputs.  Integer work: the bar is bit-exact."""
+import numpy as np
+import pytest
+
+from orthosfm_b200 import (ExhaustiveMatching, FeatureSet, KIND_SIFT_U8, KIND_SURF_S8,
+                           MatcherError, Matching, MatchingBase, Viewport, synth)
+
+pytestmark = pytest.mark.gpu
+
+from test_oracle import CASE_NAMES  # noqa: E402
+
+U8_CASES = [n for n in CASE_NAMES if n.startswith("u8.")]
+S8_CASES = [n for n in CASE_NAMES if n.startswith("s8.")]
+
+
+def vps(sift=None, surf=None):
+    n = len(sift) if sift is not None else len(surf)
+    return [Viewport(FeatureSet(sift_descriptors=None if sift is None else sift[i],
+                                surf_descriptors=None if surf is None else surf[i])) for i in range(n)]
+
+
+def matcher(sift=None, surf=None, opts=None):
+    m = ExhaustiveMatching(opts)
+    m.init(vps(sift, surf))
+    return m
+
+
+def assert_clean(m):
+    st = m.stats()
+    assert st["self_check_failures"] == 0
+    assert st["kernel_launches"] > 0
+
+
+# ------------------------------------------------------------------ tensor-core product
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (128, 256), (100, 300), (129, 257), (300, 1000)])
+def test_similarity_matrix_is_exact(n1, n2):
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    a = rng.integers(0, 256, (n1, 128), dtype=np.uint8)
+    b = rng.integers(0, 256, (n2, 128), dtype=np.uint8)
+    with matcher([a, b]) as m:
+        s = m.debug_dump_similarity(KIND_SIFT_U8, 0, 1)
+    assert np.array_equal(s, a.astype(np.int64) @ b.astype(np.int64).T)
+
+
+def test_similarity_matrix_signed_is_exact():
+    rng = np.random.default_rng(5)
+    a = rng.integers(-127, 128, (200, 64), dtype=np.int8)
+    b = rng.integers(-127, 128, (333, 64), dtype=np.int8)
+    with matcher(surf=[a, b]) as m:
+        s = m.debug_dump_similarity(KIND_SURF_S8, 0, 1)
+    assert np.array_equal(s, a.astype(np.int64) @ b.astype(np.int64).T)
+
+
+# ------------------------------------------------------------------ golden vectors
+
+@pytest.mark.parametrize("name", U8_CASES)
+def test_golden_u8(golden_cases, name):
+    z, _ = golden_cases
+    a, b, ratio = z[name + ".a"], z[name + ".b"], float(z[name + ".ratio"])
+    opts = MatchingBase.Options()
+    opts.sift_matching_opts.lowe_ratio_threshold = ratio
+    with matcher([a, b], opts=opts) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        assert np.array_equal(tw.matches_1_2, z[name + ".t12"])
+        assert np.array_equal(tw.matches_2_1, z[name + ".t21"])
+        res = m.pairwise_match(0, 1)
+        assert np.array_equal(res.matches_1_2, z[name + ".f12"])
+        assert np.array_equal(res.matches_2_1, z[name + ".f21"])
+        assert m.last_consistent == int(z[name + ".count"])
+        assert_clean(m)
+
+
+@pytest.mark.parametrize("name", S8_CASES)
+def test_golden_s8(golden_cases, name):
+    z, _ = golden_cases
+    a, b, ratio = z[name + ".a"], z[name + ".b"], float(z[name + ".ratio"])
+    opts = MatchingBase.Options()
+    opts.surf_matching_opts.lowe_ratio_threshold = ratio
+    with matcher(surf=[a, b], opts=opts) as m:
+        tw = m.twoway_match(KIND_SURF_S8, 0, 1)
+        assert np.array_equal(tw.matches_1_2, z[name + ".t12"])
+        assert np.array_equal(tw.matches_2_1, z[name + ".t21"])
+        res = m.pairwise_match(0, 1)
+        assert np.array_equal(res.matches_1_2, z[name + ".f12"])
+        assert np.array_equal(res.matches_2_1, z[name + ".f21"])
+        assert_clean(m)
+
+
+def test_golden_real_image_pair(golden_real):
+    g = golden_real
+    with matcher([g["sift_0"], g["sift_1"]]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 1, 0)
+        assert np.array_equal(tw.matches_1_2, g["twoway_12"])
+        assert np.array_equal(tw.matches_2_1, g["twoway_21"])
+        res = m.pairwise_match(1, 0)
+        assert np.array_equal(res.matches_1_2, g["match_12"])
+        assert np.array_equal(res.matches_2_1, g["match_21"])
+        assert m.last_consistent == 810
+        assert m.pairwise_match_lowres(1, 0, 500) == int(g["lowres_500"])
+        assert_clean(m)
+
+
+def test_quantiser_matches_convert_descriptor(ora, golden_real):
+    """set_view_f32 quantises on the device exactly like convert_descriptor."""
+    g = golden_real
+    rng = np.random.default_rng(11)
+    f = np.concatenate([g["float_sample"], rng.uniform(-0.2, 1.3, (200, 128)).astype(np.float32)])
+    f[64, :6] = [0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 0.49999 / 255, 1.0]
+    s = rng.uniform(-1.2, 1.2, (150, 64)).astype(np.float32)
+    s[0, :4] = [0.5 / 127, -0.5 / 127, 1.5 / 127, -126.5 / 127]
+    qs, qf = ora.quantize_sift(f), ora.quantize_surf(s)
+    with ExhaustiveMatching() as m:
+        m.init([Viewport(FeatureSet(f, s)), Viewport(FeatureSet(qs, qf))])
+        # identical quantised sets -> the similarity of view 0 with view 1 has the squared
+        # norms on its diagonal and is symmetric; compare it with the oracle's bytes
+        got = m.debug_dump_similarity(KIND_SIFT_U8, 0, 1)
+        want = qs.astype(np.int64) @ qs.astype(np.int64).T
+        assert np.array_equal(got, want)
+        got = m.debug_dump_similarity(KIND_SURF_S8, 0, 1)
+        assert np.array_equal(got, qf.astype(np.int64) @ qf.astype(np.int64).T)
+
+
+# ------------------------------------------------------------------ seeded random shapes
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 1000), (1000, 1), (127, 255), (128, 256), (129, 257),
+                                   (500, 700), (2000, 3000), (4096, 4096), (5000, 333)])
+def test_twoway_and_filtered_match_oracle(ora, n1, n2):
+    vs = synth.sift_views(7, 2, max(n1, n2))
+    a, b = vs[0][:n1], vs[1][:n2]
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        res = m.pairwise_match(0, 1)
+        assert_clean(m)
+    o12, o21 = ora.twoway("u8", a, b, 0.8)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+    f12, f21 = ora.remove_inconsistent(o12, o21)
+    assert np.array_equal(res.matches_1_2, f12) and np.array_equal(res.matches_2_1, f21)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_adversarial_bytes_match_oracle(ora, seed):
+    """Arbitrary bytes: inner products up to 8.3e6, every 16-bit lane wraps."""
+    rng = np.random.default_rng(seed)
+    hi = [256, 96, 48, 200][seed]
+    n1, n2 = int(rng.integers(1, 600)), int(rng.integers(1, 600))
+    a = rng.integers(0, hi, (n1, 128), dtype=np.uint8)
+    b = rng.integers(0, hi, (n2, 128), dtype=np.uint8)
+    k = min(n1, n2) // 3
+    b[:k] = a[:k]                       # exact duplicates
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        assert_clean(m)
+    o12, o21 = ora.twoway("u8", a, b, 0.8)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+
+
+@pytest.mark.parametrize("ratio,dist", [(0.8, None), (1.0, None), (0.6, None), (0.8, 150.0), (0.95, 60.0)])
+def test_thresholds(ora, ratio, dist):
+    vs = synth.sift_views(9, 2, 900)
+    opts = MatchingBase.Options()
+    opts.sift_matching_opts.lowe_ratio_threshold = ratio
+    if dist is not None:
+        opts.sift_matching_opts.distance_threshold = dist
+    with matcher(vs, opts=opts) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+    kw = {} if dist is None else {"dist": dist}
+    o12, o21 = ora.twoway("u8", vs[0], vs[1], ratio, **kw)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+
+
+def test_surf_synthetic_matches_oracle(ora):
+    pool = synth.surf_pool(4, 400)
+    a, b = synth.surf_view(4, 0, 1500, pool), synth.surf_view(4, 1, 1100, pool)
+    with matcher(surf=[a, b]) as m:
+        tw = m.twoway_match(KIND_SURF_S8, 0, 1)
+        assert_clean(m)
+    o12, o21 = ora.twoway("s8", a, b, 0.7)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+    assert (o12 >= 0).sum() > 50
+
+
+# ------------------------------------------------------------------ the plugin surface
+
+def test_pairwise_match_sift_plus_surf_combined(ora):
+    """ExhaustiveMatching::pairwise_match incl. combine_results and the rule that a feature
+    type only takes part if view_1 has descriptors of it."""
+    sp, fp = synth.scene_pool(5, 300), synth.surf_pool(5, 200)
+    sizes = [(600, 300), (700, 250), (0, 200), (400, 0), (0, 0)]
+    sift = [synth.sift_view(5, v, s, sp) for v, (s, _) in enumerate(sizes)]
+    surf = [synth.surf_view(5, v, f, fp) for v, (_, f) in enumerate(sizes)]
+    with matcher(sift, surf) as m:
+        for v1 in range(len(sizes)):
+            for v2 in range(len(sizes)):
+                if v1 == v2:
+                    continue
+                res = m.pairwise_match(v1, v2)
+                o12, o21 = ora.pairwise_match(sift[v1], sift[v2], surf[v1], surf[v2])
+                assert np.array_equal(res.matches_1_2, o12), (v1, v2)
+                assert np.array_equal(res.matches_2_1, o21), (v1, v2)
+                assert m.pairwise_match_lowres(v1, v2, 150) == \
+                    ora.pairwise_match_lowres(sift[v1], sift[v2], surf[v1], surf[v2], 150)
+        assert_clean(m)
+
+
+def test_batched_equals_single_pair_and_compact_lists(ora):
+    import torch
+    sizes = [700, 1, 0, 333, 1024, 129]
+    pool = synth.scene_pool(6, 400)
+    views = [synth.sift_view(6, v, n, pool) for v, n in enumerate(sizes)]
+    pairs = synth.all_pairs(len(sizes))
+    with matcher(views) as m:
+        results, counts = m.match_pairs(pairs)
+        out_ij = torch.empty((4096, 2), dtype=torch.int32, device="cuda")
+        loff = m.match_pairs_compact(pairs, out_ij)
+        ij = out_ij.cpu().numpy()
+        for p, (v1, v2) in enumerate(pairs):
+            o12, o21 = ora.match_filtered("u8", views[v1], views[v2], 0.8)
+            assert np.array_equal(results[p].matches_1_2, o12), (v1, v2)
+            assert np.array_equal(results[p].matches_2_1, o21), (v1, v2)
+            assert counts[p] == int((o12 >= 0).sum())
+            lst = ij[loff[p]:loff[p + 1]]
+            idx = np.nonzero(o12 >= 0)[0]
+            assert np.array_equal(lst[:, 0], idx) and np.array_equal(lst[:, 1], o12[idx])
+        assert_clean(m)
+        # too small a list buffer is an error, not a silent truncation
+        with pytest.raises(MatcherError):
+            m.match_pairs_compact(pairs, out_ij[:3])
+
+
+def test_error_behaviour():
+    vs = synth.sift_views(8, 2, 64)
+    m = ExhaustiveMatching()
+    with pytest.raises(MatcherError) as ei:      # match before init/commit
+        m.pairwise_match_lowres(0, 1, 10)
+    assert ei.value.code == -4
+    m.init(vps(vs))
+    with pytest.raises(MatcherError) as ei:
+        m.pairwise_match_lowres(0, 5, 10)
+    assert ei.value.code == -1
+    with pytest.raises(MatcherError):
+        m.match_pairs(np.array([[0, -1]], np.int32))
+    # the handle stays usable after an error
+    assert isinstance(m.pairwise_match(0, 1), Matching.Result)
+    m.close()
+
+
+# ------------------------------------------------------------------ full-size properties
+
+def test_full_size_pair_properties(ora):
+    """BASELINE config 2 sizes (8192 x 8192): checked through size-independent properties
+    plus a sample of rows against the oracle's nearest-neighbour search."""
+    pool = synth.scene_pool(2, 4096)
+    a, b = synth.sift_view(2, 0, 8192, pool), synth.sift_view(2, 1, 8192, pool)
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        res = m.pairwise_match(0, 1)
+        swapped = m.pairwise_match(1, 0)
+        assert_clean(m)
+    m12, m21 = res.matches_1_2, res.matches_2_1
+    # mutual filter: both vectors hold exactly the same pairs
+    i = np.nonzero(m12 >= 0)[0]
+    assert np.array_equal(m21[m12[i]], i)
+    j = np.nonzero(m21 >= 0)[0]
+    assert np.array_equal(m12[m21[j]], j) and i.size == j.size
+    # filtered is a subset of the one-way result
+    assert np.array_equal(m12[i], tw.matches_1_2[i])
+    # swapping the views swaps the vectors
+    assert np.array_equal(swapped.matches_1_2, m21) and np.array_equal(swapped.matches_2_1, m12)
+    assert i.size > 1000   # planted near-duplicates are found
+    # sample rows against the oracle, both directions
+    rng = np.random.default_rng(0)
+    for r in rng.integers(0, 8192, 48):
+        o = ora.twoway("u8", a[r:r + 1], b, 0.8)[0][0]
+        assert tw.matches_1_2[r] == o
+        o = ora.twoway("u8", b[r:r + 1], a, 0.8)[0][0]
+        assert tw.matches_2_1[r] == o
+
+
+def test_many_pairs_one_launch(ora):
+    """12 views x 2048: the persistent kernel over 66 pairs; every pair checked."""
+    views = synth.sift_views(12, 12, 2048)
+    pairs = synth.all_pairs(12)
+    with matcher(views) as m:
+        results, counts = m.match_pairs(pairs)
+        assert_clean(m)
+    for p, (v1, v2) in enumerate(pairs):
+        o12, o21 = ora.match_filtered("u8", views[v1], views[v2], 0.8)
+        assert np.array_equal(results[p].matches_1_2, o12), (v1, v2)
+        assert np.array_equal(results[p].matches_2_1, o21), (v1, v2)

@@ -1,0 +1,148 @@
+"""CPU tests: the C restatement (oracle/) against the golden vectors generated from the
+reference itself, and -- where oracle/_ref exists -- directly against the reference on
+fresh seeded inputs.  This is what pins the oracle (the reference
+ships no golden vectors of its own)."""
+import numpy as np
+import pytest
+
+from orthosfm_b200 import synth
+
+CASE_NAMES = [
+    "u8.synth_700x700", "u8.synth_300x650", "u8.synth_ratio1", "u8.duplicates",
+    "u8.random_bytes", "u8.straddle_65536", "u8.single_candidate", "u8.single_query",
+    "u8.zeros", "u8.lane_wrap", "s8.synth_500x640", "s8.random_bytes", "s8.big_positive",
+    "s8.all_negative", "f32.synth_200x260",
+]
+
+
+def test_golden_case_list_is_complete(golden_cases):
+    _, names = golden_cases
+    assert sorted(names) == sorted(CASE_NAMES)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_oracle_matches_golden(ora, golden_cases, name):
+    z, _ = golden_cases
+    kind = name.split(".")[0]
+    a, b, ratio = z[name + ".a"], z[name + ".b"], float(z[name + ".ratio"])
+    t12, t21 = ora.twoway(kind, a, b, ratio)
+    assert np.array_equal(t12, z[name + ".t12"])
+    assert np.array_equal(t21, z[name + ".t21"])
+    f12, f21 = ora.remove_inconsistent(t12, t21)
+    assert np.array_equal(f12, z[name + ".f12"])
+    assert np.array_equal(f21, z[name + ".f21"])
+    assert ora.count_consistent(t12, t21) == int(z[name + ".count"])
+    # count of the unfiltered result == survivors of the mutual filter
+    assert int((f12 >= 0).sum()) == int(z[name + ".count"])
+
+
+def test_oracle_combine_results_golden(ora, golden_cases):
+    z, _ = golden_cases
+    c12, c21 = ora.combine_results(z["combine.s12"], z["combine.s21"], z["combine.f12"], z["combine.f21"])
+    assert np.array_equal(c12, z["combine.c12"])
+    assert np.array_equal(c21, z["combine.c21"])
+
+
+def test_oracle_real_image_pair(ora, golden_real):
+    g = golden_real
+    t12, t21 = ora.twoway("u8", g["sift_1"], g["sift_0"], 0.8)
+    assert np.array_equal(t12, g["twoway_12"]) and np.array_equal(t21, g["twoway_21"])
+    empty = np.zeros((0, 64), np.int8)
+    m12, m21 = ora.pairwise_match(g["sift_1"], g["sift_0"], empty, empty)
+    assert np.array_equal(m12, g["match_12"]) and np.array_equal(m21, g["match_21"])
+    assert int((m12 >= 0).sum()) == 810
+    assert ora.pairwise_match_lowres(g["sift_1"], g["sift_0"], empty, empty, 500) == int(g["lowres_500"]) == 187
+
+
+def test_oracle_quantiser_golden(ora, golden_real):
+    g = golden_real
+    assert np.array_equal(ora.quantize_sift(g["float_sample"]), g["float_sample_q"])
+
+
+def test_quantiser_rounding_rule(ora):
+    # convert_descriptor: clamp, *255, round half away from zero, truncate to uchar
+    x = np.zeros((1, 128), np.float32)
+    x[0, :8] = [0.0, 1.0, 2.0, -0.3, 0.5 / 255, 1.5 / 255, 0.49999 / 255, 254.5 / 255]
+    q = ora.quantize_sift(x)[0, :8]
+    assert q.tolist() == [0, 255, 255, 0, 1, 2, 0, 255]
+    s = np.zeros((1, 64), np.float32)
+    s[0, :6] = [-1.0, 1.0, -2.0, 0.5 / 127, -0.5 / 127, -1.5 / 127]
+    assert ora.quantize_surf(s)[0, :6].tolist() == [-127, 127, -127, 1, -1, -2]
+
+
+def test_oracle_edge_semantics(ora):
+    """Appendix A of SURVEY.md, each verified against the compiled reference there."""
+    v = synth.sift_views(3, 1, 64)[0]
+    # two identical perfect candidates: the later index wins, d1 = d2 -> ratio 1 > 0.64 rejects
+    # unless d = 0 (0/0 = NaN accepts)
+    q = np.full((1, 128), 0, np.uint8)
+    q[0, :16] = 63                      # |q|^2 = 63504 < 65536: no wrap
+    cands = np.concatenate([v[:5], q, v[5:9], q])
+    d1, d2, i1, i2 = ora.nn("u8", q[0], cands)
+    assert (i1, i2) == (10, 5) and d1 == d2 == 2 * (65025 - 63504)
+    # single candidate: second best stays 0 -> d2 = 65534
+    d1, d2, i1, _ = ora.nn("u8", q[0], q)
+    assert d2 == 65534.0 and i1 == 0
+    # lane wrap: 16 x 64*64 in one lane is seen as 0
+    w = np.zeros((1, 128), np.uint8)
+    w[0, 0::8] = 64
+    d1, _, _, _ = ora.nn("u8", w[0], w)
+    assert d1 == 65534.0
+    # empty sets
+    m12, m21 = ora.twoway("u8", v[:0], v, 0.8)
+    assert m12.size == 0 and (m21 == -1).all()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_vs_reference_fresh_inputs(ora, ref, seed):
+    rng = np.random.default_rng(100 + seed)
+    n1, n2 = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    vs = synth.sift_views(10 + seed, 2, max(n1, n2))
+    cases = [("u8", vs[0][:n1], vs[1][:n2], 0.8),
+             ("u8", rng.integers(0, 256, (n1, 128), dtype=np.uint8),
+              rng.integers(0, 256, (n2, 128), dtype=np.uint8), 0.8),
+             ("u8", rng.integers(0, 48, (n1, 128), dtype=np.uint8),
+              rng.integers(0, 48, (n2, 128), dtype=np.uint8), 0.9),
+             ("s8", rng.integers(-127, 128, (n1, 64), dtype=np.int8),
+              rng.integers(-127, 128, (n2, 64), dtype=np.int8), 0.7),
+             ("s8", synth.surf_view(seed, 0, n1), synth.surf_view(seed, 1, n2), 0.7)]
+    fa = rng.standard_normal((n1, 128)).astype(np.float32)
+    fb = rng.standard_normal((n2, 128)).astype(np.float32)
+    cases.append(("f32", fa / np.linalg.norm(fa, axis=1, keepdims=True),
+                  fb / np.linalg.norm(fb, axis=1, keepdims=True), 0.8))
+    for kind, a, b, ratio in cases:
+        o = ora.twoway(kind, a, b, ratio)
+        r = ref.twoway(kind, a, b, ratio)
+        assert np.array_equal(o[0], r[0]) and np.array_equal(o[1], r[1]), kind
+        assert ora.nn(kind, a[0], b) == ref.nn(kind, a[0], b)
+        of, rf = ora.remove_inconsistent(*o), ref.remove_inconsistent(*r)
+        assert np.array_equal(of[0], rf[0]) and np.array_equal(of[1], rf[1])
+
+
+def test_oracle_pairwise_match_vs_reference_plugin(ora, ref):
+    """ExhaustiveMatching::{init,pairwise_match,pairwise_match_lowres} on float input,
+    including a view without SIFT features (the combine_results size quirk)."""
+    rng = np.random.default_rng(7)
+
+    def sift_f(n):
+        x = np.abs(rng.standard_normal((n, 128))).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        return np.minimum(x, 0.2) / np.linalg.norm(np.minimum(x, 0.2), axis=1, keepdims=True)
+
+    def surf_f(n):
+        x = rng.standard_normal((n, 64)).astype(np.float32)
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    views = [(sift_f(300), surf_f(120)), (sift_f(350), surf_f(90)), (sift_f(0), surf_f(80)),
+             (sift_f(200), surf_f(0))]
+    views[1][0][:100] = views[0][0][:100]
+    views[1][1][:40] = views[0][1][:40]
+    views[2][1][:30] = views[0][1][:30]
+    ex = ref.exhaustive(views)
+    q = [(ora.quantize_sift(s), ora.quantize_surf(f)) for s, f in views]
+    for v1, v2 in [(1, 0), (0, 1), (2, 0), (0, 2), (3, 0), (0, 3), (2, 3), (3, 2)]:
+        r12, r21 = ex.pairwise_match(v1, v2)
+        o12, o21 = ora.pairwise_match(q[v1][0], q[v2][0], q[v1][1], q[v2][1])
+        assert np.array_equal(o12, r12) and np.array_equal(o21, r21), (v1, v2)
+        assert ora.pairwise_match_lowres(q[v1][0], q[v2][0], q[v1][1], q[v2][1], 150) == \
+            ex.pairwise_match_lowres(v1, v2, 150)
