@@ -31,7 +31,7 @@ using namespace osfm;
 namespace {
 
 constexpr int kPadRows = 256;                  // readable zero rows after the last view
-constexpr int64_t kMaxBatchRows = 48ll << 20;  // job rows per batch (bounds scratch memory)
+constexpr int64_t kMaxBatchRows = 16ll << 20;  // job rows per batch (bounds scratch memory)
 constexpr int64_t kMaxBatchDense = 1ll << 30;  // dense result ints per batch (4 GiB)
 
 struct KindPool {
@@ -101,11 +101,22 @@ struct osfm_matcher {
     DevBuf<int4> d_rowres;
     DevBuf<int32_t> d_oneway;
     DevBuf<int64_t> d_slow;
+    DevBuf<int64_t> d_cand;
     DevBuf<PairPart> d_parts;
     DevBuf<int32_t> d_dense;
     DevBuf<int32_t> d_counts;
     DevBuf<int64_t> d_listoff;
     DevBuf<float> d_ftmp;
+    // scratch of the EXACT pass (rows whose best similarity reached 2^16)
+    DevBuf<int> d_slow_cnt;
+    DevBuf<int> d_job_xrow;
+    DevBuf<ScanJob> d_xjobs;
+    DevBuf<uint8_t> d_xpool;
+    DevBuf<int64_t> d_xrow_map;
+    int* d_xmeta = nullptr;
+    CUtensorMap tmap_x;
+    uint8_t* tmap_x_for = nullptr;
+    size_t tmap_x_rows = 0;
     unsigned long long* d_counters = nullptr;  // see PostParams::counters
 
     int scan_mode = 0;
@@ -156,17 +167,21 @@ void free_kind(KindPool& k) {
     k.rows = 0; k.off.clear(); k.n.clear(); k.maxnorm2.clear();
 }
 
-int make_tmap(osfm_matcher* m, KindPool& k) {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(k.rows + kPadRows)};
+// 2-D tensor map over a pool of 128-byte rows; one TMA box = 128 rows (a query half or half
+// a candidate tile), SWIZZLE_128B so the tile lands in the layout tcgen05.mma reads.
+int encode_tmap(osfm_matcher* m, CUtensorMap* map, void* base, int64_t rows_with_pad) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(rows_with_pad)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(kRowBytes)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kRowBytes), static_cast<cuuint32_t>(kBlockM)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kRowBytes), static_cast<cuuint32_t>(kHalfM)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = m->encode(&k.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, k.pool, dims, strides, box, estr,
+    CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(m, OSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return OSFM_OK;
 }
+
+int make_tmap(osfm_matcher* m, KindPool& k) { return encode_tmap(m, &k.tmap, k.pool, k.rows + kPadRows); }
 
 // Per-row squared norms + per-view maxima for the signed kind (wrap certificate).
 int compute_norms(osfm_matcher* m, KindPool& k) {
@@ -195,14 +210,53 @@ int compute_norms(osfm_matcher* m, KindPool& k) {
 
 template <int MODE>
 cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kScanSmemBytes);
     if (e != cudaSuccess) return e;
     int const grid = std::min(m->num_sms, total_items);
-    uint32_t const idesc = make_idesc_i8(kBlockM, kBlockN, k.is_signed ? 1 : 0, k.is_signed ? 1 : 0);
-    scan_kernel<MODE><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, m->d_jobs.p, total_items, m->d_rowres.p, idesc, dump, dump_ld);
+    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, k.is_signed ? 1 : 0, k.is_signed ? 1 : 0);
+    ExactParams ex;
+    memset(&ex, 0, sizeof ex);
+    scan_kernel<MODE, false><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
+        k.tmap, k.tmap, m->d_jobs.p, total_items, m->d_rowres.p, idesc, dump, dump_ld, ex);
     return cudaGetLastError();
+}
+
+// Second pass over the rows finalize_kernel<false> flagged (unsigned kind): plan, gather,
+// and the EXACT variant of the scan kernel.  Everything is sized on the device; the host
+// never learns how many rows there were until it reads the counters.
+int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int64_t rows, const PostParams& pp) {
+    CU_TRY(m, m->d_job_xrow.reserve(static_cast<size_t>(njobs)));
+    CU_TRY(m, m->d_xjobs.reserve(static_cast<size_t>(njobs) + 1));
+    CU_TRY(m, m->d_xrow_map.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, m->d_xpool.reserve(static_cast<size_t>(rows + kPadRows) * kRowBytes));
+    if (m->tmap_x_for != m->d_xpool.p || m->tmap_x_rows != m->d_xpool.cap) {
+        OS_TRY(encode_tmap(m, &m->tmap_x, m->d_xpool.p, static_cast<int64_t>(m->d_xpool.cap / kRowBytes)));
+        m->tmap_x_for = m->d_xpool.p;
+        m->tmap_x_rows = m->d_xpool.cap;
+    }
+    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_slow_cnt.p, m->d_xjobs.p,
+                                                 m->d_job_xrow.p, m->d_xmeta, m->d_counters);
+    CU_TRY(m, cudaGetLastError());
+    exact_gather_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_slow_cnt.p,
+                                                              m->d_job_xrow.p, m->d_slow.p, k.pool,
+                                                              m->d_xpool.p, m->d_xrow_map.p);
+    CU_TRY(m, cudaGetLastError());
+    CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+    ExactParams ex;
+    ex.qpool = m->d_xpool.p;
+    ex.cpool = k.pool;
+    ex.xrow_map = m->d_xrow_map.p;
+    ex.oneway = pp.oneway;
+    ex.total_items_dev = m->d_xmeta;
+    ex.sq_lowe = pp.sq_lowe;
+    ex.sq_dist = pp.sq_dist;
+    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, 0, 0);
+    scan_kernel<0, true><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
+        m->tmap_x, k.tmap, m->d_xjobs.p, 0, nullptr, idesc, nullptr, 0, ex);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += 3;
+    return OSFM_OK;
 }
 
 // Runs scan + finalize + wrap emulation for a list of jobs of one kind.  On return (in
@@ -228,7 +282,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         j.c_maxnorm2 = k.is_signed ? k.maxnorm2[s.c_view] : 0;
         out_row[i] = rows;
         rows += s.q_n;
-        items += (s.q_n + kBlockM - 1) / kBlockM;
+        items += (s.q_n + kItemM - 1) / kItemM;
         jobs.push_back(j);
     }
     if (jobs.empty()) return OSFM_OK;
@@ -244,10 +298,14 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     CU_TRY(m, m->d_rowres.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_slow.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, m->d_cand.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, m->d_slow_cnt.reserve(static_cast<size_t>(njobs)));
+    CU_TRY(m, cudaMemsetAsync(m->d_slow_cnt.p, 0, sizeof(int) * njobs, m->stream));
     CU_TRY(m, cudaMemcpyAsync(m->d_jobs.p, jobs.data(), sizeof(ScanJob) * jobs.size(),
                               cudaMemcpyHostToDevice, m->stream));
     // pageable source: the copy is staged before the call returns, `jobs` may die.
-    CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));
+    CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));      // [0]
+    CU_TRY(m, cudaMemsetAsync(m->d_counters + 4, 0, sizeof(unsigned long long), m->stream));  // [4]
 
     CU_TRY(m, cudaEventRecord(m->ev[0], m->stream));
     cudaError_t e;
@@ -274,17 +332,29 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     pp.slow_list = m->d_slow.p;
     pp.counters = m->d_counters;
     pp.norm2 = k.d_norm2;
+    pp.slow_cnt = m->d_slow_cnt.p;
+    pp.cand_list = m->d_cand.p;
     int const grid = static_cast<int>((rows + 255) / 256);
-    if (k.is_signed) finalize_kernel<true><<<grid, 256, 0, m->stream>>>(pp);
-    else             finalize_kernel<false><<<grid, 256, 0, m->stream>>>(pp);
+    int const rgrid = m->num_sms * 8;
+    if (k.is_signed) {
+        classify_kernel<true><<<grid, 256, 0, m->stream>>>(pp);
+        refine_kernel<true><<<rgrid, 256, 0, m->stream>>>(pp);
+    } else {
+        classify_kernel<false><<<grid, 256, 0, m->stream>>>(pp);
+        refine_kernel<false><<<rgrid, 256, 0, m->stream>>>(pp);
+    }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(m, e, "finalize_kernel launch");
-    int const sgrid = m->num_sms * 2;
-    if (k.is_signed) slow_rows_kernel<true><<<sgrid, 256, 0, m->stream>>>(pp);
-    else             slow_rows_kernel<false><<<sgrid, 256, 0, m->stream>>>(pp);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
+    if (e != cudaSuccess) return cuda_fail(m, e, "classify/refine launch");
     m->stats.kernel_launches += 2;
+    if (k.is_signed) {
+        // adversarial signed input only: warp-per-row emulation on CUDA cores
+        slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
+        m->stats.kernel_launches++;
+    } else {
+        OS_TRY(launch_exact_pass(m, k, njobs, rows, pp));
+    }
 
     // Scan time of this launch; read after the caller's next synchronisation.
     // (cudaEventElapsedTime needs completed events, so we synchronise on ev[1] lazily in
@@ -486,8 +556,10 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     m->num_sms = prop.multiProcessorCount;
     CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 4 * sizeof(unsigned long long)));
-    CU_TRY(m, cudaMemset(m->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 8 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMemset(m->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xmeta), 4 * sizeof(int)));
+    CU_TRY(m, cudaMemset(m->d_xmeta, 0, 4 * sizeof(int)));
 
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -517,8 +589,12 @@ void osfm_match_destroy(osfm_matcher* m) {
     free_kind(m->kind[0]);
     free_kind(m->kind[1]);
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release(); m->d_slow.release();
+    m->d_cand.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
     m->d_ftmp.release();
+    m->d_slow_cnt.release(); m->d_job_xrow.release(); m->d_xjobs.release(); m->d_xpool.release();
+    m->d_xrow_map.release();
+    if (m->d_xmeta) cudaFree(m->d_xmeta);
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->hang_host) {
         HangReport* null_ptr = nullptr;

@@ -89,92 +89,37 @@ struct PostParams {
     float sq_lowe;              // lowe_ratio_threshold^2   (matching.h:126)
     float sq_dist;              // distance_threshold^2     (matching.h:127)
     int64_t* slow_list;         // rows that need the wrap emulation
-    unsigned long long* counters;  // [0] slow rows of this batch, [1] candidate rows,
-                                   // [2] self-check failures, [3] slow rows (cumulative)
+    unsigned long long* counters;  // [0] slow rows of this batch (signed kind), [1] candidate
+                                   // rows (cumulative), [2] self-check failures, [3] slow rows
+                                   // (cumulative), [4] candidate rows of this batch
     const int32_t* norm2;       // signed kind: squared norm per pool row
+    int* slow_cnt;              // unsigned kind: slow rows per job; the rows of job j are
+                                // listed at slow_list[jobs[j].out_row + 0 .. slow_cnt[j])
+    int64_t* cand_list;         // rows that need the exact second best; length = counters[4]
 };
 
-__device__ __forceinline__ int find_job(const ScanJob* __restrict__ jobs, int njobs, int64_t g) {
-    int lo = 0, hi = njobs;
-    while (hi - lo > 1) {
-        int const mid = (lo + hi) >> 1;
-        if (jobs[mid].out_row <= g) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-// nearest_neighbor.cc:262-267 (unsigned) and :234-237 (signed): inner product -> distance.
+// classify_kernel: one thread per job row.  Rows whose ratio test fails even with the lower
+// bound on the second-best similarity are final (-1).  Rows that pass become *candidates*
+// and are appended to a list (warp-aggregated atomic); rows whose best similarity reached
+// 2^16 (unsigned) or whose norms cannot exclude a 16-bit lane wrap (signed) go to the slow
+// list instead.
 template <bool SIGNED>
-__device__ __forceinline__ int ip_to_dist(int ip) {
-    if (SIGNED) {
-        int const x = min(16129, max(0, ip));
-        return 32258 - 2 * x;
-    } else {
-        int const x = 65025 - min(65025, ip);
-        return min(32767, x) * 2;
-    }
-}
-
-// matching.h:138-143.  The quotient is an IEEE float division; 0/0 = NaN compares
-// false and therefore accepts.
-__device__ __forceinline__ bool passes_tests(int d1, int d2, float sq_lowe, float sq_dist) {
-    float const f1 = static_cast<float>(d1);
-    float const f2 = static_cast<float>(d2);
-    if (f1 > sq_dist) return false;
-    if (__fdiv_rn(f1, f2) > sq_lowe) return false;
-    return true;
-}
-
-template <bool SIGNED>
-__device__ __forceinline__ int dot_row(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b) {
-    const uint4* pa = reinterpret_cast<const uint4*>(a);
-    const uint4* pb = reinterpret_cast<const uint4*>(b);
-    int acc = 0;
-#pragma unroll
-    for (int i = 0; i < kRowBytes / 16; ++i) {
-        uint4 const x = __ldg(pa + i);
-        uint4 const y = __ldg(pb + i);
-        if (SIGNED) {
-            acc = __dp4a(static_cast<int>(x.x), static_cast<int>(y.x), acc);
-            acc = __dp4a(static_cast<int>(x.y), static_cast<int>(y.y), acc);
-            acc = __dp4a(static_cast<int>(x.z), static_cast<int>(y.z), acc);
-            acc = __dp4a(static_cast<int>(x.w), static_cast<int>(y.w), acc);
-        } else {
-            unsigned u = static_cast<unsigned>(acc);
-            u = __dp4a(x.x, y.x, u);
-            u = __dp4a(x.y, y.y, u);
-            u = __dp4a(x.z, y.z, u);
-            u = __dp4a(x.w, y.w, u);
-            acc = static_cast<int>(u);
-        }
-    }
-    return acc;
-}
-
-// One thread per job row.  Rows whose ratio test fails even with the lower bound on
-// the second-best similarity are final.  The others are re-examined by the whole warp:
-// lane l recomputes the similarity with candidate pos*32 + l, which yields the exact
-// arg-max (highest index on ties) and the exact second best.
-template <bool SIGNED>
-__global__ void __launch_bounds__(256) finalize_kernel(PostParams p)
+__global__ void __launch_bounds__(256) classify_kernel(PostParams p)
 {
     int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     int const lane = threadIdx.x & 31;
-    bool const valid = g < p.total_rows;
-
-    int q_prow = 0, c_row = 0, c_n = 0, v1 = 0, pos = 0, v2 = 0, result = -1;
-    bool cand = false, slow = false;
-    if (valid) {
-        ScanJob const job = p.jobs[find_job(p.jobs, p.njobs, g)];
-        q_prow = job.q_row + static_cast<int>(g - job.out_row);
-        c_row = job.c_row;
-        c_n = job.c_n;
+    bool cand = false;
+    if (g < p.total_rows) {
+        int const ji = find_job(p.jobs, p.njobs, g);
+        ScanJob const job = p.jobs[ji];
         int4 const rr = p.rowres[g];
-        v1 = rr.x; pos = rr.y; v2 = rr.z;
+        int const v1 = rr.x, v2 = rr.z;
+        int result = -1;
+        bool slow;
         if (SIGNED) {
             // No 16-bit lane can wrap if |a||b| < 2^15 (Cauchy-Schwarz per lane).
-            slow = static_cast<int64_t>(p.norm2[q_prow]) * static_cast<int64_t>(job.c_maxnorm2)
-                   >= (1ll << 30);
+            int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
+            slow = static_cast<int64_t>(p.norm2[q_prow]) * static_cast<int64_t>(job.c_maxnorm2) >= (1ll << 30);
             if (!slow) {
                 if (v1 < 0) {
                     // no candidate reached the initial best of 0: index stays 0
@@ -184,84 +129,74 @@ __global__ void __launch_bounds__(256) finalize_kernel(PostParams p)
                     cand = passes_tests(ip_to_dist<true>(v1), ip_to_dist<true>(v2), p.sq_lowe, p.sq_dist);
                 }
             }
+            if (slow) p.slow_list[atomicAdd(p.counters + 0, 1ull)] = g;
         } else {
             // Any similarity >= 2^16 makes the reference's 16-bit lanes / stores wrap.
             slow = v1 >= 65536;
             if (!slow)
                 cand = passes_tests(ip_to_dist<false>(v1), ip_to_dist<false>(v2), p.sq_lowe, p.sq_dist);
+            else
+                p.slow_list[job.out_row + atomicAdd(p.slow_cnt + ji, 1)] = g;
         }
-        if (slow) {
-            unsigned long long const k = atomicAdd(p.counters + 0, 1ull);
-            p.slow_list[k] = g;
-        }
+        if (!slow && !cand) p.oneway[g] = result;
     }
+    unsigned const cmask = __ballot_sync(0xffffffffu, cand);
+    if (cmask != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(cmask)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) p.cand_list[base + __popc(cmask & ((1u << lane) - 1u))] = g;
+    }
+}
 
-    unsigned cmask = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0 && cmask != 0) atomicAdd(p.counters + 1, static_cast<unsigned long long>(__popc(cmask)));
-    while (cmask != 0) {
-        int const src = __ffs(cmask) - 1;
-        cmask &= cmask - 1;
-        int const b_q = __shfl_sync(0xffffffffu, q_prow, src);
-        int const b_crow = __shfl_sync(0xffffffffu, c_row, src);
-        int const b_cn = __shfl_sync(0xffffffffu, c_n, src);
-        int const b_v1 = __shfl_sync(0xffffffffu, v1, src);
-        int const b_pos = __shfl_sync(0xffffffffu, pos, src);
-        int const b_v2 = __shfl_sync(0xffffffffu, v2, src);
-
-        int const col = b_pos * kChunk + lane;
-        int dot = INT_MIN / 2;
-        if (col < b_cn)
-            dot = dot_row<SIGNED>(p.pool + static_cast<int64_t>(b_q) * kRowBytes,
-                                  p.pool + (static_cast<int64_t>(b_crow) + col) * kRowBytes);
-        unsigned const eq = __ballot_sync(0xffffffffu, dot == b_v1);
-        int const jl = 31 - __clz(eq);  // highest index wins ties (nearest_neighbor.cc:89)
-        int const second = __reduce_max_sync(0xffffffffu, lane == jl ? INT_MIN / 2 : dot);
-        if (lane == src) {
+// refine_kernel: half a warp per candidate row.  Lane l recomputes the similarity with
+// candidate pos*16 + l, which yields the exact arg-max (highest index on ties) and the exact
+// second best; then the reference's tests decide.  Grid-strides over the candidate list,
+// whose length is only known on the device.
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) refine_kernel(PostParams p)
+{
+    unsigned long long const ncand = *reinterpret_cast<volatile unsigned long long*>(p.counters + 4);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ncand > 0) atomicAdd(p.counters + 1, ncand);
+    int const lane = threadIdx.x & 31;
+    int const sub = lane & 15;
+    unsigned const hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+    int const hshift = lane & 16;
+    unsigned long long const nhalf = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 4;
+    unsigned long long k = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+    // both halves of a warp must iterate the same number of times (full-mask ballots)
+    unsigned long long const kmax = ((ncand + 1) >> 1) << 1;
+    for (; k < kmax; k += nhalf) {
+        bool const active = k < ncand;
+        int dot = INT_MIN / 2, v1 = 0, v2 = 0, pos = 0;
+        int64_t g = 0;
+        if (active) {
+            g = p.cand_list[k];
+            ScanJob const job = p.jobs[find_job(p.jobs, p.njobs, g)];
+            int4 const rr = p.rowres[g];
+            v1 = rr.x; pos = rr.y; v2 = rr.z;
+            int const col = pos * kSub + sub;
+            if (col < job.c_n)
+                dot = dot_row<SIGNED>(p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes,
+                                      p.pool + (static_cast<int64_t>(job.c_row) + col) * kRowBytes);
+        }
+        unsigned const eq = (__ballot_sync(0xffffffffu, active && dot == v1) & hmask) >> hshift;
+        int const jl = 31 - __clz(eq);   // highest index wins ties (nearest_neighbor.cc:89); -1 if none
+        int const second = __reduce_max_sync(hmask, sub == jl ? INT_MIN / 2 : dot);
+        if (active && sub == 0) {
             if (eq == 0) {
-                atomicAdd(p.counters + 2, 1ull);  // the scan and the refine disagree: a bug
-                result = -1;
+                atomicAdd(p.counters + 2, 1ull);   // the scan and the refine disagree: a bug
+                p.oneway[g] = -1;
             } else {
-                int const s2 = max(b_v2, second);
-                result = passes_tests(ip_to_dist<SIGNED>(b_v1), ip_to_dist<SIGNED>(s2), p.sq_lowe, p.sq_dist)
-                             ? b_pos * kChunk + jl : -1;
+                int const s2 = max(v2, second);
+                p.oneway[g] = passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(s2), p.sq_lowe, p.sq_dist)
+                                  ? pos * kSub + jl : -1;
             }
         }
     }
-    if (valid && !slow) p.oneway[g] = result;
 }
 
 // ---------------------------------------------------------------- wrap emulation
-
-// The reference's inner product as its SSE2 loop computes it (nearest_neighbor.cc:75-84):
-// eight 16-bit lanes, lane k summing elements k, k+8, ... modulo 2^16, then added as int.
-template <bool SIGNED>
-__device__ __forceinline__ int wrapped_ip(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b) {
-    unsigned s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint2* pa = reinterpret_cast<const uint2*>(a);
-    const uint2* pb = reinterpret_cast<const uint2*>(b);
-    for (int t = 0; t < kRowBytes / 8; ++t) {
-        uint2 const x = __ldg(pa + t);
-        uint2 const y = __ldg(pb + t);
-        unsigned const xa[2] = {x.x, x.y};
-        unsigned const ya[2] = {y.x, y.y};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            unsigned const xb = (xa[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            unsigned const yb = (ya[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            if (SIGNED)
-                s[k] += static_cast<unsigned>(static_cast<int>(static_cast<signed char>(xb)) *
-                                              static_cast<int>(static_cast<signed char>(yb)));
-            else
-                s[k] += xb * yb;
-        }
-    }
-    int ip = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        ip += SIGNED ? static_cast<int>(static_cast<short>(s[k] & 0xffffu))
-                     : static_cast<int>(s[k] & 0xffffu);
-    return ip;
-}
 
 // One warp per flagged row: replays the reference's sequential scan including the
 // truncating 16-bit stores of best / second best (nearest_neighbor.cc:87-100).
@@ -289,17 +224,110 @@ __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
             int const lim = min(32, job.c_n - base);
             for (int l = 0; l < lim; ++l) {
                 int const x = __shfl_sync(0xffffffffu, ip, l);
-                if (x >= b2) {
-                    int const stored = SIGNED ? static_cast<int>(static_cast<short>(x & 0xffff))
-                                              : (x & 0xffff);
-                    if (x >= b1) { b2 = b1; b1 = stored; i1 = base + l; }
-                    else         { b2 = stored; }
-                }
+                ref_scan_step<SIGNED>(x, base + l, b1, b2, i1);
             }
         }
         if (lane == 0)
             p.oneway[g] = passes_tests(ip_to_dist<SIGNED>(b1), ip_to_dist<SIGNED>(b2), p.sq_lowe, p.sq_dist)
                               ? i1 : -1;
+    }
+}
+
+// ---------------------------------------------------------------- exact pass set-up
+
+// Single CTA.  Turns the per-job slow-row counts into the job list of the EXACT scan pass:
+// job j with cnt > 0 becomes {gathered rows [x0, x0 + cnt) vs the same candidate view}.
+// meta[0] = work items, meta[1] = jobs, meta[2] = gathered rows.
+__global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restrict__ jobs, int njobs,
+                                                          const int* __restrict__ slow_cnt,
+                                                          ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
+                                                          int* __restrict__ meta,
+                                                          unsigned long long* __restrict__ counters)
+{
+    __shared__ int wsum[3][32];
+    __shared__ int run[3];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3) run[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < njobs; base += blockDim.x) {
+        int const i = base + threadIdx.x;
+        int const cnt = i < njobs ? slow_cnt[i] : 0;
+        int const val[3] = {cnt, (cnt + kItemM - 1) / kItemM, cnt > 0 ? 1 : 0};
+        int incl[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            int x = val[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int const y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            incl[k] = x;
+            if (lane == 31) wsum[k][warp] = x;
+        }
+        __syncthreads();
+        int pre[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            int before = run[k];
+            for (int w = 0; w < warp; ++w) before += wsum[k][w];
+            pre[k] = before + incl[k] - val[k];   // exclusive prefix
+        }
+        if (cnt > 0) {
+            ScanJob x;
+            x.q_row = pre[0];
+            x.q_n = cnt;
+            x.c_row = jobs[i].c_row;
+            x.c_n = jobs[i].c_n;
+            x.out_row = pre[0];
+            x.item_start = pre[1];
+            x.c_maxnorm2 = 0;
+            xjobs[pre[2]] = x;
+            job_xrow[i] = pre[0];
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) run[k] = pre[k] + val[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ScanJob s;
+        s.q_row = 0; s.q_n = 0; s.c_row = 0; s.c_n = 0; s.c_maxnorm2 = 0;
+        s.out_row = run[0];
+        s.item_start = run[1];
+        xjobs[run[2]] = s;
+        meta[0] = run[1];
+        meta[1] = run[2];
+        meta[2] = run[0];
+        if (run[0] > 0) atomicAdd(counters + 3, static_cast<unsigned long long>(run[0]));
+    }
+}
+
+// Copies the slow rows' descriptors into the scratch query pool and records where their
+// result goes.  Grid-stride over jobs; 8 threads move one 128-byte row.
+__global__ void __launch_bounds__(256) exact_gather_kernel(const ScanJob* __restrict__ jobs, int njobs,
+                                                           const int* __restrict__ slow_cnt,
+                                                           const int* __restrict__ job_xrow,
+                                                           const int64_t* __restrict__ slow_list,
+                                                           const uint8_t* __restrict__ pool,
+                                                           uint8_t* __restrict__ xpool,
+                                                           int64_t* __restrict__ xrow_map)
+{
+    for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+        int const cnt = slow_cnt[j];
+        if (cnt == 0) continue;
+        ScanJob const job = jobs[j];
+        int const x0 = job_xrow[j];
+        for (int e = threadIdx.x; e < cnt * 8; e += blockDim.x) {
+            int const s = e >> 3, part = e & 7;
+            int64_t const g = slow_list[job.out_row + s];
+            int64_t const src_row = static_cast<int64_t>(job.q_row) + (g - job.out_row);
+            reinterpret_cast<uint4*>(xpool + (static_cast<int64_t>(x0) + s) * kRowBytes)[part] =
+                __ldg(reinterpret_cast<const uint4*>(pool + src_row * kRowBytes) + part);
+            if (part == 0) xrow_map[x0 + s] = g;
+        }
     }
 }
 

