@@ -299,11 +299,14 @@ def run_ours(args, config):
         h2d = sum(v.nbytes for v in host_views)
         e2e_times = []
         res = counts = None
+        me.init(vps)
+        dense_host = torch.empty(me.pairs_result_size(my_pairs) + 16, dtype=torch.int32).pin_memory().numpy()
         for it in range(2 + min(args.steps, 5)):
+            flush.fill_(1)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            me.init(vps)                                   # H2D of every view + pool assembly
-            res, counts = me.match_pairs(my_pairs)         # kernels + D2H of the dense results
+            me.init(vps)                                       # H2D of every view (pinned source)
+            res, counts = me.match_pairs(my_pairs, dense_host)  # kernels + D2H of the dense results
             torch.cuda.synchronize()
             if it >= 2:
                 e2e_times.append(time.perf_counter() - t0)

@@ -75,9 +75,12 @@ void osfm_match_destroy(osfm_matcher* m);
 const char* osfm_match_last_error(const osfm_matcher* m);
 
 /* ---- staging: replaces ExhaustiveMatching::init (exhaustive_matching.cc:56-112).
- * The caller may free its buffers as soon as set_view returns, exactly like
- * bundler::Matching::init frees the float descriptors right after
- * matcher->init (bundler_matching.cc:53-55). ------------------------------------ */
+ * begin / set_view x N / commit together are one init() call.  The host-to-device copies
+ * are asynchronous: the buffers handed to set_view must stay valid until
+ * osfm_match_commit() returns, after which the caller may free them -- exactly where
+ * bundler::Matching::init frees the float descriptors, right after matcher->init
+ * (bundler_matching.cc:53-55).  Views staged in increasing view_id order land directly in
+ * their final place in the pool (no second copy). ------------------------------------ */
 
 /* Declares the number of views (ViewportList::size()).  Resets the handle. */
 int osfm_match_begin(osfm_matcher* m, int num_views);

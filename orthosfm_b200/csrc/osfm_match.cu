@@ -45,7 +45,15 @@ struct KindPool {
     std::vector<int32_t> maxnorm2;  // signed kind only
     int32_t* d_norm2 = nullptr;     // signed kind only
     CUtensorMap tmap;
-    std::vector<uint8_t*> staged;   // per-view device buffers before commit
+    // Staging arena: views are appended in the order set_view is called.  When that is the
+    // view-id order (the normal case) the arena simply becomes the pool at commit; it is
+    // kept across begin() calls so that re-staging allocates nothing.
+    uint8_t* arena = nullptr;
+    int64_t arena_cap = 0;          // rows
+    int64_t arena_used = 0;         // rows
+    std::vector<int64_t> stage_off; // arena row of each staged view (-1: not staged)
+    int last_staged = -1;
+    bool in_order = true;
     float lowe = 0.8f, dist = FLT_MAX;
 };
 
@@ -158,14 +166,18 @@ int cuda_fail(osfm_matcher* m, cudaError_t e, const char* what) {
         if (r__ != OSFM_OK) return r__; \
     } while (0)
 
-void free_kind(KindPool& k) {
-    for (uint8_t* p : k.staged) if (p) cudaFree(p);
-    k.staged.clear();
-    if (k.owned && k.pool) cudaFree(k.pool);
+// Forgets the views (keeps the staging arena's memory unless release_arena).
+void reset_kind(KindPool& k, bool release_arena) {
+    if (k.owned && k.pool && k.pool != k.arena) cudaFree(k.pool);
     if (k.d_norm2) cudaFree(k.d_norm2);
     k.pool = nullptr; k.owned = false; k.d_norm2 = nullptr;
     k.rows = 0; k.off.clear(); k.n.clear(); k.maxnorm2.clear();
+    k.stage_off.clear(); k.arena_used = 0; k.last_staged = -1; k.in_order = true;
+    if (release_arena && k.arena) { cudaFree(k.arena); k.arena = nullptr; k.arena_cap = 0; }
 }
+
+// Makes room for `rows` more rows in the staging arena (contents are preserved).
+int arena_reserve(osfm_matcher* m, KindPool& k, int64_t rows);
 
 // 2-D tensor map over a pool of 128-byte rows; one TMA box = 128 rows (a query half or half
 // a candidate tile), SWIZZLE_128B so the tile lands in the layout tcgen05.mma reads.
@@ -205,6 +217,25 @@ int compute_norms(osfm_matcher* m, KindPool& k) {
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     cudaFree(d_view);
     cudaFree(d_max);
+    return OSFM_OK;
+}
+
+int arena_reserve(osfm_matcher* m, KindPool& k, int64_t rows) {
+    int64_t const need = k.arena_used + rows;
+    if (need <= k.arena_cap) return OSFM_OK;
+    int64_t const cap = std::max<int64_t>(need + need / 2, 4096);
+    uint8_t* fresh = nullptr;
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&fresh), static_cast<size_t>(cap) * kRowBytes));
+    if (k.arena) {
+        if (k.arena_used > 0)
+            CU_TRY(m, cudaMemcpyAsync(fresh, k.arena, static_cast<size_t>(k.arena_used) * kRowBytes,
+                                      cudaMemcpyDeviceToDevice, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        if (k.pool == k.arena) k.pool = fresh;
+        cudaFree(k.arena);
+    }
+    k.arena = fresh;
+    k.arena_cap = cap;
     return OSFM_OK;
 }
 
@@ -586,8 +617,8 @@ void osfm_match_destroy(osfm_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    free_kind(m->kind[0]);
-    free_kind(m->kind[1]);
+    reset_kind(m->kind[0], true);
+    reset_kind(m->kind[1], true);
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release(); m->d_slow.release();
     m->d_cand.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
@@ -614,10 +645,10 @@ int osfm_match_begin(osfm_matcher* m, int num_views) {
     CU_TRY(m, cudaSetDevice(m->device));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     for (int kd = 0; kd < 2; ++kd) {
-        free_kind(m->kind[kd]);
+        reset_kind(m->kind[kd], false);
         m->kind[kd].n.assign(num_views, 0);
         m->kind[kd].off.assign(num_views, 0);
-        m->kind[kd].staged.assign(num_views, nullptr);
+        m->kind[kd].stage_off.assign(num_views, -1);
     }
     m->num_views = num_views;
     m->began = true;
@@ -625,18 +656,21 @@ int osfm_match_begin(osfm_matcher* m, int num_views) {
     return OSFM_OK;
 }
 
+// Stages one view of one kind at the end of the arena.  All copies are asynchronous on the
+// handle's stream; the source must stay valid until osfm_match_commit() returns.
 static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n, int stride, bool is_float) {
     KindPool& k = m->kind[kd];
-    if (k.staged[view]) { cudaFree(k.staged[view]); k.staged[view] = nullptr; }
+    if (k.stage_off[view] >= 0 || view < k.last_staged) k.in_order = false;  // re-staged or out of order
     k.n[view] = 0;
+    k.stage_off[view] = -1;
     if (n <= 0) return OSFM_OK;
     if (!src) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null descriptor pointer with n = %d", n);
-    uint8_t* d = nullptr;
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), static_cast<size_t>(n) * kRowBytes));
-    k.staged[view] = d;
+    OS_TRY(arena_reserve(m, k, n));
+    uint8_t* const d = k.arena + static_cast<size_t>(k.arena_used) * kRowBytes;
     if (is_float) {
         if (stride < k.dim) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "stride %d < descriptor length %d", stride, k.dim);
         size_t const count = static_cast<size_t>(n - 1) * stride + k.dim;
+        if (count > m->d_ftmp.cap) CU_TRY(m, cudaStreamSynchronize(m->stream));  // still read by a kernel
         CU_TRY(m, m->d_ftmp.reserve(count));
         CU_TRY(m, cudaMemcpyAsync(m->d_ftmp.p, src, count * sizeof(float), cudaMemcpyHostToDevice, m->stream));
         int64_t const total = static_cast<int64_t>(n) * kRowBytes;
@@ -645,17 +679,17 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
         else             quantize_kernel<false><<<grid, 256, 0, m->stream>>>(m->d_ftmp.p, n, k.dim, stride, d);
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
-        CU_TRY(m, cudaStreamSynchronize(m->stream));  // caller may free src; d_ftmp is reused
     } else if (k.dim == kRowBytes) {
         CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
     } else {
         // 64-byte rows are zero-padded to the 128-byte pool pitch
         CU_TRY(m, cudaMemsetAsync(d, 0, static_cast<size_t>(n) * kRowBytes, m->stream));
         CU_TRY(m, cudaMemcpy2DAsync(d, kRowBytes, src, k.dim, k.dim, n, cudaMemcpyHostToDevice, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
     }
+    k.stage_off[view] = k.arena_used;
+    k.arena_used += n;
     k.n[view] = n;
+    k.last_staged = std::max(k.last_staged, view);
     return OSFM_OK;
 }
 
@@ -690,24 +724,39 @@ int osfm_match_commit(osfm_matcher* m) {
     CU_TRY(m, cudaSetDevice(m->device));
     for (int kd = 0; kd < 2; ++kd) {
         KindPool& k = m->kind[kd];
-        int64_t rows = 0;
-        for (int v = 0; v < m->num_views; ++v) { k.off[v] = rows; rows += k.n[v]; }
+        int64_t const rows = k.arena_used;
         if (rows + kPadRows > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "descriptor pool exceeds 2^31 rows");
         k.rows = rows;
-        size_t const bytes = static_cast<size_t>(rows + kPadRows) * kRowBytes;
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.pool), bytes));
-        k.owned = true;
+        if (k.in_order) {
+            // the arena already is the pool: view v sits where it was staged
+            OS_TRY(arena_reserve(m, k, kPadRows));
+            k.pool = k.arena;
+            k.owned = true;
+            int64_t next = 0;
+            for (int v = 0; v < m->num_views; ++v) {
+                k.off[v] = k.stage_off[v] >= 0 ? k.stage_off[v] : next;
+                next = k.off[v] + k.n[v];
+            }
+        } else {
+            size_t const bytes = static_cast<size_t>(rows + kPadRows) * kRowBytes;
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.pool), bytes));
+            k.owned = true;
+            int64_t next = 0;
+            for (int v = 0; v < m->num_views; ++v) {
+                k.off[v] = next;
+                if (k.n[v] > 0)
+                    CU_TRY(m, cudaMemcpyAsync(k.pool + static_cast<size_t>(next) * kRowBytes,
+                                              k.arena + static_cast<size_t>(k.stage_off[v]) * kRowBytes,
+                                              static_cast<size_t>(k.n[v]) * kRowBytes, cudaMemcpyDeviceToDevice, m->stream));
+                next += k.n[v];
+            }
+        }
         CU_TRY(m, cudaMemsetAsync(k.pool + static_cast<size_t>(rows) * kRowBytes, 0,
                                   static_cast<size_t>(kPadRows) * kRowBytes, m->stream));
-        for (int v = 0; v < m->num_views; ++v)
-            if (k.n[v] > 0)
-                CU_TRY(m, cudaMemcpyAsync(k.pool + static_cast<size_t>(k.off[v]) * kRowBytes, k.staged[v],
-                                          static_cast<size_t>(k.n[v]) * kRowBytes, cudaMemcpyDeviceToDevice, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
-        for (uint8_t*& p : k.staged) { if (p) cudaFree(p); p = nullptr; }
         OS_TRY(make_tmap(m, k));
         OS_TRY(compute_norms(m, k));
     }
+    CU_TRY(m, cudaStreamSynchronize(m->stream));  // from here on the caller may free its buffers
     m->committed = true;
     return OSFM_OK;
 }
@@ -729,14 +778,15 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
     int64_t prow[2] = {sift_pool_rows, surf_pool_rows};
     for (int kd = 0; kd < 2; ++kd) {
         KindPool& k = m->kind[kd];
-        free_kind(k);
+        reset_kind(k, false);
         k.n.assign(num_views, 0);
         k.off.assign(num_views, 0);
-        k.staged.assign(num_views, nullptr);
+        k.stage_off.assign(num_views, -1);
         if (!pools[kd]) {
-            // empty pool: still needs a valid (tiny) allocation for the tensor map
-            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.pool), static_cast<size_t>(kPadRows) * kRowBytes));
-            CU_TRY(m, cudaMemset(k.pool, 0, static_cast<size_t>(kPadRows) * kRowBytes));
+            // empty pool: the (possibly empty) arena provides the padding rows for the tensor map
+            OS_TRY(arena_reserve(m, k, kPadRows));
+            CU_TRY(m, cudaMemsetAsync(k.arena, 0, static_cast<size_t>(kPadRows) * kRowBytes, m->stream));
+            k.pool = k.arena;
             k.owned = true;
             k.rows = 0;
         } else {
@@ -757,6 +807,7 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
         OS_TRY(make_tmap(m, k));
         OS_TRY(compute_norms(m, k));
     }
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
     m->num_views = num_views;
     m->began = true;
     m->committed = true;

@@ -367,6 +367,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     tc_fence_after_sync();
                     int const qrow = job.q_row + rb * kItemM + h * kHalfM + row;
                     const uint8_t* const qptr = ex.qpool + static_cast<int64_t>(qrow) * kRowBytes;
+                    // rows past the end of the job hold whatever follows in the scratch pool;
+                    // they must not drag the warp into the update path
+                    bool const live = rb * kItemM + h * kHalfM + row < job.q_n;
                     for (int c = 0; c < kChunksPerTile; ++c) {
                         int32_t v[32];
                         tmem_ld_32x32b_x32(taddr0 + h * kBlockN + c * kChunk, v);
@@ -379,7 +382,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         if (ncols < kBlockN) mask_chunk(v, c * kChunk, ncols);
                         // b2 <= 65535, so a candidate whose lanes wrap (>= 65536) always triggers
                         int const cmax = max32(v);
-                        bool const trig = cmax >= b2[h];
+                        bool const trig = live && cmax >= b2[h];
                         if (__any_sync(0xffffffffu, trig)) {
                             int const col0 = t * kBlockN + c * kChunk;
                             if (__any_sync(0xffffffffu, trig && cmax >= 65536)) {

@@ -145,6 +145,7 @@ class ExhaustiveMatching:
             raise ValueError("Viewports must not be null")  # bundler_matching.cc:47-48
         self._check(self._L.osfm_match_begin(self._h, len(viewports)))
         self._sizes = []
+        keep = []   # staging copies are asynchronous: sources must outlive osfm_match_commit
         for v, vp in enumerate(viewports):
             fs = vp.features if hasattr(vp, "features") else vp
             sift = None if fs.sift_descriptors is None else np.asarray(fs.sift_descriptors)
@@ -161,8 +162,10 @@ class ExhaustiveMatching:
                 f = None if surf is None else np.ascontiguousarray(surf, np.float32).reshape(-1, 64)
                 self._check(self._L.osfm_match_set_view_f32(self._h, v, _ptr(s), n_sift, 128,
                                                             _ptr(f), n_surf, 64))
+            keep.append((s, f))
             self._sizes.append((n_sift, n_surf))
         self._check(self._L.osfm_match_commit(self._h))
+        del keep
 
     def init_device_pool(self, sift_pool, row_offsets, sizes) -> None:
         """Adopts a SIFT descriptor pool already resident on this GPU (a torch uint8
@@ -226,27 +229,39 @@ class ExhaustiveMatching:
         return Matching.Result(m12[:n1].copy(), m21[:n2].copy())
 
     # -- batched ------------------------------------------------------------------------------
-    def match_pairs(self, pairs) -> tuple:
+    def match_pairs(self, pairs, out: Optional[np.ndarray] = None) -> tuple:
         """All pairs in one pass.  Returns (results, n_consistent): a list of
         Matching.Result (views into one dense buffer) and an int32 array of
-        count_consistent_matches per pair."""
+        count_consistent_matches per pair.  ``out`` may be a caller-owned int32 buffer
+        (e.g. page-locked memory) that receives the dense results."""
         pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         npairs = pr.shape[0]
         i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         total = self._L.osfm_match_pairs_result_size(self._h, pr.ctypes.data_as(i32p), npairs)
         if total < 0:
             self._check(int(total))
-        dense = np.empty(max(int(total), 1), np.int32)
+        if out is not None:
+            if out.dtype != np.int32 or out.size < total or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a contiguous int32 buffer of at least {total} elements")
+            dense = out.reshape(-1)
+        else:
+            dense = np.empty(max(int(total), 1), np.int32)
         offsets = np.zeros(2 * npairs + 1, np.int64)
         counts = np.zeros(max(npairs, 1), np.int32)
         self._check(self._L.osfm_match_pairs(self._h, pr.ctypes.data_as(i32p), npairs,
                                              dense.ctypes.data_as(i32p), offsets.ctypes.data_as(i64p),
                                              counts.ctypes.data_as(i32p)))
-        out = []
-        for p in range(npairs):
-            a, b, c = offsets[2 * p], offsets[2 * p + 1], offsets[2 * p + 2]
-            out.append(Matching.Result(dense[a:b], dense[b:c]))
-        return out, counts[:npairs]
+        off = offsets.tolist()
+        out_list = [Matching.Result(dense[off[2 * p]:off[2 * p + 1]], dense[off[2 * p + 1]:off[2 * p + 2]])
+                    for p in range(npairs)]
+        return out_list, counts[:npairs]
+
+    def pairs_result_size(self, pairs) -> int:
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        total = self._L.osfm_match_pairs_result_size(self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), pr.shape[0])
+        if total < 0:
+            self._check(int(total))
+        return int(total)
 
     def match_pairs_compact(self, pairs, out_ij) -> np.ndarray:
         """Device-resident batched matching (SIFT): surviving (i, j) index pairs of every
