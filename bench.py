@@ -178,14 +178,15 @@ def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
         counts = np.array([int((impl.match_filtered("u8", views[a], views[b], 0.8)[0] >= 0).sum())
                            for a, b in sample])
     dt = time.perf_counter() - t
-    if dt < budget_s / 2 and kind == "reference" and len(pairs) >= 2 * npairs:
-        # one more batch for a steadier number
+    npairs_total = npairs
+    # keep going (fresh pairs of the same workload) until about 10 s of CPU work are in
+    nxt = npairs
+    while dt < budget_s / 2 and kind == "reference" and nxt + npairs <= len(pairs):
         t = time.perf_counter()
-        impl.match_pairs_u8(views, pairs[npairs:2 * npairs], 0.8)
-        dt2 = time.perf_counter() - t
-        dt, npairs_total = dt + dt2, 2 * npairs
-    else:
-        npairs_total = npairs
+        impl.match_pairs_u8(views, pairs[nxt:nxt + npairs], 0.8)
+        dt += time.perf_counter() - t
+        nxt += npairs
+        npairs_total += npairs
     value = npairs_total * n * n / dt
     return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{npairs_total} of the workload's pairs ({n} x {n}), {dt:.1f} s; "

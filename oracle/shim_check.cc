@@ -1,0 +1,179 @@
+/*
+ * shim_check.cc -- drop-in proof.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiled (oracle/Makefile, target ref) against the reference's own headers and linked
+ * with the reference's own matcher objects AND libosfm_match.so.  It drives both
+ * sfm::ExhaustiveMatching (the reference, CPU) and sfm::GpuExhaustiveMatching (the C++
+ * binding over the C ABI, orthosfm_b200/csrc/gpu_exhaustive_matching.h) through the same
+ * sfm::MatchingBase pointer, on the same bundler::ViewportList, the way
+ * bundler::Matching does (src/mve/sfm/bundler_matching.cc:45-56, 139-162), and compares
+ * every Matching::Result element for element.
+ *
+ * The binary lands in oracle/_ref/ (git-ignored, travels to the GPU box);
+ * tests/test_gpu_parity.py::test_reference_side_binding runs it.
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include "sfm/bundler_common.h"
+#include "sfm/exhaustive_matching.h"
+#include "sfm/matching_base.h"
+
+#include "gpu_exhaustive_matching.h"
+
+namespace
+{
+    void
+    fill_views (sfm::bundler::ViewportList* viewports, std::vector<int> const& n_sift,
+        std::vector<int> const& n_surf, unsigned seed)
+    {
+        std::mt19937 rng(seed);
+        std::normal_distribution<float> gauss(0.0f, 1.0f);
+        /* shared "scene" descriptors so that some pairs really match */
+        int const pool = 400;
+        std::vector<std::vector<float>> sift_pool(pool, std::vector<float>(128));
+        std::vector<std::vector<float>> surf_pool(pool, std::vector<float>(64));
+        auto normalise = [] (std::vector<float>& v, bool clampit)
+        {
+            float n = 0.0f;
+            for (float x : v) n += x * x;
+            n = std::sqrt(n);
+            for (float& x : v) x /= n;
+            if (!clampit) return;
+            for (float& x : v) x = std::min(x, 0.2f);
+            n = 0.0f;
+            for (float x : v) n += x * x;
+            n = std::sqrt(n);
+            for (float& x : v) x /= n;
+        };
+        for (int i = 0; i < pool; ++i)
+        {
+            for (float& x : sift_pool[i]) x = std::fabs(gauss(rng));
+            normalise(sift_pool[i], true);
+            for (float& x : surf_pool[i]) x = gauss(rng);
+            normalise(surf_pool[i], false);
+        }
+        viewports->resize(n_sift.size());
+        for (std::size_t v = 0; v < n_sift.size(); ++v)
+        {
+            sfm::FeatureSet& fs = (*viewports)[v].features;
+            fs.sift_descriptors.resize(n_sift[v]);
+            for (int i = 0; i < n_sift[v]; ++i)
+            {
+                std::vector<float> d(128);
+                if (rng() % 3 == 0)
+                {
+                    d = sift_pool[rng() % pool];
+                    for (float& x : d) x = std::max(0.0f, x + 0.004f * gauss(rng));
+                }
+                else
+                    for (float& x : d) x = std::fabs(gauss(rng));
+                normalise(d, true);
+                sfm::Sift::Descriptor& out = fs.sift_descriptors[i];
+                out.x = out.y = out.scale = out.orientation = 0.0f;
+                for (int k = 0; k < 128; ++k) out.data[k] = d[k];
+            }
+            fs.surf_descriptors.resize(n_surf[v]);
+            for (int i = 0; i < n_surf[v]; ++i)
+            {
+                std::vector<float> d(64);
+                if (rng() % 3 == 0)
+                {
+                    d = surf_pool[rng() % pool];
+                    for (float& x : d) x += 0.01f * gauss(rng);
+                }
+                else
+                    for (float& x : d) x = gauss(rng);
+                normalise(d, false);
+                sfm::Surf::Descriptor& out = fs.surf_descriptors[i];
+                out.x = out.y = out.scale = out.orientation = 0.0f;
+                for (int k = 0; k < 64; ++k) out.data[k] = d[k];
+            }
+        }
+    }
+}
+
+int
+main (void)
+{
+    std::vector<int> const n_sift = { 900, 1300, 0, 257, 640 };
+    std::vector<int> const n_surf = { 300, 0, 410, 129, 0 };
+    sfm::bundler::ViewportList viewports;
+    fill_views(&viewports, n_sift, n_surf, 1234u);
+
+    std::unique_ptr<sfm::MatchingBase> ref(new sfm::ExhaustiveMatching());
+    std::unique_ptr<sfm::MatchingBase> gpu;
+    try
+    {
+        gpu.reset(new sfm::GpuExhaustiveMatching(0));
+        ref->init(&viewports);
+        gpu->init(&viewports);
+    }
+    catch (std::exception const& e)
+    {
+        std::printf("SHIM_CHECK ERROR %s\n", e.what());
+        return 2;
+    }
+    /* bundler::Matching::init frees the descriptors here (bundler_matching.cc:53-55) */
+    for (std::size_t i = 0; i < viewports.size(); ++i)
+    {
+        /* same effect as FeatureSet::clear_descriptors() (not linked here: feature_set.cc
+         * would pull in the SURF extractor) */
+        sfm::Sift::Descriptors().swap(viewports[i].features.sift_descriptors);
+        sfm::Surf::Descriptors().swap(viewports[i].features.surf_descriptors);
+    }
+
+    int bad = 0, pairs = 0;
+    long consistent = 0;
+    for (int v1 = 0; v1 < (int)viewports.size(); ++v1)
+        for (int v2 = 0; v2 < (int)viewports.size(); ++v2)
+        {
+            if (v1 == v2) continue;
+            sfm::Matching::Result a, b;
+            ref->pairwise_match(v1, v2, &a);
+            gpu->pairwise_match(v1, v2, &b);
+            bool const same = a.matches_1_2 == b.matches_1_2 && a.matches_2_1 == b.matches_2_1;
+            int const la = ref->pairwise_match_lowres(v1, v2, 200);
+            int const lb = gpu->pairwise_match_lowres(v1, v2, 200);
+            consistent += sfm::Matching::count_consistent_matches(a);
+            if (!same || la != lb)
+            {
+                ++bad;
+                std::printf("MISMATCH pair (%d,%d): sizes %zu/%zu vs %zu/%zu lowres %d vs %d\n", v1, v2,
+                    a.matches_1_2.size(), a.matches_2_1.size(), b.matches_1_2.size(), b.matches_2_1.size(), la, lb);
+            }
+            ++pairs;
+        }
+
+    /* the batched entry point must give the same as the per-pair one */
+    std::vector<std::pair<int, int>> list;
+    for (int v1 = 1; v1 < (int)viewports.size(); ++v1)
+        for (int v2 = 0; v2 < v1; ++v2)
+            list.push_back(std::make_pair(v1, v2));
+    std::vector<sfm::Matching::Result> all;
+    static_cast<sfm::GpuExhaustiveMatching*>(gpu.get())->pairwise_match_all(list, &all);
+    for (std::size_t p = 0; p < list.size(); ++p)
+    {
+        sfm::Matching::Result a;
+        ref->pairwise_match(list[p].first, list[p].second, &a);
+        if (!(a.matches_1_2 == all[p].matches_1_2 && a.matches_2_1 == all[p].matches_2_1))
+        {
+            ++bad;
+            std::printf("MISMATCH batched pair (%d,%d)\n", list[p].first, list[p].second);
+        }
+    }
+
+    /* error convention: exceptions, like the rest of MVE */
+    bool threw = false;
+    try { sfm::Matching::Result r; gpu->pairwise_match(0, 99, &r); }
+    catch (std::invalid_argument const&) { threw = true; }
+    if (!threw) { ++bad; std::printf("MISMATCH: bad view id did not throw std::invalid_argument\n"); }
+
+    std::printf("SHIM_CHECK %s pairs=%d consistent=%ld mismatches=%d\n", bad == 0 ? "PASS" : "FAIL",
+        pairs, consistent, bad);
+    return bad == 0 ? 0 : 1;
+}

@@ -292,3 +292,21 @@ def test_many_pairs_one_launch(ora):
         o12, o21 = ora.match_filtered("u8", views[v1], views[v2], 0.8)
         assert np.array_equal(results[p].matches_1_2, o12), (v1, v2)
         assert np.array_equal(results[p].matches_2_1, o21), (v1, v2)
+
+
+# ------------------------------------------------------------------ the reference-side binding
+
+def test_reference_side_binding():
+    """oracle/_ref/shim_check is the C++ subclass of sfm::MatchingBase
+    (orthosfm_b200/csrc/gpu_exhaustive_matching.h) compiled against the reference's own
+    headers and run, in one process, against the reference's own sfm::ExhaustiveMatching on
+    the same bundler::ViewportList (float SIFT + SURF descriptors, views without SIFT or
+    without SURF included).  Built only where /root/reference exists; the binary travels."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "shim_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_check not built (needs /root/reference)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SHIM_CHECK PASS" in r.stdout, r.stdout
