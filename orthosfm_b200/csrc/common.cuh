@@ -98,23 +98,27 @@ __device__ __forceinline__ int dot_row(const uint8_t* __restrict__ a, const uint
 // eight 16-bit lanes, lane k summing elements k, k+8, ... modulo 2^16, then added as int.
 template <bool SIGNED>
 __device__ __noinline__ int wrapped_ip(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b) {
-    unsigned s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint2* pa = reinterpret_cast<const uint2*>(a);
-    const uint2* pb = reinterpret_cast<const uint2*>(b);
-    for (int t = 0; t < kRowBytes / 8; ++t) {
-        uint2 const x = __ldg(pa + t);
-        uint2 const y = __ldg(pb + t);
-        unsigned const xa[2] = {x.x, x.y};
-        unsigned const ya[2] = {y.x, y.y};
+    // all 16 loads are issued before the first use: one memory latency, not sixteen
+    uint4 x[kRowBytes / 16], y[kRowBytes / 16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            unsigned const xb = (xa[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            unsigned const yb = (ya[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    for (int i = 0; i < kRowBytes / 16; ++i) {
+        x[i] = __ldg(reinterpret_cast<const uint4*>(a) + i);
+        y[i] = __ldg(reinterpret_cast<const uint4*>(b) + i);
+    }
+    unsigned s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < kRowBytes / 16; ++i) {
+        unsigned const xa[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        unsigned const ya[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {   // byte e of this 16-byte group belongs to lane e % 8
+            unsigned const xb = (xa[e >> 2] >> (8 * (e & 3))) & 0xffu;
+            unsigned const yb = (ya[e >> 2] >> (8 * (e & 3))) & 0xffu;
             if (SIGNED)
-                s[k] += static_cast<unsigned>(static_cast<int>(static_cast<signed char>(xb)) *
-                                              static_cast<int>(static_cast<signed char>(yb)));
+                s[e & 7] += static_cast<unsigned>(static_cast<int>(static_cast<signed char>(xb)) *
+                                                  static_cast<int>(static_cast<signed char>(yb)));
             else
-                s[k] += xb * yb;
+                s[e & 7] += xb * yb;
         }
     }
     int ip = 0;

@@ -118,6 +118,7 @@ struct osfm_matcher {
     // scratch of the EXACT pass (rows whose best similarity reached 2^16)
     DevBuf<int> d_slow_cnt;
     DevBuf<int> d_job_xrow;
+    DevBuf<int32_t> d_seg_first;
     DevBuf<ScanJob> d_xjobs;
     DevBuf<uint8_t> d_xpool;
     DevBuf<int64_t> d_xrow_map;
@@ -256,9 +257,9 @@ cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int
 // Second pass over the rows finalize_kernel<false> flagged (unsigned kind): plan, gather,
 // and the EXACT variant of the scan kernel.  Everything is sized on the device; the host
 // never learns how many rows there were until it reads the counters.
-int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int64_t rows, const PostParams& pp) {
+int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp) {
     CU_TRY(m, m->d_job_xrow.reserve(static_cast<size_t>(njobs)));
-    CU_TRY(m, m->d_xjobs.reserve(static_cast<size_t>(njobs) + 1));
+    CU_TRY(m, m->d_xjobs.reserve(static_cast<size_t>(nseg) + 1));
     CU_TRY(m, m->d_xrow_map.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_xpool.reserve(static_cast<size_t>(rows + kPadRows) * kRowBytes));
     if (m->tmap_x_for != m->d_xpool.p || m->tmap_x_rows != m->d_xpool.cap) {
@@ -266,8 +267,8 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int64_t row
         m->tmap_x_for = m->d_xpool.p;
         m->tmap_x_rows = m->d_xpool.cap;
     }
-    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_slow_cnt.p, m->d_xjobs.p,
-                                                 m->d_job_xrow.p, m->d_xmeta, m->d_counters);
+    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, m->d_slow_cnt.p,
+                                                 m->d_xjobs.p, m->d_job_xrow.p, m->d_xmeta, m->d_counters);
     CU_TRY(m, cudaGetLastError());
     exact_gather_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_slow_cnt.p,
                                                               m->d_job_xrow.p, m->d_slow.p, k.pool,
@@ -299,10 +300,23 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     out_row.assign(specs.size(), -1);
     std::vector<ScanJob> jobs;
     jobs.reserve(specs.size() + 1);
+    // Jobs are ordered by candidate view: concurrently running work items then stream the
+    // same candidate tiles (L2 locality), and the EXACT pass can merge the slow rows of all
+    // jobs that share a candidate view into full 256-row items.
+    std::vector<uint32_t> order(specs.size());
+    for (size_t i = 0; i < specs.size(); ++i) order[i] = static_cast<uint32_t>(i);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (specs[a].c_view != specs[b].c_view) return specs[a].c_view < specs[b].c_view;
+        return specs[a].c_n < specs[b].c_n;
+    });
+    std::vector<int32_t> seg_first;   // first job of every (candidate view, c_n) segment
     int64_t rows = 0, items = 0;
-    for (size_t i = 0; i < specs.size(); ++i) {
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+        size_t const i = order[oi];
         JobSpec const& s = specs[i];
         if (s.q_n <= 0 || s.c_n <= 0) continue;
+        if (jobs.empty() || jobs.back().c_row != static_cast<int32_t>(k.off[s.c_view]) || jobs.back().c_n != s.c_n)
+            seg_first.push_back(static_cast<int32_t>(jobs.size()));
         ScanJob j;
         j.q_row = static_cast<int32_t>(k.off[s.q_view]);
         j.q_n = s.q_n;
@@ -319,6 +333,8 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     if (jobs.empty()) return OSFM_OK;
     if (items > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many work items in one batch");
     int const njobs = static_cast<int>(jobs.size());
+    int const nseg = static_cast<int>(seg_first.size());
+    seg_first.push_back(njobs);
     ScanJob sentinel;
     memset(&sentinel, 0, sizeof sentinel);
     sentinel.out_row = rows;
@@ -332,6 +348,9 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     CU_TRY(m, m->d_cand.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_slow_cnt.reserve(static_cast<size_t>(njobs)));
     CU_TRY(m, cudaMemsetAsync(m->d_slow_cnt.p, 0, sizeof(int) * njobs, m->stream));
+    CU_TRY(m, m->d_seg_first.reserve(seg_first.size()));
+    CU_TRY(m, cudaMemcpyAsync(m->d_seg_first.p, seg_first.data(), sizeof(int32_t) * seg_first.size(),
+                              cudaMemcpyHostToDevice, m->stream));
     CU_TRY(m, cudaMemcpyAsync(m->d_jobs.p, jobs.data(), sizeof(ScanJob) * jobs.size(),
                               cudaMemcpyHostToDevice, m->stream));
     // pageable source: the copy is staged before the call returns, `jobs` may die.
@@ -384,7 +403,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
         m->stats.kernel_launches++;
     } else {
-        OS_TRY(launch_exact_pass(m, k, njobs, rows, pp));
+        OS_TRY(launch_exact_pass(m, k, njobs, nseg, rows, pp));
     }
 
     // Scan time of this launch; read after the caller's next synchronisation.
@@ -623,7 +642,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_cand.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
     m->d_ftmp.release();
-    m->d_slow_cnt.release(); m->d_job_xrow.release(); m->d_xjobs.release(); m->d_xpool.release();
+    m->d_slow_cnt.release(); m->d_job_xrow.release(); m->d_seg_first.release(); m->d_xjobs.release(); m->d_xpool.release();
     m->d_xrow_map.release();
     if (m->d_xmeta) cudaFree(m->d_xmeta);
     if (m->d_counters) cudaFree(m->d_counters);

@@ -84,7 +84,7 @@ struct PostParams {
     const ScanJob* jobs;        // njobs + 1 entries (sentinel: out_row = total_rows)
     int njobs;
     int64_t total_rows;
-    const int4* rowres;         // (v1, pos, v2 lower bound) per job row
+    const int4* rowres;         // (v1, pos, v2 lower bound, job index) per job row
     int32_t* oneway;            // out: index of the match in the candidate view or -1
     float sq_lowe;              // lowe_ratio_threshold^2   (matching.h:126)
     float sq_dist;              // distance_threshold^2     (matching.h:127)
@@ -110,10 +110,10 @@ __global__ void __launch_bounds__(256) classify_kernel(PostParams p)
     int const lane = threadIdx.x & 31;
     bool cand = false;
     if (g < p.total_rows) {
-        int const ji = find_job(p.jobs, p.njobs, g);
-        ScanJob const job = p.jobs[ji];
         int4 const rr = p.rowres[g];
         int const v1 = rr.x, v2 = rr.z;
+        int const ji = rr.w;                 // the scan kernel recorded the row's job
+        ScanJob const job = p.jobs[ji];
         int result = -1;
         bool slow;
         if (SIGNED) {
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(256) refine_kernel(PostParams p)
         int64_t g = 0;
         if (active) {
             g = p.cand_list[k];
-            ScanJob const job = p.jobs[find_job(p.jobs, p.njobs, g)];
             int4 const rr = p.rowres[g];
+            ScanJob const job = p.jobs[rr.w];
             v1 = rr.x; pos = rr.y; v2 = rr.z;
             int const col = pos * kSub + sub;
             if (col < job.c_n)
@@ -235,10 +235,13 @@ __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
 
 // ---------------------------------------------------------------- exact pass set-up
 
-// Single CTA.  Turns the per-job slow-row counts into the job list of the EXACT scan pass:
-// job j with cnt > 0 becomes {gathered rows [x0, x0 + cnt) vs the same candidate view}.
-// meta[0] = work items, meta[1] = jobs, meta[2] = gathered rows.
-__global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restrict__ jobs, int njobs,
+// Single CTA.  Turns the per-job slow-row counts into the job list of the EXACT scan pass.
+// Jobs arrive ordered by candidate view; a *segment* is a run of jobs with the same
+// candidate set, and the slow rows of all its jobs are gathered back to back so that they
+// form full 256-row work items against that candidate view.  One thread per segment.
+// meta[0] = work items, meta[1] = exact jobs, meta[2] = gathered rows.
+__global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restrict__ jobs,
+                                                          const int32_t* __restrict__ seg_first, int nseg,
                                                           const int* __restrict__ slow_cnt,
                                                           ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
                                                           int* __restrict__ meta,
@@ -249,9 +252,11 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 3) run[threadIdx.x] = 0;
     __syncthreads();
-    for (int base = 0; base < njobs; base += blockDim.x) {
-        int const i = base + threadIdx.x;
-        int const cnt = i < njobs ? slow_cnt[i] : 0;
+    for (int base = 0; base < nseg; base += blockDim.x) {
+        int const sgi = base + threadIdx.x;
+        int cnt = 0;
+        if (sgi < nseg)
+            for (int j = seg_first[sgi]; j < seg_first[sgi + 1]; ++j) cnt += slow_cnt[j];
         int const val[3] = {cnt, (cnt + kItemM - 1) / kItemM, cnt > 0 ? 1 : 0};
         int incl[3];
 #pragma unroll
@@ -274,16 +279,21 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
             pre[k] = before + incl[k] - val[k];   // exclusive prefix
         }
         if (cnt > 0) {
+            ScanJob const first = jobs[seg_first[sgi]];
             ScanJob x;
             x.q_row = pre[0];
             x.q_n = cnt;
-            x.c_row = jobs[i].c_row;
-            x.c_n = jobs[i].c_n;
+            x.c_row = first.c_row;
+            x.c_n = first.c_n;
             x.out_row = pre[0];
             x.item_start = pre[1];
             x.c_maxnorm2 = 0;
             xjobs[pre[2]] = x;
-            job_xrow[i] = pre[0];
+            int at = pre[0];
+            for (int j = seg_first[sgi]; j < seg_first[sgi + 1]; ++j) {
+                job_xrow[j] = at;
+                at += slow_cnt[j];
+            }
         }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) {

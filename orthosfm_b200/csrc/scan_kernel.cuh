@@ -166,7 +166,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     int const warp = threadIdx.x >> 5;
     int const lane = threadIdx.x & 31;
     int const total_items = EXACT ? *ex.total_items_dev : total_items_host;
-    // In the EXACT pass only column group 0 works (it scans whole rows in order).
+    // In the EXACT pass one group of four warps per query half scans whole rows in order.
     constexpr uint32_t kAccEmptyCount = EXACT ? 4 : kEpilogueWarps;
 
     if (threadIdx.x == 0) {
@@ -336,94 +336,89 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         st[h].merge(o.x, o.y, o.z);
                     }
                     int64_t const r = static_cast<int64_t>(rb) * kItemM + h * kHalfM + row;
-                    if (r < job.q_n) rowres[job.out_row + r] = make_int4(st[h].v1, st[h].pos, st[h].v2, 0);
+                    if (r < job.q_n) rowres[job.out_row + r] = make_int4(st[h].v1, st[h].pos, st[h].v2, j);
                 }
             }
             named_barrier_sync(2, kEpilogueWarps * 32);
         }
-    } else if ((warp >> 2) == 0) {
-        // ===================== EXACT epilogue: 4 warps replay the reference's scan ==========
+    } else if ((warp >> 2) < 2) {
+        // ===================== EXACT epilogue: 2 x 4 warps replay the reference's scan ======
+        int const my_h = warp >> 2;          // the query half this group owns
         int const quad = warp & 3;
         int const row = quad * 32 + lane;
-        uint32_t const taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        uint32_t const taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + my_h * kBlockN;
 
         int j = 0;
-        uint32_t hcnt[2] = {0, 0};
+        uint32_t hcnt = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             while (it >= jobs[j + 1].item_start) ++j;
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
             int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
+            if (my_h >= nh) continue;
             int const ntiles = (job.c_n + kBlockN - 1) / kBlockN;
+            int const r_in_job = rb * kItemM + my_h * kHalfM + row;
+            // rows past the end of the job hold whatever follows in the scratch pool; they
+            // must not drag the warp into the update path
+            bool const live = r_in_job < job.q_n;
+            const uint8_t* const qptr = ex.qpool + (static_cast<int64_t>(job.q_row) + r_in_job) * kRowBytes;
+            const uint8_t* const cbase = ex.cpool + static_cast<int64_t>(job.c_row) * kRowBytes;
 
-            int b1[2] = {0, 0}, b2[2] = {0, 0}, i1[2] = {0, 0};   // nearest_neighbor.cc:246-249
+            int b1 = 0, b2 = 0, i1 = 0;   // nearest_neighbor.cc:246-249
             for (int t = 0; t < ntiles; ++t) {
                 int const ncols = job.c_n - t * kBlockN;
+                mbar_wait(acc_full(my_h), hcnt & 1, kWaitAccFull, hcnt);
+                ++hcnt;
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int c = 0; c < kChunksPerTile; ++c) {
+                    int32_t v[32];
+                    tmem_ld_32x32b_x32(taddr0 + c * kChunk, v);
+                    tmem_ld_wait_regs(v);
+                    if (c == kChunksPerTile - 1) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(my_h));
+                    }
+                    if (ncols < kBlockN) mask_chunk(v, c * kChunk, ncols);
+                    // b2 <= 65535, so a candidate whose lanes wrap (>= 65536) always triggers
+                    int const cmax = max32(v);
+                    bool const trig = live && cmax >= b2;
+                    if (!__any_sync(0xffffffffu, trig)) continue;
+                    int const col0 = t * kBlockN + c * kChunk;
+                    if (__any_sync(0xffffffffu, trig && cmax >= 65536)) {
+                        // rare: some candidate needs the wrapped-lane emulation
+                        if (trig) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h >= nh) break;
-                    mbar_wait(acc_full(h), hcnt[h] & 1, kWaitAccFull, hcnt[h]);
-                    ++hcnt[h];
-                    tc_fence_after_sync();
-                    int const qrow = job.q_row + rb * kItemM + h * kHalfM + row;
-                    const uint8_t* const qptr = ex.qpool + static_cast<int64_t>(qrow) * kRowBytes;
-                    // rows past the end of the job hold whatever follows in the scratch pool;
-                    // they must not drag the warp into the update path
-                    bool const live = rb * kItemM + h * kHalfM + row < job.q_n;
-                    for (int c = 0; c < kChunksPerTile; ++c) {
-                        int32_t v[32];
-                        tmem_ld_32x32b_x32(taddr0 + h * kBlockN + c * kChunk, v);
-                        tmem_ld_wait_regs(v);
-                        if (c == kChunksPerTile - 1) {
-                            tc_fence_before_sync();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(acc_empty(h));
-                        }
-                        if (ncols < kBlockN) mask_chunk(v, c * kChunk, ncols);
-                        // b2 <= 65535, so a candidate whose lanes wrap (>= 65536) always triggers
-                        int const cmax = max32(v);
-                        bool const trig = live && cmax >= b2[h];
-                        if (__any_sync(0xffffffffu, trig)) {
-                            int const col0 = t * kBlockN + c * kChunk;
-                            if (__any_sync(0xffffffffu, trig && cmax >= 65536)) {
-                                // rare: some candidate needs the wrapped-lane emulation
-                                if (trig) {
-#pragma unroll
-                                    for (int q = 0; q < 32; ++q) {
-                                        int x = v[q];
-                                        if (x >= b2[h]) {   // wrapping only lowers x: no update otherwise
-                                            if (x >= 65536)
-                                                x = wrapped_ip<false>(qptr, ex.cpool + (static_cast<int64_t>(job.c_row) + col0 + q) * kRowBytes);
-                                            ref_scan_step<false>(x, col0 + q, b1[h], b2[h], i1[h]);
-                                        }
-                                    }
+                            for (int q = 0; q < 32; ++q) {
+                                int x = v[q];
+                                if (x >= b2) {   // wrapping only lowers x: no update otherwise
+                                    if (x >= 65536)
+                                        x = wrapped_ip<false>(qptr, cbase + static_cast<int64_t>(col0 + q) * kRowBytes);
+                                    ref_scan_step<false>(x, col0 + q, b1, b2, i1);
                                 }
-                            } else {
-                                // common: plain sequential top-2 with the reference's tie rule,
-                                // branch-free (values < 2^16 are stored untruncated)
-                                int s1 = b1[h], s2 = b2[h], si = i1[h];
-#pragma unroll
-                                for (int q = 0; q < 32; ++q) {
-                                    int const x = v[q];
-                                    bool const ge2 = x >= s2;
-                                    bool const ge1 = ge2 && x >= s1;
-                                    s2 = ge1 ? s1 : (ge2 ? x : s2);
-                                    s1 = ge1 ? x : s1;
-                                    si = ge1 ? col0 + q : si;
-                                }
-                                if (trig) { b1[h] = s1; b2[h] = s2; i1[h] = si; }
                             }
                         }
+                    } else {
+                        // common: plain sequential top-2 with the reference's tie rule,
+                        // branch-free (values < 2^16 are stored untruncated)
+                        int s1 = b1, s2 = b2, si = i1;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            int const x = v[q];
+                            bool const ge2 = x >= s2;
+                            bool const ge1 = ge2 && x >= s1;
+                            s2 = ge1 ? s1 : (ge2 ? x : s2);
+                            s1 = ge1 ? x : s1;
+                            si = ge1 ? col0 + q : si;
+                        }
+                        if (trig) { b1 = s1; b2 = s2; i1 = si; }
                     }
                 }
             }
-            for (int h = 0; h < nh; ++h) {
-                int64_t const r = static_cast<int64_t>(rb) * kItemM + h * kHalfM + row;
-                if (r < job.q_n) {
-                    bool const ok = passes_tests(ip_to_dist<false>(b1[h]), ip_to_dist<false>(b2[h]),
-                                                 ex.sq_lowe, ex.sq_dist);
-                    ex.oneway[ex.xrow_map[job.out_row + r]] = ok ? i1[h] : -1;
-                }
+            if (live) {
+                bool const ok = passes_tests(ip_to_dist<false>(b1), ip_to_dist<false>(b2), ex.sq_lowe, ex.sq_dist);
+                ex.oneway[ex.xrow_map[job.out_row + r_in_job]] = ok ? i1 : -1;
             }
         }
     }
