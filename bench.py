@@ -118,7 +118,7 @@ def run_reference_arm(args, config):
         return
     import oracle
     ref = oracle.Reference()
-    cores = ref.num_threads()
+    cores = ref.use_all_cores()
     views = make_views_numpy(min(config["views"], 12), N_DESC)
     from orthosfm_b200 import synth
     all_pairs = synth.all_pairs(len(views))
@@ -167,7 +167,7 @@ def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
         impl, kind = oracle.Reference(), "reference"
     else:
         impl, kind = oracle.Oracle(), "port"
-    cores = impl.num_threads()
+    cores = impl.use_all_cores()
     npairs = max(1, min(len(pairs), cores))
     sample = pairs[:npairs]
     n = views[0].shape[0]
@@ -231,7 +231,8 @@ def run_ours(args, config):
     torch.cuda.synchronize()
     broadcast_ms = 1e3 * (time.perf_counter() - t_b)
 
-    owned = osd.partition_pairs(pairs, sizes, world)[rank]
+    all_owned = osd.partition_pairs(pairs, sizes, world)
+    owned = all_owned[rank]
     my_pairs = pairs[owned]
     my_cmp = int(len(my_pairs)) * n * n
 
@@ -248,7 +249,8 @@ def run_ours(args, config):
 
     def step():
         loff = m.match_pairs_compact(my_pairs, out_ij)
-        gathered = osd.gather_match_lists(out_ij, loff, owned, npairs, dst=0) if world > 1 else (out_ij, loff)
+        gathered = osd.gather_match_lists(out_ij, loff, owned, npairs, dst=0, all_owned=all_owned) \
+            if world > 1 else (out_ij, loff)
         return loff, gathered
 
     for _ in range(max(args.warmup, 3)):

@@ -86,6 +86,18 @@ class _Impl:
     def num_threads(self) -> int:
         return int(self._f("num_threads")())
 
+    def set_num_threads(self, n: int) -> None:
+        self._f("set_num_threads")(C.c_int(int(n)))
+
+    def use_all_cores(self) -> int:
+        """torchrun exports OMP_NUM_THREADS=1; use every core this process may run on."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        self.set_num_threads(n)
+        return self.num_threads()
+
     # -- NearestNeighbor<T>::find ------------------------------------
     def nn(self, kind: str, query, elements, sse3_order: bool = True):
         npdt, ct, _ = _KIND[kind]

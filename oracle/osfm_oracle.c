@@ -481,6 +481,16 @@ osfm_oracle_pairwise_match_lowres (
     return 0;
 }
 
+void
+osfm_oracle_set_num_threads (int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int
 osfm_oracle_num_threads (void)
 {

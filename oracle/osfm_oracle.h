@@ -104,6 +104,7 @@ int osfm_oracle_pairwise_match_lowres(
 
 /* Number of OpenMP threads the oracle will use (1 if built without OpenMP). */
 int osfm_oracle_num_threads(void);
+void osfm_oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,17 @@ struct osfm_ref_nn_result
     int index_2nd_best;
 };
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use the cores it is given */
+void
+osfm_ref_set_num_threads (int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int
 osfm_ref_num_threads (void)
 {

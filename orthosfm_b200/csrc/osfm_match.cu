@@ -110,6 +110,7 @@ struct osfm_matcher {
     DevBuf<int32_t> d_oneway;
     DevBuf<int64_t> d_slow;
     DevBuf<int64_t> d_cand;
+    DevBuf<int4> d_big;
     DevBuf<PairPart> d_parts;
     DevBuf<int32_t> d_dense;
     DevBuf<int32_t> d_counts;
@@ -283,11 +284,29 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, i
     ex.total_items_dev = m->d_xmeta;
     ex.sq_lowe = pp.sq_lowe;
     ex.sq_dist = pp.sq_dist;
+    ex.replay_list = m->d_cand.p;          // free again: refine_kernel precedes this pass
+    ex.replay_count = m->d_counters + 8;
+    CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
+    ex.big_list = m->d_big.p;
+    ex.big_count = m->d_counters + 12;
+    CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
+    CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, 0, 0);
     scan_kernel<0, true><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
         m->tmap_x, k.tmap, m->d_xjobs.p, 0, nullptr, idesc, nullptr, 0, ex);
     CU_TRY(m, cudaGetLastError());
-    m->stats.kernel_launches += 3;
+    // certify the big candidates; rows that fail (a 16-bit lane really wrapped) get the
+    // warp-per-row replay.  counters[8] is the replay list length; counters[11] absorbs the
+    // replay kernel's (already counted) total.
+    verify_big_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(pp, m->d_big.p, m->d_counters + 12,
+                                                            m->d_cand.p, m->d_counters + 8);
+    CU_TRY(m, cudaGetLastError());
+    PostParams rp = pp;
+    rp.slow_list = m->d_cand.p;
+    rp.counters = m->d_counters + 8;
+    slow_rows_kernel<false><<<m->num_sms * 2, 256, 0, m->stream>>>(rp);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += 5;
     return OSFM_OK;
 }
 
@@ -606,8 +625,8 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     m->num_sms = prop.multiProcessorCount;
     CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 8 * sizeof(unsigned long long)));
-    CU_TRY(m, cudaMemset(m->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 16 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMemset(m->d_counters, 0, 16 * sizeof(unsigned long long)));
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xmeta), 4 * sizeof(int)));
     CU_TRY(m, cudaMemset(m->d_xmeta, 0, 4 * sizeof(int)));
 
@@ -639,7 +658,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     reset_kind(m->kind[0], true);
     reset_kind(m->kind[1], true);
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release(); m->d_slow.release();
-    m->d_cand.release();
+    m->d_cand.release(); m->d_big.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
     m->d_ftmp.release();
     m->d_slow_cnt.release(); m->d_job_xrow.release(); m->d_seg_first.release(); m->d_xjobs.release(); m->d_xpool.release();

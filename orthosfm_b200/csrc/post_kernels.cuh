@@ -341,6 +341,27 @@ __global__ void __launch_bounds__(256) exact_gather_kernel(const ScanJob* __rest
     }
 }
 
+// Certifies the EXACT pass: for every big candidate it met, the value it used (the true
+// inner product) must equal the reference's lane-wise 16-bit sum.  Where it does not, the row
+// is queued for the CUDA-core replay.  One thread per record; grid-strides over the list.
+__global__ void __launch_bounds__(256) verify_big_kernel(PostParams p, const int4* __restrict__ big_list,
+                                                         const unsigned long long* __restrict__ big_count,
+                                                         int64_t* __restrict__ replay_list,
+                                                         unsigned long long* __restrict__ replay_count)
+{
+    unsigned long long const n = *reinterpret_cast<const volatile unsigned long long*>(big_count);
+    unsigned long long const stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int4 const rec = big_list[k];
+        int64_t const g = (static_cast<int64_t>(rec.y) << 32) | static_cast<unsigned int>(rec.x);
+        ScanJob const job = p.jobs[p.rowres[g].w];
+        const uint8_t* q = p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes;
+        const uint8_t* c = p.pool + (static_cast<int64_t>(job.c_row) + rec.z) * kRowBytes;
+        if (wrapped_ip<false>(q, c) != rec.w)
+            replay_list[atomicAdd(replay_count, 1ull)] = g;
+    }
+}
+
 // ---------------------------------------------------------------- mutual filter
 
 // One feature kind of one image pair.  in12 / in21 index oneway[] (or -1 when that

@@ -86,11 +86,14 @@ __device__ __noinline__ void report_hang(uint32_t code, uint32_t parity, uint32_
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t code = 0,
                                           uint32_t aux = 0) {
     if (mbar_try_wait(bar, parity)) return;
-    uint64_t const t0 = globaltimer_ns();
+    uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3fffu) == 0u) {
-            if (globaltimer_ns() - t0 > 4000000000ull) report_hang(code, parity, aux);
+        // a failed try has already slept in hardware; look at the clock only now and then
+        if ((++spins & 0xffffu) == 0u) {   // rarely: reading the global timer is slow
+            uint64_t const now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) report_hang(code, parity, aux);
         }
     }
 }

@@ -84,7 +84,13 @@ struct ExactParams {
     int32_t* oneway;
     const int* total_items_dev;  // number of work items, computed on the device
     float sq_lowe, sq_dist;
+    int64_t* replay_list;        // rows that need the full replay on CUDA cores
+    unsigned long long* replay_count;
+    int4* big_list;              // (row lo, row hi, column, similarity) of every big candidate met
+    unsigned long long* big_count;
 };
+
+constexpr int kMaxBigPerRow = 4;   // big candidates per row that verify_big_kernel will certify
 
 // Ties the 32 registers to the completion of the tcgen05.ld that produced them, so the
 // compiler cannot schedule their consumers above the wait.
@@ -361,64 +367,87 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             // rows past the end of the job hold whatever follows in the scratch pool; they
             // must not drag the warp into the update path
             bool const live = r_in_job < job.q_n;
-            const uint8_t* const qptr = ex.qpool + (static_cast<int64_t>(job.q_row) + r_in_job) * kRowBytes;
-            const uint8_t* const cbase = ex.cpool + static_cast<int64_t>(job.c_row) * kRowBytes;
 
-            int b1 = 0, b2 = 0, i1 = 0;   // nearest_neighbor.cc:246-249
+            // Reference state (nearest_neighbor.cc:246-249), replayed in column order.
+            //
+            // A candidate >= 2^16 ("big") enters with the value the tensor core computed.  That
+            // equals the reference's lane-wise 16-bit sum unless one of the eight lanes itself
+            // reached 2^16, which needs an adversarial descriptor; every big candidate is
+            // therefore recorded and verify_big_kernel re-checks it with the lane emulation
+            // afterwards.  Rows that fail the check (or have more than kMaxBigPerRow big
+            // candidates) are replayed on CUDA cores by slow_rows_kernel, which overwrites the
+            // result written here.
+            int b1 = 0, b2 = 0, i1 = 0, nbig = 0;
+            int64_t const g = live ? ex.xrow_map[job.out_row + r_in_job] : 0;
             for (int t = 0; t < ntiles; ++t) {
                 int const ncols = job.c_n - t * kBlockN;
                 mbar_wait(acc_full(my_h), hcnt & 1, kWaitAccFull, hcnt);
                 ++hcnt;
                 tc_fence_after_sync();
+                int32_t v[32], vn[32];
+                tmem_ld_32x32b_x32(taddr0, v);
 #pragma unroll 1
                 for (int c = 0; c < kChunksPerTile; ++c) {
-                    int32_t v[32];
-                    tmem_ld_32x32b_x32(taddr0 + c * kChunk, v);
                     tmem_ld_wait_regs(v);
-                    if (c == kChunksPerTile - 1) {
+                    // prefetch the next chunk while this one is processed
+                    if (c + 1 < kChunksPerTile) {
+                        tmem_ld_32x32b_x32(taddr0 + (c + 1) * kChunk, vn);
+                    } else {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(acc_empty(my_h));
                     }
                     if (ncols < kBlockN) mask_chunk(v, c * kChunk, ncols);
-                    // b2 <= 65535, so a candidate whose lanes wrap (>= 65536) always triggers
+                    // b2 <= 65535, so a big candidate always triggers
                     int const cmax = max32(v);
                     bool const trig = live && cmax >= b2;
-                    if (!__any_sync(0xffffffffu, trig)) continue;
-                    int const col0 = t * kBlockN + c * kChunk;
-                    if (__any_sync(0xffffffffu, trig && cmax >= 65536)) {
-                        // rare: some candidate needs the wrapped-lane emulation
-                        if (trig) {
+                    if (__any_sync(0xffffffffu, trig)) {
+                        int const col0 = t * kBlockN + c * kChunk;
+                        if (__any_sync(0xffffffffu, trig && cmax >= 65536)) {
+                            // rare: a triggered lane meets a big candidate
+                            if (trig) {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) {
-                                int x = v[q];
-                                if (x >= b2) {   // wrapping only lowers x: no update otherwise
-                                    if (x >= 65536)
-                                        x = wrapped_ip<false>(qptr, cbase + static_cast<int64_t>(col0 + q) * kRowBytes);
-                                    ref_scan_step<false>(x, col0 + q, b1, b2, i1);
+                                for (int q = 0; q < 32; ++q) {
+                                    int const x = v[q];
+                                    if (x >= b2) {
+                                        if (x >= 65536) {
+                                            if (nbig < kMaxBigPerRow)
+                                                ex.big_list[atomicAdd(ex.big_count, 1ull)] =
+                                                    make_int4(static_cast<int>(g), static_cast<int>(g >> 32), col0 + q, x);
+                                            ++nbig;
+                                        }
+                                        ref_scan_step<false>(x, col0 + q, b1, b2, i1);
+                                    }
                                 }
                             }
-                        }
-                    } else {
-                        // common: plain sequential top-2 with the reference's tie rule,
-                        // branch-free (values < 2^16 are stored untruncated)
-                        int s1 = b1, s2 = b2, si = i1;
+                        } else {
+                            // common: plain sequential top-2 with the reference's tie rule,
+                            // branch-free (values < 2^16 are stored untruncated)
+                            int s1 = b1, s2 = b2, si = i1;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            int const x = v[q];
-                            bool const ge2 = x >= s2;
-                            bool const ge1 = ge2 && x >= s1;
-                            s2 = ge1 ? s1 : (ge2 ? x : s2);
-                            s1 = ge1 ? x : s1;
-                            si = ge1 ? col0 + q : si;
+                            for (int q = 0; q < 32; ++q) {
+                                int const x = v[q];
+                                bool const ge2 = x >= s2;
+                                bool const ge1 = ge2 && x >= s1;
+                                s2 = ge1 ? s1 : (ge2 ? x : s2);
+                                s1 = ge1 ? x : s1;
+                                si = ge1 ? col0 + q : si;
+                            }
+                            if (trig) { b1 = s1; b2 = s2; i1 = si; }
                         }
-                        if (trig) { b1 = s1; b2 = s2; i1 = si; }
+                    }
+                    if (c + 1 < kChunksPerTile) {
+                        tmem_ld_wait_regs(vn);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = vn[q];
                     }
                 }
             }
             if (live) {
                 bool const ok = passes_tests(ip_to_dist<false>(b1), ip_to_dist<false>(b2), ex.sq_lowe, ex.sq_dist);
-                ex.oneway[ex.xrow_map[job.out_row + r_in_job]] = ok ? i1 : -1;
+                ex.oneway[g] = ok ? i1 : -1;
+                if (nbig > kMaxBigPerRow)   // cannot be certified by verify_big_kernel
+                    ex.replay_list[atomicAdd(ex.replay_count, 1ull)] = g;
             }
         }
     }

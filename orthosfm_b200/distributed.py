@@ -51,15 +51,20 @@ def broadcast_pool(pool, src: int = 0):
 
 
 def gather_match_lists(local_ij, local_offsets: np.ndarray, owned: np.ndarray, npairs: int,
-                       dst: int = 0) -> Tuple[object, np.ndarray]:
+                       dst: int = 0, all_owned: Sequence[np.ndarray] | None = None) -> Tuple[object, np.ndarray]:
     """Gathers every rank's compacted (i, j) lists to ``dst`` and orders them by global
     pair index.
 
     local_ij      int32 tensor [>= local_offsets[-1], 2] on this rank's device
     local_offsets int64 array, len(owned) + 1
     owned         global pair indices of this rank's lists (ascending)
+    all_owned     every rank's ``owned`` (the partition is deterministic, so callers normally
+                  pass ``partition_pairs(...)``; if omitted it is exchanged once)
     Returns (ij, offsets) on ``dst`` -- ij int32 [total, 2], offsets int64 [npairs + 1] --
-    and (None, None) on the other ranks."""
+    and (None, None) on the other ranks.
+
+    Two collectives: one all-gather of the (padded) per-pair list lengths, one gather of the
+    (padded) payloads; the reorder into pair order is a single indexed copy on the device."""
     import torch
     import torch.distributed as dist
 
@@ -73,50 +78,47 @@ def gather_match_lists(local_ij, local_offsets: np.ndarray, owned: np.ndarray, n
 
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = local_ij.device
-    # 1. every rank learns every pair's list length (one small all-reduce)
-    counts = torch.zeros(npairs, dtype=torch.int64, device=dev)
-    if len(owned):
-        counts[torch.as_tensor(owned, device=dev)] = torch.as_tensor(np.diff(local_offsets), device=dev)
-    dist.all_reduce(counts)
-    counts_h = counts.cpu().numpy()
-    offsets = np.zeros(npairs + 1, np.int64)
-    offsets[1:] = np.cumsum(counts_h)
-    # per-rank totals follow from the (deterministic) partition
-    owner = np.full(npairs, -1, np.int64)
-    all_owned: List[np.ndarray] = [None] * world  # type: ignore[list-item]
-    gathered = [None] * world
-    dist.all_gather_object(gathered, np.asarray(owned, np.int64))
-    for r in range(world):
-        all_owned[r] = gathered[r]
-        owner[all_owned[r]] = r
-    totals = [int(counts_h[all_owned[r]].sum()) for r in range(world)]
+    if all_owned is None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, np.asarray(owned, np.int64))
+        all_owned = gathered
+    max_owned = max(len(o) for o in all_owned)
 
-    # 2. payload: point-to-point into rank dst's staging buffers
-    my_total = int(local_offsets[-1])
-    if rank != dst:
-        if my_total > 0:
-            dist.send(local_ij[:my_total].contiguous(), dst=dst)
-        return None, None
-    stage = []
+    # 1. per-pair list lengths of every rank
+    mine = torch.zeros(max_owned, dtype=torch.int64, device=dev)
+    if len(owned):
+        mine[:len(owned)] = torch.as_tensor(np.diff(local_offsets), device=dev)
+    lens_all = torch.empty(world * max_owned, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens_all, mine)
+    lens_h = lens_all.cpu().numpy().reshape(world, max_owned)
+    counts = np.zeros(npairs, np.int64)
+    totals = np.zeros(world, np.int64)
     for r in range(world):
-        if r == dst:
-            stage.append(local_ij[:my_total])
-        elif totals[r] > 0:
-            buf = torch.empty((totals[r], 2), dtype=torch.int32, device=dev)
-            dist.recv(buf, src=r)
-            stage.append(buf)
-        else:
-            stage.append(torch.empty((0, 2), dtype=torch.int32, device=dev))
-    # 3. reorder rank-major lists into global pair order
+        counts[all_owned[r]] = lens_h[r, :len(all_owned[r])]
+        totals[r] = lens_h[r, :len(all_owned[r])].sum()
+    offsets = np.zeros(npairs + 1, np.int64)
+    offsets[1:] = np.cumsum(counts)
+
+    # 2. payloads, padded to the largest rank total
+    pad = int(max(int(totals.max()), 1))
+    send = local_ij[:pad] if local_ij.shape[0] >= pad else torch.cat(
+        [local_ij, torch.zeros((pad - local_ij.shape[0], 2), dtype=torch.int32, device=dev)])
+    send = send.contiguous()
+    if rank == dst:
+        recv = [torch.empty((pad, 2), dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.gather(send, recv, dst=dst)
+    else:
+        dist.gather(send, None, dst=dst)
+        return None, None
+
+    # 3. rank-major lists -> global pair order, one indexed copy per rank
     out = torch.empty((int(offsets[-1]), 2), dtype=torch.int32, device=dev)
     for r in range(world):
         if totals[r] == 0:
             continue
-        lens = counts_h[all_owned[r]]
-        src_off = np.concatenate([[0], np.cumsum(lens)])
-        dst_off = offsets[all_owned[r]]
-        # build one gather index for the whole rank
-        idx = np.concatenate([np.arange(dst_off[k], dst_off[k] + lens[k]) for k in range(len(lens))]) \
-            if len(lens) else np.zeros(0, np.int64)
-        out[torch.as_tensor(idx, device=dev)] = stage[r][:int(src_off[-1])]
+        lens = torch.as_tensor(counts[all_owned[r]], device=dev)
+        dst_off = torch.as_tensor(offsets[all_owned[r]], device=dev)
+        src_off = torch.cumsum(lens, 0) - lens
+        idx = torch.repeat_interleave(dst_off - src_off, lens) + torch.arange(int(totals[r]), device=dev)
+        out[idx] = recv[r][:int(totals[r])]
     return out, offsets
