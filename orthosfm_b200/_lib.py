@@ -22,7 +22,7 @@ EXPORTS = [
     "osfm_match_destroy", "osfm_match_last_error", "osfm_match_begin",
     "osfm_match_set_view_f32", "osfm_match_set_view_q8", "osfm_match_commit",
     "osfm_match_commit_device", "osfm_match_num_views", "osfm_match_view_size",
-    "osfm_match_pair", "osfm_match_pair_twoway", "osfm_match_pair_lowres",
+    "osfm_match_pair", "osfm_match_pair_twoway", "osfm_match_twoway_f32", "osfm_match_pair_lowres",
     "osfm_match_pairs_result_size", "osfm_match_pairs", "osfm_match_pairs_compact_device",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity",
 ]
@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     L.osfm_match_pair.argtypes = [vp, C.c_int, C.c_int, i32p, ip, i32p, ip, ip]
     L.osfm_match_pair_twoway.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, i32p]
     L.osfm_match_pair_lowres.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, ip]
+    L.osfm_match_twoway_f32.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_float, i32p, i32p]
     L.osfm_match_pairs_result_size.argtypes = [vp, i32p, C.c_int]
     L.osfm_match_pairs_result_size.restype = C.c_int64
     L.osfm_match_pairs.argtypes = [vp, i32p, C.c_int, i32p, i64p, i32p]

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/osfm_match.h"
+#include "float_kernels.cuh"
 #include "post_kernels.cuh"
 #include "scan_kernel.cuh"
 
@@ -993,6 +994,51 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
     // survivors of the mutual filter (matching.cc:39-47 vs :19-36).
     OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, &cnt));
     if (n_consistent) *n_consistent = cnt;
+    return OSFM_OK;
+}
+
+// ---- float path ---------------------------------------------------------------------------
+
+int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2, int dim,
+                          float lowe_ratio_threshold, float distance_threshold,
+                          int32_t* matches_1_2, int32_t* matches_2_1) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (n1 < 0 || n2 < 0 || dim <= 0 || dim > kFDim || (dim & 3) != 0)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "float path needs n >= 0 and dim a multiple of 4 in (0, %d]", kFDim);
+    if ((n1 > 0 && (!set_1 || !matches_1_2)) || (n2 > 0 && (!set_2 || !matches_2_1)))
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null pointer");
+    // oneway_match: either set empty -> every entry -1 (matching.h:121-124)
+    if (n1 == 0 || n2 == 0) {
+        for (int i = 0; i < n1; ++i) matches_1_2[i] = -1;
+        for (int i = 0; i < n2; ++i) matches_2_1[i] = -1;
+        return OSFM_OK;
+    }
+    CU_TRY(m, cudaSetDevice(m->device));
+    size_t const f1 = static_cast<size_t>(n1) * kFDim, f2 = static_cast<size_t>(n2) * kFDim;
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    CU_TRY(m, m->d_ftmp.reserve(f1 + f2));
+    CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(n1) + n2));
+    float* const d1 = m->d_ftmp.p;
+    float* const d2 = m->d_ftmp.p + f1;
+    if (dim < kFDim) CU_TRY(m, cudaMemsetAsync(m->d_ftmp.p, 0, (f1 + f2) * sizeof(float), m->stream));
+    CU_TRY(m, cudaMemcpy2DAsync(d1, kFDim * sizeof(float), set_1, dim * sizeof(float), dim * sizeof(float), n1,
+                                cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpy2DAsync(d2, kFDim * sizeof(float), set_2, dim * sizeof(float), dim * sizeof(float), n2,
+                                cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaFuncSetAttribute(float_oneway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFloatSmemBytes));
+    float const sq_lowe = lowe_ratio_threshold * lowe_ratio_threshold;    // MATH_POW2 in float
+    float const sq_dist = distance_threshold * distance_threshold;
+    float_oneway_kernel<<<(n1 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
+        d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p);
+    float_oneway_kernel<<<(n2 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
+        d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += 2;
+    CU_TRY(m, cudaMemcpyAsync(matches_1_2, m->d_oneway.p, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(matches_2_1, m->d_oneway.p + n1, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
     return OSFM_OK;
 }
 

@@ -228,6 +228,22 @@ class ExhaustiveMatching:
                                                    m12.ctypes.data_as(i32p), m21.ctypes.data_as(i32p)))
         return Matching.Result(m12[:n1].copy(), m21[:n2].copy())
 
+    # -- Matching::twoway_match<float> ------------------------------------------------------
+    def twoway_match_f32(self, options: Matching.Options, set_1, set_2) -> Matching.Result:
+        """The float descriptor path (matching.h:148-159 with T = float): bit-identical to
+        the reference's SSE3 build.  ``set_1`` / ``set_2`` are n x descriptor_length floats."""
+        dim = int(options.descriptor_length)
+        a = np.ascontiguousarray(set_1, np.float32).reshape(-1, dim)
+        b = np.ascontiguousarray(set_2, np.float32).reshape(-1, dim)
+        m12 = np.empty(max(a.shape[0], 1), np.int32)
+        m21 = np.empty(max(b.shape[0], 1), np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_twoway_f32(
+            self._h, _ptr(a), a.shape[0], _ptr(b), b.shape[0], dim,
+            C.c_float(options.lowe_ratio_threshold), C.c_float(options.distance_threshold),
+            m12.ctypes.data_as(i32p), m21.ctypes.data_as(i32p)))
+        return Matching.Result(m12[:a.shape[0]].copy(), m21[:b.shape[0]].copy())
+
     # -- batched ------------------------------------------------------------------------------
     def match_pairs(self, pairs, out: Optional[np.ndarray] = None) -> tuple:
         """All pairs in one pass.  Returns (results, n_consistent): a list of

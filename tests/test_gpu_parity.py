@@ -181,6 +181,53 @@ def test_surf_synthetic_matches_oracle(ora):
     assert (o12 >= 0).sum() > 50
 
 
+# ------------------------------------------------------------------ float path
+
+def _unit(x):
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+def test_golden_f32(golden_cases):
+    z, _ = golden_cases
+    name = "f32.synth_200x260"
+    with ExhaustiveMatching() as m:
+        r = m.twoway_match_f32(Matching.Options(128, float(z[name + ".ratio"]), 3.402823466e+38),
+                               z[name + ".a"], z[name + ".b"])
+    assert np.array_equal(r.matches_1_2, z[name + ".t12"])
+    assert np.array_equal(r.matches_2_1, z[name + ".t21"])
+
+
+@pytest.mark.parametrize("n1,n2,dim,ratio,dist", [(1, 1, 128, 0.8, None), (300, 500, 128, 0.8, None),
+                                                  (777, 65, 128, 0.9, 0.5), (200, 1000, 64, 0.7, None),
+                                                  (1500, 1500, 128, 0.8, None), (64, 129, 64, 1.0, 0.05)])
+def test_float_path_is_bit_identical_to_reference_order(ora, n1, n2, dim, ratio, dist):
+    """twoway_match<float>: the GPU forms every inner product in the reference's SSE3
+    summation order, so the bar is equality, not the 1e-5 tie tolerance."""
+    rng = np.random.default_rng(n1 * 7 + n2)
+    signed = dim == 64
+    a = rng.standard_normal((n1, dim)) if signed else np.abs(rng.standard_normal((n1, dim)))
+    b = rng.standard_normal((n2, dim)) if signed else np.abs(rng.standard_normal((n2, dim)))
+    a, b = _unit(a), _unit(b)
+    k = min(n1, n2) // 3
+    b[:k] = _unit(a[:k] + 0.02 * rng.standard_normal((k, dim)))
+    if k > 4:
+        b[k:k + 2] = a[:2]              # exact duplicates: ties and d = 0
+    thr = 3.402823466e+38 if dist is None else dist
+    with ExhaustiveMatching() as m:
+        r = m.twoway_match_f32(Matching.Options(dim, ratio, thr), a, b)
+    o12, o21 = ora.twoway("f32", a, b, ratio, dist=thr, sse3_order=True)
+    assert np.array_equal(r.matches_1_2, o12) and np.array_equal(r.matches_2_1, o21)
+    if n1 > 100 and ratio < 1.0:
+        assert (o12 >= 0).sum() > 10
+
+
+def test_float_path_empty_sets():
+    a = _unit(np.abs(np.random.default_rng(0).standard_normal((5, 128))))
+    with ExhaustiveMatching() as m:
+        r = m.twoway_match_f32(Matching.Options(128, 0.8, 3.402823466e+38), a[:0], a)
+    assert r.matches_1_2.size == 0 and (r.matches_2_1 == -1).all()
+
+
 # ------------------------------------------------------------------ the plugin surface
 
 def test_pairwise_match_sift_plus_surf_combined(ora):
