@@ -104,9 +104,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+NOISE = "renorm"   # planted matches are re-normalised unit vectors, like real SIFT (synth.py)
+
+
 def make_views_numpy(num_views: int, n: int):
     from orthosfm_b200 import synth
-    return synth.sift_views(CFG, num_views, n)
+    return synth.sift_views(CFG, num_views, n, noise=NOISE)
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -339,7 +342,7 @@ def run_ours(args, config):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": pk["bf16_burst"],
                      "unit": "TFLOP/s", "frac": achieved_tops / pk["bf16_burst"], "traffic": None,
-                     "kernel": "scan_kernel<0> (tcgen05.mma kind::i8 + fused top-2 epilogue)",
+                     "kernel": "scan_kernel<0,false,false> (tcgen05.mma kind::i8 + fused 16-bit packed top-2 filter epilogue)",
                      "peak_source": pk["source"] + ", dense bf16 burst; the kernel computes both "
                                     "match directions, achieved counts each unique comparison once (256 OP)",
                      "kernel_ms": scan_avg_ms, "frac_of_sustained": achieved_tops / pk["bf16_sustained"]},
@@ -364,7 +367,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--noise", default="renorm", choices=["renorm", "lsb"],
+                    help="perturbation of the planted matches (orthosfm_b200/synth.py); 'lsb' leaves the "
+                         "16-bit range on purpose and stresses the wrap handling")
     args = ap.parse_args()
+    global NOISE
+    NOISE = args.noise
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ngpu = max(args.gpus, world)
     views = VIEWS_FOR_GPUS.get(ngpu) or int(round((1 + (1 + 8 * 630 * ngpu) ** 0.5) / 2))
@@ -373,7 +381,7 @@ def main():
                      f"pairs, two-way match + ratio test 0.8 + mutual filter"
                      + (" [BASELINE config 2]" if ngpu == 1 else f" [config 2 per-GPU load x {ngpu} GPUs]")),
         "views": views, "descriptors_per_view": N_DESC, "pairs": views * (views - 1) // 2,
-        "planted_fraction": 0.25, "l2": "flushed between timed steps (256 MB write)",
+        "planted_fraction": 0.25, "planted_noise": args.noise, "l2": "flushed between timed steps (256 MB write)",
         "parallelism": f"pairs sharded over {ngpu} GPU(s), pool replicated",
     }
     if args.impl == "reference":

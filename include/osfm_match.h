@@ -183,8 +183,8 @@ int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int n
 typedef struct {
     int64_t kernel_launches;     /* launches of this library's kernels so far      */
     int64_t scan_items;          /* (job, 128-row block) work items processed       */
-    int64_t candidate_rows;      /* rows that needed the exact second-best refine   */
-    int64_t slow_rows;           /* rows re-evaluated with the 16-bit wrap emulation */
+    int64_t candidate_rows;      /* rows that passed the scan kernel's filter (re-run exactly) */
+    int64_t slow_rows;           /* rows without the 16-bit norm certificate (skip the filter) */
     int64_t self_check_failures; /* must stay 0                                      */
     double  last_scan_ms;        /* CUDA-event time of the last scan kernel launch(es) */
     double  last_total_ms;       /* CUDA-event time of the last batched call, device part */
@@ -202,6 +202,20 @@ int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
  * ld = 256 * ceil(n_c / 256). */
 int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int view_c,
     int32_t* out, int64_t out_ints);
+
+/* Writes the same matrix as the scan kernel's filter reads it from tensor memory:
+ * 16-bit packed (tcgen05.ld ... .pack::16b), word k of a row = columns 2k (bits 0-15) and
+ * 2k+1 (bits 16-31), truncated to 16 bits; out is n_q x ld/2 words. */
+int osfm_match_debug_dump_packed(osfm_matcher* m, int kind, int view_q, int view_c,
+    uint32_t* out, int64_t out_words);
+
+/* Runs the scan kernel over both directions of the given SIFT pairs with clock64()
+ * time stamps of CTA 0's pipeline events: out receives 19 warps x 256 events x 4
+ * int64 (epilogue warps 0-15: wait start, accumulator ready, stage handed back, half;
+ * warp 16, the TMA producer: wait start, ring slot free, tile; warps 17-18, the MMA
+ * issuers: wait start, stage free, issued, candidate-tile wait start). */
+int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs,
+    int64_t* out, int64_t out_words);
 
 #ifdef __cplusplus
 }

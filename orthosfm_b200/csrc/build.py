@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libosfm_match.so")
 SOURCES = ["osfm_match.cu"]
-HEADERS = ["ptx.cuh", "scan_kernel.cuh", "post_kernels.cuh", "../../include/osfm_match.h"]
+HEADERS = ["ptx.cuh", "common.cuh", "scan_kernel.cuh", "post_kernels.cuh", "float_kernels.cuh",
+           "gpu_exhaustive_matching.h", "../../include/osfm_match.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

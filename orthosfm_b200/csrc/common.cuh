@@ -14,9 +14,6 @@ constexpr int kItemM = 256;      // query rows per work item (two M halves share
 constexpr int kBlockN = 256;     // candidate rows per tile (= TMEM columns per accumulator)
 constexpr int kChunk = 32;       // candidates per tcgen05.ld.x32
 constexpr int kChunksPerTile = kBlockN / kChunk;
-constexpr int kSub = 16;         // candidates per epilogue sub-chunk: the granularity at which the
-                                 // scan locates the best match, and the window finalize re-examines
-constexpr int kSubsPerTile = kBlockN / kSub;      // 16
 
 constexpr int kInitV1 = -(1 << 30);   // "nothing seen yet" (never multiplied)
 constexpr int kMasked = -(1 << 24);   // similarity of a column past the end of the view: below
@@ -31,7 +28,7 @@ struct ScanJob {
     int32_t c_n;         // number of candidate descriptors
     int64_t out_row;     // first index of this job's rows in rowres[] / oneway[] (or xrow_map[])
     int32_t item_start;  // first work item of this job
-    int32_t c_maxnorm2;  // signed kind: largest squared norm in the candidate view
+    int32_t c_view;      // candidate view id (indexes the per-view largest squared norm)
 };
 
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }

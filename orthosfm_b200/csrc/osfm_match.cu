@@ -35,29 +35,6 @@ constexpr int kPadRows = 256;                  // readable zero rows after the l
 constexpr int64_t kMaxBatchRows = 16ll << 20;  // job rows per batch (bounds scratch memory)
 constexpr int64_t kMaxBatchDense = 1ll << 30;  // dense result ints per batch (4 GiB)
 
-struct KindPool {
-    bool is_signed = false;
-    int dim = 128;
-    uint8_t* pool = nullptr;        // rows of kRowBytes bytes
-    bool owned = false;
-    int64_t rows = 0;               // rows that belong to views
-    std::vector<int64_t> off;       // first row of each view
-    std::vector<int32_t> n;         // descriptors per view
-    std::vector<int32_t> maxnorm2;  // signed kind only
-    int32_t* d_norm2 = nullptr;     // signed kind only
-    CUtensorMap tmap;
-    // Staging arena: views are appended in the order set_view is called.  When that is the
-    // view-id order (the normal case) the arena simply becomes the pool at commit; it is
-    // kept across begin() calls so that re-staging allocates nothing.
-    uint8_t* arena = nullptr;
-    int64_t arena_cap = 0;          // rows
-    int64_t arena_used = 0;         // rows
-    std::vector<int64_t> stage_off; // arena row of each staged view (-1: not staged)
-    int last_staged = -1;
-    bool in_order = true;
-    float lowe = 0.8f, dist = FLT_MAX;
-};
-
 struct JobSpec { int q_view, q_n, c_view, c_n; };
 
 template <typename T>
@@ -74,6 +51,32 @@ struct DevBuf {
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct KindPool {
+    bool is_signed = false;
+    int dim = 128;
+    uint8_t* pool = nullptr;        // rows of kRowBytes bytes
+    bool owned = false;
+    int64_t rows = 0;               // rows that belong to views
+    std::vector<int64_t> off;       // first row of each view
+    std::vector<int32_t> n;         // descriptors per view
+    // wrap certificate (scan_kernel.cuh): squared norm per pool row, largest per view
+    DevBuf<int32_t> d_norm2;
+    DevBuf<int32_t> d_viewmax;
+    DevBuf<int64_t> d_view_off;
+    DevBuf<int32_t> d_view_n;
+    CUtensorMap tmap;
+    // Staging arena: views are appended in the order set_view is called.  When that is the
+    // view-id order (the normal case) the arena simply becomes the pool at commit; it is
+    // kept across begin() calls so that re-staging allocates nothing.
+    uint8_t* arena = nullptr;
+    int64_t arena_cap = 0;          // rows
+    int64_t arena_used = 0;         // rows
+    std::vector<int64_t> stage_off; // arena row of each staged view (-1: not staged)
+    int last_staged = -1;
+    bool in_order = true;
+    float lowe = 0.8f, dist = FLT_MAX;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -107,7 +110,7 @@ struct osfm_matcher {
     KindPool kind[2];
 
     DevBuf<ScanJob> d_jobs;
-    DevBuf<int4> d_rowres;
+    DevBuf<int2> d_rowres;
     DevBuf<int32_t> d_oneway;
     DevBuf<int64_t> d_slow;
     DevBuf<int64_t> d_cand;
@@ -172,11 +175,11 @@ int cuda_fail(osfm_matcher* m, cudaError_t e, const char* what) {
 // Forgets the views (keeps the staging arena's memory unless release_arena).
 void reset_kind(KindPool& k, bool release_arena) {
     if (k.owned && k.pool && k.pool != k.arena) cudaFree(k.pool);
-    if (k.d_norm2) cudaFree(k.d_norm2);
-    k.pool = nullptr; k.owned = false; k.d_norm2 = nullptr;
-    k.rows = 0; k.off.clear(); k.n.clear(); k.maxnorm2.clear();
+    k.pool = nullptr; k.owned = false;
+    k.rows = 0; k.off.clear(); k.n.clear();
     k.stage_off.clear(); k.arena_used = 0; k.last_staged = -1; k.in_order = true;
     if (release_arena && k.arena) { cudaFree(k.arena); k.arena = nullptr; k.arena_cap = 0; }
+    if (release_arena) { k.d_norm2.release(); k.d_viewmax.release(); k.d_view_off.release(); k.d_view_n.release(); }
 }
 
 // Makes room for `rows` more rows in the staging arena (contents are preserved).
@@ -198,28 +201,28 @@ int encode_tmap(osfm_matcher* m, CUtensorMap* map, void* base, int64_t rows_with
 
 int make_tmap(osfm_matcher* m, KindPool& k) { return encode_tmap(m, &k.tmap, k.pool, k.rows + kPadRows); }
 
-// Per-row squared norms + per-view maxima for the signed kind (wrap certificate).
+// Per-row squared norms + per-view maxima (the filter's wrap certificate).  Asynchronous on
+// the handle's stream; k.off / k.n are staged by the runtime before the calls return.
 int compute_norms(osfm_matcher* m, KindPool& k) {
-    k.maxnorm2.assign(k.n.size(), 0);
-    if (!k.is_signed || k.rows == 0) return OSFM_OK;
-    std::vector<int32_t> row_view(k.rows);
-    for (size_t v = 0; v < k.n.size(); ++v)
-        for (int i = 0; i < k.n[v]; ++i) row_view[k.off[v] + i] = static_cast<int32_t>(v);
-    int32_t *d_view = nullptr, *d_max = nullptr;
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_view), sizeof(int32_t) * k.rows));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_max), sizeof(int32_t) * k.n.size()));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&k.d_norm2), sizeof(int32_t) * (k.rows + kPadRows)));
-    CU_TRY(m, cudaMemcpyAsync(d_view, row_view.data(), sizeof(int32_t) * k.rows, cudaMemcpyHostToDevice, m->stream));
-    CU_TRY(m, cudaMemsetAsync(d_max, 0, sizeof(int32_t) * k.n.size(), m->stream));
-    CU_TRY(m, cudaMemsetAsync(k.d_norm2, 0, sizeof(int32_t) * (k.rows + kPadRows), m->stream));
+    size_t const nv = k.n.size();
+    CU_TRY(m, k.d_norm2.reserve(static_cast<size_t>(k.rows + kPadRows)));
+    CU_TRY(m, k.d_viewmax.reserve(std::max<size_t>(nv, 1)));
+    CU_TRY(m, cudaMemsetAsync(k.d_viewmax.p, 0, sizeof(int32_t) * std::max<size_t>(nv, 1), m->stream));
+    if (k.rows == 0 || nv == 0) return OSFM_OK;
+    CU_TRY(m, k.d_view_off.reserve(nv));
+    CU_TRY(m, k.d_view_n.reserve(nv));
+    CU_TRY(m, cudaMemcpyAsync(k.d_view_off.p, k.off.data(), sizeof(int64_t) * nv, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(k.d_view_n.p, k.n.data(), sizeof(int32_t) * nv, cudaMemcpyHostToDevice, m->stream));
     int const grid = static_cast<int>((k.rows + 255) / 256);
-    rownorm_kernel<<<grid, 256, 0, m->stream>>>(k.pool, k.rows, d_view, k.d_norm2, d_max);
+    if (k.is_signed) rownorm_kernel<true><<<grid, 256, 0, m->stream>>>(k.pool, k.rows, k.d_norm2.p);
+    else             rownorm_kernel<false><<<grid, 256, 0, m->stream>>>(k.pool, k.rows, k.d_norm2.p);
     CU_TRY(m, cudaGetLastError());
-    m->stats.kernel_launches++;
-    CU_TRY(m, cudaMemcpyAsync(k.maxnorm2.data(), d_max, sizeof(int32_t) * k.n.size(), cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(m, cudaStreamSynchronize(m->stream));
-    cudaFree(d_view);
-    cudaFree(d_max);
+    int max_n = 0;
+    for (int32_t n : k.n) max_n = std::max(max_n, n);
+    dim3 const vgrid(static_cast<unsigned>(nv), static_cast<unsigned>(std::max(1, (max_n + kViewMaxChunk - 1) / kViewMaxChunk)));
+    viewmax_kernel<<<vgrid, 256, 0, m->stream>>>(k.d_norm2.p, k.d_view_off.p, k.d_view_n.p, k.d_viewmax.p);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += 2;
     return OSFM_OK;
 }
 
@@ -242,23 +245,32 @@ int arena_reserve(osfm_matcher* m, KindPool& k, int64_t rows) {
     return OSFM_OK;
 }
 
-template <int MODE>
-cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+int ksteps_of(const KindPool& k) { return (k.dim + 31) / 32; }
+
+template <int MODE, bool SIGNED>
+cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, false, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kScanSmemBytes);
     if (e != cudaSuccess) return e;
     int const grid = std::min(m->num_sms, total_items);
-    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, k.is_signed ? 1 : 0, k.is_signed ? 1 : 0);
+    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     ExactParams ex;
     memset(&ex, 0, sizeof ex);
-    scan_kernel<MODE, false><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, m->d_jobs.p, total_items, m->d_rowres.p, idesc, dump, dump_ld, ex);
+    scan_kernel<MODE, false, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
+        k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p);
     return cudaGetLastError();
 }
 
-// Second pass over the rows finalize_kernel<false> flagged (unsigned kind): plan, gather,
-// and the EXACT variant of the scan kernel.  Everything is sized on the device; the host
-// never learns how many rows there were until it reads the counters.
+template <int MODE>
+cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
+    return k.is_signed ? launch_scan_t<MODE, true>(m, k, total_items, dump, dump_ld)
+                       : launch_scan_t<MODE, false>(m, k, total_items, dump, dump_ld);
+}
+
+// Second pass, over the survivors of the filter: plan, gather, and the EXACT variant of the
+// scan kernel.  Everything is sized on the device; the host never learns how many rows there
+// were until it reads the counters.
+template <bool SIGNED>
 int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp) {
     CU_TRY(m, m->d_job_xrow.reserve(static_cast<size_t>(njobs)));
     CU_TRY(m, m->d_xjobs.reserve(static_cast<size_t>(nseg) + 1));
@@ -276,7 +288,7 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, i
                                                               m->d_job_xrow.p, m->d_slow.p, k.pool,
                                                               m->d_xpool.p, m->d_xrow_map.p);
     CU_TRY(m, cudaGetLastError());
-    CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+    CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, true, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
     ExactParams ex;
     ex.qpool = m->d_xpool.p;
     ex.cpool = k.pool;
@@ -285,43 +297,49 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, i
     ex.total_items_dev = m->d_xmeta;
     ex.sq_lowe = pp.sq_lowe;
     ex.sq_dist = pp.sq_dist;
-    ex.replay_list = m->d_cand.p;          // free again: refine_kernel precedes this pass
+    ex.replay_list = m->d_cand.p;
     ex.replay_count = m->d_counters + 8;
-    CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
-    ex.big_list = m->d_big.p;
+    ex.big_list = nullptr;
     ex.big_count = m->d_counters + 12;
-    CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
-    CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
-    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, 0, 0);
-    scan_kernel<0, true><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
-        m->tmap_x, k.tmap, m->d_xjobs.p, 0, nullptr, idesc, nullptr, 0, ex);
+    ex.self_check = m->d_counters + 2;
+    if (!SIGNED) {
+        CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
+        ex.big_list = m->d_big.p;
+        CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
+        CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
+    }
+    uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
+    scan_kernel<0, true, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
+        m->tmap_x, k.tmap, m->d_xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr);
     CU_TRY(m, cudaGetLastError());
-    // certify the big candidates; rows that fail (a 16-bit lane really wrapped) get the
-    // warp-per-row replay.  counters[8] is the replay list length; counters[11] absorbs the
-    // replay kernel's (already counted) total.
-    verify_big_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(pp, m->d_big.p, m->d_counters + 12,
-                                                            m->d_cand.p, m->d_counters + 8);
-    CU_TRY(m, cudaGetLastError());
-    PostParams rp = pp;
-    rp.slow_list = m->d_cand.p;
-    rp.counters = m->d_counters + 8;
-    slow_rows_kernel<false><<<m->num_sms * 2, 256, 0, m->stream>>>(rp);
-    CU_TRY(m, cudaGetLastError());
-    m->stats.kernel_launches += 5;
+    m->stats.kernel_launches += 3;
+    if (!SIGNED) {
+        // certify the big candidates; rows that fail (a 16-bit lane really wrapped) get the
+        // warp-per-row replay.  counters[8] is the replay list length.
+        verify_big_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(pp, m->d_big.p, m->d_counters + 12,
+                                                                m->d_cand.p, m->d_counters + 8);
+        CU_TRY(m, cudaGetLastError());
+        PostParams rp = pp;
+        rp.slow_list = m->d_cand.p;
+        rp.counters = m->d_counters + 8;
+        slow_rows_kernel<false><<<m->num_sms * 2, 256, 0, m->stream>>>(rp);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches += 2;
+    }
     return OSFM_OK;
 }
 
-// Runs scan + finalize + wrap emulation for a list of jobs of one kind.  On return (in
-// stream order) m->d_oneway holds, for job i, q_n one-way results starting at out_row[i]
+// Runs filter scan + EXACT pass (+ wrap emulation) for a list of jobs of one kind.  On return
+// (in stream order) m->d_oneway holds, for job i, q_n one-way results starting at out_row[i]
 // (out_row[i] = -1 if the job was not run because one side is empty).
 int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
-             std::vector<int64_t>& out_row, int32_t* dump = nullptr, int64_t dump_ld = 0) {
+             std::vector<int64_t>& out_row, int32_t* dump = nullptr, int64_t dump_ld = 0, int dump_mode = 3) {
     KindPool& k = m->kind[kind_id];
     out_row.assign(specs.size(), -1);
     std::vector<ScanJob> jobs;
     jobs.reserve(specs.size() + 1);
     // Jobs are ordered by candidate view: concurrently running work items then stream the
-    // same candidate tiles (L2 locality), and the EXACT pass can merge the slow rows of all
+    // same candidate tiles (L2 locality), and the EXACT pass can merge the survivors of all
     // jobs that share a candidate view into full 256-row items.
     std::vector<uint32_t> order(specs.size());
     for (size_t i = 0; i < specs.size(); ++i) order[i] = static_cast<uint32_t>(i);
@@ -335,7 +353,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         size_t const i = order[oi];
         JobSpec const& s = specs[i];
         if (s.q_n <= 0 || s.c_n <= 0) continue;
-        if (jobs.empty() || jobs.back().c_row != static_cast<int32_t>(k.off[s.c_view]) || jobs.back().c_n != s.c_n)
+        if (jobs.empty() || jobs.back().c_view != s.c_view || jobs.back().c_n != s.c_n)
             seg_first.push_back(static_cast<int32_t>(jobs.size()));
         ScanJob j;
         j.q_row = static_cast<int32_t>(k.off[s.q_view]);
@@ -344,7 +362,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         j.c_n = s.c_n;
         j.out_row = rows;
         j.item_start = static_cast<int32_t>(items);
-        j.c_maxnorm2 = k.is_signed ? k.maxnorm2[s.c_view] : 0;
+        j.c_view = s.c_view;
         out_row[i] = rows;
         rows += s.q_n;
         items += (s.q_n + kItemM - 1) / kItemM;
@@ -352,6 +370,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     }
     if (jobs.empty()) return OSFM_OK;
     if (items > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many work items in one batch");
+    if (rows > static_cast<int64_t>(kSurvRowMask)) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many rows in one batch");
     int const njobs = static_cast<int>(jobs.size());
     int const nseg = static_cast<int>(seg_first.size());
     seg_first.push_back(njobs);
@@ -362,7 +381,6 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     jobs.push_back(sentinel);
 
     CU_TRY(m, m->d_jobs.reserve(jobs.size()));
-    CU_TRY(m, m->d_rowres.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_slow.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_cand.reserve(static_cast<size_t>(rows)));
@@ -375,55 +393,66 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
                               cudaMemcpyHostToDevice, m->stream));
     // pageable source: the copy is staged before the call returns, `jobs` may die.
     CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));      // [0]
-    CU_TRY(m, cudaMemsetAsync(m->d_counters + 4, 0, sizeof(unsigned long long), m->stream));  // [4]
+
+    CU_TRY(m, m->d_rowres.reserve(static_cast<size_t>(rows)));
+    float const sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
+    float const sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
 
     CU_TRY(m, cudaEventRecord(m->ev[0], m->stream));
     cudaError_t e;
-    switch (dump ? 3 : m->scan_mode) {
+    switch (dump ? dump_mode : m->scan_mode) {
         case 1: e = launch_scan<1>(m, k, static_cast<int>(items), nullptr, 0); break;
-        case 2: e = launch_scan<2>(m, k, static_cast<int>(items), nullptr, 0); break;
+        case 2: e = launch_scan<2>(m, k, static_cast<int>(items), m->d_oneway.p, 0); break;
         case 3: e = launch_scan<3>(m, k, static_cast<int>(items), dump, dump_ld); break;
+        case 4: e = launch_scan<4>(m, k, static_cast<int>(items), dump, dump_ld); break;
+        case 5: e = launch_scan<5>(m, k, static_cast<int>(items), dump, dump_ld); break;
         default: e = launch_scan<0>(m, k, static_cast<int>(items), nullptr, 0); break;
     }
     if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
     CU_TRY(m, cudaEventRecord(m->ev[1], m->stream));
     m->stats.kernel_launches++;
     m->stats.scan_items += items;
+    if (dump) return OSFM_OK;   // debug dumps produce no results
+
+    ClassifyParams cp;
+    cp.jobs = m->d_jobs.p;
+    cp.total_rows = rows;
+    cp.rowres = m->d_rowres.p;
+    cp.norm2 = k.d_norm2.p;
+    cp.viewmax = k.d_viewmax.p;
+    cp.oneway = m->d_oneway.p;
+    cp.surv_list = m->d_slow.p;
+    cp.surv_cnt = m->d_slow_cnt.p;
+    cp.uncert_list = m->d_cand.p;
+    cp.counters = m->d_counters;
+    cp.sq_lowe = sq_lowe;
+    cp.sq_dist = sq_dist;
+    int const cgrid = static_cast<int>((rows + 255) / 256);
+    if (k.is_signed) classify_kernel<true><<<cgrid, 256, 0, m->stream>>>(cp);
+    else             classify_kernel<false><<<cgrid, 256, 0, m->stream>>>(cp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(m, e, "classify_kernel launch");
+    m->stats.kernel_launches++;
 
     PostParams pp;
     pp.pool = k.pool;
     pp.jobs = m->d_jobs.p;
     pp.njobs = njobs;
-    pp.total_rows = rows;
-    pp.rowres = m->d_rowres.p;
     pp.oneway = m->d_oneway.p;
-    pp.sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
-    pp.sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
-    pp.slow_list = m->d_slow.p;
+    pp.sq_lowe = sq_lowe;
+    pp.sq_dist = sq_dist;
+    pp.slow_list = m->d_cand.p;
     pp.counters = m->d_counters;
-    pp.norm2 = k.d_norm2;
-    pp.slow_cnt = m->d_slow_cnt.p;
-    pp.cand_list = m->d_cand.p;
-    int const grid = static_cast<int>((rows + 255) / 256);
-    int const rgrid = m->num_sms * 8;
     if (k.is_signed) {
-        classify_kernel<true><<<grid, 256, 0, m->stream>>>(pp);
-        refine_kernel<true><<<rgrid, 256, 0, m->stream>>>(pp);
-    } else {
-        classify_kernel<false><<<grid, 256, 0, m->stream>>>(pp);
-        refine_kernel<false><<<rgrid, 256, 0, m->stream>>>(pp);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(m, e, "classify/refine launch");
-    m->stats.kernel_launches += 2;
-    if (k.is_signed) {
-        // adversarial signed input only: warp-per-row emulation on CUDA cores
+        // rows without the norm certificate (adversarial input only): warp-per-row emulation
+        // on CUDA cores.  It only reads d_cand, which the EXACT pass does not touch when signed.
         slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
         m->stats.kernel_launches++;
+        OS_TRY(launch_exact_pass<true>(m, k, njobs, nseg, rows, pp));
     } else {
-        OS_TRY(launch_exact_pass(m, k, njobs, nseg, rows, pp));
+        OS_TRY(launch_exact_pass<false>(m, k, njobs, nseg, rows, pp));
     }
 
     // Scan time of this launch; read after the caller's next synchronisation.
@@ -531,12 +560,12 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
 }
 
 int read_counters(osfm_matcher* m) {
-    unsigned long long c[4];
+    unsigned long long c[6];
     CU_TRY(m, cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     m->stats.candidate_rows = static_cast<int64_t>(c[1]);
     m->stats.self_check_failures = static_cast<int64_t>(c[2]);
     m->stats.slow_rows = static_cast<int64_t>(c[3]);
-    if (c[2] != 0) return fail(m, OSFM_ERR_INTERNAL, "kernel self-check failed %llu times (scan/refine mismatch)", c[2]);
+    if (c[2] != 0) return fail(m, OSFM_ERR_INTERNAL, "kernel self-check failed %llu times (filter / EXACT pass mismatch)", c[2]);
     return OSFM_OK;
 }
 
@@ -1123,13 +1152,13 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
 }
 
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
-    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;
+    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;   /* 3, 4: dump entry points */
     std::lock_guard<std::mutex> lock(m->mu);
     m->scan_mode = mode;
     return OSFM_OK;
 }
 
-int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int view_c, int32_t* out, int64_t out_ints) {
+static int debug_dump(osfm_matcher* m, int kind, int view_q, int view_c, int32_t* out, int64_t out_ints, int mode) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -1140,19 +1169,57 @@ int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int 
     int const nq = m->kind[kind].n[view_q], nc = m->kind[kind].n[view_c];
     if (nq <= 0 || nc <= 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "empty view");
     int64_t const ld = static_cast<int64_t>(kBlockN) * ((nc + kBlockN - 1) / kBlockN);
-    if (!out || out_ints < static_cast<int64_t>(nq) * ld) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "dump buffer too small");
+    int64_t const ints = static_cast<int64_t>(nq) * (mode == 4 ? ld / 2 : ld);
+    if (!out || out_ints < ints) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "dump buffer too small");
     int32_t* d = nullptr;
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int32_t) * nq * ld));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int32_t) * ints));
     std::vector<JobSpec> specs(1, JobSpec{view_q, nq, view_c, nc});
     std::vector<int64_t> out_row;
-    int r = run_jobs(m, kind, specs, out_row, d, ld);
+    int r = run_jobs(m, kind, specs, out_row, d, ld, mode);
     if (r == OSFM_OK) {
         cudaError_t e = cudaStreamSynchronize(m->stream);
-        if (e == cudaSuccess) e = cudaMemcpy(out, d, sizeof(int32_t) * nq * ld, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, sizeof(int32_t) * ints, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) r = cuda_fail(m, e, "dump copy");
     }
     cudaFree(d);
     return r;
+}
+
+int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int view_c, int32_t* out, int64_t out_ints) {
+    return debug_dump(m, kind, view_q, view_c, out, out_ints, 3);
+}
+
+int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, int64_t* out, int64_t out_words) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    int64_t const words = static_cast<int64_t>(kScanThreads / 32) * kTraceEvents * 4;   // 19 warps
+    if (!out || out_words < words) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "trace buffer too small (%lld words)", (long long)words);
+    CU_TRY(m, cudaSetDevice(m->device));
+    std::vector<JobSpec> specs;
+    for (int i = 0; i < npairs; ++i) {
+        int const a = pairs[2 * i], b = pairs[2 * i + 1];
+        OS_TRY(check_view(m, a));
+        OS_TRY(check_view(m, b));
+        specs.push_back({a, m->kind[0].n[a], b, m->kind[0].n[b]});
+        specs.push_back({b, m->kind[0].n[b], a, m->kind[0].n[a]});
+    }
+    int64_t* d = nullptr;
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int64_t) * words));
+    CU_TRY(m, cudaMemset(d, 0, sizeof(int64_t) * words));
+    std::vector<int64_t> out_row;
+    int r = run_jobs(m, 0, specs, out_row, reinterpret_cast<int32_t*>(d), 0, 5);
+    if (r == OSFM_OK) {
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, sizeof(int64_t) * words, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) r = cuda_fail(m, e, "trace copy");
+    }
+    cudaFree(d);
+    return r;
+}
+
+int osfm_match_debug_dump_packed(osfm_matcher* m, int kind, int view_q, int view_c, uint32_t* out, int64_t out_words) {
+    return debug_dump(m, kind, view_q, view_c, reinterpret_cast<int32_t*>(out), out_words, 4);
 }
 
 }  // extern "C"

@@ -55,11 +55,11 @@ __global__ void quantize_kernel(const float* __restrict__ in, int n, int dim, in
     out[idx] = q;
 }
 
-// Squared norm of every pool row and its maximum per view (signed kind only: they
-// certify that no 16-bit lane of the reference's SSE loop can wrap, see finalize).
-__global__ void rownorm_kernel(const uint8_t* __restrict__ pool, int64_t rows,
-                               const int32_t* __restrict__ row_view, int32_t* __restrict__ norm2,
-                               int32_t* __restrict__ view_max)
+// Squared norm of every pool row, and its maximum per view: the Cauchy-Schwarz certificate
+// that lets the scan kernel's filter work on 16-bit packed similarities (scan_kernel.cuh).
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) rownorm_kernel(const uint8_t* __restrict__ pool, int64_t rows,
+                                                      int32_t* __restrict__ norm2)
 {
     int64_t const r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= rows) return;
@@ -68,13 +68,41 @@ __global__ void rownorm_kernel(const uint8_t* __restrict__ pool, int64_t rows,
 #pragma unroll
     for (int i = 0; i < kRowBytes / 16; ++i) {
         uint4 const x = __ldg(p + i);
-        acc = __dp4a(static_cast<int>(x.x), static_cast<int>(x.x), acc);
-        acc = __dp4a(static_cast<int>(x.y), static_cast<int>(x.y), acc);
-        acc = __dp4a(static_cast<int>(x.z), static_cast<int>(x.z), acc);
-        acc = __dp4a(static_cast<int>(x.w), static_cast<int>(x.w), acc);
+        if (SIGNED) {
+            acc = __dp4a(static_cast<int>(x.x), static_cast<int>(x.x), acc);
+            acc = __dp4a(static_cast<int>(x.y), static_cast<int>(x.y), acc);
+            acc = __dp4a(static_cast<int>(x.z), static_cast<int>(x.z), acc);
+            acc = __dp4a(static_cast<int>(x.w), static_cast<int>(x.w), acc);
+        } else {
+            unsigned u = static_cast<unsigned>(acc);
+            u = __dp4a(x.x, x.x, u);
+            u = __dp4a(x.y, x.y, u);
+            u = __dp4a(x.z, x.z, u);
+            u = __dp4a(x.w, x.w, u);
+            acc = static_cast<int>(u);   // <= 128 * 255^2 < 2^23
+        }
     }
     norm2[r] = acc;
-    atomicMax(view_max + row_view[r], acc);
+}
+
+constexpr int kViewMaxChunk = 8192;   // rows per CTA
+
+// grid = (views, chunks): view_max[v] = max of norm2 over the view's rows (views may overlap
+// or leave gaps in a caller-provided device pool).  view_max must be zeroed beforehand.
+__global__ void __launch_bounds__(256) viewmax_kernel(const int32_t* __restrict__ norm2,
+                                                      const int64_t* __restrict__ view_off,
+                                                      const int32_t* __restrict__ view_n,
+                                                      int32_t* __restrict__ view_max)
+{
+    int const v = blockIdx.x;
+    int const n = view_n[v];
+    int const lo = blockIdx.y * kViewMaxChunk;
+    if (lo >= n) return;
+    const int32_t* p = norm2 + view_off[v];
+    int m = 0;
+    for (int i = lo + threadIdx.x; i < min(n, lo + kViewMaxChunk); i += blockDim.x) m = max(m, p[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(view_max + v, m);
 }
 
 // ---------------------------------------------------------------- finalisation
@@ -83,117 +111,92 @@ struct PostParams {
     const uint8_t* pool;
     const ScanJob* jobs;        // njobs + 1 entries (sentinel: out_row = total_rows)
     int njobs;
-    int64_t total_rows;
-    const int4* rowres;         // (v1, pos, v2 lower bound, job index) per job row
     int32_t* oneway;            // out: index of the match in the candidate view or -1
     float sq_lowe;              // lowe_ratio_threshold^2   (matching.h:126)
     float sq_dist;              // distance_threshold^2     (matching.h:127)
-    int64_t* slow_list;         // rows that need the wrap emulation
-    unsigned long long* counters;  // [0] slow rows of this batch (signed kind), [1] candidate
-                                   // rows (cumulative), [2] self-check failures, [3] slow rows
-                                   // (cumulative), [4] candidate rows of this batch
-    const int32_t* norm2;       // signed kind: squared norm per pool row
-    int* slow_cnt;              // unsigned kind: slow rows per job; the rows of job j are
-                                // listed at slow_list[jobs[j].out_row + 0 .. slow_cnt[j])
-    int64_t* cand_list;         // rows that need the exact second best; length = counters[4]
+    int64_t* slow_list;         // rows slow_rows_kernel replays
+    unsigned long long* counters;  // [0] length of slow_list
 };
 
-// classify_kernel: one thread per job row.  Rows whose ratio test fails even with the lower
-// bound on the second-best similarity are final (-1).  Rows that pass become *candidates*
-// and are appended to a list (warp-aggregated atomic); rows whose best similarity reached
-// 2^16 (unsigned) or whose norms cannot exclude a 16-bit lane wrap (signed) go to the slow
-// list instead.
+// ---------------------------------------------------------------- filter decision
+
+struct ClassifyParams {
+    const ScanJob* jobs;
+    int64_t total_rows;
+    const int2* rowres;          // pack_rowres(v1, v2 lower bound, job) per job row
+    const int32_t* norm2;        // squared norm of every pool row
+    const int32_t* viewmax;      // largest squared norm per view (index: ScanJob::c_view)
+    int32_t* oneway;             // out: -1 for rows the filter rejects
+    int64_t* surv_list;          // survivors of job j: surv_list[jobs[j].out_row + 0 .. surv_cnt[j])
+    int* surv_cnt;
+    int64_t* uncert_list;        // signed kind: rows without certificate (CUDA-core replay), flat
+    unsigned long long* counters;  // [0] uncert_list length, [1] certified survivors (cumulative),
+                                   // [3] rows without certificate (cumulative)
+    float sq_lowe, sq_dist;
+};
+
+// One thread per job row: applies the reference's tests (matching.h:126-144) to the scan
+// kernel's (best, lower bound of second best).  A row that fails them is final (-1): the
+// ratio test is monotone in the second best.  A row that passes is a *survivor* and is
+// queued, per job, for the EXACT pass.  Both statements need the row's similarities to have
+// fitted the filter's 16 bits, which the norm certificate guarantees; rows without it join the
+// survivors (unsigned) or go to the CUDA-core replay (signed: the reference's 16-bit lanes may
+// wrap as well).
 template <bool SIGNED>
-__global__ void __launch_bounds__(256) classify_kernel(PostParams p)
+__global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 {
     int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     int const lane = threadIdx.x & 31;
-    bool cand = false;
-    if (g < p.total_rows) {
-        int4 const rr = p.rowres[g];
-        int const v1 = rr.x, v2 = rr.z;
-        int const ji = rr.w;                 // the scan kernel recorded the row's job
+    bool certified = false, survive = false, live = g < p.total_rows;
+    int ji = -1, v1 = 0;
+    int64_t out_row = 0;
+    if (live) {
+        int2 const rr = p.rowres[g];
+        v1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
+        int const v2 = SIGNED ? (rr.x >> 16) : static_cast<int>(static_cast<uint32_t>(rr.x) >> 16);
+        ji = rr.y;
         ScanJob const job = p.jobs[ji];
-        int result = -1;
-        bool slow;
-        if (SIGNED) {
-            // No 16-bit lane can wrap if |a||b| < 2^15 (Cauchy-Schwarz per lane).
-            int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
-            slow = static_cast<int64_t>(p.norm2[q_prow]) * static_cast<int64_t>(job.c_maxnorm2) >= (1ll << 30);
-            if (!slow) {
-                if (v1 < 0) {
-                    // no candidate reached the initial best of 0: index stays 0
-                    int const d = ip_to_dist<true>(0);
-                    result = passes_tests(d, d, p.sq_lowe, p.sq_dist) ? 0 : -1;
-                } else {
-                    cand = passes_tests(ip_to_dist<true>(v1), ip_to_dist<true>(v2), p.sq_lowe, p.sq_dist);
-                }
-            }
-            if (slow) p.slow_list[atomicAdd(p.counters + 0, 1ull)] = g;
-        } else {
-            // Any similarity >= 2^16 makes the reference's 16-bit lanes / stores wrap.
-            slow = v1 >= 65536;
-            if (!slow)
-                cand = passes_tests(ip_to_dist<false>(v1), ip_to_dist<false>(v2), p.sq_lowe, p.sq_dist);
-            else
-                p.slow_list[job.out_row + atomicAdd(p.slow_cnt + ji, 1)] = g;
-        }
-        if (!slow && !cand) p.oneway[g] = result;
+        out_row = job.out_row;
+        int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+        certified = static_cast<int64_t>(p.norm2[job.q_row + static_cast<int>(g - job.out_row)]) *
+                    static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
+        // signed: a row whose best is the initial 0 may have no candidate >= 0 at all; the
+        // EXACT pass sorts that out (the index then stays 0)
+        survive = certified && ((SIGNED && v1 == 0) ||
+                                passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(v2), p.sq_lowe, p.sq_dist));
+        if (certified && !survive) p.oneway[g] = -1;
     }
-    unsigned const cmask = __ballot_sync(0xffffffffu, cand);
-    if (cmask != 0) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(cmask)));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand) p.cand_list[base + __popc(cmask & ((1u << lane) - 1u))] = g;
+    // survivors (and unsigned rows without certificate) -> the job's list; one atomic per job
+    // present in the warp (a warp spans at most a few jobs)
+    bool const to_exact = live && (survive || (!SIGNED && !certified));
+    unsigned const xm = __ballot_sync(0xffffffffu, to_exact);
+    if (to_exact) {
+        unsigned const peers = __match_any_sync(xm, ji);
+        int const leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(p.surv_cnt + ji, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(g, v1, certified);
     }
-}
-
-// refine_kernel: half a warp per candidate row.  Lane l recomputes the similarity with
-// candidate pos*16 + l, which yields the exact arg-max (highest index on ties) and the exact
-// second best; then the reference's tests decide.  Grid-strides over the candidate list,
-// whose length is only known on the device.
-template <bool SIGNED>
-__global__ void __launch_bounds__(256) refine_kernel(PostParams p)
-{
-    unsigned long long const ncand = *reinterpret_cast<volatile unsigned long long*>(p.counters + 4);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && ncand > 0) atomicAdd(p.counters + 1, ncand);
-    int const lane = threadIdx.x & 31;
-    int const sub = lane & 15;
-    unsigned const hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
-    int const hshift = lane & 16;
-    unsigned long long const nhalf = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 4;
-    unsigned long long k = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
-    // both halves of a warp must iterate the same number of times (full-mask ballots)
-    unsigned long long const kmax = ((ncand + 1) >> 1) << 1;
-    for (; k < kmax; k += nhalf) {
-        bool const active = k < ncand;
-        int dot = INT_MIN / 2, v1 = 0, v2 = 0, pos = 0;
-        int64_t g = 0;
-        if (active) {
-            g = p.cand_list[k];
-            int4 const rr = p.rowres[g];
-            ScanJob const job = p.jobs[rr.w];
-            v1 = rr.x; pos = rr.y; v2 = rr.z;
-            int const col = pos * kSub + sub;
-            if (col < job.c_n)
-                dot = dot_row<SIGNED>(p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes,
-                                      p.pool + (static_cast<int64_t>(job.c_row) + col) * kRowBytes);
-        }
-        unsigned const eq = (__ballot_sync(0xffffffffu, active && dot == v1) & hmask) >> hshift;
-        int const jl = 31 - __clz(eq);   // highest index wins ties (nearest_neighbor.cc:89); -1 if none
-        int const second = __reduce_max_sync(hmask, sub == jl ? INT_MIN / 2 : dot);
-        if (active && sub == 0) {
-            if (eq == 0) {
-                atomicAdd(p.counters + 2, 1ull);   // the scan and the refine disagree: a bug
-                p.oneway[g] = -1;
-            } else {
-                int const s2 = max(v2, second);
-                p.oneway[g] = passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(s2), p.sq_lowe, p.sq_dist)
-                                  ? pos * kSub + jl : -1;
-            }
-        }
+    unsigned const um = __ballot_sync(0xffffffffu, live && !certified);
+    unsigned const sm = __ballot_sync(0xffffffffu, survive);
+    if (SIGNED && um != 0) {
+        unsigned long long ub = 0;
+        if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
+        ub = __shfl_sync(0xffffffffu, ub, 0);
+        if (live && !certified) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
     }
+    // statistics: one atomic per CTA
+    __shared__ unsigned s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 0) {
+        if (sm) atomicAdd(&s_cnt[0], __popc(sm));
+        if (um) atomicAdd(&s_cnt[1], __popc(um));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt[0]) atomicAdd(p.counters + 1, static_cast<unsigned long long>(s_cnt[0]));
+    if (threadIdx.x == 1 && s_cnt[1]) atomicAdd(p.counters + 3, static_cast<unsigned long long>(s_cnt[1]));
 }
 
 // ---------------------------------------------------------------- wrap emulation
@@ -203,11 +206,9 @@ __global__ void __launch_bounds__(256) refine_kernel(PostParams p)
 template <bool SIGNED>
 __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
 {
-    // The list length is only known on the device (written by finalize_kernel, which
-    // precedes this launch in stream order); the grid strides over it.
+    // The list length is only known on the device (written by a kernel that precedes this
+    // launch in stream order); the grid strides over it.
     int64_t const nslow = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.counters + 0));
-    if (blockIdx.x == 0 && threadIdx.x == 0 && nslow > 0)
-        atomicAdd(p.counters + 3, static_cast<unsigned long long>(nslow));
     int const lane = threadIdx.x & 31;
     int64_t const nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < nslow; w += nwarps) {
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
             x.c_n = first.c_n;
             x.out_row = pre[0];
             x.item_start = pre[1];
-            x.c_maxnorm2 = 0;
+            x.c_view = first.c_view;
             xjobs[pre[2]] = x;
             int at = pre[0];
             for (int j = seg_first[sgi]; j < seg_first[sgi + 1]; ++j) {
@@ -304,14 +305,14 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
     }
     if (threadIdx.x == 0) {
         ScanJob s;
-        s.q_row = 0; s.q_n = 0; s.c_row = 0; s.c_n = 0; s.c_maxnorm2 = 0;
+        s.q_row = 0; s.q_n = 0; s.c_row = 0; s.c_n = 0; s.c_view = 0;
         s.out_row = run[0];
         s.item_start = run[1];
         xjobs[run[2]] = s;
         meta[0] = run[1];
         meta[1] = run[2];
         meta[2] = run[0];
-        if (run[0] > 0) atomicAdd(counters + 3, static_cast<unsigned long long>(run[0]));
+        if (run[0] > 0) atomicAdd(counters + 5, static_cast<unsigned long long>(run[0]));   // rows of the EXACT pass (cumulative)
     }
 }
 
@@ -332,11 +333,11 @@ __global__ void __launch_bounds__(256) exact_gather_kernel(const ScanJob* __rest
         int const x0 = job_xrow[j];
         for (int e = threadIdx.x; e < cnt * 8; e += blockDim.x) {
             int const s = e >> 3, part = e & 7;
-            int64_t const g = slow_list[job.out_row + s];
-            int64_t const src_row = static_cast<int64_t>(job.q_row) + (g - job.out_row);
+            int64_t const entry = slow_list[job.out_row + s];
+            int64_t const src_row = static_cast<int64_t>(job.q_row) + (surv_row(entry) - job.out_row);
             reinterpret_cast<uint4*>(xpool + (static_cast<int64_t>(x0) + s) * kRowBytes)[part] =
                 __ldg(reinterpret_cast<const uint4*>(pool + src_row * kRowBytes) + part);
-            if (part == 0) xrow_map[x0 + s] = g;
+            if (part == 0) xrow_map[x0 + s] = entry;
         }
     }
 }
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256) verify_big_kernel(PostParams p, const int
     for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
         int4 const rec = big_list[k];
         int64_t const g = (static_cast<int64_t>(rec.y) << 32) | static_cast<unsigned int>(rec.x);
-        ScanJob const job = p.jobs[p.rowres[g].w];
+        ScanJob const job = p.jobs[find_job(p.jobs, p.njobs, g)];
         const uint8_t* q = p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes;
         const uint8_t* c = p.pool + (static_cast<int64_t>(job.c_row) + rec.z) * kRowBytes;
         if (wrapped_ip<false>(q, c) != rec.w)

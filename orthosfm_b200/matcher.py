@@ -311,3 +311,24 @@ class ExhaustiveMatching:
         self._check(self._L.osfm_match_debug_dump_similarity(
             self._h, kind, view_q, view_c, out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(out.size)))
         return out[:, :nc]
+
+    def debug_dump_packed(self, kind: int, view_q: int, view_c: int) -> np.ndarray:
+        """The similarity matrix as the filter epilogue reads it from tensor memory
+        (tcgen05.ld .pack::16b): uint16, truncated to 16 bits, columns in order."""
+        k = 0 if kind == KIND_SIFT_U8 else 1
+        nq = self._sizes[view_q][k]
+        nc = self._sizes[view_c][k]
+        ld = 256 * ((nc + 255) // 256)
+        out = np.zeros((nq, ld // 2), np.uint32)
+        self._check(self._L.osfm_match_debug_dump_packed(
+            self._h, kind, view_q, view_c, out.ctypes.data_as(C.c_void_p), C.c_int64(out.size)))
+        return out.view(np.uint16)[:, :nc]   # little endian: low half = even column
+
+    def debug_trace(self, pairs) -> np.ndarray:
+        """clock64() stamps of CTA 0's pipeline events (see osfm_match_debug_trace)."""
+        pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        out = np.zeros((19, 256, 4), np.int64)
+        self._check(self._L.osfm_match_debug_trace(
+            self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), len(pr),
+            out.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(out.size)))
+        return out

@@ -6,8 +6,17 @@ quantised like convert_descriptor (src/mve/sfm/exhaustive_matching.cc:18-27):
 ``q = floor(255 * clamp(x, 0, 1) + 0.5)`` stored as one byte.
 
 Pure noise produces no consistent matches, so a fraction of every image's
-descriptors is a +-1 LSB perturbed copy of a shared "scene" pool; those are the
-rows that survive the ratio test and the mutual filter.
+descriptors is a perturbed copy of a shared "scene" pool; those are the rows that
+survive the ratio test and the mutual filter.  Two perturbations:
+
+``noise="renorm"``  what a second photograph does: Gaussian noise on the float
+    descriptor, then SIFT's normalise / clamp / normalise and the quantiser again, so
+    every row is a quantised *unit* vector (squared norm 65025 +- a few hundred) and an
+    inner product of 2^16 -- where the reference's 16-bit arithmetic wraps -- is rare.
+    This is what the benchmark uses.
+``noise="lsb"``     +-1 LSB on the quantised bytes without re-normalising.  Not what
+    SIFT produces (norms drift by +-400, every tenth planted pair reaches 2^16), which
+    makes it a good stress test of the wrap handling; the parity tests default to it.
 """
 from __future__ import annotations
 
@@ -30,8 +39,11 @@ def scene_pool(cfg: int, size: int) -> np.ndarray:
     return _normalise_clamp_quantise(np.abs(rng.standard_normal((size, SIFT_DIM), dtype=np.float32)))
 
 
+RENORM_SIGMA = 0.004   # per-dimension noise of a planted copy, in units of the unit vector
+
+
 def sift_view(cfg: int, view: int, n: int, pool: np.ndarray | None = None,
-              planted_fraction: float = 0.25) -> np.ndarray:
+              planted_fraction: float = 0.25, noise: str = "lsb") -> np.ndarray:
     """``n x 128`` uint8 descriptors of image ``view`` (seed = 1000*cfg + view)."""
     rng = np.random.Generator(np.random.MT19937(1000 * cfg + view))
     desc = _normalise_clamp_quantise(np.abs(rng.standard_normal((n, SIFT_DIM), dtype=np.float32)))
@@ -39,15 +51,22 @@ def sift_view(cfg: int, view: int, n: int, pool: np.ndarray | None = None,
         k = min(int(n * planted_fraction), pool.shape[0])
         rows = rng.permutation(n)[:k]
         picks = rng.permutation(pool.shape[0])[:k]
-        noise = rng.integers(-1, 2, size=(k, SIFT_DIM), dtype=np.int16)
-        desc[rows] = np.clip(pool[picks].astype(np.int16) + noise, 0, 255).astype(np.uint8)
+        if noise == "lsb":
+            d = rng.integers(-1, 2, size=(k, SIFT_DIM), dtype=np.int16)
+            desc[rows] = np.clip(pool[picks].astype(np.int16) + d, 0, 255).astype(np.uint8)
+        elif noise == "renorm":
+            x = pool[picks].astype(np.float32) / 255.0
+            x = np.abs(x + RENORM_SIGMA * rng.standard_normal((k, SIFT_DIM), dtype=np.float32))
+            desc[rows] = _normalise_clamp_quantise(x)
+        else:
+            raise ValueError(f"unknown noise model {noise!r}")
     return desc
 
 
 def sift_views(cfg: int, num_views: int, n: int, planted_fraction: float = 0.25,
-               pool_size: int | None = None) -> list[np.ndarray]:
+               pool_size: int | None = None, noise: str = "lsb") -> list[np.ndarray]:
     pool = scene_pool(cfg, pool_size if pool_size is not None else max(n // 2, 1))
-    return [sift_view(cfg, v, n, pool, planted_fraction) for v in range(num_views)]
+    return [sift_view(cfg, v, n, pool, planted_fraction, noise) for v in range(num_views)]
 
 
 def surf_view(cfg: int, view: int, n: int, pool: np.ndarray | None = None,
@@ -84,7 +103,8 @@ def all_pairs(num_views: int) -> np.ndarray:
     return out
 
 
-def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction: float = 0.25):
+def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction: float = 0.25,
+                     noise: str = "lsb"):
     """Same distribution generated on the device with torch (for the large bench
     configurations where 4 GB of numpy randoms would dominate start-up).  Returns
     a ``num_views*n x 128`` uint8 tensor; seeded, but not bit-identical to the
@@ -94,12 +114,14 @@ def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction:
     g = torch.Generator(device=device)
     g.manual_seed(1000 * cfg + 7)
 
-    def make(rows: int) -> "torch.Tensor":
-        x = torch.randn((rows, SIFT_DIM), generator=g, device=device, dtype=torch.float32).abs_()
+    def quantise(x: "torch.Tensor") -> "torch.Tensor":
         x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
         x = x.clamp_max(0.2)
         x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
         return torch.floor(255.0 * x.clamp(0.0, 1.0) + 0.5).to(torch.uint8)
+
+    def make(rows: int) -> "torch.Tensor":
+        return quantise(torch.randn((rows, SIFT_DIM), generator=g, device=device, dtype=torch.float32).abs_())
 
     pool = make(max(n // 2, 1))
     k = min(int(n * planted_fraction), pool.shape[0])
@@ -112,6 +134,11 @@ def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction:
         for v in range(num_views):
             rows = torch.randperm(n, generator=g, device=device)[:k] + v * n
             picks = torch.randperm(pool.shape[0], generator=g, device=device)[:k]
-            noise = torch.randint(-1, 2, (k, SIFT_DIM), generator=g, device=device, dtype=torch.int16)
-            out[rows] = (pool[picks].to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+            if noise == "lsb":
+                d = torch.randint(-1, 2, (k, SIFT_DIM), generator=g, device=device, dtype=torch.int16)
+                out[rows] = (pool[picks].to(torch.int16) + d).clamp_(0, 255).to(torch.uint8)
+            else:
+                x = pool[picks].to(torch.float32) / 255.0
+                x = (x + RENORM_SIGMA * torch.randn((k, SIFT_DIM), generator=g, device=device)).abs_()
+                out[rows] = quantise(x)
     return out

@@ -53,6 +53,27 @@ def test_similarity_matrix_signed_is_exact():
     assert np.array_equal(s, a.astype(np.int64) @ b.astype(np.int64).T)
 
 
+@pytest.mark.parametrize("n1,n2", [(5, 7), (128, 256), (200, 1000)])
+def test_packed_tmem_layout(n1, n2):
+    """The filter epilogue reads the accumulator with tcgen05.ld .pack::16b: it must see the
+    low 16 bits of every similarity, columns in order (low half-word = even column)."""
+    rng = np.random.default_rng(n1 + n2)
+    a = rng.integers(0, 256, (n1, 128), dtype=np.uint8)     # products far beyond 16 bits
+    b = rng.integers(0, 256, (n2, 128), dtype=np.uint8)
+    with matcher([a, b]) as m:
+        s = m.debug_dump_packed(KIND_SIFT_U8, 0, 1)
+    assert np.array_equal(s, ((a.astype(np.int64) @ b.astype(np.int64).T) & 0xffff).astype(np.uint16))
+
+
+def test_packed_tmem_layout_signed():
+    rng = np.random.default_rng(11)
+    a = rng.integers(-127, 128, (150, 64), dtype=np.int8)
+    b = rng.integers(-127, 128, (300, 64), dtype=np.int8)
+    with matcher(surf=[a, b]) as m:
+        s = m.debug_dump_packed(KIND_SURF_S8, 0, 1)
+    assert np.array_equal(s, ((a.astype(np.int64) @ b.astype(np.int64).T) & 0xffff).astype(np.uint16))
+
+
 # ------------------------------------------------------------------ golden vectors
 
 @pytest.mark.parametrize("name", U8_CASES)
@@ -137,6 +158,48 @@ def test_twoway_and_filtered_match_oracle(ora, n1, n2):
     assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
     f12, f21 = ora.remove_inconsistent(o12, o21)
     assert np.array_equal(res.matches_1_2, f12) and np.array_equal(res.matches_2_1, f21)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (300, 1000), (129, 257), (2000, 3000), (4096, 4100)])
+def test_unit_norm_descriptors_take_the_filter(ora, n1, n2):
+    """Quantised unit vectors (what SIFT produces, synth noise="renorm"): almost every row
+    carries the 16-bit norm certificate, so this exercises the packed filter epilogue and the
+    EXACT pass over its survivors rather than the uncertified route."""
+    vs = synth.sift_views(17, 2, max(n1, n2), noise="renorm")
+    a, b = vs[0][:n1], vs[1][:n2]
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        res = m.pairwise_match(0, 1)
+        assert_clean(m)
+        st = m.stats()
+    rows = 2 * (n1 + n2)
+    assert st["slow_rows"] <= 0.05 * rows + 4, st      # few rows without certificate ...
+    assert st["candidate_rows"] < 0.6 * rows + 8, st   # ... and the filter rejects most rows
+    o12, o21 = ora.twoway("u8", a, b, 0.8)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+    f12, f21 = ora.remove_inconsistent(o12, o21)
+    assert np.array_equal(res.matches_1_2, f12) and np.array_equal(res.matches_2_1, f21)
+    if min(n1, n2) >= 1000:
+        assert (f12 >= 0).sum() > 20
+
+
+def test_duplicate_descriptors_and_ties(ora):
+    """Exact duplicates inside and across views: best == second best (ratio 1, or 0/0 = NaN
+    which accepts), ties broken towards the highest index (nearest_neighbor.cc:89)."""
+    vs = synth.sift_views(18, 2, 1200, noise="renorm")
+    a, b = vs[0].copy(), vs[1].copy()
+    b[100:140] = a[100:140]          # identical descriptor in both views
+    b[700:720] = a[100:120]          # ... and a second copy of some of them (tie, later index)
+    a[300:310] = a[100:110]          # duplicates inside a view
+    b[1100] = b[3]
+    for ratio in (0.8, 1.0):
+        opts = MatchingBase.Options()
+        opts.sift_matching_opts.lowe_ratio_threshold = ratio
+        with matcher([a, b], opts=opts) as m:
+            tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+            assert_clean(m)
+        o12, o21 = ora.twoway("u8", a, b, ratio)
+        assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])

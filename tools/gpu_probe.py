@@ -61,9 +61,9 @@ def parity(n1, n2, cfg=2, ratio=0.8):
             "cand": st["candidate_rows"], "slow": st["slow_rows"], "selfcheck": st["self_check_failures"]}
 
 
-def timing(num_views, n, modes=(0, 1, 2)):
+def timing(num_views, n, modes=(0, 1, 2), noise="renorm"):
     import torch
-    views = synth.sift_views(2, num_views, n)
+    views = synth.sift_views(2, num_views, n, noise=noise)
     pairs = synth.all_pairs(num_views)
     r = {}
     with ExhaustiveMatching() as m:
@@ -87,7 +87,8 @@ def timing(num_views, n, modes=(0, 1, 2)):
             r[f"mode{mode}"] = {"scan_ms": round(best["last_scan_ms"], 3), "total_ms": round(best["last_total_ms"], 3),
                                 "Tcmp/s_scan": round(cmp_ / best["last_scan_ms"] / 1e9, 3),
                                 "TOPs_alg": round(cmp_ * 256 / best["last_scan_ms"] / 1e9, 1),
-                                "matches": None if loff is None else int(loff[-1])}
+                                "matches": None if loff is None else int(loff[-1]),
+                                "cand": st["candidate_rows"], "slow": st["slow_rows"]}
         m.debug_set_scan_mode(0)
     return r
 
@@ -104,6 +105,7 @@ if __name__ == "__main__":
     if which in ("all", "timing"):
         step("timing_8x8192", lambda: timing(8, 8192))
         step("timing_36x8192", lambda: timing(36, 8192))
+        step("timing_36x8192_lsb", lambda: timing(36, 8192, modes=(0,), noise="lsb"))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe.json", "w") as f:
         json.dump(out, f, indent=1)

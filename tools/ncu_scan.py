@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from orthosfm_b200 import ExhaustiveMatching, FeatureSet, Viewport, synth
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-views = synth.sift_views(2, nv, 8192)
+noise = sys.argv[2] if len(sys.argv) > 2 else "renorm"
+views = synth.sift_views(2, nv, 8192, noise=noise)
 pairs = synth.all_pairs(nv)
 with ExhaustiveMatching() as m:
     m.init([Viewport(FeatureSet(sift_descriptors=v)) for v in views])
