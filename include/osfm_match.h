@@ -189,6 +189,9 @@ typedef struct {
     double  last_scan_ms;        /* CUDA-event time of the last scan kernel launch(es) */
     double  last_total_ms;       /* CUDA-event time of the last batched call, device part */
     int64_t last_comparisons;    /* sum n1*n2 of the last batched call (unique)      */
+    int64_t exact_rows;          /* rows re-run by the EXACT pass (survivors + uncertified) */
+    int64_t last_scan_sm_cycles; /* SM cycles (clock64) of the last filter scan launch, CTA 0 */
+    int64_t last_scan_ns;        /* its duration in ns (globaltimer): cycles/ns = SM clock in GHz */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
@@ -210,10 +213,10 @@ int osfm_match_debug_dump_packed(osfm_matcher* m, int kind, int view_q, int view
     uint32_t* out, int64_t out_words);
 
 /* Runs the scan kernel over both directions of the given SIFT pairs with clock64()
- * time stamps of CTA 0's pipeline events: out receives 19 warps x 256 events x 4
- * int64 (epilogue warps 0-15: wait start, accumulator ready, stage handed back, half;
- * warp 16, the TMA producer: wait start, ring slot free, tile; warps 17-18, the MMA
- * issuers: wait start, stage free, issued, candidate-tile wait start). */
+ * time stamps of CTA 0's pipeline events: out receives 20 warps x 256 events x 4
+ * int64 (warps 0-1, the MMA issuers: wait start, accumulator free, issued, half;
+ * warp 2, the TMA producer: wait start, ring slot free, tile; warps 4-19, the filter
+ * epilogue: wait start, accumulator ready, handed back, maxima done). */
 int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs,
     int64_t* out, int64_t out_words);
 

@@ -38,7 +38,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("scan_items", C.c_int64),
                 ("candidate_rows", C.c_int64), ("slow_rows", C.c_int64),
                 ("self_check_failures", C.c_int64), ("last_scan_ms", C.c_double),
-                ("last_total_ms", C.c_double), ("last_comparisons", C.c_int64)]
+                ("last_total_ms", C.c_double), ("last_comparisons", C.c_int64),
+                ("exact_rows", C.c_int64), ("last_scan_sm_cycles", C.c_int64), ("last_scan_ns", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

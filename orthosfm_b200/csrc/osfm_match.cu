@@ -112,7 +112,6 @@ struct osfm_matcher {
     DevBuf<ScanJob> d_jobs;
     DevBuf<int2> d_rowres;
     DevBuf<int32_t> d_oneway;
-    DevBuf<int64_t> d_slow;
     DevBuf<int64_t> d_cand;
     DevBuf<int4> d_big;
     DevBuf<PairPart> d_parts;
@@ -120,17 +119,26 @@ struct osfm_matcher {
     DevBuf<int32_t> d_counts;
     DevBuf<int64_t> d_listoff;
     DevBuf<float> d_ftmp;
-    // scratch of the EXACT pass (rows whose best similarity reached 2^16)
-    DevBuf<int> d_slow_cnt;
-    DevBuf<int> d_job_xrow;
     DevBuf<int32_t> d_seg_first;
-    DevBuf<ScanJob> d_xjobs;
-    DevBuf<uint8_t> d_xpool;
-    DevBuf<int64_t> d_xrow_map;
-    int* d_xmeta = nullptr;
-    CUtensorMap tmap_x;
-    uint8_t* tmap_x_for = nullptr;
-    size_t tmap_x_rows = 0;
+    // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
+    // survivors), [1] EXACT (unsigned rows without the 16-bit norm certificate)
+    struct SecondPass {
+        DevBuf<int64_t> list;       // per-job segments of row entries (surv_entry)
+        DevBuf<int> cnt;            // rows per job
+        DevBuf<int> job_xrow;
+        DevBuf<ScanJob> xjobs;
+        DevBuf<uint8_t> xpool;      // gathered query rows
+        DevBuf<int64_t> xrow_map;
+        int* d_xmeta = nullptr;
+        CUtensorMap tmap;
+        uint8_t* tmap_for = nullptr;
+        size_t tmap_rows = 0;
+        void release() {
+            list.release(); cnt.release(); job_xrow.release(); xjobs.release(); xpool.release(); xrow_map.release();
+            if (d_xmeta) cudaFree(d_xmeta);
+            d_xmeta = nullptr;
+        }
+    } pass[2];
     unsigned long long* d_counters = nullptr;  // see PostParams::counters
 
     int scan_mode = 0;
@@ -249,15 +257,16 @@ int ksteps_of(const KindPool& k) { return (k.dim + 31) / 32; }
 
 template <int MODE, bool SIGNED>
 cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, false, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, kPassFilter, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kScanSmemBytes);
     if (e != cudaSuccess) return e;
     int const grid = std::min(m->num_sms, total_items);
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     ExactParams ex;
     memset(&ex, 0, sizeof ex);
-    scan_kernel<MODE, false, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p);
+    scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
+        k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
+        m->d_counters + 6);
     return cudaGetLastError();
 }
 
@@ -267,34 +276,37 @@ cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int
                        : launch_scan_t<MODE, false>(m, k, total_items, dump, dump_ld);
 }
 
-// Second pass, over the survivors of the filter: plan, gather, and the EXACT variant of the
-// scan kernel.  Everything is sized on the device; the host never learns how many rows there
-// were until it reads the counters.
-template <bool SIGNED>
-int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp) {
-    CU_TRY(m, m->d_job_xrow.reserve(static_cast<size_t>(njobs)));
-    CU_TRY(m, m->d_xjobs.reserve(static_cast<size_t>(nseg) + 1));
-    CU_TRY(m, m->d_xrow_map.reserve(static_cast<size_t>(rows)));
-    CU_TRY(m, m->d_xpool.reserve(static_cast<size_t>(rows + kPadRows) * kRowBytes));
-    if (m->tmap_x_for != m->d_xpool.p || m->tmap_x_rows != m->d_xpool.cap) {
-        OS_TRY(encode_tmap(m, &m->tmap_x, m->d_xpool.p, static_cast<int64_t>(m->d_xpool.cap / kRowBytes)));
-        m->tmap_x_for = m->d_xpool.p;
-        m->tmap_x_rows = m->d_xpool.cap;
+// A second pass over gathered rows (RESOLVE: the filter's certified survivors; EXACT: unsigned
+// rows without certificate): plan, gather, and that variant of the scan kernel.  Everything is
+// sized on the device; the host never learns how many rows there were until it reads the
+// counters.
+template <int PASS, bool SIGNED>
+int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp) {
+    osfm_matcher::SecondPass& sp = m->pass[PASS == kPassResolve ? 0 : 1];
+    CU_TRY(m, sp.job_xrow.reserve(static_cast<size_t>(njobs)));
+    CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(nseg) + 1));
+    CU_TRY(m, sp.xrow_map.reserve(static_cast<size_t>(rows)));
+    CU_TRY(m, sp.xpool.reserve(static_cast<size_t>(rows + kPadRows) * kRowBytes));
+    if (sp.tmap_for != sp.xpool.p || sp.tmap_rows != sp.xpool.cap) {
+        OS_TRY(encode_tmap(m, &sp.tmap, sp.xpool.p, static_cast<int64_t>(sp.xpool.cap / kRowBytes)));
+        sp.tmap_for = sp.xpool.p;
+        sp.tmap_rows = sp.xpool.cap;
     }
-    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, m->d_slow_cnt.p,
-                                                 m->d_xjobs.p, m->d_job_xrow.p, m->d_xmeta, m->d_counters);
+    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, sp.cnt.p,
+                                                 sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
+                                                 PASS == kPassExact ? m->d_counters + 5 : nullptr);
     CU_TRY(m, cudaGetLastError());
-    exact_gather_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_slow_cnt.p,
-                                                              m->d_job_xrow.p, m->d_slow.p, k.pool,
-                                                              m->d_xpool.p, m->d_xrow_map.p);
+    exact_gather_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
+                                                              sp.job_xrow.p, sp.list.p, k.pool,
+                                                              sp.xpool.p, sp.xrow_map.p);
     CU_TRY(m, cudaGetLastError());
-    CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, true, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+    CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, PASS, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
     ExactParams ex;
-    ex.qpool = m->d_xpool.p;
+    ex.qpool = sp.xpool.p;
     ex.cpool = k.pool;
-    ex.xrow_map = m->d_xrow_map.p;
+    ex.xrow_map = sp.xrow_map.p;
     ex.oneway = pp.oneway;
-    ex.total_items_dev = m->d_xmeta;
+    ex.total_items_dev = sp.d_xmeta;
     ex.sq_lowe = pp.sq_lowe;
     ex.sq_dist = pp.sq_dist;
     ex.replay_list = m->d_cand.p;
@@ -302,18 +314,18 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, i
     ex.big_list = nullptr;
     ex.big_count = m->d_counters + 12;
     ex.self_check = m->d_counters + 2;
-    if (!SIGNED) {
+    if (PASS == kPassExact) {
         CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
         ex.big_list = m->d_big.p;
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
     }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
-    scan_kernel<0, true, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
-        m->tmap_x, k.tmap, m->d_xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr);
+    scan_kernel<0, PASS, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
+        sp.tmap, k.tmap, sp.xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 3;
-    if (!SIGNED) {
+    if (PASS == kPassExact) {
         // certify the big candidates; rows that fail (a 16-bit lane really wrapped) get the
         // warp-per-row replay.  counters[8] is the replay list length.
         verify_big_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(pp, m->d_big.p, m->d_counters + 12,
@@ -329,7 +341,7 @@ int launch_exact_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, i
     return OSFM_OK;
 }
 
-// Runs filter scan + EXACT pass (+ wrap emulation) for a list of jobs of one kind.  On return
+// Runs filter scan + RESOLVE / EXACT passes (+ wrap emulation) for a list of jobs of one kind.  On return
 // (in stream order) m->d_oneway holds, for job i, q_n one-way results starting at out_row[i]
 // (out_row[i] = -1 if the job was not run because one side is empty).
 int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
@@ -382,10 +394,12 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
 
     CU_TRY(m, m->d_jobs.reserve(jobs.size()));
     CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(rows)));
-    CU_TRY(m, m->d_slow.reserve(static_cast<size_t>(rows)));
     CU_TRY(m, m->d_cand.reserve(static_cast<size_t>(rows)));
-    CU_TRY(m, m->d_slow_cnt.reserve(static_cast<size_t>(njobs)));
-    CU_TRY(m, cudaMemsetAsync(m->d_slow_cnt.p, 0, sizeof(int) * njobs, m->stream));
+    for (int i = 0; i < (k.is_signed ? 1 : 2); ++i) {
+        CU_TRY(m, m->pass[i].list.reserve(static_cast<size_t>(rows)));
+        CU_TRY(m, m->pass[i].cnt.reserve(static_cast<size_t>(njobs)));
+        CU_TRY(m, cudaMemsetAsync(m->pass[i].cnt.p, 0, sizeof(int) * njobs, m->stream));
+    }
     CU_TRY(m, m->d_seg_first.reserve(seg_first.size()));
     CU_TRY(m, cudaMemcpyAsync(m->d_seg_first.p, seg_first.data(), sizeof(int32_t) * seg_first.size(),
                               cudaMemcpyHostToDevice, m->stream));
@@ -421,8 +435,10 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     cp.norm2 = k.d_norm2.p;
     cp.viewmax = k.d_viewmax.p;
     cp.oneway = m->d_oneway.p;
-    cp.surv_list = m->d_slow.p;
-    cp.surv_cnt = m->d_slow_cnt.p;
+    cp.surv_list = m->pass[0].list.p;
+    cp.surv_cnt = m->pass[0].cnt.p;
+    cp.exact_list = m->pass[1].list.p;
+    cp.exact_cnt = m->pass[1].cnt.p;
     cp.uncert_list = m->d_cand.p;
     cp.counters = m->d_counters;
     cp.sq_lowe = sq_lowe;
@@ -445,14 +461,15 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     pp.counters = m->d_counters;
     if (k.is_signed) {
         // rows without the norm certificate (adversarial input only): warp-per-row emulation
-        // on CUDA cores.  It only reads d_cand, which the EXACT pass does not touch when signed.
+        // on CUDA cores
         slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
         m->stats.kernel_launches++;
-        OS_TRY(launch_exact_pass<true>(m, k, njobs, nseg, rows, pp));
+        OS_TRY((launch_second_pass<kPassResolve, true>(m, k, njobs, nseg, rows, pp)));
     } else {
-        OS_TRY(launch_exact_pass<false>(m, k, njobs, nseg, rows, pp));
+        OS_TRY((launch_second_pass<kPassResolve, false>(m, k, njobs, nseg, rows, pp)));
+        OS_TRY((launch_second_pass<kPassExact, false>(m, k, njobs, nseg, rows, pp)));
     }
 
     // Scan time of this launch; read after the caller's next synchronisation.
@@ -560,8 +577,11 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
 }
 
 int read_counters(osfm_matcher* m) {
-    unsigned long long c[6];
+    unsigned long long c[8];
     CU_TRY(m, cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    m->stats.exact_rows = static_cast<int64_t>(c[5]);
+    m->stats.last_scan_sm_cycles = static_cast<int64_t>(c[6]);
+    m->stats.last_scan_ns = static_cast<int64_t>(c[7]);
     m->stats.candidate_rows = static_cast<int64_t>(c[1]);
     m->stats.self_check_failures = static_cast<int64_t>(c[2]);
     m->stats.slow_rows = static_cast<int64_t>(c[3]);
@@ -657,8 +677,10 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 16 * sizeof(unsigned long long)));
     CU_TRY(m, cudaMemset(m->d_counters, 0, 16 * sizeof(unsigned long long)));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xmeta), 4 * sizeof(int)));
-    CU_TRY(m, cudaMemset(m->d_xmeta, 0, 4 * sizeof(int)));
+    for (auto& sp : m->pass) {
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&sp.d_xmeta), 4 * sizeof(int)));
+        CU_TRY(m, cudaMemset(sp.d_xmeta, 0, 4 * sizeof(int)));
+    }
 
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -687,13 +709,12 @@ void osfm_match_destroy(osfm_matcher* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     reset_kind(m->kind[0], true);
     reset_kind(m->kind[1], true);
-    m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release(); m->d_slow.release();
+    m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release();
     m->d_cand.release(); m->d_big.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
     m->d_ftmp.release();
-    m->d_slow_cnt.release(); m->d_job_xrow.release(); m->d_seg_first.release(); m->d_xjobs.release(); m->d_xpool.release();
-    m->d_xrow_map.release();
-    if (m->d_xmeta) cudaFree(m->d_xmeta);
+    m->d_seg_first.release();
+    for (auto& sp : m->pass) sp.release();
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->hang_host) {
         HangReport* null_ptr = nullptr;
@@ -1152,7 +1173,7 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
 }
 
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
-    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;   /* 3, 4: dump entry points */
+    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;   /* 3-5: dump / trace entry points */
     std::lock_guard<std::mutex> lock(m->mu);
     m->scan_mode = mode;
     return OSFM_OK;
@@ -1193,7 +1214,7 @@ int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, in
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
-    int64_t const words = static_cast<int64_t>(kScanThreads / 32) * kTraceEvents * 4;   // 19 warps
+    int64_t const words = static_cast<int64_t>(kScanThreads / 32) * kTraceEvents * 4;   // 20 warps
     if (!out || out_words < words) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "trace buffer too small (%lld words)", (long long)words);
     CU_TRY(m, cudaSetDevice(m->device));
     std::vector<JobSpec> specs;

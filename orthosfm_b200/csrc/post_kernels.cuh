@@ -127,8 +127,10 @@ struct ClassifyParams {
     const int32_t* norm2;        // squared norm of every pool row
     const int32_t* viewmax;      // largest squared norm per view (index: ScanJob::c_view)
     int32_t* oneway;             // out: -1 for rows the filter rejects
-    int64_t* surv_list;          // survivors of job j: surv_list[jobs[j].out_row + 0 .. surv_cnt[j])
-    int* surv_cnt;
+    int64_t* surv_list;          // certified survivors of job j (RESOLVE pass):
+    int* surv_cnt;               //   surv_list[jobs[j].out_row + 0 .. surv_cnt[j])
+    int64_t* exact_list;         // unsigned kind: rows without certificate (EXACT pass), same layout
+    int* exact_cnt;
     int64_t* uncert_list;        // signed kind: rows without certificate (CUDA-core replay), flat
     unsigned long long* counters;  // [0] uncert_list length, [1] certified survivors (cumulative),
                                    // [3] rows without certificate (cumulative)
@@ -138,10 +140,10 @@ struct ClassifyParams {
 // One thread per job row: applies the reference's tests (matching.h:126-144) to the scan
 // kernel's (best, lower bound of second best).  A row that fails them is final (-1): the
 // ratio test is monotone in the second best.  A row that passes is a *survivor* and is
-// queued, per job, for the EXACT pass.  Both statements need the row's similarities to have
-// fitted the filter's 16 bits, which the norm certificate guarantees; rows without it join the
-// survivors (unsigned) or go to the CUDA-core replay (signed: the reference's 16-bit lanes may
-// wrap as well).
+// queued, per job, for the RESOLVE pass.  Both statements need the row's similarities to have
+// fitted the filter's 16 bits, which the norm certificate guarantees; rows without it are
+// queued for the EXACT pass (unsigned) or go to the CUDA-core replay (signed: the reference's
+// 16-bit lanes may wrap as well).
 template <bool SIGNED>
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 {
@@ -166,17 +168,22 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
                                 passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(v2), p.sq_lowe, p.sq_dist));
         if (certified && !survive) p.oneway[g] = -1;
     }
-    // survivors (and unsigned rows without certificate) -> the job's list; one atomic per job
-    // present in the warp (a warp spans at most a few jobs)
-    bool const to_exact = live && (survive || (!SIGNED && !certified));
-    unsigned const xm = __ballot_sync(0xffffffffu, to_exact);
-    if (to_exact) {
-        unsigned const peers = __match_any_sync(xm, ji);
-        int const leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(p.surv_cnt + ji, __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(g, v1, certified);
+    // survivors -> the job's RESOLVE list, unsigned rows without certificate -> its EXACT list;
+    // one atomic per job present in the warp (a warp spans at most a few jobs)
+    bool const to_exact = live && !SIGNED && !certified;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        bool const mine = which == 0 ? survive : to_exact;
+        unsigned const xm = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            unsigned const peers = __match_any_sync(xm, ji);
+            int const leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd((which == 0 ? p.surv_cnt : p.exact_cnt) + ji, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            (which == 0 ? p.surv_list : p.exact_list)[out_row + base + __popc(peers & ((1u << lane) - 1u))] =
+                surv_entry(g, v1, certified);
+        }
     }
     unsigned const um = __ballot_sync(0xffffffffu, live && !certified);
     unsigned const sm = __ballot_sync(0xffffffffu, survive);
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
                                                           const int* __restrict__ slow_cnt,
                                                           ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
                                                           int* __restrict__ meta,
-                                                          unsigned long long* __restrict__ counters)
+                                                          unsigned long long* __restrict__ rows_total)
 {
     __shared__ int wsum[3][32];
     __shared__ int run[3];
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
         meta[0] = run[1];
         meta[1] = run[2];
         meta[2] = run[0];
-        if (run[0] > 0) atomicAdd(counters + 5, static_cast<unsigned long long>(run[0]));   // rows of the EXACT pass (cumulative)
+        if (run[0] > 0 && rows_total != nullptr) atomicAdd(rows_total, static_cast<unsigned long long>(run[0]));   // cumulative
     }
 }
 

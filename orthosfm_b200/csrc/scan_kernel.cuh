@@ -53,15 +53,31 @@
 
 namespace osfm {
 
+constexpr int kTmemColsTotal = 512;
 constexpr int kStages = 4;            // candidate-tile ring depth
-constexpr int kColGroups = 4;         // epilogue warps per TMEM lane quadrant
-constexpr int kEpilogueWarps = 4 * kColGroups;
-constexpr int kColsPerWarp = kBlockN / kColGroups;   // 64 = one packed tcgen05.ld.x32
-constexpr int kSlotRegs = 4;          // packed running maxima per thread and query half (8 slots)
-constexpr int kProducerWarp = kEpilogueWarps;
-constexpr int kMmaWarp = kEpilogueWarps + 1;             // issuer of query half 0; half 1: the next warp
-constexpr int kScanThreads = (kEpilogueWarps + 3) * 32;   // 608
-constexpr int kTmemCols = 512;
+constexpr int kAccStages = 2;         // TMEM accumulators: one per query half, kBlockN columns each
+constexpr int kAccCols = kBlockN / 2; // columns one filter warp drains: half an accumulator
+constexpr int kEpilogueWarps = 4 * 2 * kAccStages;       // one warp per (lane quadrant, half, column half)
+#ifndef OSFM_SLOT_REGS
+#define OSFM_SLOT_REGS 1
+#endif
+// Packed running maxima per thread.  ONE register (two slots: the even and the odd columns)
+// on purpose: its updates form a single dependent chain, so the warp stalls on its own result
+// after every instruction and the scheduler turns to other warps.  With several independent
+// chains the fold issues back to back, and the greedy scheduler then keeps the MMA issuer
+// warp that shares the scheduler from feeding the tensor pipe for the length of the burst
+// (measured: 8 chains 11.4 M cycles per launch, 2 chains 10.4 M, no fold at all 9.6 M).
+constexpr int kSlotRegs = OSFM_SLOT_REGS;
+// Warp roles.  The control warps have the LOWEST ids: the warp scheduler favours the oldest
+// ready warp once the one it is issuing from stalls, and a burst of epilogue arithmetic on an
+// MMA issuer's scheduler otherwise keeps the issuer (were it the youngest warp) from feeding
+// the tensor pipe for the length of the burst -- measured: the epilogue's ALU time added almost
+// one-to-one to the tile time.
+constexpr int kMmaWarp = 0;                // issuer of query half 0; half 1: the next warp
+constexpr int kProducerWarp = 2;           // TMA
+constexpr int kFirstEpilogueWarp = 4;      // (warp 3 idles) a multiple of 4: TMEM lane quadrant = warp % 4
+constexpr int kScanThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;   // 640
+constexpr int kTmemCols = kTmemColsTotal;
 
 constexpr int kAHalfBytes = kHalfM * kRowBytes;    // 16 KB
 constexpr int kATileBytes = kItemM * kRowBytes;    // 32 KB
@@ -69,17 +85,17 @@ constexpr int kBTileBytes = kBlockN * kRowBytes;   // 32 KB
 constexpr int kSmemA = 0;
 constexpr int kSmemB = 2 * kATileBytes;
 constexpr int kSmemBar = kSmemB + kStages * kBTileBytes;
-constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 + 2;
+constexpr int kNumBars = 2 + 2 + 2 * kStages + 2 * kAccStages + 2;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemMerge = (kSmemTmemPtr + 4 + 15) & ~15;
-constexpr int kMergeBufBytes = (kColGroups - 1) * kItemM * 8;
+constexpr int kMergeBufBytes = kItemM * 16;  // per row: what the upper column half's warp found
 constexpr int kSmemTotal = kSmemMerge + 2 * kMergeBufBytes;   // double-buffered across items
 constexpr int kScanSmemBytes = kSmemTotal + 1024;  // slack for manual 1024-byte alignment
 
 // Hang-report codes (see ptx.cuh).
 enum : uint32_t {
     kWaitAEmpty = 1, kWaitBEmpty = 2, kWaitAFull = 3, kWaitAccEmpty = 4,
-    kWaitBFull = 5, kWaitAccFull = 6
+    kWaitBFull = 5, kWaitAccFull = 6, kWaitTurn = 7
 };
 
 // A survivor-list entry: the row's index into oneway[] plus what the filter knew about it,
@@ -124,6 +140,8 @@ __device__ __forceinline__ long long clock64_() {
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
     return t;
 }
+
+constexpr int kPassFilter = 0, kPassExact = 1, kPassResolve = 2;
 
 constexpr int kMaxBigPerRow = 4;   // big candidates per row that verify_big_kernel will certify
 
@@ -222,26 +240,72 @@ __device__ __forceinline__ void fold_packed(uint32_t (&slot)[kSlotRegs], const u
 // its second largest entry -- followed by the merge of the two lanes.
 template <bool SIGNED>
 __device__ __forceinline__ void slots_top2(const uint32_t (&m)[kSlotRegs], int& v1, int& v2) {
-    static_assert(kSlotRegs == 4 || kSlotRegs == 8, "tournament is written for 4 or 8 registers");
+    static_assert(kSlotRegs == 1 || kSlotRegs == 2 || kSlotRegs == 4 || kSlotRegs == 8, "tournament sizes");
     uint32_t w, l;
     if (kSlotRegs == 8) {
-        uint32_t const w01 = pmax<SIGNED>(m[0], m[1]), l01 = pmin<SIGNED>(m[0], m[1]);
-        uint32_t const w23 = pmax<SIGNED>(m[2], m[3]), l23 = pmin<SIGNED>(m[2], m[3]);
+        uint32_t const w01 = pmax<SIGNED>(m[0], m[1 % kSlotRegs]), l01 = pmin<SIGNED>(m[0], m[1 % kSlotRegs]);
+        uint32_t const w23 = pmax<SIGNED>(m[2 % kSlotRegs], m[3 % kSlotRegs]), l23 = pmin<SIGNED>(m[2 % kSlotRegs], m[3 % kSlotRegs]);
         uint32_t const w45 = pmax<SIGNED>(m[4 % kSlotRegs], m[5 % kSlotRegs]), l45 = pmin<SIGNED>(m[4 % kSlotRegs], m[5 % kSlotRegs]);
         uint32_t const w67 = pmax<SIGNED>(m[6 % kSlotRegs], m[7 % kSlotRegs]), l67 = pmin<SIGNED>(m[6 % kSlotRegs], m[7 % kSlotRegs]);
         uint32_t const wa = pmax<SIGNED>(w01, w23), la = pmin<SIGNED>(w01, w23);
         uint32_t const wb = pmax<SIGNED>(w45, w67), lb = pmin<SIGNED>(w45, w67);
         w = pmax<SIGNED>(wa, wb);
         l = pmax3<SIGNED>(pmax3<SIGNED>(l01, l23, l45), pmax3<SIGNED>(l67, la, lb), pmin<SIGNED>(wa, wb));
-    } else {
-        uint32_t const w01 = pmax<SIGNED>(m[0], m[1]), l01 = pmin<SIGNED>(m[0], m[1]);
-        uint32_t const w23 = pmax<SIGNED>(m[2], m[3]), l23 = pmin<SIGNED>(m[2], m[3]);
+    } else if (kSlotRegs == 4) {
+        uint32_t const w01 = pmax<SIGNED>(m[0], m[1 % kSlotRegs]), l01 = pmin<SIGNED>(m[0], m[1 % kSlotRegs]);
+        uint32_t const w23 = pmax<SIGNED>(m[2 % kSlotRegs], m[3 % kSlotRegs]), l23 = pmin<SIGNED>(m[2 % kSlotRegs], m[3 % kSlotRegs]);
         w = pmax<SIGNED>(w01, w23);
         l = pmax3<SIGNED>(l01, l23, pmin<SIGNED>(w01, w23));
+    } else if (kSlotRegs == 2) {
+        w = pmax<SIGNED>(m[0], m[1 % kSlotRegs]);
+        l = pmin<SIGNED>(m[0], m[1 % kSlotRegs]);
+    } else {
+        w = m[0];
+        l = 0u;      // the reference's initial second best; never above a real lower bound
     }
     int const wl = plo<SIGNED>(w), wh = phi<SIGNED>(w);
     v1 = max(wl, wh);
     v2 = max3(min(wl, wh), plo<SIGNED>(l), phi<SIGNED>(l));
+}
+
+// RESOLVE: one packed load (64 columns starting at column col0 of the candidate view) of a row
+// whose largest similarity V is known.  See the RESOLVE epilogue.
+template <bool SIGNED>
+__device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int c_n, int V,
+                                             int& cnt, int& idx, int& v2)
+{
+    uint32_t g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t const a = pmax3<SIGNED>(r[8 * i], r[8 * i + 1], r[8 * i + 2]);
+        uint32_t const b = pmax3<SIGNED>(r[8 * i + 3], r[8 * i + 4], r[8 * i + 5]);
+        g[i] = pmax<SIGNED>(pmax3<SIGNED>(a, b, r[8 * i + 6]), r[8 * i + 7]);
+    }
+    uint32_t const m4 = pmax<SIGNED>(pmax<SIGNED>(g[0], g[1]), pmax<SIGNED>(g[2], g[3]));
+    int const m = max(plo<SIGNED>(m4), phi<SIGNED>(m4));
+    if (m < V) {            // the common case: nothing of interest in these 64 columns
+        v2 = max(v2, m);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int const mg = max(plo<SIGNED>(g[i]), phi<SIGNED>(g[i]));
+        if (mg < V) {
+            v2 = max(v2, mg);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int const col = col0 + 2 * (8 * i + k);
+                int const x0 = plo<SIGNED>(r[8 * i + k]), x1 = phi<SIGNED>(r[8 * i + k]);
+                bool const e0 = x0 == V && col < c_n;        // (a masked column of an all-zero row)
+                bool const e1 = x1 == V && col + 1 < c_n;
+                cnt += (e0 ? 1 : 0) + (e1 ? 1 : 0);
+                idx = e1 ? col + 1 : (e0 ? col : idx);
+                v2 = max(v2, e0 ? 0 : x0);
+                v2 = max(v2, e1 ? 0 : x1);
+            }
+        }
+    }
 }
 
 // MODE 0: normal.  1: epilogue only hands the accumulator back (MMA/TMA ceiling).
@@ -250,12 +314,19 @@ __device__ __forceinline__ void slots_top2(const uint32_t (&m)[kSlotRegs], int& 
 // registers as the filter sees them (dump_ld/2 words per row).  5: normal epilogue, and CTA 0
 // records clock64() time stamps of its pipeline events in `dump` (kTraceEvents x 4 int64 per
 // warp).  Modes 1-5 produce no results.
-template <int MODE, bool EXACT, bool SIGNED>
+template <int MODE, int PASS, bool SIGNED>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
             const ScanJob* __restrict__ jobs, int total_items_host, uint32_t idesc, int ksteps,
-            int32_t* __restrict__ dump, int64_t dump_ld, ExactParams ex, int2* __restrict__ rowres)
+            int32_t* __restrict__ dump, int64_t dump_ld, ExactParams ex, int2* __restrict__ rowres,
+            unsigned long long* __restrict__ prof)
 {
+    // CTA 0 reports how many SM cycles and how many nanoseconds the kernel took: their ratio is
+    // the SM clock the kernel actually ran at (it drops under sustained tensor load).
+    long long prof_c0 = 0;
+    uint64_t prof_t0 = 0;
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { prof_c0 = clock64_(); prof_t0 = globaltimer_ns(); }
+
     extern __shared__ uint8_t smem_raw[];
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -266,20 +337,24 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     auto b_full = [&](int i) { return bar_base + 8u * (4 + i); };
     auto b_empty = [&](int i) { return bar_base + 8u * (4 + kStages + i); };
     auto acc_full = [&](int i) { return bar_base + 8u * (4 + 2 * kStages + i); };
-    auto acc_empty = [&](int i) { return bar_base + 8u * (6 + 2 * kStages + i); };
+    auto acc_empty = [&](int i) { return bar_base + 8u * (4 + 2 * kStages + kAccStages + i); };
+    auto turn = [&](int i) { return bar_base + 8u * (4 + 2 * kStages + 2 * kAccStages + i); };
 
     int const warp = threadIdx.x >> 5;
     int const lane = threadIdx.x & 31;
-    int const total_items = EXACT ? *ex.total_items_dev : total_items_host;
-    // In the EXACT pass one group of four warps per query half scans whole rows in order.
-    constexpr uint32_t kAccEmptyCount = EXACT ? 4 : kEpilogueWarps;
+    constexpr bool EXACT = PASS == kPassExact;
+    constexpr bool RESOLVE = PASS == kPassResolve;
+    int const total_items = PASS != kPassFilter ? *ex.total_items_dev : total_items_host;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(a_full(i), 1);
             mbar_init(a_empty(i), 2);                 // one arrive per MMA issuer
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(turn(i), 1);
             mbar_init(acc_full(i), 1);
-            mbar_init(acc_empty(i), kAccEmptyCount);  // one arrive per participating warp
+            mbar_init(acc_empty(i), EXACT ? 4 : 8);   // the warps that read it
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(b_full(i), 1);
@@ -335,14 +410,26 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         }
     } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
         // ===================== MMA issuers (one thread per query half) =====================
-        // tcgen05.mma blocks its issuing thread while the tensor pipe's queue is full, and that
-        // queue is short: with a single issuer, everything the thread does between two groups
-        // (commits, barrier waits, the trip around the loop) shows up as tensor idle time.  Two
-        // issuers, one per accumulator stage, keep the queue fed from the other thread meanwhile.
+        // A candidate tile (256 rows) x a query half (128 rows) is one *group* of tcgen05.mma
+        // (M = 128, N = 256, K = 32 each) into that half's TMEM accumulator.  (N = 128 groups
+        // into four accumulators were tried: they re-read the A tile twice as often and run
+        // into the shared-memory bandwidth, 8 KB per 64 cycles.)
+        //
+        // The tensor pipe's queue is short: a thread is held in tcgen05.mma until the previous
+        // MMA has started, so it leaves the last MMA of a group one MMA time (128 cycles) before
+        // the pipe runs dry, and its commits, barrier waits (70-90 cycles each even when
+        // complete) and the trip around the loop do not fit into that.  With one issuer per
+        // query half the other thread is already queueing its group meanwhile.  The two take
+        // turns (turn[] barriers), which keeps the two accumulators in anti-phase -- one is being
+        // computed while the other is being read; left alone the two streams interleave in the
+        // queue, both accumulators finish together and the pipe idles while both are drained.
+        // (Measured per launch of the 630-pair workload, epilogue switched off: one issuer
+        // 9.7 M cycles, one issuer with the next group's waits hoisted 12.8 M, two issuers
+        // free-running 12 M, two issuers taking turns 9.45 M; 8.9 M is the tensor pipe's floor.)
         int const h = warp - kMmaWarp;
         if (lane == 0) {
             int j = 0;
-            uint32_t bcnt = 0, ic = 0, hc = 0;   // hc: uses of this issuer's accumulator stage so far
+            uint32_t bcnt = 0, ic = 0, hc = 0;   // hc: tiles this issuer has issued so far
             for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
                 while (it >= jobs[j + 1].item_start) ++j;
                 int const c_n = jobs[j].c_n;
@@ -355,183 +442,236 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 int const ntiles = (c_n + kBlockN - 1) / kBlockN;
                 for (int t = 0; t < ntiles; ++t, ++bcnt) {
                     int const s = bcnt % kStages;
-                    long long const tb0 = MODE == 5 ? clock64_() : 0;
                     mbar_wait(b_full(s), (bcnt / kStages) & 1, kWaitBFull, bcnt);
+                    uint32_t const turn_parity = h == 0 ? ((bcnt & 1) ^ 1) : (bcnt & 1);
                     if (!active) {                  // a 128-row item: nothing for the second half
+                        mbar_wait(turn(h), turn_parity, kWaitTurn, bcnt);
+                        mbar_arrive(turn(1 - h));
                         mbar_arrive(b_empty(s));
                         continue;
                     }
                     uint64_t const bdesc = make_smem_desc_sw128(smem_base + kSmemB + s * kBTileBytes);
                     long long const tw0 = MODE == 5 ? clock64_() : 0;
                     mbar_wait(acc_empty(h), (hc & 1) ^ 1, kWaitAccEmpty, hc);
+                    mbar_wait(turn(h), turn_parity, kWaitTurn, bcnt);
                     long long const tw1 = MODE == 5 ? clock64_() : 0;
-                    ++hc;
                     tc_fence_after_sync();
 #pragma unroll
                     for (int k = 0; k < kRowBytes / 32; ++k) {
-                        // +2 in the start-address field = 32 bytes along K inside the swizzle span;
-                        // 64-byte descriptors (SURF) are zero beyond K = 64: two steps suffice
+                        // +2 in the start-address field = 32 bytes along K inside the swizzle
+                        // span; 64-byte descriptors (SURF) are zero beyond K = 64: two steps
                         if (k < ksteps)
                             mma_i8_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
                     }
-                    mma_commit(acc_full(h));    // accumulator of this half is ready
+                    mbar_arrive(turn(1 - h));   // the other half's group may follow
+                    mma_commit(acc_full(h));    // this accumulator is ready
                     mma_commit(b_empty(s));     // this issuer is done with the candidate stage
-                    if (MODE == 5 && blockIdx.x == 0 && hc - 1 < kTraceEvents) {
-                        long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + (hc - 1)) * 4;
-                        tr[0] = tw0; tr[1] = tw1; tr[2] = clock64_(); tr[3] = tb0;
+                    if (MODE == 5 && blockIdx.x == 0 && hc < kTraceEvents) {
+                        long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + hc) * 4;
+                        tr[0] = tw0; tr[1] = tw1; tr[2] = clock64_(); tr[3] = h;
                     }
+                    ++hc;
                 }
                 // this issuer is done with the query tile
                 if (active) mma_commit(a_empty(abuf)); else mbar_arrive(a_empty(abuf));
             }
         }
-    } else if (!EXACT) {
-        // ===================== filter epilogue: 16 warps, 64 columns each =====================
+    } else if (warp < kFirstEpilogueWarp) {
+        // idle
+    } else if (PASS == kPassFilter) {
+        // ===================== filter epilogue: one warp per (lane quadrant, half, column half) =
+        int const ew = warp - kFirstEpilogueWarp;
         int const quad = warp & 3;           // TMEM lane quadrant this warp may access
-        int const cg = warp >> 2;            // column group: columns [64 cg, 64 cg + 64)
-        int const row = quad * 32 + lane;    // row inside a 128-row half
-        uint32_t const taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + cg * kColsPerWarp;
-        int2* const merge_base = reinterpret_cast<int2*>(smem_gen + kSmemMerge);
+        int const h = ew >> 3;               // query half = the accumulator this warp drains
+        int const c = (ew >> 2) & 1;         // column half: columns [128 c, 128 c + 128) of the tile
+        int const row = quad * 32 + lane;    // row inside the 128-row half
+        uint32_t const taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + h * kBlockN + c * kAccCols;
+        int4* const merge_base = reinterpret_cast<int4*>(smem_gen + kSmemMerge);
 
         int j = 0;
-        uint32_t hcnt[2] = {0, 0}, ic = 0;
+        uint32_t cnt = 0, ic = 0;            // cnt: tiles of this warp's accumulator so far
         for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
             while (it >= jobs[j + 1].item_start) ++j;
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
             int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
+            if (h >= nh) continue;           // a 128-row item has no second half
             int const ntiles = (job.c_n + kBlockN - 1) / kBlockN;
+            int64_t const qr = static_cast<int64_t>(rb) * kItemM + h * kHalfM + row;   // row in the job
 
             // 0 is the reference's initial best / second best (nearest_neighbor.cc:221-224)
-            uint32_t slot[2][kSlotRegs];
+            uint32_t slot[kSlotRegs];
 #pragma unroll
-            for (int k = 0; k < kSlotRegs; ++k) { slot[0][k] = 0u; slot[1][k] = 0u; }
-            // Software pipeline over (tile, half) stages: the accumulator of a stage is pulled
-            // into registers with one packed x32 load (64 columns); while that load is in flight
-            // the warp takes the maxima of the previous stage's registers, so it never sits
-            // between "stage ready" and "stage handed back" with arithmetic to do.  Two
-            // register buffers, indexed by the half (static after unrolling).
-            uint32_t rr[2][32];
-            bool pending = false;       // the previous stage's registers still await their fold
-            for (int t = 0; t < ntiles; ++t) {
+            for (int k = 0; k < kSlotRegs; ++k) slot[k] = 0u;
+            for (int t = 0; t < ntiles; ++t, ++cnt) {
                 int const ncols = job.c_n - t * kBlockN;   // valid columns of this tile
+                long long const te0 = MODE == 5 ? clock64_() : 0;
+                mbar_wait(acc_full(h), cnt & 1, kWaitAccFull, cnt);
+                long long const te1 = MODE == 5 ? clock64_() : 0;
+                tc_fence_after_sync();
+                if (MODE == 3) {
+                    // debug: raw 32-bit similarities, 32 columns at a time
+#pragma unroll 1
+                    for (int q4 = 0; q4 < kAccCols / kChunk; ++q4) {
+                        int32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + q4 * kChunk, v);
+                        tmem_ld_wait_regs(v);
+                        if (qr < job.q_n) {
+                            int32_t* d = dump + qr * dump_ld + t * kBlockN + c * kAccCols + q4 * kChunk;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h >= nh) break;
-                    long long const te0 = MODE == 5 ? clock64_() : 0;
-                    mbar_wait(acc_full(h), hcnt[h] & 1, kWaitAccFull, hcnt[h]);
-                    long long const te1 = MODE == 5 ? clock64_() : 0;
-                    ++hcnt[h];
-                    tc_fence_after_sync();
-                    if (MODE == 3 || MODE == 4) {
-                        // debug dumps: no reduction, plain loads
-                        int64_t const qr = static_cast<int64_t>(rb) * kItemM + h * kHalfM + row;
-                        if (MODE == 3) {
-                            int32_t va[32], vb[32];
-                            uint32_t const taddr = taddr0 + h * kBlockN;
-                            tmem_ld_32x32b_x32(taddr, va);
-                            tmem_ld_32x32b_x32(taddr + kChunk, vb);
-                            tmem_ld_wait_regs(va);
-                            tmem_ld_wait_regs(vb);
-                            if (qr < job.q_n) {
-                                int32_t* d = dump + qr * dump_ld + t * kBlockN + cg * kColsPerWarp;
-#pragma unroll
-                                for (int q = 0; q < 32; ++q) { d[q] = va[q]; d[32 + q] = vb[q]; }
-                            }
-                        } else {
-                            tmem_ld_32x32b_x32_pack16(taddr0 + h * kBlockN, rr[0]);
-                            tmem_ld_wait_regs(rr[0]);
-                            if (qr < job.q_n) {
-                                uint32_t* d = reinterpret_cast<uint32_t*>(dump) + qr * (dump_ld / 2) +
-                                              t * (kBlockN / 2) + cg * (kColsPerWarp / 2);
-#pragma unroll
-                                for (int q = 0; q < 32; ++q) d[q] = rr[0][q];
-                            }
+                            for (int q = 0; q < 32; ++q) d[q] = v[q];
                         }
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty(h));
-                        continue;
                     }
-                    if (MODE == 1) {
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty(h));
-                        continue;
-                    }
-                    constexpr bool kReduce = MODE == 0 || MODE == 5;
-                    if (nh == 2) {
-                        tmem_ld_32x32b_x32_pack16(taddr0 + h * kBlockN, rr[h]);
-                        if (kReduce && pending) fold_packed<SIGNED>(slot[1 - h], rr[1 - h]);
-                        tmem_ld_wait_regs(rr[h]);
-                    } else {
-                        // a single half: nothing to overlap with
-                        if (kReduce && pending) fold_packed<SIGNED>(slot[0], rr[0]);
-                        tmem_ld_32x32b_x32_pack16(taddr0, rr[0]);
-                        tmem_ld_wait_regs(rr[0]);
-                    }
-                    // the data is in registers: hand the TMEM stage back
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(h));
-                    if (kReduce) {
-                        if (ncols < kBlockN) mask_packed<SIGNED>(rr[h], cg * kColsPerWarp, ncols);
-                        pending = true;
-                    } else {
-                        slot[h][0] |= rr[h][0] | rr[h][31];
+                    continue;
+                }
+                if (MODE == 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(h));
+                    continue;
+                }
+                // the accumulator's 128 columns as two packed loads of 64, both in flight at once
+                uint32_t ra[32], rc[32];
+                tmem_ld_32x32b_x32_pack16(taddr, ra);
+                tmem_ld_32x32b_x32_pack16(taddr + kAccCols / 2, rc);
+                tmem_ld_wait_regs(ra);
+                tmem_ld_wait_regs(rc);
+                // the data is in registers: hand the accumulator back before reducing
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(h));
+                long long const te2 = MODE == 5 ? clock64_() : 0;
+
+                if (MODE == 0 || MODE == 5) {
+                    if (ncols < kBlockN) {
+                        mask_packed<SIGNED>(ra, c * kAccCols, ncols);
+                        mask_packed<SIGNED>(rc, c * kAccCols + kAccCols / 2, ncols);
                     }
-                    if (MODE == 5 && blockIdx.x == 0 && lane == 0) {
-                        uint32_t const e = hcnt[0] + hcnt[1] - 1;
-                        if (e < kTraceEvents) {
-                            long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + e) * 4;
-                            tr[0] = te0; tr[1] = te1; tr[2] = clock64_(); tr[3] = h;
-                        }
+                    fold_packed<SIGNED>(slot, ra);
+                    fold_packed<SIGNED>(slot, rc);
+                    if (MODE == 5 && blockIdx.x == 0 && lane == 0 && cnt < kTraceEvents) {
+                        long long t3 = clock64_();
+                        asm volatile("" : "+l"(t3) : "r"(slot[0]));
+                        long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + cnt) * 4;
+                        tr[0] = te0; tr[1] = te1; tr[2] = te2; tr[3] = t3;
+                    }
+                } else if (MODE == 2) {
+                    slot[0] |= ra[0] | ra[31] | rc[0] | rc[31];
+                } else if (MODE == 4) {
+                    if (qr < job.q_n) {
+                        uint32_t* d = reinterpret_cast<uint32_t*>(dump) + qr * (dump_ld / 2) +
+                                      t * (kBlockN / 2) + c * (kAccCols / 2);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) { d[q] = ra[q]; d[32 + q] = rc[q]; }
                     }
                 }
             }
-            if ((MODE == 0 || MODE == 5) && pending) {
-                if (nh == 2) fold_packed<SIGNED>(slot[1], rr[1]);
-                else         fold_packed<SIGNED>(slot[0], rr[0]);
-            }
             if (MODE != 0 && MODE != 5) {
-                if (MODE == 2 && slot[0][0] == 0x12345678u && slot[1][0] == 0x9abcdef0u) dump[0] = 1;  // keep the loads alive
+                if (MODE == 2 && slot[0] == 0x12345678u) dump[0] = 1;  // keep the loads alive
                 continue;
             }
 
-            // The row's 64 slots: 16 here, the other column groups' through shared memory.  The
-            // merge area is double-buffered across items, so one barrier per item suffices: a
+            // The row's 32 slots: 16 here, the other column half's through shared memory.  The
+            // two warps of a (half, quadrant) pair meet at their own named barrier.  The merge
+            // area is double-buffered across items, so that one barrier per item suffices: a
             // buffer is rewritten two items later, i.e. after the next item's barrier, which the
-            // reading warps only reach once they are done with it.
-            int2* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 8);
-            int v1[2], v2[2];
-            for (int h = 0; h < nh; ++h) slots_top2<SIGNED>(slot[h], v1[h], v2[h]);
-            if (cg != 0) {
-                for (int h = 0; h < nh; ++h)
-                    merge[(cg - 1) * kItemM + h * kHalfM + row] = make_int2(v1[h], v2[h]);
-            }
-            named_barrier_sync(1, kEpilogueWarps * 32);
-            if (cg == 0) {
-                for (int h = 0; h < nh; ++h) {
-#pragma unroll
-                    for (int g = 0; g < kColGroups - 1; ++g) {
-                        int2 const o = merge[g * kItemM + h * kHalfM + row];
-                        v2[h] = max3(min(v1[h], o.x), v2[h], o.y);
-                        v1[h] = max(v1[h], o.x);
-                    }
-                    int const r_in_job = rb * kItemM + h * kHalfM + row;
-                    if (r_in_job < job.q_n) rowres[job.out_row + r_in_job] = pack_rowres(v1[h], v2[h], j);
-                }
+            // reading warp only reaches once it is done with this one.
+            int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
+            int v1, v2;
+            slots_top2<SIGNED>(slot, v1, v2);
+            if (c == 1) *merge = make_int4(v1, v2, 0, 0);
+            named_barrier_sync(1 + h * 4 + quad, 64);
+            if (c == 0) {
+                int4 const o = *merge;
+                v2 = max3(min(v1, o.x), v2, o.y);
+                v1 = max(v1, o.x);
+                if (qr < job.q_n) rowres[job.out_row + qr] = pack_rowres(v1, v2, j);
             }
         }
-    } else if ((warp >> 2) < 2) {
+    } else if (RESOLVE) {
+        // ===================== RESOLVE epilogue: exact result for the filter's survivors ======
+        // Same warp layout as the filter.  Every row here carries the 16-bit norm certificate
+        // and its best similarity V, which the filter found exactly, so the packed 16-bit view
+        // of the accumulator is exact and nothing can exceed V.  What the reference's scan
+        // (nearest_neighbor.cc:87-100) ends with follows from three facts about the row:
+        //   idx = the last column whose similarity equals V (">=" lets the later one win),
+        //   cnt = how many columns equal V (two or more: the second best is V itself),
+        //   v2  = the largest similarity below V, not less than the initial 0.
+        // Per load of 64 columns the warp takes the maximum of four groups of 16 columns; only a
+        // thread whose group maximum equals V looks at that group's values one by one.
+        int const ew = warp - kFirstEpilogueWarp;
+        int const quad = warp & 3;
+        int const h = ew >> 3;
+        int const c = (ew >> 2) & 1;
+        int const row = quad * 32 + lane;
+        uint32_t const taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + h * kBlockN + c * kAccCols;
+        int4* const merge_base = reinterpret_cast<int4*>(smem_gen + kSmemMerge);
+
+        int j = 0;
+        uint32_t cnt_tiles = 0, ic = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
+            while (it >= jobs[j + 1].item_start) ++j;
+            ScanJob const job = jobs[j];
+            int const rb = it - job.item_start;
+            int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
+            if (h >= nh) continue;
+            int const ntiles = (job.c_n + kBlockN - 1) / kBlockN;
+            int const r_in_job = rb * kItemM + h * kHalfM + row;
+            // rows past the end of the job hold whatever follows in the scratch pool
+            bool const live = r_in_job < job.q_n;
+            int64_t const entry = live ? ex.xrow_map[job.out_row + r_in_job] : 0;
+            uint32_t const v16 = static_cast<uint32_t>((static_cast<uint64_t>(entry) >> kSurvRowBits) & 0xffffu);
+            // a dead row must never take the slow path: give it a V nothing can reach
+            int const V = live ? (SIGNED ? static_cast<int>(static_cast<short>(v16)) : static_cast<int>(v16)) : 0x7fffffff;
+
+            int cnt = 0, idx = -1, v2 = 0;
+            for (int t = 0; t < ntiles; ++t, ++cnt_tiles) {
+                int const ncols = job.c_n - t * kBlockN;
+                mbar_wait(acc_full(h), cnt_tiles & 1, kWaitAccFull, cnt_tiles);
+                tc_fence_after_sync();
+                uint32_t ra[32], rc[32];
+                tmem_ld_32x32b_x32_pack16(taddr, ra);
+                tmem_ld_32x32b_x32_pack16(taddr + kAccCols / 2, rc);
+                tmem_ld_wait_regs(ra);
+                tmem_ld_wait_regs(rc);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(h));
+                if (ncols < kBlockN) {
+                    mask_packed<SIGNED>(ra, c * kAccCols, ncols);
+                    mask_packed<SIGNED>(rc, c * kAccCols + kAccCols / 2, ncols);
+                }
+                int const col0 = t * kBlockN + c * kAccCols;
+                resolve_load<SIGNED>(ra, col0, job.c_n, V, cnt, idx, v2);
+                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, cnt, idx, v2);
+            }
+            int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
+            if (c == 1) *merge = make_int4(cnt, idx, v2, 0);
+            named_barrier_sync(1 + h * 4 + quad, 64);
+            if (c == 0 && live) {
+                int4 const o = *merge;
+                cnt += o.x;
+                idx = max(idx, o.y);
+                v2 = max(v2, o.z);
+                int const second = cnt >= 2 ? V : v2;
+                bool const ok = passes_tests(ip_to_dist<SIGNED>(V), ip_to_dist<SIGNED>(second), ex.sq_lowe, ex.sq_dist);
+                // signed: a best of 0 may be the initial value, reached by no candidate: index 0
+                ex.oneway[surv_row(entry)] = ok ? max(idx, 0) : -1;
+                if (cnt == 0 && !(SIGNED && V == 0)) atomicAdd(ex.self_check, 1ull);   // the filter's best was not found
+            }
+        }
+    } else if (EXACT && ((warp - kFirstEpilogueWarp) >> 2) < 2) {
         // ===================== EXACT epilogue: 2 x 4 warps replay the reference's scan ======
-        int const my_h = warp >> 2;          // the query half this group owns
+        int const my_h = (warp - kFirstEpilogueWarp) >> 2;   // the query half this group owns
         int const quad = warp & 3;
         int const row = quad * 32 + lane;
         uint32_t const taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + my_h * kBlockN;
 
         int j = 0;
-        uint32_t hcnt = 0;
+        uint32_t hcnt = 0;                   // tiles this group has processed so far
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             while (it >= jobs[j + 1].item_start) ++j;
             ScanJob const job = jobs[j];
@@ -557,10 +697,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             int b1 = 0, b2 = 0, i1 = 0, nbig = 0;
             int64_t const entry = live ? ex.xrow_map[job.out_row + r_in_job] : 0;
             int64_t const g = surv_row(entry);
-            for (int t = 0; t < ntiles; ++t) {
+            for (int t = 0; t < ntiles; ++t, ++hcnt) {
                 int const ncols = job.c_n - t * kBlockN;
                 mbar_wait(acc_full(my_h), hcnt & 1, kWaitAccFull, hcnt);
-                ++hcnt;
                 tc_fence_after_sync();
                 int32_t v[32], vn[32];
                 tmem_ld_32x32b_x32(taddr0, v);
@@ -639,6 +778,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     if (warp == kMmaWarp) {
         __syncwarp();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        prof[0] = static_cast<unsigned long long>(clock64_() - prof_c0);
+        prof[1] = globaltimer_ns() - prof_t0;
     }
 }
 

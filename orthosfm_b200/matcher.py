@@ -327,7 +327,7 @@ class ExhaustiveMatching:
     def debug_trace(self, pairs) -> np.ndarray:
         """clock64() stamps of CTA 0's pipeline events (see osfm_match_debug_trace)."""
         pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
-        out = np.zeros((19, 256, 4), np.int64)
+        out = np.zeros((20, 256, 4), np.int64)
         self._check(self._L.osfm_match_debug_trace(
             self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), len(pr),
             out.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(out.size)))

@@ -88,7 +88,9 @@ def timing(num_views, n, modes=(0, 1, 2), noise="renorm"):
                                 "Tcmp/s_scan": round(cmp_ / best["last_scan_ms"] / 1e9, 3),
                                 "TOPs_alg": round(cmp_ * 256 / best["last_scan_ms"] / 1e9, 1),
                                 "matches": None if loff is None else int(loff[-1]),
-                                "cand": st["candidate_rows"], "slow": st["slow_rows"]}
+                                "cand": st["candidate_rows"], "slow": st["slow_rows"],
+                                "sm_ghz": round(best["last_scan_sm_cycles"] / max(best["last_scan_ns"], 1), 3),
+                                "Mcycles": round(best["last_scan_sm_cycles"] / 1e6, 3)}
         m.debug_set_scan_mode(0)
     return r
 
@@ -103,8 +105,7 @@ if __name__ == "__main__":
         for n1, n2 in [(128, 256), (500, 700), (1000, 1), (1, 1000), (2000, 3000), (4096, 4096)]:
             step(f"parity_{n1}x{n2}", lambda n1=n1, n2=n2: parity(n1, n2))
     if which in ("all", "timing"):
-        step("timing_8x8192", lambda: timing(8, 8192))
-        step("timing_36x8192", lambda: timing(36, 8192))
+        step("timing_36x8192", lambda: timing(36, 8192, modes=(0, 1, 2)))
         step("timing_36x8192_lsb", lambda: timing(36, 8192, modes=(0,), noise="lsb"))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe.json", "w") as f:

@@ -10,15 +10,15 @@ with ExhaustiveMatching() as m:
     m.match_pairs(pairs[:4])
     tr = m.debug_trace(pairs)
 np.save("gpurun_out/trace.npy", tr)
-t0 = tr[17][32, 2]
-for w in (17, 18):
+t0 = tr[0][32, 2]
+for w in (0, 1):
     mma = tr[w]
-    print(f"MMA issuer warp {w}: tiles 32..48: b_full wait start | acc_empty wait start, stage free, issued | period")
+    print(f"MMA issuer warp {w}: groups 64..88: acc_empty wait start, accumulator free, issued | period | accumulator")
     for e in range(32, 48):
-        print(e, mma[e, 3] - t0, "|", mma[e, 0] - t0, mma[e, 1] - t0, mma[e, 2] - t0, "|", mma[e, 2] - mma[e - 1, 2])
+        print(e, mma[e, 0] - t0, mma[e, 1] - t0, mma[e, 2] - t0, "|", mma[e, 2] - mma[e - 1, 2], "|", mma[e, 3])
     d = np.diff(mma[16:250, 2])
-    print("  mean issue period (cycles per tile):", d.mean(), "min", d.min(), "max", d.max())
-for w in (0, 5):
-    print(f"epilogue warp {w}: (wait start, acc ready, handed back, half)")
-    for e in range(64, 76):
-        print(e, *(tr[w, e, :3] - t0), tr[w, e, 3], " ready->back", tr[w, e, 2] - tr[w, e, 1])
+    print("  mean issue period (cycles per group of 128x128x128):", d.mean(), "min", d.min(), "max", d.max())
+for w in (4, 8, 13, 18):
+    print(f"epilogue warp {w} (half {(w - 4) >> 3}, column half {((w - 4) >> 2) & 1}): wait start, acc ready, handed back, maxima done | ready->back, fold")
+    for e in range(32, 44):
+        print(e, *(tr[w, e] - t0), "|", tr[w, e, 2] - tr[w, e, 1], tr[w, e, 3] - tr[w, e, 2])
