@@ -105,6 +105,67 @@ __global__ void __launch_bounds__(256) viewmax_kernel(const int32_t* __restrict_
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(view_max + v, m);
 }
 
+constexpr int kDangerCap = 1024;   // high-norm candidates listed per view
+
+// One CTA (kDangerCap threads) per view.  A query row a whose norm product with the view's
+// largest norm reaches 2^32 has no certificate from the norms alone -- but only the view's
+// few highest-norm rows can actually take a similarity to 2^16.  This kernel lists them:
+// every row b with |b|^2 * gmax >= 2^32 (gmax = the largest squared norm in the whole pool:
+// no other row can be dangerous for any query), sorted by norm, descending, as (row in view,
+// squared norm) pairs.  classify_kernel then computes the few similarities a doubtful query
+// row has with the head of that list and certifies the row after the fact if none reaches
+// 2^16.  danger_cnt[v] = -1 if the view has more than kDangerCap such rows.
+__global__ void __launch_bounds__(kDangerCap) danger_kernel(const int32_t* __restrict__ norm2,
+                                                            const int64_t* __restrict__ view_off,
+                                                            const int32_t* __restrict__ view_n,
+                                                            const int32_t* __restrict__ view_max, int nviews,
+                                                            int2* __restrict__ danger, int32_t* __restrict__ danger_cnt)
+{
+    __shared__ int2 ent[kDangerCap];
+    __shared__ int count;
+    __shared__ int gmax_s;
+    int const v = blockIdx.x;
+    if (threadIdx.x == 0) { count = 0; gmax_s = 0; }
+    __syncthreads();
+    int gm = 0;
+    for (int i = threadIdx.x; i < nviews; i += blockDim.x) gm = max(gm, view_max[i]);
+    gm = __reduce_max_sync(0xffffffffu, gm);
+    if ((threadIdx.x & 31) == 0) atomicMax(&gmax_s, gm);
+    __syncthreads();
+    int64_t const gmax = gmax_s;
+    int const n = view_n[v];
+    const int32_t* p = norm2 + view_off[v];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int const x = p[i];
+        if (static_cast<int64_t>(x) * gmax >= (1ll << 32)) {
+            int const at = atomicAdd(&count, 1);
+            if (at < kDangerCap) ent[at] = make_int2(i, x);
+        }
+    }
+    __syncthreads();
+    int const cnt = count;
+    if (cnt > kDangerCap) {
+        if (threadIdx.x == 0) danger_cnt[v] = -1;
+        return;
+    }
+    // bitonic sort of kDangerCap slots (unused ones hold norm -1), descending by norm
+    if (threadIdx.x >= cnt) ent[threadIdx.x] = make_int2(0, -1);
+    __syncthreads();
+    for (int k = 2; k <= kDangerCap; k <<= 1) {
+        for (int jx = k >> 1; jx > 0; jx >>= 1) {
+            int const i = threadIdx.x, l = i ^ jx;
+            if (l > i) {
+                int2 const a = ent[i], b = ent[l];
+                bool const desc = (i & k) == 0;
+                if (desc ? (a.y < b.y) : (a.y > b.y)) { ent[i] = b; ent[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x < cnt) danger[static_cast<int64_t>(v) * kDangerCap + threadIdx.x] = ent[threadIdx.x];
+    if (threadIdx.x == 0) danger_cnt[v] = cnt;
+}
+
 // ---------------------------------------------------------------- finalisation
 
 struct PostParams {
@@ -126,14 +187,18 @@ struct ClassifyParams {
     const int2* rowres;          // pack_rowres(v1, v2 lower bound, job) per job row
     const int32_t* norm2;        // squared norm of every pool row
     const int32_t* viewmax;      // largest squared norm per view (index: ScanJob::c_view)
+    const uint8_t* pool;
+    const int2* danger;          // per view: its highest-norm rows (danger_kernel)
+    const int32_t* danger_cnt;
     int32_t* oneway;             // out: -1 for rows the filter rejects
     int64_t* surv_list;          // certified survivors of job j (RESOLVE pass):
     int* surv_cnt;               //   surv_list[jobs[j].out_row + 0 .. surv_cnt[j])
     int64_t* exact_list;         // unsigned kind: rows without certificate (EXACT pass), same layout
     int* exact_cnt;
-    int64_t* uncert_list;        // signed kind: rows without certificate (CUDA-core replay), flat
+    int64_t* uncert_list;        // rows without certificate from the norms alone, flat: signed kind:
+                                 // CUDA-core replay; unsigned kind: certify_kernel's input
     unsigned long long* counters;  // [0] uncert_list length, [1] certified survivors (cumulative),
-                                   // [3] rows without certificate (cumulative)
+                                   // [3] rows that stay without certificate (cumulative)
     float sq_lowe, sq_dist;
 };
 
@@ -160,34 +225,33 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
         ScanJob const job = p.jobs[ji];
         out_row = job.out_row;
         int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
-        certified = static_cast<int64_t>(p.norm2[job.q_row + static_cast<int>(g - job.out_row)]) *
-                    static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
+        int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
+        int64_t const qn2 = p.norm2[q_prow];
+        certified = qn2 * static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
         // signed: a row whose best is the initial 0 may have no candidate >= 0 at all; the
         // EXACT pass sorts that out (the index then stays 0)
         survive = certified && ((SIGNED && v1 == 0) ||
                                 passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(v2), p.sq_lowe, p.sq_dist));
         if (certified && !survive) p.oneway[g] = -1;
     }
-    // survivors -> the job's RESOLVE list, unsigned rows without certificate -> its EXACT list;
-    // one atomic per job present in the warp (a warp spans at most a few jobs)
-    bool const to_exact = live && !SIGNED && !certified;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-        bool const mine = which == 0 ? survive : to_exact;
-        unsigned const xm = __ballot_sync(0xffffffffu, mine);
-        if (mine) {
+    // survivors -> the job's RESOLVE list; one atomic per job present in the warp (a warp spans
+    // at most a few jobs)
+    {
+        unsigned const xm = __ballot_sync(0xffffffffu, survive);
+        if (survive) {
             unsigned const peers = __match_any_sync(xm, ji);
             int const leader = __ffs(peers) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd((which == 0 ? p.surv_cnt : p.exact_cnt) + ji, __popc(peers));
+            if (lane == leader) base = atomicAdd(p.surv_cnt + ji, __popc(peers));
             base = __shfl_sync(peers, base, leader);
-            (which == 0 ? p.surv_list : p.exact_list)[out_row + base + __popc(peers & ((1u << lane) - 1u))] =
-                surv_entry(g, v1, certified);
+            p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(g, v1, true);
         }
     }
+    // rows without certificate -> flat list (signed: replayed on CUDA cores; unsigned: looked
+    // at again by certify_kernel)
     unsigned const um = __ballot_sync(0xffffffffu, live && !certified);
     unsigned const sm = __ballot_sync(0xffffffffu, survive);
-    if (SIGNED && um != 0) {
+    if (um != 0) {
         unsigned long long ub = 0;
         if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
         ub = __shfl_sync(0xffffffffu, ub, 0);
@@ -199,11 +263,65 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
     __syncthreads();
     if (lane == 0) {
         if (sm) atomicAdd(&s_cnt[0], __popc(sm));
-        if (um) atomicAdd(&s_cnt[1], __popc(um));
+        if (SIGNED && um) atomicAdd(&s_cnt[1], __popc(um));   // unsigned: certify_kernel counts
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt[0]) atomicAdd(p.counters + 1, static_cast<unsigned long long>(s_cnt[0]));
     if (threadIdx.x == 1 && s_cnt[1]) atomicAdd(p.counters + 3, static_cast<unsigned long long>(s_cnt[1]));
+}
+
+// Unsigned kind, one warp per row that has no certificate from the norms alone.  Only the
+// candidate view's few highest-norm rows (danger_kernel's list, sorted) can take a similarity
+// of this row to 2^16: the lanes compute those similarities exactly.  If none reaches 2^16, no
+// similarity of the row left the 16-bit range, the filter saw the row exactly, and it is
+// treated like any certified row (rejected, or queued for the RESOLVE pass); otherwise it is
+// queued for the EXACT pass.  Grid-strides over the list, whose length is only known on the
+// device.
+__global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
+{
+    int64_t const n = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.counters + 0));
+    int const lane = threadIdx.x & 31;
+    int64_t const nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    unsigned n_exact = 0, n_surv = 0;
+    for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+        int64_t const g = p.uncert_list[w];
+        int2 const rr = p.rowres[g];
+        int const v1 = rr.x & 0xffff;
+        int const v2 = static_cast<int>(static_cast<uint32_t>(rr.x) >> 16);
+        int const ji = rr.y;
+        ScanJob const job = p.jobs[ji];
+        int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
+        int64_t const qn2 = p.norm2[q_prow];
+        int const dc = p.danger_cnt[job.c_view];
+        bool wraps = dc < 0;       // too many high-norm rows in the view to list
+        const int2* dl = p.danger + static_cast<int64_t>(job.c_view) * kDangerCap;
+        for (int base = 0; base < dc && !wraps; base += 32) {
+            int const i = base + lane;
+            int2 const e = i < dc ? dl[i] : make_int2(0, 0);
+            bool const risky = qn2 * static_cast<int64_t>(e.y) >= (1ll << 32);
+            bool hit = false;
+            if (risky && e.x < job.c_n)
+                hit = dot_row<false>(p.pool + static_cast<int64_t>(q_prow) * kRowBytes,
+                                     p.pool + (static_cast<int64_t>(job.c_row) + e.x) * kRowBytes) >= 65536;
+            wraps = __any_sync(0xffffffffu, hit);
+            if (!__all_sync(0xffffffffu, risky)) break;      // sorted by norm: the rest is harmless
+        }
+        if (lane == 0) {
+            if (wraps) {
+                p.exact_list[job.out_row + atomicAdd(p.exact_cnt + ji, 1)] = surv_entry(g, v1, false);
+                ++n_exact;
+            } else if (passes_tests(ip_to_dist<false>(v1), ip_to_dist<false>(v2), p.sq_lowe, p.sq_dist)) {
+                p.surv_list[job.out_row + atomicAdd(p.surv_cnt + ji, 1)] = surv_entry(g, v1, true);
+                ++n_surv;
+            } else {
+                p.oneway[g] = -1;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (n_exact) atomicAdd(p.counters + 3, static_cast<unsigned long long>(n_exact));
+        if (n_surv) atomicAdd(p.counters + 1, static_cast<unsigned long long>(n_surv));
+    }
 }
 
 // ---------------------------------------------------------------- wrap emulation
