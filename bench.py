@@ -72,7 +72,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -85,11 +85,11 @@ class ClockSampler:
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.2] or self.samples
+        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.05] or self.samples
         for _, line in rows:
             parts = [x.strip() for x in line.split(",")]
             try:
@@ -264,7 +264,7 @@ def run_ours(args, config):
 
     sampler = ClockSampler(local_rank)
     launches0 = m.stats()["kernel_launches"]
-    wall, scan_ms, dev_ms = [], [], []
+    wall, scan_ms, dev_ms, sm_ghz = [], [], [], []
     t_region0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)          # evict the pool from L2 between timed iterations
@@ -276,8 +276,13 @@ def run_ours(args, config):
         st = m.stats()
         scan_ms.append(st["last_scan_ms"])
         dev_ms.append(st["last_total_ms"])
+        if st.get("last_scan_ns"):
+            sm_ghz.append(st["last_scan_sm_cycles"] / st["last_scan_ns"])
     t_region1 = time.perf_counter()
     clocks = sampler.stop(t_region0, t_region1)
+    if sm_ghz:
+        # clock64 / globaltimer inside the scan kernel: the SM clock the kernel really ran at
+        clocks["sm_mhz_in_scan_kernel"] = round(1e3 * statistics.median(sm_ghz), 1)
     launches = m.stats()["kernel_launches"] - launches0
 
     step_s = sum(wall) / len(wall)
@@ -293,7 +298,7 @@ def run_ours(args, config):
     total_cmp = npairs * n * n
     value = total_cmp / step_s
 
-    # ---- e2e through the host API (HOST buffers in, dense Result vectors out) ------------
+    # ---- e2e through the host API (HOST buffers in, HOST results out) ---------------------
     e2e = None
     cpu_base = None
     check = None
@@ -303,26 +308,44 @@ def run_ours(args, config):
         me = ExhaustiveMatching(device=local_rank)
         vps = [Viewport(FeatureSet(sift_descriptors=v)) for v in host_views]
         h2d = sum(v.nbytes for v in host_views)
-        e2e_times = []
         res = counts = None
         me.init(vps)
         dense_host = torch.empty(me.pairs_result_size(my_pairs) + 16, dtype=torch.int32).pin_memory().numpy()
-        for it in range(2 + min(args.steps, 5)):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            me.init(vps)                                       # H2D of every view (pinned source)
-            res, counts = me.match_pairs(my_pairs, dense_host)  # kernels + D2H of the dense results
-            torch.cuda.synchronize()
-            if it >= 2:
-                e2e_times.append(time.perf_counter() - t0)
-        d2h = int(sum(r.matches_1_2.nbytes + r.matches_2_1.nbytes for r in res) + counts.nbytes)
-        e2e_s = sum(e2e_times) / len(e2e_times)
-        e2e = {"value": my_cmp * world / e2e_s if world == 1 else my_cmp / e2e_s * world,
-               "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * e2e_s,
-               "note": "osfm_match_begin/set_view_q8/commit + osfm_match_pairs with host buffers"
-                       + ("" if world == 1 else "; rank 0's shard, scaled by the number of ranks")}
+        lists_host = torch.empty((len(my_pairs) * n // 4 + 4096, 2), dtype=torch.int32).pin_memory().numpy()
+        reps = 2 + min(args.steps, 10)
+
+        def timed(fn):
+            ts = []
+            for it in range(reps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                me.init(vps)            # begin / set_view_q8 / commit: H2D of every view (pinned source)
+                r = fn()                # kernels + D2H of the results
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(time.perf_counter() - t0)
+            return sum(ts) / len(ts), r
+
+        # (a) the correspondence lists bundler::Matching::two_view_matching builds (bundler_matching.cc:178-192)
+        lists_s, loff_h = timed(lambda: me.match_pairs_lists(my_pairs, lists_host))
+        d2h_lists = int(loff_h[-1]) * 8 + loff_h.nbytes
+        # (b) the dense Matching::Result vectors of every pair
+        dense_s, (res, counts) = timed(lambda: me.match_pairs(my_pairs, dense_host))
+        d2h_dense = int(sum(r.matches_1_2.nbytes + r.matches_2_1.nbytes for r in res) + counts.nbytes)
+        lists_equal_dense = all(
+            np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 0], np.nonzero(res[p].matches_1_2 >= 0)[0]) and
+            np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 1], res[p].matches_1_2[res[p].matches_1_2 >= 0])
+            for p in range(0, len(my_pairs), 37))
+        scale = 1 if world == 1 else world
+        e2e = {"value": my_cmp * scale / lists_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": d2h_lists, "ms_per_step": 1e3 * lists_s,
+               "note": "osfm_match_begin/set_view_q8/commit (H2D from pinned host memory) + osfm_match_pairs_compact "
+                       "(per-pair (i, j) correspondence lists to host memory)"
+                       + ("" if world == 1 else "; rank 0's shard, scaled by the number of ranks"),
+               "dense": {"value": my_cmp * scale / dense_s, "ms_per_step": 1e3 * dense_s, "d2h_bytes_per_step": d2h_dense,
+                         "note": "same, osfm_match_pairs: the dense Matching::Result vectors of every pair"},
+               "lists_equal_dense_on_sample": bool(lists_equal_dense)}
         me.close()
         # ---- CPU baseline + result check on the sampled pairs ----------------------------
         cpu_base, ref_counts = cpu_baseline_sample(views_np, my_pairs)
@@ -351,7 +374,9 @@ def run_ours(args, config):
         "matches_per_step": total_matches,
         "matches_equal_reference_on_sample": check,
         "broadcast_ms": broadcast_ms,
-        "stats": {k: v for k, v in m.stats().items() if k in ("candidate_rows", "slow_rows", "self_check_failures")},
+        "stats": dict({k: v for k, v in m.stats().items()
+                       if k in ("candidate_rows", "slow_rows", "exact_rows", "self_check_failures")},
+                      rows_per_step=int(2 * my_cmp // n), steps_counted=max(args.warmup, 3) + args.steps),
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -364,7 +389,7 @@ def run_ours(args, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--noise", default="renorm", choices=["renorm", "lsb"],

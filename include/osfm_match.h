@@ -178,6 +178,13 @@ int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs,
 int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs,
     int32_t* d_match_ij, int64_t capacity_ij, int64_t* list_offset);
 
+/* The same with a HOST result buffer: match_ij receives the (i, j) pairs (2 ints
+ * each) of every pair's surviving matches, ordered by i -- the correspondence list
+ * bundler::Matching::two_view_matching builds from the Matching::Result
+ * (bundler_matching.cc:178-192) -- about an eighth of the bytes of the dense vectors. */
+int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs,
+    int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset);
+
 /* ---- introspection --------------------------------------------------------- */
 
 typedef struct {

@@ -120,6 +120,7 @@ struct osfm_matcher {
     DevBuf<int32_t> d_dense;
     DevBuf<int32_t> d_counts;
     DevBuf<int64_t> d_listoff;
+    DevBuf<int2> d_list;
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
@@ -730,7 +731,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     reset_kind(m->kind[1], true);
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release();
     m->d_cand.release(); m->d_big.release();
-    m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release();
+    m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release(); m->d_list.release();
     m->d_ftmp.release();
     m->d_seg_first.release();
     for (auto& sp : m->pass) sp.release();
@@ -1113,14 +1114,23 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
 
 // ---- batched, device-resident, compacted ------------------------------------------------
 
-int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
-                                    int64_t capacity_ij, int64_t* list_offset) {
-    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+// capacity_ij < 0: use (and grow) the handle's own list buffer m->d_list; *d_used receives it.
+static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
+                        int64_t capacity_ij, int64_t* list_offset, int32_t** d_used) {
     OS_TRY(require_committed(m));
     if (!list_offset) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "list_offset is null");
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
+    if (capacity_ij < 0) {
+        // a pair has at most min(n1, n2) mutual matches
+        int64_t cap = 0;
+        for (PairPlan const& p : plans) cap += std::min(p.n1[0], p.n2[0]);
+        CU_TRY(m, cudaSetDevice(m->device));
+        CU_TRY(m, m->d_list.reserve(static_cast<size_t>(std::max<int64_t>(cap, 1))));
+        d_match_ij = reinterpret_cast<int32_t*>(m->d_list.p);
+        capacity_ij = cap;
+    }
+    if (d_used) *d_used = d_match_ij;
     for (PairPlan& p : plans) {  // SIFT only
         p.n1[1] = p.n2[1] = 0;
         p.len12 = p.n1[0]; p.len21 = p.n2[0];
@@ -1180,6 +1190,32 @@ int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int n
     OS_TRY(read_counters(m));
     if (overflow) return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
                               (long long)list_base, (long long)capacity_ij);
+    return OSFM_OK;
+}
+
+int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
+                                    int64_t capacity_ij, int64_t* list_offset) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (capacity_ij < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative capacity");
+    return compact_core(m, pairs, npairs, d_match_ij, capacity_ij, list_offset, nullptr);
+}
+
+int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* match_ij,
+                             int64_t capacity_ij, int64_t* list_offset) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (capacity_ij < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative capacity");
+    int32_t* d = nullptr;
+    OS_TRY(compact_core(m, pairs, npairs, nullptr, -1, list_offset, &d));
+    int64_t const total = list_offset[npairs];
+    if (total > capacity_ij || (total > 0 && !match_ij))
+        return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
+                    (long long)total, (long long)capacity_ij);
+    if (total > 0) {
+        CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    }
     return OSFM_OK;
 }
 

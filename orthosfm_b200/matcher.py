@@ -293,6 +293,23 @@ class ExhaustiveMatching:
         self._check(rc)
         return loff
 
+    def match_pairs_lists(self, pairs, out_ij: np.ndarray) -> np.ndarray:
+        """Batched matching (SIFT) with a HOST result: the surviving (i, j) index pairs of every
+        image pair, ordered by i (what bundler::Matching::two_view_matching builds from the
+        Matching::Result, bundler_matching.cc:178-192), written to the int32 array ``out_ij`` of
+        shape [capacity, 2] (pinned memory makes the copy asynchronous).  Returns the int64 list
+        offsets (npairs + 1)."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pr.shape[0]
+        loff = np.zeros(npairs + 1, np.int64)
+        assert out_ij.dtype == np.int32 and out_ij.flags.c_contiguous
+        rc = self._L.osfm_match_pairs_compact(
+            self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), npairs,
+            out_ij.ctypes.data_as(C.c_void_p), C.c_int64(int(out_ij.shape[0])),
+            loff.ctypes.data_as(C.POINTER(C.c_int64)))
+        self._check(rc)
+        return loff
+
     # -- introspection --------------------------------------------------------------------------
     def stats(self) -> dict:
         s = _lib.Stats()
