@@ -49,6 +49,16 @@ UNIT = "comparisons/s"
 OPS_PER_COMPARISON = 256
 
 
+def measured_traffic():
+    """dram bytes of the roofline kernel per launch, from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -364,8 +374,12 @@ def run_ours(args, config):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": pk["bf16_burst"],
-                     "unit": "TFLOP/s", "frac": achieved_tops / pk["bf16_burst"], "traffic": None,
-                     "kernel": "scan_kernel<0,false,false> (tcgen05.mma kind::i8 + fused 16-bit packed top-2 filter epilogue)",
+                     "unit": "TFLOP/s", "frac": achieved_tops / pk["bf16_burst"],
+                     "traffic": (measured_traffic() or {}).get("dram_bytes_per_launch") if world == 1 else None,
+                     "traffic_note": "dram read + write bytes of one launch on this workload (ncu --set full, "
+                                     "profiles/r01_traffic.json); algorithmic: 37.7 MB pool + 82.6 MB row results",
+                     "tensor_pipe_active_pct_ncu": (measured_traffic() or {}).get("tensor_pipe_active_pct"),
+                     "kernel": "scan_kernel<0,0,0>: filter pass (tcgen05.mma kind::i8 + fused 16-bit packed top-2 filter epilogue)",
                      "peak_source": pk["source"] + ", dense bf16 burst; the kernel computes both "
                                     "match directions, achieved counts each unique comparison once (256 OP)",
                      "kernel_ms": scan_avg_ms, "frac_of_sustained": achieved_tops / pk["bf16_sustained"]},
