@@ -68,6 +68,7 @@ struct KindPool {
     DevBuf<int32_t> d_view_n;
     DevBuf<int2> d_danger;          // unsigned kind: kDangerCap highest-norm rows per view
     DevBuf<int32_t> d_danger_cnt;
+    DevBuf<int32_t> d_danger_floor;
     CUtensorMap tmap;
     // Staging arena: views are appended in the order set_view is called.  When that is the
     // view-id order (the normal case) the arena simply becomes the pool at commit; it is
@@ -190,7 +191,7 @@ void reset_kind(KindPool& k, bool release_arena) {
     k.rows = 0; k.off.clear(); k.n.clear();
     k.stage_off.clear(); k.arena_used = 0; k.last_staged = -1; k.in_order = true;
     if (release_arena && k.arena) { cudaFree(k.arena); k.arena = nullptr; k.arena_cap = 0; }
-    if (release_arena) { k.d_norm2.release(); k.d_viewmax.release(); k.d_view_off.release(); k.d_view_n.release(); k.d_danger.release(); k.d_danger_cnt.release(); }
+    if (release_arena) { k.d_norm2.release(); k.d_viewmax.release(); k.d_view_off.release(); k.d_view_n.release(); k.d_danger.release(); k.d_danger_cnt.release(); k.d_danger_floor.release(); }
 }
 
 // Makes room for `rows` more rows in the staging arena (contents are preserved).
@@ -237,8 +238,10 @@ int compute_norms(osfm_matcher* m, KindPool& k) {
     if (!k.is_signed) {
         CU_TRY(m, k.d_danger.reserve(nv * kDangerCap));
         CU_TRY(m, k.d_danger_cnt.reserve(nv));
+        CU_TRY(m, k.d_danger_floor.reserve(nv));
         danger_kernel<<<static_cast<unsigned>(nv), kDangerCap, 0, m->stream>>>(
-            k.d_norm2.p, k.d_view_off.p, k.d_view_n.p, k.d_viewmax.p, static_cast<int>(nv), k.d_danger.p, k.d_danger_cnt.p);
+            k.d_norm2.p, k.d_view_off.p, k.d_view_n.p, k.d_viewmax.p, k.d_danger.p, k.d_danger_cnt.p,
+            k.d_danger_floor.p);
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
     }
@@ -448,6 +451,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     cp.pool = k.pool;
     cp.danger = k.d_danger.p;
     cp.danger_cnt = k.d_danger_cnt.p;
+    cp.danger_floor = k.d_danger_floor.p;
     cp.oneway = m->d_oneway.p;
     cp.surv_list = m->pass[0].list.p;
     cp.surv_cnt = m->pass[0].cnt.p;

@@ -105,49 +105,66 @@ __global__ void __launch_bounds__(256) viewmax_kernel(const int32_t* __restrict_
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(view_max + v, m);
 }
 
-constexpr int kDangerCap = 1024;   // high-norm candidates listed per view
+constexpr int kDangerCap = 1024;    // high-norm candidates listed per view
+constexpr int kDangerBins = 4096;   // histogram range below the view's largest squared norm
 
 // One CTA (kDangerCap threads) per view.  A query row a whose norm product with the view's
 // largest norm reaches 2^32 has no certificate from the norms alone -- but only the view's
-// few highest-norm rows can actually take a similarity to 2^16.  This kernel lists them:
-// every row b with |b|^2 * gmax >= 2^32 (gmax = the largest squared norm in the whole pool:
-// no other row can be dangerous for any query), sorted by norm, descending, as (row in view,
-// squared norm) pairs.  classify_kernel then computes the few similarities a doubtful query
-// row has with the head of that list and certifies the row after the fact if none reaches
-// 2^16.  danger_cnt[v] = -1 if the view has more than kDangerCap such rows.
+// few highest-norm rows can actually take a similarity to 2^16.  This kernel lists the view's
+// (up to) kDangerCap highest-norm rows, sorted by norm, descending, as (row in view, squared
+// norm) pairs; danger_floor[v] bounds the squared norm of every row that is NOT listed.
+// certify_kernel computes the few similarities a doubtful query row has with the head of
+// that list and certifies the row after the fact if none reaches 2^16.
+// Selection: histogram of (largest norm - norm) over kDangerBins unit bins, the largest
+// distance whose cumulative count still fits the list, then collect and sort (bitonic).
 __global__ void __launch_bounds__(kDangerCap) danger_kernel(const int32_t* __restrict__ norm2,
                                                             const int64_t* __restrict__ view_off,
                                                             const int32_t* __restrict__ view_n,
-                                                            const int32_t* __restrict__ view_max, int nviews,
-                                                            int2* __restrict__ danger, int32_t* __restrict__ danger_cnt)
+                                                            const int32_t* __restrict__ view_max,
+                                                            int2* __restrict__ danger, int32_t* __restrict__ danger_cnt,
+                                                            int32_t* __restrict__ danger_floor)
 {
+    __shared__ int hist[kDangerBins];
     __shared__ int2 ent[kDangerCap];
-    __shared__ int count;
-    __shared__ int gmax_s;
+    __shared__ int count, dstar;
     int const v = blockIdx.x;
-    if (threadIdx.x == 0) { count = 0; gmax_s = 0; }
-    __syncthreads();
-    int gm = 0;
-    for (int i = threadIdx.x; i < nviews; i += blockDim.x) gm = max(gm, view_max[i]);
-    gm = __reduce_max_sync(0xffffffffu, gm);
-    if ((threadIdx.x & 31) == 0) atomicMax(&gmax_s, gm);
-    __syncthreads();
-    int64_t const gmax = gmax_s;
     int const n = view_n[v];
+    int const vmax = view_max[v];
     const int32_t* p = norm2 + view_off[v];
+    for (int i = threadIdx.x; i < kDangerBins; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) { count = 0; dstar = -1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int const d = vmax - p[i];
+        if (d < kDangerBins) atomicAdd(&hist[d], 1);
+    }
+    __syncthreads();
+    // inclusive prefix sums of the histogram, four bins per thread
+    int local[kDangerBins / kDangerCap];
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < kDangerBins / kDangerCap; ++q) { sum += hist[threadIdx.x * (kDangerBins / kDangerCap) + q]; local[q] = sum; }
+    __shared__ int part[kDangerCap];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < kDangerCap; off <<= 1) {
+        int const add = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += add;
+        __syncthreads();
+    }
+    int const before = part[threadIdx.x] - sum;
+#pragma unroll
+    for (int q = 0; q < kDangerBins / kDangerCap; ++q)
+        if (before + local[q] <= kDangerCap) atomicMax(&dstar, threadIdx.x * (kDangerBins / kDangerCap) + q);
+    __syncthreads();
+    int const dmax = dstar;            // rows with vmax - norm <= dmax are listed (-1: none fits)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int const x = p[i];
-        if (static_cast<int64_t>(x) * gmax >= (1ll << 32)) {
-            int const at = atomicAdd(&count, 1);
-            if (at < kDangerCap) ent[at] = make_int2(i, x);
-        }
+        if (vmax - x <= dmax) ent[atomicAdd(&count, 1)] = make_int2(i, x);
     }
     __syncthreads();
     int const cnt = count;
-    if (cnt > kDangerCap) {
-        if (threadIdx.x == 0) danger_cnt[v] = -1;
-        return;
-    }
     // bitonic sort of kDangerCap slots (unused ones hold norm -1), descending by norm
     if (threadIdx.x >= cnt) ent[threadIdx.x] = make_int2(0, -1);
     __syncthreads();
@@ -163,7 +180,10 @@ __global__ void __launch_bounds__(kDangerCap) danger_kernel(const int32_t* __res
         }
     }
     if (threadIdx.x < cnt) danger[static_cast<int64_t>(v) * kDangerCap + threadIdx.x] = ent[threadIdx.x];
-    if (threadIdx.x == 0) danger_cnt[v] = cnt;
+    if (threadIdx.x == 0) {
+        danger_cnt[v] = cnt;
+        danger_floor[v] = cnt >= n ? -1 : vmax - dmax - 1;   // every row listed: nothing below
+    }
 }
 
 // ---------------------------------------------------------------- finalisation
@@ -190,6 +210,7 @@ struct ClassifyParams {
     const uint8_t* pool;
     const int2* danger;          // per view: its highest-norm rows (danger_kernel)
     const int32_t* danger_cnt;
+    const int32_t* danger_floor; // upper bound of the squared norms NOT in the view's list (-1: none)
     int32_t* oneway;             // out: -1 for rows the filter rejects
     int64_t* surv_list;          // certified survivors of job j (RESOLVE pass):
     int* surv_cnt;               //   surv_list[jobs[j].out_row + 0 .. surv_cnt[j])
@@ -293,7 +314,8 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
         int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
         int64_t const qn2 = p.norm2[q_prow];
         int const dc = p.danger_cnt[job.c_view];
-        bool wraps = dc < 0;       // too many high-norm rows in the view to list
+        // rows that are not listed are harmless if even the largest of them is
+        bool wraps = qn2 * static_cast<int64_t>(p.danger_floor[job.c_view]) >= (1ll << 32);
         const int2* dl = p.danger + static_cast<int64_t>(job.c_view) * kDangerCap;
         for (int base = 0; base < dc && !wraps; base += 32) {
             int const i = base + lane;
