@@ -222,6 +222,7 @@ def run_ours(args, config):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)      # started early: nvidia-smi takes a moment to come up
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -272,7 +273,6 @@ def run_ours(args, config):
         loff, gathered = step()
     total_matches = int(gathered[1][-1]) if rank == 0 else 0
 
-    sampler = ClockSampler(local_rank)
     launches0 = m.stats()["kernel_launches"]
     wall, scan_ms, dev_ms, sm_ghz = [], [], [], []
     t_region0 = time.perf_counter()
