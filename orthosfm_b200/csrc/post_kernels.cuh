@@ -112,7 +112,7 @@ constexpr int kDangerBins = 4096;   // histogram range below the view's largest 
 // largest norm reaches 2^32 has no certificate from the norms alone -- but only the view's
 // few highest-norm rows can actually take a similarity to 2^16.  This kernel lists the view's
 // (up to) kDangerCap highest-norm rows, sorted by norm, descending, as (row in view, squared
-// norm) pairs; danger_floor[v] bounds the squared norm of every row that is NOT listed.
+// norm) pairs; danger_floor[v] is the largest squared norm among the rows that are NOT listed.
 // certify_kernel computes the few similarities a doubtful query row has with the head of
 // that list and certifies the row after the fact if none reaches 2^16.
 // Selection: histogram of (largest norm - norm) over kDangerBins unit bins, the largest
@@ -159,10 +159,17 @@ __global__ void __launch_bounds__(kDangerCap) danger_kernel(const int32_t* __res
         if (before + local[q] <= kDangerCap) atomicMax(&dstar, threadIdx.x * (kDangerBins / kDangerCap) + q);
     __syncthreads();
     int const dmax = dstar;            // rows with vmax - norm <= dmax are listed (-1: none fits)
+    int rest = -1;                     // the largest squared norm that is not listed
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int const x = p[i];
         if (vmax - x <= dmax) ent[atomicAdd(&count, 1)] = make_int2(i, x);
+        else rest = max(rest, x);
     }
+    rest = __reduce_max_sync(0xffffffffu, rest);
+    __shared__ int floor_s;
+    if (threadIdx.x == 0) floor_s = -1;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && rest >= 0) atomicMax(&floor_s, rest);
     __syncthreads();
     int const cnt = count;
     // bitonic sort of kDangerCap slots (unused ones hold norm -1), descending by norm
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kDangerCap) danger_kernel(const int32_t* __res
     if (threadIdx.x < cnt) danger[static_cast<int64_t>(v) * kDangerCap + threadIdx.x] = ent[threadIdx.x];
     if (threadIdx.x == 0) {
         danger_cnt[v] = cnt;
-        danger_floor[v] = cnt >= n ? -1 : vmax - dmax - 1;   // every row listed: nothing below
+        danger_floor[v] = floor_s;      // -1: every row is listed
     }
 }
 

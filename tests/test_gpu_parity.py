@@ -202,6 +202,66 @@ def test_duplicate_descriptors_and_ties(ora):
         assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
 
 
+def test_degenerate_rows(ora):
+    """All-zero descriptors (every similarity 0: the best is the reference's initial value and
+    the LAST candidate wins), zero rows mixed into real ones, and a candidate count that leaves
+    a ragged last tile holding other views' rows."""
+    vs = synth.sift_views(19, 3, 700, noise="renorm")
+    a, b, c = vs[0].copy(), vs[1][:300].copy(), vs[2][:513].copy()
+    a[5] = 0
+    a[6] = 0
+    b[7] = 0
+    z = np.zeros((259, 128), np.uint8)
+    with matcher([a, b, c, z]) as m:
+        got = {(i, j): m.twoway_match(KIND_SIFT_U8, i, j) for i, j in [(0, 1), (0, 2), (1, 2), (3, 0), (3, 3), (1, 3)]}
+        assert_clean(m)
+    sets = [a, b, c, z]
+    for (i, j), tw in got.items():
+        o12, o21 = ora.twoway("u8", sets[i], sets[j], 0.8)
+        assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21), (i, j)
+
+
+def test_mixed_certified_wrapping_and_doubtful_rows(ora):
+    """One view pair containing every route through the pipeline: unit-norm rows (norm
+    certificate), rows with inflated norms that no candidate takes to 2^16 (certified after the
+    fact), and rows that really reach 2^16 (EXACT pass, wrapped 16-bit stores)."""
+    vs = synth.sift_views(20, 2, 2000, noise="renorm")
+    a, b = vs[0].copy(), vs[1].copy()
+    rng = np.random.default_rng(3)
+    hot = rng.choice(2000, 60, replace=False)
+    a[hot[:30]] = np.minimum(a[hot[:30]].astype(np.int32) + 3, 255).astype(np.uint8)   # norms up by ~10 %
+    b[hot[30:]] = np.minimum(b[hot[30:]].astype(np.int32) + 3, 255).astype(np.uint8)
+    b[hot[:10]] = a[hot[:10]]                                                            # ... some of them twins
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        assert_clean(m)
+        st = m.stats()
+    o12, o21 = ora.twoway("u8", a, b, 0.8)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+    s = a.astype(np.int64) @ b.astype(np.int64).T
+    assert (s >= 65536).any()                      # the EXACT pass had work ...
+    assert 0 < st["exact_rows"] < 400, st           # ... but only on the rows that reach 2^16
+
+
+def test_surf_degenerate_rows(ora):
+    """Signed kind: rows whose best similarity is negative (index stays 0), exactly zero, and
+    duplicates; ragged sizes."""
+    pool = synth.surf_pool(6, 300)
+    a, b = synth.surf_view(6, 0, 700, pool).copy(), synth.surf_view(6, 1, 515, pool).copy()
+    b[:40] = -a[:40]              # anti-parallel twins: large negative similarities
+    a[50] = 0                     # similarity 0 with everything
+    b[60:64] = a[100]             # four copies of one row
+    only_neg_b = -np.abs(b[:20])
+    only_pos_a = np.abs(a[:33])   # every similarity of this pair of sets is <= 0
+    with matcher(surf=[a, b, only_pos_a, only_neg_b]) as m:
+        got = {(i, j): m.twoway_match(KIND_SURF_S8, i, j) for i, j in [(0, 1), (2, 3), (3, 2), (0, 3)]}
+        assert_clean(m)
+    sets = [a, b, only_pos_a, only_neg_b]
+    for (i, j), tw in got.items():
+        o12, o21 = ora.twoway("s8", sets[i], sets[j], 0.7)
+        assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21), (i, j)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_adversarial_bytes_match_oracle(ora, seed):
     """Arbitrary bytes: inner products up to 8.3e6, every 16-bit lane wraps."""
