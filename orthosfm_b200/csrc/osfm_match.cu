@@ -278,6 +278,8 @@ cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, i
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     ExactParams ex;
     memset(&ex, 0, sizeof ex);
+    ex.norm2 = k.d_norm2.p;
+    ex.viewmax = k.d_viewmax.p;
     scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
         k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
         m->d_counters + 6);
@@ -328,6 +330,8 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     ex.big_list = nullptr;
     ex.big_count = m->d_counters + 12;
     ex.self_check = m->d_counters + 2;
+    ex.norm2 = nullptr;
+    ex.viewmax = nullptr;
     if (PASS == kPassExact) {
         CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
         ex.big_list = m->d_big.p;
@@ -396,7 +400,8 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     }
     if (jobs.empty()) return OSFM_OK;
     if (items > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many work items in one batch");
-    if (rows > static_cast<int64_t>(kSurvRowMask)) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many rows in one batch");
+    if (rows > static_cast<int64_t>(kSurvRowMask) || jobs.size() > static_cast<size_t>(kRowJobMask))
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "too many rows / jobs in one batch");
     int const njobs = static_cast<int>(jobs.size());
     int const nseg = static_cast<int>(seg_first.size());
     seg_first.push_back(njobs);

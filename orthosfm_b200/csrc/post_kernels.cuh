@@ -242,48 +242,56 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 {
     int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     int const lane = threadIdx.x & 31;
-    bool certified = false, survive = false, live = g < p.total_rows;
+    bool certified = false, survive = false, wraps = false, live = g < p.total_rows;
     int ji = -1, v1 = 0;
     int64_t out_row = 0;
     if (live) {
         int2 const rr = p.rowres[g];
         v1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
         int const v2 = SIGNED ? (rr.x >> 16) : static_cast<int>(static_cast<uint32_t>(rr.x) >> 16);
-        ji = rr.y;
+        ji = rr.y & kRowJobMask;
+        int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
         ScanJob const job = p.jobs[ji];
         out_row = job.out_row;
         int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
         int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
         int64_t const qn2 = p.norm2[q_prow];
-        certified = qn2 * static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
+        // scanned with 32-bit loads: the best itself says whether anything left the 16-bit range
+        wraps = flag == kRowWideWraps;
+        certified = flag == kRowWideOk || (!wraps && qn2 * static_cast<int64_t>(p.viewmax[job.c_view]) < limit);
         // signed: a row whose best is the initial 0 may have no candidate >= 0 at all; the
         // EXACT pass sorts that out (the index then stays 0)
         survive = certified && ((SIGNED && v1 == 0) ||
                                 passes_tests(ip_to_dist<SIGNED>(v1), ip_to_dist<SIGNED>(v2), p.sq_lowe, p.sq_dist));
         if (certified && !survive) p.oneway[g] = -1;
     }
-    // survivors -> the job's RESOLVE list; one atomic per job present in the warp (a warp spans
-    // at most a few jobs)
-    {
-        unsigned const xm = __ballot_sync(0xffffffffu, survive);
-        if (survive) {
+    // survivors -> the job's RESOLVE list, rows known to wrap -> its EXACT list; one atomic per
+    // job present in the warp (a warp spans at most a few jobs)
+#pragma unroll
+    for (int which = 0; which < (SIGNED ? 1 : 2); ++which) {
+        bool const mine = which == 0 ? survive : wraps;
+        unsigned const xm = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
             unsigned const peers = __match_any_sync(xm, ji);
             int const leader = __ffs(peers) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(p.surv_cnt + ji, __popc(peers));
+            if (lane == leader) base = atomicAdd((which == 0 ? p.surv_cnt : p.exact_cnt) + ji, __popc(peers));
             base = __shfl_sync(peers, base, leader);
-            p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(g, v1, true);
+            (which == 0 ? p.surv_list : p.exact_list)[out_row + base + __popc(peers & ((1u << lane) - 1u))] =
+                surv_entry(g, v1, which == 0);
         }
     }
     // rows without certificate -> flat list (signed: replayed on CUDA cores; unsigned: looked
     // at again by certify_kernel)
-    unsigned const um = __ballot_sync(0xffffffffu, live && !certified);
+    bool const doubtful = live && !certified && !wraps;
+    unsigned const um = __ballot_sync(0xffffffffu, doubtful);
     unsigned const sm = __ballot_sync(0xffffffffu, survive);
+    unsigned const wm = __ballot_sync(0xffffffffu, wraps);
     if (um != 0) {
         unsigned long long ub = 0;
         if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
         ub = __shfl_sync(0xffffffffu, ub, 0);
-        if (live && !certified) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
+        if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
     }
     // statistics: one atomic per CTA
     __shared__ unsigned s_cnt[2];
@@ -291,7 +299,8 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
     __syncthreads();
     if (lane == 0) {
         if (sm) atomicAdd(&s_cnt[0], __popc(sm));
-        if (SIGNED && um) atomicAdd(&s_cnt[1], __popc(um));   // unsigned: certify_kernel counts
+        if (SIGNED && um) atomicAdd(&s_cnt[1], __popc(um));   // unsigned: certify_kernel counts the rest
+        if (wm) atomicAdd(&s_cnt[1], __popc(wm));
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt[0]) atomicAdd(p.counters + 1, static_cast<unsigned long long>(s_cnt[0]));
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
         int2 const rr = p.rowres[g];
         int const v1 = rr.x & 0xffff;
         int const v2 = static_cast<int>(static_cast<uint32_t>(rr.x) >> 16);
-        int const ji = rr.y;
+        int const ji = rr.y & kRowJobMask;
         ScanJob const job = p.jobs[ji];
         int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
         int64_t const qn2 = p.norm2[q_prow];

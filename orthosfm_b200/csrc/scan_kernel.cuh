@@ -114,9 +114,19 @@ __host__ __device__ __forceinline__ int64_t surv_row(int64_t e) {
 
 // What the filter epilogue leaves per row for classify_kernel (post_kernels.cuh): the largest
 // similarity and the lower bound on the second largest, 16 bits each, and the row's job.
-__device__ __forceinline__ int2 pack_rowres(int v1, int v2, int job) {
-    return make_int2(static_cast<int>((static_cast<uint32_t>(v1) & 0xffffu) | (static_cast<uint32_t>(v2) << 16)), job);
+// The job index shares its word with a flag: how the row was scanned.
+constexpr int kRowFlagShift = 28;
+constexpr int kRowJobMask = (1 << kRowFlagShift) - 1;
+constexpr int kRowPacked = 0;     // 16-bit packed loads: valid if the row is certified
+constexpr int kRowWideOk = 1;     // 32-bit loads, best below 2^16: every similarity fits 16 bits
+constexpr int kRowWideWraps = 2;  // 32-bit loads, best reaches 2^16: the reference's arithmetic wraps
+__device__ __forceinline__ int2 pack_rowres(int v1, int v2, int job, int flag = kRowPacked) {
+    return make_int2(static_cast<int>((static_cast<uint32_t>(v1) & 0xffffu) | (static_cast<uint32_t>(v2) << 16)),
+                     job | (flag << kRowFlagShift));
 }
+// A warp of the filter takes the 32-bit route for an item if at least this many of its 32 rows
+// lack the norm certificate (unit-norm descriptors: practically never; raw bytes: always).
+constexpr int kWideThreshold = 8;
 
 // Extra arguments of the EXACT pass.
 struct ExactParams {
@@ -131,6 +141,9 @@ struct ExactParams {
     int4* big_list;              // (row lo, row hi, column, similarity) of every big candidate met
     unsigned long long* big_count;
     unsigned long long* self_check;   // filter and EXACT pass disagree on a certified row's best
+    // filter pass only: the norm certificate's inputs (squared norm per pool row, largest per view)
+    const int32_t* norm2;
+    const int32_t* viewmax;
 };
 
 constexpr int kTraceEvents = 256;   // per warp, MODE 5
@@ -498,6 +511,65 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             if (h >= nh) continue;           // a 128-row item has no second half
             int const ntiles = (job.c_n + kBlockN - 1) / kBlockN;
             int64_t const qr = static_cast<int64_t>(rb) * kItemM + h * kHalfM + row;   // row in the job
+            int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
+
+            // Unsigned rows without the norm certificate may hold similarities beyond 16 bits.
+            // A few per warp are sorted out afterwards (certify_kernel); if they are many (input
+            // that is not unit-norm), this warp reads the item's accumulators as 32-bit values
+            // instead: twice the loads and instructions, but exact for any input.  (Both column
+            // halves see the same rows and decide alike.)  A loop of its own, so that the packed
+            // loop below stays as tight as it is.
+            if (!SIGNED && MODE == 0) {
+                bool const doubtful = qr < job.q_n &&
+                    static_cast<int64_t>(ex.norm2[job.q_row + qr]) * static_cast<int64_t>(ex.viewmax[job.c_view]) >= (1ll << 32);
+                if (__popc(__ballot_sync(0xffffffffu, doubtful)) >= kWideThreshold) {
+                    int w0 = 0, w1 = 0;          // running maxima of the even / odd columns
+                    for (int t = 0; t < ntiles; ++t, ++cnt) {
+                        int const ncols = job.c_n - t * kBlockN;
+                        mbar_wait(acc_full(h), cnt & 1, kWaitAccFull, cnt);
+                        tc_fence_after_sync();
+                        // 128 columns as four 32-bit loads, two in flight at a time
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            int32_t va[32], vb[32];
+                            tmem_ld_32x32b_x32(taddr + half * 64, va);
+                            tmem_ld_32x32b_x32(taddr + half * 64 + 32, vb);
+                            tmem_ld_wait_regs(va);
+                            tmem_ld_wait_regs(vb);
+                            if (half == 1) {
+                                tc_fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(acc_empty(h));
+                            }
+                            if (ncols < kBlockN) {
+                                mask_chunk(va, c * kAccCols + half * 64, ncols);
+                                mask_chunk(vb, c * kAccCols + half * 64 + 32, ncols);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 32; q += 4) {
+                                w0 = max3(w0, va[q], va[q + 2]);
+                                w1 = max3(w1, va[q + 1], va[q + 3]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 32; q += 4) {
+                                w0 = max3(w0, vb[q], vb[q + 2]);
+                                w1 = max3(w1, vb[q + 1], vb[q + 3]);
+                            }
+                        }
+                    }
+                    int v1 = max(w0, w1), v2 = min(w0, w1);
+                    if (c == 1) *merge = make_int4(v1, v2, 0, 0);
+                    named_barrier_sync(1 + h * 4 + quad, 64);
+                    if (c == 0) {
+                        int4 const o = *merge;
+                        v2 = max3(min(v1, o.x), v2, o.y);
+                        v1 = max(v1, o.x);
+                        if (qr < job.q_n)
+                            rowres[job.out_row + qr] = pack_rowres(v1, v2, j, v1 < 65536 ? kRowWideOk : kRowWideWraps);
+                    }
+                    continue;
+                }
+            }
 
             // 0 is the reference's initial best / second best (nearest_neighbor.cc:221-224)
             uint32_t slot[kSlotRegs];
@@ -579,7 +651,6 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             // area is double-buffered across items, so that one barrier per item suffices: a
             // buffer is rewritten two items later, i.e. after the next item's barrier, which the
             // reading warp only reaches once it is done with this one.
-            int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
             int v1, v2;
             slots_top2<SIGNED>(slot, v1, v2);
             if (c == 1) *merge = make_int4(v1, v2, 0, 0);
