@@ -185,6 +185,39 @@ int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int n
 int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs,
     int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset);
 
+/* ---- two-view gates --------------------------------------------------------
+ * bundler::Matching::two_view_matching (bundler_matching.cc:139-192) up to the point
+ * where RANSAC starts, for a whole list of pairs: the pair rules of compute()
+ * (:92-100), the low-resolution gate (:146-158; all eligible pairs in one batch, and
+ * pairs that fail it are never matched in full), the full match, the match-count
+ * threshold max(8, min_feature_matches) (:161-169) and the correspondence list
+ * (i, matches_1_2[i]) in ascending i (:171-192) in the combined SIFT+SURF index space.
+ * Option defaults are the reference's (bundler_matching.h:58-76). */
+typedef struct {
+    int use_lowres_matching;
+    int num_lowres_features;
+    int min_lowres_matches;
+    int min_feature_matches;
+    int match_num_previous_frames;
+    int reserved[3];
+} osfm_two_view_options;
+void osfm_match_two_view_default_options(osfm_two_view_options* o);
+
+enum {
+    OSFM_TWO_VIEW_OK = 0,                /* list filled; count = consistent matches            */
+    OSFM_TWO_VIEW_SKIPPED = 1,           /* previous-frames rule, or a view without features   */
+    OSFM_TWO_VIEW_LOWRES_REJECTED = 2,   /* count = low-res matches < min_lowres_matches       */
+    OSFM_TWO_VIEW_TOO_FEW_MATCHES = 3    /* count = consistent matches below the threshold     */
+};
+
+/* match_ij (host) receives the lists back to back; pair p's list is
+ * match_ij[2*list_offset[p] .. 2*list_offset[p+1]) (empty unless status[p] == OK);
+ * list_offset has npairs+1 entries; status and count npairs each.  On
+ * OSFM_ERR_OUT_OF_MEMORY list_offset[npairs] holds the required capacity. */
+int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options* opts,
+    const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
+    int64_t* list_offset, int32_t* status, int32_t* count);
+
 /* ---- introspection --------------------------------------------------------- */
 
 typedef struct {

@@ -213,6 +213,39 @@ class Oracle(_Impl):
             C.c_int(num_features)))
 
 
+def two_view_candidates(impl: "Oracle", sift, surf, pairs, use_lowres_matching=False, num_lowres_features=500,
+                        min_lowres_matches=5, min_feature_matches=24, match_num_previous_frames=0):
+    """bundler::Matching::compute's pair rules and two_view_matching up to RANSAC
+    (src/mve/sfm/bundler_matching.cc:92-100, 139-192), restated over the oracle's
+    pairwise_match / pairwise_match_lowres.  Returns (status, count, ij) per pair with the
+    status codes of include/osfm_match.h."""
+    out = []
+    e8 = np.zeros((0, 128), np.uint8)
+    e64 = np.zeros((0, 64), np.int8)
+    for v1, v2 in pairs:
+        s1 = sift[v1] if sift is not None and sift[v1] is not None else e8
+        s2 = sift[v2] if sift is not None and sift[v2] is not None else e8
+        f1 = surf[v1] if surf is not None and surf[v1] is not None else e64
+        f2 = surf[v2] if surf is not None and surf[v2] is not None else e64
+        n1, n2 = len(s1) + len(f1), len(s2) + len(f2)
+        none = np.zeros((0, 2), np.int32)
+        if match_num_previous_frames != 0 and v2 + match_num_previous_frames < v1:
+            out.append((1, 0, none)); continue
+        if n1 == 0 or n2 == 0:
+            out.append((1, 0, none)); continue
+        if use_lowres_matching and n1 * n2 > 1000000:
+            k = impl.pairwise_match_lowres(s1, s2, f1, f2, num_lowres_features)
+            if k < min_lowres_matches:
+                out.append((2, k, none)); continue
+        m12, m21 = impl.pairwise_match(s1, s2, f1, f2)
+        k = impl.count_consistent(m12, m21)
+        if k < max(8, min_feature_matches):
+            out.append((3, k, none)); continue
+        i = np.nonzero(m12 >= 0)[0]
+        out.append((0, k, np.stack([i, m12[i]], axis=1).astype(np.int32)))
+    return out
+
+
 class Reference(_Impl):
     """The reference itself, compiled from /root/reference (oracle/_ref)."""
 

@@ -1124,8 +1124,12 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
 // ---- batched, device-resident, compacted ------------------------------------------------
 
 // capacity_ij < 0: use (and grow) the handle's own list buffer m->d_list; *d_used receives it.
+// sift_only: the SIFT part of every pair (device-resident multi-GPU path); otherwise SIFT and
+// SURF in the combined index space of pairwise_match.  Pairs with fewer than min_count
+// consistent matches get an empty list.  counts_out (may be null) receives every pair's count.
 static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
-                        int64_t capacity_ij, int64_t* list_offset, int32_t** d_used) {
+                        int64_t capacity_ij, int64_t* list_offset, int32_t** d_used,
+                        bool sift_only = true, int min_count = 0, int32_t* counts_out = nullptr) {
     OS_TRY(require_committed(m));
     if (!list_offset) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "list_offset is null");
     std::vector<PairPlan> plans;
@@ -1133,17 +1137,19 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
     if (capacity_ij < 0) {
         // a pair has at most min(n1, n2) mutual matches
         int64_t cap = 0;
-        for (PairPlan const& p : plans) cap += std::min(p.n1[0], p.n2[0]);
+        for (PairPlan const& p : plans)
+            cap += std::min(p.n1[0], p.n2[0]) + (sift_only ? 0 : std::min(p.n1[1], p.n2[1]));
         CU_TRY(m, cudaSetDevice(m->device));
         CU_TRY(m, m->d_list.reserve(static_cast<size_t>(std::max<int64_t>(cap, 1))));
         d_match_ij = reinterpret_cast<int32_t*>(m->d_list.p);
         capacity_ij = cap;
     }
     if (d_used) *d_used = d_match_ij;
-    for (PairPlan& p : plans) {  // SIFT only
-        p.n1[1] = p.n2[1] = 0;
-        p.len12 = p.n1[0]; p.len21 = p.n2[0];
-    }
+    if (sift_only)
+        for (PairPlan& p : plans) {
+            p.n1[1] = p.n2[1] = 0;
+            p.len12 = p.n1[0]; p.len21 = p.n2[0];
+        }
     CU_TRY(m, cudaSetDevice(m->device));
     m->scan_ms_acc = 0.0;
     CU_TRY(m, cudaEventRecord(m->ev[2], m->stream));
@@ -1154,7 +1160,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
     std::vector<PairPart> parts;
     int r = for_each_batch(plans, [&](size_t first, size_t last, int64_t dense) -> int {
         std::vector<PairPlan> sub(plans.begin() + first, plans.begin() + last);
-        OS_TRY(run_batch(m, sub, dense, kFiltered, 0));
+        OS_TRY(run_batch(m, sub, dense, kFiltered, sift_only ? 0 : -1));
         size_t const np = last - first;
         counts.resize(np);
         CU_TRY(m, cudaMemcpyAsync(counts.data(), m->d_counts.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, m->stream));
@@ -1162,6 +1168,8 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
         loff.resize(np);
         parts.clear();
         for (size_t i = 0; i < np; ++i) {
+            if (counts_out) counts_out[first + i] = counts[i];
+            if (counts[i] < min_count) counts[i] = 0;
             list_offset[first + i] = list_base;
             loff[i] = list_base;
             list_base += counts[i];
@@ -1169,7 +1177,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
                 PairPart pt;
                 memset(&pt, 0, sizeof pt);
                 pt.out12 = sub[i].out12;
-                pt.n1 = sub[i].n1[0];
+                pt.n1 = sub[i].len12;
                 pt.pair = static_cast<int32_t>(i);
                 parts.push_back(pt);
             }
@@ -1225,6 +1233,112 @@ int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs, 
         CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
         CU_TRY(m, cudaStreamSynchronize(m->stream));
     }
+    return OSFM_OK;
+}
+
+// ---- two-view gates (bundler::Matching::two_view_matching up to RANSAC) --------------------------
+
+void osfm_match_two_view_default_options(osfm_two_view_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->use_lowres_matching = 0;       // bundler_matching.h:66
+    o->num_lowres_features = 500;     // :68
+    o->min_lowres_matches = 5;        // :70
+    o->min_feature_matches = 24;      // :62
+    o->match_num_previous_frames = 0; // :72
+}
+
+int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options* opts, const int32_t* pairs,
+                                   int npairs, int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset,
+                                   int32_t* status, int32_t* count) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    OS_TRY(require_committed(m));
+    if (!opts || !list_offset || !status || !count || npairs < 0 || (npairs > 0 && !pairs) || capacity_ij < 0)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
+    // 1. the rules that need no matching (bundler_matching.cc:92-100)
+    std::vector<int32_t> todo;      // indices into pairs[]
+    auto feats = [&](int v) { return static_cast<int64_t>(m->kind[0].n[v]) + m->kind[1].n[v]; };
+    for (int i = 0; i < npairs; ++i) {
+        int const v1 = pairs[2 * i], v2 = pairs[2 * i + 1];
+        OS_TRY(check_view(m, v1));
+        OS_TRY(check_view(m, v2));
+        status[i] = OSFM_TWO_VIEW_SKIPPED;
+        count[i] = 0;
+        if (opts->match_num_previous_frames != 0 && v2 + opts->match_num_previous_frames < v1) continue;
+        if (feats(v1) == 0 || feats(v2) == 0) continue;
+        todo.push_back(i);
+    }
+    // 2. the low-resolution gate (bundler_matching.cc:146-158), all eligible pairs in one batch
+    std::vector<int32_t> full;
+    if (opts->use_lowres_matching) {
+        if (opts->num_lowres_features <= 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad num_lowres_features");
+        std::vector<int32_t> lr_pairs, lr_index;
+        for (int32_t i : todo) {
+            if (feats(pairs[2 * i]) * feats(pairs[2 * i + 1]) > 1000000) {
+                lr_pairs.push_back(pairs[2 * i]);
+                lr_pairs.push_back(pairs[2 * i + 1]);
+                lr_index.push_back(i);
+            } else {
+                full.push_back(i);
+            }
+        }
+        if (!lr_index.empty()) {
+            std::vector<PairPlan> plans;
+            OS_TRY(build_plans(m, lr_pairs.data(), static_cast<int>(lr_index.size()), opts->num_lowres_features, true, plans));
+            std::vector<int32_t> lr_counts(lr_index.size(), 0);
+            // count_consistent_matches of the unfiltered result = survivors of the mutual filter
+            OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, lr_counts.data()));
+            for (size_t k = 0; k < lr_index.size(); ++k) {
+                int32_t const i = lr_index[k];
+                if (lr_counts[k] < opts->min_lowres_matches) {
+                    status[i] = OSFM_TWO_VIEW_LOWRES_REJECTED;
+                    count[i] = lr_counts[k];
+                } else {
+                    full.push_back(i);
+                }
+            }
+            std::sort(full.begin(), full.end());
+        }
+    } else {
+        full = todo;
+    }
+    // 3. full matching of the remaining pairs, the match-count threshold (:161-169) and the
+    //    correspondence lists (:171-192)
+    for (int i = 0; i <= npairs; ++i) list_offset[i] = 0;
+    if (full.empty()) return OSFM_OK;
+    std::vector<int32_t> fp;
+    for (int32_t i : full) { fp.push_back(pairs[2 * i]); fp.push_back(pairs[2 * i + 1]); }
+    int const nf = static_cast<int>(full.size());
+    std::vector<int64_t> loff(nf + 1, 0);
+    std::vector<int32_t> cnt(nf, 0);
+    int const thr = std::max(8, opts->min_feature_matches);
+    int32_t* d = nullptr;
+    OS_TRY(compact_core(m, fp.data(), nf, nullptr, -1, loff.data(), &d, false, thr, cnt.data()));
+    int64_t const total = loff[nf];
+    if (total > capacity_ij || (total > 0 && !match_ij)) {
+        list_offset[npairs] = total;
+        return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
+                    (long long)total, (long long)capacity_ij);
+    }
+    if (total > 0) {
+        CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    }
+    // scatter the per-pair results back to the caller's pair order (lists stay in `full` order,
+    // which is ascending pair index: offsets are monotone)
+    int k = 0;
+    int64_t at = 0;
+    for (int i = 0; i < npairs; ++i) {
+        list_offset[i] = at;
+        if (k < nf && full[k] == i) {
+            count[i] = cnt[k];
+            status[i] = cnt[k] < thr ? OSFM_TWO_VIEW_TOO_FEW_MATCHES : OSFM_TWO_VIEW_OK;
+            at += loff[k + 1] - loff[k];
+            ++k;
+        }
+    }
+    list_offset[npairs] = at;
     return OSFM_OK;
 }
 

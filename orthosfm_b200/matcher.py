@@ -85,6 +85,21 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
 
 
+TWO_VIEW_OK, TWO_VIEW_SKIPPED, TWO_VIEW_LOWRES_REJECTED, TWO_VIEW_TOO_FEW_MATCHES = 0, 1, 2, 3
+
+
+class TwoViewOptions:
+    """The matcher-side fields of sfm::bundler::Matching::Options (bundler_matching.h:58-76)."""
+
+    def __init__(self, use_lowres_matching=False, num_lowres_features=500, min_lowres_matches=5,
+                 min_feature_matches=24, match_num_previous_frames=0):
+        self.use_lowres_matching = use_lowres_matching
+        self.num_lowres_features = num_lowres_features
+        self.min_lowres_matches = min_lowres_matches
+        self.min_feature_matches = min_feature_matches
+        self.match_num_previous_frames = match_num_previous_frames
+
+
 class ExhaustiveMatching:
     """Drop-in for sfm::ExhaustiveMatching, computing on a B200.
 
@@ -309,6 +324,30 @@ class ExhaustiveMatching:
             loff.ctypes.data_as(C.POINTER(C.c_int64)))
         self._check(rc)
         return loff
+
+    def two_view_candidates(self, pairs, opts: "TwoViewOptions" = None) -> list:
+        """bundler::Matching::two_view_matching up to RANSAC (bundler_matching.cc:139-192) for a
+        list of (view_1, view_2) pairs: pair rules, low-res gate, full match, match-count
+        threshold, correspondence list.  Returns one ``(status, count, ij)`` per pair, ``ij`` an
+        int32 array of shape [k, 2] (empty unless status == TWO_VIEW_OK)."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pr.shape[0]
+        o = _lib.TwoViewOptions()
+        self._L.osfm_match_two_view_default_options(C.byref(o))
+        if opts is not None:
+            for name in ("use_lowres_matching", "num_lowres_features", "min_lowres_matches",
+                         "min_feature_matches", "match_num_previous_frames"):
+                setattr(o, name, int(getattr(opts, name)))
+        cap = int(sum(min(sum(self._sizes[a]), sum(self._sizes[b])) for a, b in pr)) + 1
+        ij = np.empty((cap, 2), np.int32)
+        loff = np.zeros(npairs + 1, np.int64)
+        status = np.zeros(npairs, np.int32)
+        count = np.zeros(npairs, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_two_view_candidates(
+            self._h, C.byref(o), pr.ctypes.data_as(i32p), npairs, ij.ctypes.data_as(C.c_void_p), C.c_int64(cap),
+            loff.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(i32p), count.ctypes.data_as(i32p)))
+        return [(int(status[p]), int(count[p]), ij[loff[p]:loff[p + 1]].copy()) for p in range(npairs)]
 
     # -- introspection --------------------------------------------------------------------------
     def stats(self) -> dict:

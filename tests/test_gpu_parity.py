@@ -464,6 +464,40 @@ def test_many_pairs_one_launch(ora):
         assert np.array_equal(results[p].matches_2_1, o21), (v1, v2)
 
 
+# ------------------------------------------------------------------ two-view gates
+
+@pytest.mark.parametrize("lowres", [False, True])
+def test_two_view_candidates_match_the_reference_gates(ora, lowres):
+    """bundler::Matching::two_view_matching up to RANSAC for a batch of pairs: pair rules,
+    low-res gate (only pairs with more than 10^6 feature products), match-count threshold and
+    the correspondence lists, SIFT + SURF in the combined index space."""
+    import oracle
+    from orthosfm_b200 import TwoViewOptions
+    sp, fp = synth.scene_pool(21, 500), synth.surf_pool(21, 200)
+    other = synth.scene_pool(22, 500)
+    sizes = [(1500, 300), (1400, 0), (900, 250), (1300, 200), (0, 0), (700, 0), (1200, 100)]
+    sift = [synth.sift_view(21, v, s, sp if v not in (3, 5) else other, noise="renorm") for v, (s, _) in enumerate(sizes)]
+    surf = [synth.surf_view(21, v, f, fp) if f else None for v, (_, f) in enumerate(sizes)]
+    sift = [x if len(x) else None for x in sift]
+    pairs = synth.all_pairs(len(sizes))
+    opts = TwoViewOptions(use_lowres_matching=lowres, num_lowres_features=400, min_lowres_matches=12,
+                          min_feature_matches=50, match_num_previous_frames=0)
+    with matcher(sift, surf) as m:
+        got = m.two_view_candidates(pairs, opts)
+        prev = m.two_view_candidates(pairs, TwoViewOptions(match_num_previous_frames=2))
+        assert_clean(m)
+    want = oracle.two_view_candidates(ora, sift, surf, pairs, use_lowres_matching=lowres, num_lowres_features=400,
+                                      min_lowres_matches=12, min_feature_matches=50)
+    seen = set()
+    for p, ((gs, gc, gij), (ws, wc, wij)) in enumerate(zip(got, want)):
+        assert (gs, gc) == (ws, wc), (tuple(pairs[p]), gs, gc, ws, wc)
+        assert np.array_equal(gij, wij), tuple(pairs[p])
+        seen.add(gs)
+    assert seen >= ({0, 1, 2, 3} if lowres else {0, 1, 3}), seen       # every outcome occurs
+    want_prev = oracle.two_view_candidates(ora, sift, surf, pairs, match_num_previous_frames=2)
+    assert [(a, b) for a, b, _ in prev] == [(a, b) for a, b, _ in want_prev]
+
+
 # ------------------------------------------------------------------ the reference-side binding
 
 def test_reference_side_binding():
