@@ -252,8 +252,9 @@ def run_ours(args, config):
 
     m = ExhaustiveMatching(device=local_rank)
     m.init_device_pool(pool, offsets, sizes)
-    cap = int(len(my_pairs) * n * 0.25) + 4096
-    out_ij = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    cap = int(max(len(o) for o in all_owned) * n * 0.25) + 4096
+    fixed = osd.FixedGather(all_owned, npairs, cap, dev, dst=0) if world > 1 else None
+    out_ij = fixed.out_ij if fixed is not None else torch.empty((cap, 2), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -263,8 +264,11 @@ def run_ours(args, config):
 
     def step():
         loff = m.match_pairs_compact(my_pairs, out_ij)
-        gathered = osd.gather_match_lists(out_ij, loff, owned, npairs, dst=0, all_owned=all_owned) \
-            if world > 1 else (out_ij, loff)
+        if world > 1:
+            flat, start, count = fixed.gather(loff)      # one NCCL gather to rank 0
+            gathered = (flat, None if count is None else np.concatenate([[0], np.cumsum(count)]))
+        else:
+            gathered = (out_ij, loff)
         return loff, gathered
 
     for _ in range(max(args.warmup, 3)):

@@ -79,3 +79,43 @@ def test_gather_single_process_passthrough():
     flat = torch.from_numpy(np.concatenate(lists))
     ij, offsets = osd.gather_match_lists(flat, offs, owned, 3)
     assert np.array_equal(offsets, offs) and ij.shape[0] == offs[-1]
+
+
+def _worker_fixed(rank: int, world: int, port: int, npairs: int, out_path: str):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pairs = synth.all_pairs(int((1 + (1 + 8 * npairs) ** 0.5) / 2))
+    all_owned = osd.partition_pairs(pairs, np.full(64, 10), world)
+    owned = all_owned[rank]
+    fg = osd.FixedGather(all_owned, npairs, capacity=64, device=torch.device("cpu"))
+    for step in range(2):          # the buffers are reused step after step
+        lists = [_fake_list(int(p) + step) for p in owned]
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+        flat = np.concatenate(lists + [np.zeros((0, 2), np.int32)])
+        fg.out_ij[:len(flat)] = torch.from_numpy(flat)         # what the matcher would have written
+        ij, start, count = fg.gather(offs)
+        if rank == 0:
+            np.savez(out_path + str(step) + ".npz", ij=ij.numpy(), start=start, count=count)
+        else:
+            assert ij is None
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fixed_gather_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    npairs = 28
+    out_path = str(tmp_path / "fixed")
+    mp.spawn(_worker_fixed, args=(2, port, npairs, out_path), nprocs=2, join=True)
+    for step in range(2):
+        z = np.load(out_path + str(step) + ".npz")
+        for p in range(npairs):
+            want = _fake_list(p + step)
+            got = z["ij"][z["start"][p]:z["start"][p] + z["count"][p]]
+            assert np.array_equal(got, want), (step, p)
