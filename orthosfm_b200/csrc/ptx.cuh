@@ -245,6 +245,26 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int m, int n, int a_signed,
            | (static_cast<uint32_t>(m >> 4) << 24);   // M >> 4
 }
 
+// One lane of the (converged) warp.  Code that issues TMA / tcgen05 instructions runs
+// warp-uniformly up to this point, so that their operands live in uniform registers; inside a
+// divergent "if (lane == 0)" the compiler has to assume per-lane values and wraps every such
+// instruction in a register-to-uniform-register "waterfall" loop of a dozen vector instructions.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Marks a value that is the same in every lane as such for the compiler.
+__device__ __forceinline__ int warp_uniform(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

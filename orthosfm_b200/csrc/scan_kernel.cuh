@@ -281,12 +281,52 @@ __device__ __forceinline__ void slots_top2(const uint32_t (&m)[kSlotRegs], int& 
     v2 = max3(min(wl, wh), plo<SIGNED>(l), phi<SIGNED>(l));
 }
 
+// RESOLVE: a group of 16 consecutive columns (eight packed registers) that contains the row's
+// best value V, set aside to be looked at value by value later (see the RESOLVE epilogue).
+struct ResolvePending {
+    uint32_t r[8];
+    int col;            // first column of the group in the candidate view; -1: nothing pending
+};
+
+// Looks at a pending group: counts the columns equal to V, remembers the last one and takes
+// the maximum of the others.  (col < c_n: a masked column of an all-zero row is no column.)
+template <bool SIGNED>
+__device__ __forceinline__ void resolve_flush(ResolvePending& pd, int c_n, int V, int& cnt, int& idx, int& v2) {
+    if (pd.col < 0) return;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int const col = pd.col + 2 * k;
+        int const x0 = plo<SIGNED>(pd.r[k]), x1 = phi<SIGNED>(pd.r[k]);
+        bool const e0 = x0 == V && col < c_n;
+        bool const e1 = x1 == V && col + 1 < c_n;
+        cnt += (e0 ? 1 : 0) + (e1 ? 1 : 0);
+        idx = e1 ? col + 1 : (e0 ? col : idx);
+        v2 = max(v2, e0 ? 0 : x0);
+        v2 = max(v2, e1 ? 0 : x1);
+    }
+    pd.col = -1;
+}
+
 // RESOLVE: one packed load (64 columns starting at column col0 of the candidate view) of a row
-// whose largest similarity V is known.  See the RESOLVE epilogue.
+// whose largest similarity V is known.  Groups that cannot contain V only feed v2; a group
+// that does is set aside (columns are visited in ascending order, so flushing the previous
+// pending group first keeps "the last column equal to V" right).
 template <bool SIGNED>
 __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int c_n, int V,
-                                             int& cnt, int& idx, int& v2)
+                                             ResolvePending& pd, int& cnt, int& idx, int& v2)
 {
+    // the load's maximum as ONE dependent chain (like the filter's fold: a warp that stalls on
+    // its own result leaves issue slots to the MMA issuers; a tree would issue back to back)
+    uint32_t acc = pmax3<SIGNED>(r[0], r[1], r[2]);
+#pragma unroll
+    for (int k = 3; k < 31; k += 2) acc = pmax3<SIGNED>(acc, r[k], r[k + 1]);
+    acc = pmax<SIGNED>(acc, r[31]);
+    int const m = max(plo<SIGNED>(acc), phi<SIGNED>(acc));
+    if (m < V) {            // the common case: nothing of interest in these 64 columns
+        v2 = max(v2, m);
+        return;
+    }
+    // some lane has V in this load: maxima of the four groups of 16 columns
     uint32_t g[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -294,29 +334,16 @@ __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, 
         uint32_t const b = pmax3<SIGNED>(r[8 * i + 3], r[8 * i + 4], r[8 * i + 5]);
         g[i] = pmax<SIGNED>(pmax3<SIGNED>(a, b, r[8 * i + 6]), r[8 * i + 7]);
     }
-    uint32_t const m4 = pmax<SIGNED>(pmax<SIGNED>(g[0], g[1]), pmax<SIGNED>(g[2], g[3]));
-    int const m = max(plo<SIGNED>(m4), phi<SIGNED>(m4));
-    if (m < V) {            // the common case: nothing of interest in these 64 columns
-        v2 = max(v2, m);
-        return;
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int const mg = max(plo<SIGNED>(g[i]), phi<SIGNED>(g[i]));
         if (mg < V) {
             v2 = max(v2, mg);
         } else {
+            resolve_flush<SIGNED>(pd, c_n, V, cnt, idx, v2);     // rare: a second hit before the flush
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                int const col = col0 + 2 * (8 * i + k);
-                int const x0 = plo<SIGNED>(r[8 * i + k]), x1 = phi<SIGNED>(r[8 * i + k]);
-                bool const e0 = x0 == V && col < c_n;        // (a masked column of an all-zero row)
-                bool const e1 = x1 == V && col + 1 < c_n;
-                cnt += (e0 ? 1 : 0) + (e1 ? 1 : 0);
-                idx = e1 ? col + 1 : (e0 ? col : idx);
-                v2 = max(v2, e0 ? 0 : x0);
-                v2 = max(v2, e1 ? 0 : x1);
-            }
+            for (int k = 0; k < 8; ++k) pd.r[k] = r[8 * i + k];
+            pd.col = col0 + 16 * i;
         }
     }
 }
@@ -439,19 +466,22 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         // (Measured per launch of the 630-pair workload, epilogue switched off: one issuer
         // 9.7 M cycles, one issuer with the next group's waits hoisted 12.8 M, two issuers
         // free-running 12 M, two issuers taking turns 9.45 M; 8.9 M is the tensor pipe's floor.)
-        int const h = warp - kMmaWarp;
-        if (lane == 0) {
+        // The whole warp runs this loop converged (see elect_one_sync in ptx.cuh); one elected
+        // lane issues.
+        int const h = warp_uniform(warp - kMmaWarp);
+        uint32_t const tmem_u = warp_uniform(tmem_base);
+        {
             int j = 0;
             uint32_t bcnt = 0, ic = 0, hc = 0;   // hc: tiles this issuer has issued so far
             for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
-                while (it >= jobs[j + 1].item_start) ++j;
-                int const c_n = jobs[j].c_n;
-                int const rb = it - jobs[j].item_start;
-                bool const active = (jobs[j].q_n - rb * kItemM > kHalfM) || h == 0;
+                while (it >= warp_uniform(jobs[j + 1].item_start)) ++j;
+                int const c_n = warp_uniform(jobs[j].c_n);
+                int const rb = it - warp_uniform(jobs[j].item_start);
+                bool const active = (warp_uniform(jobs[j].q_n) - rb * kItemM > kHalfM) || h == 0;
                 int const abuf = ic & 1;
                 mbar_wait(a_full(abuf), (ic >> 1) & 1, kWaitAFull, ic);
                 uint64_t const adesc = make_smem_desc_sw128(smem_base + kSmemA + abuf * kATileBytes + h * kAHalfBytes);
-                uint32_t const d_tmem = tmem_base + h * kBlockN;
+                uint32_t const d_tmem = tmem_u + h * kBlockN;
                 int const ntiles = (c_n + kBlockN - 1) / kBlockN;
                 for (int t = 0; t < ntiles; ++t, ++bcnt) {
                     int const s = bcnt % kStages;
@@ -459,8 +489,11 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     uint32_t const turn_parity = h == 0 ? ((bcnt & 1) ^ 1) : (bcnt & 1);
                     if (!active) {                  // a 128-row item: nothing for the second half
                         mbar_wait(turn(h), turn_parity, kWaitTurn, bcnt);
-                        mbar_arrive(turn(1 - h));
-                        mbar_arrive(b_empty(s));
+                        if (elect_one_sync()) {
+                            mbar_arrive(turn(1 - h));
+                            mbar_arrive(b_empty(s));
+                        }
+                        __syncwarp();
                         continue;
                     }
                     uint64_t const bdesc = make_smem_desc_sw128(smem_base + kSmemB + s * kBTileBytes);
@@ -469,24 +502,30 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     mbar_wait(turn(h), turn_parity, kWaitTurn, bcnt);
                     long long const tw1 = MODE == 5 ? clock64_() : 0;
                     tc_fence_after_sync();
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < kRowBytes / 32; ++k) {
-                        // +2 in the start-address field = 32 bytes along K inside the swizzle
-                        // span; 64-byte descriptors (SURF) are zero beyond K = 64: two steps
-                        if (k < ksteps)
-                            mma_i8_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < kRowBytes / 32; ++k) {
+                            // +2 in the start-address field = 32 bytes along K inside the swizzle
+                            // span; 64-byte descriptors (SURF) are zero beyond K = 64: two steps
+                            if (k < ksteps)
+                                mma_i8_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+                        }
+                        mbar_arrive(turn(1 - h));   // the other half's group may follow
+                        mma_commit(acc_full(h));    // this accumulator is ready
+                        mma_commit(b_empty(s));     // this issuer is done with the candidate stage
+                        if (MODE == 5 && blockIdx.x == 0 && hc < kTraceEvents) {
+                            long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + hc) * 4;
+                            tr[0] = tw0; tr[1] = tw1; tr[2] = clock64_(); tr[3] = h;
+                        }
                     }
-                    mbar_arrive(turn(1 - h));   // the other half's group may follow
-                    mma_commit(acc_full(h));    // this accumulator is ready
-                    mma_commit(b_empty(s));     // this issuer is done with the candidate stage
-                    if (MODE == 5 && blockIdx.x == 0 && hc < kTraceEvents) {
-                        long long* tr = reinterpret_cast<long long*>(dump) + (static_cast<size_t>(warp) * kTraceEvents + hc) * 4;
-                        tr[0] = tw0; tr[1] = tw1; tr[2] = clock64_(); tr[3] = h;
-                    }
+                    __syncwarp();
                     ++hc;
                 }
                 // this issuer is done with the query tile
-                if (active) mma_commit(a_empty(abuf)); else mbar_arrive(a_empty(abuf));
+                if (elect_one_sync()) {
+                    if (active) mma_commit(a_empty(abuf)); else mbar_arrive(a_empty(abuf));
+                }
+                __syncwarp();
             }
         }
     } else if (warp < kFirstEpilogueWarp) {
@@ -671,8 +710,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         //   idx = the last column whose similarity equals V (">=" lets the later one win),
         //   cnt = how many columns equal V (two or more: the second best is V itself),
         //   v2  = the largest similarity below V, not less than the initial 0.
-        // Per load of 64 columns the warp takes the maximum of four groups of 16 columns; only a
-        // thread whose group maximum equals V looks at that group's values one by one.
+        // Per load of 64 columns the warp takes the maximum of four groups of 16 columns; a
+        // thread whose group maximum equals V sets that group's registers aside, and the groups
+        // set aside are looked at value by value every eighth tile -- for many lanes at once,
+        // instead of dragging the whole warp through the scan whenever one lane has a hit.
         int const ew = warp - kFirstEpilogueWarp;
         int const quad = warp & 3;
         int const h = ew >> 3;
@@ -699,6 +740,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             int const V = live ? (SIGNED ? static_cast<int>(static_cast<short>(v16)) : static_cast<int>(v16)) : 0x7fffffff;
 
             int cnt = 0, idx = -1, v2 = 0;
+            ResolvePending pd;
+            pd.col = -1;
             for (int t = 0; t < ntiles; ++t, ++cnt_tiles) {
                 int const ncols = job.c_n - t * kBlockN;
                 mbar_wait(acc_full(h), cnt_tiles & 1, kWaitAccFull, cnt_tiles);
@@ -716,9 +759,14 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     mask_packed<SIGNED>(rc, c * kAccCols + kAccCols / 2, ncols);
                 }
                 int const col0 = t * kBlockN + c * kAccCols;
-                resolve_load<SIGNED>(ra, col0, job.c_n, V, cnt, idx, v2);
-                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, cnt, idx, v2);
+                resolve_load<SIGNED>(ra, col0, job.c_n, V, pd, cnt, idx, v2);
+                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, pd, cnt, idx, v2);
+                // groups set aside are looked at every eighth tile, when most lanes of the warp
+                // have one (a row's best sits in one tile of, here, eight): the value-by-value
+                // scan then runs once for many rows instead of once per row
+                if ((t & 7) == 7) resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
             }
+            resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
             int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
             if (c == 1) *merge = make_int4(cnt, idx, v2, 0);
             named_barrier_sync(1 + h * 4 + quad, 64);
