@@ -14,6 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
+] + os.environ.get("OSFM_NVCC_EXTRA", "").split() + [
 ]
 
 
