@@ -281,6 +281,11 @@ __device__ __forceinline__ void slots_top2(const uint32_t (&m)[kSlotRegs], int& 
     v2 = max3(min(wl, wh), plo<SIGNED>(l), phi<SIGNED>(l));
 }
 
+#ifndef OSFM_RESOLVE_CHAINS
+#define OSFM_RESOLVE_CHAINS 2
+#endif
+constexpr int kResolveChains = OSFM_RESOLVE_CHAINS;   // dependent chains of the RESOLVE load maximum
+
 // RESOLVE: a group of 16 consecutive columns (eight packed registers) that contains the row's
 // best value V, set aside to be looked at value by value later (see the RESOLVE epilogue).
 struct ResolvePending {
@@ -317,11 +322,21 @@ __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, 
 {
     // the load's maximum as ONE dependent chain (like the filter's fold: a warp that stalls on
     // its own result leaves issue slots to the MMA issuers; a tree would issue back to back)
-    uint32_t acc = pmax3<SIGNED>(r[0], r[1], r[2]);
+    uint32_t acc[kResolveChains];
 #pragma unroll
-    for (int k = 3; k < 31; k += 2) acc = pmax3<SIGNED>(acc, r[k], r[k + 1]);
-    acc = pmax<SIGNED>(acc, r[31]);
-    int const m = max(plo<SIGNED>(acc), phi<SIGNED>(acc));
+    for (int q = 0; q < kResolveChains; ++q) acc[q] = r[q];
+#pragma unroll
+    for (int k = kResolveChains; k + 2 * kResolveChains <= 32; k += 2 * kResolveChains)
+#pragma unroll
+        for (int q = 0; q < kResolveChains; ++q)
+            acc[q] = pmax3<SIGNED>(acc[q], r[k + 2 * q], r[k + 2 * q + 1]);
+    // (32 - kResolveChains) is not a multiple of 2 * kResolveChains for every choice: the rest
+#pragma unroll
+    for (int k = kResolveChains + ((32 - kResolveChains) / (2 * kResolveChains)) * 2 * kResolveChains; k < 32; ++k)
+        acc[0] = pmax<SIGNED>(acc[0], r[k]);
+#pragma unroll
+    for (int q = 1; q < kResolveChains; ++q) acc[0] = pmax<SIGNED>(acc[0], acc[q]);
+    int const m = max(plo<SIGNED>(acc[0]), phi<SIGNED>(acc[0]));
     if (m < V) {            // the common case: nothing of interest in these 64 columns
         v2 = max(v2, m);
         return;
