@@ -451,6 +451,65 @@ def test_full_size_pair_properties(ora):
         assert tw.matches_2_1[r] == o
 
 
+def test_baseline_config_2_lists_equal_the_reference():
+    """BASELINE config 2 at full size (36 x 8192, all 630 pairs in one batched call): the
+    correspondence lists of a spread of pairs against the reference matcher itself (compiled
+    from its sources, oracle/_ref) or, where that is not built, the C restatement."""
+    import oracle
+    views = synth.sift_views(2, 36, 8192, noise="renorm")
+    pairs = synth.all_pairs(36)
+    with matcher(views) as m:
+        out = np.empty((630 * 2048, 2), np.int32)
+        loff = m.match_pairs_lists(pairs, out)
+        assert_clean(m)
+        st = m.stats()
+    assert st["exact_rows"] < 64                     # unit-norm data: next to nothing reaches 2^16
+    sample = list(range(0, 630, 53))                 # 12 pairs
+    impl = oracle.Reference() if oracle.have_ref() else oracle.Oracle()
+    from concurrent.futures import ThreadPoolExecutor      # (ctypes releases the GIL)
+    with ThreadPoolExecutor(len(sample)) as ex:
+        want = list(ex.map(lambda p: impl.match_filtered("u8", views[pairs[p][0]], views[pairs[p][1]], 0.8)[0], sample))
+    for p, o12 in zip(sample, want):
+        v1, v2 = pairs[p]
+        i = np.nonzero(o12 >= 0)[0]
+        got = out[loff[p]:loff[p + 1]]
+        assert np.array_equal(got[:, 0], i) and np.array_equal(got[:, 1], o12[i]), (v1, v2)
+        assert i.size > 500
+
+
+def test_config_5_single_large_pair(ora):
+    """BASELINE config 5: one pair of 200 000 x 200 000 descriptors (782 work items per
+    direction, ragged last tile): list ordering, mutual consistency through a second call with
+    the views swapped, and sampled rows against the oracle."""
+    import torch
+    n = 200000
+    dev = torch.device("cuda", 0)
+    pool = synth.torch_sift_views(5, 2, n, dev, noise="renorm")
+    pool = torch.cat([pool, torch.zeros((256, 128), dtype=torch.uint8, device=dev)])
+    m = ExhaustiveMatching(device=0)
+    m.init_device_pool(pool, np.array([0, n], np.int64), np.array([n, n], np.int32))
+    out = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    loff = m.match_pairs_compact(np.array([[1, 0]], np.int32), out)
+    a = out[:int(loff[1])].cpu().numpy()
+    loff2 = m.match_pairs_compact(np.array([[0, 1]], np.int32), out)
+    b = out[:int(loff2[1])].cpu().numpy()
+    st = m.stats()
+    m.close()
+    assert st["self_check_failures"] == 0
+    assert a.shape[0] > 10000 and np.all(np.diff(a[:, 0]) > 0)
+    # swapping the views transposes the list
+    bs = b[np.argsort(b[:, 1], kind="stable")]
+    assert np.array_equal(bs[:, ::-1], a)
+    v1 = pool[n:2 * n].cpu().numpy()
+    v0 = pool[:n].cpu().numpy()
+    got = dict(zip(a[:, 0].tolist(), a[:, 1].tolist()))
+    rng = np.random.default_rng(5)
+    for r in list(rng.integers(0, n, 10)) + a[:6, 0].tolist():
+        o = int(ora.twoway("u8", v1[r:r + 1], v0, 0.8)[0][0])
+        back = int(ora.twoway("u8", v0[o:o + 1], v1, 0.8)[0][0]) if o >= 0 else -1
+        assert got.get(int(r), -1) == (o if (o >= 0 and back == r) else -1), r
+
+
 def test_many_pairs_one_launch(ora):
     """12 views x 2048: the persistent kernel over 66 pairs; every pair checked."""
     views = synth.sift_views(12, 12, 2048)
