@@ -248,6 +248,20 @@ __device__ __forceinline__ void fold_packed(uint32_t (&slot)[kSlotRegs], const u
     }
 }
 
+// Both loads of a tile at once, pairing a register of the first with one of the second.  The
+// very first instruction then needs both loads, which keeps ptxas from sinking the second
+// tcgen05.ld below the fold of the first (it does, to save registers, and the two load
+// latencies then add up on the path that hands the accumulator back).
+template <bool SIGNED>
+__device__ __forceinline__ void fold_packed2(uint32_t (&slot)[kSlotRegs], const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+#pragma unroll
+    for (int k = 0; k < kSlotRegs; ++k) {
+#pragma unroll
+        for (int q = 0; q < 32 / kSlotRegs; ++q)
+            slot[k] = pmax3<SIGNED>(slot[k], a[k + q * kSlotRegs], b[k + q * kSlotRegs]);
+    }
+}
+
 // Largest and second largest (with multiplicity) of the 16 slot maxima held in eight packed
 // registers: a tournament per 16-bit lane -- the maximum over all "losers" of a tournament is
 // its second largest entry -- followed by the merge of the two lanes.
@@ -629,8 +643,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             uint32_t slot[kSlotRegs];
 #pragma unroll
             for (int k = 0; k < kSlotRegs; ++k) slot[k] = 0u;
-            for (int t = 0; t < ntiles; ++t, ++cnt) {
-                int const ncols = job.c_n - t * kBlockN;   // valid columns of this tile
+            // full tiles here; a ragged last tile (debug modes: every tile) after the loop / inside
+            int const nloop = (MODE == 0 || MODE == 5) ? job.c_n / kBlockN : ntiles;
+            for (int t = 0; t < nloop; ++t, ++cnt) {
                 long long const te0 = MODE == 5 ? clock64_() : 0;
                 mbar_wait(acc_full(h), cnt & 1, kWaitAccFull, cnt);
                 long long const te1 = MODE == 5 ? clock64_() : 0;
@@ -672,12 +687,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 long long const te2 = MODE == 5 ? clock64_() : 0;
 
                 if (MODE == 0 || MODE == 5) {
-                    if (ncols < kBlockN) {
-                        mask_packed<SIGNED>(ra, c * kAccCols, ncols);
-                        mask_packed<SIGNED>(rc, c * kAccCols + kAccCols / 2, ncols);
-                    }
-                    fold_packed<SIGNED>(slot, ra);
-                    fold_packed<SIGNED>(slot, rc);
+                    fold_packed2<SIGNED>(slot, ra, rc);
                     if (MODE == 5 && blockIdx.x == 0 && lane == 0 && cnt < kTraceEvents) {
                         long long t3 = clock64_();
                         asm volatile("" : "+l"(t3) : "r"(slot[0]));
@@ -693,6 +703,36 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 #pragma unroll
                         for (int q = 0; q < 32; ++q) { d[q] = ra[q]; d[32 + q] = rc[q]; }
                     }
+                }
+            }
+            if ((MODE == 0 || MODE == 5) && nloop < ntiles) {
+                int const t = nloop;
+                int const ncols = job.c_n - t * kBlockN;   // valid columns of this tile
+                mbar_wait(acc_full(h), cnt & 1, kWaitAccFull, cnt);
+                tc_fence_after_sync();
+                {
+                    // A ragged last tile: the columns past the end of the view hold other views'
+                    // rows.  Handled apart (32 columns at a time, 32-bit, valid columns only), so
+                    // that the loop above carries no masking code.  (The values of a certified row
+                    // fit 16 bits; an uncertified row's result is not used.)
+                    int e0 = SIGNED ? -32768 : 0, e1 = e0;
+#pragma unroll 1
+                    for (int q4 = 0; q4 < kAccCols / kChunk; ++q4) {
+                        int32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + q4 * kChunk, v);
+                        tmem_ld_wait_regs(v);
+                        int const col0 = c * kAccCols + q4 * kChunk;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 2) {
+                            if (col0 + q < ncols) e0 = max(e0, v[q]);
+                            if (col0 + q + 1 < ncols) e1 = max(e1, v[q + 1]);
+                        }
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(h));
+                    slot[0] = pmax<SIGNED>(slot[0], (static_cast<uint32_t>(e0) & 0xffffu) | (static_cast<uint32_t>(e1) << 16));
+                    ++cnt;
                 }
             }
             if (MODE != 0 && MODE != 5) {
@@ -761,6 +801,30 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 int const ncols = job.c_n - t * kBlockN;
                 mbar_wait(acc_full(h), cnt_tiles & 1, kWaitAccFull, cnt_tiles);
                 tc_fence_after_sync();
+                if (ncols < kBlockN) {
+                    // a ragged last tile, apart from the loop proper (see the filter): value by
+                    // value over the valid columns
+                    resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
+#pragma unroll 1
+                    for (int q4 = 0; q4 < kAccCols / kChunk; ++q4) {
+                        int32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + q4 * kChunk, v);
+                        tmem_ld_wait_regs(v);
+                        int const colq = t * kBlockN + c * kAccCols + q4 * kChunk;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            bool const valid = colq + q < job.c_n;
+                            bool const eq = valid && v[q] == V;
+                            cnt += eq ? 1 : 0;
+                            idx = eq ? colq + q : idx;
+                            v2 = max(v2, (valid && !eq) ? v[q] : 0);
+                        }
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(h));
+                    continue;
+                }
                 uint32_t ra[32], rc[32];
                 tmem_ld_32x32b_x32_pack16(taddr, ra);
                 tmem_ld_32x32b_x32_pack16(taddr + kAccCols / 2, rc);
@@ -769,10 +833,6 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(h));
-                if (ncols < kBlockN) {
-                    mask_packed<SIGNED>(ra, c * kAccCols, ncols);
-                    mask_packed<SIGNED>(rc, c * kAccCols + kAccCols / 2, ncols);
-                }
                 int const col0 = t * kBlockN + c * kAccCols;
                 resolve_load<SIGNED>(ra, col0, job.c_n, V, pd, cnt, idx, v2);
                 resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, pd, cnt, idx, v2);
