@@ -312,7 +312,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
                                                  PASS == kPassExact ? m->d_counters + 5 : nullptr);
     CU_TRY(m, cudaGetLastError());
-    exact_gather_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
+    exact_gather_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
                                                               sp.job_xrow.p, sp.list.p, k.pool,
                                                               sp.xpool.p, sp.xrow_map.p);
     CU_TRY(m, cudaGetLastError());
@@ -473,7 +473,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     if (e != cudaSuccess) return cuda_fail(m, e, "classify_kernel launch");
     m->stats.kernel_launches++;
     if (!k.is_signed) {
-        certify_kernel<<<m->num_sms * 8, 256, 0, m->stream>>>(cp);
+        certify_kernel<<<m->num_sms * 32, 256, 0, m->stream>>>(cp);   // latency-bound: many warps
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(m, e, "certify_kernel launch");
         m->stats.kernel_launches++;
