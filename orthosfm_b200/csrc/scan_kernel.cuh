@@ -767,7 +767,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         //   v2  = the largest similarity below V, not less than the initial 0.
         // Per load of 64 columns the warp takes the maximum of four groups of 16 columns; a
         // thread whose group maximum equals V sets that group's registers aside, and the groups
-        // set aside are looked at value by value every eighth tile -- for many lanes at once,
+        // set aside are looked at value by value at the end of the item -- for all lanes at once,
         // instead of dragging the whole warp through the scan whenever one lane has a hit.
         int const ew = warp - kFirstEpilogueWarp;
         int const quad = warp & 3;
@@ -836,11 +836,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 int const col0 = t * kBlockN + c * kAccCols;
                 resolve_load<SIGNED>(ra, col0, job.c_n, V, pd, cnt, idx, v2);
                 resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, pd, cnt, idx, v2);
-                // groups set aside are looked at every eighth tile, when most lanes of the warp
-                // have one (a row's best sits in one tile of, here, eight): the value-by-value
-                // scan then runs once for many rows instead of once per row
-                if ((t & 7) == 7) resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
             }
+            // The group set aside is looked at once, here: a row has one column equal to V unless
+            // it has duplicates, so the value-by-value scan runs once per item for all the rows
+            // of the warp instead of once per hit.
             resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
             int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
             if (c == 1) *merge = make_int4(cnt, idx, v2, 0);
