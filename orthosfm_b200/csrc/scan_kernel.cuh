@@ -1,5 +1,5 @@
 // scan_kernel.cuh -- the hot kernel: all-pairs 8-bit descriptor similarity on tcgen05
-// tensor cores with a fused running top-2 epilogue.  sm_100a only.
+// tensor cores with fused top-2 epilogues.  sm_100a only.
 //
 // What it replaces (reference, paths relative to /root/reference):
 //   short_inner_prod<T> + the top-2 scan of NearestNeighbor<T>::find
@@ -15,34 +15,40 @@
 //     traffic per similarity,
 //   - issues tcgen05.mma kind::i8 (M=128, N=256, 4 x K=32; u8 x u8 or s8 x s8 -> s32,
 //     exact) into the TMEM accumulator of that half (2 x 256 columns = all of TMEM),
-//   - 16 epilogue warps (4 per TMEM lane quadrant, 64 columns each) pull the accumulator
-//     into registers with tcgen05.ld, hand the TMEM stage straight back to the MMA warp,
-//     and then reduce from registers.  The similarity matrix never leaves the SM.
+//   - 16 epilogue warps, one per (TMEM lane quadrant, query half, 128-column half), pull
+//     their part of that half's accumulator into registers with tcgen05.ld, hand the
+//     accumulator straight back to the MMA issuers, and then reduce from registers.  The
+//     similarity matrix never leaves the SM.
+// Warps 0 and 1 issue the MMAs (one per query half, taking turns), warp 2 drives TMA.
 //
-// Per row the fast epilogue is a *filter*.  It reads the accumulator with
-// tcgen05.ld ... .pack::16b (two adjacent columns per 32-bit register) and keeps sixteen
-// packed running maxima per thread with three-input 16-bit SIMD max instructions
-// (VIMNMX3.U16x2 / .S16x2): one instruction per four similarities.  At the end of a work item
-// the 64 "slot" maxima of a row (16 per thread x 4 column groups) give
+// Three passes share this pipeline and differ in the epilogue (template parameter PASS):
+//
+// FILTER (all rows).  Reads the accumulator with tcgen05.ld ... .pack::16b (two adjacent
+// columns per 32-bit register) and folds it with three-input 16-bit SIMD max instructions
+// (VIMNMX3.U16x2 / .S16x2, one instruction per four similarities) into one packed register
+// per thread: the running maxima of the even and of the odd columns of the warp's column
+// half.  At the end of a work item the four "slot" maxima of a row give
 //   v1  = the largest similarity of the row (exact), and
 //   v2  = the second largest slot maximum, clamped below at 0 -- a lower bound on the
 //         reference's second-best inner product (exact unless best and second best share a
 //         slot).
 // The reference's ratio test is monotone in the second best, so a row that fails it with the
-// lower bound fails it for good and is final (-1) right here.  The rows that pass (the
-// *survivors*, typically the rows that really have a match) are appended to a per-job list and
-// re-run by the EXACT pass below, which produces the reference's bytes.
+// lower bound fails it for good (classify_kernel writes -1).  The rows that pass (the
+// *survivors*, typically the rows that really have a match) go to the RESOLVE pass.
 //
 // The 16-bit packing is only valid if no similarity of the row leaves the 16-bit range.  That
 // is certified per (row, candidate view) by Cauchy-Schwarz from the squared norms computed at
 // commit: |a|^2 * max|b|^2 < 2^32 (unsigned) or < 2^30 (signed; this also excludes a wrap of
-// the reference's 16-bit SSE lanes).  Rows without the certificate skip the filter: unsigned
-// rows join the survivors, signed rows go to the CUDA-core replay (slow_rows_kernel).
+// the reference's 16-bit SSE lanes).  A few rows without that certificate are looked at again
+// by certify_kernel; a warp with many of them reads the item with 32-bit loads instead.
 //
-// EXACT = true is the second pass, over the gathered survivor rows: the same MMA pipeline
-// recomputes their similarities and eight epilogue warps replay the reference's sequential
-// best / second-best scan per row, in column order (nearest_neighbor.cc:87-100), including
-// the 16-bit wrap of the lanes and stores for candidates that reach 2^16.
+// RESOLVE (the gathered survivors).  Same packed loads; the row's best value V is known, and
+// the epilogue finds the last column equal to V, how many there are, and the largest value
+// below V -- which is all the reference's sequential scan ends with.
+//
+// EXACT (the gathered rows that really reach 2^16, unsigned).  32-bit loads; eight epilogue
+// warps replay the reference's sequential best / second-best scan per row, in column order
+// (nearest_neighbor.cc:87-100), including the 16-bit wrap of its lanes and stores.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
