@@ -510,6 +510,56 @@ def test_config_5_single_large_pair(ora):
         assert got.get(int(r), -1) == (o if (o >= 0 and back == r) else -1), r
 
 
+def test_more_rows_than_one_batch(ora):
+    """40 views x 16384, all 780 pairs: 25.6 M job rows, i.e. more than the 16 M rows one batch
+    of scratch memory holds; lists of pairs from every batch against the oracle (sampled rows),
+    and the list of a pair matched alone."""
+    import torch
+    nv, n = 40, 16384
+    dev = torch.device("cuda", 0)
+    pool = synth.torch_sift_views(13, nv, n, dev, noise="renorm")
+    pool = torch.cat([pool, torch.zeros((256, 128), dtype=torch.uint8, device=dev)])
+    m = ExhaustiveMatching(device=0)
+    m.init_device_pool(pool, np.arange(nv, dtype=np.int64) * n, np.full(nv, n, np.int32))
+    pairs = synth.all_pairs(nv)
+    out = torch.empty((len(pairs) * n // 4, 2), dtype=torch.int32, device=dev)
+    loff = m.match_pairs_compact(pairs, out)
+    lists = out[:int(loff[-1])].cpu().numpy()
+    st = m.stats()
+    assert st["self_check_failures"] == 0
+    single = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    rng = np.random.default_rng(1)
+    for p in (0, 399, 400, 779):           # first / last pairs of both batches
+        v1, v2 = pairs[p]
+        got = lists[loff[p]:loff[p + 1]]
+        assert got.shape[0] > 1000 and np.all(np.diff(got[:, 0]) > 0)
+        lo = m.match_pairs_compact(pairs[p:p + 1], single)
+        assert np.array_equal(single[:int(lo[1])].cpu().numpy(), got), p
+        a = pool[v1 * n:(v1 + 1) * n].cpu().numpy()
+        b = pool[v2 * n:(v2 + 1) * n].cpu().numpy()
+        d = dict(zip(got[:, 0].tolist(), got[:, 1].tolist()))
+        for r in rng.integers(0, n, 6):
+            o = int(ora.twoway("u8", a[r:r + 1], b, 0.8)[0][0])
+            back = int(ora.twoway("u8", b[o:o + 1], a, 0.8)[0][0]) if o >= 0 else -1
+            assert d.get(int(r), -1) == (o if (o >= 0 and back == r) else -1), (p, r)
+    m.close()
+
+
+def test_concurrent_callers_are_serialised(ora):
+    """pairwise_match is const and called from an OpenMP loop in the reference
+    (bundler_matching.cc:74): the handle serialises concurrent callers."""
+    from concurrent.futures import ThreadPoolExecutor
+    vs = synth.sift_views(14, 5, 600, noise="renorm")
+    pairs = [tuple(p) for p in synth.all_pairs(5)]
+    with matcher(vs) as m:
+        with ThreadPoolExecutor(8) as ex:
+            res = list(ex.map(lambda p: m.pairwise_match(int(p[0]), int(p[1])), pairs * 3))
+        assert_clean(m)
+    for (v1, v2), r in zip(pairs * 3, res):
+        o12, o21 = ora.match_filtered("u8", vs[v1], vs[v2], 0.8)
+        assert np.array_equal(r.matches_1_2, o12) and np.array_equal(r.matches_2_1, o21)
+
+
 def test_many_pairs_one_launch(ora):
     """12 views x 2048: the persistent kernel over 66 pairs; every pair checked."""
     views = synth.sift_views(12, 12, 2048)
