@@ -15,7 +15,6 @@ constexpr int kBlockN = 256;     // candidate rows per tile (= TMEM columns per 
 constexpr int kChunk = 32;       // candidates per tcgen05.ld.x32
 constexpr int kChunksPerTile = kBlockN / kChunk;
 
-constexpr int kInitV1 = -(1 << 30);   // "nothing seen yet" (never multiplied)
 constexpr int kMasked = -(1 << 24);   // similarity of a column past the end of the view: below
                                       // any real value (|s| < 2^23) and kMasked * 8 fits an int
 

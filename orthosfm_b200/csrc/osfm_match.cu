@@ -308,11 +308,11 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         sp.tmap_for = sp.xpool.p;
         sp.tmap_rows = sp.xpool.cap;
     }
-    exact_plan_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, sp.cnt.p,
+    plan_rows_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, sp.cnt.p,
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
                                                  PASS == kPassExact ? m->d_counters + 5 : nullptr);
     CU_TRY(m, cudaGetLastError());
-    exact_gather_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
+    gather_rows_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
                                                               sp.job_xrow.p, sp.list.p, k.pool,
                                                               sp.xpool.p, sp.xrow_map.p);
     CU_TRY(m, cudaGetLastError());

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
 // candidate set, and the slow rows of all its jobs are gathered back to back so that they
 // form full 256-row work items against that candidate view.  One thread per segment.
 // meta[0] = work items, meta[1] = exact jobs, meta[2] = gathered rows.
-__global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restrict__ jobs,
+__global__ void __launch_bounds__(1024) plan_rows_kernel(const ScanJob* __restrict__ jobs,
                                                           const int32_t* __restrict__ seg_first, int nseg,
                                                           const int* __restrict__ slow_cnt,
                                                           ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(1024) exact_plan_kernel(const ScanJob* __restr
 
 // Copies the slow rows' descriptors into the scratch query pool and records where their
 // result goes.  Grid-stride over jobs; 8 threads move one 128-byte row.
-__global__ void __launch_bounds__(256) exact_gather_kernel(const ScanJob* __restrict__ jobs, int njobs,
+__global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restrict__ jobs, int njobs,
                                                            const int* __restrict__ slow_cnt,
                                                            const int* __restrict__ job_xrow,
                                                            const int64_t* __restrict__ slow_list,

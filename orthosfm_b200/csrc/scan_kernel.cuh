@@ -227,33 +227,6 @@ template <bool SIGNED> __device__ __forceinline__ int phi(uint32_t x) {
     return SIGNED ? (static_cast<int>(x) >> 16) : static_cast<int>(x >> 16);
 }
 
-// Columns of a ragged last tile that lie past the end of the view hold other views' rows:
-// replace them by the smallest value.  Register k of a packed load holds columns
-// first_col + 2k (low half) and first_col + 2k + 1 (high half).
-template <bool SIGNED>
-__device__ __forceinline__ void mask_packed(uint32_t (&r)[32], int first_col, int ncols) {
-    uint32_t const lo_min = SIGNED ? 0x00008000u : 0u;
-    uint32_t const hi_min = SIGNED ? 0x80000000u : 0u;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        int const c = first_col + 2 * k;
-        if (c >= ncols) r[k] = lo_min | hi_min;
-        else if (c + 1 >= ncols) r[k] = (r[k] & 0x0000ffffu) | hi_min;
-    }
-}
-
-// Folds one packed x32 load (64 columns) into the running slot registers: slot k keeps the
-// maxima of the columns congruent to 2k and 2k+1 modulo 2 * kSlotRegs.
-template <bool SIGNED>
-__device__ __forceinline__ void fold_packed(uint32_t (&slot)[kSlotRegs], const uint32_t (&r)[32]) {
-#pragma unroll
-    for (int k = 0; k < kSlotRegs; ++k) {
-#pragma unroll
-        for (int q = 0; q < 32 / kSlotRegs; q += 2)
-            slot[k] = pmax3<SIGNED>(slot[k], r[k + q * kSlotRegs], r[k + (q + 1) * kSlotRegs]);
-    }
-}
-
 // Both loads of a tile at once, pairing a register of the first with one of the second.  The
 // very first instruction then needs both loads, which keeps ptxas from sinking the second
 // tcgen05.ld below the fold of the first (it does, to save registers, and the two load
