@@ -218,6 +218,22 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
     const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
     int64_t* list_offset, int32_t* status, int32_t* count);
 
+/* ---- tracks ------------------------------------------------------------------
+ * Replaces sfm::bundler::Tracks::compute incl. remove_invalid_tracks
+ * (src/mve/sfm/bundler_tracks.cc:47-203) up to the numbering of the tracks: the tracks
+ * are the connected components of the match graph (nodes = (view, feature), edges =
+ * the matches of every pair) that do not hold two features of one view.
+ * features_per_view: num_views counts; pair p joins views pair_views[2p] and
+ * pair_views[2p+1] with the matches match_ij[2*list_offset[p] .. 2*list_offset[p+1])
+ * (host, (feature in view 1, feature in view 2)).  track_of_feature (host, sum of
+ * features_per_view ints, view after view) receives Viewport::track_ids: the track of
+ * every feature or -1; tracks are numbered in ascending order of their first feature.
+ * num_conflicting (may be NULL): components dropped because of a view conflict (the
+ * reference's num_invalid_tracks).  The handle only provides the device and stream. */
+int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_per_view,
+    const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij, int npairs,
+    int32_t* track_of_feature, int32_t* num_tracks, int32_t* num_conflicting);
+
 /* ---- introspection --------------------------------------------------------- */
 
 typedef struct {

@@ -246,6 +246,63 @@ def two_view_candidates(impl: "Oracle", sift, surf, pairs, use_lowres_matching=F
     return out
 
 
+def canonical_track_ids(track_ids: np.ndarray) -> np.ndarray:
+    """Relabels per-feature track ids (-1 = none) in order of first appearance, so that two
+    labelings of the same partition become identical arrays."""
+    t = np.asarray(track_ids, np.int64)
+    out = np.full(t.shape, -1, np.int32)
+    used = t >= 0
+    if used.any():
+        _, first = np.unique(t[used], return_index=True)
+        order = np.argsort(first)                       # old labels by first appearance
+        remap = np.empty(order.size, np.int64)
+        remap[order] = np.arange(order.size)
+        labels = np.unique(t[used])
+        out[used] = remap[np.searchsorted(labels, t[used])]
+    return out
+
+
+def tracks_compute(features, pair_views, offsets, ij):
+    """sfm::bundler::Tracks::compute (src/mve/sfm/bundler_tracks.cc:47-203) restated: sequential
+    track-id propagation over the match lists in order, unify into the larger track, then
+    tracks with two features of one view are dropped.  Returns Viewport::track_ids of all
+    views, concatenated (ids as the reference numbers them), and the number of tracks."""
+    features = np.asarray(features, np.int64)
+    base = np.concatenate([[0], np.cumsum(features)])
+    tid = np.full(int(base[-1]), -1, np.int64)
+    tracks = []                                             # lists of global feature ids
+    ij = np.asarray(ij).reshape(-1, 2)
+    for p in range(len(pair_views)):
+        v1, v2 = pair_views[p]
+        for k in range(offsets[p], offsets[p + 1]):
+            a, b = base[v1] + ij[k, 0], base[v2] + ij[k, 1]
+            t1, t2 = tid[a], tid[b]
+            if t1 == -1 and t2 == -1:
+                tid[a] = tid[b] = len(tracks)
+                tracks.append([a, b])
+            elif t1 == -1:
+                tid[a] = t2
+                tracks[t2].append(a)
+            elif t2 == -1:
+                tid[b] = t1
+                tracks[t1].append(b)
+            elif t1 != t2:
+                if len(tracks[t1]) < len(tracks[t2]):       # unify_tracks, :23-43
+                    t1, t2 = t2, t1
+                for g in tracks[t2]:
+                    tid[g] = t1
+                tracks[t1].extend(tracks[t2])
+                tracks[t2] = []
+    view_of = np.repeat(np.arange(len(features)), features)
+    keep = []
+    for t in tracks:                                        # remove_invalid_tracks, :148-203
+        keep.append(bool(t) and len(set(view_of[t].tolist())) == len(t))
+    remap = np.full(len(tracks), -1, np.int64)
+    remap[np.nonzero(keep)[0]] = np.arange(int(np.sum(keep)))
+    out = np.where(tid >= 0, remap[np.maximum(tid, 0)], -1).astype(np.int32)
+    return out, int(np.sum(keep))
+
+
 class Reference(_Impl):
     """The reference itself, compiled from /root/reference (oracle/_ref)."""
 
@@ -269,6 +326,19 @@ class Reference(_Impl):
                                          _ptr(pr, C.c_int), C.c_int(pr.shape[0]),
                                          C.c_float(ratio), _ptr(counts, C.c_int))
         return counts[:pr.shape[0]].copy()
+
+    def tracks_compute(self, features, pair_views, offsets, ij):
+        """The reference's own Tracks::compute through ref_driver.cc."""
+        features = _c(features, np.int32)
+        pv = _c(np.asarray(pair_views).reshape(-1, 2), np.int32)
+        off = _c(offsets, np.int64)
+        ijc = _c(np.asarray(ij).reshape(-1, 2), np.int32)
+        out = np.full(int(features.sum()), -9, np.int32)
+        f = self.lib.osfm_ref_tracks_compute
+        f.restype = C.c_int
+        n = f(C.c_int(len(features)), _ptr(features, C.c_int), C.c_int(len(pv)), _ptr(pv, C.c_int),
+              off.ctypes.data_as(C.POINTER(C.c_longlong)), _ptr(ijc, C.c_int), _ptr(out, C.c_int))
+        return out, int(n)
 
     def exhaustive(self, views_float):
         """views_float: list of (sift n x 128 float32, surf n x 64 float32)."""

@@ -20,6 +20,7 @@
  *   sfm::ExhaustiveMatching::{init,pairwise_match,pairwise_match_lowres}
  *                                             src/mve/sfm/exhaustive_matching.cc:56,115,147
  *   sfm::Sift::process                        src/mve/sfm/sift.cc (fixture producer only)
+ *   sfm::bundler::Tracks::compute             src/mve/sfm/bundler_tracks.cc:47-146
  */
 #include <algorithm>
 #include <cstdint>
@@ -32,6 +33,7 @@
 #endif
 
 #include "sfm/bundler_common.h"
+#include "sfm/bundler_tracks.h"
 #include "sfm/exhaustive_matching.h"
 #include "sfm/matching.h"
 #include "sfm/nearest_neighbor.h"
@@ -367,6 +369,41 @@ osfm_ref_sift_gray8 (const uint8_t* pixels, int width, int height,
         std::copy(descr[i].data.begin(), descr[i].data.end(),
             out_desc + (std::size_t)i * 128);
     return n;
+}
+
+/* ---- bundler::Tracks::compute (the consumer of the pairwise match lists) ------ */
+
+/* features[v] = number of features of view v; pair p = views (pair_views[2p],
+ * pair_views[2p+1]) with the correspondences ij[2*off[p]] .. ij[2*off[p+1]).
+ * track_ids receives, view after view, Viewport::track_ids as compute() leaves them
+ * (bundler_tracks.cc:58,148-203).  Returns the number of tracks. */
+int
+osfm_ref_tracks_compute (int num_views, const int* features, int npairs,
+    const int* pair_views, const long long* off, const int* ij, int* track_ids)
+{
+    sfm::bundler::ViewportList viewports(num_views);
+    for (int v = 0; v < num_views; ++v)
+    {
+        viewports[v].features.positions.resize(features[v]);
+        viewports[v].features.colors.resize(features[v], math::Vec3uc(0, 0, 0));
+    }
+    sfm::bundler::PairwiseMatching matching(npairs);
+    for (int p = 0; p < npairs; ++p)
+    {
+        matching[p].view_1_id = pair_views[2 * p + 0];
+        matching[p].view_2_id = pair_views[2 * p + 1];
+        for (long long k = off[p]; k < off[p + 1]; ++k)
+            matching[p].matches.push_back(std::make_pair(ij[2 * k], ij[2 * k + 1]));
+    }
+    sfm::bundler::TrackList tracks;
+    sfm::bundler::Tracks::Options topts;
+    sfm::bundler::Tracks computer(topts);
+    computer.compute(matching, &viewports, &tracks);
+    std::size_t at = 0;
+    for (int v = 0; v < num_views; ++v)
+        for (int f = 0; f < features[v]; ++f)
+            track_ids[at++] = viewports[v].track_ids[f];
+    return static_cast<int>(tracks.size());
 }
 
 } /* extern "C" */

@@ -24,7 +24,7 @@ EXPORTS = [
     "osfm_match_commit_device", "osfm_match_num_views", "osfm_match_view_size",
     "osfm_match_pair", "osfm_match_pair_twoway", "osfm_match_twoway_f32", "osfm_match_pair_lowres",
     "osfm_match_pairs_result_size", "osfm_match_pairs", "osfm_match_pairs_compact_device", "osfm_match_pairs_compact",
-    "osfm_match_two_view_default_options", "osfm_match_two_view_candidates",
+    "osfm_match_two_view_default_options", "osfm_match_two_view_candidates", "osfm_tracks_compute",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
 ]
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     L.osfm_match_two_view_default_options.restype = None
     L.osfm_match_two_view_candidates.argtypes = [vp, C.POINTER(TwoViewOptions), i32p, C.c_int, vp, C.c_int64,
                                                  i64p, i32p, i32p]
+    L.osfm_tracks_compute.argtypes = [vp, C.c_int, i32p, i32p, i64p, i32p, C.c_int, i32p, i32p, i32p]
     L.osfm_match_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
     L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]

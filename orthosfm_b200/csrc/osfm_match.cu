@@ -26,6 +26,7 @@
 #include "float_kernels.cuh"
 #include "post_kernels.cuh"
 #include "scan_kernel.cuh"
+#include "tracks_kernels.cuh"
 
 using namespace osfm;
 
@@ -1340,6 +1341,107 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
     }
     list_offset[npairs] = at;
     return OSFM_OK;
+}
+
+// ---- tracks (bundler::Tracks::compute) -------------------------------------------------------
+
+int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_per_view, const int32_t* pair_views,
+                        const int64_t* list_offset, const int32_t* match_ij, int npairs,
+                        int32_t* track_of_feature, int32_t* num_tracks, int32_t* num_conflicting) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (num_views < 0 || npairs < 0 || (num_views > 0 && !features_per_view) ||
+        (npairs > 0 && (!pair_views || !list_offset)) || !num_tracks)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
+    std::vector<int64_t> base(num_views + 1, 0);
+    for (int v = 0; v < num_views; ++v) {
+        if (features_per_view[v] < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative feature count");
+        base[v + 1] = base[v] + features_per_view[v];
+    }
+    int64_t const n64 = base[num_views];
+    if (n64 > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "more than 2^31 features");
+    int const n = static_cast<int>(n64);
+    int64_t const nedges = npairs > 0 ? list_offset[npairs] : 0;
+    for (int p = 0; p < npairs; ++p) {
+        OS_TRY((pair_views[2 * p] >= 0 && pair_views[2 * p] < num_views && pair_views[2 * p + 1] >= 0 &&
+                pair_views[2 * p + 1] < num_views && list_offset[p] <= list_offset[p + 1])
+                   ? OSFM_OK : fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad pair %d", p));
+    }
+    *num_tracks = 0;
+    if (num_conflicting) *num_conflicting = 0;
+    if (n == 0) return OSFM_OK;
+    if (!track_of_feature || (nedges > 0 && !match_ij)) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null buffer");
+    CU_TRY(m, cudaSetDevice(m->device));
+
+    // device scratch (sized per call; tracks are built once per reconstruction)
+    uint64_t cap = 1024;
+    while (cap < 2ull * static_cast<uint64_t>(n)) cap <<= 1;
+    int const nblocks = (n + kScanBlock - 1) / kScanBlock;
+    int *d_parent = nullptr, *d_size = nullptr, *d_conflict = nullptr, *d_flag = nullptr, *d_id = nullptr,
+        *d_bsum = nullptr, *d_small = nullptr;
+    int32_t *d_pv = nullptr, *d_vn = nullptr, *d_out = nullptr;
+    int64_t *d_off = nullptr, *d_base = nullptr;
+    int2* d_ij = nullptr;
+    unsigned long long* d_table = nullptr;
+    auto release = [&]() {
+        cudaFree(d_parent); cudaFree(d_size); cudaFree(d_conflict); cudaFree(d_flag); cudaFree(d_id); cudaFree(d_bsum);
+        cudaFree(d_small); cudaFree(d_pv); cudaFree(d_vn); cudaFree(d_out); cudaFree(d_off); cudaFree(d_base);
+        cudaFree(d_ij); cudaFree(d_table);
+    };
+    auto run = [&]() -> int {
+        size_t const ni = sizeof(int) * static_cast<size_t>(n);
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_parent), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_size), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_conflict), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_flag), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_id), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_out), ni));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_bsum), sizeof(int) * (nblocks + 1)));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_small), sizeof(int) * 4));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_table), sizeof(unsigned long long) * cap));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_base), sizeof(int64_t) * (num_views + 1)));
+        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_vn), sizeof(int32_t) * std::max(num_views, 1)));
+        CU_TRY(m, cudaMemsetAsync(d_size, 0, ni, m->stream));
+        CU_TRY(m, cudaMemsetAsync(d_conflict, 0, ni, m->stream));
+        CU_TRY(m, cudaMemsetAsync(d_small, 0, sizeof(int) * 4, m->stream));
+        CU_TRY(m, cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * cap, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(d_base, base.data(), sizeof(int64_t) * (num_views + 1), cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(d_vn, features_per_view, sizeof(int32_t) * num_views, cudaMemcpyHostToDevice, m->stream));
+        int const g = (n + 255) / 256;
+        tracks_init_kernel<<<g, 256, 0, m->stream>>>(d_parent, n);
+        if (nedges > 0) {
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_pv), sizeof(int32_t) * 2 * npairs));
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(int64_t) * (npairs + 1)));
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_ij), sizeof(int2) * nedges));
+            CU_TRY(m, cudaMemcpyAsync(d_pv, pair_views, sizeof(int32_t) * 2 * npairs, cudaMemcpyHostToDevice, m->stream));
+            CU_TRY(m, cudaMemcpyAsync(d_off, list_offset, sizeof(int64_t) * (npairs + 1), cudaMemcpyHostToDevice, m->stream));
+            CU_TRY(m, cudaMemcpyAsync(d_ij, match_ij, sizeof(int2) * nedges, cudaMemcpyHostToDevice, m->stream));
+            int64_t const ge = (nedges + 255) / 256;
+            tracks_union_kernel<<<static_cast<unsigned>(ge), 256, 0, m->stream>>>(d_parent, d_pv, d_off, npairs, d_ij, nedges,
+                                                                                 d_base, d_vn, d_small + 0);
+        }
+        tracks_root_kernel<<<g, 256, 0, m->stream>>>(d_parent, n, d_size);
+        tracks_conflict_kernel<<<g, 256, 0, m->stream>>>(d_parent, n, d_size, d_base, num_views, d_table, cap - 1, d_conflict);
+        tracks_flag_kernel<<<g, 256, 0, m->stream>>>(d_parent, d_size, d_conflict, n, d_flag, d_small + 1);
+        scan_partial_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum);
+        scan_sums_kernel<<<1, 1024, 0, m->stream>>>(d_bsum, nblocks, d_small + 2);
+        scan_apply_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum, d_id);
+        tracks_assign_kernel<<<g, 256, 0, m->stream>>>(d_parent, d_id, n, d_out);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches += nedges > 0 ? 9 : 8;
+        int small[4];
+        CU_TRY(m, cudaMemcpyAsync(track_of_feature, d_out, ni, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(small, d_small, sizeof small, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        if (small[0] != 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d matches refer to features outside their view", small[0]);
+        *num_tracks = small[2];
+        if (num_conflicting) *num_conflicting = small[1];
+        return OSFM_OK;
+    };
+    int const r = run();
+    release();
+    return r;
 }
 
 // ---- introspection ----------------------------------------------------------------------

@@ -349,6 +349,23 @@ class ExhaustiveMatching:
             loff.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(i32p), count.ctypes.data_as(i32p)))
         return [(int(status[p]), int(count[p]), ij[loff[p]:loff[p + 1]].copy()) for p in range(npairs)]
 
+    def tracks_compute(self, features_per_view, pair_views, offsets, ij) -> tuple:
+        """sfm::bundler::Tracks::compute (bundler_tracks.cc:47-203) on the device: returns
+        (track id of every feature or -1, view after view; number of tracks; number of
+        components dropped for holding two features of one view).  Tracks are numbered in
+        ascending order of their first feature."""
+        f = np.ascontiguousarray(features_per_view, np.int32)
+        pv = np.ascontiguousarray(np.asarray(pair_views, np.int32).reshape(-1, 2))
+        off = np.ascontiguousarray(offsets, np.int64)
+        m = np.ascontiguousarray(np.asarray(ij, np.int32).reshape(-1, 2))
+        out = np.full(int(f.sum()), -9, np.int32)
+        nt, nc = C.c_int32(0), C.c_int32(0)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_tracks_compute(
+            self._h, len(f), f.ctypes.data_as(i32p), pv.ctypes.data_as(i32p), off.ctypes.data_as(C.POINTER(C.c_int64)),
+            m.ctypes.data_as(i32p), len(pv), out.ctypes.data_as(i32p), C.byref(nt), C.byref(nc)))
+        return out, int(nt.value), int(nc.value)
+
     # -- introspection --------------------------------------------------------------------------
     def stats(self) -> dict:
         s = _lib.Stats()

@@ -607,6 +607,65 @@ def test_two_view_candidates_match_the_reference_gates(ora, lowres):
     assert [(a, b) for a, b, _ in prev] == [(a, b) for a, b, _ in want_prev]
 
 
+# ------------------------------------------------------------------ tracks
+
+def _random_match_lists(rng, feats, density):
+    pairs, lists, off = [], [], [0]
+    for v1 in range(1, len(feats)):
+        for v2 in range(v1):
+            if feats[v1] == 0 or feats[v2] == 0 or rng.random() > density:
+                continue
+            k = int(rng.integers(1, max(2, min(feats[v1], feats[v2]) // 3)))
+            i = np.sort(rng.choice(feats[v1], k, replace=False))
+            j = rng.choice(feats[v2], k, replace=False)
+            pairs.append((v1, v2))
+            lists.append(np.stack([i, j], 1))
+            off.append(off[-1] + k)
+    ij = np.concatenate(lists).astype(np.int32) if lists else np.zeros((0, 2), np.int32)
+    return pairs, np.array(off, np.int64), ij
+
+
+@pytest.mark.parametrize("seed,nviews,density", [(0, 6, 0.8), (1, 12, 0.5), (2, 30, 0.3), (3, 3, 1.0)])
+def test_tracks_equal_the_reference_partition(seed, nviews, density):
+    """Connected components of the match graph minus the components with two features of one
+    view = bundler::Tracks::compute, up to the numbering of the tracks (compared after
+    relabelling both in order of first appearance)."""
+    import oracle
+    rng = np.random.default_rng(seed)
+    feats = rng.integers(0, 400, nviews)
+    feats[rng.integers(0, nviews)] = 0
+    pairs, off, ij = _random_match_lists(rng, feats, density)
+    with ExhaustiveMatching() as m:
+        got, nt, nconf = m.tracks_compute(feats, pairs, off, ij)
+    want, nw = (oracle.Reference() if oracle.have_ref() else oracle).tracks_compute(feats, pairs, off, ij)
+    assert nt == nw
+    assert np.array_equal(got, oracle.canonical_track_ids(want))
+    assert np.array_equal(got, oracle.canonical_track_ids(got))       # numbered by first feature
+    if nviews >= 12:
+        assert nconf > 0                                              # conflicts occurred and were dropped
+
+
+def test_tracks_from_matcher_output(ora):
+    """The whole chain on the device side of the seam: match lists of all pairs of six views
+    (the matcher) -> tracks, against the oracle's tracks from the oracle's match lists."""
+    import oracle
+    vs = synth.sift_views(23, 6, 1500, noise="renorm")
+    pairs = synth.all_pairs(6)
+    with matcher(vs) as m:
+        out = np.empty((len(pairs) * 1500, 2), np.int32)
+        loff = m.match_pairs_lists(pairs, out)
+        got, nt, _ = m.tracks_compute([1500] * 6, pairs, loff, out[:loff[-1]])
+    lists = []
+    for v1, v2 in pairs:
+        o12, _ = ora.match_filtered("u8", vs[v1], vs[v2], 0.8)
+        i = np.nonzero(o12 >= 0)[0]
+        lists.append(np.stack([i, o12[i]], 1))
+    off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    want, nw = oracle.tracks_compute([1500] * 6, pairs, off, np.concatenate(lists))
+    assert nt == nw and nt > 100
+    assert np.array_equal(got, oracle.canonical_track_ids(want))
+
+
 # ------------------------------------------------------------------ the reference-side binding
 
 def test_reference_side_binding():

@@ -146,3 +146,30 @@ def test_oracle_pairwise_match_vs_reference_plugin(ora, ref):
         assert np.array_equal(o12, r12) and np.array_equal(o21, r21), (v1, v2)
         assert ora.pairwise_match_lowres(q[v1][0], q[v2][0], q[v1][1], q[v2][1], 150) == \
             ex.pairwise_match_lowres(v1, v2, 150)
+
+
+def test_tracks_restatement_equals_reference(ref):
+    """oracle.tracks_compute (the restatement of bundler::Tracks::compute) against the
+    reference's own code through ref_driver.cc: same track ids, feature by feature."""
+    import oracle
+    rng = np.random.default_rng(7)
+    feats = np.array([60, 45, 70, 0, 38, 52])
+    pairs, lists, off = [], [], [0]
+    for v1 in range(1, len(feats)):
+        for v2 in range(v1):
+            if feats[v1] == 0 or feats[v2] == 0 or rng.random() < 0.2:
+                continue
+            k = int(rng.integers(3, 30))
+            i = np.sort(rng.choice(feats[v1], k, replace=False))
+            j = rng.choice(feats[v2], k, replace=False)
+            pairs.append((v1, v2))
+            lists.append(np.stack([i, j], 1))
+            off.append(off[-1] + k)
+    ij = np.concatenate(lists).astype(np.int32)
+    off = np.array(off, np.int64)
+    a, na = ref.tracks_compute(feats, pairs, off, ij)
+    b, nb = oracle.tracks_compute(feats, pairs, off, ij)
+    assert na == nb and np.array_equal(a, b)
+    assert na > 10 and (a >= 0).sum() > 2 * na - 1
+    c = oracle.canonical_track_ids(a)
+    assert c.max() + 1 == na and np.array_equal(oracle.canonical_track_ids(c), c)
