@@ -123,6 +123,10 @@ struct osfm_matcher {
     DevBuf<int32_t> d_counts;
     DevBuf<int64_t> d_listoff;
     DevBuf<int2> d_list;
+    DevBuf<int> tr_ints;                 // tracks scratch (osfm_tracks_compute)
+    DevBuf<unsigned long long> tr_table;
+    DevBuf<int64_t> tr_meta;
+    DevBuf<int32_t> tr_meta32;
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
@@ -742,6 +746,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release();
     m->d_cand.release(); m->d_big.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release(); m->d_list.release();
+    m->tr_ints.release(); m->tr_table.release(); m->tr_meta.release(); m->tr_meta32.release();
     m->d_ftmp.release();
     m->d_seg_first.release();
     for (auto& sp : m->pass) sp.release();
@@ -1374,74 +1379,65 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
     if (!track_of_feature || (nedges > 0 && !match_ij)) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null buffer");
     CU_TRY(m, cudaSetDevice(m->device));
 
-    // device scratch (sized per call; tracks are built once per reconstruction)
+    // device scratch: grown on demand, kept with the handle
     uint64_t cap = 1024;
     while (cap < 2ull * static_cast<uint64_t>(n)) cap <<= 1;
     int const nblocks = (n + kScanBlock - 1) / kScanBlock;
-    int *d_parent = nullptr, *d_size = nullptr, *d_conflict = nullptr, *d_flag = nullptr, *d_id = nullptr,
-        *d_bsum = nullptr, *d_small = nullptr;
-    int32_t *d_pv = nullptr, *d_vn = nullptr, *d_out = nullptr;
-    int64_t *d_off = nullptr, *d_base = nullptr;
-    int2* d_ij = nullptr;
-    unsigned long long* d_table = nullptr;
-    auto release = [&]() {
-        cudaFree(d_parent); cudaFree(d_size); cudaFree(d_conflict); cudaFree(d_flag); cudaFree(d_id); cudaFree(d_bsum);
-        cudaFree(d_small); cudaFree(d_pv); cudaFree(d_vn); cudaFree(d_out); cudaFree(d_off); cudaFree(d_base);
-        cudaFree(d_ij); cudaFree(d_table);
-    };
-    auto run = [&]() -> int {
-        size_t const ni = sizeof(int) * static_cast<size_t>(n);
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_parent), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_size), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_conflict), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_flag), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_id), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_out), ni));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_bsum), sizeof(int) * (nblocks + 1)));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_small), sizeof(int) * 4));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_table), sizeof(unsigned long long) * cap));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_base), sizeof(int64_t) * (num_views + 1)));
-        CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_vn), sizeof(int32_t) * std::max(num_views, 1)));
-        CU_TRY(m, cudaMemsetAsync(d_size, 0, ni, m->stream));
-        CU_TRY(m, cudaMemsetAsync(d_conflict, 0, ni, m->stream));
-        CU_TRY(m, cudaMemsetAsync(d_small, 0, sizeof(int) * 4, m->stream));
-        CU_TRY(m, cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * cap, m->stream));
-        CU_TRY(m, cudaMemcpyAsync(d_base, base.data(), sizeof(int64_t) * (num_views + 1), cudaMemcpyHostToDevice, m->stream));
-        CU_TRY(m, cudaMemcpyAsync(d_vn, features_per_view, sizeof(int32_t) * num_views, cudaMemcpyHostToDevice, m->stream));
-        int const g = (n + 255) / 256;
-        tracks_init_kernel<<<g, 256, 0, m->stream>>>(d_parent, n);
-        if (nedges > 0) {
-            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_pv), sizeof(int32_t) * 2 * npairs));
-            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(int64_t) * (npairs + 1)));
-            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d_ij), sizeof(int2) * nedges));
-            CU_TRY(m, cudaMemcpyAsync(d_pv, pair_views, sizeof(int32_t) * 2 * npairs, cudaMemcpyHostToDevice, m->stream));
-            CU_TRY(m, cudaMemcpyAsync(d_off, list_offset, sizeof(int64_t) * (npairs + 1), cudaMemcpyHostToDevice, m->stream));
-            CU_TRY(m, cudaMemcpyAsync(d_ij, match_ij, sizeof(int2) * nedges, cudaMemcpyHostToDevice, m->stream));
-            int64_t const ge = (nedges + 255) / 256;
-            tracks_union_kernel<<<static_cast<unsigned>(ge), 256, 0, m->stream>>>(d_parent, d_pv, d_off, npairs, d_ij, nedges,
-                                                                                 d_base, d_vn, d_small + 0);
-        }
-        tracks_root_kernel<<<g, 256, 0, m->stream>>>(d_parent, n, d_size);
-        tracks_conflict_kernel<<<g, 256, 0, m->stream>>>(d_parent, n, d_size, d_base, num_views, d_table, cap - 1, d_conflict);
-        tracks_flag_kernel<<<g, 256, 0, m->stream>>>(d_parent, d_size, d_conflict, n, d_flag, d_small + 1);
-        scan_partial_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum);
-        scan_sums_kernel<<<1, 1024, 0, m->stream>>>(d_bsum, nblocks, d_small + 2);
-        scan_apply_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum, d_id);
-        tracks_assign_kernel<<<g, 256, 0, m->stream>>>(d_parent, d_id, n, d_out);
-        CU_TRY(m, cudaGetLastError());
-        m->stats.kernel_launches += nedges > 0 ? 9 : 8;
-        int small[4];
-        CU_TRY(m, cudaMemcpyAsync(track_of_feature, d_out, ni, cudaMemcpyDeviceToHost, m->stream));
-        CU_TRY(m, cudaMemcpyAsync(small, d_small, sizeof small, cudaMemcpyDeviceToHost, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
-        if (small[0] != 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d matches refer to features outside their view", small[0]);
-        *num_tracks = small[2];
-        if (num_conflicting) *num_conflicting = small[1];
-        return OSFM_OK;
-    };
-    int const r = run();
-    release();
-    return r;
+    size_t const ni = sizeof(int) * static_cast<size_t>(n);
+    // one int array holds parent | root | size | conflict | flag | id | out | block sums | 4 counters
+    size_t const ints = 7 * static_cast<size_t>(n) + static_cast<size_t>(nblocks) + 1 + 4;
+    CU_TRY(m, m->tr_ints.reserve(ints));
+    CU_TRY(m, m->tr_table.reserve(cap));
+    CU_TRY(m, m->tr_meta.reserve(static_cast<size_t>(num_views) + 1 + static_cast<size_t>(npairs) + 1));
+    CU_TRY(m, m->tr_meta32.reserve(static_cast<size_t>(std::max(num_views, 1)) + 2 * static_cast<size_t>(npairs)));
+    int* const d_parent = m->tr_ints.p;
+    int* const d_root = d_parent + n;
+    int* const d_size = d_root + n;
+    int* const d_conflict = d_size + n;
+    int* const d_flag = d_conflict + n;
+    int* const d_id = d_flag + n;
+    int32_t* const d_out = d_id + n;
+    int* const d_bsum = d_out + n;
+    int* const d_small = d_bsum + nblocks + 1;
+    int64_t* const d_base = m->tr_meta.p;
+    int64_t* const d_off = d_base + num_views + 1;
+    int32_t* const d_vn = m->tr_meta32.p;
+    int32_t* const d_pv = d_vn + std::max(num_views, 1);
+    unsigned long long* const d_table = m->tr_table.p;
+    CU_TRY(m, cudaMemsetAsync(d_size, 0, 2 * ni, m->stream));                       // size, conflict
+    CU_TRY(m, cudaMemsetAsync(d_small, 0, sizeof(int) * 4, m->stream));
+    CU_TRY(m, cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * cap, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(d_base, base.data(), sizeof(int64_t) * (num_views + 1), cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(d_vn, features_per_view, sizeof(int32_t) * num_views, cudaMemcpyHostToDevice, m->stream));
+    int const g = (n + 255) / 256;
+    tracks_init_kernel<<<g, 256, 0, m->stream>>>(d_parent, n);
+    if (nedges > 0) {
+        CU_TRY(m, m->d_list.reserve(static_cast<size_t>(nedges)));
+        int2* const d_ij = m->d_list.p;
+        CU_TRY(m, cudaMemcpyAsync(d_pv, pair_views, sizeof(int32_t) * 2 * npairs, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(d_off, list_offset, sizeof(int64_t) * (npairs + 1), cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(d_ij, match_ij, sizeof(int2) * nedges, cudaMemcpyHostToDevice, m->stream));
+        int64_t const ge = (nedges + 255) / 256;
+        tracks_union_kernel<<<static_cast<unsigned>(ge), 256, 0, m->stream>>>(d_parent, d_pv, d_off, npairs, d_ij, nedges,
+                                                                             d_base, d_vn, d_small + 0);
+    }
+    tracks_root_kernel<<<g, 256, 0, m->stream>>>(d_parent, n, d_root, d_size);
+    tracks_conflict_kernel<<<g, 256, 0, m->stream>>>(d_root, n, d_size, d_base, num_views, d_table, cap - 1, d_conflict);
+    tracks_flag_kernel<<<g, 256, 0, m->stream>>>(d_root, d_size, d_conflict, n, d_flag, d_small + 1);
+    scan_partial_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum);
+    scan_sums_kernel<<<1, 1024, 0, m->stream>>>(d_bsum, nblocks, d_small + 2);
+    scan_apply_kernel<<<nblocks, 256, 0, m->stream>>>(d_flag, n, d_bsum, d_id);
+    tracks_assign_kernel<<<g, 256, 0, m->stream>>>(d_root, d_id, n, d_out);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += nedges > 0 ? 9 : 8;
+    int small[4];
+    CU_TRY(m, cudaMemcpyAsync(track_of_feature, d_out, ni, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(small, d_small, sizeof small, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    if (small[0] != 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d matches refer to features outside their view", small[0]);
+    *num_tracks = small[2];
+    if (num_conflicting) *num_conflicting = small[1];
+    return OSFM_OK;
 }
 
 // ---- introspection ----------------------------------------------------------------------

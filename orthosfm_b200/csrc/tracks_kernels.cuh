@@ -77,12 +77,19 @@ __global__ void __launch_bounds__(256) tracks_union_kernel(int* __restrict__ par
     }
 }
 
-// root[i] for every node, component sizes (at the root).
-__global__ void __launch_bounds__(256) tracks_root_kernel(int* __restrict__ parent, int n, int* __restrict__ size) {
+// root[i] for every node (read-only walk: path compression here would let one thread overwrite
+// the final root another thread has just stored with a mere ancestor), component sizes.
+__global__ void __launch_bounds__(256) tracks_root_kernel(const int* __restrict__ parent, int n,
+                                                          int* __restrict__ root, int* __restrict__ size) {
     int const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int const r = uf_find(parent, i);
-    parent[i] = r;
+    int r = i;
+    while (true) {
+        int const p = parent[r];
+        if (p == r) break;
+        r = p;
+    }
+    root[i] = r;
     atomicAdd(size + r, 1);
 }
 

@@ -645,6 +645,37 @@ def test_tracks_equal_the_reference_partition(seed, nviews, density):
         assert nconf > 0                                              # conflicts occurred and were dropped
 
 
+def test_tracks_heavy_merging_is_deterministic():
+    """Long chains and heavily contended unions (each feature matched in most pairs), three
+    times over: the partition is the reference's every time."""
+    import oracle
+    rng = np.random.default_rng(11)
+    nviews, nf = 40, 2500
+    feats = np.full(nviews, nf)
+    pairs, lists, off = [], [], [0]
+    for v1 in range(1, nviews):
+        for v2 in range(v1):
+            k = 1500
+            i = np.sort(rng.choice(nf, k, replace=False))
+            # mostly "the same physical point" (same index) plus a few wrong matches that fuse
+            # tracks and create conflicts
+            j = i.copy()
+            wrong = rng.random(k) < 0.002
+            j[wrong] = rng.integers(0, nf, int(wrong.sum()))
+            pairs.append((v1, v2))
+            lists.append(np.stack([i, j], 1))
+            off.append(off[-1] + k)
+    ij = np.concatenate(lists).astype(np.int32)
+    off = np.array(off, np.int64)
+    want, nw = (oracle.Reference() if oracle.have_ref() else oracle).tracks_compute(feats, pairs, off, ij)
+    want = oracle.canonical_track_ids(want)
+    with ExhaustiveMatching() as m:
+        for _ in range(3):
+            got, nt, nconf = m.tracks_compute(feats, pairs, off, ij)
+            assert nt == nw and nconf > 0
+            assert np.array_equal(got, want)
+
+
 def test_tracks_from_matcher_output(ora):
     """The whole chain on the device side of the seam: match lists of all pairs of six views
     (the matcher) -> tracks, against the oracle's tracks from the oracle's match lists."""
