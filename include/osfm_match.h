@@ -41,7 +41,8 @@ typedef enum {
     OSFM_ERR_CUDA = -3,             /* a CUDA call failed, see last_error        */
     OSFM_ERR_STATE = -4,            /* call order violated (e.g. match before commit) */
     OSFM_ERR_OUT_OF_MEMORY = -5,
-    OSFM_ERR_INTERNAL = -6          /* self-check failed inside a kernel          */
+    OSFM_ERR_INTERNAL = -6,         /* self-check failed inside a kernel          */
+    OSFM_ERR_IO = -7                /* a file could not be read or written        */
 } osfm_status;
 
 /* Descriptor kinds (reference: exhaustive_matching.h:46-48). */
@@ -233,6 +234,59 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
 int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_per_view,
     const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij, int npairs,
     int32_t* track_of_feature, int32_t* num_tracks, int32_t* num_conflicting);
+
+/* ---- on-disk format --------------------------------------------------------
+ * The MVE "prebundle" file (sfm::bundler::save_prebundle_to_file /
+ * load_prebundle_from_file, src/mve/sfm/bundler_common.cc:56-190): feature
+ * positions and colors per view plus the pairwise match lists -- the file through
+ * which MVE's own tools pick up a matching result.  Byte-identical to the
+ * reference's writer for the same data.  positions (2 floats per feature) and colors
+ * (3 bytes per feature) are concatenated over the views and may be NULL (written as
+ * empty vectors).  Host code only; no handle needed. */
+int osfm_io_save_prebundle(const char* path, int num_views, const int32_t* features_per_view,
+    const float* positions, const uint8_t* colors, int npairs, const int32_t* pair_views,
+    const int64_t* list_offset, const int32_t* match_ij);
+
+typedef struct osfm_prebundle osfm_prebundle;
+/* Reads a file; the counts size the buffers for osfm_io_prebundle_get (any of which
+ * may be NULL): n_positions / n_colors [num_views], positions [2*num_positions],
+ * colors [3*num_colors], pair_views [2*npairs], list_offset [npairs+1],
+ * match_ij [2*num_matches]. */
+int osfm_io_load_prebundle(const char* path, osfm_prebundle** out, int* num_views,
+    int64_t* num_positions, int64_t* num_colors, int* npairs, int64_t* num_matches);
+int osfm_io_prebundle_get(const osfm_prebundle* h, int32_t* n_positions, int32_t* n_colors,
+    float* positions, uint8_t* colors, int32_t* pair_views, int64_t* list_offset, int32_t* match_ij);
+void osfm_io_prebundle_free(osfm_prebundle* h);
+
+/* tracks.txt (orthosfm::saveTracksToFile / loadTracksFromFile,
+ * src/matching/matching_io.cpp:16-95; replayed with --calculated-tracks,
+ * src/sfm/reconstruct.cpp:70-78) written from osfm_tracks_compute's result: one line per
+ * track, "count;{viewID;localID;globalID;x;y;r;g;b}*", the Feature fields as the MVE bridge
+ * fills them (src/matching/matching_mve.cpp:455-466): globalID = 32768*view + feature,
+ * x|y = image_width * (position + 0.5).  positions: normalised MVE feature positions,
+ * 2 floats per feature, concatenated over the views; colors (r, g, b bytes) may be NULL
+ * (zeros, what the bridge writes before propagateColorsToTracks).  Tracks come in ascending
+ * id, features inside a track in ascending (view, feature). */
+int osfm_io_save_tracks(const char* path, int num_views, const int32_t* features_per_view,
+    const int32_t* track_of_feature, int num_tracks, const float* positions, double image_width,
+    const uint8_t* colors);
+
+/* The AAA_BBB.txt files of orthosfm::saveTracksToPairwiseFiles
+ * (src/matching/matching_io.cpp:97-140): for every two views sharing a track, the lines
+ * "x1 y1 x2 y2" of the tracks seen by both.  View ids are the view indices. */
+int osfm_io_save_pairwise_tracks(const char* folder, int num_views, const int32_t* features_per_view,
+    const int32_t* track_of_feature, int num_tracks, const float* positions, double image_width,
+    int* files_written);
+
+typedef struct osfm_track_table osfm_track_table;
+/* Reads a tracks.txt; osfm_io_track_table_get fills (any may be NULL) track_offset
+ * [num_tracks+1], ids [3*num_features] (view, local id, global id), xy [2*num_features],
+ * rgb [3*num_features]. */
+int osfm_io_load_tracks(const char* path, osfm_track_table** out, int64_t* num_tracks,
+    int64_t* num_features);
+int osfm_io_track_table_get(const osfm_track_table* h, int64_t* track_offset, uint32_t* ids,
+    float* xy, uint32_t* rgb);
+void osfm_io_track_table_free(osfm_track_table* h);
 
 /* ---- introspection --------------------------------------------------------- */
 

@@ -303,6 +303,89 @@ def tracks_compute(features, pair_views, offsets, ij):
     return out, int(np.sum(keep))
 
 
+# ---- tracks.txt / AAA_BBB.txt -------------------------------------------------------------------
+# PARITY UNPINNED: src/matching/matching_io.cpp includes Boost, OpenCV and Eigen headers (through
+# data_structures/track.h), none of which is in this image, so the reference's writer cannot be
+# compiled here; the functions below restate it line by line and the reference holds no golden
+# file for these formats.
+
+def _g(x) -> str:
+    """operator<<(ostream&, float) with the default precision 6 -- printf's %g."""
+    return "%g" % float(np.float32(x))
+
+
+def tracks_from_ids(features, track_ids, positions, image_width, colors=None):
+    """The std::vector<Track> of the MVE bridge (src/matching/matching_mve.cpp:455-466) for
+    the given Viewport::track_ids: per track a list of
+    (viewID, localFeatureID, globalFeatureID, x, y, r, g, b).  Features inside a track in
+    ascending (view, feature) -- the reference's order inside a track follows its walk over
+    the pairs and is not part of the format (loadTracksFromFile takes any)."""
+    track_ids = np.asarray(track_ids)
+    tracks = [[] for _ in range(int(track_ids.max()) + 1 if len(track_ids) else 0)]
+    at = 0
+    for v, n in enumerate(features):
+        for f in range(int(n)):
+            t = int(track_ids[at])
+            if t >= 0:
+                x = np.float32(float(image_width) * (float(np.float32(positions[at][0])) + 0.5))
+                y = np.float32(float(image_width) * (float(np.float32(positions[at][1])) + 0.5))
+                rgb = (0, 0, 0) if colors is None else tuple(int(c) for c in colors[at])
+                tracks[t].append((v, f, 32768 * v + f, x, y) + rgb)
+            at += 1
+    return tracks
+
+
+def save_tracks_text(tracks) -> str:
+    """orthosfm::saveTracksToFile (src/matching/matching_io.cpp:16-50)."""
+    out = []
+    for tr in tracks:
+        line = "%d;" % len(tr)
+        line += ";".join("%d;%d;%d;%s;%s;%d;%d;%d" % (f[0], f[1], f[2], _g(f[3]), _g(f[4]), f[5], f[6], f[7])
+                         for f in tr)
+        out.append(line + "\n")
+    return "".join(out)
+
+
+def load_tracks_text(text: str):
+    """orthosfm::loadTracksFromFile (src/matching/matching_io.cpp:52-95)."""
+    tracks = []
+    for line in text.splitlines():
+        tok = line.split(";")
+        n = int(tok[0])
+        tr = []
+        for k in range(n):
+            q = tok[1 + 8 * k: 9 + 8 * k]
+            tr.append((int(q[0]), int(q[1]), int(q[2]), np.float32(q[3]), np.float32(q[4]), int(q[5]), int(q[6]),
+                       int(q[7])))
+        tracks.append(tr)
+    return tracks
+
+
+def save_pairwise_tracks_text(tracks, view_ids) -> dict:
+    """orthosfm::saveTracksToPairwiseFiles (src/matching/matching_io.cpp:97-140) with
+    filterTracksToAvailableCameras(ids, tracks, true, false) (src/util/common.cpp:85-130):
+    {file name: content}."""
+    files = {}
+    for a in range(len(view_ids)):
+        for b in range(a + 1, len(view_ids)):
+            ids = [view_ids[a], view_ids[b]]
+            filtered = []
+            for tr in tracks:
+                cur = [f for f in tr if f[0] in ids]
+                if len(cur) == len(ids):
+                    filtered.append(cur)
+            if not filtered:
+                continue
+            text = ""
+            for tr in filtered:
+                for k, vid in enumerate(ids):
+                    for f in tr:
+                        if f[0] == vid:
+                            text += _g(f[3]) + " " + _g(f[4]) + (" " if k == 0 else "\n")
+            files["%03d_%03d.txt" % (ids[0], ids[1])] = text
+    return files
+
+
 class Reference(_Impl):
     """The reference itself, compiled from /root/reference (oracle/_ref)."""
 
@@ -339,6 +422,33 @@ class Reference(_Impl):
         n = f(C.c_int(len(features)), _ptr(features, C.c_int), C.c_int(len(pv)), _ptr(pv, C.c_int),
               off.ctypes.data_as(C.POINTER(C.c_longlong)), _ptr(ijc, C.c_int), _ptr(out, C.c_int))
         return out, int(n)
+
+    def save_prebundle(self, path, features, positions, colors, pair_views, offsets, ij) -> None:
+        """The reference's own save_prebundle_to_file (bundler_common.cc:180-188)."""
+        features = _c(features, np.int32)
+        pv = _c(np.asarray(pair_views).reshape(-1, 2), np.int32)
+        off = _c(offsets, np.int64)
+        ijc = _c(np.asarray(ij).reshape(-1, 2), np.int32)
+        pos, col = _c(positions, np.float32), _c(colors, np.uint8)
+        f = self.lib.osfm_ref_save_prebundle
+        f.restype = C.c_int
+        rc = f(path.encode(), C.c_int(len(features)), _ptr(features, C.c_int), _ptr(pos, C.c_float),
+               _ptr(col, C.c_ubyte), C.c_int(len(pv)), _ptr(pv, C.c_int),
+               off.ctypes.data_as(C.POINTER(C.c_longlong)), _ptr(ijc, C.c_int))
+        if rc != 0:
+            raise OSError(f"reference could not write {path}")
+
+    def load_prebundle_digest(self, path):
+        """Counts and checksums of a prebundle file as the reference's load_prebundle_from_file
+        reads it (bundler_common.cc:110-178, 190-198)."""
+        counts = np.zeros(4, np.int64)
+        sums = np.zeros(3, np.float64)
+        f = self.lib.osfm_ref_load_prebundle_digest
+        f.restype = C.c_int
+        rc = f(path.encode(), counts.ctypes.data_as(C.POINTER(C.c_longlong)), sums.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc != 0:
+            raise OSError(f"reference could not read {path}")
+        return counts, sums
 
     def exhaustive(self, views_float):
         """views_float: list of (sift n x 128 float32, surf n x 64 float32)."""

@@ -21,6 +21,8 @@
  *                                             src/mve/sfm/exhaustive_matching.cc:56,115,147
  *   sfm::Sift::process                        src/mve/sfm/sift.cc (fixture producer only)
  *   sfm::bundler::Tracks::compute             src/mve/sfm/bundler_tracks.cc:47-146
+ *   sfm::bundler::save_prebundle_to_file / load_prebundle_from_file
+ *                                             src/mve/sfm/bundler_common.cc:56-190
  */
 #include <algorithm>
 #include <cstdint>
@@ -404,6 +406,71 @@ osfm_ref_tracks_compute (int num_views, const int* features, int npairs,
         for (int f = 0; f < features[v]; ++f)
             track_ids[at++] = viewports[v].track_ids[f];
     return static_cast<int>(tracks.size());
+}
+
+/* ---- prebundle file through the reference's own writer / reader -------------- */
+
+/* Writes `path` with save_prebundle_to_file.  positions: 2 floats, colors: 3 bytes per
+ * feature, concatenated over the views. */
+int
+osfm_ref_save_prebundle (const char* path, int num_views, const int* features,
+    const float* positions, const unsigned char* colors, int npairs,
+    const int* pair_views, const long long* off, const int* ij)
+{
+    sfm::bundler::ViewportList viewports(num_views);
+    std::size_t at = 0;
+    for (int v = 0; v < num_views; ++v)
+    {
+        for (int f = 0; f < features[v]; ++f, ++at)
+        {
+            viewports[v].features.positions.push_back(
+                math::Vec2f(positions[2 * at], positions[2 * at + 1]));
+            viewports[v].features.colors.push_back(
+                math::Vec3uc(colors[3 * at], colors[3 * at + 1], colors[3 * at + 2]));
+        }
+    }
+    sfm::bundler::PairwiseMatching matching(npairs);
+    for (int p = 0; p < npairs; ++p)
+    {
+        matching[p].view_1_id = pair_views[2 * p + 0];
+        matching[p].view_2_id = pair_views[2 * p + 1];
+        for (long long k = off[p]; k < off[p + 1]; ++k)
+            matching[p].matches.push_back(std::make_pair(ij[2 * k], ij[2 * k + 1]));
+    }
+    try { sfm::bundler::save_prebundle_to_file(viewports, matching, path); }
+    catch (...) { return -1; }
+    return 0;
+}
+
+/* Reads `path` with load_prebundle_from_file and returns a digest the test compares:
+ * counts[0..3] = views, features (positions), pairs, matches; sums[0..2] = sum of the
+ * positions, of the color bytes, of i*31 + j*17 + view ids over the matches. */
+int
+osfm_ref_load_prebundle_digest (const char* path, long long* counts, double* sums)
+{
+    sfm::bundler::ViewportList viewports;
+    sfm::bundler::PairwiseMatching matching;
+    try { sfm::bundler::load_prebundle_from_file(path, &viewports, &matching); }
+    catch (...) { return -1; }
+    counts[0] = viewports.size(); counts[1] = 0; counts[2] = matching.size(); counts[3] = 0;
+    sums[0] = sums[1] = sums[2] = 0.0;
+    for (std::size_t v = 0; v < viewports.size(); ++v)
+    {
+        counts[1] += viewports[v].features.positions.size();
+        for (std::size_t f = 0; f < viewports[v].features.positions.size(); ++f)
+            sums[0] += viewports[v].features.positions[f][0] + 2.0 * viewports[v].features.positions[f][1];
+        for (std::size_t f = 0; f < viewports[v].features.colors.size(); ++f)
+            sums[1] += viewports[v].features.colors[f][0] + 3.0 * viewports[v].features.colors[f][1]
+                + 5.0 * viewports[v].features.colors[f][2];
+    }
+    for (std::size_t p = 0; p < matching.size(); ++p)
+    {
+        counts[3] += matching[p].matches.size();
+        sums[2] += 1000.0 * matching[p].view_1_id + 7.0 * matching[p].view_2_id;
+        for (std::size_t k = 0; k < matching[p].matches.size(); ++k)
+            sums[2] += 31.0 * matching[p].matches[k].first + 17.0 * matching[p].matches[k].second;
+    }
+    return 0;
 }
 
 } /* extern "C" */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libosfm_match.so")
 OSFM_OK = 0
 ERR_NAMES = {
     -1: "OSFM_ERR_INVALID_ARGUMENT", -2: "OSFM_ERR_NO_DEVICE", -3: "OSFM_ERR_CUDA",
-    -4: "OSFM_ERR_STATE", -5: "OSFM_ERR_OUT_OF_MEMORY", -6: "OSFM_ERR_INTERNAL",
+    -4: "OSFM_ERR_STATE", -5: "OSFM_ERR_OUT_OF_MEMORY", -6: "OSFM_ERR_INTERNAL", -7: "OSFM_ERR_IO",
 }
 KIND_SIFT_U8 = 0
 KIND_SURF_S8 = 1
@@ -25,6 +25,9 @@ EXPORTS = [
     "osfm_match_pair", "osfm_match_pair_twoway", "osfm_match_twoway_f32", "osfm_match_pair_lowres",
     "osfm_match_pairs_result_size", "osfm_match_pairs", "osfm_match_pairs_compact_device", "osfm_match_pairs_compact",
     "osfm_match_two_view_default_options", "osfm_match_two_view_candidates", "osfm_tracks_compute",
+    "osfm_io_save_prebundle", "osfm_io_load_prebundle", "osfm_io_prebundle_get", "osfm_io_prebundle_free",
+    "osfm_io_save_tracks", "osfm_io_save_pairwise_tracks", "osfm_io_load_tracks", "osfm_io_track_table_get",
+    "osfm_io_track_table_free",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
 ]
 
@@ -103,6 +106,19 @@ def load() -> C.CDLL:
     L.osfm_match_two_view_candidates.argtypes = [vp, C.POINTER(TwoViewOptions), i32p, C.c_int, vp, C.c_int64,
                                                  i64p, i32p, i32p]
     L.osfm_tracks_compute.argtypes = [vp, C.c_int, i32p, i32p, i64p, i32p, C.c_int, i32p, i32p, i32p]
+    f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    L.osfm_io_save_prebundle.argtypes = [C.c_char_p, C.c_int, i32p, f32p, u8p, C.c_int, i32p, i64p, i32p]
+    L.osfm_io_load_prebundle.argtypes = [C.c_char_p, C.POINTER(vp), ip, i64p, i64p, ip, i64p]
+    L.osfm_io_prebundle_get.argtypes = [vp, i32p, i32p, f32p, u8p, i32p, i64p, i32p]
+    L.osfm_io_prebundle_free.argtypes = [vp]
+    L.osfm_io_prebundle_free.restype = None
+    u32p = C.POINTER(C.c_uint32)
+    L.osfm_io_save_tracks.argtypes = [C.c_char_p, C.c_int, i32p, i32p, C.c_int, f32p, C.c_double, u8p]
+    L.osfm_io_save_pairwise_tracks.argtypes = [C.c_char_p, C.c_int, i32p, i32p, C.c_int, f32p, C.c_double, ip]
+    L.osfm_io_load_tracks.argtypes = [C.c_char_p, C.POINTER(vp), i64p, i64p]
+    L.osfm_io_track_table_get.argtypes = [vp, i64p, u32p, f32p, u32p]
+    L.osfm_io_track_table_free.argtypes = [vp]
+    L.osfm_io_track_table_free.restype = None
     L.osfm_match_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
     L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]

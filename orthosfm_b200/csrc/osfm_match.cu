@@ -24,6 +24,7 @@
 
 #include "../../include/osfm_match.h"
 #include "float_kernels.cuh"
+#include "io_formats.cuh"
 #include "post_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "tracks_kernels.cuh"
@@ -1439,6 +1440,136 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
     if (num_conflicting) *num_conflicting = small[1];
     return OSFM_OK;
 }
+
+// ---- on-disk format (MVE prebundle) ------------------------------------------------------------
+
+int osfm_io_save_prebundle(const char* path, int num_views, const int32_t* features_per_view,
+                           const float* positions, const uint8_t* colors, int npairs,
+                           const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij) {
+    if (!path || num_views < 0 || npairs < 0 || (num_views > 0 && !features_per_view) ||
+        (npairs > 0 && (!pair_views || !list_offset)))
+        return OSFM_ERR_INVALID_ARGUMENT;
+    for (int p = 0; p < npairs; ++p) {
+        int64_t const k = list_offset[p + 1] - list_offset[p];
+        if (k < 0 || k > INT32_MAX || (k > 0 && !match_ij)) return OSFM_ERR_INVALID_ARGUMENT;
+    }
+    return save_prebundle(path, num_views, features_per_view, positions, colors, npairs, pair_views, list_offset,
+                          match_ij) == 0 ? OSFM_OK : OSFM_ERR_IO;
+}
+
+struct osfm_prebundle {
+    PrebundleData d;
+};
+
+int osfm_io_load_prebundle(const char* path, osfm_prebundle** out, int* num_views, int64_t* num_positions,
+                           int64_t* num_colors, int* npairs, int64_t* num_matches) {
+    if (!path || !out) return OSFM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    osfm_prebundle* h = new (std::nothrow) osfm_prebundle();
+    if (!h) return OSFM_ERR_OUT_OF_MEMORY;
+    int const r = load_prebundle(path, &h->d);
+    if (r != 0) { delete h; return r == 1 ? OSFM_ERR_IO : OSFM_ERR_INVALID_ARGUMENT; }
+    if (num_views) *num_views = static_cast<int>(h->d.n_positions.size());
+    if (num_positions) *num_positions = static_cast<int64_t>(h->d.positions.size() / 2);
+    if (num_colors) *num_colors = static_cast<int64_t>(h->d.colors.size() / 3);
+    if (npairs) *npairs = static_cast<int>(h->d.pair_views.size() / 2);
+    if (num_matches) *num_matches = h->d.list_offset.back();
+    *out = h;
+    return OSFM_OK;
+}
+
+int osfm_io_prebundle_get(const osfm_prebundle* h, int32_t* n_positions, int32_t* n_colors, float* positions,
+                          uint8_t* colors, int32_t* pair_views, int64_t* list_offset, int32_t* match_ij) {
+    if (!h) return OSFM_ERR_INVALID_ARGUMENT;
+    PrebundleData const& d = h->d;
+    auto cp = [](void* dst, const void* src, size_t bytes) { if (dst && bytes) memcpy(dst, src, bytes); };
+    cp(n_positions, d.n_positions.data(), sizeof(int32_t) * d.n_positions.size());
+    cp(n_colors, d.n_colors.data(), sizeof(int32_t) * d.n_colors.size());
+    cp(positions, d.positions.data(), sizeof(float) * d.positions.size());
+    cp(colors, d.colors.data(), d.colors.size());
+    cp(pair_views, d.pair_views.data(), sizeof(int32_t) * d.pair_views.size());
+    cp(list_offset, d.list_offset.data(), sizeof(int64_t) * d.list_offset.size());
+    cp(match_ij, d.match_ij.data(), sizeof(int32_t) * d.match_ij.size());
+    return OSFM_OK;
+}
+
+void osfm_io_prebundle_free(osfm_prebundle* h) { delete h; }
+
+// ---- on-disk formats (tracks.txt, AAA_BBB.txt) -------------------------------------------------
+
+static int track_table_from_ids(int num_views, const int32_t* features_per_view, const int32_t* track_of_feature,
+                                int num_tracks, const float* positions, double image_width, const uint8_t* colors,
+                                TrackTable* t) {
+    if (num_views < 0 || num_tracks < 0 || (num_views > 0 && !features_per_view)) return OSFM_ERR_INVALID_ARGUMENT;
+    int64_t total = 0;
+    for (int v = 0; v < num_views; ++v) {
+        if (features_per_view[v] < 0) return OSFM_ERR_INVALID_ARGUMENT;
+        total += features_per_view[v];
+    }
+    if (total > 0 && !track_of_feature) return OSFM_ERR_INVALID_ARGUMENT;
+    return build_track_table(num_views, features_per_view, track_of_feature, num_tracks, positions, image_width,
+                             colors, t) == 0 ? OSFM_OK : OSFM_ERR_INVALID_ARGUMENT;
+}
+
+int osfm_io_save_tracks(const char* path, int num_views, const int32_t* features_per_view,
+                        const int32_t* track_of_feature, int num_tracks, const float* positions,
+                        double image_width, const uint8_t* colors) {
+    if (!path) return OSFM_ERR_INVALID_ARGUMENT;
+    TrackTable t;
+    int const rc = track_table_from_ids(num_views, features_per_view, track_of_feature, num_tracks, positions,
+                                        image_width, colors, &t);
+    if (rc != OSFM_OK) return rc;
+    return save_tracks(path, t) == 0 ? OSFM_OK : OSFM_ERR_IO;
+}
+
+int osfm_io_save_pairwise_tracks(const char* folder, int num_views, const int32_t* features_per_view,
+                                 const int32_t* track_of_feature, int num_tracks, const float* positions,
+                                 double image_width, int* files_written) {
+    if (!folder) return OSFM_ERR_INVALID_ARGUMENT;
+    TrackTable t;
+    int const rc = track_table_from_ids(num_views, features_per_view, track_of_feature, num_tracks, positions,
+                                        image_width, nullptr, &t);
+    if (rc != OSFM_OK) return rc;
+    std::vector<int32_t> ids(static_cast<size_t>(num_views));
+    for (int v = 0; v < num_views; ++v) ids[v] = v;
+    int const n = save_pairwise_tracks(folder, t, num_views, ids.data());
+    if (n < 0) return OSFM_ERR_IO;
+    if (files_written) *files_written = n;
+    return OSFM_OK;
+}
+
+struct osfm_track_table {
+    TrackTable t;
+};
+
+int osfm_io_load_tracks(const char* path, osfm_track_table** out, int64_t* num_tracks, int64_t* num_features) {
+    if (!path || !out) return OSFM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    osfm_track_table* h = new (std::nothrow) osfm_track_table();
+    if (!h) return OSFM_ERR_OUT_OF_MEMORY;
+    int const r = load_tracks(path, &h->t);
+    if (r != 0) { delete h; return r == 1 ? OSFM_ERR_IO : OSFM_ERR_INVALID_ARGUMENT; }
+    if (num_tracks) *num_tracks = static_cast<int64_t>(h->t.offset.size()) - 1;
+    if (num_features) *num_features = static_cast<int64_t>(h->t.features.size());
+    *out = h;
+    return OSFM_OK;
+}
+
+int osfm_io_track_table_get(const osfm_track_table* h, int64_t* track_offset, uint32_t* ids, float* xy,
+                            uint32_t* rgb) {
+    if (!h) return OSFM_ERR_INVALID_ARGUMENT;
+    TrackTable const& t = h->t;
+    if (track_offset) memcpy(track_offset, t.offset.data(), sizeof(int64_t) * t.offset.size());
+    for (size_t i = 0; i < t.features.size(); ++i) {
+        TrackFeature const& o = t.features[i];
+        if (ids) { ids[3 * i] = o.view; ids[3 * i + 1] = o.local_id; ids[3 * i + 2] = o.global_id; }
+        if (xy) { xy[2 * i] = o.x; xy[2 * i + 1] = o.y; }
+        if (rgb) { rgb[3 * i] = o.r; rgb[3 * i + 1] = o.g; rgb[3 * i + 2] = o.b; }
+    }
+    return OSFM_OK;
+}
+
+void osfm_io_track_table_free(osfm_track_table* h) { delete h; }
 
 // ---- introspection ----------------------------------------------------------------------
 

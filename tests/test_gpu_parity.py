@@ -697,6 +697,45 @@ def test_tracks_from_matcher_output(ora):
     assert np.array_equal(got, oracle.canonical_track_ids(want))
 
 
+def test_matcher_output_through_the_file_formats(ora, tmp_path):
+    """Match lists -> prebundle.sfm (read back by the reference's own loader when it is built)
+    and match lists -> tracks -> tracks.txt (equal to the restated writer on the oracle's
+    tracks)."""
+    import oracle
+    from orthosfm_b200 import io as osio
+    nv, n = 5, 1200
+    vs = synth.sift_views(31, nv, n, noise="renorm")
+    pairs = synth.all_pairs(nv)
+    rng = np.random.default_rng(5)
+    pos = (rng.random((nv * n, 2), dtype=np.float32) - 0.5)
+    col = rng.integers(0, 256, (nv * n, 3), dtype=np.uint8)
+    with matcher(vs) as m:
+        out = np.empty((len(pairs) * n, 2), np.int32)
+        loff = m.match_pairs_lists(pairs, out)
+        ij = out[:loff[-1]]
+        ids, nt, _ = m.tracks_compute([n] * nv, pairs, loff, ij)
+    pre = str(tmp_path / "prebundle.sfm")
+    osio.save_prebundle(pre, [n] * nv, pos, col, pairs, loff, ij)
+    d = osio.load_prebundle(pre)
+    assert np.array_equal(d["ij"], ij) and np.array_equal(d["offsets"], loff)
+    if oracle.have_ref():
+        counts, sums = oracle.Reference().load_prebundle_digest(pre)
+        assert counts.tolist() == [nv, nv * n, len(pairs), len(ij)]
+        pv = np.asarray(pairs, np.float64)
+        assert sums[2] == float((1000 * pv[:, 0] + 7 * pv[:, 1]).sum() + (31.0 * ij[:, 0] + 17.0 * ij[:, 1]).sum())
+    lists = []
+    for v1, v2 in pairs:
+        o12, _ = ora.match_filtered("u8", vs[v1], vs[v2], 0.8)
+        i = np.nonzero(o12 >= 0)[0]
+        lists.append(np.stack([i, o12[i]], 1))
+    off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    want, nw = oracle.tracks_compute([n] * nv, pairs, off, np.concatenate(lists))
+    txt = str(tmp_path / "tracks.txt")
+    osio.save_tracks(txt, [n] * nv, ids, nt, pos, 2048.0, col)
+    assert open(txt).read() == oracle.save_tracks_text(
+        oracle.tracks_from_ids([n] * nv, oracle.canonical_track_ids(want), pos, 2048.0, col))
+
+
 # ------------------------------------------------------------------ the reference-side binding
 
 def test_reference_side_binding():

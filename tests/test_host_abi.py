@@ -18,7 +18,7 @@ HEADER = os.path.join(ROOT, "include", "osfm_match.h")
 def _declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(osfm_(?:match|tracks)_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(osfm_(?:match|tracks|io)_\w+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")
@@ -110,3 +110,124 @@ def test_count_consistent_matches_mirror(ora):
     m12 = rng.integers(-1, 50, 80).astype(np.int32)
     m21 = rng.integers(-1, 80, 50).astype(np.int32)
     assert Matching.count_consistent_matches(Matching.Result(m12, m21)) == ora.count_consistent(m12, m21)
+
+
+def _prebundle_case(seed=0):
+    rng = np.random.default_rng(seed)
+    feats = np.array([40, 0, 25, 33], np.int32)
+    n = int(feats.sum())
+    pos = rng.random((n, 2), dtype=np.float32) * 2 - 1
+    col = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    pairs = [(2, 0), (3, 0), (3, 2)]
+    lists = [np.stack([np.sort(rng.choice(feats[a], 12, replace=False)), rng.choice(feats[b], 12, replace=False)], 1)
+             for a, b in pairs]
+    lists[1] = lists[1][:0]          # a pair with an empty list
+    off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    return feats, pos, col, pairs, off, np.concatenate(lists).astype(np.int32)
+
+
+def test_prebundle_round_trip(tmp_path):
+    """osfm_io_save_prebundle / osfm_io_load_prebundle (the MVE prebundle file,
+    bundler_common.cc:56-190): what is written is read back."""
+    from orthosfm_b200 import io as osio
+    feats, pos, col, pairs, off, ij = _prebundle_case()
+    path = str(tmp_path / "prebundle.sfm")
+    osio.save_prebundle(path, feats, pos, col, pairs, off, ij)
+    d = osio.load_prebundle(path)
+    assert np.array_equal(d["n_positions"], feats) and np.array_equal(d["n_colors"], feats)
+    assert np.array_equal(d["positions"], pos) and np.array_equal(d["colors"], col)
+    assert np.array_equal(d["pair_views"], np.asarray(pairs)) and np.array_equal(d["offsets"], off)
+    assert np.array_equal(d["ij"], ij)
+    assert open(path, "rb").read(14) == b"MVE_PREBUNDLE\n"
+    with pytest.raises(_lib.MatcherError):
+        osio.load_prebundle(str(tmp_path / "missing.sfm"))
+    bad = tmp_path / "bad.sfm"
+    bad.write_bytes(b"NOT_A_PREBUNDLE_FILE")
+    with pytest.raises(_lib.MatcherError):
+        osio.load_prebundle(str(bad))
+
+
+def test_prebundle_is_byte_identical_to_the_reference_writer(tmp_path):
+    """The same data through the reference's own save_prebundle_to_file gives the same bytes,
+    and the reference's load_prebundle_from_file reads our file."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from orthosfm_b200 import io as osio
+    ref = oracle.Reference()
+    feats, pos, col, pairs, off, ij = _prebundle_case(3)
+    ours, theirs = str(tmp_path / "ours.sfm"), str(tmp_path / "theirs.sfm")
+    osio.save_prebundle(ours, feats, pos, col, pairs, off, ij)
+    ref.save_prebundle(theirs, feats, pos, col, pairs, off, ij)
+    assert open(ours, "rb").read() == open(theirs, "rb").read()
+    counts, sums = ref.load_prebundle_digest(ours)
+    assert counts.tolist() == [len(feats), int(feats.sum()), len(pairs), len(ij)]
+    assert np.isclose(sums[0], float(pos[:, 0].astype(np.float64).sum() + 2 * pos[:, 1].astype(np.float64).sum()))
+    assert sums[1] == float((col.astype(np.float64) * [1, 3, 5]).sum())
+    pv = np.asarray(pairs, np.float64)
+    assert sums[2] == float((1000 * pv[:, 0] + 7 * pv[:, 1]).sum() + (31.0 * ij[:, 0] + 17.0 * ij[:, 1]).sum())
+
+
+def _tracks_case(seed=0):
+    rng = np.random.default_rng(seed)
+    feats = np.array([30, 0, 22, 27, 19], np.int32)
+    n = int(feats.sum())
+    view_of = np.repeat(np.arange(len(feats)), feats)
+    ids = np.full(n, -1, np.int32)
+    num_tracks = 0
+    # tracks of 2..4 views, at most one feature per view, ids ascending by first feature
+    free = [list(np.flatnonzero(view_of == v)) for v in range(len(feats))]
+    members = []
+    for _ in range(14):
+        views = sorted(rng.choice([0, 2, 3, 4], size=int(rng.integers(2, 5)), replace=False))
+        if any(not free[v] for v in views):
+            continue
+        members.append([free[v].pop(int(rng.integers(len(free[v])))) for v in views])
+    members.sort(key=lambda m: min(m))
+    for t, m in enumerate(members):
+        ids[m] = t
+    num_tracks = len(members)
+    pos = (rng.random((n, 2), dtype=np.float32) - 0.5) * np.float32(0.97)
+    col = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    return feats, ids, num_tracks, pos, col
+
+
+@pytest.mark.parametrize("with_colors", [False, True])
+def test_tracks_file_matches_the_restated_writer_and_reads_back(tmp_path, with_colors):
+    """osfm_io_save_tracks / osfm_io_load_tracks against the restatement of
+    orthosfm::saveTracksToFile / loadTracksFromFile (matching_io.cpp:16-95)."""
+    import oracle
+    from orthosfm_b200 import io as osio
+    feats, ids, nt, pos, col = _tracks_case(1)
+    width = 3000.0
+    path = str(tmp_path / "tracks.txt")
+    osio.save_tracks(path, feats, ids, nt, pos, width, col if with_colors else None)
+    want = oracle.tracks_from_ids(feats, ids, pos, width, col if with_colors else None)
+    text = open(path).read()
+    assert text == oracle.save_tracks_text(want)
+    back = osio.load_tracks(path)
+    parsed = oracle.load_tracks_text(text)
+    assert back["offsets"].tolist() == np.concatenate([[0], np.cumsum([len(t) for t in parsed])]).tolist()
+    flat = [f for t in parsed for f in t]
+    assert back["ids"].tolist() == [list(f[:3]) for f in flat]
+    assert np.array_equal(back["xy"], np.array([[f[3], f[4]] for f in flat], np.float32))
+    assert back["rgb"].tolist() == [list(f[5:]) for f in flat]
+    with pytest.raises(_lib.MatcherError):
+        osio.load_tracks(str(tmp_path / "missing.txt"))
+    with pytest.raises(_lib.MatcherError):
+        osio.save_tracks(path, feats, np.where(ids >= 0, ids + nt, ids), nt, pos, width)     # id out of range
+
+
+def test_pairwise_track_files_match_the_restated_writer(tmp_path):
+    """osfm_io_save_pairwise_tracks against the restatement of saveTracksToPairwiseFiles
+    (matching_io.cpp:97-140)."""
+    import oracle
+    from orthosfm_b200 import io as osio
+    feats, ids, nt, pos, _ = _tracks_case(2)
+    width = 1234.0
+    n = osio.save_pairwise_tracks(str(tmp_path), feats, ids, nt, pos, width)
+    want = oracle.save_pairwise_tracks_text(oracle.tracks_from_ids(feats, ids, pos, width), list(range(len(feats))))
+    assert n == len(want) and n > 0
+    assert sorted(os.listdir(tmp_path)) == sorted(want)
+    for name, text in want.items():
+        assert open(tmp_path / name).read() == text
