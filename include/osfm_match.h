@@ -219,6 +219,36 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
     const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
     int64_t* list_offset, int32_t* status, int32_t* count);
 
+/* ---- RANSAC for the fundamental matrix ---------------------------------------
+ * Replaces sfm::RansacFundamental::estimate (src/mve/sfm/ransac_fundamental.cc:26-105) as
+ * bundler::Matching::two_view_matching runs it on every pair that passed the match-count
+ * gates (src/mve/sfm/bundler_matching.cc:176-220), for all those pairs in one call.
+ *
+ * The reference draws each 8-match sample from std::rand(), one process-wide sequence
+ * consumed pair after pair.  osfm_ransac_draw_samples makes exactly those draws (it calls
+ * std::rand() itself: seed it, or not, as the reference's caller does), in the order of
+ * the pairs given, max_iterations samples of eight ascending match indices per pair;
+ * every pair needs at least 8 matches (the reference throws below that).
+ * samples: 8 * max_iterations * npairs ints. */
+int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_iterations,
+    int32_t* samples);
+
+/* Fits a fundamental matrix to every sample (normalised 8-point + rank-2 enforcement,
+ * src/mve/sfm/fundamental.cc:78-126), counts the inliers of each (Sampson distance <
+ * threshold^2, fundamental.cc:225-247) and keeps, per pair, the first sample with the most
+ * inliers -- in the reference's double arithmetic, so the inlier lists are the reference's.
+ * positions: 2 floats per feature (FeatureSet::positions), concatenated over the views;
+ * pair p joins views pair_views[2p], pair_views[2p+1] with the matches
+ * match_ij[2*list_offset[p] .. 2*list_offset[p+1]).  inlier_ij (capacity
+ * 2*list_offset[npairs] ints) receives the inlier matches of the pairs back to back,
+ * inlier_offset npairs+1 offsets; fundamental (may be NULL) 9 doubles per pair, row-major
+ * (zeros for a pair without inliers).  The thresholds on the inlier count stay with the
+ * caller (bundler_matching.cc:203-210). */
+int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* features_per_view,
+    const float* positions, const int32_t* pair_views, const int64_t* list_offset,
+    const int32_t* match_ij, int npairs, const int32_t* samples, int max_iterations,
+    double threshold, int32_t* inlier_ij, int64_t* inlier_offset, double* fundamental);
+
 /* ---- tracks ------------------------------------------------------------------
  * Replaces sfm::bundler::Tracks::compute incl. remove_invalid_tracks
  * (src/mve/sfm/bundler_tracks.cc:47-203) up to the numbering of the tracks: the tracks

@@ -386,6 +386,56 @@ def save_pairwise_tracks_text(tracks, view_ids) -> dict:
     return files
 
 
+class RansacHostCheck:
+    """orthosfm_b200/csrc/ransac_math.cuh (the device arithmetic of RANSAC-F) compiled for the
+    host (oracle/ransac_hostcheck.cc): lets CPU-only tests hold it against the reference."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libransac_hostcheck.so"))
+        self.lib.osfm_hostcheck_sampson.restype = C.c_double
+        self.lib.osfm_hostcheck_ransac.restype = C.c_int
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(_HERE, "_ref", "libransac_hostcheck.so"))
+
+    def fundamental(self, p1, p2) -> np.ndarray:
+        p1, p2 = _c(p1, np.float64), _c(p2, np.float64)
+        F = np.zeros(9, np.float64)
+        self.lib.osfm_hostcheck_fundamental(_ptr(p1, C.c_double), _ptr(p2, C.c_double), _ptr(F, C.c_double))
+        return F
+
+    def sampson(self, F, match) -> float:
+        F, match = _c(F, np.float64), _c(match, np.float64)
+        return self.lib.osfm_hostcheck_sampson(_ptr(F, C.c_double), _ptr(match, C.c_double))
+
+    def svd(self, a):
+        a = _c(a, np.float64)
+        n = a.shape[0]
+        s, v, u = np.zeros(n), np.zeros((n, n)), np.zeros((n, n))
+        if n == 9:
+            self.lib.osfm_hostcheck_svd9(_ptr(a, C.c_double), _ptr(s, C.c_double), _ptr(v, C.c_double))
+            return s, v
+        self.lib.osfm_hostcheck_svd3(_ptr(a, C.c_double), _ptr(u, C.c_double), _ptr(s, C.c_double),
+                                     _ptr(v, C.c_double))
+        return u, s, v
+
+    def ransac(self, matches_xy, samples, threshold: float = 0.0015):
+        m = _c(matches_xy, np.float64)
+        smp = _c(samples, np.int32).reshape(-1, 8)
+        inl = np.zeros(len(m), np.int32)
+        F = np.zeros(9, np.float64)
+        n = self.lib.osfm_hostcheck_ransac(_ptr(m, C.c_double), C.c_int(len(m)), _ptr(smp, C.c_int),
+                                           C.c_int(len(smp)), C.c_double(threshold), _ptr(inl, C.c_int),
+                                           _ptr(F, C.c_double))
+        return inl[:n].copy(), F
+
+
+def srand(seed: int) -> None:
+    """std::srand on the C library every library in this process shares."""
+    C.CDLL(None).srand(C.c_uint(seed))
+
+
 class Reference(_Impl):
     """The reference itself, compiled from /root/reference (oracle/_ref)."""
 
@@ -449,6 +499,43 @@ class Reference(_Impl):
         if rc != 0:
             raise OSError(f"reference could not read {path}")
         return counts, sums
+
+    def fundamental(self, p1, p2) -> np.ndarray:
+        """fundamental_8_point + enforce_fundamental_constraints (fundamental.cc:78-126) on
+        eight correspondences ([8, 2] each)."""
+        p1, p2 = _c(p1, np.float64), _c(p2, np.float64)
+        F = np.zeros(9, np.float64)
+        self.lib.osfm_ref_fundamental(_ptr(p1, C.c_double), _ptr(p2, C.c_double), _ptr(F, C.c_double))
+        return F
+
+    def sampson(self, F, match) -> float:
+        F, match = _c(F, np.float64), _c(match, np.float64)
+        f = self.lib.osfm_ref_sampson
+        f.restype = C.c_double
+        return f(_ptr(F, C.c_double), _ptr(match, C.c_double))
+
+    def svd(self, a):
+        """math::matrix_svd (matrix_svd.h) of a 9 x 9 (-> s, V) or 3 x 3 (-> U, s, V) matrix."""
+        a = _c(a, np.float64)
+        n = a.shape[0]
+        s, v, u = np.zeros(n), np.zeros((n, n)), np.zeros((n, n))
+        if n == 9:
+            self.lib.osfm_ref_svd9(_ptr(a, C.c_double), _ptr(s, C.c_double), _ptr(v, C.c_double))
+            return s, v
+        self.lib.osfm_ref_svd3(_ptr(a, C.c_double), _ptr(u, C.c_double), _ptr(s, C.c_double), _ptr(v, C.c_double))
+        return u, s, v
+
+    def ransac(self, matches_xy, iterations: int = 1000, threshold: float = 0.0015, seed: int = -1):
+        """RansacFundamental::estimate (ransac_fundamental.cc:26-60) on [n, 4] matches
+        (x1 y1 x2 y2); seed >= 0 calls std::srand(seed) first.  Returns (inlier indices, F)."""
+        m = _c(matches_xy, np.float64)
+        inl = np.zeros(len(m), np.int32)
+        F = np.zeros(9, np.float64)
+        f = self.lib.osfm_ref_ransac
+        f.restype = C.c_int
+        n = f(_ptr(m, C.c_double), C.c_int(len(m)), C.c_int(iterations), C.c_double(threshold), C.c_int(seed),
+              _ptr(inl, C.c_int), _ptr(F, C.c_double))
+        return inl[:n].copy(), F
 
     def exhaustive(self, views_float):
         """views_float: list of (sift n x 128 float32, surf n x 64 float32)."""

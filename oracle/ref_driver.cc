@@ -21,6 +21,10 @@
  *                                             src/mve/sfm/exhaustive_matching.cc:56,115,147
  *   sfm::Sift::process                        src/mve/sfm/sift.cc (fixture producer only)
  *   sfm::bundler::Tracks::compute             src/mve/sfm/bundler_tracks.cc:47-146
+ *   sfm::fundamental_8_point, enforce_fundamental_constraints, sampson_distance
+ *                                             src/mve/sfm/fundamental.cc:78-126, 225-247
+ *   sfm::RansacFundamental::estimate          src/mve/sfm/ransac_fundamental.cc:26-105
+ *   math::matrix_svd                          src/mve/math/matrix_svd.h
  *   sfm::bundler::save_prebundle_to_file / load_prebundle_from_file
  *                                             src/mve/sfm/bundler_common.cc:56-190
  */
@@ -37,6 +41,9 @@
 #include "sfm/bundler_common.h"
 #include "sfm/bundler_tracks.h"
 #include "sfm/exhaustive_matching.h"
+#include "sfm/fundamental.h"
+#include "sfm/ransac_fundamental.h"
+#include "math/matrix_svd.h"
 #include "sfm/matching.h"
 #include "sfm/nearest_neighbor.h"
 #include "sfm/sift.h"
@@ -471,6 +478,72 @@ osfm_ref_load_prebundle_digest (const char* path, long long* counts, double* sum
             sums[2] += 31.0 * matching[p].matches[k].first + 17.0 * matching[p].matches[k].second;
     }
     return 0;
+}
+
+/* ---- RANSAC for the fundamental matrix ---------------------------------------- */
+
+/* p1 / p2: 8 points x0 y0 x1 y1 ...; F row-major. */
+void
+osfm_ref_fundamental (const double* p1, const double* p2, double* F)
+{
+    sfm::Eight2DPoints a, b;
+    for (int i = 0; i < 8; ++i)
+    {
+        a(0, i) = p1[2 * i]; a(1, i) = p1[2 * i + 1]; a(2, i) = 1.0;
+        b(0, i) = p2[2 * i]; b(1, i) = p2[2 * i + 1]; b(2, i) = 1.0;
+    }
+    sfm::FundamentalMatrix f;
+    sfm::fundamental_8_point(a, b, &f);
+    sfm::enforce_fundamental_constraints(&f);
+    std::copy(f.begin(), f.end(), F);
+}
+
+double
+osfm_ref_sampson (const double* F, const double* m)
+{
+    sfm::FundamentalMatrix f;
+    std::copy(F, F + 9, f.begin());
+    sfm::Correspondence2D2D c;
+    c.p1[0] = m[0]; c.p1[1] = m[1]; c.p2[0] = m[2]; c.p2[1] = m[3];
+    return sfm::sampson_distance(f, c);
+}
+
+void
+osfm_ref_svd9 (const double* a, double* s, double* v)
+{
+    math::matrix_svd<double>(a, 9, 9, nullptr, s, v);
+}
+
+void
+osfm_ref_svd3 (const double* a, double* u, double* s, double* v)
+{
+    math::matrix_svd<double>(a, 3, 3, u, s, v);
+}
+
+/* RansacFundamental::estimate on n matches (x1 y1 x2 y2 as doubles) after std::srand(seed);
+ * seed < 0 leaves the sequence where it is.  Returns the number of inliers. */
+int
+osfm_ref_ransac (const double* matches, int n, int iterations, double threshold, int seed,
+    int* inliers, double* F)
+{
+    sfm::Correspondences2D2D m(n);
+    for (int i = 0; i < n; ++i)
+    {
+        m[i].p1[0] = matches[4 * i + 0]; m[i].p1[1] = matches[4 * i + 1];
+        m[i].p2[0] = matches[4 * i + 2]; m[i].p2[1] = matches[4 * i + 3];
+    }
+    if (seed >= 0)
+        std::srand(seed);
+    sfm::RansacFundamental::Options opts;
+    opts.max_iterations = iterations;
+    opts.threshold = threshold;
+    sfm::RansacFundamental ransac(opts);
+    sfm::RansacFundamental::Result result;
+    ransac.estimate(m, &result);
+    std::copy(result.inliers.begin(), result.inliers.end(), inliers);
+    if (!result.inliers.empty())
+        std::copy(result.fundamental.begin(), result.fundamental.end(), F);
+    return static_cast<int>(result.inliers.size());
 }
 
 } /* extern "C" */

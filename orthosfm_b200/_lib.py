@@ -28,6 +28,7 @@ EXPORTS = [
     "osfm_io_save_prebundle", "osfm_io_load_prebundle", "osfm_io_prebundle_get", "osfm_io_prebundle_free",
     "osfm_io_save_tracks", "osfm_io_save_pairwise_tracks", "osfm_io_load_tracks", "osfm_io_track_table_get",
     "osfm_io_track_table_free",
+    "osfm_ransac_draw_samples", "osfm_ransac_fundamental",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
 ]
 
@@ -119,6 +120,10 @@ def load() -> C.CDLL:
     L.osfm_io_track_table_get.argtypes = [vp, i64p, u32p, f32p, u32p]
     L.osfm_io_track_table_free.argtypes = [vp]
     L.osfm_io_track_table_free.restype = None
+    f64p = C.POINTER(C.c_double)
+    L.osfm_ransac_draw_samples.argtypes = [C.c_int, i64p, C.c_int, i32p]
+    L.osfm_ransac_fundamental.argtypes = [vp, C.c_int, i32p, f32p, i32p, i64p, i32p, C.c_int, i32p, C.c_int,
+                                          C.c_double, i32p, i64p, f64p]
     L.osfm_match_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
     L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]

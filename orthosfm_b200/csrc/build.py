@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libosfm_match.so")
 SOURCES = ["osfm_match.cu"]
 HEADERS = ["ptx.cuh", "common.cuh", "scan_kernel.cuh", "post_kernels.cuh", "float_kernels.cuh",
-           "tracks_kernels.cuh", "io_formats.cuh",
+           "tracks_kernels.cuh", "io_formats.cuh", "ransac_math.cuh", "ransac_kernels.cuh",
            "gpu_exhaustive_matching.h", "../../include/osfm_match.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

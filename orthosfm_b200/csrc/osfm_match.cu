@@ -13,6 +13,7 @@
 #include <cfloat>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -26,6 +27,7 @@
 #include "float_kernels.cuh"
 #include "io_formats.cuh"
 #include "post_kernels.cuh"
+#include "ransac_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "tracks_kernels.cuh"
 
@@ -128,6 +130,12 @@ struct osfm_matcher {
     DevBuf<unsigned long long> tr_table;
     DevBuf<int64_t> tr_meta;
     DevBuf<int32_t> tr_meta32;
+    DevBuf<float4> rs_xy;                // RANSAC scratch (osfm_ransac_fundamental)
+    DevBuf<float2> rs_pos;
+    DevBuf<int32_t> rs_samples;
+    DevBuf<double> rs_F;
+    DevBuf<int> rs_cnt;
+    DevBuf<int2> rs_out;
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
@@ -748,6 +756,8 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_cand.release(); m->d_big.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release(); m->d_list.release();
     m->tr_ints.release(); m->tr_table.release(); m->tr_meta.release(); m->tr_meta32.release();
+    m->rs_xy.release(); m->rs_pos.release(); m->rs_samples.release(); m->rs_F.release(); m->rs_cnt.release();
+    m->rs_out.release();
     m->d_ftmp.release();
     m->d_seg_first.release();
     for (auto& sp : m->pass) sp.release();
@@ -1438,6 +1448,125 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
     if (small[0] != 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d matches refer to features outside their view", small[0]);
     *num_tracks = small[2];
     if (num_conflicting) *num_conflicting = small[1];
+    return OSFM_OK;
+}
+
+// ---- RANSAC for the fundamental matrix ------------------------------------------------------------
+
+int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_iterations, int32_t* samples) {
+    if (npairs < 0 || max_iterations < 0 || (npairs > 0 && (!list_offset || !samples))) return OSFM_ERR_INVALID_ARGUMENT;
+    for (int p = 0; p < npairs; ++p) {
+        int64_t const count = list_offset[p + 1] - list_offset[p];
+        if (count < 8 || count > INT32_MAX) return OSFM_ERR_INVALID_ARGUMENT;    // the reference throws below 8
+    }
+    // RansacFundamental::estimate_8_point, ransac_fundamental.cc:70-76: rand() % count into an
+    // ordered set until it holds eight; the set is then read in ascending order.
+    for (int p = 0; p < npairs; ++p) {
+        unsigned long const count = static_cast<unsigned long>(list_offset[p + 1] - list_offset[p]);
+        int32_t* out = samples + static_cast<size_t>(p) * max_iterations * 8;
+        for (int it = 0; it < max_iterations; ++it, out += 8) {
+            int have = 0;
+            while (have < 8) {
+                int32_t const v = static_cast<int32_t>(static_cast<unsigned long>(std::rand()) % count);
+                int at = 0;
+                while (at < have && out[at] < v) ++at;
+                if (at < have && out[at] == v) continue;
+                for (int k = have; k > at; --k) out[k] = out[k - 1];
+                out[at] = v;
+                ++have;
+            }
+        }
+    }
+    return OSFM_OK;
+}
+
+int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* features_per_view, const float* positions,
+                            const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij,
+                            int npairs, const int32_t* samples, int max_iterations, double threshold,
+                            int32_t* inlier_ij, int64_t* inlier_offset, double* fundamental) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (num_views < 0 || npairs < 0 || max_iterations < 0 || (num_views > 0 && !features_per_view) || !inlier_offset ||
+        (npairs > 0 && (!pair_views || !list_offset || !samples || !positions || !match_ij || !inlier_ij)))
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
+    inlier_offset[0] = 0;
+    if (npairs == 0) return OSFM_OK;
+    std::vector<int64_t> base(num_views + 1, 0);
+    for (int v = 0; v < num_views; ++v) {
+        if (features_per_view[v] < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative feature count");
+        base[v + 1] = base[v] + features_per_view[v];
+    }
+    if (list_offset[0] != 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "list_offset[0] must be 0");
+    for (int p = 0; p < npairs; ++p) {
+        int64_t const count = list_offset[p + 1] - list_offset[p];
+        if (pair_views[2 * p] < 0 || pair_views[2 * p] >= num_views || pair_views[2 * p + 1] < 0 ||
+            pair_views[2 * p + 1] >= num_views)
+            return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad pair %d", p);
+        if (count < 8 || count > INT32_MAX)
+            return fail(m, OSFM_ERR_INVALID_ARGUMENT, "pair %d: at least 8 matches required", p);
+    }
+    int64_t const nmatches = list_offset[npairs];
+    int64_t const nfits = static_cast<int64_t>(npairs) * max_iterations;
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, m->rs_xy.reserve(static_cast<size_t>(nmatches)));
+    CU_TRY(m, m->rs_out.reserve(static_cast<size_t>(2 * nmatches)));              // input lists | inlier lists
+    CU_TRY(m, m->rs_pos.reserve(static_cast<size_t>(std::max<int64_t>(base[num_views], 1))));
+    CU_TRY(m, m->rs_samples.reserve(static_cast<size_t>(std::max<int64_t>(nfits * 8, 1))));
+    CU_TRY(m, m->rs_F.reserve(static_cast<size_t>(std::max<int64_t>(nfits * 9, 1)) + 9 * static_cast<size_t>(npairs)));
+    CU_TRY(m, m->rs_cnt.reserve(static_cast<size_t>(std::max<int64_t>(nfits, 1)) + static_cast<size_t>(npairs) + 4));
+    CU_TRY(m, m->tr_meta.reserve(static_cast<size_t>(num_views) + 1 + static_cast<size_t>(npairs) + 1));
+    CU_TRY(m, m->tr_meta32.reserve(static_cast<size_t>(std::max(num_views, 1)) + 2 * static_cast<size_t>(npairs)));
+    int64_t* const d_base = m->tr_meta.p;
+    int64_t* const d_off = d_base + num_views + 1;
+    int32_t* const d_vn = m->tr_meta32.p;
+    int32_t* const d_pv = d_vn + std::max(num_views, 1);
+    int2* const d_ij = m->rs_out.p;
+    int2* const d_inl = d_ij + nmatches;
+    double* const d_bestF = m->rs_F.p + std::max<int64_t>(nfits * 9, 1);
+    int* const d_count = m->rs_cnt.p + std::max<int64_t>(nfits, 1);
+    int* const d_bad = d_count + npairs;
+    cudaStream_t const st = m->stream;
+    CU_TRY(m, cudaMemsetAsync(d_bad, 0, sizeof(int) * 2, st));
+    CU_TRY(m, cudaMemcpyAsync(d_base, base.data(), sizeof(int64_t) * (num_views + 1), cudaMemcpyHostToDevice, st));
+    CU_TRY(m, cudaMemcpyAsync(d_vn, features_per_view, sizeof(int32_t) * num_views, cudaMemcpyHostToDevice, st));
+    CU_TRY(m, cudaMemcpyAsync(d_pv, pair_views, sizeof(int32_t) * 2 * npairs, cudaMemcpyHostToDevice, st));
+    CU_TRY(m, cudaMemcpyAsync(d_off, list_offset, sizeof(int64_t) * (npairs + 1), cudaMemcpyHostToDevice, st));
+    CU_TRY(m, cudaMemcpyAsync(d_ij, match_ij, sizeof(int2) * nmatches, cudaMemcpyHostToDevice, st));
+    if (base[num_views] > 0)
+        CU_TRY(m, cudaMemcpyAsync(m->rs_pos.p, positions, sizeof(float2) * base[num_views], cudaMemcpyHostToDevice, st));
+    if (nfits > 0)
+        CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p, samples, sizeof(int32_t) * 8 * nfits, cudaMemcpyHostToDevice, st));
+    ransac_gather_kernel<<<static_cast<unsigned>((nmatches + 255) / 256), 256, 0, st>>>(
+        d_pv, d_off, npairs, d_ij, nmatches, d_base, d_vn, m->rs_pos.p, m->rs_xy.p, d_bad + 0);
+    double const thr2 = threshold * threshold;       // ransac_fundamental.cc:97
+    if (nfits > 0) {
+        ransac_fit_kernel<<<static_cast<unsigned>((nfits + 127) / 128), 128, 0, st>>>(
+            d_off, npairs, max_iterations, m->rs_samples.p, m->rs_xy.p, m->rs_F.p, d_bad + 1);
+        ransac_count_kernel<<<static_cast<unsigned>((nfits * 32 + 255) / 256), 256, 0, st>>>(
+            d_off, npairs, max_iterations, m->rs_xy.p, m->rs_F.p, thr2, m->rs_cnt.p);
+    }
+    ransac_select_kernel<<<npairs, 256, 0, st>>>(d_off, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p, m->rs_cnt.p, thr2,
+                                                 d_inl, d_count, d_bestF);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += nfits > 0 ? 4 : 2;
+    std::vector<int> count(static_cast<size_t>(npairs) + 2);
+    std::vector<int2> inl(static_cast<size_t>(nmatches));
+    CU_TRY(m, cudaMemcpyAsync(count.data(), d_count, sizeof(int) * (npairs + 2), cudaMemcpyDeviceToHost, st));
+    CU_TRY(m, cudaMemcpyAsync(inl.data(), d_inl, sizeof(int2) * nmatches, cudaMemcpyDeviceToHost, st));
+    if (fundamental)
+        CU_TRY(m, cudaMemcpyAsync(fundamental, d_bestF, sizeof(double) * 9 * npairs, cudaMemcpyDeviceToHost, st));
+    CU_TRY(m, cudaStreamSynchronize(st));
+    if (count[npairs] != 0)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d matches refer to features outside their view", count[npairs]);
+    if (count[npairs + 1] != 0)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "%d samples are not eight ascending indices into their pair's list",
+                    count[npairs + 1]);
+    for (int p = 0; p < npairs; ++p) {
+        if (count[p] > 0)
+            memcpy(inlier_ij + 2 * inlier_offset[p], inl.data() + list_offset[p], sizeof(int2) * count[p]);
+        inlier_offset[p + 1] = inlier_offset[p] + count[p];
+    }
     return OSFM_OK;
 }
 

@@ -366,6 +366,35 @@ class ExhaustiveMatching:
             m.ctypes.data_as(i32p), len(pv), out.ctypes.data_as(i32p), C.byref(nt), C.byref(nc)))
         return out, int(nt.value), int(nc.value)
 
+    def ransac_fundamental(self, features_per_view, positions, pair_views, offsets, ij, samples=None,
+                           max_iterations: int = 1000, threshold: float = 0.0015) -> tuple:
+        """sfm::RansacFundamental::estimate (ransac_fundamental.cc:26-105) for every pair at
+        once.  samples=None draws them here from std::rand(), in pair order, as the reference
+        does (ransac_draw_samples).  Returns (inlier offsets [npairs + 1], inlier (i, j) lists,
+        fundamental matrices [npairs, 3, 3])."""
+        f = np.ascontiguousarray(features_per_view, np.int32)
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+        pv = np.ascontiguousarray(np.asarray(pair_views, np.int32).reshape(-1, 2))
+        off = np.ascontiguousarray(offsets, np.int64)
+        m = np.ascontiguousarray(np.asarray(ij, np.int32).reshape(-1, 2))
+        if len(pos) != int(f.sum()):
+            raise ValueError("positions must hold one (x, y) per feature")
+        if samples is None:
+            samples = ransac_draw_samples(off, max_iterations)
+        smp = np.ascontiguousarray(samples, np.int32)
+        if smp.size != len(pv) * max_iterations * 8:
+            raise ValueError("samples must hold 8 indices per pair and iteration")
+        out = np.empty((max(len(m), 1), 2), np.int32)
+        out_off = np.zeros(len(pv) + 1, np.int64)
+        F = np.zeros((len(pv), 3, 3), np.float64)
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        self._check(self._L.osfm_ransac_fundamental(
+            self._h, len(f), f.ctypes.data_as(i32p), pos.ctypes.data_as(C.POINTER(C.c_float)), pv.ctypes.data_as(i32p),
+            off.ctypes.data_as(i64p), m.ctypes.data_as(i32p), len(pv), smp.ctypes.data_as(i32p), int(max_iterations),
+            float(threshold), out.ctypes.data_as(i32p), out_off.ctypes.data_as(i64p),
+            F.ctypes.data_as(C.POINTER(C.c_double))))
+        return out_off, out[:out_off[-1]], F
+
     # -- introspection --------------------------------------------------------------------------
     def stats(self) -> dict:
         s = _lib.Stats()
@@ -405,3 +434,17 @@ class ExhaustiveMatching:
             self._h, pr.ctypes.data_as(C.POINTER(C.c_int32)), len(pr),
             out.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(out.size)))
         return out
+
+
+def ransac_draw_samples(offsets, max_iterations: int = 1000) -> np.ndarray:
+    """The 8-match samples RansacFundamental::estimate_8_point would draw for these pairs, in
+    order, from std::rand() (ransac_fundamental.cc:70-76): [npairs, max_iterations, 8],
+    ascending inside a sample.  Consumes the C library's rand() sequence, as the reference."""
+    off = np.ascontiguousarray(offsets, np.int64)
+    npairs = len(off) - 1
+    out = np.empty((npairs, max_iterations, 8), np.int32)
+    rc = _lib.load().osfm_ransac_draw_samples(npairs, off.ctypes.data_as(C.POINTER(C.c_int64)), int(max_iterations),
+                                              out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise MatcherError(rc, "every pair needs at least 8 matches")
+    return out

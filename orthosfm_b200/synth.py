@@ -142,3 +142,26 @@ def torch_sift_views(cfg: int, num_views: int, n: int, device, planted_fraction:
                 x = (x + RENORM_SIGMA * torch.randn((k, SIFT_DIM), generator=g, device=device)).abs_()
                 out[rows] = quantise(x)
     return out
+
+
+def two_view_scene(seed: int, n: int, outlier_fraction: float = 0.3, noise: float = 3e-4):
+    """Feature positions of n matches between two views of a random rigid scene, in MVE's
+    normalised image coordinates (roughly [-0.5, 0.5]): [n, 4] float32 (x1 y1 x2 y2).  A
+    fraction of the matches is wrong (the second point is random)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (n, 3)) + np.array([0, 0, 5.0])
+    a = rng.uniform(-0.2, 0.2, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+    Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+    Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    t = rng.uniform(-0.5, 0.5, 3)
+    focal = 1.2
+    x1 = focal * X[:, :2] / X[:, 2:3]
+    Y = X @ R.T + t
+    x2 = focal * Y[:, :2] / Y[:, 2:3]
+    x1 += rng.normal(0, noise, x1.shape)
+    x2 += rng.normal(0, noise, x2.shape)
+    wrong = rng.random(n) < outlier_fraction
+    x2[wrong] = rng.uniform(-0.5, 0.5, (int(wrong.sum()), 2))
+    return np.concatenate([x1, x2], 1).astype(np.float32)

@@ -736,6 +736,78 @@ def test_matcher_output_through_the_file_formats(ora, tmp_path):
         oracle.tracks_from_ids([n] * nv, oracle.canonical_track_ids(want), pos, 2048.0, col))
 
 
+# ------------------------------------------------------------------ RANSAC for the fundamental matrix
+
+def _ransac_case(counts, seed, outliers=0.3):
+    """Pairs of views with the given match counts: positions per view, pair lists."""
+    rng = np.random.default_rng(seed)
+    npairs = len(counts)
+    feats, pos, pairs, lists = [], [], [], []
+    for p, n in enumerate(counts):
+        xy = synth.two_view_scene(seed * 100 + p, n, outliers)
+        if p % 5 == 3:
+            xy[:, 1] = xy[:, 0]; xy[:, 3] = xy[:, 2]            # a degenerate pair: every point on one line
+        extra = int(rng.integers(0, 20))
+        pa, pb = rng.permutation(n + extra), rng.permutation(n + extra)      # match k joins features pa[k], pb[k]
+        va = np.zeros((n + extra, 2), np.float32); vb = np.zeros((n + extra, 2), np.float32)
+        va[pa[:n]] = xy[:, :2]; vb[pb[:n]] = xy[:, 2:]
+        order = np.argsort(pa[:n])                                # lists come sorted by the first feature
+        lists.append(np.stack([pa[:n][order], pb[:n][order]], 1))
+        feats += [n + extra, n + extra]
+        pos += [va, vb]
+        pairs.append((2 * p, 2 * p + 1))
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return np.array(feats, np.int32), np.concatenate(pos), np.array(pairs, np.int32), off, \
+        np.concatenate(lists).astype(np.int32), npairs
+
+
+@pytest.mark.parametrize("counts,iters", [([8, 9, 30, 200, 64, 1000], 300), ([2500, 12, 700], 1000)])
+def test_ransac_fundamental_equals_reference(counts, iters):
+    """osfm_ransac_draw_samples + osfm_ransac_fundamental against the reference's own
+    RansacFundamental::estimate run pair after pair on one std::rand() sequence
+    (ransac_fundamental.cc:26-105 as called from bundler_matching.cc:176-220): identical
+    inlier lists and fundamental matrices."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = oracle.Reference()
+    feats, pos, pairs, off, ij, npairs = _ransac_case(counts, 3)
+    base = np.concatenate([[0], np.cumsum(feats)])
+    oracle.srand(11)
+    want = []
+    for p in range(npairs):
+        l = ij[off[p]:off[p + 1]]
+        xy = np.concatenate([pos[base[pairs[p, 0]] + l[:, 0]], pos[base[pairs[p, 1]] + l[:, 1]]], 1)
+        want.append(ref.ransac(xy, iters, 0.0015))
+    oracle.srand(11)
+    with matcher(synth.sift_views(1, 2, 64)) as m:
+        ooff, oij, F = m.ransac_fundamental(feats, pos, pairs, off, ij, max_iterations=iters, threshold=0.0015)
+    assert sum(len(w[0]) for w in want) > 0
+    for p in range(npairs):
+        inl, wF = want[p]
+        assert np.array_equal(oij[ooff[p]:ooff[p + 1]], ij[off[p]:off[p + 1]][inl]), p
+        if len(inl):
+            assert np.array_equal(F[p].ravel(), wF), p
+        else:
+            assert not F[p].any()
+
+
+def test_ransac_fundamental_argument_errors():
+    feats, pos, pairs, off, ij, npairs = _ransac_case([20, 7], 5)
+    with matcher(synth.sift_views(1, 2, 64)) as m:
+        with pytest.raises(MatcherError):          # a pair with fewer than 8 matches (the reference throws)
+            m.ransac_fundamental(feats, pos, pairs, off, ij, max_iterations=10)
+        feats, pos, pairs, off, ij, npairs = _ransac_case([20, 9], 5)
+        smp = np.zeros((2, 10, 8), np.int32)       # not eight distinct ascending indices
+        with pytest.raises(MatcherError):
+            m.ransac_fundamental(feats, pos, pairs, off, ij, samples=smp, max_iterations=10)
+        bad = ij.copy(); bad[3, 1] = 10 ** 6       # a match outside its view
+        with pytest.raises(MatcherError):
+            m.ransac_fundamental(feats, pos, pairs, off, bad, max_iterations=10)
+        ooff, oij, F = m.ransac_fundamental(feats, pos, pairs[:0], off[:1], ij[:0], max_iterations=10)
+        assert ooff.tolist() == [0] and len(oij) == 0
+
+
 # ------------------------------------------------------------------ the reference-side binding
 
 def test_reference_side_binding():

@@ -18,7 +18,7 @@ HEADER = os.path.join(ROOT, "include", "osfm_match.h")
 def _declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(osfm_(?:match|tracks|io)_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(osfm_(?:match|tracks|io|ransac)_\w+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")

@@ -173,3 +173,93 @@ def test_tracks_restatement_equals_reference(ref):
     assert na > 10 and (a >= 0).sum() > 2 * na - 1
     c = oracle.canonical_track_ids(a)
     assert c.max() + 1 == na and np.array_equal(oracle.canonical_track_ids(c), c)
+
+
+# ------------------------------------------------------------------ RANSAC-F arithmetic (host build of the device code)
+
+def _hostcheck():
+    import oracle
+    if not (oracle.have_ref() and oracle.RansacHostCheck.available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return oracle.Reference(), oracle.RansacHostCheck()
+
+
+def test_svd_restatement_equals_reference_svd():
+    """orthosfm_b200/csrc/ransac_math.cuh compiled for the host gives the doubles of the
+    reference's math::matrix_svd (matrix_svd.h), 9 x 9 and 3 x 3, random, sparse, rank
+    deficient and repeated-value inputs."""
+    ref, hc = _hostcheck()
+    rng = np.random.default_rng(0)
+    for t in range(600):
+        a = rng.standard_normal((9, 9))
+        if t % 3 == 0:
+            a[8] = 0                                  # the padded 8 x 9 case
+        if t % 7 == 0:
+            a.flat[rng.integers(0, 81, 30)] = 0
+        if t % 11 == 0:
+            a[3] = a[1]; a[:, 5] = a[:, 2]            # rank deficient
+        if t % 13 == 0:
+            a = np.round(a)                           # many exact zeros and ties
+        s1, v1 = ref.svd(a)
+        s2, v2 = hc.svd(a)
+        assert np.array_equal(s1, s2) and np.array_equal(v1, v2), t
+    for t in range(600):
+        a = rng.standard_normal((3, 3))
+        if t % 5 == 0:
+            a.flat[rng.integers(0, 9, 3)] = 0
+        if t % 7 == 0:
+            a[2] = a[0]
+        if t % 11 == 0:
+            a = np.diag(rng.standard_normal(3))
+        for x, y in zip(ref.svd(a), hc.svd(a)):
+            assert np.array_equal(x, y), t
+    for a in (np.zeros((3, 3)), np.eye(3), np.zeros((9, 9)), np.eye(9), np.ones((9, 9))):
+        for x, y in zip(ref.svd(a), hc.svd(a)):
+            assert np.array_equal(x, y)
+
+
+def test_fundamental_and_sampson_equal_reference():
+    """fundamental_8_point + enforce_fundamental_constraints and sampson_distance
+    (fundamental.cc:78-126, 225-247): same doubles, degenerate samples included."""
+    ref, hc = _hostcheck()
+    rng = np.random.default_rng(1)
+    for t in range(500):
+        m = synth.two_view_scene(100 + t, 8, outlier_fraction=0.0 if t % 2 else 0.4).astype(np.float64)
+        if t % 9 == 0:
+            m[5] = m[2]                               # a repeated correspondence
+        if t % 10 == 0:
+            m[:, 1] = m[:, 0]; m[:, 3] = m[:, 2]      # all points on a line
+        if t % 25 == 0:
+            m[:] = m[0]                               # one point eight times
+        F1 = ref.fundamental(m[:, :2], m[:, 2:])
+        F2 = hc.fundamental(m[:, :2], m[:, 2:])
+        assert np.array_equal(F1, F2, equal_nan=True), t
+        q = rng.uniform(-0.5, 0.5, 4)
+        d1, d2 = ref.sampson(F1, q), hc.sampson(F2, q)
+        assert d1 == d2 or (np.isnan(d1) and np.isnan(d2)), t
+
+
+@pytest.mark.parametrize("n,outliers", [(8, 0.0), (9, 0.5), (40, 0.3), (400, 0.3), (1500, 0.6)])
+def test_ransac_restatement_and_sample_draws_equal_reference(n, outliers):
+    """srand(s); the reference's RansacFundamental::estimate  ==  srand(s);
+    osfm_ransac_draw_samples + the device arithmetic (host build): same inliers, same F.
+    Two pairs back to back share the one rand() sequence."""
+    import oracle
+    from orthosfm_b200 import ransac_draw_samples
+    ref, hc = _hostcheck()
+    a = synth.two_view_scene(n, n, outliers).astype(np.float64)
+    b = synth.two_view_scene(n + 1, n + 3, outliers).astype(np.float64)
+    iters = 200
+    oracle.srand(7)
+    want = [ref.ransac(a, iters, 0.0015), ref.ransac(b, iters, 0.0015)]
+    oracle.srand(7)
+    smp = ransac_draw_samples(np.array([0, len(a), len(a) + len(b)], np.int64), iters)
+    assert (np.diff(smp, axis=2) > 0).all() and smp.min() >= 0
+    assert smp[0].max() < len(a) and smp[1].max() < len(b)
+    got = [hc.ransac(a, smp[0], 0.0015), hc.ransac(b, smp[1], 0.0015)]
+    for (wi, wF), (gi, gF) in zip(want, got):
+        assert np.array_equal(wi, gi)
+        if len(wi):
+            assert np.array_equal(wF, gF)
+    if n >= 40 and outliers <= 0.3:
+        assert len(want[0][0]) >= 0.5 * (1 - outliers) * n      # the scene is a real two-view geometry
