@@ -208,7 +208,8 @@ enum {
     OSFM_TWO_VIEW_OK = 0,                /* list filled; count = consistent matches            */
     OSFM_TWO_VIEW_SKIPPED = 1,           /* previous-frames rule, or a view without features   */
     OSFM_TWO_VIEW_LOWRES_REJECTED = 2,   /* count = low-res matches < min_lowres_matches       */
-    OSFM_TWO_VIEW_TOO_FEW_MATCHES = 3    /* count = consistent matches below the threshold     */
+    OSFM_TWO_VIEW_TOO_FEW_MATCHES = 3,   /* count = consistent matches below the threshold     */
+    OSFM_TWO_VIEW_TOO_FEW_INLIERS = 4    /* osfm_match_two_view: count = RANSAC inliers below the threshold */
 };
 
 /* match_ij (host) receives the lists back to back; pair p's list is
@@ -218,6 +219,25 @@ enum {
 int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options* opts,
     const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
     int64_t* list_offset, int32_t* status, int32_t* count);
+
+/* The whole two-view stage, bundler::Matching::compute / two_view_matching
+ * (src/mve/sfm/bundler_matching.cc:57-220), for a list of pairs: the candidates above,
+ * then RANSAC for the fundamental matrix on every pair that passed (samples drawn from
+ * std::rand() in pair order, as the reference), then the inlier threshold
+ * max(8, min_matching_inliers).  positions: FeatureSet::positions of every view (2 floats
+ * per feature, SIFT features then SURF features), view after view.  Outputs as for
+ * osfm_match_two_view_candidates, the lists holding the inlier matches: for the pairs in the
+ * order bundler::Matching::compute visits them, the accepted ones are its PairwiseMatching. */
+typedef struct osfm_ransac_options {
+    int max_iterations;            /* 1000  */
+    int min_matching_inliers;      /* 12    */
+    double threshold;              /* 0.0015, in normalised image coordinates */
+    int reserved[4];
+} osfm_ransac_options;
+void osfm_match_ransac_default_options(osfm_ransac_options* o);
+int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts,
+    const osfm_ransac_options* ransac, const float* positions, const int32_t* pairs, int npairs,
+    int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset, int32_t* status, int32_t* count);
 
 /* ---- RANSAC for the fundamental matrix ---------------------------------------
  * Replaces sfm::RansacFundamental::estimate (src/mve/sfm/ransac_fundamental.cc:26-105) as

@@ -573,6 +573,30 @@ class _RefExhaustive:
                                                   _ptr(m21, C.c_int), C.byref(n21))
         return m12[:n12.value].copy(), m21[:n21.value].copy()
 
+    def bundler_compute(self, positions, use_lowres_matching=False, num_lowres_features=500, min_lowres_matches=5,
+                        min_feature_matches=24, min_matching_inliers=12, match_num_previous_frames=0,
+                        ransac_max_iterations=1000, ransac_threshold=0.0015, seed=-1):
+        """bundler::Matching::init + compute (bundler_matching.cc:45-133) over these viewports
+        with the given positions; consumes the descriptors (init frees them), so call once.
+        Returns [(view_1, view_2, ij)] in the order compute() accepted the pairs."""
+        pos = _c(positions, np.float32).reshape(-1, 2)
+        assert len(pos) == sum(self.sizes)
+        opts = np.array([int(use_lowres_matching), num_lowres_features, min_lowres_matches, min_feature_matches,
+                         min_matching_inliers, match_num_previous_frames, ransac_max_iterations], np.int32)
+        nv = len(self.sizes)
+        cap_pairs = nv * (nv - 1) // 2 + 1
+        cap_ij = cap_pairs * max(self.sizes) + 1
+        pairs = np.zeros((cap_pairs, 2), np.int32)
+        off = np.zeros(cap_pairs + 1, np.int64)
+        ij = np.zeros((cap_ij, 2), np.int32)
+        f = self.L.osfm_ref_bundler_compute
+        f.restype = C.c_int
+        n = f(self.h, _ptr(pos, C.c_float), _ptr(opts, C.c_int), C.c_double(ransac_threshold), C.c_int(seed),
+              _ptr(pairs, C.c_int), C.c_int(cap_pairs), off.ctypes.data_as(C.POINTER(C.c_longlong)),
+              _ptr(ij, C.c_int), C.c_longlong(cap_ij))
+        assert n >= 0
+        return [(int(pairs[p, 0]), int(pairs[p, 1]), ij[off[p]:off[p + 1]].copy()) for p in range(n)]
+
     def pairwise_match_lowres(self, v1: int, v2: int, num_features: int) -> int:
         return int(self.L.osfm_ref_exhaustive_pairwise_match_lowres(
             self.h, C.c_int(v1), C.c_int(v2), C.c_int(num_features)))

@@ -24,6 +24,7 @@
  *   sfm::fundamental_8_point, enforce_fundamental_constraints, sampson_distance
  *                                             src/mve/sfm/fundamental.cc:78-126, 225-247
  *   sfm::RansacFundamental::estimate          src/mve/sfm/ransac_fundamental.cc:26-105
+ *   sfm::bundler::Matching::init / compute    src/mve/sfm/bundler_matching.cc:45-220
  *   math::matrix_svd                          src/mve/math/matrix_svd.h
  *   sfm::bundler::save_prebundle_to_file / load_prebundle_from_file
  *                                             src/mve/sfm/bundler_common.cc:56-190
@@ -32,6 +33,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <iostream>
 #include <limits>
 #include <vector>
 #ifdef _OPENMP
@@ -39,6 +41,7 @@
 #endif
 
 #include "sfm/bundler_common.h"
+#include "sfm/bundler_matching.h"
 #include "sfm/bundler_tracks.h"
 #include "sfm/exhaustive_matching.h"
 #include "sfm/fundamental.h"
@@ -544,6 +547,78 @@ osfm_ref_ransac (const double* matches, int n, int iterations, double threshold,
     if (!result.inliers.empty())
         std::copy(result.fundamental.begin(), result.fundamental.end(), F);
     return static_cast<int>(result.inliers.size());
+}
+
+/* ---- bundler::Matching: the whole two-view stage ------------------------------ */
+
+/* Runs bundler::Matching (exhaustive matcher) over the viewports of h -- descriptors as set
+ * with osfm_ref_exhaustive_set_view, positions (2 floats per feature, sift then surf, view
+ * after view) given here -- single-threaded, as the reference's shipped build does (no
+ * OpenMP), after std::srand(seed) when seed >= 0.  opts: use_lowres_matching,
+ * num_lowres_features, min_lowres_matches, min_feature_matches, min_matching_inliers,
+ * match_num_previous_frames, ransac max_iterations; threshold separately.
+ * out_pairs receives (view_1, view_2) per accepted pair in the order compute() appended them,
+ * out_off the list offsets, out_ij the lists.  Returns the number of accepted pairs, or -1
+ * when a capacity is too small. */
+int
+osfm_ref_bundler_compute (osfm_ref_exhaustive* h, const float* positions, const int* opts,
+    double threshold, int seed, int* out_pairs, int cap_pairs, long long* out_off,
+    int* out_ij, long long cap_ij)
+{
+    std::size_t at = 0;
+    for (std::size_t v = 0; v < h->viewports.size(); ++v)
+    {
+        sfm::FeatureSet& fs = h->viewports[v].features;
+        std::size_t const n = fs.sift_descriptors.size() + fs.surf_descriptors.size();
+        fs.positions.resize(n);
+        for (std::size_t i = 0; i < n; ++i, ++at)
+            fs.positions[i] = math::Vec2f(positions[2 * at], positions[2 * at + 1]);
+    }
+    sfm::bundler::Matching::Options o;
+    o.use_lowres_matching = opts[0] != 0;
+    o.num_lowres_features = opts[1];
+    o.min_lowres_matches = opts[2];
+    o.min_feature_matches = opts[3];
+    o.min_matching_inliers = opts[4];
+    o.match_num_previous_frames = opts[5];
+    o.ransac_opts.max_iterations = opts[6];
+    o.ransac_opts.threshold = threshold;
+    o.ransac_opts.verbose_output = false;
+    o.matcher_type = sfm::bundler::Matching::MATCHER_EXHAUSTIVE;
+
+    int const threads = omp_get_max_threads();
+    omp_set_num_threads(1);
+    if (seed >= 0)
+        std::srand(seed);
+    sfm::bundler::PairwiseMatching result;
+    {
+        /* compute() reports progress on std::cout; keep the test output clean */
+        std::streambuf* old = std::cout.rdbuf(nullptr);
+        sfm::bundler::Matching matching(o);
+        matching.init(&h->viewports);
+        matching.compute(&result);
+        std::cout.rdbuf(old);
+    }
+    omp_set_num_threads(threads);
+
+    if ((int)result.size() > cap_pairs)
+        return -1;
+    out_off[0] = 0;
+    for (std::size_t p = 0; p < result.size(); ++p)
+    {
+        out_pairs[2 * p] = result[p].view_1_id;
+        out_pairs[2 * p + 1] = result[p].view_2_id;
+        long long const k = (long long)result[p].matches.size();
+        if (out_off[p] + k > cap_ij)
+            return -1;
+        for (long long i = 0; i < k; ++i)
+        {
+            out_ij[2 * (out_off[p] + i)] = result[p].matches[i].first;
+            out_ij[2 * (out_off[p] + i) + 1] = result[p].matches[i].second;
+        }
+        out_off[p + 1] = out_off[p] + k;
+    }
+    return (int)result.size();
 }
 
 } /* extern "C" */

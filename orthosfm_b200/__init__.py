@@ -8,8 +8,10 @@ the reference interface used by the tests and the benchmark.
 from ._lib import KIND_SIFT_U8, KIND_SURF_S8, MatcherError  # noqa: F401
 from .matcher import (ExhaustiveMatching, FeatureSet, Matching, MatchingBase,  # noqa: F401
                       TwoViewOptions, Viewport, TWO_VIEW_OK, TWO_VIEW_SKIPPED,
-                      TWO_VIEW_LOWRES_REJECTED, TWO_VIEW_TOO_FEW_MATCHES, ransac_draw_samples)
+                      TWO_VIEW_LOWRES_REJECTED, TWO_VIEW_TOO_FEW_MATCHES, TWO_VIEW_TOO_FEW_INLIERS,
+                      ransac_draw_samples)
 
 __all__ = ["ExhaustiveMatching", "FeatureSet", "Matching", "MatchingBase", "Viewport",
            "MatcherError", "KIND_SIFT_U8", "KIND_SURF_S8", "TwoViewOptions", "TWO_VIEW_OK",
-           "TWO_VIEW_SKIPPED", "TWO_VIEW_LOWRES_REJECTED", "TWO_VIEW_TOO_FEW_MATCHES", "ransac_draw_samples"]
+           "TWO_VIEW_SKIPPED", "TWO_VIEW_LOWRES_REJECTED", "TWO_VIEW_TOO_FEW_MATCHES", "TWO_VIEW_TOO_FEW_INLIERS",
+           "ransac_draw_samples"]

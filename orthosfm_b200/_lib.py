@@ -28,7 +28,8 @@ EXPORTS = [
     "osfm_io_save_prebundle", "osfm_io_load_prebundle", "osfm_io_prebundle_get", "osfm_io_prebundle_free",
     "osfm_io_save_tracks", "osfm_io_save_pairwise_tracks", "osfm_io_load_tracks", "osfm_io_track_table_get",
     "osfm_io_track_table_free",
-    "osfm_ransac_draw_samples", "osfm_ransac_fundamental",
+    "osfm_ransac_draw_samples", "osfm_ransac_fundamental", "osfm_match_two_view",
+    "osfm_match_ransac_default_options",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
 ]
 
@@ -43,6 +44,11 @@ class TwoViewOptions(C.Structure):
     _fields_ = [("use_lowres_matching", C.c_int), ("num_lowres_features", C.c_int),
                 ("min_lowres_matches", C.c_int), ("min_feature_matches", C.c_int),
                 ("match_num_previous_frames", C.c_int), ("reserved", C.c_int * 3)]
+
+
+class RansacOptions(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("min_matching_inliers", C.c_int), ("threshold", C.c_double),
+                ("reserved", C.c_int * 4)]
 
 
 class Stats(C.Structure):
@@ -121,6 +127,10 @@ def load() -> C.CDLL:
     L.osfm_io_track_table_free.argtypes = [vp]
     L.osfm_io_track_table_free.restype = None
     f64p = C.POINTER(C.c_double)
+    L.osfm_match_ransac_default_options.argtypes = [C.POINTER(RansacOptions)]
+    L.osfm_match_ransac_default_options.restype = None
+    L.osfm_match_two_view.argtypes = [vp, C.POINTER(TwoViewOptions), C.POINTER(RansacOptions), f32p, i32p, C.c_int,
+                                      vp, C.c_int64, i64p, i32p, i32p]
     L.osfm_ransac_draw_samples.argtypes = [C.c_int, i64p, C.c_int, i32p]
     L.osfm_ransac_fundamental.argtypes = [vp, C.c_int, i32p, f32p, i32p, i64p, i32p, C.c_int, i32p, C.c_int,
                                           C.c_double, i32p, i64p, f64p]

@@ -1570,6 +1570,76 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     return OSFM_OK;
 }
 
+// ---- the whole two-view stage: gates, RANSAC, inlier threshold --------------------------------------
+
+void osfm_match_ransac_default_options(osfm_ransac_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->max_iterations = 1000;          // RansacFundamental::Options, ransac_fundamental.h:88-93
+    o->threshold = 0.0015;
+    o->min_matching_inliers = 12;      // bundler::Matching::Options, bundler_matching.h:66
+}
+
+int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, const osfm_ransac_options* ransac,
+                        const float* positions, const int32_t* pairs, int npairs, int32_t* match_ij,
+                        int64_t capacity_ij, int64_t* list_offset, int32_t* status, int32_t* count) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    if (!ransac || ransac->max_iterations < 0) {
+        std::lock_guard<std::mutex> lock(m->mu);
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad RANSAC options");
+    }
+    // 1. bundler_matching.cc:92-192: pair rules, low-res gate, full match, match-count threshold
+    OS_TRY(osfm_match_two_view_candidates(m, opts, pairs, npairs, match_ij, capacity_ij, list_offset, status, count));
+    std::vector<int32_t> ok, pv;
+    std::vector<int64_t> off(1, 0);
+    for (int i = 0; i < npairs; ++i) {
+        if (status[i] != OSFM_TWO_VIEW_OK) continue;
+        ok.push_back(i);
+        pv.push_back(pairs[2 * i]);
+        pv.push_back(pairs[2 * i + 1]);
+        off.push_back(list_offset[i + 1]);      // rejected pairs have empty lists: the lists of the others are back to back
+    }
+    int const nok = static_cast<int>(ok.size());
+    if (nok == 0) return OSFM_OK;
+    std::vector<int32_t> fpv;
+    {
+        std::lock_guard<std::mutex> lock(m->mu);
+        if (!positions) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "positions required");
+        fpv.resize(m->kind[0].n.size());
+        for (size_t v = 0; v < fpv.size(); ++v) fpv[v] = m->kind[0].n[v] + m->kind[1].n[v];
+    }
+    // 2. :194-201: RANSAC, the draws in the order the reference reaches the pairs
+    std::vector<int32_t> samples(static_cast<size_t>(nok) * ransac->max_iterations * 8);
+    if (osfm_ransac_draw_samples(nok, off.data(), ransac->max_iterations, samples.data()) != OSFM_OK) {
+        std::lock_guard<std::mutex> lock(m->mu);
+        return fail(m, OSFM_ERR_INTERNAL, "candidate list shorter than 8 matches");
+    }
+    std::vector<int32_t> inl(static_cast<size_t>(2 * off[nok]));
+    std::vector<int64_t> inl_off(static_cast<size_t>(nok) + 1, 0);
+    OS_TRY(osfm_ransac_fundamental(m, static_cast<int>(fpv.size()), fpv.data(), positions, pv.data(), off.data(), match_ij,
+                                   nok, samples.data(), ransac->max_iterations, ransac->threshold, inl.data(),
+                                   inl_off.data(), nullptr));
+    // 3. :203-220: the inlier threshold; the inliers replace the candidate lists
+    int const thr = std::max(8, ransac->min_matching_inliers);
+    int64_t at = 0;
+    int k = 0;
+    for (int i = 0; i < npairs; ++i) {
+        list_offset[i] = at;
+        if (status[i] != OSFM_TWO_VIEW_OK) continue;
+        int64_t const n = inl_off[k + 1] - inl_off[k];
+        count[i] = static_cast<int32_t>(n);
+        if (n < thr) {
+            status[i] = OSFM_TWO_VIEW_TOO_FEW_INLIERS;
+        } else {
+            memcpy(match_ij + 2 * at, inl.data() + 2 * inl_off[k], sizeof(int32_t) * 2 * n);
+            at += n;
+        }
+        ++k;
+    }
+    list_offset[npairs] = at;
+    return OSFM_OK;
+}
+
 // ---- on-disk format (MVE prebundle) ------------------------------------------------------------
 
 int osfm_io_save_prebundle(const char* path, int num_views, const int32_t* features_per_view,

@@ -86,13 +86,18 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 TWO_VIEW_OK, TWO_VIEW_SKIPPED, TWO_VIEW_LOWRES_REJECTED, TWO_VIEW_TOO_FEW_MATCHES = 0, 1, 2, 3
+TWO_VIEW_TOO_FEW_INLIERS = 4
 
 
 class TwoViewOptions:
     """The matcher-side fields of sfm::bundler::Matching::Options (bundler_matching.h:58-76)."""
 
     def __init__(self, use_lowres_matching=False, num_lowres_features=500, min_lowres_matches=5,
-                 min_feature_matches=24, match_num_previous_frames=0):
+                 min_feature_matches=24, match_num_previous_frames=0, min_matching_inliers=12,
+                 ransac_max_iterations=1000, ransac_threshold=0.0015):
+        self.min_matching_inliers = min_matching_inliers
+        self.ransac_max_iterations = ransac_max_iterations
+        self.ransac_threshold = ransac_threshold
         self.use_lowres_matching = use_lowres_matching
         self.num_lowres_features = num_lowres_features
         self.min_lowres_matches = min_lowres_matches
@@ -347,6 +352,39 @@ class ExhaustiveMatching:
         self._check(self._L.osfm_match_two_view_candidates(
             self._h, C.byref(o), pr.ctypes.data_as(i32p), npairs, ij.ctypes.data_as(C.c_void_p), C.c_int64(cap),
             loff.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(i32p), count.ctypes.data_as(i32p)))
+        return [(int(status[p]), int(count[p]), ij[loff[p]:loff[p + 1]].copy()) for p in range(npairs)]
+
+    def two_view_matching(self, pairs, positions, opts: "TwoViewOptions" = None) -> list:
+        """bundler::Matching::compute's loop body for a list of pairs (bundler_matching.cc:92-220):
+        candidates, RANSAC-F (samples from std::rand() in pair order), inlier threshold.
+        ``positions``: [sum of features, 2] float32, view after view.  Returns one
+        ``(status, count, ij)`` per pair; the TWO_VIEW_OK ones are the PairwiseMatching."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pr.shape[0]
+        opts = opts if opts is not None else TwoViewOptions()
+        o = _lib.TwoViewOptions()
+        self._L.osfm_match_two_view_default_options(C.byref(o))
+        for name in ("use_lowres_matching", "num_lowres_features", "min_lowres_matches",
+                     "min_feature_matches", "match_num_previous_frames"):
+            setattr(o, name, int(getattr(opts, name)))
+        r = _lib.RansacOptions()
+        self._L.osfm_match_ransac_default_options(C.byref(r))
+        r.max_iterations = int(opts.ransac_max_iterations)
+        r.min_matching_inliers = int(opts.min_matching_inliers)
+        r.threshold = float(opts.ransac_threshold)
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+        if len(pos) != sum(sum(sz) for sz in self._sizes):
+            raise ValueError("positions must hold one (x, y) per feature of every view")
+        cap = int(sum(min(sum(self._sizes[a]), sum(self._sizes[b])) for a, b in pr)) + 1
+        ij = np.empty((cap, 2), np.int32)
+        loff = np.zeros(npairs + 1, np.int64)
+        status = np.zeros(npairs, np.int32)
+        count = np.zeros(npairs, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_two_view(
+            self._h, C.byref(o), C.byref(r), pos.ctypes.data_as(C.POINTER(C.c_float)), pr.ctypes.data_as(i32p), npairs,
+            ij.ctypes.data_as(C.c_void_p), C.c_int64(cap), loff.ctypes.data_as(C.POINTER(C.c_int64)),
+            status.ctypes.data_as(i32p), count.ctypes.data_as(i32p)))
         return [(int(status[p]), int(count[p]), ij[loff[p]:loff[p + 1]].copy()) for p in range(npairs)]
 
     def tracks_compute(self, features_per_view, pair_views, offsets, ij) -> tuple:

@@ -165,3 +165,33 @@ def two_view_scene(seed: int, n: int, outlier_fraction: float = 0.3, noise: floa
     wrong = rng.random(n) < outlier_fraction
     x2[wrong] = rng.uniform(-0.5, 0.5, (int(wrong.sum()), 2))
     return np.concatenate([x1, x2], 1).astype(np.float32)
+
+
+def sfm_scene(seed: int, num_views: int, n: int, scene_points: int, visible: float = 0.5, noise: float = 2e-4):
+    """A multi-view scene for the whole two-view stage: ``scene_points`` 3-D points, each with
+    a SIFT descriptor; every view sees a random ``visible`` fraction of them from its own pose
+    (descriptor re-quantised with a little noise, position = projection + noise) and fills the
+    rest of its ``n`` features with private descriptors at random positions.  Returns
+    (list of [n, 128] uint8 descriptors, list of [n, 2] float32 positions)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (scene_points, 3)) + np.array([0, 0, 5.0])
+    pool = _normalise_clamp_quantise(np.abs(rng.standard_normal((scene_points, SIFT_DIM), dtype=np.float32)))
+    descs, poss = [], []
+    for v in range(num_views):
+        a = rng.uniform(-0.25, 0.25, 3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+        Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+        Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+        Y = X @ (Rz @ Ry @ Rx).T + rng.uniform(-0.5, 0.5, 3)
+        proj = 1.2 * Y[:, :2] / Y[:, 2:3]
+        k = min(int(scene_points * visible), n)
+        seen = rng.permutation(scene_points)[:k]
+        desc = _normalise_clamp_quantise(np.abs(rng.standard_normal((n, SIFT_DIM), dtype=np.float32)))
+        pos = rng.uniform(-0.5, 0.5, (n, 2))
+        rows = rng.permutation(n)[:k]
+        x = pool[seen].astype(np.float32) / 255.0
+        desc[rows] = _normalise_clamp_quantise(np.abs(x + RENORM_SIGMA * rng.standard_normal(x.shape, dtype=np.float32)))
+        pos[rows] = proj[seen] + rng.normal(0, noise, (k, 2))
+        descs.append(desc)
+        poss.append(pos.astype(np.float32))
+    return descs, poss

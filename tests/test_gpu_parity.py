@@ -5,6 +5,7 @@ import pytest
 
 from orthosfm_b200 import (ExhaustiveMatching, FeatureSet, KIND_SIFT_U8, KIND_SURF_S8,
                            MatcherError, Matching, MatchingBase, Viewport, synth)
+from orthosfm_b200 import TwoViewOptions, TWO_VIEW_OK, TWO_VIEW_SKIPPED, TWO_VIEW_LOWRES_REJECTED, TWO_VIEW_TOO_FEW_MATCHES  # noqa: E402,F811
 
 pytestmark = pytest.mark.gpu
 
@@ -806,6 +807,43 @@ def test_ransac_fundamental_argument_errors():
             m.ransac_fundamental(feats, pos, pairs, off, bad, max_iterations=10)
         ooff, oij, F = m.ransac_fundamental(feats, pos, pairs[:0], off[:1], ij[:0], max_iterations=10)
         assert ooff.tolist() == [0] and len(oij) == 0
+
+
+@pytest.mark.parametrize("lowres", [False, True])
+def test_two_view_stage_equals_reference_bundler_matching(lowres):
+    """osfm_match_two_view over all pairs in the order of bundler::Matching::compute against
+    the reference's own bundler::Matching (init + compute, bundler_matching.cc:45-220) on the
+    same viewports and the same std::rand() seed: the same pairs survive, with the same
+    inlier matches."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    nv, n = 7, 1200
+    descs, poss = synth.sfm_scene(4, nv, n, 900, visible=0.45)
+    descs[5] = descs[5][:0]; poss[5] = poss[5][:0]              # a view without features
+    descs[6] = _unrelated(descs[6])                              # a view that matches nothing
+    empty = np.zeros((0, 64), np.float32)
+    rx = oracle.Reference().exhaustive([(d.astype(np.float32) / 255.0, empty) for d in descs])
+    kw = dict(use_lowres_matching=lowres, num_lowres_features=400, min_lowres_matches=12, min_feature_matches=50,
+              min_matching_inliers=30, ransac_max_iterations=250, ransac_threshold=0.0015)
+    want = rx.bundler_compute(np.concatenate(poss), seed=5, **kw)
+    pairs = [(a, b) for a in range(nv) for b in range(a)]       # i -> (view_1, view_2), bundler_matching.cc:92-93
+    opts = TwoViewOptions(**kw)
+    oracle.srand(5)
+    with matcher(descs) as m:
+        got = m.two_view_matching(pairs, np.concatenate(poss), opts)
+    accepted = [(a, b, ij) for (a, b), (st, cnt, ij) in zip(pairs, got) if st == TWO_VIEW_OK]
+    assert len(want) >= 8 and len(accepted) == len(want)
+    for (wa, wb, wij), (a, b, ij) in zip(want, accepted):
+        assert (wa, wb) == (a, b)
+        assert np.array_equal(wij, ij), (a, b)
+    statuses = {st for st, _, _ in got}
+    assert TWO_VIEW_SKIPPED in statuses and (TWO_VIEW_TOO_FEW_MATCHES in statuses or TWO_VIEW_LOWRES_REJECTED in statuses)
+
+
+def _unrelated(desc):
+    rng = np.random.default_rng(99)
+    return synth._normalise_clamp_quantise(np.abs(rng.standard_normal(desc.shape, dtype=np.float32)))
 
 
 # ------------------------------------------------------------------ the reference-side binding

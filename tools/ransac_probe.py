@@ -8,7 +8,7 @@ from orthosfm_b200 import synth, ransac_draw_samples, Matching
 from orthosfm_b200.matcher import ExhaustiveMatching
 sys.path.insert(0, "tests")
 
-npairs, n, iters = 630, 1024, 1000
+npairs, n, iters = int(sys.argv[1]) if len(sys.argv) > 1 else 630, 1024, 1000
 feats, pos, pairs, lists = [], [], [], []
 for p in range(npairs):
     xy = synth.two_view_scene(p, n, 0.3)
