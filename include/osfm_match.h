@@ -262,8 +262,10 @@ int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_ite
  * match_ij[2*list_offset[p] .. 2*list_offset[p+1]).  inlier_ij (capacity
  * 2*list_offset[npairs] ints) receives the inlier matches of the pairs back to back,
  * inlier_offset npairs+1 offsets; fundamental (may be NULL) 9 doubles per pair, row-major
- * (zeros for a pair without inliers).  The thresholds on the inlier count stay with the
- * caller (bundler_matching.cc:203-210). */
+ * (zeros for a pair without inliers).  samples == NULL: the library draws them itself, as
+ * osfm_ransac_draw_samples would, chunk of pairs by chunk while the device works on the
+ * chunk before (the draws are the longer leg).  The thresholds on the inlier count stay
+ * with the caller (bundler_matching.cc:203-210). */
 int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* features_per_view,
     const float* positions, const int32_t* pair_views, const int64_t* list_offset,
     const int32_t* match_ij, int npairs, const int32_t* samples, int max_iterations,

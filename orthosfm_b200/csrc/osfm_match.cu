@@ -136,6 +136,9 @@ struct osfm_matcher {
     DevBuf<double> rs_F;
     DevBuf<int> rs_cnt;
     DevBuf<int2> rs_out;
+    int32_t* rs_stage[2] = {nullptr, nullptr};   // pinned staging for samples drawn here, double-buffered
+    size_t rs_stage_ints = 0;
+    cudaEvent_t rs_stage_free[2] = {nullptr, nullptr};
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
@@ -758,6 +761,12 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->tr_ints.release(); m->tr_table.release(); m->tr_meta.release(); m->tr_meta32.release();
     m->rs_xy.release(); m->rs_pos.release(); m->rs_samples.release(); m->rs_F.release(); m->rs_cnt.release();
     m->rs_out.release();
+    for (int k = 0; k < 2; ++k) {
+        if (m->rs_stage[k]) cudaFreeHost(m->rs_stage[k]);
+        if (m->rs_stage_free[k]) cudaEventDestroy(m->rs_stage_free[k]);
+        m->rs_stage[k] = nullptr; m->rs_stage_free[k] = nullptr;
+    }
+    m->rs_stage_ints = 0;
     m->d_ftmp.release();
     m->d_seg_first.release();
     for (auto& sp : m->pass) sp.release();
@@ -1453,17 +1462,11 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
 
 // ---- RANSAC for the fundamental matrix ------------------------------------------------------------
 
-int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_iterations, int32_t* samples) {
-    if (npairs < 0 || max_iterations < 0 || (npairs > 0 && (!list_offset || !samples))) return OSFM_ERR_INVALID_ARGUMENT;
-    for (int p = 0; p < npairs; ++p) {
-        int64_t const count = list_offset[p + 1] - list_offset[p];
-        if (count < 8 || count > INT32_MAX) return OSFM_ERR_INVALID_ARGUMENT;    // the reference throws below 8
-    }
-    // RansacFundamental::estimate_8_point, ransac_fundamental.cc:70-76: rand() % count into an
-    // ordered set until it holds eight; the set is then read in ascending order.
+// RansacFundamental::estimate_8_point, ransac_fundamental.cc:70-76: rand() % count into an
+// ordered set until it holds eight; the set is then read in ascending order.
+static void draw_samples_for_pairs(int npairs, const int64_t* list_offset, int max_iterations, int32_t* out) {
     for (int p = 0; p < npairs; ++p) {
         unsigned long const count = static_cast<unsigned long>(list_offset[p + 1] - list_offset[p]);
-        int32_t* out = samples + static_cast<size_t>(p) * max_iterations * 8;
         for (int it = 0; it < max_iterations; ++it, out += 8) {
             int have = 0;
             while (have < 8) {
@@ -1477,6 +1480,15 @@ int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_ite
             }
         }
     }
+}
+
+int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_iterations, int32_t* samples) {
+    if (npairs < 0 || max_iterations < 0 || (npairs > 0 && (!list_offset || !samples))) return OSFM_ERR_INVALID_ARGUMENT;
+    for (int p = 0; p < npairs; ++p) {
+        int64_t const count = list_offset[p + 1] - list_offset[p];
+        if (count < 8 || count > INT32_MAX) return OSFM_ERR_INVALID_ARGUMENT;    // the reference throws below 8
+    }
+    draw_samples_for_pairs(npairs, list_offset, max_iterations, samples);
     return OSFM_OK;
 }
 
@@ -1488,7 +1500,7 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0 || npairs < 0 || max_iterations < 0 || (num_views > 0 && !features_per_view) || !inlier_offset ||
-        (npairs > 0 && (!pair_views || !list_offset || !samples || !positions || !match_ij || !inlier_ij)))
+        (npairs > 0 && (!pair_views || !list_offset || !positions || !match_ij || !inlier_ij)))
         return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
     inlier_offset[0] = 0;
     if (npairs == 0) return OSFM_OK;
@@ -1535,21 +1547,54 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     CU_TRY(m, cudaMemcpyAsync(d_ij, match_ij, sizeof(int2) * nmatches, cudaMemcpyHostToDevice, st));
     if (base[num_views] > 0)
         CU_TRY(m, cudaMemcpyAsync(m->rs_pos.p, positions, sizeof(float2) * base[num_views], cudaMemcpyHostToDevice, st));
-    if (nfits > 0)
-        CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p, samples, sizeof(int32_t) * 8 * nfits, cudaMemcpyHostToDevice, st));
     ransac_gather_kernel<<<static_cast<unsigned>((nmatches + 255) / 256), 256, 0, st>>>(
         d_pv, d_off, npairs, d_ij, nmatches, d_base, d_vn, m->rs_pos.p, m->rs_xy.p, d_bad + 0);
     double const thr2 = threshold * threshold;       // ransac_fundamental.cc:97
-    if (nfits > 0) {
-        ransac_fit_kernel<<<static_cast<unsigned>((nfits + 127) / 128), 128, 0, st>>>(
-            d_off, npairs, max_iterations, m->rs_samples.p, m->rs_xy.p, m->rs_F.p, d_bad + 1);
-        ransac_count_kernel<<<static_cast<unsigned>((nfits * 32 + 255) / 256), 256, 0, st>>>(
-            d_off, npairs, max_iterations, m->rs_xy.p, m->rs_F.p, thr2, m->rs_cnt.p);
+    // Pairs go through in chunks.  When the samples are drawn here, the draws of one chunk (host,
+    // std::rand()) run while the device works on the chunk before: the draws are the longer
+    // leg (about 20 ns per rand() call, 8000+ calls per pair), so the device time hides
+    // behind them.
+    int const per_pair = 8 * max_iterations;
+    int const chunk = std::max(1, std::min(npairs, (1 << 19) / std::max(per_pair, 1)));      // about 2 MB of samples
+    if (!samples && per_pair > 0) {
+        size_t const want = static_cast<size_t>(chunk) * per_pair;
+        if (want > m->rs_stage_ints) {
+            for (int k = 0; k < 2; ++k) {
+                if (m->rs_stage[k]) cudaFreeHost(m->rs_stage[k]);
+                m->rs_stage[k] = nullptr;
+                CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&m->rs_stage[k]), want * sizeof(int32_t), cudaHostAllocDefault));
+                if (!m->rs_stage_free[k]) CU_TRY(m, cudaEventCreateWithFlags(&m->rs_stage_free[k], cudaEventDisableTiming));
+            }
+            m->rs_stage_ints = want;
+        }
     }
-    ransac_select_kernel<<<npairs, 256, 0, st>>>(d_off, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p, m->rs_cnt.p, thr2,
-                                                 d_inl, d_count, d_bestF);
+    int launches = 1;
+    for (int p0 = 0, c = 0; p0 < npairs; p0 += chunk, ++c) {
+        int const np = std::min(chunk, npairs - p0);
+        int64_t const fits = static_cast<int64_t>(np) * max_iterations;
+        int64_t const f0 = static_cast<int64_t>(p0) * max_iterations;
+        if (fits > 0) {
+            const int32_t* src = samples ? samples + f0 * 8 : nullptr;
+            if (!samples) {
+                int const buf = c & 1;
+                if (c >= 2) CU_TRY(m, cudaEventSynchronize(m->rs_stage_free[buf]));       // its last copy has left
+                draw_samples_for_pairs(np, list_offset + p0, max_iterations, m->rs_stage[buf]);
+                src = m->rs_stage[buf];
+            }
+            CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p + f0 * 8, src, sizeof(int32_t) * 8 * fits, cudaMemcpyHostToDevice, st));
+            if (!samples) CU_TRY(m, cudaEventRecord(m->rs_stage_free[c & 1], st));
+            ransac_fit_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(
+                d_off + p0, np, max_iterations, m->rs_samples.p + f0 * 8, m->rs_xy.p, m->rs_F.p + f0 * 9, d_bad + 1);
+            ransac_count_kernel<<<static_cast<unsigned>((fits * 32 + 255) / 256), 256, 0, st>>>(
+                d_off + p0, np, max_iterations, m->rs_xy.p, m->rs_F.p + f0 * 9, thr2, m->rs_cnt.p + f0);
+            launches += 2;
+        }
+        ransac_select_kernel<<<np, 256, 0, st>>>(d_off + p0, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p + f0 * 9,
+                                                 m->rs_cnt.p + f0, thr2, d_inl, d_count + p0, d_bestF + 9 * p0);
+        launches += 1;
+    }
     CU_TRY(m, cudaGetLastError());
-    m->stats.kernel_launches += nfits > 0 ? 4 : 2;
+    m->stats.kernel_launches += launches;
     std::vector<int> count(static_cast<size_t>(npairs) + 2);
     std::vector<int2> inl(static_cast<size_t>(nmatches));
     CU_TRY(m, cudaMemcpyAsync(count.data(), d_count, sizeof(int) * (npairs + 2), cudaMemcpyDeviceToHost, st));
@@ -1608,16 +1653,11 @@ int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, cons
         fpv.resize(m->kind[0].n.size());
         for (size_t v = 0; v < fpv.size(); ++v) fpv[v] = m->kind[0].n[v] + m->kind[1].n[v];
     }
-    // 2. :194-201: RANSAC, the draws in the order the reference reaches the pairs
-    std::vector<int32_t> samples(static_cast<size_t>(nok) * ransac->max_iterations * 8);
-    if (osfm_ransac_draw_samples(nok, off.data(), ransac->max_iterations, samples.data()) != OSFM_OK) {
-        std::lock_guard<std::mutex> lock(m->mu);
-        return fail(m, OSFM_ERR_INTERNAL, "candidate list shorter than 8 matches");
-    }
+    // 2. :194-201: RANSAC; the samples are drawn inside, in the order the reference reaches the pairs
     std::vector<int32_t> inl(static_cast<size_t>(2 * off[nok]));
     std::vector<int64_t> inl_off(static_cast<size_t>(nok) + 1, 0);
     OS_TRY(osfm_ransac_fundamental(m, static_cast<int>(fpv.size()), fpv.data(), positions, pv.data(), off.data(), match_ij,
-                                   nok, samples.data(), ransac->max_iterations, ransac->threshold, inl.data(),
+                                   nok, nullptr, ransac->max_iterations, ransac->threshold, inl.data(),
                                    inl_off.data(), nullptr));
     // 3. :203-220: the inlier threshold; the inliers replace the candidate lists
     int const thr = std::max(8, ransac->min_matching_inliers);

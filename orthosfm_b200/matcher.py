@@ -407,8 +407,8 @@ class ExhaustiveMatching:
     def ransac_fundamental(self, features_per_view, positions, pair_views, offsets, ij, samples=None,
                            max_iterations: int = 1000, threshold: float = 0.0015) -> tuple:
         """sfm::RansacFundamental::estimate (ransac_fundamental.cc:26-105) for every pair at
-        once.  samples=None draws them here from std::rand(), in pair order, as the reference
-        does (ransac_draw_samples).  Returns (inlier offsets [npairs + 1], inlier (i, j) lists,
+        once.  samples=None: the library draws them from std::rand(), in pair order, as the
+        reference does, overlapped with the device work.  Returns (inlier offsets [npairs + 1], inlier (i, j) lists,
         fundamental matrices [npairs, 3, 3])."""
         f = np.ascontiguousarray(features_per_view, np.int32)
         pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
@@ -417,18 +417,19 @@ class ExhaustiveMatching:
         m = np.ascontiguousarray(np.asarray(ij, np.int32).reshape(-1, 2))
         if len(pos) != int(f.sum()):
             raise ValueError("positions must hold one (x, y) per feature")
-        if samples is None:
-            samples = ransac_draw_samples(off, max_iterations)
-        smp = np.ascontiguousarray(samples, np.int32)
-        if smp.size != len(pv) * max_iterations * 8:
-            raise ValueError("samples must hold 8 indices per pair and iteration")
+        smp = None
+        if samples is not None:
+            smp = np.ascontiguousarray(samples, np.int32)
+            if smp.size != len(pv) * max_iterations * 8:
+                raise ValueError("samples must hold 8 indices per pair and iteration")
         out = np.empty((max(len(m), 1), 2), np.int32)
         out_off = np.zeros(len(pv) + 1, np.int64)
         F = np.zeros((len(pv), 3, 3), np.float64)
         i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         self._check(self._L.osfm_ransac_fundamental(
             self._h, len(f), f.ctypes.data_as(i32p), pos.ctypes.data_as(C.POINTER(C.c_float)), pv.ctypes.data_as(i32p),
-            off.ctypes.data_as(i64p), m.ctypes.data_as(i32p), len(pv), smp.ctypes.data_as(i32p), int(max_iterations),
+            off.ctypes.data_as(i64p), m.ctypes.data_as(i32p), len(pv),
+            None if smp is None else smp.ctypes.data_as(i32p), int(max_iterations),
             float(threshold), out.ctypes.data_as(i32p), out_off.ctypes.data_as(i64p),
             F.ctypes.data_as(C.POINTER(C.c_double))))
         return out_off, out[:out_off[-1]], F

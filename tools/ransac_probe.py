@@ -24,6 +24,12 @@ with matcher(synth.sift_views(1, 2, 64)) as m:
         ooff, oij, F = m.ransac_fundamental(feats, pos, pairs, off, ij, samples=smp, max_iterations=iters)
         t2 = time.perf_counter()
         print(f"draw {1e3*(t1-t0):.1f} ms, device call {1e3*(t2-t1):.1f} ms, inliers {ooff[-1]}", flush=True)
+        oracle.srand(1)
+        t0 = time.perf_counter()
+        ooff2, oij2, F2 = m.ransac_fundamental(feats, pos, pairs, off, ij, max_iterations=iters)
+        t1 = time.perf_counter()
+        assert np.array_equal(ooff, ooff2) and np.array_equal(oij, oij2) and np.array_equal(F, F2)
+        print(f"draws inside, overlapped: {1e3*(t1-t0):.1f} ms", flush=True)
 if oracle.have_ref():
     ref = oracle.Reference()
     oracle.srand(1)
