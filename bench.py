@@ -210,6 +210,49 @@ def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
 
 # --------------------------------------------------------------------------- our arm
 
+def downstream_rows(me, pairs, n, num_views, lists, loff):
+    """Not part of the metric: the steps after the matcher timed
+    once on this workload's own match lists, with the reference beside them on a few pairs."""
+    import oracle
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-0.5, 0.5, (num_views * n, 2)).astype(np.float32)       # timing does not depend on the geometry
+    feats = [n] * num_views
+    ij = lists[:loff[-1]]
+    keep = np.flatnonzero(np.diff(loff) >= 8)
+    kp = np.asarray(pairs)[keep]
+    koff = np.concatenate([[0], np.cumsum(np.diff(loff)[keep])]).astype(np.int64)
+    kij = np.concatenate([ij[loff[p]:loff[p + 1]] for p in keep]) if len(keep) else ij[:0]
+    out = {"pairs": int(len(keep)), "matches": int(koff[-1]), "ransac_iterations": 1000}
+    for rep in range(2):
+        oracle.srand(1)
+        t0 = time.perf_counter()
+        ooff, oij, F = me.ransac_fundamental(feats, pos, kp, koff, kij, max_iterations=1000, threshold=0.0015)
+        out["ransac_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ids, ntracks, _ = me.tracks_compute(feats, pairs, loff, ij)
+        out["tracks_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["tracks"] = int(ntracks)
+    out["note"] = ("osfm_ransac_fundamental (std::rand draws on the host inside, overlapped with the device) and "
+                   "osfm_tracks_compute on this step's match lists; host buffers in and out")
+    if oracle.have_ref():
+        ref = oracle.Reference()
+        base = np.arange(num_views) * n
+        k = min(4, len(keep))
+        oracle.srand(1)
+        t0 = time.perf_counter()
+        same = True
+        for p in range(k):
+            l = kij[koff[p]:koff[p + 1]]
+            xy = np.concatenate([pos[base[kp[p][0]] + l[:, 0]], pos[base[kp[p][1]] + l[:, 1]]], 1)
+            inl, _ = ref.ransac(xy, 1000, 0.0015)
+            same = same and np.array_equal(oij[ooff[p]:ooff[p + 1]], l[inl])
+        dt = time.perf_counter() - t0
+        out["reference_ransac_ms_extrapolated"] = 1e3 * dt / max(k, 1) * len(keep)
+        out["reference_ransac_sample"] = f"{k} pairs, 1 core"
+        out["ransac_equals_reference_on_sample"] = bool(same)
+    return out
+
+
 def run_ours(args, config):
     import torch
     import torch.distributed as dist
@@ -360,6 +403,7 @@ def run_ours(args, config):
                "dense": {"value": my_cmp * scale / dense_s, "ms_per_step": 1e3 * dense_s, "d2h_bytes_per_step": d2h_dense,
                          "note": "same, osfm_match_pairs: the dense Matching::Result vectors of every pair"},
                "lists_equal_dense_on_sample": bool(lists_equal_dense)}
+        downstream = downstream_rows(me, my_pairs, n, len(views_np), lists_host, loff_h) if world == 1 else None
         me.close()
         # ---- CPU baseline + result check on the sampled pairs ----------------------------
         cpu_base, ref_counts = cpu_baseline_sample(views_np, my_pairs)
@@ -396,6 +440,7 @@ def run_ours(args, config):
         "matches_per_step": total_matches,
         "matches_equal_reference_on_sample": check,
         "broadcast_ms": broadcast_ms,
+        "downstream": downstream if rank == 0 and world == 1 else None,
         "stats": dict({k: v for k, v in m.stats().items()
                        if k in ("candidate_rows", "slow_rows", "exact_rows", "self_check_failures")},
                       rows_per_step=int(2 * my_cmp // n), steps_counted=max(args.warmup, 3) + args.steps),

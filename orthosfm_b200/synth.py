@@ -167,16 +167,23 @@ def two_view_scene(seed: int, n: int, outlier_fraction: float = 0.3, noise: floa
     return np.concatenate([x1, x2], 1).astype(np.float32)
 
 
-def sfm_scene(seed: int, num_views: int, n: int, scene_points: int, visible: float = 0.5, noise: float = 2e-4):
+def sfm_scene(seed: int, num_views: int, n: int, scene_points: int, visible: float = 0.5, noise: float = 2e-4,
+              surf_n: int = 0):
     """A multi-view scene for the whole two-view stage: ``scene_points`` 3-D points, each with
     a SIFT descriptor; every view sees a random ``visible`` fraction of them from its own pose
     (descriptor re-quantised with a little noise, position = projection + noise) and fills the
     rest of its ``n`` features with private descriptors at random positions.  Returns
-    (list of [n, 128] uint8 descriptors, list of [n, 2] float32 positions)."""
+    (list of [n, 128] uint8 descriptors, list of [n, 2] float32 positions).  With ``surf_n``
+    every view also gets that many SURF features (half of them of a second set of scene
+    points): returns (sift, surf [surf_n, 64] int8, positions [n + surf_n, 2], SIFT rows first
+    as in FeatureSet::positions)."""
     rng = np.random.default_rng(seed)
     X = rng.uniform(-1, 1, (scene_points, 3)) + np.array([0, 0, 5.0])
     pool = _normalise_clamp_quantise(np.abs(rng.standard_normal((scene_points, SIFT_DIM), dtype=np.float32)))
-    descs, poss = [], []
+    ks = surf_n // 2
+    Xs = rng.uniform(-1, 1, (ks, 3)) + np.array([0, 0, 5.0])
+    spool = surf_view(seed, 10 ** 6, ks) if ks else None
+    descs, poss, surfs = [], [], []
     for v in range(num_views):
         a = rng.uniform(-0.25, 0.25, 3)
         Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
@@ -193,5 +200,17 @@ def sfm_scene(seed: int, num_views: int, n: int, scene_points: int, visible: flo
         desc[rows] = _normalise_clamp_quantise(np.abs(x + RENORM_SIGMA * rng.standard_normal(x.shape, dtype=np.float32)))
         pos[rows] = proj[seen] + rng.normal(0, noise, (k, 2))
         descs.append(desc)
+        if surf_n:
+            q = surf_view(seed, v, surf_n)
+            spos = rng.uniform(-0.5, 0.5, (surf_n, 2))
+            srows = rng.permutation(surf_n)[:ks]
+            d = rng.integers(-1, 2, size=(ks, SURF_DIM), dtype=np.int16)
+            q[srows] = np.clip(spool.astype(np.int16) + d, -127, 127).astype(np.int8)
+            Ys = Xs @ (Rz @ Ry @ Rx).T + (Y[0] - X[0] @ (Rz @ Ry @ Rx).T)
+            spos[srows] = 1.2 * Ys[:, :2] / Ys[:, 2:3] + rng.normal(0, noise, (ks, 2))
+            surfs.append(q)
+            pos = np.concatenate([pos, spos])
         poss.append(pos.astype(np.float32))
+    if surf_n:
+        return descs, surfs, poss
     return descs, poss

@@ -841,6 +841,29 @@ def test_two_view_stage_equals_reference_bundler_matching(lowres):
     assert TWO_VIEW_SKIPPED in statuses and (TWO_VIEW_TOO_FEW_MATCHES in statuses or TWO_VIEW_LOWRES_REJECTED in statuses)
 
 
+def test_two_view_stage_with_sift_and_surf_equals_reference():
+    """The same with SIFT and SURF features: the lists, the positions and the RANSAC samples
+    live in the combined [sift..., surf...] index space (matching.cc:50-89)."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    nv = 5
+    sift, surf, poss = synth.sfm_scene(8, nv, 900, 600, visible=0.5, surf_n=400)
+    rx = oracle.Reference().exhaustive([(d.astype(np.float32) / 255.0, s.astype(np.float32) / np.float32(127.0))
+                                        for d, s in zip(sift, surf)])
+    kw = dict(min_feature_matches=40, min_matching_inliers=25, ransac_max_iterations=200)
+    want = rx.bundler_compute(np.concatenate(poss), seed=9, **kw)
+    pairs = [(a, b) for a in range(nv) for b in range(a)]
+    oracle.srand(9)
+    with matcher(sift, surf) as m:
+        got = m.two_view_matching(pairs, np.concatenate(poss), TwoViewOptions(**kw))
+    accepted = [(a, b, ij) for (a, b), (st, cnt, ij) in zip(pairs, got) if st == TWO_VIEW_OK]
+    assert len(want) == len(pairs) == len(accepted)
+    for (wa, wb, wij), (a, b, ij) in zip(want, accepted):
+        assert (wa, wb) == (a, b) and np.array_equal(wij, ij), (a, b)
+        assert (ij[:, 0] >= 900).any() and (ij[:, 0] < 900).any()      # SURF and SIFT matches among the inliers
+
+
 def _unrelated(desc):
     rng = np.random.default_rng(99)
     return synth._normalise_clamp_quantise(np.abs(rng.standard_normal(desc.shape, dtype=np.float32)))
