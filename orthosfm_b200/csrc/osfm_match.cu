@@ -1462,22 +1462,85 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
 
 // ---- RANSAC for the fundamental matrix ------------------------------------------------------------
 
+// The reference draws from std::rand().  Under glibc that is random() behind a lock (about
+// 20 ns a call, and a pair needs 8000+ calls); RandSequence reads the very same generator
+// without the lock: setstate() parks the process-wide generator on a scratch state and hands
+// out its real state, setstate_r() attaches a private random_data to that state, random_r()
+// steps it (the same additive-feedback recurrence, the same values), and the destructor stores
+// the advanced position back and makes it the process-wide state again.  Whoever calls rand()
+// afterwards continues exactly where the reference's own draws would have left the sequence.
+// Not for use while another thread calls rand() (neither is the reference).
+class RandSequence {
+public:
+#if defined(__GLIBC__)
+    RandSequence() {
+        memset(&park_rd_, 0, sizeof park_rd_);
+        memset(&rd_, 0, sizeof rd_);
+        // two valid scratch states: one for the process-wide generator to rest on, one for rd_
+        // to be initialised with (setstate_r writes through the state it leaves)
+        if (initstate_r(1u, park_, sizeof park_, &park_rd_) != 0 || initstate_r(1u, spare_, sizeof spare_, &rd_) != 0) return;
+        real_ = setstate(park_);
+        if (!real_) return;
+        if (setstate_r(real_, &rd_) != 0) { setstate(real_); real_ = nullptr; return; }
+    }
+    ~RandSequence() {
+        if (!real_) return;
+        setstate_r(spare_, &rd_);      // writes the position reached into the real state
+        setstate(real_);
+    }
+    int next() {
+        if (!real_) return std::rand();
+        int32_t v;
+        random_r(&rd_, &v);
+        return static_cast<int>(v);
+    }
+private:
+    alignas(8) char park_[128];
+    alignas(8) char spare_[128];
+    struct random_data park_rd_, rd_;
+    char* real_ = nullptr;
+#else
+    int next() { return std::rand(); }
+#endif
+    RandSequence(const RandSequence&) = delete;
+    RandSequence& operator=(const RandSequence&) = delete;
+};
+
 // RansacFundamental::estimate_8_point, ransac_fundamental.cc:70-76: rand() % count into an
 // ordered set until it holds eight; the set is then read in ascending order.
+static inline void order2(int32_t& a, int32_t& b) {
+    int32_t const lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
 static void draw_samples_for_pairs(int npairs, const int64_t* list_offset, int max_iterations, int32_t* out) {
+    RandSequence seq;
     for (int p = 0; p < npairs; ++p) {
-        unsigned long const count = static_cast<unsigned long>(list_offset[p + 1] - list_offset[p]);
+        // rand() % count without a division per draw (Lemire's fastmod: exact for 32-bit operands)
+        uint32_t const count = static_cast<uint32_t>(list_offset[p + 1] - list_offset[p]);
+        uint64_t const magic = ~0ull / count + 1;
         for (int it = 0; it < max_iterations; ++it, out += 8) {
+            // the std::set of the reference: distinct values, read in ascending order.  Kept
+            // unsorted while drawing (a duplicate is rare, so that branch predicts), sorted once
+            // by a 19-exchange network.
+            int32_t s[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
             int have = 0;
             while (have < 8) {
-                int32_t const v = static_cast<int32_t>(static_cast<unsigned long>(std::rand()) % count);
-                int at = 0;
-                while (at < have && out[at] < v) ++at;
-                if (at < have && out[at] == v) continue;
-                for (int k = have; k > at; --k) out[k] = out[k - 1];
-                out[at] = v;
-                ++have;
+                uint64_t const low = magic * static_cast<uint32_t>(seq.next());
+                int32_t const v = static_cast<int32_t>((static_cast<unsigned __int128>(low) * count) >> 64);
+                int dup = 0;
+                for (int k = 0; k < 8; ++k) dup |= (s[k] == v);
+                if (dup) continue;
+                s[have++] = v;
             }
+            order2(s[0], s[1]); order2(s[2], s[3]); order2(s[4], s[5]); order2(s[6], s[7]);
+            order2(s[0], s[2]); order2(s[1], s[3]); order2(s[4], s[6]); order2(s[5], s[7]);
+            order2(s[1], s[2]); order2(s[5], s[6]); order2(s[0], s[4]); order2(s[3], s[7]);
+            order2(s[1], s[5]); order2(s[2], s[6]);
+            order2(s[1], s[4]); order2(s[3], s[6]);
+            order2(s[2], s[4]); order2(s[3], s[5]);
+            order2(s[3], s[4]);
+            for (int k = 0; k < 8; ++k) out[k] = s[k];
         }
     }
 }

@@ -263,3 +263,35 @@ def test_ransac_restatement_and_sample_draws_equal_reference(n, outliers):
             assert np.array_equal(wF, gF)
     if n >= 40 and outliers <= 0.3:
         assert len(want[0][0]) >= 0.5 * (1 - outliers) * n      # the scene is a real two-view geometry
+
+
+def test_sample_draws_leave_the_rand_sequence_where_the_reference_would():
+    """osfm_ransac_draw_samples reads the process-wide rand() sequence without glibc's lock
+    (setstate / random_r); whoever draws next must continue as if rand() had been called:
+    reference(A), reference(B)  ==  ours(A), reference(B), and plain rand() agrees as well."""
+    import ctypes
+    import oracle
+    from orthosfm_b200 import ransac_draw_samples
+    ref, hc = _hostcheck()
+    libc = ctypes.CDLL(None)
+    a = synth.two_view_scene(1, 300, 0.3).astype(np.float64)
+    b = synth.two_view_scene(2, 200, 0.3).astype(np.float64)
+    for seed in (0, 1, 12345):
+        oracle.srand(seed)
+        ref.ransac(a, 50, 0.0015)
+        want_b = ref.ransac(b, 50, 0.0015)
+        want_next = [libc.rand() for _ in range(5)]
+        oracle.srand(seed)
+        smp = ransac_draw_samples(np.array([0, len(a)], np.int64), 50)
+        got_b = ref.ransac(b, 50, 0.0015)
+        got_next = [libc.rand() for _ in range(5)]
+        assert np.array_equal(want_b[0], got_b[0]) and np.array_equal(want_b[1], got_b[1])
+        assert want_next == got_next
+        # the first sample is the first eight distinct values of rand() % n, sorted
+        oracle.srand(seed)
+        seen = []
+        while len(seen) < 8:
+            v = libc.rand() % len(a)
+            if v not in seen:
+                seen.append(v)
+        assert sorted(seen) == smp[0, 0].tolist()
