@@ -405,6 +405,16 @@ class RansacHostCheck:
         self.lib.osfm_hostcheck_fundamental(_ptr(p1, C.c_double), _ptr(p2, C.c_double), _ptr(F, C.c_double))
         return F
 
+    def fundamental_staged(self, p1, p2):
+        """The device's route: bidiagonalise / iterate with the fixed-point stop in a strided
+        buffer / finish / rank 2.  Returns (F, trips of the 9 x 9 loop)."""
+        p1, p2 = _c(p1, np.float64), _c(p2, np.float64)
+        F = np.zeros(9, np.float64)
+        it = C.c_int(0)
+        self.lib.osfm_hostcheck_fundamental_staged(_ptr(p1, C.c_double), _ptr(p2, C.c_double), _ptr(F, C.c_double),
+                                                   C.byref(it))
+        return F, it.value
+
     def sampson(self, F, match) -> float:
         F, match = _c(F, np.float64), _c(match, np.float64)
         return self.lib.osfm_hostcheck_sampson(_ptr(F, C.c_double), _ptr(match, C.c_double))

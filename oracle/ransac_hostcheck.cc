@@ -26,22 +26,73 @@ void
 osfm_hostcheck_svd9 (const double* a, double* s, double* v)
 {
     osfm::fmath::SquareSvd<9, false> svd;
-    for (int i = 0; i < 81; ++i) svd.b[i] = a[i];
+    for (int i = 0; i < 81; ++i) svd.bm.at(i) = a[i];
     svd.run();
     for (int i = 0; i < 9; ++i) s[i] = svd.s[i];
-    for (int i = 0; i < 81; ++i) v[i] = svd.v[i];
+    for (int i = 0; i < 81; ++i) v[i] = svd.vm.at(i);
 }
 
 void
 osfm_hostcheck_svd3 (const double* a, double* u, double* s, double* v)
 {
     osfm::fmath::SquareSvd<3, true> svd;
-    for (int i = 0; i < 9; ++i) svd.b[i] = a[i];
+    for (int i = 0; i < 9; ++i) svd.bm.at(i) = a[i];
     svd.run();
     for (int i = 0; i < 3; ++i) s[i] = svd.s[i];
-    for (int i = 0; i < 9; ++i) { u[i] = svd.u[i]; v[i] = svd.v[i]; }
+    for (int i = 0; i < 9; ++i) { u[i] = svd.um.at(i); v[i] = svd.vm.at(i); }
 }
 
+
+/* The same with the iteration stopped at a fixed point (what the device kernels do), and the
+ * 9 x 9 problem taken through the device's stages: bidiagonalise, hand over the bidiagonal
+ * (17 numbers) and V, iterate in a strided buffer, finish.  iterations receives the number of
+ * trips of the 9 x 9 loop. */
+void
+osfm_hostcheck_fundamental_staged (const double* p1, const double* p2, double* F, int* iterations)
+{
+    using namespace osfm::fmath;
+    double diag[9], super[8], vv[81];
+    {
+        SquareSvd<9, false> a;
+        design_matrix(p1, p2, a.bm);
+        a.bidiagonalize(kSvdEpsilon);
+        for (int i = 0; i < 9; ++i) diag[i] = a.B(i, i);
+        for (int i = 0; i < 8; ++i) super[i] = a.B(i, i + 1);
+        for (int i = 0; i < 81; ++i) vv[i] = a.vm.at(i);
+    }
+    double buffer[81 * 3];
+    SquareSvd<9, false, StridedMatrix> b;
+    b.bm.p = buffer + 1;
+    b.bm.stride = 3;
+    for (int i = 0; i < 81; ++i) b.bm.at(i) = 0.0;
+    for (int i = 0; i < 9; ++i) b.B(i, i) = diag[i];
+    for (int i = 0; i < 8; ++i) b.B(i, i + 1) = super[i];
+    for (int i = 0; i < 81; ++i) b.vm.at(i) = vv[i];
+    /* the stepping of ransac_gk_kernel: a trip's start, then its rotation steps one by one */
+    int it = 0;
+    bool done = false;
+    b.sweep_k = b.sweep_end = 0;
+    while (!done)
+    {
+        if (!b.sweep_pending())
+        {
+            ++it;
+            done = b.trip_begin(kSvdEpsilon);
+            if (!done && !b.sweep_pending())
+                done = !b.changed || it >= 81;
+        }
+        if (!done && b.sweep_pending())
+        {
+            b.sweep_rotate(kSvdEpsilon);
+            if (!b.sweep_pending())
+                done = !b.changed || it >= 81;
+        }
+    }
+    *iterations = it;
+    b.finish(kSvdEpsilon);
+    for (int r = 0; r < 9; ++r) F[r] = b.V(r, 8);
+    enforce_rank2<true>(F);
+}
 
 /* RANSAC as ransac_kernels.cuh runs it (fit per sample, count, first best), on the host.
  * matches: x1 y1 x2 y2 per match; samples: 8 ascending indices per iteration.  Returns the

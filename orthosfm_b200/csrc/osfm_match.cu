@@ -135,6 +135,7 @@ struct osfm_matcher {
     DevBuf<int32_t> rs_samples;
     DevBuf<double> rs_F;
     DevBuf<int> rs_cnt;
+    DevBuf<double> rs_stage1;            // bidiagonal + V of every fit of one chunk
     DevBuf<int2> rs_out;
     int32_t* rs_stage[2] = {nullptr, nullptr};   // pinned staging for samples drawn here, double-buffered
     size_t rs_stage_ints = 0;
@@ -760,7 +761,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release(); m->d_list.release();
     m->tr_ints.release(); m->tr_table.release(); m->tr_meta.release(); m->tr_meta32.release();
     m->rs_xy.release(); m->rs_pos.release(); m->rs_samples.release(); m->rs_F.release(); m->rs_cnt.release();
-    m->rs_out.release();
+    m->rs_out.release(); m->rs_stage1.release();
     for (int k = 0; k < 2; ++k) {
         if (m->rs_stage[k]) cudaFreeHost(m->rs_stage[k]);
         if (m->rs_stage_free[k]) cudaEventDestroy(m->rs_stage_free[k]);
@@ -1618,7 +1619,19 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     // leg (about 20 ns per rand() call, 8000+ calls per pair), so the device time hides
     // behind them.
     int const per_pair = 8 * max_iterations;
-    int const chunk = std::max(1, std::min(npairs, (1 << 19) / std::max(per_pair, 1)));      // about 2 MB of samples
+    // about 8 MB of samples per chunk: enough fits (260 k at 1000 iterations) for the work
+    // fetching of the iteration kernel to even out its lanes
+    int const chunk = std::max(1, std::min(npairs, (1 << 21) / std::max(per_pair, 1)));
+    int64_t const chunk_fits = static_cast<int64_t>(chunk) * max_iterations;
+    CU_TRY(m, m->rs_stage1.reserve(static_cast<size_t>(std::max<int64_t>(chunk_fits, 1)) * (kBidiagDoubles + 81) + 1));
+    double* const d_bd = m->rs_stage1.p;
+    double* const d_vv = d_bd + std::max<int64_t>(chunk_fits, 1) * kBidiagDoubles;
+    unsigned long long* const d_next = reinterpret_cast<unsigned long long*>(d_vv + std::max<int64_t>(chunk_fits, 1) * 81);
+    size_t const gk_smem = sizeof(double) * 81 * kGkThreads;
+    CU_TRY(m, cudaFuncSetAttribute(ransac_gk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gk_smem)));
+    int gk_per_sm = 1;
+    CU_TRY(m, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gk_per_sm, ransac_gk_kernel, kGkThreads, gk_smem));
+    int64_t const gk_ctas = static_cast<int64_t>(std::max(gk_per_sm, 1)) * m->num_sms;
     if (!samples && per_pair > 0) {
         size_t const want = static_cast<size_t>(chunk) * per_pair;
         if (want > m->rs_stage_ints) {
@@ -1646,11 +1659,15 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
             }
             CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p + f0 * 8, src, sizeof(int32_t) * 8 * fits, cudaMemcpyHostToDevice, st));
             if (!samples) CU_TRY(m, cudaEventRecord(m->rs_stage_free[c & 1], st));
-            ransac_fit_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(
-                d_off + p0, np, max_iterations, m->rs_samples.p + f0 * 8, m->rs_xy.p, m->rs_F.p + f0 * 9, d_bad + 1);
+            ransac_bidiag_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(
+                d_off + p0, np, max_iterations, m->rs_samples.p + f0 * 8, m->rs_xy.p, d_bd, d_vv, d_bad + 1);
+            CU_TRY(m, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st));
+            ransac_gk_kernel<<<static_cast<unsigned>(std::min<int64_t>(gk_ctas, (fits + kGkThreads - 1) / kGkThreads)),
+                               kGkThreads, gk_smem, st>>>(fits, d_bd, d_vv, d_next, m->rs_F.p + f0 * 9);
+            ransac_rank2_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(fits, m->rs_F.p + f0 * 9);
             ransac_count_kernel<<<static_cast<unsigned>((fits * 32 + 255) / 256), 256, 0, st>>>(
                 d_off + p0, np, max_iterations, m->rs_xy.p, m->rs_F.p + f0 * 9, thr2, m->rs_cnt.p + f0);
-            launches += 2;
+            launches += 4;
         }
         ransac_select_kernel<<<np, 256, 0, st>>>(d_off + p0, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p + f0 * 9,
                                                  m->rs_cnt.p + f0, thr2, d_inl, d_count + p0, d_bestF + 9 * p0);

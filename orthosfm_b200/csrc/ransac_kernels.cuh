@@ -10,7 +10,8 @@
 // pair, so the draws are made on the host in that order (osfm_ransac_draw_samples) and come
 // here as a table of eight ascending match indices per (pair, iteration).  Everything else is
 // independent across (pair, iteration) and runs here:
-//   fit     one thread per (pair, iteration): 9 x 9 and 3 x 3 SVD (ransac_math.cuh)
+//   fit     9 x 9 and 3 x 3 SVD per (pair, iteration) in three stages (ransac_math.cuh):
+//           bidiagonalise / iterate with work fetching / rank 2
 //   count   one warp per (pair, iteration): Sampson distance of every match of the pair
 //   select  one CTA per pair: the first iteration with the most inliers wins (the reference
 //           replaces its best only on a strictly larger count); its inliers, in match order,
@@ -52,15 +53,28 @@ __global__ void __launch_bounds__(256) ransac_gather_kernel(const int32_t* __res
     xy[e] = make_float4(a.x, a.y, b.x, b.y);
 }
 
-// One thread per (pair, iteration).  samples: 8 ascending match indices (relative to the pair's
-// list) per thread.  F: 9 doubles per thread.
-__global__ void __launch_bounds__(128) ransac_fit_kernel(const int64_t* __restrict__ list_offset, int npairs,
-                                                         int iterations, const int32_t* __restrict__ samples,
-                                                         const float4* __restrict__ xy, double* __restrict__ F,
-                                                         int* __restrict__ bad)
+// ---- the fit, in three stages --------------------------------------------------------------------
+// Two thirds of the design matrices never meet the reference's convergence test (their zero
+// singular value is not deflated) and would run all 81 trips of its loop; nearly all of those
+// sit on a fixed point after about 30 trips, where the loop may stop without changing anything
+// (ransac_math.cuh).  One thread per fit from start to end cannot use that: a warp waits for its
+// slowest lane (measured: 7.7 of 32 lanes active on average).  So the loop gets a kernel of its
+// own in which a lane that has finished a fit fetches the next one.
+
+constexpr int kBidiagDoubles = 17;     // diagonal (9) and superdiagonal (8)
+constexpr int kGkThreads = 128;
+
+// Stage 1, one thread per (pair, iteration): design matrix and Householder bidiagonalisation.
+// samples: 8 ascending match indices (relative to the pair's list) per thread.  bd / vv:
+// element-major ([element][fit]) so that neighbouring threads write neighbouring words.
+__global__ void __launch_bounds__(128) ransac_bidiag_kernel(const int64_t* __restrict__ list_offset, int npairs,
+                                                            int iterations, const int32_t* __restrict__ samples,
+                                                            const float4* __restrict__ xy, double* __restrict__ bd,
+                                                            double* __restrict__ vv, int* __restrict__ bad)
 {
+    int64_t const total = static_cast<int64_t>(npairs) * iterations;
     int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<int64_t>(npairs) * iterations) return;
+    if (t >= total) return;
     int const pair = static_cast<int>(t / iterations);
     int64_t const begin = list_offset[pair];
     int64_t const count = list_offset[pair + 1] - begin;
@@ -75,9 +89,83 @@ __global__ void __launch_bounds__(128) ransac_fit_kernel(const int64_t* __restri
         p1[2 * k] = m.x; p1[2 * k + 1] = m.y;
         p2[2 * k] = m.z; p2[2 * k + 1] = m.w;
     }
-    if (!ok) { atomicAdd(bad, 1); return; }
+    if (!ok) {
+        atomicAdd(bad, 1);
+        for (int k = 0; k < 16; ++k) { p1[k] = 0.0; p2[k] = 0.0; }
+    }
+    fmath::SquareSvd<9, false> svd;
+    fmath::design_matrix(p1, p2, svd.bm);
+    svd.bidiagonalize(fmath::kSvdEpsilon);
+    for (int i = 0; i < 9; ++i) bd[i * total + t] = svd.B(i, i);
+    for (int i = 0; i < 8; ++i) bd[(9 + i) * total + t] = svd.B(i, i + 1);
+    for (int i = 0; i < 81; ++i) vv[i * total + t] = svd.vm.at(i);
+}
+
+// Stage 2, persistent.  Measured on the first version of this kernel (one trip of the loop per
+// pass): a trip's sweep has 1 to 8 rotation steps, most matrices are down to one step while
+// some lane of the warp still has eight, and 4.6 of 32 lanes were active in the rotations.  So
+// the unit of work per pass is ONE rotation step: a lane at a trip boundary runs the trip's
+// start (zero tests, block choice, shift), every lane with steps pending runs one, and a lane
+// whose fit has ended takes the next fit from `next`.  B lives in shared memory (81 doubles
+// per lane, strided by the CTA size: conflict-free whatever element a lane touches), V in local
+// memory.  fvec: the singular vector of the smallest singular value, 9 doubles per fit.
+__global__ void __launch_bounds__(kGkThreads) ransac_gk_kernel(int64_t total, const double* __restrict__ bd,
+                                                               const double* __restrict__ vv,
+                                                               unsigned long long* __restrict__ next,
+                                                               double* __restrict__ fvec)
+{
+    extern __shared__ double gk_shared[];
+    fmath::SquareSvd<9, false, fmath::StridedMatrix> svd;
+    svd.bm.p = gk_shared + threadIdx.x;
+    svd.bm.stride = kGkThreads;
+    svd.sweep_k = svd.sweep_end = 0;
+    int64_t t = -1;
+    int trips = 0;
+    bool active = false, exhausted = false;
+    while (true) {
+        if (!active && !exhausted) {
+            t = static_cast<int64_t>(atomicAdd(next, 1ull));
+            if (t < total) {
+                for (int i = 0; i < 81; ++i) svd.bm.at(i) = 0.0;
+                for (int i = 0; i < 9; ++i) svd.B(i, i) = bd[i * total + t];
+                for (int i = 0; i < 8; ++i) svd.B(i, i + 1) = bd[(9 + i) * total + t];
+                for (int i = 0; i < 81; ++i) svd.vm.at(i) = vv[i * total + t];
+                trips = 0;
+                svd.sweep_k = svd.sweep_end = 0;
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        bool done = false;
+        if (active && !svd.sweep_pending()) {           // at a trip boundary
+            ++trips;
+            done = svd.trip_begin(fmath::kSvdEpsilon);
+            if (!done && !svd.sweep_pending())           // a trip without rotation steps
+                done = !svd.changed || trips >= 81;
+        }
+        if (active && !done && svd.sweep_pending()) {
+            svd.sweep_rotate(fmath::kSvdEpsilon);
+            if (!svd.sweep_pending())                    // the trip is complete
+                done = !svd.changed || trips >= 81;
+        }
+        if (done) {
+            svd.finish(fmath::kSvdEpsilon);
+            for (int r = 0; r < 9; ++r) fvec[t * 9 + r] = svd.V(r, 8);
+            active = false;
+        }
+    }
+}
+
+// Stage 3, one thread per fit: rank 2 enforced (3 x 3 SVD with U), in place.
+__global__ void __launch_bounds__(128) ransac_rank2_kernel(int64_t total, double* __restrict__ F)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
     double f[9];
-    fmath::fundamental_from_eight(p1, p2, f);
+    for (int k = 0; k < 9; ++k) f[k] = F[t * 9 + k];
+    fmath::enforce_rank2<true>(f);
     for (int k = 0; k < 9; ++k) F[t * 9 + k] = f[k];
 }
 

@@ -21,7 +21,8 @@
 // and ones of its padded update matrices are skipped: adding an exact zero changes no partial
 // sum (only the sign of an exact zero result can differ, which no later step observes).
 // The left singular vectors are only accumulated when asked for (the 8-point solve ignores
-// them and they feed back into nothing).
+// them and they feed back into nothing).  The iteration may stop at a fixed point (see
+// SquareSvd::changed): the reference would only repeat the same no-op until its limit.
 #pragma once
 
 #include <cmath>
@@ -45,7 +46,32 @@ OSFM_HD double add(double a, double b) { return a + b; }
 OSFM_HD double sub(double a, double b) { return a - b; }
 #endif
 
+// true when the two doubles differ in any bit
+#if defined(__CUDA_ARCH__)
+OSFM_HD bool differs(double a, double b) { return __double_as_longlong(a) != __double_as_longlong(b); }
+#else
+OSFM_HD bool differs(double a, double b) {
+    long long x, y;
+    __builtin_memcpy(&x, &a, 8);
+    __builtin_memcpy(&y, &b, 8);
+    return x != y;
+}
+#endif
+
 constexpr double kSvdEpsilon = 1e-12;     // MATH_SVD_DEFAULT_ZERO_THRESHOLD, matrix_svd.h:30
+
+// Where an N x N matrix lives: in the thread's own memory, or strided through a buffer shared
+// by the threads of a CTA (element i of this thread at p[i * stride]).
+template <int N>
+struct LocalMatrix {
+    double a[N * N];
+    OSFM_HD double& at(int i) { return a[i]; }
+};
+struct StridedMatrix {
+    double* p;
+    int stride;
+    OSFM_HD double& at(int i) { return p[i * stride]; }
+};
 
 // MATH_EPSILON_EQ(x, 0, eps), math/defines.h:96
 OSFM_HD bool near_zero(double x, double eps) { return (sub(0.0, eps) <= x) && (x <= add(0.0, eps)); }
@@ -71,56 +97,79 @@ OSFM_HD void householder_vector(const double* in, int len, double* v, double* be
     for (int i = 0; i < len; ++i) v[i] = v[i] / first;
 }
 
-// Givens coefficients (matrix_qr.h:50-73)
+// Givens coefficients (matrix_qr.h:50-73).  Written with selects instead of the reference's
+// three-way branch: inside a warp every lane works on its own matrix, and a data-dependent
+// branch in a loop body splits the warp for the rest of the loop (measured: 4.6 of 32 lanes
+// active in the rotations).  Only the selected quotient is computed, so nothing is evaluated
+// that the reference does not evaluate.
 OSFM_HD void givens(double alpha, double beta, double* c, double* s, double eps)
 {
-    if (near_zero(beta, eps)) { *c = 1.0; *s = 0.0; return; }
-    if (fabs(beta) > fabs(alpha)) {
-        double const tao = (-alpha) / beta;
-        *s = 1.0 / sqrt(add(1.0, mul(tao, tao)));
-        *c = mul(*s, tao);
-    } else {
-        double const tao = (-beta) / alpha;
-        *c = 1.0 / sqrt(add(1.0, mul(tao, tao)));
-        *s = mul(*c, tao);
-    }
+    bool const tiny = near_zero(beta, eps);
+    bool const steep = fabs(beta) > fabs(alpha);
+    double const num = steep ? -alpha : -beta;
+    double const den = tiny ? 1.0 : (steep ? beta : alpha);
+    double const tao = num / den;
+    double const r = 1.0 / sqrt(add(1.0, mul(tao, tao)));
+    double const rt = mul(r, tao);
+    *c = tiny ? 1.0 : (steep ? rt : r);
+    *s = tiny ? 0.0 : (steep ? r : rt);
 }
+
+// index of the lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+OSFM_HD int lowest_bit(unsigned x) { return __ffs(static_cast<int>(x)) - 1; }
+#else
+OSFM_HD int lowest_bit(unsigned x) { return __builtin_ctz(x); }
+#endif
 
 // SVD of a square N x N matrix, A = U diag(s) V^T, singular values sorted descending as the
 // reference sorts them.  All matrices row-major.  U is produced only when WANT_U.
-template <int N, bool WANT_U>
+template <int N, bool WANT_U, class BStore = LocalMatrix<N>>
 struct SquareSvd {
-    double b[N * N];     // A on entry; the bidiagonal / diagonal form afterwards
-    double v[N * N];
-    double u[WANT_U ? N * N : 1];
+    BStore bm;           // A on entry; the bidiagonal / diagonal form afterwards
+    LocalMatrix<N> vm;
+    LocalMatrix<WANT_U ? N : 1> um;
     double s[N];
+    // STOP_AT_FIXED_POINT: an iteration that changes no bit of B, V, U would be repeated
+    // unchanged until the reference's iteration limit (the loop's state is those matrices
+    // alone), so the loop may end there.  That is the usual end for the 8-point design matrix:
+    // its zero singular value is never deflated, two thirds of all samples would run all 81
+    // iterations, and 93 % of those sit on a fixed point after about 30.
+    bool changed;
 
-    OSFM_HD double& B(int r, int c) { return b[r * N + c]; }
-    OSFM_HD double& V(int r, int c) { return v[r * N + c]; }
-    OSFM_HD double& U(int r, int c) { return u[r * N + c]; }
+    OSFM_HD double& B(int r, int c) { return bm.at(r * N + c); }
+    OSFM_HD double& V(int r, int c) { return vm.at(r * N + c); }
+    OSFM_HD double& U(int r, int c) { return um.at(r * N + c); }
+
+    OSFM_HD void put(double& slot, double value) {
+        changed = changed | differs(slot, value);
+        slot = value;
+    }
 
     // rotate columns i, k of an N x N matrix (matrix_qr.h:75-88)
-    OSFM_HD static void rot_columns(double* m, int i, int k, double c, double s_) {
+    template <class M>
+    OSFM_HD void rot_columns(M& m, int i, int k, double c, double s_) {
         for (int j = 0; j < N; ++j) {
-            double const t1 = m[j * N + i], t2 = m[j * N + k];
-            m[j * N + i] = sub(mul(c, t1), mul(s_, t2));
-            m[j * N + k] = add(mul(s_, t1), mul(c, t2));
+            double const t1 = m.at(j * N + i), t2 = m.at(j * N + k);
+            put(m.at(j * N + i), sub(mul(c, t1), mul(s_, t2)));
+            put(m.at(j * N + k), add(mul(s_, t1), mul(c, t2)));
         }
     }
     // rotate rows i, k (matrix_qr.h:90-103)
-    OSFM_HD static void rot_rows(double* m, int i, int k, double c, double s_) {
+    template <class M>
+    OSFM_HD void rot_rows(M& m, int i, int k, double c, double s_) {
         for (int j = 0; j < N; ++j) {
-            double const t1 = m[i * N + j], t2 = m[k * N + j];
-            m[i * N + j] = sub(mul(c, t1), mul(s_, t2));
-            m[k * N + j] = add(mul(s_, t1), mul(c, t2));
+            double const t1 = m.at(i * N + j), t2 = m.at(k * N + j);
+            put(m.at(i * N + j), sub(mul(c, t1), mul(s_, t2)));
+            put(m.at(k * N + j), add(mul(s_, t1), mul(c, t2)));
         }
     }
 
     OSFM_HD void bidiagonalize(double eps) {
-        for (int i = 0; i < N * N; ++i) v[i] = 0.0;
+        for (int i = 0; i < N * N; ++i) vm.at(i) = 0.0;
         for (int i = 0; i < N; ++i) V(i, i) = 1.0;
         if (WANT_U) {
-            for (int i = 0; i < N * N; ++i) u[i] = 0.0;
+            for (int i = 0; i < N * N; ++i) um.at(i) = 0.0;
             for (int i = 0; i < N; ++i) U(i, i) = 1.0;
         }
         double h[N * N], hv[N], line[N], in[N];
@@ -184,9 +233,18 @@ struct SquareSvd {
         }
     }
 
-    // one implicit-shift QR sweep over rows/columns p .. N-q-1 (matrix_svd.h:440-509)
-    OSFM_HD void gk_step(int p, int q, double eps) {
+    // One implicit-shift QR sweep over rows/columns p .. N-q-1 (matrix_svd.h:440-509), cut into
+    // its start (the shift) and its rotation steps so that a caller can interleave the steps
+    // of many matrices (ransac_kernels.cuh).  State between the pieces: sweep_k, sweep_end,
+    // sweep_alpha, sweep_beta.
+    int sweep_k, sweep_end;
+    double sweep_alpha, sweep_beta;
+
+    OSFM_HD bool sweep_pending() const { return sweep_k < sweep_end; }
+
+    OSFM_HD void sweep_begin(int p, int q) {
         int const len = N - q - p;
+        sweep_k = sweep_end = 0;
         if (len < 2) return;      // nothing to rotate
         // the trailing 2 x 2 block of B22 * B22^T
         double c4[4];
@@ -194,7 +252,11 @@ struct SquareSvd {
             for (int d = 0; d < 2; ++d) {
                 int const ra = p + len - 2 + a, rd = p + len - 2 + d;
                 double cur = 0.0;
-                for (int kk = 0; kk < len; ++kk) cur = add(cur, mul(B(ra, p + kk), B(rd, p + kk)));
+                for (int kk = 0; kk < N; ++kk) {        // kk < len terms; fixed trip count, no branch
+                    int const col = p + (kk < len ? kk : 0);
+                    double const term = mul(B(ra, col), B(rd, col));
+                    cur = kk < len ? add(cur, term) : cur;
+                }
                 c4[a * 2 + d] = cur;
             }
         double const tr = add(c4[0], c4[3]);
@@ -203,87 +265,126 @@ struct SquareSvd {
         double const eig_1 = sub(tr / 2.0, x), eig_2 = add(tr / 2.0, x);
         double const diff1 = fabs(sub(c4[3], eig_1)), diff2 = fabs(sub(c4[3], eig_2));
         double const mu = diff1 < diff2 ? eig_1 : eig_2;
+        sweep_alpha = sub(mul(B(p, p), B(p, p)), mu);
+        sweep_beta = mul(B(p, p), B(p, p + 1));
+        sweep_k = p;
+        sweep_end = N - q - 1;
+    }
 
-        double alpha = sub(mul(B(p, p), B(p, p)), mu);
-        double beta = mul(B(p, p), B(p, p + 1));
-        for (int k = p; k < N - q - 1; ++k) {
-            double c, s_;
-            givens(alpha, beta, &c, &s_, eps);
-            rot_columns(b, k, k + 1, c, s_);
-            rot_columns(v, k, k + 1, c, s_);
-            alpha = B(k, k);
-            beta = B(k + 1, k);
-            givens(alpha, beta, &c, &s_, eps);
-            rot_rows(b, k, k + 1, c, s_);
-            if (WANT_U) rot_columns(u, k, k + 1, c, s_);
-            if (k < N - q - 2) {
-                alpha = B(k, k + 1);
-                beta = B(k, k + 2);
-            }
+    OSFM_HD void sweep_rotate(double eps) {
+        int const k = sweep_k;
+        double c, s_;
+        givens(sweep_alpha, sweep_beta, &c, &s_, eps);
+        rot_columns(bm, k, k + 1, c, s_);
+        rot_columns(vm, k, k + 1, c, s_);
+        sweep_alpha = B(k, k);
+        sweep_beta = B(k + 1, k);
+        givens(sweep_alpha, sweep_beta, &c, &s_, eps);
+        rot_rows(bm, k, k + 1, c, s_);
+        if (WANT_U) rot_columns(um, k, k + 1, c, s_);
+        if (k < sweep_end - 1) {
+            sweep_alpha = B(k, k + 1);
+            sweep_beta = B(k, k + 2);
         }
+        sweep_k = k + 1;
     }
 
     // a zero on the diagonal: rotate the rest of its row away (matrix_svd.h:511-535)
     OSFM_HD void clear_super_entry(int row, double eps) {
         for (int i = row + 1; i < N; ++i) {
-            if (near_zero(B(row, i), eps)) { B(row, i) = 0.0; break; }
+            if (near_zero(B(row, i), eps)) { put(B(row, i), 0.0); break; }
             double norm = add(mul(B(row, i), B(row, i)), mul(B(i, i), B(i, i)));
             norm = mul(sqrt(norm), B(i, i) < 0.0 ? -1.0 : 1.0);
             double const c = B(i, i) / norm;
             double const s_ = B(row, i) / norm;
-            rot_rows(b, row, i, c, s_);
-            if (WANT_U) rot_columns(u, row, i, c, s_);
+            rot_rows(bm, row, i, c, s_);
+            if (WANT_U) rot_columns(um, row, i, c, s_);
         }
     }
 
-    // b holds A on entry.
-    OSFM_HD void run(double eps = kSvdEpsilon) {
-        bidiagonalize(eps);
-        for (int iteration = 0; iteration < N * N; ++iteration) {
-            for (int i = 0; i < N * N; ++i)
-                if (near_zero(b[i], eps)) b[i] = 0.0;
-            for (int i = 0; i < N - 1; ++i)
-                if (fabs(B(i, i + 1)) <= mul(eps, fabs(add(B(i, i), B(i + 1, i + 1))))) B(i, i + 1) = 0.0;
-
-            // q: the largest trailing block that is diagonal and cut off from the rest
-            int q = 0;
-            for (int k = 0; k < N; ++k) {
-                int const o = N - k - 1;       // block B(o.., o..)
-                bool diagonal = true;
-                for (int y = 0; y <= k && diagonal; ++y)
-                    for (int x2 = 0; x2 <= k; ++x2)
-                        if (x2 != y && !near_zero(B(o + y, o + x2), eps)) { diagonal = false; break; }
-                if (!diagonal) continue;
-                if (k < N - 1) {
-                    int const j = o - 1;
-                    bool enclosed = true;
-                    for (int i = o; i < N; ++i)
-                        if (!near_zero(B(j, i), eps) || !near_zero(B(i, j), eps)) { enclosed = false; break; }
-                    if (enclosed) q = k + 1;
-                } else {
-                    q = k + 1;
-                }
-            }
-            // z: the block above it whose superdiagonal has no zero
-            int z = 0;
-            for (int k = 0; k < N - q; ++k) {
-                int const o = N - q - k - 1;
-                bool nonzero = true;
-                for (int i = 0; i < k; ++i)
-                    if (near_zero(B(o + i, o + i + 1), eps)) { nonzero = false; break; }
-                if (nonzero) z = k + 1;
-            }
-            int const p = N - q - z;
-            if (q == N) break;
-
-            bool diagonal_non_zero = true;
-            int nz = p;
-            for (; nz < N - q - 1; ++nz)
-                if (near_zero(B(nz, nz), eps)) { diagonal_non_zero = false; B(nz, nz) = 0.0; break; }
-            if (diagonal_non_zero) gk_step(p, q, eps);
-            else clear_super_entry(nz, eps);
+    // The start of one trip of the reference's iteration loop (matrix_svd.h:565-622): the zero
+    // tests, the choice of the active block and either the start of a sweep (its rotation
+    // steps are then pending) or the clearing of a row.  Returns true when the loop ends here
+    // (converged: q == N).
+    OSFM_HD bool trip_begin(double eps) {
+        changed = false;
+        sweep_k = sweep_end = 0;
+        // The tests below are the reference's, evaluated without data-dependent branches (see
+        // givens): first the two zeroing passes, then one pass that records which entries are
+        // "zero" (|x| <= eps) as bit masks per row (zr) and per column (zc), from which the
+        // block searches read.  Nothing is modified between the mask pass and the searches.
+        for (int i = 0; i < N * N; ++i) {
+            double const x = bm.at(i);
+            put(bm.at(i), near_zero(x, eps) ? 0.0 : x);
         }
+        for (int i = 0; i < N - 1; ++i) {
+            double const x = B(i, i + 1);
+            bool const drop = fabs(x) <= mul(eps, fabs(add(B(i, i), B(i + 1, i + 1))));
+            put(B(i, i + 1), drop ? 0.0 : x);
+        }
+        unsigned zr[N], zc[N];
+        for (int i = 0; i < N; ++i) zr[i] = zc[i] = 0u;
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) {
+                unsigned const zero = near_zero(B(r, c), eps) ? 1u : 0u;
+                zr[r] |= zero << c;
+                zc[c] |= zero << r;
+            }
+        unsigned const all = (1u << N) - 1u;
+        // q: the largest trailing block that is diagonal (every off-diagonal entry zero) and cut
+        // off from the rest (the row and the column next to it are zero along the block); every
+        // block size is examined, as in the reference, and the last hit counts
+        int q = 0;
+        bool diagonal = true;
+        for (int k = 0; k < N; ++k) {
+            int const o = N - k - 1;                        // block B(o.., o..)
+            unsigned const beyond = all & ~((2u << o) - 1u);  // bits o+1 .. N-1
+            diagonal = diagonal & (((~zr[o]) & beyond) == 0u) & (((~zc[o]) & beyond) == 0u);
+            unsigned const along = all & ~((1u << o) - 1u);   // bits o .. N-1
+            int const j = o > 0 ? o - 1 : 0;
+            bool const enclosed = (((~zr[j]) & along) == 0u) & (((~zc[j]) & along) == 0u);
+            bool const hit = diagonal & ((k == N - 1) | enclosed);
+            q = hit ? k + 1 : q;
+        }
+        // z: the block above it whose superdiagonal has no zero (again the last hit counts)
+        unsigned super_zero = 0u;                             // bit r: B(r, r+1) is zero
+        unsigned diag_zero = 0u;                              // bit r: B(r, r) is zero
+        for (int r = 0; r < N; ++r) {
+            diag_zero |= ((zr[r] >> r) & 1u) << r;
+            if (r < N - 1) super_zero |= ((zr[r] >> (r + 1)) & 1u) << r;
+        }
+        int z = 0;
+        for (int k = 0; k < N; ++k) {
+            bool const valid = k < N - q;
+            int const o = valid ? N - q - k - 1 : 0;          // superdiagonal rows o .. o+k-1
+            unsigned const rows = ((1u << (o + k)) - 1u) & ~((1u << o) - 1u);
+            bool const hit = valid & ((super_zero & rows) == 0u);
+            z = hit ? k + 1 : z;
+        }
+        int const p = N - q - z;
+        if (q == N) return true;
 
+        // the first zero on the diagonal in rows p .. N-q-2
+        unsigned const candidates = diag_zero & ((1u << (N - q - 1)) - 1u) & ~((1u << p) - 1u);
+        bool const diagonal_non_zero = candidates == 0u;
+        int const nz = diagonal_non_zero ? N - q - 1 : lowest_bit(candidates);
+        if (!diagonal_non_zero) put(B(nz, nz), 0.0);
+        if (diagonal_non_zero) sweep_begin(p, q);
+        else clear_super_entry(nz, eps);
+        return false;
+    }
+
+    // One whole trip.  Returns true when the loop ends: converged or, with
+    // STOP_AT_FIXED_POINT, nothing changed.
+    template <bool STOP_AT_FIXED_POINT>
+    OSFM_HD bool gk_iteration(double eps) {
+        if (trip_begin(eps)) return true;
+        while (sweep_pending()) sweep_rotate(eps);
+        return STOP_AT_FIXED_POINT && !changed;
+    }
+
+    // After the loop: singular values, sign fix, selection sort (matrix_svd.h:624-641, 747-759).
+    OSFM_HD void finish(double eps) {
         for (int i = 0; i < N; ++i) s[i] = B(i, i);
         for (int i = 0; i < N; ++i) {
             if (s[i] < eps) {
@@ -291,7 +392,7 @@ struct SquareSvd {
                 if (WANT_U) for (int j = 0; j < N; ++j) U(j, i) = -U(j, i);
             }
         }
-        // selection sort, largest first; stops at the first all-zero tail (matrix_svd.h:747-759)
+        // largest first; stops at the first all-zero tail
         for (int i = 0; i < N; ++i) {
             double largest = 0.0;
             int pos = -1;
@@ -306,31 +407,39 @@ struct SquareSvd {
             }
         }
     }
+
+    // bm holds A on entry.
+    template <bool STOP_AT_FIXED_POINT = false>
+    OSFM_HD void run(double eps = kSvdEpsilon) {
+        bidiagonalize(eps);
+        for (int iteration = 0; iteration < N * N; ++iteration)
+            if (gk_iteration<STOP_AT_FIXED_POINT>(eps)) break;
+        finish(eps);
+    }
 };
 
-// The fundamental matrix of eight correspondences: the singular vector of the smallest singular
-// value of the 8 x 9 design matrix (padded to 9 x 9), then rank 2 enforced.
-// p1 / p2: x0 y0 x1 y1 ... (view 1 / view 2).  F row-major.
-OSFM_HD void fundamental_from_eight(const double* p1, const double* p2, double* F)
+// The 8 x 9 design matrix of eight correspondences, padded to 9 x 9 (fundamental.cc:84-98,
+// matrix_svd.h:729-733).  p1 / p2: x0 y0 x1 y1 ... (view 1 / view 2).
+template <class M>
+OSFM_HD void design_matrix(const double* p1, const double* p2, M& m)
 {
-    {
-        SquareSvd<9, false> svd;
-        for (int i = 0; i < 8; ++i) {
-            double const x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
-            double* r = svd.b + 9 * i;
-            r[0] = mul(x2, x1); r[1] = mul(x2, y1); r[2] = x2;
-            r[3] = mul(y2, x1); r[4] = mul(y2, y1); r[5] = y2;
-            r[6] = x1;          r[7] = y1;          r[8] = 1.0;
-        }
-        for (int j = 0; j < 9; ++j) svd.b[72 + j] = 0.0;
-        svd.run();
-        for (int r = 0; r < 9; ++r) F[r] = svd.V(r, 8);
+    for (int i = 0; i < 8; ++i) {
+        double const x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
+        m.at(9 * i + 0) = mul(x2, x1); m.at(9 * i + 1) = mul(x2, y1); m.at(9 * i + 2) = x2;
+        m.at(9 * i + 3) = mul(y2, x1); m.at(9 * i + 4) = mul(y2, y1); m.at(9 * i + 5) = y2;
+        m.at(9 * i + 6) = x1;          m.at(9 * i + 7) = y1;          m.at(9 * i + 8) = 1.0;
     }
+    for (int j = 0; j < 9; ++j) m.at(72 + j) = 0.0;
+}
+
+// enforce_fundamental_constraints (fundamental.cc:113-126): F = U * diag(s0, s1, 0) * V^T, each
+// product a left-to-right inner product over three terms (math/matrix.h:459-471).
+template <bool STOP_AT_FIXED_POINT>
+OSFM_HD void enforce_rank2(double* F)
+{
     SquareSvd<3, true> svd;
-    for (int i = 0; i < 9; ++i) svd.b[i] = F[i];
-    svd.run();
-    // U * diag(s0, s1, 0) * V^T, each product a left-to-right inner product over three terms
-    // (math/matrix.h:459-471)
+    for (int i = 0; i < 9; ++i) svd.bm.at(i) = F[i];
+    svd.template run<STOP_AT_FIXED_POINT>();
     double S[9] = {svd.s[0], 0.0, 0.0, 0.0, svd.s[1], 0.0, 0.0, 0.0, 0.0};
     double us[9];
     for (int i = 0; i < 3; ++i)
@@ -345,6 +454,20 @@ OSFM_HD void fundamental_from_eight(const double* p1, const double* p2, double* 
             for (int k = 0; k < 3; ++k) cur = add(cur, mul(us[i * 3 + k], svd.V(j, k)));
             F[i * 3 + j] = cur;
         }
+}
+
+// The fundamental matrix of eight correspondences: the singular vector of the smallest singular
+// value of the design matrix, then rank 2 enforced.  F row-major.
+template <bool STOP_AT_FIXED_POINT = false>
+OSFM_HD void fundamental_from_eight(const double* p1, const double* p2, double* F)
+{
+    {
+        SquareSvd<9, false> svd;
+        design_matrix(p1, p2, svd.bm);
+        svd.template run<STOP_AT_FIXED_POINT>();
+        for (int r = 0; r < 9; ++r) F[r] = svd.V(r, 8);
+    }
+    enforce_rank2<STOP_AT_FIXED_POINT>(F);
 }
 
 // fundamental.cc:225-247

@@ -223,7 +223,8 @@ def test_fundamental_and_sampson_equal_reference():
     (fundamental.cc:78-126, 225-247): same doubles, degenerate samples included."""
     ref, hc = _hostcheck()
     rng = np.random.default_rng(1)
-    for t in range(500):
+    stopped_early = 0
+    for t in range(1500):
         m = synth.two_view_scene(100 + t, 8, outlier_fraction=0.0 if t % 2 else 0.4).astype(np.float64)
         if t % 9 == 0:
             m[5] = m[2]                               # a repeated correspondence
@@ -234,9 +235,13 @@ def test_fundamental_and_sampson_equal_reference():
         F1 = ref.fundamental(m[:, :2], m[:, 2:])
         F2 = hc.fundamental(m[:, :2], m[:, 2:])
         assert np.array_equal(F1, F2, equal_nan=True), t
+        F3, trips = hc.fundamental_staged(m[:, :2], m[:, 2:])          # the device's route, fixed-point stop
+        assert np.array_equal(F1, F3, equal_nan=True), t
+        stopped_early += trips < 81
         q = rng.uniform(-0.5, 0.5, 4)
         d1, d2 = ref.sampson(F1, q), hc.sampson(F2, q)
         assert d1 == d2 or (np.isnan(d1) and np.isnan(d2)), t
+    assert stopped_early > 1200       # the stop matters: without it two thirds of the samples run 81 trips
 
 
 @pytest.mark.parametrize("n,outliers", [(8, 0.0), (9, 0.5), (40, 0.3), (400, 0.3), (1500, 0.6)])
