@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) ransac_gather_kernel(const int32_t* __res
 
 constexpr int kBidiagDoubles = 17;     // diagonal (9) and superdiagonal (8)
 constexpr int kGkThreads = 128;
+constexpr int kGkBeginBatch = 24;      // lanes that must wait at a trip boundary before the trips start
 
 // Stage 1, one thread per (pair, iteration): design matrix and Householder bidiagonalisation.
 // samples: 8 ascending match indices (relative to the pair's list) per thread.  bd / vv:
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(128) ransac_bidiag_kernel(const int64_t* __res
 __global__ void __launch_bounds__(kGkThreads) ransac_gk_kernel(int64_t total, const double* __restrict__ bd,
                                                                const double* __restrict__ vv,
                                                                unsigned long long* __restrict__ next,
-                                                               double* __restrict__ fvec)
+                                                               double* __restrict__ fvec, int begin_batch)
 {
     extern __shared__ double gk_shared[];
     fmath::SquareSvd<9, false, fmath::StridedMatrix> svd;
@@ -138,8 +139,15 @@ __global__ void __launch_bounds__(kGkThreads) ransac_gk_kernel(int64_t total, co
             }
         }
         if (!__any_sync(0xffffffffu, active)) break;
+        // A trip's start costs three rotation steps' worth of instructions and only the lanes at
+        // a trip boundary take part (measured: 6 of 32 when it ran in every pass).  So it runs
+        // only when enough lanes wait at a boundary, or when no lane has a rotation left.
+        bool const boundary = active && !svd.sweep_pending();
+        int const waiting = __popc(__ballot_sync(0xffffffffu, boundary));
+        bool const rotating = __any_sync(0xffffffffu, active && svd.sweep_pending());
+        bool const start_trips = waiting >= begin_batch || !rotating;
         bool done = false;
-        if (active && !svd.sweep_pending()) {           // at a trip boundary
+        if (boundary && start_trips) {
             ++trips;
             done = svd.trip_begin(fmath::kSvdEpsilon);
             if (!done && !svd.sweep_pending())           // a trip without rotation steps

@@ -146,22 +146,32 @@ struct SquareSvd {
         slot = value;
     }
 
-    // rotate columns i, k of an N x N matrix (matrix_qr.h:75-88)
+    // rotate columns i, k of an N x N matrix (matrix_qr.h:75-88).  All loads first: the compiler
+    // cannot tell that the stores of one row do not alias the loads of the next, and would
+    // otherwise wait for each row's stores before loading the next row.
     template <class M>
     OSFM_HD void rot_columns(M& m, int i, int k, double c, double s_) {
+        double t1[N], t2[N];
+        for (int j = 0; j < N; ++j) { t1[j] = m.at(j * N + i); t2[j] = m.at(j * N + k); }
         for (int j = 0; j < N; ++j) {
-            double const t1 = m.at(j * N + i), t2 = m.at(j * N + k);
-            put(m.at(j * N + i), sub(mul(c, t1), mul(s_, t2)));
-            put(m.at(j * N + k), add(mul(s_, t1), mul(c, t2)));
+            double const a = sub(mul(c, t1[j]), mul(s_, t2[j]));
+            double const b2 = add(mul(s_, t1[j]), mul(c, t2[j]));
+            changed = changed | differs(t1[j], a) | differs(t2[j], b2);
+            m.at(j * N + i) = a;
+            m.at(j * N + k) = b2;
         }
     }
     // rotate rows i, k (matrix_qr.h:90-103)
     template <class M>
     OSFM_HD void rot_rows(M& m, int i, int k, double c, double s_) {
+        double t1[N], t2[N];
+        for (int j = 0; j < N; ++j) { t1[j] = m.at(i * N + j); t2[j] = m.at(k * N + j); }
         for (int j = 0; j < N; ++j) {
-            double const t1 = m.at(i * N + j), t2 = m.at(k * N + j);
-            put(m.at(i * N + j), sub(mul(c, t1), mul(s_, t2)));
-            put(m.at(k * N + j), add(mul(s_, t1), mul(c, t2)));
+            double const a = sub(mul(c, t1[j]), mul(s_, t2[j]));
+            double const b2 = add(mul(s_, t1[j]), mul(c, t2[j]));
+            changed = changed | differs(t1[j], a) | differs(t2[j], b2);
+            m.at(i * N + j) = a;
+            m.at(k * N + j) = b2;
         }
     }
 
@@ -310,26 +320,26 @@ struct SquareSvd {
         changed = false;
         sweep_k = sweep_end = 0;
         // The tests below are the reference's, evaluated without data-dependent branches (see
-        // givens): first the two zeroing passes, then one pass that records which entries are
-        // "zero" (|x| <= eps) as bit masks per row (zr) and per column (zc), from which the
-        // block searches read.  Nothing is modified between the mask pass and the searches.
-        for (int i = 0; i < N * N; ++i) {
-            double const x = bm.at(i);
-            put(bm.at(i), near_zero(x, eps) ? 0.0 : x);
-        }
-        for (int i = 0; i < N - 1; ++i) {
-            double const x = B(i, i + 1);
-            bool const drop = fabs(x) <= mul(eps, fabs(add(B(i, i), B(i + 1, i + 1))));
-            put(B(i, i + 1), drop ? 0.0 : x);
-        }
+        // givens): the two zeroing passes, which also record which entries are "zero"
+        // (|x| <= eps) as bit masks per row (zr) and per column (zc); the block searches read
+        // the masks.  Nothing is modified between the passes and the searches.
         unsigned zr[N], zc[N];
         for (int i = 0; i < N; ++i) zr[i] = zc[i] = 0u;
         for (int r = 0; r < N; ++r)
             for (int c = 0; c < N; ++c) {
-                unsigned const zero = near_zero(B(r, c), eps) ? 1u : 0u;
-                zr[r] |= zero << c;
-                zc[c] |= zero << r;
+                double const x = B(r, c);
+                bool const zero = near_zero(x, eps);          // a zeroed entry stays "zero"
+                put(B(r, c), zero ? 0.0 : x);
+                zr[r] |= (zero ? 1u : 0u) << c;
+                zc[c] |= (zero ? 1u : 0u) << r;
             }
+        for (int i = 0; i < N - 1; ++i) {
+            double const x = B(i, i + 1);
+            bool const drop = fabs(x) <= mul(eps, fabs(add(B(i, i), B(i + 1, i + 1))));
+            put(B(i, i + 1), drop ? 0.0 : x);
+            zr[i] |= (drop ? 1u : 0u) << (i + 1);
+            zc[i + 1] |= (drop ? 1u : 0u) << i;
+        }
         unsigned const all = (1u << N) - 1u;
         // q: the largest trailing block that is diagonal (every off-diagonal entry zero) and cut
         // off from the rest (the row and the column next to it are zero along the block); every
