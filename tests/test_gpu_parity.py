@@ -793,6 +793,32 @@ def test_ransac_fundamental_equals_reference(counts, iters):
             assert not F[p].any()
 
 
+def test_ransac_fundamental_with_non_finite_positions_ends_and_equals_reference():
+    """A NaN, an infinite and a huge position: the iteration kernel must end (its loops are
+    bounded whatever the data) and the result is still the reference's."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = oracle.Reference()
+    feats, pos, pairs, off, ij, npairs = _ransac_case([60, 40, 90], 7)
+    pos = pos.copy()
+    base = np.concatenate([[0], np.cumsum(feats)])
+    pos[base[0] + ij[3, 0]] = np.nan
+    pos[base[3] + ij[off[1] + 5, 1], 0] = np.inf
+    pos[base[4] + ij[off[2] + 7, 0]] = 3e30
+    oracle.srand(2)
+    want = []
+    for p in range(npairs):
+        l = ij[off[p]:off[p + 1]]
+        xy = np.concatenate([pos[base[pairs[p, 0]] + l[:, 0]], pos[base[pairs[p, 1]] + l[:, 1]]], 1)
+        want.append(ref.ransac(xy, 150, 0.0015))
+    oracle.srand(2)
+    with matcher(synth.sift_views(1, 2, 64)) as m:
+        ooff, oij, F = m.ransac_fundamental(feats, pos, pairs, off, ij, max_iterations=150)
+    for p in range(npairs):
+        assert np.array_equal(oij[ooff[p]:ooff[p + 1]], ij[off[p]:off[p + 1]][want[p][0]]), p
+
+
 def test_ransac_fundamental_argument_errors():
     feats, pos, pairs, off, ij, npairs = _ransac_case([20, 7], 5)
     with matcher(synth.sift_views(1, 2, 64)) as m:

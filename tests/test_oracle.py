@@ -300,3 +300,25 @@ def test_sample_draws_leave_the_rand_sequence_where_the_reference_would():
             if v not in seen:
                 seen.append(v)
         assert sorted(seen) == smp[0, 0].tolist()
+
+
+def test_fundamental_on_non_finite_and_extreme_input_equals_reference():
+    """NaN, infinity, 1e150 and 1e-160 scales: the loop must end and the doubles (NaNs
+    included) must be the reference's, on the plain and on the staged / early-stop route."""
+    ref, hc = _hostcheck()
+    rng = np.random.default_rng(0)
+    for t in range(200):
+        m = synth.two_view_scene(t, 8, 0.0).astype(np.float64)
+        kind = t % 4
+        if kind == 0:
+            m[rng.integers(8), rng.integers(4)] = np.nan
+        elif kind == 1:
+            m[rng.integers(8), rng.integers(4)] = np.inf
+        elif kind == 2:
+            m *= 1e150
+        else:
+            m *= 1e-160
+        F1 = ref.fundamental(m[:, :2], m[:, 2:])
+        F2 = hc.fundamental(m[:, :2], m[:, 2:])
+        F3, _ = hc.fundamental_staged(m[:, :2], m[:, 2:])
+        assert np.array_equal(F1, F2, equal_nan=True) and np.array_equal(F1, F3, equal_nan=True), (t, kind)
