@@ -79,13 +79,13 @@ osfm_hostcheck_fundamental_staged (const double* p1, const double* p2, double* F
             ++it;
             done = b.trip_begin(kSvdEpsilon);
             if (!done && !b.sweep_pending())
-                done = !b.changed || it >= 81;
+                done = !b.changed() || it >= 81;
         }
         if (!done && b.sweep_pending())
         {
             b.sweep_rotate(kSvdEpsilon);
             if (!b.sweep_pending())
-                done = !b.changed || it >= 81;
+                done = !b.changed() || it >= 81;
         }
     }
     *iterations = it;

@@ -1627,12 +1627,14 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     double* const d_bd = m->rs_stage1.p;
     double* const d_vv = d_bd + std::max<int64_t>(chunk_fits, 1) * kBidiagDoubles;
     unsigned long long* const d_next = reinterpret_cast<unsigned long long*>(d_vv + std::max<int64_t>(chunk_fits, 1) * 81);
-    size_t const gk_smem = sizeof(double) * 81 * kGkThreads;
+    const char* gk_thr_env = getenv("OSFM_GK_THREADS");       // tuning knob: 32, 64 or 128
+    int const gk_threads = gk_thr_env ? std::max(32, std::min(kGkThreads, atoi(gk_thr_env) / 32 * 32)) : kGkThreads;
+    size_t const gk_smem = sizeof(double) * 81 * gk_threads;
     CU_TRY(m, cudaFuncSetAttribute(ransac_gk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gk_smem)));
     const char* gk_env = getenv("OSFM_GK_BEGIN_BATCH");      // tuning knob (tools/ransac_probe.py)
     int const gk_batch = gk_env ? std::max(1, std::min(32, atoi(gk_env))) : kGkBeginBatch;
     int gk_per_sm = 1;
-    CU_TRY(m, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gk_per_sm, ransac_gk_kernel, kGkThreads, gk_smem));
+    CU_TRY(m, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gk_per_sm, ransac_gk_kernel, gk_threads, gk_smem));
     int64_t const gk_ctas = static_cast<int64_t>(std::max(gk_per_sm, 1)) * m->num_sms;
     if (!samples && per_pair > 0) {
         size_t const want = static_cast<size_t>(chunk) * per_pair;
@@ -1664,8 +1666,8 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
             ransac_bidiag_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(
                 d_off + p0, np, max_iterations, m->rs_samples.p + f0 * 8, m->rs_xy.p, d_bd, d_vv, d_bad + 1);
             CU_TRY(m, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st));
-            ransac_gk_kernel<<<static_cast<unsigned>(std::min<int64_t>(gk_ctas, (fits + kGkThreads - 1) / kGkThreads)),
-                               kGkThreads, gk_smem, st>>>(fits, d_bd, d_vv, d_next, m->rs_F.p + f0 * 9, gk_batch);
+            ransac_gk_kernel<<<static_cast<unsigned>(std::min<int64_t>(gk_ctas, (fits + gk_threads - 1) / gk_threads)),
+                               gk_threads, gk_smem, st>>>(fits, d_bd, d_vv, d_next, m->rs_F.p + f0 * 9, gk_batch);
             ransac_rank2_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(fits, m->rs_F.p + f0 * 9);
             ransac_count_kernel<<<static_cast<unsigned>((fits * 32 + 255) / 256), 256, 0, st>>>(
                 d_off + p0, np, max_iterations, m->rs_xy.p, m->rs_F.p + f0 * 9, thr2, m->rs_cnt.p + f0);

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kGkThreads) ransac_gk_kernel(int64_t total, co
     extern __shared__ double gk_shared[];
     fmath::SquareSvd<9, false, fmath::StridedMatrix> svd;
     svd.bm.p = gk_shared + threadIdx.x;
-    svd.bm.stride = kGkThreads;
+    svd.bm.stride = static_cast<int>(blockDim.x);
     svd.sweep_k = svd.sweep_end = 0;
     int64_t t = -1;
     int trips = 0;
@@ -151,12 +151,12 @@ __global__ void __launch_bounds__(kGkThreads) ransac_gk_kernel(int64_t total, co
             ++trips;
             done = svd.trip_begin(fmath::kSvdEpsilon);
             if (!done && !svd.sweep_pending())           // a trip without rotation steps
-                done = !svd.changed || trips >= 81;
+                done = !svd.changed() || trips >= 81;
         }
         if (active && !done && svd.sweep_pending()) {
             svd.sweep_rotate(fmath::kSvdEpsilon);
             if (!svd.sweep_pending())                    // the trip is complete
-                done = !svd.changed || trips >= 81;
+                done = !svd.changed() || trips >= 81;
         }
         if (done) {
             svd.finish(fmath::kSvdEpsilon);

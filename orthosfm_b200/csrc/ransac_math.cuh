@@ -46,15 +46,14 @@ OSFM_HD double add(double a, double b) { return a + b; }
 OSFM_HD double sub(double a, double b) { return a - b; }
 #endif
 
-// true when the two doubles differ in any bit
+// the bit pattern of a double
 #if defined(__CUDA_ARCH__)
-OSFM_HD bool differs(double a, double b) { return __double_as_longlong(a) != __double_as_longlong(b); }
+OSFM_HD unsigned long long bits_of(double a) { return static_cast<unsigned long long>(__double_as_longlong(a)); }
 #else
-OSFM_HD bool differs(double a, double b) {
-    long long x, y;
+OSFM_HD unsigned long long bits_of(double a) {
+    unsigned long long x;
     __builtin_memcpy(&x, &a, 8);
-    __builtin_memcpy(&y, &b, 8);
-    return x != y;
+    return x;
 }
 #endif
 
@@ -135,14 +134,16 @@ struct SquareSvd {
     // alone), so the loop may end there.  That is the usual end for the 8-point design matrix:
     // its zero singular value is never deflated, two thirds of all samples would run all 81
     // iterations, and 93 % of those sit on a fixed point after about 30.
-    bool changed;
+    unsigned long long delta;      // OR of (old bits ^ new bits) over the stores of the trip
+    OSFM_HD bool changed() const { return delta != 0ull; }
+    OSFM_HD void note(double before, double after) { delta |= bits_of(before) ^ bits_of(after); }
 
     OSFM_HD double& B(int r, int c) { return bm.at(r * N + c); }
     OSFM_HD double& V(int r, int c) { return vm.at(r * N + c); }
     OSFM_HD double& U(int r, int c) { return um.at(r * N + c); }
 
     OSFM_HD void put(double& slot, double value) {
-        changed = changed | differs(slot, value);
+        note(slot, value);
         slot = value;
     }
 
@@ -156,7 +157,8 @@ struct SquareSvd {
         for (int j = 0; j < N; ++j) {
             double const a = sub(mul(c, t1[j]), mul(s_, t2[j]));
             double const b2 = add(mul(s_, t1[j]), mul(c, t2[j]));
-            changed = changed | differs(t1[j], a) | differs(t2[j], b2);
+            note(t1[j], a);
+            note(t2[j], b2);
             m.at(j * N + i) = a;
             m.at(j * N + k) = b2;
         }
@@ -169,7 +171,8 @@ struct SquareSvd {
         for (int j = 0; j < N; ++j) {
             double const a = sub(mul(c, t1[j]), mul(s_, t2[j]));
             double const b2 = add(mul(s_, t1[j]), mul(c, t2[j]));
-            changed = changed | differs(t1[j], a) | differs(t2[j], b2);
+            note(t1[j], a);
+            note(t2[j], b2);
             m.at(i * N + j) = a;
             m.at(k * N + j) = b2;
         }
@@ -317,7 +320,7 @@ struct SquareSvd {
     // steps are then pending) or the clearing of a row.  Returns true when the loop ends here
     // (converged: q == N).
     OSFM_HD bool trip_begin(double eps) {
-        changed = false;
+        delta = 0ull;
         sweep_k = sweep_end = 0;
         // The tests below are the reference's, evaluated without data-dependent branches (see
         // givens): the two zeroing passes, which also record which entries are "zero"
@@ -390,7 +393,7 @@ struct SquareSvd {
     OSFM_HD bool gk_iteration(double eps) {
         if (trip_begin(eps)) return true;
         while (sweep_pending()) sweep_rotate(eps);
-        return STOP_AT_FIXED_POINT && !changed;
+        return STOP_AT_FIXED_POINT && !changed();
     }
 
     // After the loop: singular values, sign fix, selection sort (matrix_svd.h:624-641, 747-759).
