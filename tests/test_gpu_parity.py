@@ -890,6 +890,35 @@ def test_two_view_stage_with_sift_and_surf_equals_reference():
         assert (ij[:, 0] >= 900).any() and (ij[:, 0] < 900).any()      # SURF and SIFT matches among the inliers
 
 
+def test_whole_chain_descriptors_to_tracks_equals_reference():
+    """Descriptors and positions in, feature tracks out: osfm_match_two_view ->
+    osfm_tracks_compute against the reference's bundler::Matching::compute ->
+    bundler::Tracks::compute on the same std::rand() seed (what calculateTracksUsingMVE runs,
+    src/matching/matching_mve.cpp:405-452): the same tracks."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    nv, n = 6, 1000
+    descs, poss = synth.sfm_scene(21, nv, n, 800, visible=0.5)
+    empty = np.zeros((0, 64), np.float32)
+    ref = oracle.Reference()
+    rx = ref.exhaustive([(d.astype(np.float32) / 255.0, empty) for d in descs])
+    kw = dict(min_feature_matches=50, min_matching_inliers=30, ransac_max_iterations=200)
+    want_pairs = rx.bundler_compute(np.concatenate(poss), seed=3, **kw)
+    wp = np.array([(a, b) for a, b, _ in want_pairs], np.int32)
+    woff = np.concatenate([[0], np.cumsum([len(ij) for _, _, ij in want_pairs])]).astype(np.int64)
+    want_ids, want_nt = ref.tracks_compute([n] * nv, wp, woff, np.concatenate([ij for _, _, ij in want_pairs]))
+    pairs = [(a, b) for a in range(nv) for b in range(a)]
+    oracle.srand(3)
+    with matcher(descs) as m:
+        got = m.two_view_matching(pairs, np.concatenate(poss), TwoViewOptions(**kw))
+        acc = [(p, ij) for p, (st, _, ij) in zip(pairs, got) if st == TWO_VIEW_OK]
+        off = np.concatenate([[0], np.cumsum([len(ij) for _, ij in acc])]).astype(np.int64)
+        ids, nt, _ = m.tracks_compute([n] * nv, [p for p, _ in acc], off, np.concatenate([ij for _, ij in acc]))
+    assert nt == want_nt and nt > 300
+    assert np.array_equal(ids, oracle.canonical_track_ids(want_ids))
+
+
 def _unrelated(desc):
     rng = np.random.default_rng(99)
     return synth._normalise_clamp_quantise(np.abs(rng.standard_normal(desc.shape, dtype=np.float32)))
