@@ -1583,14 +1583,22 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
             return fail(m, OSFM_ERR_INVALID_ARGUMENT, "pair %d: at least 8 matches required", p);
     }
     int64_t const nmatches = list_offset[npairs];
-    int64_t const nfits = static_cast<int64_t>(npairs) * max_iterations;
+    int const per_pair = 8 * max_iterations;
+    // Pairs go through in chunks of about 8 MB of samples: enough fits (260 k at 1000
+    // iterations) for the work fetching of the iteration kernel to even out its lanes, and the
+    // per-fit scratch (samples, matrices, inlier counts) is sized for one chunk, not for the job
+    const char* chunk_env = getenv("OSFM_RANSAC_CHUNK_PAIRS");      // test knob: forces small chunks
+    int const chunk = chunk_env ? std::max(1, std::min(npairs, atoi(chunk_env)))
+                                : std::max(1, std::min(npairs, (1 << 21) / std::max(per_pair, 1)));
+    int64_t const chunk_fits = static_cast<int64_t>(chunk) * max_iterations;
+    int64_t const scratch_fits = std::max<int64_t>(chunk_fits, 1);
     CU_TRY(m, cudaSetDevice(m->device));
     CU_TRY(m, m->rs_xy.reserve(static_cast<size_t>(nmatches)));
     CU_TRY(m, m->rs_out.reserve(static_cast<size_t>(2 * nmatches)));              // input lists | inlier lists
     CU_TRY(m, m->rs_pos.reserve(static_cast<size_t>(std::max<int64_t>(base[num_views], 1))));
-    CU_TRY(m, m->rs_samples.reserve(static_cast<size_t>(std::max<int64_t>(nfits * 8, 1))));
-    CU_TRY(m, m->rs_F.reserve(static_cast<size_t>(std::max<int64_t>(nfits * 9, 1)) + 9 * static_cast<size_t>(npairs)));
-    CU_TRY(m, m->rs_cnt.reserve(static_cast<size_t>(std::max<int64_t>(nfits, 1)) + static_cast<size_t>(npairs) + 4));
+    CU_TRY(m, m->rs_samples.reserve(static_cast<size_t>(scratch_fits * 8)));
+    CU_TRY(m, m->rs_F.reserve(static_cast<size_t>(scratch_fits * 9) + 9 * static_cast<size_t>(npairs)));
+    CU_TRY(m, m->rs_cnt.reserve(static_cast<size_t>(scratch_fits) + static_cast<size_t>(npairs) + 4));
     CU_TRY(m, m->tr_meta.reserve(static_cast<size_t>(num_views) + 1 + static_cast<size_t>(npairs) + 1));
     CU_TRY(m, m->tr_meta32.reserve(static_cast<size_t>(std::max(num_views, 1)) + 2 * static_cast<size_t>(npairs)));
     int64_t* const d_base = m->tr_meta.p;
@@ -1599,8 +1607,8 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     int32_t* const d_pv = d_vn + std::max(num_views, 1);
     int2* const d_ij = m->rs_out.p;
     int2* const d_inl = d_ij + nmatches;
-    double* const d_bestF = m->rs_F.p + std::max<int64_t>(nfits * 9, 1);
-    int* const d_count = m->rs_cnt.p + std::max<int64_t>(nfits, 1);
+    double* const d_bestF = m->rs_F.p + scratch_fits * 9;
+    int* const d_count = m->rs_cnt.p + scratch_fits;
     int* const d_bad = d_count + npairs;
     cudaStream_t const st = m->stream;
     CU_TRY(m, cudaMemsetAsync(d_bad, 0, sizeof(int) * 2, st));
@@ -1614,15 +1622,8 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
     ransac_gather_kernel<<<static_cast<unsigned>((nmatches + 255) / 256), 256, 0, st>>>(
         d_pv, d_off, npairs, d_ij, nmatches, d_base, d_vn, m->rs_pos.p, m->rs_xy.p, d_bad + 0);
     double const thr2 = threshold * threshold;       // ransac_fundamental.cc:97
-    // Pairs go through in chunks.  When the samples are drawn here, the draws of one chunk (host,
-    // std::rand()) run while the device works on the chunk before: the draws are the longer
-    // leg (about 20 ns per rand() call, 8000+ calls per pair), so the device time hides
-    // behind them.
-    int const per_pair = 8 * max_iterations;
-    // about 8 MB of samples per chunk: enough fits (260 k at 1000 iterations) for the work
-    // fetching of the iteration kernel to even out its lanes
-    int const chunk = std::max(1, std::min(npairs, (1 << 21) / std::max(per_pair, 1)));
-    int64_t const chunk_fits = static_cast<int64_t>(chunk) * max_iterations;
+    // When the samples are drawn here, the draws of one chunk (host) run while the device works
+    // on the chunk before.
     CU_TRY(m, m->rs_stage1.reserve(static_cast<size_t>(std::max<int64_t>(chunk_fits, 1)) * (kBidiagDoubles + 81) + 1));
     double* const d_bd = m->rs_stage1.p;
     double* const d_vv = d_bd + std::max<int64_t>(chunk_fits, 1) * kBidiagDoubles;
@@ -1661,20 +1662,20 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
                 draw_samples_for_pairs(np, list_offset + p0, max_iterations, m->rs_stage[buf]);
                 src = m->rs_stage[buf];
             }
-            CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p + f0 * 8, src, sizeof(int32_t) * 8 * fits, cudaMemcpyHostToDevice, st));
+            CU_TRY(m, cudaMemcpyAsync(m->rs_samples.p, src, sizeof(int32_t) * 8 * fits, cudaMemcpyHostToDevice, st));
             if (!samples) CU_TRY(m, cudaEventRecord(m->rs_stage_free[c & 1], st));
             ransac_bidiag_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(
-                d_off + p0, np, max_iterations, m->rs_samples.p + f0 * 8, m->rs_xy.p, d_bd, d_vv, d_bad + 1);
+                d_off + p0, np, max_iterations, m->rs_samples.p, m->rs_xy.p, d_bd, d_vv, d_bad + 1);
             CU_TRY(m, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st));
             ransac_gk_kernel<<<static_cast<unsigned>(std::min<int64_t>(gk_ctas, (fits + gk_threads - 1) / gk_threads)),
-                               gk_threads, gk_smem, st>>>(fits, d_bd, d_vv, d_next, m->rs_F.p + f0 * 9, gk_batch);
-            ransac_rank2_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(fits, m->rs_F.p + f0 * 9);
+                               gk_threads, gk_smem, st>>>(fits, d_bd, d_vv, d_next, m->rs_F.p, gk_batch);
+            ransac_rank2_kernel<<<static_cast<unsigned>((fits + 127) / 128), 128, 0, st>>>(fits, m->rs_F.p);
             ransac_count_kernel<<<static_cast<unsigned>((fits * 32 + 255) / 256), 256, 0, st>>>(
-                d_off + p0, np, max_iterations, m->rs_xy.p, m->rs_F.p + f0 * 9, thr2, m->rs_cnt.p + f0);
+                d_off + p0, np, max_iterations, m->rs_xy.p, m->rs_F.p, thr2, m->rs_cnt.p);
             launches += 4;
         }
-        ransac_select_kernel<<<np, 256, 0, st>>>(d_off + p0, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p + f0 * 9,
-                                                 m->rs_cnt.p + f0, thr2, d_inl, d_count + p0, d_bestF + 9 * p0);
+        ransac_select_kernel<<<np, 256, 0, st>>>(d_off + p0, max_iterations, m->rs_xy.p, d_ij, m->rs_F.p,
+                                                 m->rs_cnt.p, thr2, d_inl, d_count + p0, d_bestF + 9 * p0);
         launches += 1;
     }
     CU_TRY(m, cudaGetLastError());

@@ -793,6 +793,37 @@ def test_ransac_fundamental_equals_reference(counts, iters):
             assert not F[p].any()
 
 
+@pytest.mark.parametrize("chunk_pairs,own_samples", [(1, False), (2, False), (4, True)])
+def test_ransac_fundamental_in_chunks_equals_reference(chunk_pairs, own_samples, monkeypatch):
+    """The call works through the pairs in chunks (draws of one chunk on the host while the
+    device runs the one before; per-fit scratch reused): forced to 1, 2 and 4 pairs per chunk
+    over 7 pairs, samples drawn inside or handed in."""
+    import oracle
+    from orthosfm_b200 import ransac_draw_samples
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = oracle.Reference()
+    feats, pos, pairs, off, ij, npairs = _ransac_case([30, 9, 120, 64, 8, 300, 45], 13)
+    base = np.concatenate([[0], np.cumsum(feats)])
+    iters = 120
+    oracle.srand(4)
+    want = []
+    for p in range(npairs):
+        l = ij[off[p]:off[p + 1]]
+        xy = np.concatenate([pos[base[pairs[p, 0]] + l[:, 0]], pos[base[pairs[p, 1]] + l[:, 1]]], 1)
+        want.append(ref.ransac(xy, iters, 0.0015))
+    monkeypatch.setenv("OSFM_RANSAC_CHUNK_PAIRS", str(chunk_pairs))
+    oracle.srand(4)
+    smp = ransac_draw_samples(off, iters) if own_samples else None
+    with matcher(synth.sift_views(1, 2, 64)) as m:
+        ooff, oij, F = m.ransac_fundamental(feats, pos, pairs, off, ij, samples=smp, max_iterations=iters)
+    for p in range(npairs):
+        inl, wF = want[p]
+        assert np.array_equal(oij[ooff[p]:ooff[p + 1]], ij[off[p]:off[p + 1]][inl]), p
+        if len(inl):
+            assert np.array_equal(F[p].ravel(), wF), p
+
+
 def test_ransac_fundamental_with_non_finite_positions_ends_and_equals_reference():
     """A NaN, an infinite and a huge position: the iteration kernel must end (its loops are
     bounded whatever the data) and the result is still the reference's."""
