@@ -355,6 +355,26 @@ def run_ours(args, config):
     total_cmp = npairs * n * n
     value = total_cmp / step_s
 
+    # ---- the int8 tensor pipe's own ceiling on this box: the same launch with the epilogue
+    # reduced to handing the accumulators back (debug scan mode 1: TMA + tcgen05.mma only) ----
+    mma_only_ms = None
+    if world == 1:
+        try:
+            m.debug_set_scan_mode(1)
+            ts = []
+            for _ in range(5):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                try:
+                    m.match_pairs_compact(my_pairs, out_ij)
+                except Exception:  # noqa: BLE001  -- results are meaningless in this mode
+                    pass
+                ts.append(m.stats()["last_scan_ms"])
+            mma_only_ms = min(ts[1:])
+        finally:
+            m.debug_set_scan_mode(0)
+        m.match_pairs_compact(my_pairs, out_ij)      # leave the handle with a real result
+
     # ---- e2e through the host API (HOST buffers in, HOST results out) ---------------------
     e2e = None
     cpu_base = None
@@ -434,7 +454,12 @@ def run_ours(args, config):
                      # the same launch as the int8 pipe sees it: both directions are executed
                      "executed_tops": 2.0 * achieved_tops,
                      "int8_dense_nominal_tops": 4500.0,
-                     "frac_of_int8_nominal": 2.0 * achieved_tops / 4500.0},
+                     "frac_of_int8_nominal": 2.0 * achieved_tops / 4500.0,
+                     # measured on this box in this run: the same launch without the epilogue's work
+                     "int8_mma_only_ms": mma_only_ms,
+                     "int8_mma_only_tops": (2.0 * my_cmp * OPS_PER_COMPARISON / (mma_only_ms * 1e-3) / 1e12
+                                            if mma_only_ms else None),
+                     "frac_of_int8_mma_only": (mma_only_ms / scan_avg_ms) if mma_only_ms else None},
         "cpu_baseline": cpu_base,
         "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "matches_per_step": total_matches,
