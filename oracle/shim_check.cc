@@ -7,7 +7,10 @@
  * binding over the C ABI, orthosfm_b200/csrc/gpu_exhaustive_matching.h) through the same
  * sfm::MatchingBase pointer, on the same bundler::ViewportList, the way
  * bundler::Matching does (src/mve/sfm/bundler_matching.cc:45-56, 139-162), and compares
- * every Matching::Result element for element.
+ * every Matching::Result element for element.  It then runs the reference's whole two-view
+ * stage, sfm::bundler::Matching (init + compute), against sfm::bundler::GpuMatching
+ * (orthosfm_b200/csrc/gpu_bundler_matching.h) on a scene with real two-view geometry and
+ * the same std::rand() seed, and compares the PairwiseMatching.
  *
  * The binary lands in oracle/_ref/ (git-ignored, travels to the GPU box);
  * tests/test_gpu_parity.py::test_reference_side_binding runs it.
@@ -23,10 +26,134 @@
 #include "sfm/exhaustive_matching.h"
 #include "sfm/matching_base.h"
 
+#include "sfm/bundler_matching.h"
+
+#include <omp.h>
+
 #include "gpu_exhaustive_matching.h"
+#include "gpu_bundler_matching.h"
 
 namespace
 {
+    /* A small multi-view scene: 3-D points with a SIFT descriptor each, seen by every view
+     * from its own pose (positions = projections, MVE's normalised coordinates), plus
+     * private features at random positions. */
+    void
+    fill_scene (sfm::bundler::ViewportList* viewports, int num_views, int n, int scene_points, unsigned seed)
+    {
+        std::mt19937 rng(seed);
+        std::normal_distribution<float> gauss(0.0f, 1.0f);
+        std::uniform_real_distribution<float> uni(-1.0f, 1.0f);
+        auto make = [&] (std::vector<float>& d)
+        {
+            float nrm = 0.0f;
+            for (float x : d) nrm += x * x;
+            nrm = std::sqrt(nrm);
+            for (float& x : d) x = std::min(x / nrm, 0.2f);
+            nrm = 0.0f;
+            for (float x : d) nrm += x * x;
+            nrm = std::sqrt(nrm);
+            for (float& x : d) x /= nrm;
+        };
+        std::vector<std::vector<float>> pool(scene_points, std::vector<float>(128));
+        std::vector<float> X(3 * scene_points);
+        for (int i = 0; i < scene_points; ++i)
+        {
+            for (float& x : pool[i]) x = std::fabs(gauss(rng));
+            make(pool[i]);
+            X[3 * i] = uni(rng); X[3 * i + 1] = uni(rng); X[3 * i + 2] = 5.0f + uni(rng);
+        }
+        viewports->resize(num_views);
+        for (int v = 0; v < num_views; ++v)
+        {
+            float const a = 0.2f * uni(rng), b = 0.2f * uni(rng), tx = 0.5f * uni(rng), ty = 0.5f * uni(rng);
+            sfm::FeatureSet& fs = (*viewports)[v].features;
+            fs.sift_descriptors.resize(n);
+            fs.positions.resize(n);
+            fs.colors.resize(n, math::Vec3uc(0, 0, 0));
+            for (int i = 0; i < n; ++i)
+            {
+                std::vector<float> d(128);
+                float px, py;
+                if (i < scene_points && (rng() % 2 == 0))
+                {
+                    d = pool[i];
+                    for (float& x : d) x = std::max(0.0f, x + 0.004f * gauss(rng));
+                    /* rotation about y by a, about x by b, then a shift */
+                    float const x0 = X[3 * i], y0 = X[3 * i + 1], z0 = X[3 * i + 2];
+                    float const x1 = std::cos(a) * x0 + std::sin(a) * z0, z1 = -std::sin(a) * x0 + std::cos(a) * z0;
+                    float const y2 = std::cos(b) * y0 - std::sin(b) * z1, z2 = std::sin(b) * y0 + std::cos(b) * z1;
+                    px = 1.2f * (x1 + tx) / z2 + 0.0002f * gauss(rng);
+                    py = 1.2f * (y2 + ty) / z2 + 0.0002f * gauss(rng);
+                }
+                else
+                {
+                    for (float& x : d) x = std::fabs(gauss(rng));
+                    px = 0.5f * uni(rng);
+                    py = 0.5f * uni(rng);
+                }
+                make(d);
+                sfm::Sift::Descriptor& out = fs.sift_descriptors[i];
+                out.x = out.y = out.scale = out.orientation = 0.0f;
+                for (int k = 0; k < 128; ++k) out.data[k] = d[k];
+                fs.positions[i] = math::Vec2f(px, py);
+            }
+        }
+    }
+
+    /* bundler::Matching (the reference, one thread, as shipped) against bundler::GpuMatching
+     * on the same viewports and the same std::rand() seed. */
+    int
+    check_bundler (void)
+    {
+        sfm::bundler::ViewportList scene_ref, scene_gpu;
+        fill_scene(&scene_ref, 6, 900, 700, 77u);
+        scene_gpu = scene_ref;
+        sfm::bundler::Matching::Options opts;
+        opts.min_feature_matches = 40;
+        opts.min_matching_inliers = 25;
+        opts.use_lowres_matching = true;
+        opts.num_lowres_features = 300;
+        opts.min_lowres_matches = 8;
+        opts.ransac_opts.max_iterations = 200;
+        opts.ransac_opts.threshold = 0.0015;
+        opts.ransac_opts.verbose_output = false;
+
+        sfm::bundler::PairwiseMatching want, got;
+        try
+        {
+            std::FILE* quiet = std::freopen("/dev/null", "w", stdout);      /* compute() prints progress */
+            (void)quiet;
+            omp_set_num_threads(1);
+            std::srand(5);
+            sfm::bundler::Matching ref(opts);
+            ref.init(&scene_ref);
+            ref.compute(&want);
+            std::srand(5);
+            sfm::bundler::GpuMatching gpu(opts);
+            gpu.init(&scene_gpu);
+            gpu.compute(&got);
+            std::freopen("/dev/tty", "w", stdout);
+        }
+        catch (std::exception const& e)
+        {
+            std::fprintf(stderr, "BUNDLER_CHECK ERROR %s\n", e.what());
+            return 1;
+        }
+        int bad = want.size() == got.size() ? 0 : 1;
+        long inliers = 0;
+        for (std::size_t p = 0; p < std::min(want.size(), got.size()); ++p)
+        {
+            inliers += (long)want[p].matches.size();
+            if (want[p].view_1_id != got[p].view_1_id || want[p].view_2_id != got[p].view_2_id
+                || want[p].matches != got[p].matches)
+                ++bad;
+        }
+        std::fprintf(stderr, "BUNDLER_CHECK %s pairs=%zu/%zu inliers=%ld mismatches=%d\n",
+            bad == 0 && !want.empty() ? "PASS" : "FAIL", got.size(), want.size(), inliers, bad);
+        return bad == 0 && !want.empty() ? 0 : 1;
+    }
+
     void
     fill_views (sfm::bundler::ViewportList* viewports, std::vector<int> const& n_sift,
         std::vector<int> const& n_surf, unsigned seed)
@@ -175,5 +302,7 @@ main (void)
 
     std::printf("SHIM_CHECK %s pairs=%d consistent=%ld mismatches=%d\n", bad == 0 ? "PASS" : "FAIL",
         pairs, consistent, bad);
-    return bad == 0 ? 0 : 1;
+    std::fflush(stdout);
+    int const bundler_bad = check_bundler();       /* reports on stderr */
+    return bad == 0 && bundler_bad == 0 ? 0 : 1;
 }

@@ -142,6 +142,17 @@ public:
         }
     }
 
+    /** The whole two-view stage for a list of pairs (osfm_match_two_view); used by
+     *  bundler::GpuMatching (gpu_bundler_matching.h). */
+    void two_view (osfm_two_view_options const* two, osfm_ransac_options const* ransac, float const* positions,
+        int32_t const* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset,
+        int32_t* status, int32_t* count) const
+    {
+        this->require_init();
+        this->check(osfm_match_two_view(this->handle, two, ransac, positions, pairs, npairs, match_ij,
+            capacity_ij, list_offset, status, count));
+    }
+
 private:
     void require_init (void) const
     {

@@ -971,3 +971,5 @@ def test_reference_side_binding():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SHIM_CHECK PASS" in r.stdout, r.stdout
+    # the batched drop-in for bundler::Matching (gpu_bundler_matching.h) against the reference's own
+    assert "BUNDLER_CHECK PASS" in r.stderr, r.stderr
