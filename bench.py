@@ -232,8 +232,18 @@ def downstream_rows(me, pairs, n, num_views, lists, loff):
         ids, ntracks, _ = me.tracks_compute(feats, pairs, loff, ij)
         out["tracks_ms"] = 1e3 * (time.perf_counter() - t0)
     out["tracks"] = int(ntracks)
+    # the whole two-view stage in one call: gates + full match + RANSAC + inlier threshold
+    from orthosfm_b200 import TwoViewOptions
+    for rep in range(2):
+        oracle.srand(1)
+        t0 = time.perf_counter()
+        res = me.two_view_matching(pairs, pos, TwoViewOptions(min_feature_matches=50, min_matching_inliers=30))
+        out["two_view_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["two_view_pairs_through_ransac"] = int(sum(1 for st, _, _ in res if st in (0, 4)))
     out["note"] = ("osfm_ransac_fundamental (std::rand draws on the host inside, overlapped with the device) and "
-                   "osfm_tracks_compute on this step's match lists; host buffers in and out")
+                   "osfm_tracks_compute on this step's match lists; two_view_ms: osfm_match_two_view on the resident "
+                   "descriptors (match + gates + RANSAC + inlier threshold; the positions are random, so the pairs "
+                   "end at the inlier threshold); host buffers in and out")
     if oracle.have_ref():
         ref = oracle.Reference()
         base = np.arange(num_views) * n
