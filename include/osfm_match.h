@@ -105,6 +105,25 @@ int osfm_match_set_view_q8(osfm_matcher* m, int view_id,
  * descriptors.  After commit the views are immutable. */
 int osfm_match_commit(osfm_matcher* m);
 
+/* Overlapped staging.  Same cycle as begin / set_view_q8 / commit, but the host-to-device
+ * copies run on their own stream and osfm_match_commit returns WITHOUT waiting for them:
+ * the buffers handed to osfm_match_set_view_q8 must stay valid and unchanged until the first
+ * call that returns results (osfm_match_pairs*, osfm_match_pair*, osfm_match_two_view*) or
+ * osfm_match_wait_staged has returned.  A pair list in the reference's order (view_1
+ * ascending, bundler_matching.cc:92-93) is then matched in up to three phases -- pairs
+ * within the first seventh of the views, within the first third, the rest -- each starting
+ * as soon as its views have arrived, so most of the copy time hides behind the matching of
+ * the earlier pairs.  Views must be staged in ascending order (otherwise commit waits, as
+ * the plain one does); quantised descriptors only.  Results are the same as with
+ * osfm_match_begin. */
+/* osfm_match_set_view_q8 for `count` consecutive views in one call (sift / surf: one pointer
+ * per view, or NULL for "no features of this type"). */
+int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count,
+    const uint8_t* const* sift, const int32_t* n_sift, const int8_t* const* surf, const int32_t* n_surf);
+int osfm_match_begin_overlapped(osfm_matcher* m, int num_views);
+/* Waits until everything staged has arrived and is ready. */
+int osfm_match_wait_staged(osfm_matcher* m);
+
 /* Device-resident variant for the multi-GPU path: adopts a descriptor pool that
  * already lives in this device's memory (e.g. the target of an NCCL broadcast).
  * sift_pool is sum(n_sift) x 128 bytes with view v at row sift_row_offset[v];

@@ -28,6 +28,7 @@ EXPORTS = [
     "osfm_io_save_prebundle", "osfm_io_load_prebundle", "osfm_io_prebundle_get", "osfm_io_prebundle_free",
     "osfm_io_save_tracks", "osfm_io_save_pairwise_tracks", "osfm_io_load_tracks", "osfm_io_track_table_get",
     "osfm_io_track_table_free",
+    "osfm_match_begin_overlapped", "osfm_match_wait_staged", "osfm_match_set_views_q8",
     "osfm_ransac_draw_samples", "osfm_ransac_fundamental", "osfm_match_two_view",
     "osfm_match_ransac_default_options",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
@@ -127,6 +128,9 @@ def load() -> C.CDLL:
     L.osfm_io_track_table_free.argtypes = [vp]
     L.osfm_io_track_table_free.restype = None
     f64p = C.POINTER(C.c_double)
+    L.osfm_match_begin_overlapped.argtypes = [vp, C.c_int]
+    L.osfm_match_wait_staged.argtypes = [vp]
+    L.osfm_match_set_views_q8.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i32p, C.POINTER(vp), i32p]
     L.osfm_match_ransac_default_options.argtypes = [C.POINTER(RansacOptions)]
     L.osfm_match_ransac_default_options.restype = None
     L.osfm_match_two_view.argtypes = [vp, C.POINTER(TwoViewOptions), C.POINTER(RansacOptions), f32p, i32p, C.c_int,

@@ -83,6 +83,7 @@ struct KindPool {
     std::vector<int64_t> stage_off; // arena row of each staged view (-1: not staged)
     int last_staged = -1;
     bool in_order = true;
+    int norm_views = 0;             // views [0, norm_views) have their norms (lazy commit)
     float lowe = 0.8f, dist = FLT_MAX;
 };
 
@@ -115,6 +116,14 @@ struct osfm_matcher {
     int num_views = 0;
     bool began = false, committed = false;
     KindPool kind[2];
+    // Overlapped staging (osfm_match_begin_overlapped): the host-to-device copies go to their own
+    // stream, one event per view; commit returns without waiting and the first batches of a
+    // pair list are matched while the later views are still on their way.
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> view_ev;
+    std::vector<char> view_ev_set;
+    bool overlap = false;      // this begin/commit cycle stages through copy_stream
+    bool lazy = false;         // committed, but norms (and maybe copies) of later views still pending
 
     DevBuf<ScanJob> d_jobs;
     DevBuf<int2> d_rowres;
@@ -233,36 +242,87 @@ int make_tmap(osfm_matcher* m, KindPool& k) { return encode_tmap(m, &k.tmap, k.p
 
 // Per-row squared norms + per-view maxima (the filter's wrap certificate).  Asynchronous on
 // the handle's stream; k.off / k.n are staged by the runtime before the calls return.
-int compute_norms(osfm_matcher* m, KindPool& k) {
+// Buffers and the per-view tables the norm kernels read.
+int norms_prepare(osfm_matcher* m, KindPool& k) {
     size_t const nv = k.n.size();
     CU_TRY(m, k.d_norm2.reserve(static_cast<size_t>(k.rows + kPadRows)));
     CU_TRY(m, k.d_viewmax.reserve(std::max<size_t>(nv, 1)));
     CU_TRY(m, cudaMemsetAsync(k.d_viewmax.p, 0, sizeof(int32_t) * std::max<size_t>(nv, 1), m->stream));
-    if (k.rows == 0 || nv == 0) return OSFM_OK;
+    k.norm_views = 0;
+    if (k.rows == 0 || nv == 0) { k.norm_views = static_cast<int>(nv); return OSFM_OK; }
     CU_TRY(m, k.d_view_off.reserve(nv));
     CU_TRY(m, k.d_view_n.reserve(nv));
     CU_TRY(m, cudaMemcpyAsync(k.d_view_off.p, k.off.data(), sizeof(int64_t) * nv, cudaMemcpyHostToDevice, m->stream));
     CU_TRY(m, cudaMemcpyAsync(k.d_view_n.p, k.n.data(), sizeof(int32_t) * nv, cudaMemcpyHostToDevice, m->stream));
-    int const grid = static_cast<int>((k.rows + 255) / 256);
-    if (k.is_signed) rownorm_kernel<true><<<grid, 256, 0, m->stream>>>(k.pool, k.rows, k.d_norm2.p);
-    else             rownorm_kernel<false><<<grid, 256, 0, m->stream>>>(k.pool, k.rows, k.d_norm2.p);
-    CU_TRY(m, cudaGetLastError());
-    int max_n = 0;
-    for (int32_t n : k.n) max_n = std::max(max_n, n);
-    dim3 const vgrid(static_cast<unsigned>(nv), static_cast<unsigned>(std::max(1, (max_n + kViewMaxChunk - 1) / kViewMaxChunk)));
-    viewmax_kernel<<<vgrid, 256, 0, m->stream>>>(k.d_norm2.p, k.d_view_off.p, k.d_view_n.p, k.d_viewmax.p);
-    CU_TRY(m, cudaGetLastError());
-    m->stats.kernel_launches += 2;
     if (!k.is_signed) {
         CU_TRY(m, k.d_danger.reserve(nv * kDangerCap));
         CU_TRY(m, k.d_danger_cnt.reserve(nv));
         CU_TRY(m, k.d_danger_floor.reserve(nv));
-        danger_kernel<<<static_cast<unsigned>(nv), kDangerCap, 0, m->stream>>>(
-            k.d_norm2.p, k.d_view_off.p, k.d_view_n.p, k.d_viewmax.p, k.d_danger.p, k.d_danger_cnt.p,
-            k.d_danger_floor.p);
+    }
+    return OSFM_OK;
+}
+
+// Norms, per-view maxima and danger lists of the views [v0, v1) (their rows are contiguous:
+// off[] ascends with the view id).
+int norms_run(osfm_matcher* m, KindPool& k, int v0, int v1) {
+    if (v1 <= v0 || k.rows == 0) return OSFM_OK;
+    int64_t const row0 = k.off[v0];
+    int64_t const row1 = k.off[v1 - 1] + k.n[v1 - 1];
+    int max_n = 0;
+    for (int v = v0; v < v1; ++v) max_n = std::max(max_n, k.n[v]);
+    if (row1 > row0) {
+        int const grid = static_cast<int>((row1 - row0 + 255) / 256);
+        uint8_t const* const rows = k.pool + static_cast<size_t>(row0) * kRowBytes;
+        if (k.is_signed) rownorm_kernel<true><<<grid, 256, 0, m->stream>>>(rows, row1 - row0, k.d_norm2.p + row0);
+        else             rownorm_kernel<false><<<grid, 256, 0, m->stream>>>(rows, row1 - row0, k.d_norm2.p + row0);
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
     }
+    dim3 const vgrid(static_cast<unsigned>(v1 - v0), static_cast<unsigned>(std::max(1, (max_n + kViewMaxChunk - 1) / kViewMaxChunk)));
+    viewmax_kernel<<<vgrid, 256, 0, m->stream>>>(k.d_norm2.p, k.d_view_off.p + v0, k.d_view_n.p + v0, k.d_viewmax.p + v0);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches++;
+    if (!k.is_signed) {
+        danger_kernel<<<static_cast<unsigned>(v1 - v0), kDangerCap, 0, m->stream>>>(
+            k.d_norm2.p, k.d_view_off.p + v0, k.d_view_n.p + v0, k.d_viewmax.p + v0,
+            k.d_danger.p + static_cast<size_t>(v0) * kDangerCap, k.d_danger_cnt.p + v0, k.d_danger_floor.p + v0);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches++;
+    }
+    return OSFM_OK;
+}
+
+int compute_norms(osfm_matcher* m, KindPool& k) {
+    OS_TRY(norms_prepare(m, k));
+    int const nv = static_cast<int>(k.n.size());
+    OS_TRY(norms_run(m, k, 0, nv));
+    k.norm_views = nv;
+    return OSFM_OK;
+}
+
+// Lazy commit: makes the views up to max_view usable on the main stream (their copies have
+// arrived, their norms exist).  Views were staged in ascending order, so the event of the
+// first staged view >= max_view covers every earlier one.
+int ensure_views(osfm_matcher* m, int max_view) {
+    if (!m->lazy) return OSFM_OK;
+    max_view = std::min(max_view, m->num_views - 1);
+    bool need = false;
+    for (int kd = 0; kd < 2; ++kd) need = need || m->kind[kd].norm_views <= max_view;
+    if (need) {
+        int ev = -1;
+        for (int v = max_view; v < m->num_views && ev < 0; ++v)
+            if (m->view_ev_set[v]) ev = v;
+        for (int v = max_view - 1; v >= 0 && ev < 0; --v)
+            if (m->view_ev_set[v]) ev = v;            // nothing staged at or after max_view
+        if (ev >= 0) CU_TRY(m, cudaStreamWaitEvent(m->stream, m->view_ev[ev], 0));
+        for (int kd = 0; kd < 2; ++kd) {
+            KindPool& k = m->kind[kd];
+            if (k.norm_views > max_view) continue;
+            OS_TRY(norms_run(m, k, k.norm_views, max_view + 1));
+            k.norm_views = max_view + 1;
+        }
+    }
+    if (m->kind[0].norm_views >= m->num_views && m->kind[1].norm_views >= m->num_views) m->lazy = false;
     return OSFM_OK;
 }
 
@@ -273,6 +333,7 @@ int arena_reserve(osfm_matcher* m, KindPool& k, int64_t rows) {
     uint8_t* fresh = nullptr;
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&fresh), static_cast<size_t>(cap) * kRowBytes));
     if (k.arena) {
+        if (m->copy_stream) CU_TRY(m, cudaStreamSynchronize(m->copy_stream));    // copies into the old arena
         if (k.arena_used > 0)
             CU_TRY(m, cudaMemcpyAsync(fresh, k.arena, static_cast<size_t>(k.arena_used) * kRowBytes,
                                       cudaMemcpyDeviceToDevice, m->stream));
@@ -566,6 +627,11 @@ enum OutputMode { kFiltered = 0, kTwoway = 1 };
 int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense_ints, OutputMode mode,
               int only_kind /* -1: both */) {
     int const np = static_cast<int>(plans.size());
+    if (m->lazy) {
+        int max_view = 0;
+        for (PairPlan const& p : plans) max_view = std::max(max_view, std::max(p.v1, p.v2));
+        OS_TRY(ensure_views(m, max_view));
+    }
     CU_TRY(m, m->d_dense.reserve(static_cast<size_t>(std::max<int64_t>(dense_ints, 1))));
     CU_TRY(m, m->d_counts.reserve(static_cast<size_t>(np)));
     CU_TRY(m, cudaMemsetAsync(m->d_counts.p, 0, sizeof(int32_t) * np, m->stream));
@@ -637,17 +703,28 @@ int read_counters(osfm_matcher* m) {
 }
 
 // Splits `plans` into batches bounded by scratch memory; calls fn(first, last, dense_ints).
+// phase_views > 0 (a lazy commit is pending): a batch also ends where the pairs start to need
+// views of a later "phase" (the first seventh of the views, the first third, all of them: the
+// matching of one phase then lasts about as long as the copies the next one waits for), so
+// that the early pairs of a list in the reference's order (view_1 ascending) are matched while
+// the later views are still being copied.
 template <typename Fn>
-int for_each_batch(std::vector<PairPlan>& plans, Fn fn) {
+int for_each_batch(std::vector<PairPlan>& plans, Fn fn, int phase_views = 0) {
+    auto phase_of = [phase_views](PairPlan const& p) {
+        int const v = std::max(p.v1, p.v2);
+        return phase_views <= 0 ? 0 : (v < (phase_views + 6) / 7 ? 0 : (v < (phase_views + 2) / 3 ? 1 : 2));
+    };
     size_t first = 0;
     while (first < plans.size()) {
         int64_t rows = 0, dense = 0;
         size_t last = first;
+        int const phase = phase_of(plans[first]);
         while (last < plans.size()) {
             PairPlan& p = plans[last];
             int64_t const r = std::max<int64_t>(p.n1[0] + p.n2[0], p.n1[1] + p.n2[1]);
             int64_t const d = static_cast<int64_t>(p.len12) + p.len21;
             if (last > first && (rows + r > kMaxBatchRows || dense + d > kMaxBatchDense)) break;
+            if (last > first && phase_of(p) > phase) break;
             p.out12 = dense;
             p.out21 = dense + p.len12;
             rows += r; dense += d;
@@ -721,6 +798,7 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     CU_TRY(m, cudaSetDevice(m->device));
     m->num_sms = prop.multiProcessorCount;
     CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CU_TRY(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 16 * sizeof(unsigned long long)));
     CU_TRY(m, cudaMemset(m->d_counters, 0, 16 * sizeof(unsigned long long)));
@@ -753,6 +831,7 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
 void osfm_match_destroy(osfm_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
     if (m->stream) cudaStreamSynchronize(m->stream);
     reset_kind(m->kind[0], true);
     reset_kind(m->kind[1], true);
@@ -778,16 +857,19 @@ void osfm_match_destroy(osfm_matcher* m) {
         cudaFreeHost(m->hang_host);
     }
     for (auto& ev : m->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : m->view_ev) if (ev) cudaEventDestroy(ev);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
 
-int osfm_match_begin(osfm_matcher* m, int num_views) {
+static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
     CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     for (int kd = 0; kd < 2; ++kd) {
         reset_kind(m->kind[kd], false);
@@ -798,8 +880,22 @@ int osfm_match_begin(osfm_matcher* m, int num_views) {
     m->num_views = num_views;
     m->began = true;
     m->committed = false;
+    m->overlap = overlap;
+    m->lazy = false;
+    if (overlap) {
+        while (m->view_ev.size() < static_cast<size_t>(num_views)) {
+            cudaEvent_t ev = nullptr;
+            CU_TRY(m, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            m->view_ev.push_back(ev);
+        }
+        m->view_ev_set.assign(static_cast<size_t>(num_views), 0);
+    }
     return OSFM_OK;
 }
+
+int osfm_match_begin(osfm_matcher* m, int num_views) { return begin_impl(m, num_views, false); }
+
+int osfm_match_begin_overlapped(osfm_matcher* m, int num_views) { return begin_impl(m, num_views, true); }
 
 // Stages one view of one kind at the end of the arena.  All copies are asynchronous on the
 // handle's stream; the source must stay valid until osfm_match_commit() returns.
@@ -812,7 +908,9 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
     if (!src) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null descriptor pointer with n = %d", n);
     OS_TRY(arena_reserve(m, k, n));
     uint8_t* const d = k.arena + static_cast<size_t>(k.arena_used) * kRowBytes;
+    cudaStream_t const cs = m->overlap ? m->copy_stream : m->stream;
     if (is_float) {
+        if (m->overlap) return fail(m, OSFM_ERR_STATE, "overlapped staging takes quantised descriptors (set_view_q8)");
         if (stride < k.dim) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "stride %d < descriptor length %d", stride, k.dim);
         size_t const count = static_cast<size_t>(n - 1) * stride + k.dim;
         if (count > m->d_ftmp.cap) CU_TRY(m, cudaStreamSynchronize(m->stream));  // still read by a kernel
@@ -825,11 +923,11 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
     } else if (k.dim == kRowBytes) {
-        CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, cs));
     } else {
         // 64-byte rows are zero-padded to the 128-byte pool pitch
-        CU_TRY(m, cudaMemsetAsync(d, 0, static_cast<size_t>(n) * kRowBytes, m->stream));
-        CU_TRY(m, cudaMemcpy2DAsync(d, kRowBytes, src, k.dim, k.dim, n, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, cudaMemsetAsync(d, 0, static_cast<size_t>(n) * kRowBytes, cs));
+        CU_TRY(m, cudaMemcpy2DAsync(d, kRowBytes, src, k.dim, k.dim, n, cudaMemcpyHostToDevice, cs));
     }
     k.stage_off[view] = k.arena_used;
     k.arena_used += n;
@@ -850,15 +948,38 @@ int osfm_match_set_view_f32(osfm_matcher* m, int view_id, const float* sift, int
     return OSFM_OK;
 }
 
+static int set_view_q8_locked(osfm_matcher* m, int view_id, const uint8_t* sift, int n_sift,
+                              const int8_t* surf, int n_surf) {
+    OS_TRY(check_view(m, view_id));
+    OS_TRY(stage_view(m, 0, view_id, sift, n_sift, 128, false));
+    OS_TRY(stage_view(m, 1, view_id, surf, n_surf, 64, false));
+    if (m->overlap) {
+        CU_TRY(m, cudaEventRecord(m->view_ev[view_id], m->copy_stream));
+        m->view_ev_set[view_id] = 1;
+    }
+    return OSFM_OK;
+}
+
 int osfm_match_set_view_q8(osfm_matcher* m, int view_id, const uint8_t* sift, int n_sift,
                            const int8_t* surf, int n_surf) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
-    OS_TRY(check_view(m, view_id));
     CU_TRY(m, cudaSetDevice(m->device));
-    OS_TRY(stage_view(m, 0, view_id, sift, n_sift, 128, false));
-    OS_TRY(stage_view(m, 1, view_id, surf, n_surf, 64, false));
+    return set_view_q8_locked(m, view_id, sift, n_sift, surf, n_surf);
+}
+
+int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const uint8_t* const* sift,
+                            const int32_t* n_sift, const int8_t* const* surf, const int32_t* n_surf) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_views outside begin/commit");
+    if (count < 0 || (count > 0 && ((sift && !n_sift) || (surf && !n_surf))))
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
+    CU_TRY(m, cudaSetDevice(m->device));
+    for (int i = 0; i < count; ++i)
+        OS_TRY(set_view_q8_locked(m, first_view + i, sift ? sift[i] : nullptr, sift ? n_sift[i] : 0,
+                                  surf ? surf[i] : nullptr, surf ? n_surf[i] : 0));
     return OSFM_OK;
 }
 
@@ -867,6 +988,10 @@ int osfm_match_commit(osfm_matcher* m) {
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "commit outside begin/commit");
     CU_TRY(m, cudaSetDevice(m->device));
+    // Overlapped staging stays lazy only if the arena already is the pool (views staged in
+    // ascending order); otherwise everything is waited for here, as in the plain commit.
+    bool const lazy = m->overlap && m->kind[0].in_order && m->kind[1].in_order;
+    if (m->overlap && !lazy) CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     for (int kd = 0; kd < 2; ++kd) {
         KindPool& k = m->kind[kd];
         int64_t const rows = k.arena_used;
@@ -899,10 +1024,29 @@ int osfm_match_commit(osfm_matcher* m) {
         CU_TRY(m, cudaMemsetAsync(k.pool + static_cast<size_t>(rows) * kRowBytes, 0,
                                   static_cast<size_t>(kPadRows) * kRowBytes, m->stream));
         OS_TRY(make_tmap(m, k));
-        OS_TRY(compute_norms(m, k));
+        if (lazy) OS_TRY(norms_prepare(m, k));      // the norms follow view by view (ensure_views)
+        else      OS_TRY(compute_norms(m, k));
     }
-    CU_TRY(m, cudaStreamSynchronize(m->stream));  // from here on the caller may free its buffers
+    m->lazy = lazy;
+    if (lazy) {
+        // nothing to wait for: the caller keeps its buffers until the first call that returns
+        // results (or osfm_match_wait_staged) has returned
+        OS_TRY(ensure_views(m, -1));                // clears `lazy` at once if there is nothing to do
+    } else {
+        CU_TRY(m, cudaStreamSynchronize(m->stream));  // from here on the caller may free its buffers
+    }
     m->committed = true;
+    return OSFM_OK;
+}
+
+int osfm_match_wait_staged(osfm_matcher* m) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    CU_TRY(m, cudaSetDevice(m->device));
+    if (m->committed) OS_TRY(ensure_views(m, m->num_views - 1));
+    CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
     return OSFM_OK;
 }
 
@@ -916,7 +1060,10 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
     CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->overlap = false;
+    m->lazy = false;
     const void* pools[2] = {sift_pool, surf_pool};
     const int64_t* offs[2] = {sift_row_offset, surf_row_offset};
     const int32_t* ns[2] = {n_sift, n_surf};
@@ -1018,7 +1165,7 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
             }
         host_base += dense;
         return OSFM_OK;
-    });
+    }, m->lazy ? m->num_views : 0);
     if (r != OSFM_OK) return r;
     if (offsets) offsets[2 * plans.size()] = host_base;
     CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));
@@ -1221,7 +1368,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
         m->stats.kernel_launches++;
         CU_TRY(m, cudaStreamSynchronize(m->stream));
         return OSFM_OK;
-    });
+    }, m->lazy ? m->num_views : 0);
     if (r != OSFM_OK) return r;
     list_offset[plans.size()] = list_base;
     CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));
@@ -1914,6 +2061,8 @@ static int debug_dump(osfm_matcher* m, int kind, int view_q, int view_c, int32_t
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
+    CU_TRY(m, cudaSetDevice(m->device));
+    OS_TRY(ensure_views(m, m->num_views - 1));
     if (kind != 0 && kind != 1) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "unknown kind %d", kind);
     OS_TRY(check_view(m, view_q));
     OS_TRY(check_view(m, view_c));
@@ -1945,6 +2094,8 @@ int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, in
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
+    CU_TRY(m, cudaSetDevice(m->device));
+    OS_TRY(ensure_views(m, m->num_views - 1));
     int64_t const words = static_cast<int64_t>(kScanThreads / 32) * kTraceEvents * 4;   // 20 warps
     if (!out || out_words < words) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "trace buffer too small (%lld words)", (long long)words);
     CU_TRY(m, cudaSetDevice(m->device));

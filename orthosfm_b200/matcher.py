@@ -105,6 +105,34 @@ class TwoViewOptions:
         self.match_num_previous_frames = match_num_previous_frames
 
 
+class PackedViews:
+    """Quantised descriptors of a list of viewports with the pointer tables the C ABI takes,
+    built once (ExhaustiveMatching.init accepts it in place of the viewports and then stages
+    every view with a single call)."""
+
+    def __init__(self, viewports: Sequence["Viewport"]):
+        self.sift, self.surf, self.sizes = [], [], []
+        for vp in viewports:
+            fs = vp.features if hasattr(vp, "features") else vp
+            s = None if fs.sift_descriptors is None else np.asarray(fs.sift_descriptors)
+            f = None if fs.surf_descriptors is None else np.asarray(fs.surf_descriptors)
+            if (s is not None and s.dtype != np.uint8) or (f is not None and f.dtype != np.int8):
+                raise ValueError("PackedViews takes quantised descriptors (uint8 SIFT, int8 SURF)")
+            s = None if s is None else np.ascontiguousarray(s).reshape(-1, 128)
+            f = None if f is None else np.ascontiguousarray(f).reshape(-1, 64)
+            self.sift.append(s)
+            self.surf.append(f)
+            self.sizes.append((0 if s is None else s.shape[0], 0 if f is None else f.shape[0]))
+        n = len(self.sizes)
+        self.p_sift = (C.c_void_p * n)(*[None if a is None or a.shape[0] == 0 else a.ctypes.data for a in self.sift])
+        self.p_surf = (C.c_void_p * n)(*[None if a is None or a.shape[0] == 0 else a.ctypes.data for a in self.surf])
+        self.n_sift = (C.c_int32 * n)(*[a for a, _ in self.sizes])
+        self.n_surf = (C.c_int32 * n)(*[b for _, b in self.sizes])
+
+    def __len__(self):
+        return len(self.sizes)
+
+
 class ExhaustiveMatching:
     """Drop-in for sfm::ExhaustiveMatching, computing on a B200.
 
@@ -136,6 +164,7 @@ class ExhaustiveMatching:
             raise MatcherError(rc, msg)
         self._sizes: List[tuple] = []
         self._keepalive = None
+        self._staged_sources = None
 
     # -- plumbing ---------------------------------------------------------------------
     def _check(self, rc: int) -> None:
@@ -160,10 +189,22 @@ class ExhaustiveMatching:
         self.close()
 
     # -- ExhaustiveMatching::init ----------------------------------------------------------
-    def init(self, viewports: Sequence[Viewport]) -> None:
+    def init(self, viewports: Sequence[Viewport], overlap_copies: bool = False) -> None:
+        """``overlap_copies``: stage through osfm_match_begin_overlapped -- commit does not wait
+        for the host-to-device copies, the first batched call matches the early pairs while the
+        later views arrive.  The descriptor arrays (quantised, uint8 / int8) are kept alive
+        here until the next init / wait_staged / close."""
         if viewports is None:
             raise ValueError("Viewports must not be null")  # bundler_matching.cc:47-48
-        self._check(self._L.osfm_match_begin(self._h, len(viewports)))
+        begin = self._L.osfm_match_begin_overlapped if overlap_copies else self._L.osfm_match_begin
+        self._check(begin(self._h, len(viewports)))
+        if isinstance(viewports, PackedViews):
+            pk = viewports
+            self._check(self._L.osfm_match_set_views_q8(self._h, 0, len(pk), pk.p_sift, pk.n_sift, pk.p_surf, pk.n_surf))
+            self._sizes = list(pk.sizes)
+            self._check(self._L.osfm_match_commit(self._h))
+            self._staged_sources = pk if overlap_copies else None
+            return
         self._sizes = []
         keep = []   # staging copies are asynchronous: sources must outlive osfm_match_commit
         for v, vp in enumerate(viewports):
@@ -185,7 +226,12 @@ class ExhaustiveMatching:
             keep.append((s, f))
             self._sizes.append((n_sift, n_surf))
         self._check(self._L.osfm_match_commit(self._h))
-        del keep
+        self._staged_sources = keep if overlap_copies else None
+
+    def wait_staged(self) -> None:
+        """After an overlapped init: returns when every view has arrived on the device."""
+        self._check(self._L.osfm_match_wait_staged(self._h))
+        self._staged_sources = None
 
     def init_device_pool(self, sift_pool, row_offsets, sizes) -> None:
         """Adopts a SIFT descriptor pool already resident on this GPU (a torch uint8

@@ -737,6 +737,65 @@ def test_matcher_output_through_the_file_formats(ora, tmp_path):
         oracle.tracks_from_ids([n] * nv, oracle.canonical_track_ids(want), pos, 2048.0, col))
 
 
+# ------------------------------------------------------------------ overlapped staging
+
+def test_overlapped_staging_gives_the_same_results():
+    """osfm_match_begin_overlapped: commit does not wait for the copies and the pair list is
+    matched in phases as the views arrive.  Same lists, dense results, single pairs and gates
+    as the plain cycle -- with SIFT and SURF, pairs in the reference's order, in reverse order
+    (the first pair needs the last view) and over repeated cycles on one handle."""
+    nv, n = 13, 1500
+    sift = synth.sift_views(41, nv, n, noise="renorm")
+    pool = synth.surf_pool(41, 300)
+    surf = [synth.surf_view(41, v, 300 + 10 * v, pool) for v in range(nv)]
+    surf[4] = surf[4][:0]
+    pairs = [(a, b) for a in range(nv) for b in range(a)]
+    cap = len(pairs) * (n + 500)
+    with matcher(sift, surf) as m:
+        out = np.empty((cap, 2), np.int32)
+        want_off = m.match_pairs_lists(pairs, out).copy()
+        want = out[:want_off[-1]].copy()
+        want_rev_out = np.empty((cap, 2), np.int32)
+        want_rev_off = m.match_pairs_lists(pairs[::-1], want_rev_out).copy()
+        want_single = m.pairwise_match(nv - 1, 2)
+        want_gates = m.two_view_candidates(pairs, TwoViewOptions(use_lowres_matching=True, num_lowres_features=300,
+                                                                 min_lowres_matches=10, min_feature_matches=30))
+    m = ExhaustiveMatching()
+    try:
+        for cycle in range(3):
+            m.init(vps(sift, surf), overlap_copies=True)
+            got = np.empty((cap, 2), np.int32)
+            if cycle == 0:
+                off = m.match_pairs_lists(pairs, got)
+                assert np.array_equal(off, want_off) and np.array_equal(got[:off[-1]], want)
+            elif cycle == 1:
+                off = m.match_pairs_lists(pairs[::-1], got)
+                assert np.array_equal(off, want_rev_off) and np.array_equal(got[:off[-1]], want_rev_out[:off[-1]])
+            else:
+                r = m.pairwise_match(nv - 1, 2)          # right after commit: needs the last view
+                assert np.array_equal(r.matches_1_2, want_single.matches_1_2)
+                assert np.array_equal(r.matches_2_1, want_single.matches_2_1)
+                gates = m.two_view_candidates(pairs, TwoViewOptions(use_lowres_matching=True, num_lowres_features=300,
+                                                                    min_lowres_matches=10, min_feature_matches=30))
+                for (s1, c1, l1), (s2, c2, l2) in zip(want_gates, gates):
+                    assert s1 == s2 and c1 == c2 and np.array_equal(l1, l2)
+            m.wait_staged()
+            assert_clean(m)
+        m.init(vps(sift, surf))                          # and back to the plain cycle
+        off = m.match_pairs_lists(pairs, got)
+        assert np.array_equal(off, want_off) and np.array_equal(got[:off[-1]], want)
+        from orthosfm_b200 import PackedViews            # every view staged by one osfm_match_set_views_q8 call
+        packed = PackedViews(vps(sift, surf))
+        for overlap in (False, True):
+            m.init(packed, overlap_copies=overlap)
+            off = m.match_pairs_lists(pairs, got)
+            assert np.array_equal(off, want_off) and np.array_equal(got[:off[-1]], want)
+        with pytest.raises(MatcherError):                # float descriptors are quantised on the device: plain cycle only
+            m.init(vps([s.astype(np.float32) / 255 for s in sift]), overlap_copies=True)
+    finally:
+        m.close()
+
+
 # ------------------------------------------------------------------ RANSAC for the fundamental matrix
 
 def _ransac_case(counts, seed, outliers=0.3):
