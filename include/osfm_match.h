@@ -110,9 +110,9 @@ int osfm_match_commit(osfm_matcher* m);
  * the buffers handed to osfm_match_set_view_q8 must stay valid and unchanged until the first
  * call that returns results (osfm_match_pairs*, osfm_match_pair*, osfm_match_two_view*) or
  * osfm_match_wait_staged has returned.  A pair list in the reference's order (view_1
- * ascending, bundler_matching.cc:92-93) is then matched in up to three phases -- pairs
- * within the first seventh of the views, within the first third, the rest -- each starting
- * as soon as its views have arrived, so most of the copy time hides behind the matching of
+ * ascending, bundler_matching.cc:92-93) is then matched in two phases -- the pairs within
+ * the first quarter of the views, then the rest -- each starting as soon as its views have
+ * arrived, so most of the copy time hides behind the matching of
  * the earlier pairs.  Views must be staged in ascending order (otherwise commit waits, as
  * the plain one does); quantised descriptors only.  Results are the same as with
  * osfm_match_begin. */

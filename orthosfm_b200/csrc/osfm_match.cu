@@ -704,15 +704,17 @@ int read_counters(osfm_matcher* m) {
 
 // Splits `plans` into batches bounded by scratch memory; calls fn(first, last, dense_ints).
 // phase_views > 0 (a lazy commit is pending): a batch also ends where the pairs start to need
-// views of a later "phase" (the first seventh of the views, the first third, all of them: the
-// matching of one phase then lasts about as long as the copies the next one waits for), so
+// views of a later "phase".  Two phases: the pairs within the first quarter of the views, then
+// the rest -- every extra batch costs about 0.25 ms of fixed work and host round trips
+// (measured), and matching the first sixteenth of the pairs already lasts as long as the
+// remaining copies (three finer phases hid more of the copies and lost more than that), so
 // that the early pairs of a list in the reference's order (view_1 ascending) are matched while
 // the later views are still being copied.
 template <typename Fn>
 int for_each_batch(std::vector<PairPlan>& plans, Fn fn, int phase_views = 0) {
     auto phase_of = [phase_views](PairPlan const& p) {
         int const v = std::max(p.v1, p.v2);
-        return phase_views <= 0 ? 0 : (v < (phase_views + 6) / 7 ? 0 : (v < (phase_views + 2) / 3 ? 1 : 2));
+        return phase_views <= 0 ? 0 : (v < (phase_views + 3) / 4 ? 0 : 1);
     };
     size_t first = 0;
     while (first < plans.size()) {
