@@ -174,6 +174,7 @@ struct osfm_matcher {
 
     int scan_mode = 0;
     double scan_ms_acc = 0.0;
+    bool scan_time_pending = false;   // ev[0], ev[1] of the last run_jobs not yet read
     osfm_match_stats stats;
 };
 
@@ -587,6 +588,8 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
 }
 
 int collect_scan_time(osfm_matcher* m) {
+    if (!m->scan_time_pending) return OSFM_OK;
+    m->scan_time_pending = false;
     if (cudaEventQuery(m->ev[1]) == cudaErrorNotReady) CU_TRY(m, cudaEventSynchronize(m->ev[1]));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->scan_ms_acc += ms;
@@ -649,7 +652,12 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
             any = any || p.n1[kd] > 0 || p.n2[kd] > 0;
         }
         if (!any) continue;
+        // the previous kind's scan time has to be read before its events are recorded again;
+        // everything else the two kinds share is ordered by the stream.  No host round trip
+        // after the last kind: the caller synchronises once, after queueing its own copies.
+        OS_TRY(collect_scan_time(m));
         OS_TRY(run_jobs(m, kd, specs, out_row));
+        m->scan_time_pending = true;
         parts.clear();
         int max_n = 0;
         for (int i = 0; i < np; ++i) {
@@ -683,8 +691,6 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
             copy_twoway_kernel<<<grid, 256, 0, m->stream>>>(m->d_parts.p, m->d_oneway.p, m->d_dense.p);
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
-        OS_TRY(collect_scan_time(m));  // also orders the reuse of `parts` / scratch across kinds
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
     }
     return OSFM_OK;
 }
@@ -1160,6 +1166,7 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
             CU_TRY(m, cudaMemcpyAsync(n_consistent + first, m->d_counts.p, sizeof(int32_t) * (last - first),
                                       cudaMemcpyDeviceToHost, m->stream));
         CU_TRY(m, cudaStreamSynchronize(m->stream));
+        OS_TRY(collect_scan_time(m));
         if (offsets)
             for (size_t i = first; i < last; ++i) {
                 offsets[2 * i] = host_base + plans[i].out12;
@@ -1341,6 +1348,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
         counts.resize(np);
         CU_TRY(m, cudaMemcpyAsync(counts.data(), m->d_counts.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, m->stream));
         CU_TRY(m, cudaStreamSynchronize(m->stream));
+        OS_TRY(collect_scan_time(m));
         loff.resize(np);
         parts.clear();
         for (size_t i = 0; i < np; ++i) {
@@ -1368,7 +1376,8 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
             m->d_parts.p, m->d_dense.p, m->d_listoff.p, reinterpret_cast<int2*>(d_match_ij));
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches++;
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
+        // no host round trip here: the next batch is ordered behind this kernel by the stream,
+        // and the pageable sources above were staged before cudaMemcpyAsync returned
         return OSFM_OK;
     }, m->lazy ? m->num_views : 0);
     if (r != OSFM_OK) return r;
