@@ -718,9 +718,16 @@ int read_counters(osfm_matcher* m) {
 // the later views are still being copied.
 template <typename Fn>
 int for_each_batch(std::vector<PairPlan>& plans, Fn fn, int phase_views = 0) {
-    auto phase_of = [phase_views](PairPlan const& p) {
+    // OSFM_OVERLAP_PHASES="a" or "a,b" (tuning knob): phase limits at 1/a (and 1/b) of the views
+    int d1 = 4, d2 = 0;
+    if (const char* env = phase_views > 0 ? getenv("OSFM_OVERLAP_PHASES") : nullptr) {
+        if (sscanf(env, "%d,%d", &d1, &d2) < 1 || d1 < 1) { d1 = 4; d2 = 0; }
+    }
+    auto phase_of = [phase_views, d1, d2](PairPlan const& p) {
         int const v = std::max(p.v1, p.v2);
-        return phase_views <= 0 ? 0 : (v < (phase_views + 3) / 4 ? 0 : 1);
+        if (phase_views <= 0) return 0;
+        if (v < (phase_views + d1 - 1) / d1) return 0;
+        return d2 > 0 && v >= (phase_views + d2 - 1) / d2 ? 2 : 1;
     };
     size_t first = 0;
     while (first < plans.size()) {

@@ -12,7 +12,8 @@ pairs = synth.all_pairs(nv)
 lists = torch.empty((len(pairs) * n // 4 + 4096, 2), dtype=torch.int32).pin_memory().numpy()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 me = ExhaustiveMatching()
-for mode in ("plain", "overlap", "overlap+packed"):
+modes = sys.argv[1].split(":") if len(sys.argv) > 1 else ["plain", "overlap", "overlap+packed"]
+for mode in modes:
     rows = []
     for it in range(8):
         flush.fill_(1); torch.cuda.synchronize()
