@@ -1815,8 +1815,12 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
         }
     }
     int launches = 1;
-    for (int p0 = 0, c = 0; p0 < npairs; p0 += chunk, ++c) {
-        int const np = std::min(chunk, npairs - p0);
+    // When the samples are drawn here the first chunks are small (1/8, 1/4, 1/2 of a chunk): the
+    // device has nothing to do while the first chunk is drawn, so that one should be short.
+    int np = 0;
+    for (int p0 = 0, c = 0; p0 < npairs; p0 += np, ++c) {
+        int const ramp = (!samples && !chunk_env && c < 3) ? std::max(1, chunk >> (3 - c)) : chunk;
+        np = std::min(ramp, npairs - p0);
         int64_t const fits = static_cast<int64_t>(np) * max_iterations;
         int64_t const f0 = static_cast<int64_t>(p0) * max_iterations;
         if (fits > 0) {
