@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OSFM_MATCH_ABI_VERSION 1
+#define OSFM_MATCH_ABI_VERSION 2
 
 typedef enum {
     OSFM_OK = 0,
@@ -373,6 +373,8 @@ typedef struct {
     int64_t exact_rows;          /* rows re-run by the EXACT pass (survivors + uncertified) */
     int64_t last_scan_sm_cycles; /* SM cycles (clock64) of the last filter scan launch, CTA 0 */
     int64_t last_scan_ns;        /* its duration in ns (globaltimer): cycles/ns = SM clock in GHz */
+    int64_t claimed_rows;        /* rows of the reverse direction of a pair that some forward match claims
+                                    (the only rows of that direction that are evaluated), cumulative */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
@@ -381,6 +383,10 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
 /* mode 0 = normal; 1 = scan kernel skips the epilogue reduction (MMA+TMA only);
  * 2 = epilogue reads TMEM but does not reduce.  Results are invalid for != 0. */
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
+/* on != 0: the filtered entry points run BOTH directions of every pair through the filter pass
+ * (Matching::twoway_match as the reference executes it, matching.h:155-158) instead of one
+ * direction plus the claimed rows of the other.  Same results; for A/B tests and timing. */
+int osfm_match_debug_set_both_directions(osfm_matcher* m, int on);
 /* Writes the raw int32 similarity matrix of one (query view, candidate view)
  * SIFT job as computed by the tensor-core kernel: out is n_q x ld ints,
  * ld = 256 * ceil(n_c / 256). */

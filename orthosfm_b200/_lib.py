@@ -32,6 +32,7 @@ EXPORTS = [
     "osfm_ransac_draw_samples", "osfm_ransac_fundamental", "osfm_match_two_view",
     "osfm_match_ransac_default_options",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
+    "osfm_match_debug_set_both_directions",
 ]
 
 
@@ -57,7 +58,8 @@ class Stats(C.Structure):
                 ("candidate_rows", C.c_int64), ("slow_rows", C.c_int64),
                 ("self_check_failures", C.c_int64), ("last_scan_ms", C.c_double),
                 ("last_total_ms", C.c_double), ("last_comparisons", C.c_int64),
-                ("exact_rows", C.c_int64), ("last_scan_sm_cycles", C.c_int64), ("last_scan_ns", C.c_int64)]
+                ("exact_rows", C.c_int64), ("last_scan_sm_cycles", C.c_int64), ("last_scan_ns", C.c_int64),
+                ("claimed_rows", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -140,6 +142,7 @@ def load() -> C.CDLL:
                                           C.c_double, i32p, i64p, f64p]
     L.osfm_match_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
+    L.osfm_match_debug_set_both_directions.argtypes = [vp, C.c_int]
     L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.osfm_match_debug_trace.argtypes = [vp, i32p, C.c_int, i64p, C.c_int64]
     L.osfm_match_debug_dump_packed.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]

@@ -39,7 +39,10 @@ constexpr int kPadRows = 256;                  // readable zero rows after the l
 constexpr int64_t kMaxBatchRows = 16ll << 20;  // job rows per batch (bounds scratch memory)
 constexpr int64_t kMaxBatchDense = 1ll << 30;  // dense result ints per batch (4 GiB)
 
-struct JobSpec { int q_view, q_n, c_view, c_n; };
+// One direction of one image pair.  reverse = false: goes through the filter pass.  reverse = true:
+// the other direction of spec `partner`, evaluated only for the rows the partner's results claim
+// (post_kernels.cuh, "reverse direction of a pair").
+struct JobSpec { int q_view, q_n, c_view, c_n; bool reverse; int partner; };
 
 template <typename T>
 struct DevBuf {
@@ -122,7 +125,10 @@ struct osfm_matcher {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> view_ev;
     std::vector<char> view_ev_set;
+    std::vector<int64_t> view_ev_seq;   // order in which the events were recorded
+    int64_t ev_seq = 0;
     bool overlap = false;      // this begin/commit cycle stages through copy_stream
+    bool copies_in_flight = false;   // copy_stream may still be reading the caller's buffers
     bool lazy = false;         // committed, but norms (and maybe copies) of later views still pending
 
     DevBuf<ScanJob> d_jobs;
@@ -151,6 +157,8 @@ struct osfm_matcher {
     cudaEvent_t rs_stage_free[2] = {nullptr, nullptr};
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
+    DevBuf<int32_t> d_rev_of;            // per job: the reverse job of its pair (or -1)
+    DevBuf<uint32_t> d_replay_flags;     // bitmap over a batch's rows: already in the replay list
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
     // survivors), [1] EXACT (unsigned rows without the 16-bit norm certificate)
     struct SecondPass {
@@ -173,6 +181,7 @@ struct osfm_matcher {
     unsigned long long* d_counters = nullptr;  // see PostParams::counters
 
     int scan_mode = 0;
+    bool both_directions = false;     // debug / A-B switch: run both directions through the filter
     double scan_ms_acc = 0.0;
     bool scan_time_pending = false;   // ev[0], ev[1] of the last run_jobs not yet read
     osfm_match_stats stats;
@@ -302,19 +311,18 @@ int compute_norms(osfm_matcher* m, KindPool& k) {
 }
 
 // Lazy commit: makes the views up to max_view usable on the main stream (their copies have
-// arrived, their norms exist).  Views were staged in ascending order, so the event of the
-// first staged view >= max_view covers every earlier one.
+// arrived, their norms exist).
 int ensure_views(osfm_matcher* m, int max_view) {
     if (!m->lazy) return OSFM_OK;
     max_view = std::min(max_view, m->num_views - 1);
     bool need = false;
     for (int kd = 0; kd < 2; ++kd) need = need || m->kind[kd].norm_views <= max_view;
     if (need) {
+        // copy_stream is in order: the event recorded last among the views up to max_view
+        // covers every copy those views need
         int ev = -1;
-        for (int v = max_view; v < m->num_views && ev < 0; ++v)
-            if (m->view_ev_set[v]) ev = v;
-        for (int v = max_view - 1; v >= 0 && ev < 0; --v)
-            if (m->view_ev_set[v]) ev = v;            // nothing staged at or after max_view
+        for (int v = 0; v <= max_view; ++v)
+            if (m->view_ev_set[v] && (ev < 0 || m->view_ev_seq[v] > m->view_ev_seq[ev])) ev = v;
         if (ev >= 0) CU_TRY(m, cudaStreamWaitEvent(m->stream, m->view_ev[ev], 0));
         for (int kd = 0; kd < 2; ++kd) {
             KindPool& k = m->kind[kd];
@@ -377,7 +385,8 @@ cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int
 // sized on the device; the host never learns how many rows there were until it reads the
 // counters.
 template <int PASS, bool SIGNED>
-int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp) {
+int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp,
+                       bool verify) {
     osfm_matcher::SecondPass& sp = m->pass[PASS == kPassResolve ? 0 : 1];
     CU_TRY(m, sp.job_xrow.reserve(static_cast<size_t>(njobs)));
     CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(nseg) + 1));
@@ -412,9 +421,15 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     ex.self_check = m->d_counters + 2;
     ex.norm2 = nullptr;
     ex.viewmax = nullptr;
+    ex.verify = verify ? 1 : 0;
+    ex.replay_flags = nullptr;
     if (PASS == kPassExact) {
         CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
         ex.big_list = m->d_big.p;
+        size_t const flag_words = static_cast<size_t>(rows / 32 + 1);
+        CU_TRY(m, m->d_replay_flags.reserve(flag_words));
+        CU_TRY(m, cudaMemsetAsync(m->d_replay_flags.p, 0, flag_words * sizeof(uint32_t), m->stream));
+        ex.replay_flags = m->d_replay_flags.p;
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
     }
@@ -427,7 +442,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         // certify the big candidates; rows that fail (a 16-bit lane really wrapped) get the
         // warp-per-row replay.  counters[8] is the replay list length.
         verify_big_kernel<<<m->num_sms * 2, 256, 0, m->stream>>>(pp, m->d_big.p, m->d_counters + 12,
-                                                                m->d_cand.p, m->d_counters + 8);
+                                                                m->d_cand.p, m->d_counters + 8, m->d_replay_flags.p);
         CU_TRY(m, cudaGetLastError());
         PostParams rp = pp;
         rp.slow_list = m->d_cand.p;
@@ -439,43 +454,54 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     return OSFM_OK;
 }
 
-// Runs filter scan + RESOLVE / EXACT passes (+ wrap emulation) for a list of jobs of one kind.  On return
-// (in stream order) m->d_oneway holds, for job i, q_n one-way results starting at out_row[i]
-// (out_row[i] = -1 if the job was not run because one side is empty).
+// Runs the filter scan + RESOLVE / EXACT passes (+ wrap emulation) for a list of jobs of one kind,
+// then the reverse jobs (evaluated for their claimed rows only).  On return (in stream order)
+// m->d_oneway holds, for job i, q_n one-way results starting at out_row[i] (out_row[i] = -1 if the
+// job was not run because one side is empty).  A reverse job's rows hold the reference's result
+// where it can survive the mutual filter and -1 elsewhere.
 int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
              std::vector<int64_t>& out_row, int32_t* dump = nullptr, int64_t dump_ld = 0, int dump_mode = 3) {
     KindPool& k = m->kind[kind_id];
     out_row.assign(specs.size(), -1);
     std::vector<ScanJob> jobs;
     jobs.reserve(specs.size() + 1);
-    // Jobs are ordered by candidate view: concurrently running work items then stream the
-    // same candidate tiles (L2 locality), and the EXACT pass can merge the survivors of all
-    // jobs that share a candidate view into full 256-row items.
+    // Forward jobs first, then the reverse jobs; each group ordered by candidate view:
+    // concurrently running work items then stream the same candidate tiles (L2 locality), and the
+    // second passes can merge the rows of all jobs that share a candidate view into full 256-row
+    // items.
     std::vector<uint32_t> order(specs.size());
     for (size_t i = 0; i < specs.size(); ++i) order[i] = static_cast<uint32_t>(i);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (specs[a].reverse != specs[b].reverse) return !specs[a].reverse;
         if (specs[a].c_view != specs[b].c_view) return specs[a].c_view < specs[b].c_view;
         return specs[a].c_n < specs[b].c_n;
     });
-    std::vector<int32_t> seg_first;   // first job of every (candidate view, c_n) segment
-    int64_t rows = 0, items = 0;
+    std::vector<int32_t> seg_first;   // first job of every (direction, candidate view, c_n) segment
+    std::vector<int32_t> job_of(specs.size(), -1);
+    int64_t rows = 0, items = 0, fwd_rows = 0;
+    bool prev_reverse = false;
     for (size_t oi = 0; oi < order.size(); ++oi) {
         size_t const i = order[oi];
         JobSpec const& s = specs[i];
         if (s.q_n <= 0 || s.c_n <= 0) continue;
-        if (jobs.empty() || jobs.back().c_view != s.c_view || jobs.back().c_n != s.c_n)
+        if (jobs.empty() || prev_reverse != s.reverse || jobs.back().c_view != s.c_view || jobs.back().c_n != s.c_n)
             seg_first.push_back(static_cast<int32_t>(jobs.size()));
+        prev_reverse = s.reverse;
         ScanJob j;
         j.q_row = static_cast<int32_t>(k.off[s.q_view]);
         j.q_n = s.q_n;
         j.c_row = static_cast<int32_t>(k.off[s.c_view]);
         j.c_n = s.c_n;
         j.out_row = rows;
-        j.item_start = static_cast<int32_t>(items);
+        j.item_start = static_cast<int32_t>(items);   // reverse jobs: no items in the filter pass
         j.c_view = s.c_view;
         out_row[i] = rows;
+        job_of[i] = static_cast<int32_t>(jobs.size());
         rows += s.q_n;
-        items += (s.q_n + kItemM - 1) / kItemM;
+        if (!s.reverse) {
+            items += (s.q_n + kItemM - 1) / kItemM;
+            fwd_rows = rows;
+        }
         jobs.push_back(j);
     }
     if (jobs.empty()) return OSFM_OK;
@@ -485,6 +511,10 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     int const njobs = static_cast<int>(jobs.size());
     int const nseg = static_cast<int>(seg_first.size());
     seg_first.push_back(njobs);
+    std::vector<int32_t> rev_of(njobs, -1);
+    for (size_t i = 0; i < specs.size(); ++i)
+        if (specs[i].reverse && job_of[i] >= 0 && specs[i].partner >= 0 && job_of[specs[i].partner] >= 0)
+            rev_of[job_of[specs[i].partner]] = job_of[i];
     ScanJob sentinel;
     memset(&sentinel, 0, sizeof sentinel);
     sentinel.out_row = rows;
@@ -504,7 +534,12 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
                               cudaMemcpyHostToDevice, m->stream));
     CU_TRY(m, cudaMemcpyAsync(m->d_jobs.p, jobs.data(), sizeof(ScanJob) * jobs.size(),
                               cudaMemcpyHostToDevice, m->stream));
-    // pageable source: the copy is staged before the call returns, `jobs` may die.
+    bool const have_reverse = rows > fwd_rows;
+    if (have_reverse) {
+        CU_TRY(m, m->d_rev_of.reserve(static_cast<size_t>(njobs)));
+        CU_TRY(m, cudaMemcpyAsync(m->d_rev_of.p, rev_of.data(), sizeof(int32_t) * njobs, cudaMemcpyHostToDevice, m->stream));
+    }
+    // pageable sources: the copies are staged before the calls return, the vectors may die.
     CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));      // [0]
 
     CU_TRY(m, m->d_rowres.reserve(static_cast<size_t>(rows)));
@@ -512,24 +547,26 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     float const sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
 
     CU_TRY(m, cudaEventRecord(m->ev[0], m->stream));
-    cudaError_t e;
-    switch (dump ? dump_mode : m->scan_mode) {
-        case 1: e = launch_scan<1>(m, k, static_cast<int>(items), nullptr, 0); break;
-        case 2: e = launch_scan<2>(m, k, static_cast<int>(items), m->d_oneway.p, 0); break;
-        case 3: e = launch_scan<3>(m, k, static_cast<int>(items), dump, dump_ld); break;
-        case 4: e = launch_scan<4>(m, k, static_cast<int>(items), dump, dump_ld); break;
-        case 5: e = launch_scan<5>(m, k, static_cast<int>(items), dump, dump_ld); break;
-        default: e = launch_scan<0>(m, k, static_cast<int>(items), nullptr, 0); break;
+    cudaError_t e = cudaSuccess;
+    if (items > 0) {
+        switch (dump ? dump_mode : m->scan_mode) {
+            case 1: e = launch_scan<1>(m, k, static_cast<int>(items), nullptr, 0); break;
+            case 2: e = launch_scan<2>(m, k, static_cast<int>(items), m->d_oneway.p, 0); break;
+            case 3: e = launch_scan<3>(m, k, static_cast<int>(items), dump, dump_ld); break;
+            case 4: e = launch_scan<4>(m, k, static_cast<int>(items), dump, dump_ld); break;
+            case 5: e = launch_scan<5>(m, k, static_cast<int>(items), dump, dump_ld); break;
+            default: e = launch_scan<0>(m, k, static_cast<int>(items), nullptr, 0); break;
+        }
+        if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
+        m->stats.kernel_launches++;
     }
-    if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
     CU_TRY(m, cudaEventRecord(m->ev[1], m->stream));
-    m->stats.kernel_launches++;
     m->stats.scan_items += items;
     if (dump) return OSFM_OK;   // debug dumps produce no results
 
     ClassifyParams cp;
     cp.jobs = m->d_jobs.p;
-    cp.total_rows = rows;
+    cp.total_rows = fwd_rows;
     cp.rowres = m->d_rowres.p;
     cp.norm2 = k.d_norm2.p;
     cp.viewmax = k.d_viewmax.p;
@@ -546,18 +583,6 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     cp.counters = m->d_counters;
     cp.sq_lowe = sq_lowe;
     cp.sq_dist = sq_dist;
-    int const cgrid = static_cast<int>((rows + 255) / 256);
-    if (k.is_signed) classify_kernel<true><<<cgrid, 256, 0, m->stream>>>(cp);
-    else             classify_kernel<false><<<cgrid, 256, 0, m->stream>>>(cp);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(m, e, "classify_kernel launch");
-    m->stats.kernel_launches++;
-    if (!k.is_signed) {
-        certify_kernel<<<m->num_sms * 32, 256, 0, m->stream>>>(cp);   // latency-bound: many warps
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(m, e, "certify_kernel launch");
-        m->stats.kernel_launches++;
-    }
 
     PostParams pp;
     pp.pool = k.pool;
@@ -568,17 +593,70 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     pp.sq_dist = sq_dist;
     pp.slow_list = m->d_cand.p;
     pp.counters = m->d_counters;
-    if (k.is_signed) {
-        // rows without the norm certificate (adversarial input only): warp-per-row emulation
-        // on CUDA cores
-        slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
+
+    // The rows queued by classify_kernel / targets_kernel: CUDA-core replay of the signed rows
+    // without certificate, RESOLVE pass, EXACT pass.
+    auto second_passes = [&](bool verify) -> int {
+        if (k.is_signed) {
+            // rows without the norm certificate (adversarial input only): warp-per-row emulation
+            slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
+            CU_TRY(m, cudaGetLastError());
+            m->stats.kernel_launches++;
+            OS_TRY((launch_second_pass<kPassResolve, true>(m, k, njobs, nseg, rows, pp, verify)));
+        } else {
+            OS_TRY((launch_second_pass<kPassResolve, false>(m, k, njobs, nseg, rows, pp, verify)));
+            OS_TRY((launch_second_pass<kPassExact, false>(m, k, njobs, nseg, rows, pp, verify)));
+        }
+        return OSFM_OK;
+    };
+
+    if (fwd_rows > 0) {
+        int const cgrid = static_cast<int>((fwd_rows + 255) / 256);
+        if (k.is_signed) classify_kernel<true><<<cgrid, 256, 0, m->stream>>>(cp);
+        else             classify_kernel<false><<<cgrid, 256, 0, m->stream>>>(cp);
         e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(m, e, "slow_rows_kernel launch");
+        if (e != cudaSuccess) return cuda_fail(m, e, "classify_kernel launch");
         m->stats.kernel_launches++;
-        OS_TRY((launch_second_pass<kPassResolve, true>(m, k, njobs, nseg, rows, pp)));
-    } else {
-        OS_TRY((launch_second_pass<kPassResolve, false>(m, k, njobs, nseg, rows, pp)));
-        OS_TRY((launch_second_pass<kPassExact, false>(m, k, njobs, nseg, rows, pp)));
+        if (!k.is_signed) {
+            certify_kernel<false><<<m->num_sms * 32, 256, 0, m->stream>>>(cp);   // latency-bound: many warps
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(m, e, "certify_kernel launch");
+            m->stats.kernel_launches++;
+        }
+        OS_TRY(second_passes(false));
+    }
+
+    if (have_reverse) {
+        // the forward results are final: which rows of the other view do they claim?
+        int64_t const rev_rows = rows - fwd_rows;
+        CU_TRY(m, cudaMemsetAsync(m->d_oneway.p + fwd_rows, 0xff, sizeof(int32_t) * rev_rows, m->stream));
+        CU_TRY(m, cudaMemsetAsync(m->d_rowres.p + fwd_rows, 0xff, sizeof(int2) * rev_rows, m->stream));
+        for (int i = 0; i < (k.is_signed ? 1 : 2); ++i)
+            CU_TRY(m, cudaMemsetAsync(m->pass[i].cnt.p, 0, sizeof(int) * njobs, m->stream));
+        CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));  // [0]
+        ClaimParams cl;
+        cl.jobs = m->d_jobs.p;
+        cl.rev_of = m->d_rev_of.p;
+        cl.fwd_rows = fwd_rows;
+        cl.total_rows = rows;
+        cl.pool = k.pool;
+        cl.oneway = m->d_oneway.p;
+        cl.rowres = m->d_rowres.p;
+        int const fgrid = static_cast<int>((fwd_rows + 255) / 256);
+        int const rgrid = static_cast<int>((rev_rows + 255) / 256);
+        cp.total_rows = rows;
+        if (k.is_signed) {
+            claim_kernel<true><<<fgrid, 256, 0, m->stream>>>(cl);
+            targets_kernel<true><<<rgrid, 256, 0, m->stream>>>(cp, fwd_rows);
+        } else {
+            claim_kernel<false><<<fgrid, 256, 0, m->stream>>>(cl);
+            targets_kernel<false><<<rgrid, 256, 0, m->stream>>>(cp, fwd_rows);
+            certify_kernel<true><<<m->num_sms * 32, 256, 0, m->stream>>>(cp);
+            m->stats.kernel_launches++;
+        }
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches += 2;
+        OS_TRY(second_passes(true));
     }
 
     // Scan time of this launch; read after the caller's next synchronisation.
@@ -646,9 +724,13 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
         if (only_kind >= 0 && kd != only_kind) continue;
         specs.clear();
         bool any = false;
+        // kFiltered: only mutual matches survive, so the second direction of a pair is evaluated
+        // for the rows the first direction's results claim (one tensor-core product per pair);
+        // kTwoway returns both unfiltered directions, which takes both products.
         for (PairPlan const& p : plans) {
-            specs.push_back({p.v1, p.n1[kd], p.v2, p.n2[kd]});
-            specs.push_back({p.v2, p.n2[kd], p.v1, p.n1[kd]});
+            int const fwd = static_cast<int>(specs.size());
+            specs.push_back({p.v1, p.n1[kd], p.v2, p.n2[kd], false, -1});
+            specs.push_back({p.v2, p.n2[kd], p.v1, p.n1[kd], mode == kFiltered && !m->both_directions, fwd});
             any = any || p.n1[kd] > 0 || p.n2[kd] > 0;
         }
         if (!any) continue;
@@ -704,6 +786,7 @@ int read_counters(osfm_matcher* m) {
     m->stats.candidate_rows = static_cast<int64_t>(c[1]);
     m->stats.self_check_failures = static_cast<int64_t>(c[2]);
     m->stats.slow_rows = static_cast<int64_t>(c[3]);
+    m->stats.claimed_rows = static_cast<int64_t>(c[4]);
     if (c[2] != 0) return fail(m, OSFM_ERR_INTERNAL, "kernel self-check failed %llu times (filter / EXACT pass mismatch)", c[2]);
     return OSFM_OK;
 }
@@ -749,6 +832,17 @@ int for_each_batch(std::vector<PairPlan>& plans, Fn fn, int phase_views = 0) {
         if (r != OSFM_OK) return r;
         first = last;
     }
+    return OSFM_OK;
+}
+
+// Overlapped staging: the contract lets the caller release its descriptor buffers after the
+// first call that returns results.  A call that touched only some views has waited (on the
+// device) for those views alone, so every result-returning call ends by waiting for whatever is
+// left of the copies (normally nothing: they finished long before the matching did).
+int finish_staging(osfm_matcher* m) {
+    if (!m->copies_in_flight) return OSFM_OK;
+    CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
+    m->copies_in_flight = false;
     return OSFM_OK;
 }
 
@@ -864,6 +958,8 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->rs_stage_ints = 0;
     m->d_ftmp.release();
     m->d_seg_first.release();
+    m->d_rev_of.release();
+    m->d_replay_flags.release();
     for (auto& sp : m->pass) sp.release();
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->hang_host) {
@@ -886,6 +982,7 @@ static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
     CU_TRY(m, cudaSetDevice(m->device));
     CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->copies_in_flight = false;
     for (int kd = 0; kd < 2; ++kd) {
         reset_kind(m->kind[kd], false);
         m->kind[kd].n.assign(num_views, 0);
@@ -904,6 +1001,7 @@ static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
             m->view_ev.push_back(ev);
         }
         m->view_ev_set.assign(static_cast<size_t>(num_views), 0);
+        m->view_ev_seq.assign(static_cast<size_t>(num_views), 0);
     }
     return OSFM_OK;
 }
@@ -919,6 +1017,7 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
     if (k.stage_off[view] >= 0 || view < k.last_staged) k.in_order = false;  // re-staged or out of order
     k.n[view] = 0;
     k.stage_off[view] = -1;
+    k.last_staged = std::max(k.last_staged, view);    // empty views count: ids must ascend for the lazy commit
     if (n <= 0) return OSFM_OK;
     if (!src) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "null descriptor pointer with n = %d", n);
     OS_TRY(arena_reserve(m, k, n));
@@ -947,7 +1046,6 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
     k.stage_off[view] = k.arena_used;
     k.arena_used += n;
     k.n[view] = n;
-    k.last_staged = std::max(k.last_staged, view);
     return OSFM_OK;
 }
 
@@ -971,6 +1069,8 @@ static int set_view_q8_locked(osfm_matcher* m, int view_id, const uint8_t* sift,
     if (m->overlap) {
         CU_TRY(m, cudaEventRecord(m->view_ev[view_id], m->copy_stream));
         m->view_ev_set[view_id] = 1;
+        m->view_ev_seq[view_id] = ++m->ev_seq;
+        m->copies_in_flight = true;
     }
     return OSFM_OK;
 }
@@ -1061,6 +1161,7 @@ int osfm_match_wait_staged(osfm_matcher* m) {
     CU_TRY(m, cudaSetDevice(m->device));
     if (m->committed) OS_TRY(ensure_views(m, m->num_views - 1));
     CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
+    m->copies_in_flight = false;
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     return OSFM_OK;
 }
@@ -1191,6 +1292,7 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
     m->stats.last_total_ms = ms;
     m->stats.last_scan_ms = m->scan_ms_acc;
     m->stats.last_comparisons = comparisons_of(plans);
+    OS_TRY(finish_staging(m));
     return read_counters(m);
 }
 
@@ -1396,6 +1498,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
     m->stats.last_total_ms = ms;
     m->stats.last_scan_ms = m->scan_ms_acc;
     m->stats.last_comparisons = comparisons_of(plans);
+    OS_TRY(finish_staging(m));
     OS_TRY(read_counters(m));
     if (overflow) return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
                               (long long)list_base, (long long)capacity_ij);
@@ -2072,6 +2175,13 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
     return OSFM_OK;
 }
 
+int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->both_directions = on != 0;
+    return OSFM_OK;
+}
+
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
     if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;   /* 3-5: dump / trace entry points */
     std::lock_guard<std::mutex> lock(m->mu);
@@ -2096,7 +2206,7 @@ static int debug_dump(osfm_matcher* m, int kind, int view_q, int view_c, int32_t
     if (!out || out_ints < ints) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "dump buffer too small");
     int32_t* d = nullptr;
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int32_t) * ints));
-    std::vector<JobSpec> specs(1, JobSpec{view_q, nq, view_c, nc});
+    std::vector<JobSpec> specs(1, JobSpec{view_q, nq, view_c, nc, false, -1});
     std::vector<int64_t> out_row;
     int r = run_jobs(m, kind, specs, out_row, d, ld, mode);
     if (r == OSFM_OK) {
@@ -2126,8 +2236,8 @@ int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, in
         int const a = pairs[2 * i], b = pairs[2 * i + 1];
         OS_TRY(check_view(m, a));
         OS_TRY(check_view(m, b));
-        specs.push_back({a, m->kind[0].n[a], b, m->kind[0].n[b]});
-        specs.push_back({b, m->kind[0].n[b], a, m->kind[0].n[a]});
+        specs.push_back({a, m->kind[0].n[a], b, m->kind[0].n[b], false, -1});
+        specs.push_back({b, m->kind[0].n[b], a, m->kind[0].n[a], false, -1});
     }
     int64_t* d = nullptr;
     CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(int64_t) * words));

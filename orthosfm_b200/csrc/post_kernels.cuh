@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 // treated like any certified row (rejected, or queued for the RESOLVE pass); otherwise it is
 // queued for the EXACT pass.  Grid-strides over the list, whose length is only known on the
 // device.
+// TARGETS: the rows are claimed rows of a reverse job (targets_kernel): rowres holds (V, job),
+// and a row certified after the fact is queued for the RESOLVE pass whatever its value.
+template <bool TARGETS>
 __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
 {
     int64_t const n = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.counters + 0));
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
             if (wraps) {
                 p.exact_list[job.out_row + atomicAdd(p.exact_cnt + ji, 1)] = surv_entry(g, v1, false);
                 ++n_exact;
-            } else if (passes_tests(ip_to_dist<false>(v1), ip_to_dist<false>(v2), p.sq_lowe, p.sq_dist)) {
+            } else if (TARGETS || passes_tests(ip_to_dist<false>(v1), ip_to_dist<false>(v2), p.sq_lowe, p.sq_dist)) {
                 p.surv_list[job.out_row + atomicAdd(p.surv_cnt + ji, 1)] = surv_entry(g, v1, true);
                 ++n_surv;
             } else {
@@ -359,6 +362,106 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
     if (lane == 0) {
         if (n_exact) atomicAdd(p.counters + 3, static_cast<unsigned long long>(n_exact));
         if (n_surv) atomicAdd(p.counters + 1, static_cast<unsigned long long>(n_surv));
+    }
+}
+
+// ---------------------------------------------------------------- reverse direction of a pair
+//
+// Matching::twoway_match (matching.h:148-159) scans both directions of a pair, and
+// remove_inconsistent_matches (matching.cc:19-36) then keeps i -> j only if j -> i.  After the
+// mutual filter a row j of the second view therefore matters only if some row i of the first
+// view *claims* it (oneway_12[i] == j), and all that matters about it is whether its own nearest
+// neighbour, under the reference's rules, is that i.  So only the forward direction of a pair
+// goes through the filter pass (one tensor-core product per pair instead of two); the reverse
+// direction is evaluated for the claimed rows alone:
+//   claim_kernel    V[j] = the largest similarity any claimant has with j (clamped at the
+//                   reference's initial 0), kept in the (otherwise unused) rowres slot of j;
+//   targets_kernel  queues the claimed rows like classify_kernel queues survivors: rows with
+//                   the 16-bit norm certificate for the RESOLVE pass in verify mode (a similarity
+//                   above V: some row that is no claimant is nearer, the result is -1 for the
+//                   mutual filter; otherwise V is the row's best and RESOLVE's result is the
+//                   reference's), the others for the EXACT pass / the CUDA-core replay, which
+//                   need no V.
+// Rows nobody claims keep the -1 the host wrote beforehand.
+
+struct ClaimParams {
+    const ScanJob* jobs;
+    const int32_t* rev_of;       // per job: its pair's reverse job (or -1)
+    int64_t fwd_rows;            // rows [0, fwd_rows) belong to forward (scanned) jobs
+    int64_t total_rows;
+    const uint8_t* pool;
+    const int32_t* oneway;
+    int2* rowres;                // forward rows: the filter's record; reverse rows: (V, job), preset to -1
+};
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) claim_kernel(ClaimParams p)
+{
+    int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= p.fwd_rows) return;
+    int const mt = p.oneway[g];
+    if (mt < 0) return;
+    int const ji = p.rowres[g].y & kRowJobMask;
+    int const rj = p.rev_of[ji];
+    if (rj < 0) return;
+    ScanJob const job = p.jobs[ji];
+    int s = dot_row<SIGNED>(p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes,
+                            p.pool + (static_cast<int64_t>(job.c_row) + mt) * kRowBytes);
+    s = max(s, 0);               // the reference's best starts at 0 (nearest_neighbor.cc:221-224, 246-249)
+    int2* const slot = p.rowres + p.jobs[rj].out_row + mt;
+    atomicMax(&slot->x, s);
+    slot->y = rj;                // every claimant writes the same value
+}
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) targets_kernel(ClassifyParams p, int64_t first_row)
+{
+    int64_t const g = first_row + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int const lane = threadIdx.x & 31;
+    bool survive = false, wraps = false, doubtful = false;
+    int ji = -1, v1 = 0;
+    int64_t out_row = 0;
+    if (g < p.total_rows) {
+        int2 const rr = p.rowres[g];
+        if (rr.x >= 0) {         // claimed
+            v1 = rr.x;
+            ji = rr.y;
+            ScanJob const job = p.jobs[ji];
+            out_row = job.out_row;
+            int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+            int64_t const qn2 = p.norm2[job.q_row + static_cast<int>(g - job.out_row)];
+            bool const certified = qn2 * static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
+            // without certificate: signed -> CUDA-core replay; unsigned -> certify_kernel looks at
+            // the few candidates that could take the row to 2^16
+            survive = certified;
+            doubtful = !certified;
+        }
+    }
+#pragma unroll
+    for (int which = 0; which < (SIGNED ? 1 : 2); ++which) {
+        bool const mine = which == 0 ? survive : wraps;
+        unsigned const xm = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            unsigned const peers = __match_any_sync(xm, ji);
+            int const leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd((which == 0 ? p.surv_cnt : p.exact_cnt) + ji, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            (which == 0 ? p.surv_list : p.exact_list)[out_row + base + __popc(peers & ((1u << lane) - 1u))] =
+                surv_entry(g, v1, which == 0);
+        }
+    }
+    unsigned const um = __ballot_sync(0xffffffffu, doubtful);
+    if (um != 0) {
+        unsigned long long ub = 0;
+        if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
+        ub = __shfl_sync(0xffffffffu, ub, 0);
+        if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
+    }
+    unsigned const tm = __ballot_sync(0xffffffffu, survive || wraps || doubtful);
+    if (lane == 0) {
+        if (tm) atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(tm)));   // claimed rows (cumulative)
+        if (SIGNED && um) atomicAdd(p.counters + 3, static_cast<unsigned long long>(__popc(um)));   // unsigned: certify_kernel counts
     }
 }
 
@@ -511,7 +614,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
 __global__ void __launch_bounds__(256) verify_big_kernel(PostParams p, const int4* __restrict__ big_list,
                                                          const unsigned long long* __restrict__ big_count,
                                                          int64_t* __restrict__ replay_list,
-                                                         unsigned long long* __restrict__ replay_count)
+                                                         unsigned long long* __restrict__ replay_count,
+                                                         uint32_t* __restrict__ replay_flags)
 {
     unsigned long long const n = *reinterpret_cast<const volatile unsigned long long*>(big_count);
     unsigned long long const stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -521,7 +625,8 @@ __global__ void __launch_bounds__(256) verify_big_kernel(PostParams p, const int
         ScanJob const job = p.jobs[find_job(p.jobs, p.njobs, g)];
         const uint8_t* q = p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes;
         const uint8_t* c = p.pool + (static_cast<int64_t>(job.c_row) + rec.z) * kRowBytes;
-        if (wrapped_ip<false>(q, c) != rec.w)
+        // a row has up to kMaxBigPerRow records: it enters the list once
+        if (wrapped_ip<false>(q, c) != rec.w && mark_once(replay_flags, g))
             replay_list[atomicAdd(replay_count, 1ull)] = g;
     }
 }

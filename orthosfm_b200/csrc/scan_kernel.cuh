@@ -142,15 +142,30 @@ struct ExactParams {
     int32_t* oneway;
     const int* total_items_dev;  // number of work items, computed on the device
     float sq_lowe, sq_dist;
-    int64_t* replay_list;        // rows that need the full replay on CUDA cores
-    unsigned long long* replay_count;
+    int64_t* replay_list;        // rows that need the full replay on CUDA cores (each row once:
+    unsigned long long* replay_count;   // replay_flags is a bitmap over the batch's rows)
+    uint32_t* replay_flags;
     int4* big_list;              // (row lo, row hi, column, similarity) of every big candidate met
     unsigned long long* big_count;
     unsigned long long* self_check;   // filter and EXACT pass disagree on a certified row's best
     // filter pass only: the norm certificate's inputs (squared norm per pool row, largest per view)
     const int32_t* norm2;
     const int32_t* viewmax;
+    // RESOLVE pass only.  0: the rows are the filter's survivors, V is the row's largest
+    // similarity (anything above it is a self-check failure).  1: the rows are the *claimed*
+    // rows of the reverse direction of a pair (see claim_kernel in post_kernels.cuh), V is the
+    // largest similarity any claimant has with the row; a similarity above V means that the
+    // row's nearest neighbour is not one of its claimants, and the row's result is -1 as far as
+    // the mutual filter is concerned.
+    int verify;
 };
+
+// Sets bit g of a bitmap; true for the caller that set it.  Keeps a row from entering the replay
+// list more than once (the list is sized for one entry per row).
+__device__ __forceinline__ bool mark_once(uint32_t* flags, int64_t g) {
+    uint32_t const bit = 1u << (g & 31);
+    return (atomicOr(flags + (g >> 5), bit) & bit) == 0u;
+}
 
 constexpr int kTraceEvents = 256;   // per warp, MODE 5
 
@@ -310,7 +325,7 @@ __device__ __forceinline__ void resolve_flush(ResolvePending& pd, int c_n, int V
 // that does is set aside (columns are visited in ascending order, so flushing the previous
 // pending group first keeps "the last column equal to V" right).
 template <bool SIGNED>
-__device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int c_n, int V,
+__device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int c_n, int& V, bool& beaten,
                                              ResolvePending& pd, int& cnt, int& idx, int& v2)
 {
     // the load's maximum as ONE dependent chain (like the filter's fold: a warp that stalls on
@@ -332,6 +347,11 @@ __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, 
     int const m = max(plo<SIGNED>(acc[0]), phi<SIGNED>(acc[0]));
     if (m < V) {            // the common case: nothing of interest in these 64 columns
         v2 = max(v2, m);
+        return;
+    }
+    if (m > V) {            // reverse pass: a row that is no claimant is nearer than every claimant
+        beaten = true;
+        V = 0x7fffffff;     // nothing reaches this: the row stays on the fast path from here on
         return;
     }
     // some lane has V in this load: maxima of the four groups of 16 columns
@@ -771,7 +791,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             int64_t const entry = live ? ex.xrow_map[job.out_row + r_in_job] : 0;
             uint32_t const v16 = static_cast<uint32_t>((static_cast<uint64_t>(entry) >> kSurvRowBits) & 0xffffu);
             // a dead row must never take the slow path: give it a V nothing can reach
-            int const V = live ? (SIGNED ? static_cast<int>(static_cast<short>(v16)) : static_cast<int>(v16)) : 0x7fffffff;
+            int const V0 = live ? (SIGNED ? static_cast<int>(static_cast<short>(v16)) : static_cast<int>(v16)) : 0x7fffffff;
+            int V = V0;
+            bool beaten = false;    // some similarity exceeds V (legitimate in the reverse pass only)
 
             int cnt = 0, idx = -1, v2 = 0;
             ResolvePending pd;
@@ -794,6 +816,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         for (int q = 0; q < 32; ++q) {
                             bool const valid = colq + q < job.c_n;
                             bool const eq = valid && v[q] == V;
+                            beaten = beaten || (valid && v[q] > V);
                             cnt += eq ? 1 : 0;
                             idx = eq ? colq + q : idx;
                             v2 = max(v2, (valid && !eq) ? v[q] : 0);
@@ -813,26 +836,34 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(h));
                 int const col0 = t * kBlockN + c * kAccCols;
-                resolve_load<SIGNED>(ra, col0, job.c_n, V, pd, cnt, idx, v2);
-                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, pd, cnt, idx, v2);
+                resolve_load<SIGNED>(ra, col0, job.c_n, V, beaten, pd, cnt, idx, v2);
+                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, beaten, pd, cnt, idx, v2);
             }
             // The group set aside is looked at once, here: a row has one column equal to V unless
             // it has duplicates, so the value-by-value scan runs once per item for all the rows
             // of the warp instead of once per hit.
             resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
             int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
-            if (c == 1) *merge = make_int4(cnt, idx, v2, 0);
+            if (c == 1) *merge = make_int4(cnt, idx, v2, beaten ? 1 : 0);
             named_barrier_sync(1 + h * 4 + quad, 64);
             if (c == 0 && live) {
                 int4 const o = *merge;
                 cnt += o.x;
                 idx = max(idx, o.y);
                 v2 = max(v2, o.z);
-                int const second = cnt >= 2 ? V : v2;
-                bool const ok = passes_tests(ip_to_dist<SIGNED>(V), ip_to_dist<SIGNED>(second), ex.sq_lowe, ex.sq_dist);
-                // signed: a best of 0 may be the initial value, reached by no candidate: index 0
-                ex.oneway[surv_row(entry)] = ok ? max(idx, 0) : -1;
-                if (cnt == 0 && !(SIGNED && V == 0)) atomicAdd(ex.self_check, 1ull);   // the filter's best was not found
+                beaten = beaten || o.w != 0;
+                if (beaten) {
+                    // reverse pass: the row's nearest neighbour is none of its claimants, so
+                    // whatever it is, the mutual filter drops it.  Forward pass: cannot happen.
+                    ex.oneway[surv_row(entry)] = -1;
+                    if (!ex.verify) atomicAdd(ex.self_check, 1ull);
+                } else {
+                    int const second = cnt >= 2 ? V0 : v2;
+                    bool const ok = passes_tests(ip_to_dist<SIGNED>(V0), ip_to_dist<SIGNED>(second), ex.sq_lowe, ex.sq_dist);
+                    // signed: a best of 0 may be the initial value, reached by no candidate: index 0
+                    ex.oneway[surv_row(entry)] = ok ? max(idx, 0) : -1;
+                    if (cnt == 0 && !(SIGNED && V0 == 0)) atomicAdd(ex.self_check, 1ull);   // the row's best was not found
+                }
             }
         }
     } else if (EXACT && ((warp - kFirstEpilogueWarp) >> 2) < 2) {
@@ -935,7 +966,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             if (live) {
                 bool const ok = passes_tests(ip_to_dist<SIGNED>(b1), ip_to_dist<SIGNED>(b2), ex.sq_lowe, ex.sq_dist);
                 ex.oneway[g] = ok ? i1 : -1;
-                if (nbig > kMaxBigPerRow)   // cannot be certified by verify_big_kernel
+                if (nbig > kMaxBigPerRow && mark_once(ex.replay_flags, g))   // cannot be certified by verify_big_kernel
                     ex.replay_list[atomicAdd(ex.replay_count, 1ull)] = g;
                 // a certified row has no big candidate: the filter's best is the true best
                 if ((static_cast<uint64_t>(entry) & kSurvCertified) != 0 &&

@@ -280,6 +280,98 @@ def test_adversarial_bytes_match_oracle(ora, seed):
     assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
 
 
+def _one_product_cases():
+    """(name, kind, a, b, ratio): inputs that reach every route of the reverse-direction pass."""
+    cases = []
+    vs = synth.sift_views(31, 2, 1500, noise="renorm")
+    cases.append(("renorm", "u8", vs[0], vs[1][:1300], 0.8))
+    vs = synth.sift_views(32, 2, 900)                       # "lsb": norms drift, many rows reach 2^16
+    cases.append(("lsb", "u8", vs[0][:700], vs[1], 0.8))
+    a, b = synth.sift_views(33, 2, 1200, noise="renorm")
+    a, b = a.copy(), b.copy()
+    b[100:140] = a[100:140]                                 # twins across the views
+    b[700:720] = a[100:120]                                 # ... twice: several claimants / ties
+    a[300:310] = a[100:110]                                 # two rows of a claim the same row of b
+    b[1100] = b[3]
+    a[5] = 0
+    b[7] = 0
+    cases.append(("ties", "u8", a, b, 0.8))
+    cases.append(("ties-ratio-1", "u8", a, b, 1.0))
+    rng = np.random.default_rng(34)
+    a = rng.integers(0, 256, (333, 128), dtype=np.uint8)    # arbitrary bytes: every 16-bit lane wraps
+    b = rng.integers(0, 256, (517, 128), dtype=np.uint8)
+    b[:100] = a[:100]
+    cases.append(("bytes", "u8", a, b, 0.8))
+    a = rng.integers(0, 48, (400, 128), dtype=np.uint8)     # small bytes: nothing certified, nothing wraps
+    b = rng.integers(0, 48, (300, 128), dtype=np.uint8)
+    b[:50] = a[:50]
+    cases.append(("small-bytes", "u8", a, b, 0.8))
+    z = np.zeros((259, 128), np.uint8)
+    cases.append(("zeros", "u8", z, vs[1][:300], 1.0))
+    pool = synth.surf_pool(35, 300)
+    a, b = synth.surf_view(35, 0, 700, pool).copy(), synth.surf_view(35, 1, 515, pool).copy()
+    b[:40] = -a[:40]
+    a[50] = 0
+    b[60:64] = a[100]
+    cases.append(("surf", "s8", a, b, 0.7))
+    cases.append(("surf-ratio-1", "s8", a, b, 1.0))
+    cases.append(("surf-negative", "s8", np.abs(a[:33]), -np.abs(b[:20]), 1.0))   # every similarity <= 0
+    a = rng.integers(-127, 128, (300, 64), dtype=np.int8)   # arbitrary signed bytes: no norm certificate
+    b = rng.integers(-127, 128, (280, 64), dtype=np.int8)
+    b[:60] = a[:60]
+    cases.append(("surf-bytes", "s8", a, b, 0.7))
+    return cases
+
+
+@pytest.mark.parametrize("case", _one_product_cases(), ids=lambda c: c[0])
+def test_one_product_per_pair_equals_both_directions(ora, case):
+    """pairwise_match runs ONE direction of a pair through the filter pass and evaluates the
+    other direction only for the rows the first one claims (post_kernels.cuh, claim_kernel).
+    The result must be what the reference's two full scans + remove_inconsistent_matches give,
+    and what the same kernels give with both directions scanned."""
+    _, kind, a, b, ratio = case
+    opts = MatchingBase.Options()
+    opts.sift_matching_opts.lowe_ratio_threshold = ratio
+    opts.surf_matching_opts.lowe_ratio_threshold = ratio
+    kw = {"sift": [a, b]} if kind == "u8" else {"surf": [a, b]}
+    with matcher(opts=opts, **kw) as m:
+        one = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
+        lowres_one = m.pairwise_match_lowres(0, 1, 200)
+        claimed = m.stats()["claimed_rows"]
+        m.debug_set_both_directions(True)
+        both = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
+        lowres_both = m.pairwise_match_lowres(0, 1, 200)
+        assert m.stats()["claimed_rows"] == claimed       # nothing is claimed when both directions are scanned
+        assert_clean(m)
+    o12, o21 = ora.twoway(kind, a, b, ratio)
+    f12, f21 = ora.remove_inconsistent(o12, o21)
+    for r in (one[0], both[0]):
+        assert np.array_equal(r.matches_1_2, f12) and np.array_equal(r.matches_2_1, f21)
+    for r in (one[1], both[1]):
+        assert np.array_equal(r.matches_1_2, f21) and np.array_equal(r.matches_2_1, f12)
+    assert lowres_one == lowres_both
+    assert 0 <= claimed <= (o12 >= 0).sum() + (o21 >= 0).sum() + 200   # at most one row per forward match
+
+
+def test_replay_list_holds_each_row_once(ora):
+    """Saturated / arbitrary bytes at a size where the EXACT pass's replay list would overflow
+    if a row entered it once per big candidate: every similarity reaches 2^16 and every 16-bit
+    lane wraps, so every row is replayed on CUDA cores -- once."""
+    rng = np.random.default_rng(77)
+    a = rng.integers(128, 256, (10240, 128), dtype=np.uint8)
+    a[::7] = 255
+    b = rng.integers(128, 256, (1031, 128), dtype=np.uint8)
+    b[::5] = 255
+    with matcher([a, b]) as m:
+        tw = m.twoway_match(KIND_SIFT_U8, 0, 1)
+        res = m.pairwise_match(0, 1)
+        assert_clean(m)
+    o12, o21 = ora.twoway("u8", a, b, 0.8)
+    assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21)
+    f12, f21 = ora.remove_inconsistent(o12, o21)
+    assert np.array_equal(res.matches_1_2, f12) and np.array_equal(res.matches_2_1, f21)
+
+
 @pytest.mark.parametrize("ratio,dist", [(0.8, None), (1.0, None), (0.6, None), (0.8, 150.0), (0.95, 60.0)])
 def test_thresholds(ora, ratio, dist):
     vs = synth.sift_views(9, 2, 900)

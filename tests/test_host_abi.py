@@ -41,7 +41,7 @@ def test_header_symbols_all_exported(lib_path):
 
 def test_library_loads_and_reports_abi(lib_path):
     L = _lib.load()
-    assert L.osfm_match_abi_version() == 1
+    assert L.osfm_match_abi_version() == 2
     cfg = _lib.Config()
     L.osfm_match_default_config(cfg)
     assert cfg.device == 0
