@@ -5,23 +5,26 @@
 
 Metric (BASELINE.json): descriptor comparisons/s (one comparison = one 128-d dot product
 = 256 OP; pairs/s is reported next to it).  A *step* is one pass of the hot path over the
-whole batch of image pairs:
+whole batch of image pairs of the workload BASELINE.json names for that GPU count:
 
-  N = 1   BASELINE config 2: 36 images x 8192 SIFT descriptors, all 630 pairs.
-  N > 1   weak scaling of the same per-GPU load: V images x 8192 with V(V-1)/2 ~ 630*N
-          pairs (N=2: 51, N=4: 72, N=8: 101), descriptor pool generated on rank 0 and
-          replicated by one NCCL broadcast, pairs partitioned across ranks, match lists
-          gathered to rank 0 inside the timed step.
+  N = 1     config 2: 36 images x 8192 SIFT descriptors, all 630 pairs.
+  N = 2, 4  config 3: 200 images x 16384, all 19 900 pairs sharded over the GPUs (strong scaling;
+            N = 1 and N = 8 also run it, reported under "config3", so the curve is like for like).
+  N = 8     config 4: 1000 images x 32768, all 499 500 pairs, descriptor pool (4.19 GB)
+            replicated by one NCCL broadcast.
+  One process per GPU (torchrun); the pool is generated on rank 0 and broadcast, the pairs are
+  partitioned by cost n1*n2, and every step ends with the match lists gathered on rank 0.
 
-value   device-resident throughput (pool already in HBM; kernels + list compaction,
-        (+ the NCCL gather for N > 1)), CUDA-event / synchronised timing, max over ranks.
-e2e     the same metric through the reference-facing host API with HOST buffers:
-        osfm_match_begin / set_view_q8 / commit (H2D from pinned memory) +
-        osfm_match_pairs (dense Matching::Result vectors, D2H) every step.
-roofline  the scan kernel (tcgen05 kind::i8) against the measured bf16 tensor peak in
-        MEASURED_PEAKS.json; achieved = sum(n1*n2)*256 OP per launch / CUDA-event time.
+value     device-resident throughput: pool already in HBM; kernels + list compaction + (N > 1)
+          the NCCL gather of the lists to rank 0.  Wall clock between barriers, max over ranks.
+e2e       the same metric from HOST descriptors to HOST match lists, every step: H2D from
+          pinned memory, (N > 1: NCCL broadcast, per-rank commit,) matching, (gather,) D2H.
+          Measured, never extrapolated.  N = 1 also reports the reference's own plugin entry
+          (float descriptors through sfm::MatchingBase::init, then pairwise_match pair by pair).
+roofline  the filter pass (tcgen05 kind::i8, one product per pair) against the int8 tensor
+          peak; kernel time from CUDA events recorded inside the library around that launch.
 cpu_baseline  the reference's own matcher (oracle/_ref, compiled from its sources) on the
-        host cores, on a bounded sample of the same workload.
+          host cores, on a bounded sample of the same workload; all cores and one core.
 
 --impl reference times only that CPU reference (rank 0), same metric and config.
 """
@@ -41,22 +44,63 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_DESC = 8192
-VIEWS_FOR_GPUS = {1: 36, 2: 51, 4: 72, 8: 101}
-CFG = 2
 METRIC = "descriptor comparisons/sec"
 UNIT = "comparisons/s"
 OPS_PER_COMPARISON = 256
+INT8_DENSE_NOMINAL_TOPS = 4500.0      # B200 dense int8 / fp8 (B200_PROFILING.md): 2x the bf16 figure
+
+# BASELINE.json configs 2-4
+WORKLOADS = {
+    2: {"views": 36, "n": 8192},
+    3: {"views": 200, "n": 16384},
+    4: {"views": 1000, "n": 32768},
+}
 
 
-def measured_traffic():
+def config_for_gpus(ngpu: int) -> int:
+    forced = os.environ.get("OSFM_BENCH_CONFIG")
+    if forced:
+        return int(forced)
+    return 2 if ngpu <= 1 else (4 if ngpu >= 8 else 3)
+
+
+def workload(cfg: int) -> dict:
+    w = dict(WORKLOADS[cfg])
+    v = os.environ.get("OSFM_BENCH_VIEWS")         # experiments only: fewer views of the same size
+    if v:
+        w["views"] = int(v)
+    return w
+
+
+def describe(cfg: int, ngpu: int, noise: str) -> dict:
+    w = workload(cfg)
+    views, n = w["views"], w["n"]
+    pairs = views * (views - 1) // 2
+    pool_mb = views * n * 128 / 1e6
+    return {
+        "workload": (f"BASELINE config {cfg}: {views} images x {n} SIFT descriptors (128-d u8), all {pairs} pairs"
+                     f"{'' if ngpu == 1 else f' sharded over {ngpu} GPUs'}, two-way match + ratio test 0.8 + mutual filter"),
+        "baseline_config": cfg, "views": views, "descriptors_per_view": n, "pairs": pairs,
+        "planted_fraction": 0.25, "planted_noise": noise,
+        "pool_bytes": views * n * 128,
+        "l2": ("flushed between timed steps (256 MB write)" if pool_mb < 256 else
+               f"descriptor pool {pool_mb:.0f} MB > 126 MB L2; also flushed between timed steps (256 MB write)"),
+        "parallelism": (f"pairs partitioned by cost over {ngpu} GPU(s), one process per GPU, descriptor pool replicated"
+                        + ("" if ngpu == 1 else " by one NCCL broadcast, match lists gathered to rank 0 over NCCL")),
+    }
+
+
+def traffic_profile():
     """dram bytes of the roofline kernel per launch, from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f)
-    except (OSError, ValueError):
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name
+            return d
+        except (OSError, ValueError):
+            continue
+    return None
 
 
 def peaks():
@@ -117,27 +161,24 @@ class ClockSampler:
 NOISE = "renorm"   # planted matches are re-normalised unit vectors, like real SIFT (synth.py)
 
 
-def make_views_numpy(num_views: int, n: int):
-    from orthosfm_b200 import synth
-    return synth.sift_views(CFG, num_views, n, noise=NOISE)
-
-
 # --------------------------------------------------------------------------- reference arm
 
-def run_reference_arm(args, config):
-    """The reference's own CPU matcher on the host cores (rank 0 only)."""
+def run_reference_arm(args, cfg, config):
+    """The reference's own CPU matcher on the host cores (rank 0 only): every step matches
+    `cores` pairs of the workload's view size (rows subsampled when a step would take too long)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
+    from orthosfm_b200 import synth
     ref = oracle.Reference()
     cores = ref.use_all_cores()
-    views = make_views_numpy(min(config["views"], 12), N_DESC)
-    from orthosfm_b200 import synth
+    n_full = workload(cfg)["n"]
+    views = synth.sift_views(cfg, min(workload(cfg)["views"], 8), n_full, noise=NOISE)
     all_pairs = synth.all_pairs(len(views))
-    n = N_DESC
     sample_pairs = max(1, min(cores, len(all_pairs)))
     pairs = all_pairs[:sample_pairs]
+    n = n_full
 
     def one_step(nrows):
         vs = [v[:nrows] for v in views]
@@ -158,14 +199,14 @@ def run_reference_arm(args, config):
     cmp_per_step = sample_pairs * n * n
     value = cmp_per_step / (ms * 1e-3)
     sample = (f"{sample_pairs} pairs of {n} x {n} descriptors per step (first pairs of the workload"
-              f"{'' if n == N_DESC else ', rows subsampled to keep the run bounded'}); "
+              f"{'' if n == n_full else ', rows subsampled to keep the run bounded'}); "
               f"twoway_match + remove_inconsistent_matches, OpenMP over pairs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config,
-        "pairs_per_s": sample_pairs / (ms * 1e-3) * (n * n) / float(N_DESC * N_DESC),
+        "pairs_per_s": sample_pairs / (ms * 1e-3) * (n * n) / float(n_full * n_full),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,8 +214,8 @@ def run_reference_arm(args, config):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
-    """Reference matcher on a bounded sample of the same workload, all host cores."""
+def cpu_baseline_sample(views, pairs, budget_s: float = 16.0):
+    """Reference matcher on a bounded sample of the same workload: all host cores, then one."""
     import oracle
     if oracle.have_ref():
         impl, kind = oracle.Reference(), "reference"
@@ -192,7 +233,6 @@ def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
                            for a, b in sample])
     dt = time.perf_counter() - t
     npairs_total = npairs
-    # keep going (fresh pairs of the same workload) until about 10 s of CPU work are in
     nxt = npairs
     while dt < budget_s / 2 and kind == "reference" and nxt + npairs <= len(pairs):
         t = time.perf_counter()
@@ -201,11 +241,18 @@ def cpu_baseline_sample(views, pairs, budget_s: float = 20.0):
         nxt += npairs
         npairs_total += npairs
     value = npairs_total * n * n / dt
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{npairs_total} of the workload's pairs ({n} x {n}), {dt:.1f} s; "
-                      f"twoway_match + remove_inconsistent_matches, OpenMP over pairs; "
-                      f"value counts unique comparisons (the reference executes 2x that)",
-            "pairs_per_s": npairs_total / dt}, counts
+    out = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{npairs_total} of the workload's pairs ({n} x {n}), {dt:.1f} s; "
+                     f"twoway_match + remove_inconsistent_matches, OpenMP over pairs; "
+                     f"value counts unique comparisons (the reference executes 2x that)",
+           "pairs_per_s": npairs_total / dt}
+    # one core: what the reference's shipped CMake build does (its OpenMP pragmas are inert)
+    t = time.perf_counter()
+    impl.match_filtered("u8", views[sample[0][0]], views[sample[0][1]], 0.8)
+    dt1 = time.perf_counter() - t
+    out["single_thread"] = {"value": n * n / dt1, "unit": UNIT, "cores": 1,
+                            "sample": f"1 pair ({n} x {n}), {dt1:.1f} s", "pairs_per_s": 1.0 / dt1}
+    return out, counts
 
 
 # --------------------------------------------------------------------------- our arm
@@ -232,7 +279,6 @@ def downstream_rows(me, pairs, n, num_views, lists, loff):
         ids, ntracks, _ = me.tracks_compute(feats, pairs, loff, ij)
         out["tracks_ms"] = 1e3 * (time.perf_counter() - t0)
     out["tracks"] = int(ntracks)
-    # the whole two-view stage in one call: gates + full match + RANSAC + inlier threshold
     from orthosfm_b200 import TwoViewOptions
     for rep in range(2):
         oracle.srand(1)
@@ -263,12 +309,295 @@ def downstream_rows(me, pairs, n, num_views, lists, loff):
     return out
 
 
-def run_ours(args, config):
+class Job:
+    """One workload on this process group: pool on every rank, pairs partitioned, a step function."""
+
+    def __init__(self, cfg, dev, rank, world, local_rank, noise):
+        import torch
+        import torch.distributed as dist
+        from orthosfm_b200 import ExhaustiveMatching, synth
+        from orthosfm_b200 import distributed as osd
+        self.torch, self.dist, self.osd = torch, dist, osd
+        self.cfg, self.dev, self.rank, self.world = cfg, dev, rank, world
+        w = workload(cfg)
+        self.num_views, self.n = w["views"], w["n"]
+        n, nv = self.n, self.num_views
+        self.pairs = synth.all_pairs(nv)
+        self.npairs = len(self.pairs)
+        self.sizes = np.full(nv, n, np.int32)
+        self.offsets = np.arange(nv, dtype=np.int64) * n
+        self.pool = torch.zeros((nv * n + 256, 128), dtype=torch.uint8, device=dev)
+        self.views_np = None
+        if rank == 0:
+            if cfg == 2 and nv <= 64:
+                self.views_np = synth.sift_views(cfg, nv, n, noise=noise)
+                self.pool[:nv * n] = torch.from_numpy(np.concatenate(self.views_np)).to(dev)
+            else:
+                self.pool[:nv * n] = synth.torch_sift_views(cfg, nv, n, dev, noise=noise)
+        torch.cuda.synchronize()
+        self.host_barrier()
+        t_b = time.perf_counter()
+        osd.broadcast_pool(self.pool, src=0)
+        torch.cuda.synchronize()
+        self.broadcast_ms = 1e3 * (time.perf_counter() - t_b)
+        self.all_owned = osd.partition_pairs(self.pairs, self.sizes, world)
+        self.owned = self.all_owned[rank]
+        self.my_pairs = self.pairs[self.owned]
+        self.my_cmp = int(len(self.my_pairs)) * n * n
+        self.total_cmp = self.npairs * n * n
+        self.m = ExhaustiveMatching(device=local_rank)
+        self.m.init_device_pool(self.pool, self.offsets, self.sizes)
+        # planted fraction 0.25 -> about n/8 mutual matches per pair; room for twice that
+        cap = int(max(len(o) for o in self.all_owned) * n * 0.25) + 4096
+        self.gather = osd.ListGather(self.all_owned, self.npairs, cap, dev, dst=0) if world > 1 else None
+        self.out_ij = self.gather.out_ij if self.gather is not None else \
+            torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def step(self):
+        """Device-resident step: match this rank's shard, gather the lists on rank 0."""
+        loff = self.m.match_pairs_compact(self.my_pairs, self.out_ij)
+        if self.world > 1:
+            return loff, self.gather.gather(loff)      # (flat, start, count) on rank 0
+        return loff, (self.out_ij, loff)
+
+    def timed_steps(self, steps, warmup):
+        torch = self.torch
+        for _ in range(warmup):
+            self.flush.fill_(1)
+            self.host_barrier()
+            self.step()
+        launches0 = self.m.stats()["kernel_launches"]
+        wall, dev_ms, sm_ghz = [], [], []
+        phase = {}
+        for _ in range(steps):
+            self.flush.fill_(1)          # evict the pool from L2 between timed iterations
+            self.host_barrier()
+            t0 = time.perf_counter()
+            self.step()
+            self.host_barrier()
+            wall.append(time.perf_counter() - t0)
+            st = self.m.stats()
+            dev_ms.append(st["last_total_ms"])
+            for k, v in st["last_phase_ms"].items():
+                phase.setdefault(k, []).append(v)
+            if st.get("last_scan_ns"):
+                sm_ghz.append(st["last_scan_sm_cycles"] / st["last_scan_ns"])
+        launches = self.m.stats()["kernel_launches"] - launches0
+        step_s = sum(wall) / len(wall)
+        phase_ms = {k: sum(v) / len(v) for k, v in phase.items()}
+        if self.world > 1:
+            t = torch.tensor([step_s, phase_ms["filter"], sum(dev_ms) / len(dev_ms)], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            step_s, filter_max, dev_max = float(t[0]), float(t[1]), float(t[2])
+            lt = torch.tensor([launches], device=self.dev, dtype=torch.int64)
+            self.dist.all_reduce(lt)
+            launches = int(lt[0])
+        else:
+            filter_max, dev_max = phase_ms["filter"], sum(dev_ms) / len(dev_ms)
+        return {"step_s": step_s, "phase_ms": phase_ms, "filter_ms_max": filter_max, "device_ms_max": dev_max,
+                "launches": launches, "sm_ghz": sm_ghz}
+
+    def sample_check(self, k=16):
+        """Gathered lists of k pairs spread over all ranks == the same pairs matched on ONE GPU (rank 0,
+        whole pool) == the reference matcher (oracle/_ref).  Rank 0 returns the verdicts."""
+        torch = self.torch
+        loff, gathered = self.step()
+        if self.rank != 0:
+            return None
+        idx = np.unique(np.linspace(0, self.npairs - 1, k).astype(np.int64))
+        if self.world > 1:
+            flat, start, count = gathered
+            got = [flat[start[p]:start[p] + count[p]].cpu().numpy() for p in idx]
+        else:
+            flat, off = gathered
+            got = [flat[off[p]:off[p + 1]].cpu().numpy() for p in idx]
+        # the same pairs in one call on this GPU alone
+        single = torch.empty((len(idx) * self.n, 2), dtype=torch.int32, device=self.dev)
+        soff = self.m.match_pairs_compact(self.pairs[idx], single)
+        one = [single[soff[i]:soff[i + 1]].cpu().numpy() for i in range(len(idx))]
+        equal_single = all(np.array_equal(a, b) for a, b in zip(got, one))
+        ranks = sorted({r for r in range(self.world) for p in idx if p in set(self.all_owned[r].tolist())}) \
+            if self.world > 1 else [0]
+        equal_ref = None
+        try:
+            import oracle
+            if oracle.have_ref():
+                ref = oracle.Reference()
+                sub = idx[np.unique(np.linspace(0, len(idx) - 1, 4).astype(np.int64))]
+                n = self.n
+
+                def check_pair(p):
+                    v1, v2 = self.pairs[p]
+                    a = self.pool[v1 * n:(v1 + 1) * n].cpu().numpy()
+                    b = self.pool[v2 * n:(v2 + 1) * n].cpu().numpy()
+                    g = got[int(np.nonzero(idx == p)[0][0])]
+                    if n <= 8192:       # the whole list (one core, about 3 s)
+                        o12 = ref.match_filtered("u8", a, b, 0.8)[0]
+                        i = np.nonzero(o12 >= 0)[0]
+                        return np.array_equal(g[:, 0], i) and np.array_equal(g[:, 1], o12[i]), len(i)
+                    # large views: sampled rows of view_1 through the reference's nearest-neighbour search
+                    # in both directions (a full pair costs minutes of CPU at these sizes)
+                    have = dict(zip(g[:, 0].tolist(), g[:, 1].tolist()))
+                    rng = np.random.default_rng(int(p))
+                    rows = np.unique(np.concatenate([rng.integers(0, n, 40), g[:24, 0]]))
+                    ok = True
+                    for r in rows:
+                        o = int(ref.twoway("u8", a[r:r + 1], b, 0.8)[0][0])
+                        back = int(ref.twoway("u8", b[o:o + 1], a, 0.8)[0][0]) if o >= 0 else -1
+                        ok = ok and have.get(int(r), -1) == (o if (o >= 0 and back == r) else -1)
+                    return ok, len(rows)
+                from concurrent.futures import ThreadPoolExecutor      # (ctypes releases the GIL)
+                with ThreadPoolExecutor(len(sub)) as ex:
+                    res = list(ex.map(check_pair, sub))
+                equal_ref = {"equal": bool(all(r[0] for r in res)), "pairs": int(len(sub)),
+                             "how": "whole lists" if n <= 8192 else f"{sum(r[1] for r in res)} sampled rows, both directions"}
+        except Exception as ex:  # noqa: BLE001
+            equal_ref = {"error": repr(ex)}
+        return {"pairs": int(len(idx)), "ranks_covered": len(ranks), "equal_single_gpu": bool(equal_single),
+                "equal_reference": equal_ref, "matches_in_sample": int(sum(len(g) for g in got))}
+
+    def close(self):
+        self.m.close()
+
+
+def e2e_multi(job, reps):
+    """N > 1, measured: rank 0 holds the descriptors in pinned host memory.  Every repetition:
+    H2D on rank 0, NCCL broadcast, every rank adopts the pool (norms), matches its shard, lists
+    gathered on rank 0 and copied to pinned host memory.  Wall clock on rank 0 between barriers."""
+    torch, dist = job.torch, job.dist
+    from orthosfm_b200 import ExhaustiveMatching
+    rows = job.num_views * job.n
+    host_pool = None
+    if job.rank == 0:
+        host_pool = torch.empty((rows, 128), dtype=torch.uint8, pin_memory=True)
+        host_pool.copy_(job.pool[:rows])
+    pool2 = torch.zeros_like(job.pool)
+    me = ExhaustiveMatching(device=job.dev.index)
+    host_lists = None
+    ts, d2h = [], 0
+    for it in range(reps + 1):
+        job.flush.fill_(1)
+        job.host_barrier()
+        t0 = time.perf_counter()
+        if job.rank == 0:
+            pool2[:rows].copy_(host_pool, non_blocking=True)
+        job.osd.broadcast_pool(pool2, src=0)
+        me.init_device_pool(pool2, job.offsets, job.sizes)
+        loff = me.match_pairs_compact(job.my_pairs, job.out_ij)
+        flat, start, count = job.gather.gather(loff)
+        if job.rank == 0:
+            used = job.gather.used_rows()
+            if host_lists is None or host_lists.shape[0] < used:
+                host_lists = torch.empty((int(used * 1.1) + 1024, 2), dtype=torch.int32, pin_memory=True)
+            job.gather.to_host(host_lists, start)
+            d2h = used * 8 + count.nbytes
+        job.host_barrier()
+        if it > 0:
+            ts.append(time.perf_counter() - t0)
+    me.close()
+    if job.rank != 0:
+        return None
+    s = sum(ts) / len(ts)
+    return {"value": job.total_cmp / s, "unit": UNIT, "h2d_bytes_per_step": int(rows * 128), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": 1e3 * s, "repetitions": len(ts),
+            "note": "measured on all ranks: H2D of the whole pool on rank 0 (pinned source), NCCL broadcast, "
+                    "osfm_match_commit_device on every rank, osfm_match_pairs_compact_device on every rank's shard, "
+                    "NCCL gather of the lists to rank 0, D2H into pinned memory; wall clock on rank 0 between barriers"}
+
+
+def e2e_single(job, steps):
+    """N = 1: host buffers in and out through the C ABI, every step."""
+    torch = job.torch
+    from orthosfm_b200 import ExhaustiveMatching, FeatureSet, PackedViews, Viewport
+    n, nv = job.n, job.num_views
+    views_np = job.views_np if job.views_np is not None else \
+        [job.pool[v * n:(v + 1) * n].cpu().numpy() for v in range(nv)]
+    host_views = [torch.from_numpy(v).pin_memory().numpy() for v in views_np]
+    me = ExhaustiveMatching(device=job.dev.index)
+    vps = [Viewport(FeatureSet(sift_descriptors=v)) for v in host_views]
+    packed = PackedViews(vps)        # pointer tables over the pinned descriptors, built once
+    h2d = sum(v.nbytes for v in host_views)
+    me.init(vps)
+    my_pairs = job.my_pairs
+    dense_host = torch.empty(me.pairs_result_size(my_pairs) + 16, dtype=torch.int32).pin_memory().numpy()
+    lists_host = torch.empty((len(my_pairs) * n // 4 + 4096, 2), dtype=torch.int32).pin_memory().numpy()
+    reps = 2 + min(steps, 10)
+
+    def timed(fn, init=lambda: me.init(packed, overlap_copies=True), reps=reps):
+        ts = []
+        for it in range(reps):
+            job.flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            init()                  # H2D of every view
+            r = fn()                # kernels + D2H of the results
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(time.perf_counter() - t0)
+        return sum(ts) / len(ts), r
+
+    # (a) the correspondence lists bundler::Matching::two_view_matching builds (bundler_matching.cc:178-192)
+    lists_s, loff_h = timed(lambda: me.match_pairs_lists(my_pairs, lists_host))
+    d2h_lists = int(loff_h[-1]) * 8 + loff_h.nbytes
+    # (b) the dense Matching::Result vectors of every pair
+    dense_s, (res, counts) = timed(lambda: me.match_pairs(my_pairs, dense_host))
+    d2h_dense = int(sum(r.matches_1_2.nbytes + r.matches_2_1.nbytes for r in res) + counts.nbytes)
+    lists_equal_dense = all(
+        np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 0], np.nonzero(res[p].matches_1_2 >= 0)[0]) and
+        np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 1], res[p].matches_1_2[res[p].matches_1_2 >= 0])
+        for p in range(0, len(my_pairs), 37))
+    e2e = {"value": job.my_cmp / lists_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": d2h_lists, "ms_per_step": 1e3 * lists_s,
+           "note": "osfm_match_begin_overlapped/set_views_q8/commit (H2D from pinned host memory, on its own stream; the early "
+                   "pairs are matched while the later views arrive) + osfm_match_pairs_compact "
+                   "(per-pair (i, j) correspondence lists to host memory).  The library's batched entry point with "
+                   "pre-quantised descriptors: an upper bound for a caller; the reference's own plugin entry is `plugin`",
+           "dense": {"value": job.my_cmp / dense_s, "ms_per_step": 1e3 * dense_s, "d2h_bytes_per_step": d2h_dense,
+                     "note": "same, osfm_match_pairs: the dense Matching::Result vectors of every pair"},
+           "lists_equal_dense_on_sample": bool(lists_equal_dense)}
+    # (c) what the reference's plugin interface does (bundler_matching.cc:51,74-132,162): init() with FLOAT
+    # descriptors in pageable memory (quantised on the device, convert_descriptor), then pairwise_match once per
+    # pair in compute()'s order, each returning its Matching::Result to the host
+    try:
+        floats = [(v.astype(np.float32) / 255.0) for v in views_np]
+        fvps = [Viewport(FeatureSet(sift_descriptors=f)) for f in floats]
+        h2d_f = sum(f.nbytes for f in floats)
+        plug = {}
+        for name, window in (("per_pair", 0), ("lookahead", len(my_pairs))):
+            def loop():
+                out = 0
+                for v1, v2 in my_pairs:
+                    out += int((me.pairwise_match(int(v1), int(v2)).matches_1_2 >= 0).sum())
+                return out
+
+            def init_float():
+                me.init(fvps)
+                me.set_lookahead(window)
+            s, nm = timed(loop, init_float, reps=4)
+            plug[name] = {"value": job.my_cmp / s, "ms_per_step": 1e3 * s, "matches": int(nm)}
+        me.set_lookahead(0)
+        plug["h2d_bytes_per_step"] = int(h2d_f)
+        plug["d2h_bytes_per_step"] = d2h_dense
+        plug["note"] = ("ExhaustiveMatching.init (osfm_match_set_view_f32: float descriptors from pageable memory, "
+                        "quantised on the device) + osfm_match_pair for every pair in bundler::Matching::compute's "
+                        "order.  per_pair: every call is its own launch sequence and D2H; lookahead: the first "
+                        "miss matches the following pairs of the reference's enumeration in one batch "
+                        "(osfm_match_set_lookahead) and later calls are served from that result")
+        e2e["plugin"] = plug
+    except Exception as ex:  # noqa: BLE001
+        e2e["plugin"] = {"error": repr(ex)}
+    return e2e, me, lists_host, loff_h, counts, views_np
+
+
+def run_ours(args, cfg, config):
     import torch
     import torch.distributed as dist
-
-    from orthosfm_b200 import ExhaustiveMatching, FeatureSet, PackedViews, Viewport, synth
-    from orthosfm_b200 import distributed as osd
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -279,212 +608,138 @@ def run_ours(args, config):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    num_views = config["views"]
-    n = N_DESC
-    pairs = synth.all_pairs(num_views)
-    npairs = len(pairs)
-    sizes = np.full(num_views, n, np.int32)
-    offsets = np.arange(num_views, dtype=np.int64) * n
-
-    # ---- descriptor pool: generated once on rank 0, replicated by one broadcast ----------
-    pool = torch.zeros((num_views * n + 256, 128), dtype=torch.uint8, device=dev)
-    views_np = None
-    if rank == 0:
-        views_np = make_views_numpy(num_views, n)
-        pool[:num_views * n] = torch.from_numpy(np.concatenate(views_np)).to(dev)
-    torch.cuda.synchronize()
-    t_b = time.perf_counter()
-    osd.broadcast_pool(pool, src=0)
-    torch.cuda.synchronize()
-    broadcast_ms = 1e3 * (time.perf_counter() - t_b)
-
-    all_owned = osd.partition_pairs(pairs, sizes, world)
-    owned = all_owned[rank]
-    my_pairs = pairs[owned]
-    my_cmp = int(len(my_pairs)) * n * n
-
-    m = ExhaustiveMatching(device=local_rank)
-    m.init_device_pool(pool, offsets, sizes)
-    cap = int(max(len(o) for o in all_owned) * n * 0.25) + 4096
-    fixed = osd.FixedGather(all_owned, npairs, cap, dev, dst=0) if world > 1 else None
-    out_ij = fixed.out_ij if fixed is not None else torch.empty((cap, 2), dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
-        loff = m.match_pairs_compact(my_pairs, out_ij)
-        if world > 1:
-            flat, start, count = fixed.gather(loff)      # one NCCL gather to rank 0
-            gathered = (flat, None if count is None else np.concatenate([[0], np.cumsum(count)]))
-        else:
-            gathered = (out_ij, loff)
-        return loff, gathered
-
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        barrier()
-        loff, gathered = step()
-    total_matches = int(gathered[1][-1]) if rank == 0 else 0
-
-    launches0 = m.stats()["kernel_launches"]
-    wall, scan_ms, dev_ms, sm_ghz = [], [], [], []
+    job = Job(cfg, dev, rank, world, local_rank, NOISE)
+    n, npairs = job.n, job.npairs
+    warmup = max(args.warmup, 3)
     t_region0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)          # evict the pool from L2 between timed iterations
-        barrier()
-        t0 = time.perf_counter()
-        step()
-        barrier()
-        wall.append(time.perf_counter() - t0)
-        st = m.stats()
-        scan_ms.append(st["last_scan_ms"])
-        dev_ms.append(st["last_total_ms"])
-        if st.get("last_scan_ns"):
-            sm_ghz.append(st["last_scan_sm_cycles"] / st["last_scan_ns"])
+    r = job.timed_steps(args.steps, warmup)
     t_region1 = time.perf_counter()
     clocks = sampler.stop(t_region0, t_region1)
-    if sm_ghz:
+    if r["sm_ghz"]:
         # clock64 / globaltimer inside the scan kernel: the SM clock the kernel really ran at
-        clocks["sm_mhz_in_scan_kernel"] = round(1e3 * statistics.median(sm_ghz), 1)
-    launches = m.stats()["kernel_launches"] - launches0
-
-    step_s = sum(wall) / len(wall)
-    if world > 1:
-        t = torch.tensor([step_s, float(sum(scan_ms) / len(scan_ms))], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_s, scan_avg_ms = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt[0])
-    else:
-        scan_avg_ms = sum(scan_ms) / len(scan_ms)
-    total_cmp = npairs * n * n
-    value = total_cmp / step_s
+        clocks["sm_mhz_in_scan_kernel"] = round(1e3 * statistics.median(r["sm_ghz"]), 1)
+    step_s = r["step_s"]
+    value = job.total_cmp / step_s
+    check = job.sample_check(16)
 
     # ---- the int8 tensor pipe's own ceiling on this box: the same launch with the epilogue
     # reduced to handing the accumulators back (debug scan mode 1: TMA + tcgen05.mma only) ----
     mma_only_ms = None
+    both_ms = None
     if world == 1:
         try:
-            m.debug_set_scan_mode(1)
+            job.m.debug_set_scan_mode(1)
             ts = []
-            for _ in range(5):
-                flush.fill_(1)
+            for _ in range(4):
+                job.flush.fill_(1)
                 torch.cuda.synchronize()
                 try:
-                    m.match_pairs_compact(my_pairs, out_ij)
+                    job.m.match_pairs_compact(job.my_pairs, job.out_ij)
                 except Exception:  # noqa: BLE001  -- results are meaningless in this mode
                     pass
-                ts.append(m.stats()["last_scan_ms"])
+                ts.append(job.m.stats()["last_phase_ms"]["filter"])
             mma_only_ms = min(ts[1:])
         finally:
-            m.debug_set_scan_mode(0)
-        m.match_pairs_compact(my_pairs, out_ij)      # leave the handle with a real result
+            job.m.debug_set_scan_mode(0)
+        # A/B: both directions of every pair through the filter pass, as round 1 did
+        job.m.debug_set_both_directions(True)
+        ts = []
+        for _ in range(4):
+            job.flush.fill_(1)
+            torch.cuda.synchronize()
+            job.m.match_pairs_compact(job.my_pairs, job.out_ij)
+            ts.append(job.m.stats()["last_total_ms"])
+        both_ms = min(ts[1:])
+        job.m.debug_set_both_directions(False)
+        job.m.match_pairs_compact(job.my_pairs, job.out_ij)      # leave the handle with a real result
 
-    # ---- e2e through the host API (HOST buffers in, HOST results out) ---------------------
-    e2e = None
-    cpu_base = None
-    check = None
-    if rank == 0:
-        # every rank would do the same with its shard; measured on rank 0's shard for N > 1
-        host_views = [torch.from_numpy(v).pin_memory().numpy() for v in views_np]
-        me = ExhaustiveMatching(device=local_rank)
-        vps = [Viewport(FeatureSet(sift_descriptors=v)) for v in host_views]
-        packed = PackedViews(vps)        # pointer tables over the pinned descriptors, built once
-        h2d = sum(v.nbytes for v in host_views)
-        res = counts = None
-        me.init(vps)
-        dense_host = torch.empty(me.pairs_result_size(my_pairs) + 16, dtype=torch.int32).pin_memory().numpy()
-        lists_host = torch.empty((len(my_pairs) * n // 4 + 4096, 2), dtype=torch.int32).pin_memory().numpy()
-        reps = 2 + min(args.steps, 10)
-
-        def timed(fn):
-            ts = []
-            for it in range(reps):
-                flush.fill_(1)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                me.init(packed, overlap_copies=True)   # begin_overlapped / set_views_q8 / commit: H2D of every view (pinned source)
-                r = fn()                # kernels + D2H of the results
-                torch.cuda.synchronize()
-                if it >= 2:
-                    ts.append(time.perf_counter() - t0)
-            return sum(ts) / len(ts), r
-
-        # (a) the correspondence lists bundler::Matching::two_view_matching builds (bundler_matching.cc:178-192)
-        lists_s, loff_h = timed(lambda: me.match_pairs_lists(my_pairs, lists_host))
-        d2h_lists = int(loff_h[-1]) * 8 + loff_h.nbytes
-        # (b) the dense Matching::Result vectors of every pair
-        dense_s, (res, counts) = timed(lambda: me.match_pairs(my_pairs, dense_host))
-        d2h_dense = int(sum(r.matches_1_2.nbytes + r.matches_2_1.nbytes for r in res) + counts.nbytes)
-        lists_equal_dense = all(
-            np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 0], np.nonzero(res[p].matches_1_2 >= 0)[0]) and
-            np.array_equal(lists_host[loff_h[p]:loff_h[p + 1], 1], res[p].matches_1_2[res[p].matches_1_2 >= 0])
-            for p in range(0, len(my_pairs), 37))
-        scale = 1 if world == 1 else world
-        e2e = {"value": my_cmp * scale / lists_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": d2h_lists, "ms_per_step": 1e3 * lists_s,
-               "note": "osfm_match_begin_overlapped/set_views_q8/commit (H2D from pinned host memory, on its own stream; the early "
-                       "pairs are matched while the later views arrive) + osfm_match_pairs_compact "
-                       "(per-pair (i, j) correspondence lists to host memory)"
-                       + ("" if world == 1 else "; rank 0's shard, scaled by the number of ranks"),
-               "dense": {"value": my_cmp * scale / dense_s, "ms_per_step": 1e3 * dense_s, "d2h_bytes_per_step": d2h_dense,
-                         "note": "same, osfm_match_pairs: the dense Matching::Result vectors of every pair"},
-               "lists_equal_dense_on_sample": bool(lists_equal_dense)}
-        downstream = downstream_rows(me, my_pairs, n, len(views_np), lists_host, loff_h) if world == 1 else None
+    # ---- e2e (HOST buffers in, HOST results out), measured -----------------------------------
+    e2e = cpu_base = ref_check = downstream = None
+    if world == 1:
+        e2e, me, lists_host, loff_h, counts, views_np = e2e_single(job, args.steps)
+        if cfg == 2:
+            downstream = downstream_rows(me, job.my_pairs, n, job.num_views, lists_host, loff_h)
         me.close()
-        # ---- CPU baseline + result check on the sampled pairs ----------------------------
-        cpu_base, ref_counts = cpu_baseline_sample(views_np, my_pairs)
+        cpu_base, ref_counts = cpu_baseline_sample(views_np, job.my_pairs)
         k = len(ref_counts)
-        check = bool(np.array_equal(np.asarray(counts[:k]), np.asarray(ref_counts)))
+        ref_check = bool(np.array_equal(np.asarray(counts[:k]), np.asarray(ref_counts)))
+    else:
+        e2e = e2e_multi(job, 2 if cfg >= 4 else 3)
+
+    final_stats = job.m.stats()
+    # ---- config 3 under an extra key at N = 1 and N = 8, so the strong-scaling curve is like for like
+    extra3 = None
+    if cfg != 3 and world in (1, 8) and not os.environ.get("OSFM_BENCH_NO_CONFIG3"):
+        job.close()
+        del job.pool, job.out_ij, job.gather
+        torch.cuda.empty_cache()
+        j3 = Job(3, dev, rank, world, local_rank, NOISE)
+        r3 = j3.timed_steps(3, 1)
+        c3 = j3.sample_check(8)
+        extra3 = {"workload": describe(3, world, NOISE)["workload"], "value": j3.total_cmp / r3["step_s"], "unit": UNIT,
+                  "ms_per_step": 1e3 * r3["step_s"], "steps": 3, "warmup": 1, "pairs_per_s": j3.npairs / r3["step_s"],
+                  "filter_ms": r3["filter_ms_max"], "lists_equal_single_gpu_on_sample": c3, "broadcast_ms": j3.broadcast_ms}
+        j3.close()
 
     pk = peaks()
-    achieved_tops = (my_cmp * OPS_PER_COMPARISON) / (scan_avg_ms * 1e-3) / 1e12
+    filter_ms = r["filter_ms_max"]
+    achieved_tops = (job.my_cmp * OPS_PER_COMPARISON) / (filter_ms * 1e-3) / 1e12
+    tp = traffic_profile() or {}
+    step_tops = job.total_cmp * OPS_PER_COMPARISON / step_s / 1e12 / world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * step_s, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "warmup": warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config,
         "pairs_per_s": npairs / step_s,
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": pk["bf16_burst"],
-                     "unit": "TFLOP/s", "frac": achieved_tops / pk["bf16_burst"],
-                     "traffic": (measured_traffic() or {}).get("dram_bytes_per_launch") if world == 1 else None,
-                     "traffic_note": "dram read + write bytes of one launch on this workload (ncu --set full, "
-                                     "profiles/r01_traffic.json); algorithmic: 37.7 MB pool + 82.6 MB row results",
-                     "tensor_pipe_active_pct_ncu": (measured_traffic() or {}).get("tensor_pipe_active_pct"),
-                     "kernel": "scan_kernel<0,0,0>: filter pass (tcgen05.mma kind::i8 + fused 16-bit packed top-2 filter epilogue)",
-                     "peak_source": pk["source"] + ", dense bf16 burst; the kernel computes both "
-                                    "match directions, achieved counts each unique comparison once (256 OP)",
-                     "kernel_ms": scan_avg_ms, "frac_of_sustained": achieved_tops / pk["bf16_sustained"],
-                     # the same launch as the int8 pipe sees it: both directions are executed
-                     "executed_tops": 2.0 * achieved_tops,
-                     "int8_dense_nominal_tops": 4500.0,
-                     "frac_of_int8_nominal": 2.0 * achieved_tops / 4500.0,
-                     # measured on this box in this run: the same launch without the epilogue's work
-                     "int8_mma_only_ms": mma_only_ms,
-                     "int8_mma_only_tops": (2.0 * my_cmp * OPS_PER_COMPARISON / (mma_only_ms * 1e-3) / 1e12
-                                            if mma_only_ms else None),
-                     "frac_of_int8_mma_only": (mma_only_ms / scan_avg_ms) if mma_only_ms else None},
+        "gpu_launches": int(r["launches"]),
+        "roofline": {
+            "bound": "tensor", "achieved": achieved_tops, "peak": INT8_DENSE_NOMINAL_TOPS, "unit": "TFLOP/s",
+            "frac": achieved_tops / INT8_DENSE_NOMINAL_TOPS,
+            "kernel": "scan_kernel<0,0,0>: filter pass (tcgen05.mma kind::i8 u8 x u8 -> s32, ONE product per pair, "
+                      "fused 16-bit packed top-2 filter epilogue)",
+            "kernel_ms": filter_ms,
+            "kernel_ms_source": "CUDA events recorded by the library on its stream around this launch, averaged over "
+                                "the timed steps" + ("" if world == 1 else ", max over ranks"),
+            "peak_source": "nominal dense int8 tensor peak of B200 (4500 TOP/s = 2 x the nominal bf16 figure; "
+                           "MEASURED_PEAKS.json has no int8 entry).  achieved = ALGORITHMIC work: sum n1*n2 x 256 OP, "
+                           "each unique comparison once, which is also what the kernel executes",
+            "int8_mma_only_ms": mma_only_ms,
+            "int8_mma_only_tops": (job.my_cmp * OPS_PER_COMPARISON / (mma_only_ms * 1e-3) / 1e12 if mma_only_ms else None),
+            "frac_of_int8_mma_only": (mma_only_ms / filter_ms) if mma_only_ms else None,
+            "int8_mma_only_note": "measured in this run: the same launch with the epilogue reduced to handing the "
+                                  "accumulators back (TMA + tcgen05.mma only)",
+            "frac_of_bf16_measured": achieved_tops / pk["bf16_burst"],
+            "bf16_peak": pk["bf16_burst"], "bf16_peak_source": pk["source"] + ", dense bf16 burst",
+            "whole_step_tops_per_gpu": step_tops, "whole_step_frac": step_tops / INT8_DENSE_NOMINAL_TOPS,
+            "traffic": tp.get("dram_bytes_per_launch") if world == 1 and cfg == 2 else None,
+            "traffic_source": (f"from_profile: {tp.get('file')} (ncu --set full capture of this kernel on this workload, "
+                               "not measured in this run); algorithmic: 37.7 MB pool + 41 MB row results"
+                               if tp and world == 1 and cfg == 2 else None),
+            "tensor_pipe_active_pct_from_profile": tp.get("tensor_pipe_active_pct") if world == 1 and cfg == 2 else None,
+        },
+        "phase_ms": {k: round(v, 4) for k, v in r["phase_ms"].items()},
+        "phase_ms_note": "CUDA events inside the library, this rank, averaged over the timed steps: filter pass; "
+                         "classify + certify; RESOLVE / EXACT of the forward direction; claims; RESOLVE / EXACT of the "
+                         "claimed rows of the reverse direction; mutual filter; list compaction",
+        "both_directions_device_ms": both_ms,
         "cpu_baseline": cpu_base,
-        "device_ms_per_step": sum(dev_ms) / len(dev_ms),
-        "matches_per_step": total_matches,
-        "matches_equal_reference_on_sample": check,
-        "broadcast_ms": broadcast_ms,
-        "downstream": downstream if rank == 0 and world == 1 else None,
-        "stats": dict({k: v for k, v in m.stats().items()
-                       if k in ("candidate_rows", "slow_rows", "exact_rows", "self_check_failures")},
-                      rows_per_step=int(2 * my_cmp // n), steps_counted=max(args.warmup, 3) + args.steps),
+        "device_ms_per_step": r["device_ms_max"],
+        "lists_equal_single_gpu_on_sample": check,
+        "matches_equal_reference_on_sample": ref_check,
+        "broadcast_ms": job.broadcast_ms,
+        "config3": extra3,
+        "downstream": downstream,
+        "stats": {k: v for k, v in final_stats.items()
+                  if k in ("candidate_rows", "slow_rows", "exact_rows", "claimed_rows", "self_check_failures")} | {
+            "rows_per_step": int(2 * job.my_cmp // n), "steps_counted": warmup + args.steps},
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
-    m.close()
+    if extra3 is None:
+        job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -504,19 +759,12 @@ def main():
     NOISE = args.noise
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ngpu = max(args.gpus, world)
-    views = VIEWS_FOR_GPUS.get(ngpu) or int(round((1 + (1 + 8 * 630 * ngpu) ** 0.5) / 2))
-    config = {
-        "workload": (f"{views} images x {N_DESC} SIFT descriptors (128-d u8), all {views * (views - 1) // 2} "
-                     f"pairs, two-way match + ratio test 0.8 + mutual filter"
-                     + (" [BASELINE config 2]" if ngpu == 1 else f" [config 2 per-GPU load x {ngpu} GPUs]")),
-        "views": views, "descriptors_per_view": N_DESC, "pairs": views * (views - 1) // 2,
-        "planted_fraction": 0.25, "planted_noise": args.noise, "l2": "flushed between timed steps (256 MB write)",
-        "parallelism": f"pairs sharded over {ngpu} GPU(s), pool replicated",
-    }
+    cfg = config_for_gpus(ngpu)
+    config = describe(cfg, ngpu, args.noise)
     if args.impl == "reference":
-        run_reference_arm(args, config)
+        run_reference_arm(args, cfg, config)
     else:
-        run_ours(args, config)
+        run_ours(args, cfg, config)
 
 
 if __name__ == "__main__":

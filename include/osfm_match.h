@@ -155,6 +155,17 @@ int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id,
     int32_t* matches_1_2, int* len_1_2, int32_t* matches_2_1, int* len_2_1,
     int* n_consistent);
 
+/* Look-ahead for callers that ask pair by pair, as the unchanged reference does: the loop of
+ * bundler::Matching::compute (bundler_matching.cc:74-132) calls pairwise_match_lowres /
+ * pairwise_match once per pair, in the order i -> (view_1, view_2) of bundler_matching.cc:92-93.
+ * With max_pairs > 1, an osfm_match_pair(view_1 > view_2) call whose pair is not cached
+ * matches that pair AND the max_pairs - 1 pairs that follow it in this order in one batched pass
+ * (dense results kept in pinned host memory, at most 1 GiB); the calls that follow are served
+ * from it.  osfm_match_pair_lowres does the same with a window of 16 x max_pairs.  Results are
+ * identical; pairs the caller skips (its low-res gate) were matched for nothing.  0 (default): off.
+ * The cache is dropped by osfm_match_begin* / osfm_match_commit_device. */
+int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs);
+
 /* Replaces Matching::twoway_match<T> (matching.h:148-159) for one feature kind:
  * both one-way results WITHOUT the mutual filter.  matches_1_2 has n1 entries
  * of that kind, matches_2_1 n2. */
@@ -375,6 +386,10 @@ typedef struct {
     int64_t last_scan_ns;        /* its duration in ns (globaltimer): cycles/ns = SM clock in GHz */
     int64_t claimed_rows;        /* rows of the reverse direction of a pair that some forward match claims
                                     (the only rows of that direction that are evaluated), cumulative */
+    double  last_phase_ms[8];    /* CUDA-event time of the last batched call per phase, summed over its
+                                    batches: [0] filter pass, [1] classify + certify, [2] RESOLVE / EXACT of
+                                    the forward direction, [3] claims + targets, [4] RESOLVE / EXACT of the
+                                    claimed rows, [5] mutual filter, [6] list compaction, [7] unused */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);

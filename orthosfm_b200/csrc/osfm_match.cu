@@ -103,6 +103,37 @@ struct PairPlan {
     int len12, len21;
 };
 
+// Device time per phase of a batched call: events recorded on the handle's stream between the
+// phases, read after the call's synchronisations (osfm_match_stats::last_phase_ms).
+enum Phase { kPhFilter = 0, kPhClassify, kPhResolveFwd, kPhClaim, kPhResolveRev, kPhMutual, kPhCompact, kPhCount };
+struct PhaseTimer {
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> phase;          // phase that starts at event i (-1: untimed)
+    double acc[kPhCount] = {0, 0, 0, 0, 0, 0, 0};
+    cudaError_t mark(cudaStream_t s, int ph) {
+        if (phase.size() == pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            pool.push_back(e);
+        }
+        cudaError_t r = cudaEventRecord(pool[phase.size()], s);
+        if (r == cudaSuccess) phase.push_back(ph);
+        return r;
+    }
+    // all marks must have completed (call after synchronising the stream)
+    void collect() {
+        for (size_t i = 0; i + 1 < phase.size(); ++i) {
+            if (phase[i] < 0) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) == cudaSuccess) acc[phase[i]] += ms;
+        }
+        phase.clear();
+    }
+    void reset() { phase.clear(); for (double& a : acc) a = 0.0; }
+    void release() { for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear(); phase.clear(); }
+};
+
 }  // namespace
 
 struct osfm_matcher {
@@ -180,10 +211,23 @@ struct osfm_matcher {
     } pass[2];
     unsigned long long* d_counters = nullptr;  // see PostParams::counters
 
+    // Look-ahead for the pair-by-pair plugin loop (osfm_match_set_lookahead): dense results / low-res
+    // counts of a window of pairs in the reference's enumeration order, kept in pinned host memory.
+    int lookahead = 0;
+    struct PairCache {
+        int64_t first = -1;               // flat pair index of the first cached pair (-1: empty)
+        int count = 0;
+        int num_features = 0;             // low-res cache: the feature limit it was computed with
+        std::vector<int64_t> offsets;     // dense cache: 2 * count + 1
+        std::vector<int32_t> counts;
+        int32_t* host = nullptr;          // dense cache: pinned
+        size_t host_cap = 0;              // ints
+        void clear() { first = -1; count = 0; }
+    } cache_full, cache_lowres;
+
     int scan_mode = 0;
     bool both_directions = false;     // debug / A-B switch: run both directions through the filter
-    double scan_ms_acc = 0.0;
-    bool scan_time_pending = false;   // ev[0], ev[1] of the last run_jobs not yet read
+    PhaseTimer phases;
     osfm_match_stats stats;
 };
 
@@ -546,7 +590,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     float const sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
     float const sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
 
-    CU_TRY(m, cudaEventRecord(m->ev[0], m->stream));
+    CU_TRY(m, m->phases.mark(m->stream, kPhFilter));
     cudaError_t e = cudaSuccess;
     if (items > 0) {
         switch (dump ? dump_mode : m->scan_mode) {
@@ -560,9 +604,16 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
         m->stats.kernel_launches++;
     }
-    CU_TRY(m, cudaEventRecord(m->ev[1], m->stream));
+    CU_TRY(m, m->phases.mark(m->stream, kPhClassify));
     m->stats.scan_items += items;
-    if (dump) return OSFM_OK;   // debug dumps produce no results
+    if (dump) { CU_TRY(m, m->phases.mark(m->stream, -1)); return OSFM_OK; }   // debug dumps produce no results
+    if (m->scan_mode != 0) {
+        // timing modes: the filter wrote no row records, so nothing downstream may look at them;
+        // every row reports "no match"
+        CU_TRY(m, cudaMemsetAsync(m->d_oneway.p, 0xff, sizeof(int32_t) * rows, m->stream));
+        CU_TRY(m, m->phases.mark(m->stream, -1));
+        return OSFM_OK;
+    }
 
     ClassifyParams cp;
     cp.jobs = m->d_jobs.p;
@@ -623,11 +674,13 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
             if (e != cudaSuccess) return cuda_fail(m, e, "certify_kernel launch");
             m->stats.kernel_launches++;
         }
+        CU_TRY(m, m->phases.mark(m->stream, kPhResolveFwd));
         OS_TRY(second_passes(false));
     }
 
     if (have_reverse) {
         // the forward results are final: which rows of the other view do they claim?
+        CU_TRY(m, m->phases.mark(m->stream, kPhClaim));
         int64_t const rev_rows = rows - fwd_rows;
         CU_TRY(m, cudaMemsetAsync(m->d_oneway.p + fwd_rows, 0xff, sizeof(int32_t) * rev_rows, m->stream));
         CU_TRY(m, cudaMemsetAsync(m->d_rowres.p + fwd_rows, 0xff, sizeof(int2) * rev_rows, m->stream));
@@ -656,22 +709,25 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         }
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches += 2;
+        CU_TRY(m, m->phases.mark(m->stream, kPhResolveRev));
         OS_TRY(second_passes(true));
     }
+    CU_TRY(m, m->phases.mark(m->stream, -1));
 
-    // Scan time of this launch; read after the caller's next synchronisation.
-    // (cudaEventElapsedTime needs completed events, so we synchronise on ev[1] lazily in
-    // collect_scan_time().)
     return OSFM_OK;
 }
 
+// Adds up the phase times recorded so far; the stream must have been synchronised.
 int collect_scan_time(osfm_matcher* m) {
-    if (!m->scan_time_pending) return OSFM_OK;
-    m->scan_time_pending = false;
-    if (cudaEventQuery(m->ev[1]) == cudaErrorNotReady) CU_TRY(m, cudaEventSynchronize(m->ev[1]));
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->scan_ms_acc += ms;
+    m->phases.collect();
     return OSFM_OK;
+}
+
+void publish_phase_times(osfm_matcher* m) {
+    m->phases.collect();
+    for (int i = 0; i < kPhCount; ++i) m->stats.last_phase_ms[i] = m->phases.acc[i];
+    m->stats.last_phase_ms[kPhCount] = 0.0;
+    m->stats.last_scan_ms = m->phases.acc[kPhFilter];
 }
 
 int check_view(osfm_matcher* m, int v) {
@@ -737,9 +793,7 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
         // the previous kind's scan time has to be read before its events are recorded again;
         // everything else the two kinds share is ordered by the stream.  No host round trip
         // after the last kind: the caller synchronises once, after queueing its own copies.
-        OS_TRY(collect_scan_time(m));
         OS_TRY(run_jobs(m, kd, specs, out_row));
-        m->scan_time_pending = true;
         parts.clear();
         int max_n = 0;
         for (int i = 0; i < np; ++i) {
@@ -767,11 +821,13 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
                                   cudaMemcpyHostToDevice, m->stream));
         dim3 const grid(static_cast<unsigned>(parts.size()),
                         static_cast<unsigned>((max_n + kMutualChunk - 1) / kMutualChunk));
+        CU_TRY(m, m->phases.mark(m->stream, kPhMutual));
         if (mode == kFiltered)
             mutual_kernel<<<grid, 256, 0, m->stream>>>(m->d_parts.p, m->d_oneway.p, m->d_dense.p, m->d_counts.p);
         else
             copy_twoway_kernel<<<grid, 256, 0, m->stream>>>(m->d_parts.p, m->d_oneway.p, m->d_dense.p);
         CU_TRY(m, cudaGetLastError());
+        CU_TRY(m, m->phases.mark(m->stream, -1));
         m->stats.kernel_launches++;
     }
     return OSFM_OK;
@@ -967,6 +1023,8 @@ void osfm_match_destroy(osfm_matcher* m) {
         cudaMemcpyToSymbol(g_hang_report, &null_ptr, sizeof null_ptr);
         cudaFreeHost(m->hang_host);
     }
+    m->phases.release();
+    if (m->cache_full.host) cudaFreeHost(m->cache_full.host);
     for (auto& ev : m->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : m->view_ev) if (ev) cudaEventDestroy(ev);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -992,6 +1050,8 @@ static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
     m->num_views = num_views;
     m->began = true;
     m->committed = false;
+    m->cache_full.clear();
+    m->cache_lowres.clear();
     m->overlap = overlap;
     m->lazy = false;
     if (overlap) {
@@ -1219,6 +1279,8 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
     m->num_views = num_views;
     m->began = true;
     m->committed = true;
+    m->cache_full.clear();
+    m->cache_lowres.clear();
     return OSFM_OK;
 }
 
@@ -1261,7 +1323,7 @@ int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int 
 static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, OutputMode mode, int only_kind,
                              int32_t* matches, int64_t* offsets, int32_t* n_consistent) {
     CU_TRY(m, cudaSetDevice(m->device));
-    m->scan_ms_acc = 0.0;
+    m->phases.reset();
     CU_TRY(m, cudaEventRecord(m->ev[2], m->stream));
     int64_t host_base = 0;
     int r = for_each_batch(plans, [&](size_t first, size_t last, int64_t dense) -> int {
@@ -1290,7 +1352,7 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
     float ms = 0.f;
     cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]);
     m->stats.last_total_ms = ms;
-    m->stats.last_scan_ms = m->scan_ms_acc;
+    publish_phase_times(m);
     m->stats.last_comparisons = comparisons_of(plans);
     OS_TRY(finish_staging(m));
     return read_counters(m);
@@ -1306,11 +1368,80 @@ int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t*
     return match_pairs_dense(m, plans, kFiltered, -1, matches, offsets, n_consistent);
 }
 
+// The window of pairs that follows (view_1, view_2) in the reference's enumeration
+// (bundler_matching.cc:92-93: i -> view_1 = (int)(0.5 + sqrt(0.25 + 2 i)), view_2 = i - view_1 (view_1 - 1) / 2,
+// i.e. view_1 ascending, view_2 = 0 .. view_1 - 1), at most `limit` pairs.
+static void lookahead_window(int num_views, int v1, int v2, int limit, std::vector<int32_t>& pairs) {
+    pairs.clear();
+    for (int a = v1; a < num_views && static_cast<int>(pairs.size()) < 2 * limit; ++a)
+        for (int b = (a == v1 ? v2 : 0); b < a && static_cast<int>(pairs.size()) < 2 * limit; ++b) {
+            pairs.push_back(a);
+            pairs.push_back(b);
+        }
+}
+
+static int64_t flat_pair_index(int v1, int v2) { return static_cast<int64_t>(v1) * (v1 - 1) / 2 + v2; }
+
+int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs) {
+    if (!m || max_pairs < 0) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->lookahead = max_pairs;
+    m->cache_full.clear();
+    m->cache_lowres.clear();
+    return OSFM_OK;
+}
+
+// Serves osfm_match_pair from the look-ahead cache, filling it first if (view_1, view_2) is not in it.
+static int pair_from_lookahead(osfm_matcher* m, int v1, int v2, int32_t* matches_1_2, int* len_1_2,
+                               int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
+    osfm_matcher::PairCache& c = m->cache_full;
+    int64_t const idx = flat_pair_index(v1, v2);
+    if (c.first < 0 || idx < c.first || idx >= c.first + c.count) {
+        constexpr int64_t kMaxCacheInts = 1ll << 28;     // 1 GiB of pinned host memory at most
+        std::vector<int32_t> pairs;
+        lookahead_window(m->num_views, v1, v2, m->lookahead, pairs);
+        std::vector<PairPlan> plans;
+        OS_TRY(build_plans(m, pairs.data(), static_cast<int>(pairs.size() / 2), 0, false, plans));
+        int64_t total = 0;
+        size_t keep = 0;
+        for (; keep < plans.size(); ++keep) {
+            int64_t const d = static_cast<int64_t>(plans[keep].len12) + plans[keep].len21;
+            if (keep > 0 && total + d > kMaxCacheInts) break;
+            total += d;
+        }
+        plans.resize(keep);
+        c.clear();
+        if (static_cast<size_t>(total) + 1 > c.host_cap) {
+            CU_TRY(m, cudaSetDevice(m->device));
+            if (c.host) cudaFreeHost(c.host);
+            c.host = nullptr; c.host_cap = 0;
+            size_t const want = static_cast<size_t>(total) + static_cast<size_t>(total) / 8 + 1024;
+            CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&c.host), want * sizeof(int32_t), cudaHostAllocDefault));
+            c.host_cap = want;
+        }
+        c.offsets.assign(2 * plans.size() + 1, 0);
+        c.counts.assign(plans.size(), 0);
+        OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, c.host, c.offsets.data(), c.counts.data()));
+        c.first = idx;
+        c.count = static_cast<int>(plans.size());
+    }
+    size_t const k = static_cast<size_t>(idx - c.first);
+    int64_t const o12 = c.offsets[2 * k], o21 = c.offsets[2 * k + 1], end = c.offsets[2 * k + 2];
+    if (matches_1_2 && o21 > o12) memcpy(matches_1_2, c.host + o12, sizeof(int32_t) * (o21 - o12));
+    if (matches_2_1 && end > o21) memcpy(matches_2_1, c.host + o21, sizeof(int32_t) * (end - o21));
+    if (len_1_2) *len_1_2 = static_cast<int>(o21 - o12);
+    if (len_2_1) *len_2_1 = static_cast<int>(end - o21);
+    if (n_consistent) *n_consistent = c.counts[k];
+    return OSFM_OK;
+}
+
 int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id, int32_t* matches_1_2, int* len_1_2,
                     int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
+    if (m->lookahead > 1 && view_1_id > view_2_id && view_2_id >= 0 && view_1_id < m->num_views)
+        return pair_from_lookahead(m, view_1_id, view_2_id, matches_1_2, len_1_2, matches_2_1, len_2_1, n_consistent);
     int32_t pr[2] = {view_1_id, view_2_id};
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pr, 1, 0, false, plans));
@@ -1357,6 +1488,26 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     if (num_features == 0 || num_features > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad num_features");
+    if (m->lookahead > 1 && view_1_id > view_2_id && view_2_id >= 0 && view_1_id < m->num_views) {
+        // the low-res gate is cheap (500 x 500 per pair): a window of 16 x the look-ahead
+        osfm_matcher::PairCache& c = m->cache_lowres;
+        int64_t const idx = flat_pair_index(view_1_id, view_2_id);
+        if (c.first < 0 || c.num_features != static_cast<int>(num_features) || idx < c.first || idx >= c.first + c.count) {
+            std::vector<int32_t> pairs;
+            int const limit = static_cast<int>(std::min<int64_t>(16ll * m->lookahead, 1 << 20));
+            lookahead_window(m->num_views, view_1_id, view_2_id, limit, pairs);
+            std::vector<PairPlan> plans;
+            OS_TRY(build_plans(m, pairs.data(), static_cast<int>(pairs.size() / 2), static_cast<int>(num_features), true, plans));
+            c.clear();
+            c.counts.assign(plans.size(), 0);
+            OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, c.counts.data()));
+            c.first = idx;
+            c.count = static_cast<int>(plans.size());
+            c.num_features = static_cast<int>(num_features);
+        }
+        if (n_consistent) *n_consistent = c.counts[static_cast<size_t>(idx - c.first)];
+        return OSFM_OK;
+    }
     int32_t pr[2] = {view_1_id, view_2_id};
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pr, 1, static_cast<int>(num_features), true, plans));
@@ -1443,7 +1594,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
             p.len12 = p.n1[0]; p.len21 = p.n2[0];
         }
     CU_TRY(m, cudaSetDevice(m->device));
-    m->scan_ms_acc = 0.0;
+    m->phases.reset();
     CU_TRY(m, cudaEventRecord(m->ev[2], m->stream));
     int64_t list_base = 0;
     bool overflow = false;
@@ -1481,9 +1632,11 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
         CU_TRY(m, m->d_parts.reserve(parts.size()));
         CU_TRY(m, cudaMemcpyAsync(m->d_listoff.p, loff.data(), sizeof(int64_t) * np, cudaMemcpyHostToDevice, m->stream));
         CU_TRY(m, cudaMemcpyAsync(m->d_parts.p, parts.data(), sizeof(PairPart) * parts.size(), cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, m->phases.mark(m->stream, kPhCompact));
         compact_kernel<<<static_cast<unsigned>(parts.size()), 1024, 0, m->stream>>>(
             m->d_parts.p, m->d_dense.p, m->d_listoff.p, reinterpret_cast<int2*>(d_match_ij));
         CU_TRY(m, cudaGetLastError());
+        CU_TRY(m, m->phases.mark(m->stream, -1));
         m->stats.kernel_launches++;
         // no host round trip here: the next batch is ordered behind this kernel by the stream,
         // and the pageable sources above were staged before cudaMemcpyAsync returned
@@ -1496,7 +1649,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
     float ms = 0.f;
     cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]);
     m->stats.last_total_ms = ms;
-    m->stats.last_scan_ms = m->scan_ms_acc;
+    publish_phase_times(m);
     m->stats.last_comparisons = comparisons_of(plans);
     OS_TRY(finish_staging(m));
     OS_TRY(read_counters(m));

@@ -182,6 +182,8 @@ class FixedGather:
                 self.dist.gather(self.buf, self.recv_list, dst=self.dst)
             else:
                 self.dist.gather(self.buf, None, dst=self.dst)
+                if self.buf.is_cuda:
+                    torch.cuda.current_stream().synchronize()    # the payload has left: the next step may overwrite it
                 return None, None, None
             self.hdr_host.copy_(self.recv[:, :self.max_owned].reshape(self.world, -1).view(torch.int64),
                                 non_blocking=False)
@@ -195,3 +197,108 @@ class FixedGather:
             start[o] = r * self.rows + self.max_owned + np.cumsum(c) - c
         flat = (self.recv if self.world > 1 else self.buf[None]).view(-1, 2)
         return flat, start, count
+
+
+class ListGather:
+    """Gather of the per-pair match lists to one rank that moves only what was produced.
+
+    Every rank owns one buffer ``[header | payload]``: the matcher writes its compacted (i, j)
+    lists straight into the payload part (``out_ij``), the header holds the per-pair list
+    lengths.  A step is: one tiny all-gather of the used sizes, then one point-to-point message
+    per rank carrying exactly ``header + used payload`` (``FixedGather`` moves the whole
+    capacity).  The lists stay rank-major on the destination; ``start[p]`` / ``count[p]`` locate
+    pair ``p`` (consumers walk the pair list anyway, src/mve/sfm/bundler_matching.cc:74-132).
+    ``gather`` returns after the transfers have completed on every rank, so the buffers may be
+    rewritten by the next step at once."""
+
+    def __init__(self, all_owned: Sequence[np.ndarray], npairs: int, capacity: int, device, dst: int = 0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dst = dst
+        self.device = device
+        self.all_owned = [np.asarray(o, np.int64) for o in all_owned]
+        self.npairs = npairs
+        self.max_owned = max(1, max(len(o) for o in self.all_owned))
+        self.hdr_rows = (self.max_owned + 1) // 2            # int32 lengths, two per (i, j) row
+        self.capacity = int(capacity)
+        self.rows = self.hdr_rows + self.capacity
+        self.cuda = getattr(device, "type", str(device)) == "cuda"
+        self.buf = torch.zeros((self.rows, 2), dtype=torch.int32, device=device)
+        self.out_ij = self.buf[self.hdr_rows:]               # what the matcher writes into
+        self.header = self.buf[:self.hdr_rows].view(-1)      # [2 * hdr_rows] int32
+        self.lens_host = torch.zeros(2 * self.hdr_rows, dtype=torch.int32, pin_memory=self.cuda)
+        self.sizes_dev = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.recv = None
+        self.used = np.zeros(self.world, np.int64)           # payload rows received per rank (dst only)
+        if self.rank == dst and self.world > 1:
+            self.recv = torch.empty((self.world, self.rows, 2), dtype=torch.int32, device=device)
+            self.hdr_host = torch.zeros((self.world, 2 * self.hdr_rows), dtype=torch.int32, pin_memory=self.cuda)
+
+    def gather(self, local_offsets: np.ndarray):
+        """local_offsets: this rank's list offsets (len(owned) + 1) as the matcher returned them.
+        Returns (flat_ij, start, count) on the destination -- flat_ij int32 [world * rows, 2] --
+        and (None, None, None) elsewhere."""
+        torch, dist = self.torch, self.dist
+        n = len(local_offsets) - 1
+        total = int(local_offsets[-1]) if n >= 0 and len(local_offsets) else 0
+        if total > self.capacity:
+            raise ValueError(f"match lists need {total} rows, capacity {self.capacity}")
+        self.lens_host.zero_()
+        if n > 0:
+            self.lens_host[:n] = torch.from_numpy(np.diff(local_offsets).astype(np.int32))
+        self.header.copy_(self.lens_host, non_blocking=True)
+        if self.world == 1:
+            lens = self.lens_host.numpy()[None, :]
+            self.used[0] = total
+            flat = self.buf
+        else:
+            mine = torch.tensor([total], dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(self.sizes_dev, mine)
+            used = self.sizes_dev.cpu().numpy()              # synchronises: the header copy above is done too
+            send_rows = self.hdr_rows + total
+            if self.rank == self.dst:
+                ops = [dist.P2POp(dist.irecv, self.recv[r, :self.hdr_rows + int(used[r])], r)
+                       for r in range(self.world) if r != self.dst]
+                self.recv[self.dst, :send_rows].copy_(self.buf[:send_rows], non_blocking=True)
+            else:
+                ops = [dist.P2POp(dist.isend, self.buf[:send_rows], self.dst)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if self.rank != self.dst:
+                if self.cuda:
+                    torch.cuda.current_stream().synchronize()    # the payload has left: the buffer is free
+                return None, None, None
+            self.used[:] = used
+            self.hdr_host.copy_(self.recv[:, :self.hdr_rows].reshape(self.world, -1), non_blocking=False)
+            lens = self.hdr_host.numpy()
+            flat = self.recv.view(-1, 2)
+        start = np.zeros(self.npairs, np.int64)
+        count = np.zeros(self.npairs, np.int64)
+        for r in range(self.world):
+            o = self.all_owned[r]
+            c = lens[r, :len(o)].astype(np.int64)
+            count[o] = c
+            start[o] = r * self.rows + self.hdr_rows + np.cumsum(c) - c
+        return flat, start, count
+
+    def used_rows(self) -> int:
+        """Payload rows of the last gather (destination)."""
+        return int(self.used.sum())
+
+    def to_host(self, host_ij, start: np.ndarray):
+        """Copies the gathered payloads (used parts only) back to back into ``host_ij`` (a pinned
+        int32 [>= used_rows, 2] tensor) and returns the pairs' start offsets in it."""
+        src = self.recv if self.world > 1 else self.buf[None]
+        host_start = start.copy()
+        at = 0
+        for r in range(self.world):
+            u = int(self.used[r])
+            if u:
+                host_ij[at:at + u].copy_(src[r, self.hdr_rows:self.hdr_rows + u], non_blocking=True)
+            o = self.all_owned[r]
+            host_start[o] = start[o] - (r * self.rows + self.hdr_rows) + at
+            at += u
+        return host_start

@@ -480,6 +480,11 @@ class ExhaustiveMatching:
             F.ctypes.data_as(C.POINTER(C.c_double))))
         return out_off, out[:out_off[-1]], F
 
+    def set_lookahead(self, max_pairs: int) -> None:
+        """osfm_match_set_lookahead: pairwise_match / pairwise_match_lowres called pair by pair in
+        the reference's order are served from batched passes over the next ``max_pairs`` pairs."""
+        self._check(self._L.osfm_match_set_lookahead(self._h, int(max_pairs)))
+
     # -- introspection --------------------------------------------------------------------------
     def stats(self) -> dict:
         s = _lib.Stats()

@@ -888,6 +888,53 @@ def test_overlapped_staging_gives_the_same_results():
         m.close()
 
 
+def test_lookahead_serves_the_pair_by_pair_loop(ora):
+    """osfm_match_set_lookahead: the unchanged loop of bundler::Matching::compute
+    (bundler_matching.cc:74-132: pairwise_match_lowres, then pairwise_match, pair by pair in the
+    order of :92-93) gets the same results from batched passes over the pairs that follow."""
+    nv, n = 9, 700
+    sift = synth.sift_views(51, nv, n, noise="renorm")
+    sift[3] = sift[3][:0]                                    # an empty view in the middle
+    pool = synth.surf_pool(51, 200)
+    surf = [synth.surf_view(51, v, 150 + 7 * v, pool) for v in range(nv)]
+    pairs = [(a, b) for a in range(1, nv) for b in range(a)]
+    with matcher(sift, surf) as m:
+        want = [(m.pairwise_match_lowres(a, b, 300), m.pairwise_match(a, b)) for a, b in pairs]
+        launches0 = m.stats()["kernel_launches"]
+        for window in (5, 1000):
+            m.set_lookahead(window)
+            for k, (a, b) in enumerate(pairs):
+                if k % 7 == 3:
+                    continue                                 # the caller may skip pairs ...
+                assert m.pairwise_match_lowres(a, b, 300) == want[k][0]
+                r = m.pairwise_match(a, b)
+                assert np.array_equal(r.matches_1_2, want[k][1].matches_1_2), (window, a, b)
+                assert np.array_equal(r.matches_2_1, want[k][1].matches_2_1), (window, a, b)
+            r = m.pairwise_match(2, 1)                       # ... or go back
+            assert np.array_equal(r.matches_1_2, want[2][1].matches_1_2)
+            r = m.pairwise_match(1, 2)                       # view_1 < view_2: not in the enumeration, direct
+            assert np.array_equal(r.matches_1_2, want[2][1].matches_2_1)
+        batched = m.stats()["kernel_launches"] - launches0
+        m.set_lookahead(0)
+        r = m.pairwise_match(5, 2)
+        assert np.array_equal(r.matches_1_2, want[pairs.index((5, 2))][1].matches_1_2)
+        assert_clean(m)
+    assert batched < launches0                               # far fewer launches than pair by pair
+
+
+def test_phase_times_add_up():
+    views = synth.sift_views(52, 6, 2048, noise="renorm")
+    with matcher(views) as m:
+        out = np.empty((15 * 2048, 2), np.int32)
+        m.match_pairs_lists(synth.all_pairs(6), out)
+        st = m.stats()
+    ph = st["last_phase_ms"]
+    assert set(ph) == {"filter", "classify", "resolve_fwd", "claim", "resolve_rev", "mutual", "compact"}
+    assert all(v >= 0 for v in ph.values()) and ph["filter"] > 0 and ph["resolve_fwd"] > 0 and ph["resolve_rev"] > 0
+    assert abs(st["last_scan_ms"] - ph["filter"]) < 1e-9
+    assert sum(ph.values()) <= st["last_total_ms"] * 1.02 + 0.05
+
+
 # ------------------------------------------------------------------ RANSAC for the fundamental matrix
 
 def _ransac_case(counts, seed, outliers=0.3):
