@@ -72,6 +72,25 @@ int osfm_match_abi_version(void);
 
 /* Replaces `new ExhaustiveMatching()` (bundler_matching.cc:34). */
 int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out);
+
+/* One matcher over several GPUs of the box, in one process: what the reference's single call
+ * bundler::Matching::compute (bundler_matching.cc:57-133, reached from
+ * src/matching/matching_mve.cpp:413-415) needs to use more than one device.  devices[0] is the
+ * primary (cfg->device is ignored): views are staged there, and osfm_match_commit /
+ * osfm_match_commit_device replicate the descriptor pool to the other devices with one
+ * ncclBroadcast per feature kind over NVLink (libnccl.so.2 is loaded at run time; a
+ * single-device handle never needs it).  The batched entry points -- osfm_match_pairs,
+ * osfm_match_pairs_compact, osfm_match_two_view_candidates, osfm_match_two_view -- cut the
+ * caller's pair list into one contiguous range per device by cost sum(n1 * n2) (the unit the
+ * reference's OpenMP loop parallelises over, bundler_matching.cc:74), run every range on its
+ * device from a host thread of its own, and deliver the results into the caller's host
+ * buffers in pair order; there is no collective on the data path.  Everything else (single
+ * pairs, RANSAC, tracks) runs on the primary.  Results are identical to a single-device
+ * handle's.  Overlapped staging is accepted but commit waits for the copies. */
+int osfm_match_create_multi(const osfm_match_config* cfg, const int* devices, int num_devices,
+    osfm_matcher** out);
+/* 1 for osfm_match_create handles. */
+int osfm_match_num_devices(const osfm_matcher* m);
 void osfm_match_destroy(osfm_matcher* m);
 const char* osfm_match_last_error(const osfm_matcher* m);
 

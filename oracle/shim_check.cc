@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <memory>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "sfm/bundler_common.h"
@@ -35,6 +36,28 @@
 
 namespace
 {
+    /* OSFM_SHIM_DEVICES="0,1": run every GPU object of this check over those devices
+     * (osfm_match_create_multi); default: device 0. */
+    std::vector<int>
+    shim_devices (void)
+    {
+        std::vector<int> out;
+        char const* env = std::getenv("OSFM_SHIM_DEVICES");
+        std::string tok;
+        for (char const* c = env ? env : ""; ; ++c)
+        {
+            if (*c == ',' || *c == '\0')
+            {
+                if (!tok.empty()) out.push_back(std::atoi(tok.c_str()));
+                tok.clear();
+                if (*c == '\0') break;
+            }
+            else tok.push_back(*c);
+        }
+        if (out.empty()) out.push_back(0);
+        return out;
+    }
+
     /* A small multi-view scene: 3-D points with a SIFT descriptor each, seen by every view
      * from its own pose (positions = projections, MVE's normalised coordinates), plus
      * private features at random positions. */
@@ -130,7 +153,7 @@ namespace
             ref.init(&scene_ref);
             ref.compute(&want);
             std::srand(5);
-            sfm::bundler::GpuMatching gpu(opts);
+            sfm::bundler::GpuMatching gpu(opts, nullptr, shim_devices());
             gpu.init(&scene_gpu);
             gpu.compute(&got);
             std::freopen("/dev/tty", "w", stdout);
@@ -236,7 +259,7 @@ main (void)
     std::unique_ptr<sfm::MatchingBase> gpu;
     try
     {
-        gpu.reset(new sfm::GpuExhaustiveMatching(0));
+        gpu.reset(new sfm::GpuExhaustiveMatching(shim_devices()));
         ref->init(&viewports);
         gpu->init(&viewports);
     }
@@ -291,6 +314,31 @@ main (void)
         {
             ++bad;
             std::printf("MISMATCH batched pair (%d,%d)\n", list[p].first, list[p].second);
+        }
+    }
+
+    /* the loop of bundler::Matching::compute (bundler_matching.cc:74-132, order of :92-93) asks
+     * pair by pair; the shim serves it from batched look-ahead passes (window 4096 by default,
+     * which covers this whole list, and a window of 3 that has to be refilled) */
+    for (int window : { 4096, 3 })
+    {
+        sfm::GpuExhaustiveMatching looped(shim_devices());
+        looped.set_lookahead(window);
+        sfm::bundler::ViewportList again;
+        fill_views(&again, n_sift, n_surf, 1234u);
+        looped.init(&again);
+        for (std::size_t p = 0; p < list.size(); ++p)
+        {
+            sfm::Matching::Result a, b;
+            ref->pairwise_match(list[p].first, list[p].second, &a);
+            int const la = ref->pairwise_match_lowres(list[p].first, list[p].second, 200);
+            int const lb = looped.pairwise_match_lowres(list[p].first, list[p].second, 200);
+            looped.pairwise_match(list[p].first, list[p].second, &b);
+            if (!(a.matches_1_2 == b.matches_1_2 && a.matches_2_1 == b.matches_2_1) || la != lb)
+            {
+                ++bad;
+                std::printf("MISMATCH look-ahead %d pair (%d,%d)\n", window, list[p].first, list[p].second);
+            }
         }
     }
 

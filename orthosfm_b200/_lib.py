@@ -33,6 +33,7 @@ EXPORTS = [
     "osfm_match_ransac_default_options",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
     "osfm_match_debug_set_both_directions", "osfm_match_set_lookahead",
+    "osfm_match_create_multi", "osfm_match_num_devices",
 ]
 
 
@@ -95,6 +96,8 @@ def load() -> C.CDLL:
     L.osfm_match_default_config.restype = None
     L.osfm_match_abi_version.restype = C.c_int
     L.osfm_match_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.osfm_match_create_multi.argtypes = [C.POINTER(Config), ip, C.c_int, C.POINTER(vp)]
+    L.osfm_match_num_devices.argtypes = [vp]
     L.osfm_match_destroy.argtypes = [vp]
     L.osfm_match_destroy.restype = None
     L.osfm_match_last_error.argtypes = [vp]

@@ -42,6 +42,14 @@ public:
             throw std::runtime_error("GpuMatching replaces the exhaustive matcher only");
     }
 
+    /** Several GPUs of this box: the pairs of compute() are sharded over them. */
+    GpuMatching (Options const& options, Progress* progress, std::vector<int> const& devices)
+        : opts(options), progress(progress), matcher(devices), viewports(nullptr)
+    {
+        if (this->opts.matcher_type != Matching::MATCHER_EXHAUSTIVE)
+            throw std::runtime_error("GpuMatching replaces the exhaustive matcher only");
+    }
+
     /** Stages the descriptors on the device and frees them in the viewports, as
      *  bundler::Matching::init does (bundler_matching.cc:45-56); the positions stay. */
     void init (ViewportList* viewports)

@@ -21,6 +21,7 @@
 #ifndef OSFM_GPU_EXHAUSTIVE_MATCHING_HEADER
 #define OSFM_GPU_EXHAUSTIVE_MATCHING_HEADER
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -36,7 +37,22 @@ SFM_NAMESPACE_BEGIN
 class GpuExhaustiveMatching : public MatchingBase
 {
 public:
-    explicit GpuExhaustiveMatching (int device = 0) : device(device), handle(nullptr) {}
+    /** One GPU.  The environment variable OSFM_DEVICES ("0,1,2,3" or "all") overrides the
+     *  choice, so that an unchanged binary can be given the whole box. */
+    explicit GpuExhaustiveMatching (int device = 0) : devices(1, device), lookahead(4096), handle(nullptr)
+    {
+        this->devices_from_environment();
+    }
+
+    /** Several GPUs of this box behind one matcher (osfm_match_create_multi): the descriptor
+     *  pool is replicated with an NCCL broadcast in init(), batched calls are sharded. */
+    explicit GpuExhaustiveMatching (std::vector<int> const& devices)
+        : devices(devices.empty() ? std::vector<int>(1, 0) : devices), lookahead(4096), handle(nullptr) {}
+
+    /** Pairs matched ahead of a pairwise_match() / pairwise_match_lowres() call that follows
+     *  the enumeration of bundler::Matching::compute (osfm_match_set_lookahead); 0 = none.
+     *  Takes effect at the next init(). */
+    void set_lookahead (int max_pairs) { this->lookahead = max_pairs; }
 
     ~GpuExhaustiveMatching (void) override
     {
@@ -59,12 +75,14 @@ public:
              * so the handle is created here, not in the constructor. */
             osfm_match_config cfg;
             osfm_match_default_config(&cfg);
-            cfg.device = this->device;
+            cfg.device = this->devices[0];
             cfg.sift_lowe_ratio = this->opts.sift_matching_opts.lowe_ratio_threshold;
             cfg.sift_distance_threshold = this->opts.sift_matching_opts.distance_threshold;
             cfg.surf_lowe_ratio = this->opts.surf_matching_opts.lowe_ratio_threshold;
             cfg.surf_distance_threshold = this->opts.surf_matching_opts.distance_threshold;
-            int const rc = osfm_match_create(&cfg, &this->handle);
+            int const rc = this->devices.size() > 1
+                ? osfm_match_create_multi(&cfg, this->devices.data(), static_cast<int>(this->devices.size()), &this->handle)
+                : osfm_match_create(&cfg, &this->handle);
             if (rc != OSFM_OK)
             {
                 std::string msg = this->handle ? osfm_match_last_error(this->handle) : "allocation failed";
@@ -87,6 +105,9 @@ public:
                 static_cast<int>(sizeof(Surf::Descriptor) / sizeof(float))));
         }
         this->check(osfm_match_commit(this->handle));
+        /* The unchanged loop of bundler::Matching::compute asks pair by pair
+         * (bundler_matching.cc:74-132): serve it from batched passes over the pairs that follow. */
+        this->check(osfm_match_set_lookahead(this->handle, this->lookahead));
     }
 
     /** Matches all feature types yielding a single matching result. */
@@ -171,7 +192,47 @@ private:
         throw std::runtime_error(msg);
     }
 
-    int device;
+    void devices_from_environment (void)
+    {
+        char const* env = std::getenv("OSFM_DEVICES");
+        if (env == nullptr || *env == '\0')
+            return;
+        std::vector<int> list;
+        if (std::string(env) == "all")
+        {
+            /* the library reports a bad ordinal; 64 is more than any box has */
+            for (int d = 0; d < 64; ++d)
+            {
+                osfm_match_config cfg;
+                osfm_match_default_config(&cfg);
+                cfg.device = d;
+                osfm_matcher* probe = nullptr;
+                int const rc = osfm_match_create(&cfg, &probe);
+                if (probe != nullptr) osfm_match_destroy(probe);
+                if (rc != OSFM_OK) break;
+                list.push_back(d);
+            }
+        }
+        else
+        {
+            std::string tok;
+            for (char const* c = env; ; ++c)
+            {
+                if (*c == ',' || *c == '\0')
+                {
+                    if (!tok.empty()) list.push_back(std::atoi(tok.c_str()));
+                    tok.clear();
+                    if (*c == '\0') break;
+                }
+                else tok.push_back(*c);
+            }
+        }
+        if (!list.empty())
+            this->devices = list;
+    }
+
+    std::vector<int> devices;
+    int lookahead;
     osfm_matcher* handle;
 };
 

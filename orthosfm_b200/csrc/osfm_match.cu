@@ -18,10 +18,14 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nccl.h>      // types and prototypes only: the library is resolved at run time (NcclApi)
 
 #include "../../include/osfm_match.h"
 #include "float_kernels.cuh"
@@ -101,6 +105,37 @@ struct PairPlan {
     int n1[2], n2[2];        // effective sizes per kind (0 if the kind does not contribute)
     int64_t out12, out21;    // offsets of the combined vectors in the dense result
     int len12, len21;
+};
+
+// NCCL, bound at run time: a multi-device matcher replicates its descriptor pool with one
+// ncclBroadcast over NVLink (osfm_match_create_multi).  dlopen instead of a link-time dependency
+// so that a host process that already carries an NCCL (PyTorch bundles its own) is not handed a
+// second copy, and a single-device user needs none.
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(lib, "ncclBroadcast"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!CommInitAll || !CommDestroy || !GroupStart || !GroupEnd || !Broadcast || !GetErrorString) {
+            err = "libnccl.so.2 lacks an expected symbol";
+            return false;
+        }
+        return true;
+    }
 };
 
 // Device time per phase of a batched call: events recorded on the handle's stream between the
@@ -210,6 +245,14 @@ struct osfm_matcher {
         }
     } pass[2];
     unsigned long long* d_counters = nullptr;  // see PostParams::counters
+
+    // Multi-device matcher (osfm_match_create_multi): this handle is the primary; peers[] are full
+    // handles on the other devices that hold a replica of the pool and take a share of every
+    // batched call.  comms[0] belongs to this device, comms[1 + i] to peers[i].
+    std::vector<osfm_matcher*> peers;
+    std::vector<ncclComm_t> comms;
+    NcclApi nccl;
+    double last_broadcast_ms = 0.0;
 
     // Look-ahead for the pair-by-pair plugin loop (osfm_match_set_lookahead): dense results / low-res
     // counts of a window of pairs in the reference's enumeration order, kept in pinned host memory.
@@ -995,6 +1038,11 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
 
 void osfm_match_destroy(osfm_matcher* m) {
     if (!m) return;
+    for (ncclComm_t c : m->comms)
+        if (c && m->nccl.CommDestroy) m->nccl.CommDestroy(c);
+    m->comms.clear();
+    for (osfm_matcher* p : m->peers) osfm_match_destroy(p);
+    m->peers.clear();
     cudaSetDevice(m->device);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
     if (m->stream) cudaStreamSynchronize(m->stream);
@@ -1030,6 +1078,112 @@ void osfm_match_destroy(osfm_matcher* m) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
+}
+
+int osfm_match_create_multi(const osfm_match_config* cfg, const int* devices, int num_devices, osfm_matcher** out) {
+    if (!out) return OSFM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!devices || num_devices < 1) return OSFM_ERR_INVALID_ARGUMENT;
+    osfm_match_config c;
+    if (cfg) c = *cfg; else osfm_match_default_config(&c);
+    c.device = devices[0];
+    int rc = osfm_match_create(&c, out);
+    osfm_matcher* m = *out;
+    if (rc != OSFM_OK || num_devices == 1) return rc;
+    for (int i = 1; i < num_devices; ++i) {
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "device %d listed twice", devices[i]);
+        c.device = devices[i];
+        osfm_matcher* p = nullptr;
+        rc = osfm_match_create(&c, &p);
+        if (rc != OSFM_OK) {
+            m->err = "device " + std::to_string(devices[i]) + ": " + (p ? p->err : std::string("allocation failed"));
+            if (p) osfm_match_destroy(p);
+            return rc;
+        }
+        m->peers.push_back(p);
+    }
+    std::string err;
+    if (!m->nccl.load(err)) return fail(m, OSFM_ERR_CUDA, "%s", err.c_str());
+    m->comms.assign(static_cast<size_t>(num_devices), nullptr);
+    ncclResult_t const nr = m->nccl.CommInitAll(m->comms.data(), num_devices, devices);
+    if (nr != ncclSuccess) {
+        m->comms.clear();
+        return fail(m, OSFM_ERR_CUDA, "ncclCommInitAll: %s", m->nccl.GetErrorString(nr));
+    }
+    CU_TRY(m, cudaSetDevice(m->device));
+    return OSFM_OK;
+}
+
+int osfm_match_num_devices(const osfm_matcher* m) {
+    return m ? 1 + static_cast<int>(m->peers.size()) : OSFM_ERR_INVALID_ARGUMENT;
+}
+
+// Replicates the committed pools of the primary to every peer with one NCCL broadcast per kind
+// (NVLink), then lets every peer finish its own commit (tensor map, norms).  The primary's stream
+// has been synchronised: its pools are complete.
+static int replicate_to_peers(osfm_matcher* m) {
+    if (m->peers.empty()) return OSFM_OK;
+    cudaEvent_t t0 = m->ev[2], t1 = m->ev[3];
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaEventRecord(t0, m->stream));
+    for (int kd = 0; kd < 2; ++kd) {
+        KindPool& k = m->kind[kd];
+        size_t const bytes = static_cast<size_t>(k.rows + kPadRows) * kRowBytes;
+        for (osfm_matcher* p : m->peers) {
+            std::lock_guard<std::mutex> lock(p->mu);
+            KindPool& pk = p->kind[kd];
+            CU_TRY(p, cudaSetDevice(p->device));
+            CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
+            CU_TRY(p, cudaStreamSynchronize(p->stream));
+            reset_kind(pk, false);
+            pk.n = k.n;
+            pk.off = k.off;
+            pk.stage_off.assign(k.n.size(), -1);
+            int const rc = arena_reserve(p, pk, k.rows + kPadRows);
+            if (rc != OSFM_OK) { m->err = "device " + std::to_string(p->device) + ": " + p->err; return rc; }
+            pk.pool = pk.arena;
+            pk.owned = true;
+            pk.rows = k.rows;
+            pk.arena_used = k.rows;
+            pk.lowe = k.lowe; pk.dist = k.dist;
+        }
+        ncclResult_t nr = m->nccl.GroupStart();
+        if (nr == ncclSuccess) nr = m->nccl.Broadcast(k.pool, k.pool, bytes, ncclUint8, 0, m->comms[0], m->stream);
+        for (size_t i = 0; i < m->peers.size() && nr == ncclSuccess; ++i)
+            nr = m->nccl.Broadcast(m->peers[i]->kind[kd].pool, m->peers[i]->kind[kd].pool, bytes, ncclUint8, 0,
+                                   m->comms[1 + i], m->peers[i]->stream);
+        ncclResult_t const ne = m->nccl.GroupEnd();
+        if (nr == ncclSuccess) nr = ne;
+        if (nr != ncclSuccess) return fail(m, OSFM_ERR_CUDA, "ncclBroadcast: %s", m->nccl.GetErrorString(nr));
+    }
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaEventRecord(t1, m->stream));
+    for (osfm_matcher* p : m->peers) {
+        std::lock_guard<std::mutex> lock(p->mu);
+        CU_TRY(p, cudaSetDevice(p->device));
+        for (int kd = 0; kd < 2; ++kd) {
+            int rc = make_tmap(p, p->kind[kd]);
+            if (rc == OSFM_OK) rc = compute_norms(p, p->kind[kd]);
+            if (rc != OSFM_OK) { m->err = "device " + std::to_string(p->device) + ": " + p->err; return rc; }
+        }
+        p->num_views = m->num_views;
+        p->began = true;
+        p->committed = true;
+        p->overlap = false;
+        p->lazy = false;
+        p->cache_full.clear();
+        p->cache_lowres.clear();
+    }
+    for (osfm_matcher* p : m->peers) {
+        CU_TRY(p, cudaSetDevice(p->device));
+        CU_TRY(p, cudaStreamSynchronize(p->stream));
+    }
+    CU_TRY(m, cudaSetDevice(m->device));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) m->last_broadcast_ms = ms;
+    return OSFM_OK;
 }
 
 static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
@@ -1165,7 +1319,8 @@ int osfm_match_commit(osfm_matcher* m) {
     CU_TRY(m, cudaSetDevice(m->device));
     // Overlapped staging stays lazy only if the arena already is the pool (views staged in
     // ascending order); otherwise everything is waited for here, as in the plain commit.
-    bool const lazy = m->overlap && m->kind[0].in_order && m->kind[1].in_order;
+    // (a multi-device matcher broadcasts the complete pool at commit: nothing stays lazy)
+    bool const lazy = m->overlap && m->kind[0].in_order && m->kind[1].in_order && m->peers.empty();
     if (m->overlap && !lazy) CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     for (int kd = 0; kd < 2; ++kd) {
         KindPool& k = m->kind[kd];
@@ -1210,6 +1365,8 @@ int osfm_match_commit(osfm_matcher* m) {
     } else {
         CU_TRY(m, cudaStreamSynchronize(m->stream));  // from here on the caller may free its buffers
     }
+    m->copies_in_flight = m->copies_in_flight && lazy;
+    OS_TRY(replicate_to_peers(m));
     m->committed = true;
     return OSFM_OK;
 }
@@ -1278,9 +1435,10 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     m->num_views = num_views;
     m->began = true;
-    m->committed = true;
     m->cache_full.clear();
     m->cache_lowres.clear();
+    OS_TRY(replicate_to_peers(m));
+    m->committed = true;
     return OSFM_OK;
 }
 
@@ -1358,6 +1516,9 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
     return read_counters(m);
 }
 
+static int dense_dispatch(osfm_matcher* m, std::vector<PairPlan>& plans, OutputMode mode, int only_kind,
+                          int32_t* matches, int64_t* offsets, int32_t* n_consistent);
+
 int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* matches, int64_t* offsets,
                      int32_t* n_consistent) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
@@ -1365,7 +1526,7 @@ int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t*
     OS_TRY(require_committed(m));
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
-    return match_pairs_dense(m, plans, kFiltered, -1, matches, offsets, n_consistent);
+    return dense_dispatch(m, plans, kFiltered, -1, matches, offsets, n_consistent);
 }
 
 // The window of pairs that follows (view_1, view_2) in the reference's enumeration
@@ -1658,6 +1819,168 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
     return OSFM_OK;
 }
 
+}  // extern "C" (templates below)
+
+// ---- multi-device: every batched call is cut into one contiguous range of pairs per device ------
+//
+// Image pairs are independent (bundler_matching.cc:74-132 has no cross-pair state), so there is
+// no data-path collective: the pool is replicated once at commit (replicate_to_peers), every device
+// matches its range of the caller's pair list on its own handle and stream from its own host thread,
+// and the results land in the caller's buffers in pair order.
+
+struct Shard { osfm_matcher* h; size_t first, last; int rc; };
+
+// Contiguous ranges of (nearly) equal cost sum(n1 * n2), one per device.
+static std::vector<Shard> make_shards(osfm_matcher* m, const std::vector<PairPlan>& plans) {
+    size_t const nd = 1 + m->peers.size(), n = plans.size();
+    std::vector<double> cost(n);
+    double total = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        cost[i] = 1.0;   // a pair is never free (fixed per-pair work), so empty pairs spread as well
+        for (int kd = 0; kd < 2; ++kd) cost[i] += static_cast<double>(plans[i].n1[kd]) * plans[i].n2[kd];
+        total += cost[i];
+    }
+    std::vector<Shard> out;
+    size_t at = 0;
+    double acc = 0.0;
+    for (size_t d = 0; d < nd; ++d) {
+        double const goal = total * static_cast<double>(d + 1) / static_cast<double>(nd);
+        size_t const first = at;
+        while (at < n && (d + 1 == nd || acc + 0.5 * cost[at] <= goal)) acc += cost[at++];
+        out.push_back({d == 0 ? m : m->peers[d - 1], first, at, OSFM_OK});
+    }
+    return out;
+}
+
+// Runs fn(shard) for every non-empty shard: shard 0 (the primary, whose lock the caller holds) on
+// this thread, the others on a thread each under their own handle's lock.
+template <typename Fn>
+static int run_sharded(osfm_matcher* m, std::vector<Shard>& shards, Fn fn) {
+    std::vector<std::thread> threads;
+    try {
+        for (size_t d = 1; d < shards.size(); ++d) {
+            if (shards[d].first == shards[d].last) continue;
+            threads.emplace_back([&shards, &fn, d] {
+                Shard& sh = shards[d];
+                std::lock_guard<std::mutex> lock(sh.h->mu);
+                sh.rc = fn(sh);
+            });
+        }
+    } catch (...) {
+        for (std::thread& t : threads) t.join();
+        return fail(m, OSFM_ERR_INTERNAL, "cannot start a host thread per device");
+    }
+    if (shards[0].first < shards[0].last) shards[0].rc = fn(shards[0]);
+    for (std::thread& t : threads) t.join();
+    cudaSetDevice(m->device);
+    for (Shard& sh : shards)
+        if (sh.rc != OSFM_OK) {
+            if (sh.h != m) m->err = "device " + std::to_string(sh.h->device) + ": " + sh.h->err;
+            return sh.rc;
+        }
+    return OSFM_OK;
+}
+
+// Sums the per-device statistics of the last sharded call into the primary's.
+static void merge_peer_stats(osfm_matcher* m, const std::vector<Shard>& shards) {
+    double total_ms = 0.0, scan_ms = 0.0, phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t cmp = 0;
+    for (Shard const& sh : shards) {
+        if (sh.first == sh.last) continue;
+        osfm_match_stats const& st = sh.h->stats;
+        total_ms = std::max(total_ms, st.last_total_ms);       // the devices work side by side
+        scan_ms = std::max(scan_ms, st.last_scan_ms);
+        for (int i = 0; i < 8; ++i) phase[i] = std::max(phase[i], st.last_phase_ms[i]);
+        cmp += st.last_comparisons;
+    }
+    m->stats.last_total_ms = total_ms;
+    m->stats.last_scan_ms = scan_ms;
+    for (int i = 0; i < 8; ++i) m->stats.last_phase_ms[i] = phase[i];
+    m->stats.last_comparisons = cmp;
+}
+
+// Dense results of a plan list into HOST buffers, on one device or sharded over all of them.
+static int dense_dispatch(osfm_matcher* m, std::vector<PairPlan>& plans, OutputMode mode, int only_kind,
+                          int32_t* matches, int64_t* offsets, int32_t* n_consistent) {
+    if (m->peers.empty() || plans.size() < 2)
+        return match_pairs_dense(m, plans, mode, only_kind, matches, offsets, n_consistent);
+    std::vector<Shard> shards = make_shards(m, plans);
+    std::vector<int64_t> base(plans.size() + 1, 0);
+    for (size_t i = 0; i < plans.size(); ++i) base[i + 1] = base[i] + plans[i].len12 + plans[i].len21;
+    int const rc = run_sharded(m, shards, [&](Shard& sh) -> int {
+        std::vector<PairPlan> sub(plans.begin() + sh.first, plans.begin() + sh.last);
+        std::vector<int64_t> off(2 * sub.size() + 1, 0);
+        int const r = match_pairs_dense(sh.h, sub, mode, only_kind, matches ? matches + base[sh.first] : nullptr,
+                                        offsets ? off.data() : nullptr, n_consistent ? n_consistent + sh.first : nullptr);
+        if (r == OSFM_OK && offsets)
+            for (size_t i = 0; i < 2 * sub.size(); ++i) offsets[2 * sh.first + i] = base[sh.first] + off[i];
+        return r;
+    });
+    if (rc != OSFM_OK) return rc;
+    if (offsets) offsets[2 * plans.size()] = base[plans.size()];
+    merge_peer_stats(m, shards);
+    return OSFM_OK;
+}
+
+// Compacted correspondence lists of a pair list into a HOST buffer, in pair order, on one device or
+// sharded over all of them.  sift_only / min_count / counts_out as in compact_core.
+static int compact_to_host(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
+                           int64_t* list_offset, bool sift_only, int min_count, int32_t* counts_out) {
+    if (!list_offset) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "list_offset is null");
+    if (m->peers.empty() || npairs < 2) {
+        int32_t* d = nullptr;
+        OS_TRY(compact_core(m, pairs, npairs, nullptr, -1, list_offset, &d, sift_only, min_count, counts_out));
+        int64_t const total = list_offset[npairs];
+        if (total > capacity_ij || (total > 0 && !match_ij))
+            return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
+                        (long long)total, (long long)capacity_ij);
+        if (total > 0) {
+            CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
+            CU_TRY(m, cudaStreamSynchronize(m->stream));
+        }
+        return OSFM_OK;
+    }
+    OS_TRY(require_committed(m));
+    std::vector<PairPlan> plans;
+    OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
+    std::vector<Shard> shards = make_shards(m, plans);
+    std::vector<int32_t*> d_lists(shards.size(), nullptr);
+    std::vector<std::vector<int64_t>> loff(shards.size());
+    // 1. every device matches its range; its lists stay in its own list buffer
+    OS_TRY(run_sharded(m, shards, [&](Shard& sh) -> int {
+        size_t const d = static_cast<size_t>(&sh - shards.data());
+        size_t const cnt = sh.last - sh.first;
+        loff[d].assign(cnt + 1, 0);
+        return compact_core(sh.h, pairs + 2 * sh.first, static_cast<int>(cnt), nullptr, -1, loff[d].data(), &d_lists[d],
+                            sift_only, min_count, counts_out ? counts_out + sh.first : nullptr);
+    }));
+    // 2. where each device's lists go in the caller's buffer
+    std::vector<int64_t> base(shards.size() + 1, 0);
+    for (size_t d = 0; d < shards.size(); ++d) {
+        int64_t const total = loff[d].empty() ? 0 : loff[d].back();
+        base[d + 1] = base[d] + total;
+        for (size_t i = 0; i + 1 < loff[d].size(); ++i) list_offset[shards[d].first + i] = base[d] + loff[d][i];
+    }
+    list_offset[npairs] = base[shards.size()];
+    merge_peer_stats(m, shards);
+    if (base[shards.size()] > capacity_ij || (base[shards.size()] > 0 && !match_ij))
+        return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
+                    (long long)base[shards.size()], (long long)capacity_ij);
+    // 3. every device copies its lists to their place, side by side
+    return run_sharded(m, shards, [&](Shard& sh) -> int {
+        size_t const d = static_cast<size_t>(&sh - shards.data());
+        int64_t const total = base[d + 1] - base[d];
+        if (total == 0) return OSFM_OK;
+        CU_TRY(sh.h, cudaSetDevice(sh.h->device));
+        CU_TRY(sh.h, cudaMemcpyAsync(match_ij + 2 * base[d], d_lists[d], sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost,
+                                     sh.h->stream));
+        CU_TRY(sh.h, cudaStreamSynchronize(sh.h->stream));
+        return OSFM_OK;
+    });
+}
+
+extern "C" {
+
 int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
                                     int64_t capacity_ij, int64_t* list_offset) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
@@ -1671,17 +1994,7 @@ int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs, 
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (capacity_ij < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative capacity");
-    int32_t* d = nullptr;
-    OS_TRY(compact_core(m, pairs, npairs, nullptr, -1, list_offset, &d));
-    int64_t const total = list_offset[npairs];
-    if (total > capacity_ij || (total > 0 && !match_ij))
-        return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
-                    (long long)total, (long long)capacity_ij);
-    if (total > 0) {
-        CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
-    }
-    return OSFM_OK;
+    return compact_to_host(m, pairs, npairs, match_ij, capacity_ij, list_offset, true, 0, nullptr);
 }
 
 // ---- two-view gates (bundler::Matching::two_view_matching up to RANSAC) --------------------------
@@ -1736,7 +2049,7 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
             OS_TRY(build_plans(m, lr_pairs.data(), static_cast<int>(lr_index.size()), opts->num_lowres_features, true, plans));
             std::vector<int32_t> lr_counts(lr_index.size(), 0);
             // count_consistent_matches of the unfiltered result = survivors of the mutual filter
-            OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, lr_counts.data()));
+            OS_TRY(dense_dispatch(m, plans, kFiltered, -1, nullptr, nullptr, lr_counts.data()));
             for (size_t k = 0; k < lr_index.size(); ++k) {
                 int32_t const i = lr_index[k];
                 if (lr_counts[k] < opts->min_lowres_matches) {
@@ -1761,17 +2074,12 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
     std::vector<int64_t> loff(nf + 1, 0);
     std::vector<int32_t> cnt(nf, 0);
     int const thr = std::max(8, opts->min_feature_matches);
-    int32_t* d = nullptr;
-    OS_TRY(compact_core(m, fp.data(), nf, nullptr, -1, loff.data(), &d, false, thr, cnt.data()));
-    int64_t const total = loff[nf];
-    if (total > capacity_ij || (total > 0 && !match_ij)) {
-        list_offset[npairs] = total;
-        return fail(m, OSFM_ERR_OUT_OF_MEMORY, "match list needs %lld entries, capacity %lld",
-                    (long long)total, (long long)capacity_ij);
-    }
-    if (total > 0) {
-        CU_TRY(m, cudaMemcpyAsync(match_ij, d, sizeof(int32_t) * 2 * total, cudaMemcpyDeviceToHost, m->stream));
-        CU_TRY(m, cudaStreamSynchronize(m->stream));
+    {
+        int const rc = compact_to_host(m, fp.data(), nf, match_ij, capacity_ij, loff.data(), false, thr, cnt.data());
+        if (rc != OSFM_OK) {
+            if (rc == OSFM_ERR_OUT_OF_MEMORY) list_offset[npairs] = loff[nf];
+            return rc;
+        }
     }
     // scatter the per-pair results back to the caller's pair order (lists stay in `full` order,
     // which is ascending pair index: offsets are monotone)
@@ -2325,6 +2633,15 @@ void osfm_io_track_table_free(osfm_track_table* h) { delete h; }
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
     if (!m || !out) return OSFM_ERR_INVALID_ARGUMENT;
     *out = m->stats;
+    for (osfm_matcher const* p : m->peers) {        // a multi-device matcher reports the sum over its devices
+        out->kernel_launches += p->stats.kernel_launches;
+        out->scan_items += p->stats.scan_items;
+        out->candidate_rows += p->stats.candidate_rows;
+        out->slow_rows += p->stats.slow_rows;
+        out->exact_rows += p->stats.exact_rows;
+        out->claimed_rows += p->stats.claimed_rows;
+        out->self_check_failures += p->stats.self_check_failures;
+    }
     return OSFM_OK;
 }
 
@@ -2332,6 +2649,7 @@ int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     m->both_directions = on != 0;
+    for (osfm_matcher* p : m->peers) p->both_directions = on != 0;
     return OSFM_OK;
 }
 

@@ -141,7 +141,10 @@ class ExhaustiveMatching:
     is the batched form the pipeline should prefer (all pairs in one persistent kernel).
     """
 
-    def __init__(self, opts: Optional[MatchingBase.Options] = None, device: int = 0):
+    def __init__(self, opts: Optional[MatchingBase.Options] = None, device: int = 0,
+                 devices: Optional[Sequence[int]] = None):
+        """``devices``: several GPUs of this box behind one handle (osfm_match_create_multi): the
+        pool is replicated with an NCCL broadcast at init, the batched calls are sharded."""
         self.opts = opts if opts is not None else MatchingBase.Options()
         if self.opts.sift_matching_opts.descriptor_length != 128 or \
                 self.opts.surf_matching_opts.descriptor_length != 64:
@@ -155,7 +158,11 @@ class ExhaustiveMatching:
         cfg.surf_lowe_ratio = self.opts.surf_matching_opts.lowe_ratio_threshold
         cfg.surf_distance_threshold = self.opts.surf_matching_opts.distance_threshold
         self._h = C.c_void_p()
-        rc = self._L.osfm_match_create(C.byref(cfg), C.byref(self._h))
+        if devices is not None and len(devices) > 0:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._L.osfm_match_create_multi(C.byref(cfg), devs, len(devices), C.byref(self._h))
+        else:
+            rc = self._L.osfm_match_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = self._L.osfm_match_last_error(self._h).decode() if self._h else "allocation failed"
             if self._h:
@@ -248,6 +255,10 @@ class ExhaustiveMatching:
             C.c_int64(rows), None, None, None, C.c_int64(0)))
         self._sizes = [(int(x), 0) for x in n]
         self._keepalive = sift_pool
+
+    @property
+    def num_devices(self) -> int:
+        return int(self._L.osfm_match_num_devices(self._h))
 
     @property
     def num_views(self) -> int:

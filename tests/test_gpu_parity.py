@@ -1171,3 +1171,81 @@ def test_reference_side_binding():
     assert "SHIM_CHECK PASS" in r.stdout, r.stdout
     # the batched drop-in for bundler::Matching (gpu_bundler_matching.h) against the reference's own
     assert "BUNDLER_CHECK PASS" in r.stderr, r.stderr
+
+
+# ------------------------------------------------------------------ several GPUs behind one handle
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_multi_device_handle_equals_single_device():
+    """osfm_match_create_multi: the pool replicated by ncclBroadcast, every batched call cut into
+    one range of pairs per device.  Same dense results, lists, gates and two-view stage as one
+    device.  Skipped on a one-GPU box."""
+    if _device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import oracle
+    devs = list(range(min(_device_count(), 4)))
+    nv = 9
+    sift, surf, pos = synth.sfm_scene(61, nv, 1400, 900, surf_n=260)
+    sift[2] = sift[2][:300]                                      # unequal costs: the ranges differ in length
+    pos[2] = np.concatenate([pos[2][:300], pos[2][1400:]])
+    surf[5] = surf[5][:0]
+    pos[5] = pos[5][:1400]
+    positions = np.concatenate(pos)
+    pairs = synth.all_pairs(nv)
+    cap = len(pairs) * 2000
+    opts = TwoViewOptions(use_lowres_matching=True, num_lowres_features=300, min_lowres_matches=8,
+                          min_feature_matches=30, min_matching_inliers=20, ransac_max_iterations=100)
+
+    def run(m):
+        out = {}
+        res, counts = m.match_pairs(pairs)
+        out["dense"] = [(r.matches_1_2.copy(), r.matches_2_1.copy()) for r in res]
+        out["counts"] = counts.copy()
+        lists = np.empty((cap, 2), np.int32)
+        off = m.match_pairs_lists(pairs, lists)
+        out["lists"] = (off.copy(), lists[:off[-1]].copy())
+        out["gates"] = m.two_view_candidates(pairs, opts)
+        oracle.srand(3)
+        out["two_view"] = m.two_view_matching(pairs, positions, opts)
+        out["single"] = m.pairwise_match(7, 3)
+        return out
+
+    with ExhaustiveMatching() as m1:
+        m1.init(vps(sift, surf))
+        want = run(m1)
+    with ExhaustiveMatching(devices=devs) as mm:
+        assert mm.num_devices == len(devs)
+        for cycle in range(2):                                   # re-staging on a multi-device handle
+            mm.init(vps(sift, surf), overlap_copies=(cycle == 1))
+            got = run(mm)
+            assert_clean(mm)
+            for (a12, a21), (b12, b21) in zip(want["dense"], got["dense"]):
+                assert np.array_equal(a12, b12) and np.array_equal(a21, b21)
+            assert np.array_equal(want["counts"], got["counts"])
+            assert np.array_equal(want["lists"][0], got["lists"][0]) and np.array_equal(want["lists"][1], got["lists"][1])
+            for key in ("gates", "two_view"):
+                for (s1, c1, l1), (s2, c2, l2) in zip(want[key], got[key]):
+                    assert s1 == s2 and c1 == c2 and np.array_equal(l1, l2), key
+            assert np.array_equal(want["single"].matches_1_2, got["single"].matches_1_2)
+    with pytest.raises(MatcherError):
+        ExhaustiveMatching(devices=[0, 0])
+
+
+def test_reference_side_binding_on_two_devices():
+    """shim_check again with OSFM_SHIM_DEVICES=0,1: sfm::GpuExhaustiveMatching and
+    sfm::bundler::GpuMatching over a two-device matcher against the reference's own classes."""
+    import os
+    import subprocess
+    if _device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "shim_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_check not built (needs /root/reference)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, OSFM_SHIM_DEVICES="0,1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SHIM_CHECK PASS" in r.stdout, r.stdout
+    assert "BUNDLER_CHECK PASS" in r.stderr, r.stderr
