@@ -473,13 +473,12 @@ def e2e_multi(job, reps):
     torch, dist = job.torch, job.dist
     from orthosfm_b200 import ExhaustiveMatching
     rows = job.num_views * job.n
-    host_pool = None
+    host_pool = host_lists = None
     if job.rank == 0:
         host_pool = torch.empty((rows, 128), dtype=torch.uint8, pin_memory=True)
         host_pool.copy_(job.pool[:rows])
     pool2 = torch.zeros_like(job.pool)
     me = ExhaustiveMatching(device=job.dev.index)
-    host_lists = None
     ts, d2h = [], 0
     for it in range(reps + 1):
         job.flush.fill_(1)
@@ -501,14 +500,55 @@ def e2e_multi(job, reps):
         if it > 0:
             ts.append(time.perf_counter() - t0)
     me.close()
+    del pool2
     if job.rank != 0:
-        return None
+        return None, None, None
     s = sum(ts) / len(ts)
-    return {"value": job.total_cmp / s, "unit": UNIT, "h2d_bytes_per_step": int(rows * 128), "d2h_bytes_per_step": int(d2h),
+    return host_pool, host_lists, {"value": job.total_cmp / s, "unit": UNIT, "h2d_bytes_per_step": int(rows * 128), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": 1e3 * s, "repetitions": len(ts),
             "note": "measured on all ranks: H2D of the whole pool on rank 0 (pinned source), NCCL broadcast, "
                     "osfm_match_commit_device on every rank, osfm_match_pairs_compact_device on every rank's shard, "
                     "NCCL gather of the lists to rank 0, D2H into pinned memory; wall clock on rank 0 between barriers"}
+
+
+def e2e_single_process(job, reps, host_pool, host_lists):
+    """N > 1, rank 0 only, the other ranks idle: ONE process drives all N GPUs through the C ABI
+    (osfm_match_create_multi), which is what the reference's single call
+    bundler::Matching::compute would use.  Host descriptors in, host lists out, every repetition."""
+    torch = job.torch
+    from orthosfm_b200 import ExhaustiveMatching, FeatureSet, PackedViews, Viewport
+    n, nv = job.n, job.num_views
+    hp = host_pool.numpy()
+    vps = [Viewport(FeatureSet(sift_descriptors=hp[v * n:(v + 1) * n])) for v in range(nv)]
+    packed = PackedViews(vps)
+    out = host_lists.numpy()
+    mm = ExhaustiveMatching(devices=list(range(job.world)))
+    ts, init_ts, total, bcast = [], [], 0, 0.0
+    try:
+        for it in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mm.init(packed)                       # H2D to device 0 + ncclBroadcast to the others
+            t1 = time.perf_counter()
+            loff = mm.match_pairs_lists(job.pairs, out)
+            t2 = time.perf_counter()
+            if it > 0:
+                ts.append(t2 - t0)
+                init_ts.append(t1 - t0)
+            total = int(loff[-1])
+        st = mm.stats()
+    finally:
+        mm.close()
+    s = sum(ts) / len(ts)
+    return {"value": job.total_cmp / s, "unit": UNIT, "ms_per_step": 1e3 * s, "repetitions": len(ts),
+            "init_ms": 1e3 * sum(init_ts) / len(init_ts), "h2d_bytes_per_step": int(nv * n * 128),
+            "d2h_bytes_per_step": total * 8 + (job.npairs + 1) * 8, "matches": total,
+            "self_check_failures": st["self_check_failures"],
+            "note": f"one process, {job.world} GPUs behind one osfm_matcher (osfm_match_create_multi): begin / set_views_q8 / "
+                    "commit (H2D from pinned memory to device 0, ncclBroadcast of the pool to the other devices) + "
+                    "osfm_match_pairs_compact (pairs cut into one range per device, one host thread per device, lists "
+                    "copied into the caller's host buffer in pair order); measured on rank 0 while the other ranks "
+                    "wait on a CPU barrier"}
 
 
 def e2e_single(job, steps):
@@ -664,7 +704,46 @@ def run_ours(args, cfg, config):
         k = len(ref_counts)
         ref_check = bool(np.array_equal(np.asarray(counts[:k]), np.asarray(ref_counts)))
     else:
-        e2e = e2e_multi(job, 2 if cfg >= 4 else 3)
+        host_pool, host_lists, e2e = e2e_multi(job, 2 if cfg >= 4 else 3)
+        # the same workload through ONE process and the C ABI's multi-device handle (rank 0; the others
+        # wait on a CPU barrier so that no NCCL barrier kernel spins on their GPUs meanwhile)
+        cpu_group = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                e2e["single_process_c_abi"] = e2e_single_process(job, 1 if cfg >= 4 else 2, host_pool, host_lists)
+            except Exception as ex:  # noqa: BLE001
+                e2e["single_process_c_abi"] = {"error": repr(ex)}
+        dist.barrier(group=cpu_group)
+        del host_pool, host_lists
+
+    # ---- the reference's own GPU matcher (CudaSift FindMaxCorr10, unmodified sources compiled for sm_100)
+    # on one pair of this workload's views, same GPU
+    cudasift = None
+    if world == 1:
+        try:
+            import oracle
+            if oracle.have_cudasift():
+                a = job.pool[n:2 * n].cpu().numpy()
+                b = job.pool[:n].cpu().numpy()
+                mean_ms, min_ms, cs_match, _, _ = oracle.CudaSiftReference().match(a, b, reps=5)
+                ours = job.m.twoway_match(0, 1, 0).matches_1_2      # view 1 -> view 0, rows that pass the ratio test
+                both = ours >= 0
+                agree = float((cs_match[both] == ours[both]).mean()) if both.any() else None
+                cudasift = {"one_way_ms": mean_ms, "one_way_ms_min": min_ms,
+                            "comparisons_per_s": n * n / (mean_ms * 1e-3),
+                            "pair_ms_two_directions": 2 * mean_ms,
+                            "workload": f"one pair of this workload's views, {n} x {n} float descriptors (the same "
+                                        "quantised rows, unit-normalised)",
+                            "kernel": "MatchSiftData -> CleanMatches + FindMaxCorr10 (src/cuda_sift/matching.cu:1090-1206, "
+                                      "301-397), unmodified, nvcc -arch=sm_100; time = its own cudaEvent timer incl. the "
+                                      "read-back of 5 floats per point",
+                            "note": "one direction, FP32 CUDA cores, top-2 score/ambiguity only: no ratio threshold, no "
+                                    "cross-check, tail n2 mod 32 skipped -- a different algorithm, timed for scale only",
+                            "argmax_agrees_with_our_accepted_matches": agree}
+        except Exception as ex:  # noqa: BLE001
+            cudasift = {"error": repr(ex)}
 
     final_stats = job.m.stats()
     # ---- config 3 under an extra key at N = 1 and N = 8, so the strong-scaling curve is like for like
@@ -726,6 +805,7 @@ def run_ours(args, cfg, config):
                          "claimed rows of the reverse direction; mutual filter; list compaction",
         "both_directions_device_ms": both_ms,
         "cpu_baseline": cpu_base,
+        "cudasift_baseline": cudasift,
         "device_ms_per_step": r["device_ms_max"],
         "lists_equal_single_gpu_on_sample": check,
         "matches_equal_reference_on_sample": ref_check,

@@ -616,3 +616,36 @@ class _RefExhaustive:
             self.L.osfm_ref_exhaustive_destroy(self.h)
         except Exception:
             pass
+
+
+_CUDASIFT_SO = os.path.join(_HERE, "_ref", "libcudasift_ref.so")
+
+
+def have_cudasift() -> bool:
+    return os.path.exists(_CUDASIFT_SO)
+
+
+class CudaSiftReference:
+    """The reference's own GPU matcher -- CudaSift's MatchSiftData / FindMaxCorr10
+    (/root/reference/src/cuda_sift/matching.cu:1090-1206, 301-397), the unmodified sources
+    compiled for sm_100 (oracle/Makefile, cudasift_driver.cu).  One-way FP32 nearest neighbour
+    with score and ambiguity: a baseline to time on the same GPU, not a parity target."""
+
+    def __init__(self):
+        self.lib = C.CDLL(_CUDASIFT_SO)
+        self.lib.osfm_cudasift_match.restype = C.c_int
+
+    def match(self, set_1, set_2, reps: int = 5):
+        """Returns (mean ms, min ms, match index per row of set_1, score, ambiguity)."""
+        a = _c(set_1, np.uint8).reshape(-1, 128)
+        b = _c(set_2, np.uint8).reshape(-1, 128)
+        ms = np.zeros(2, np.float64)
+        match = np.zeros(a.shape[0], np.int32)
+        score = np.zeros(a.shape[0], np.float32)
+        amb = np.zeros(a.shape[0], np.float32)
+        rc = self.lib.osfm_cudasift_match(_ptr(a, C.c_uint8), C.c_int(a.shape[0]), _ptr(b, C.c_uint8),
+                                          C.c_int(b.shape[0]), C.c_int(reps), _ptr(ms, C.c_double),
+                                          _ptr(match, C.c_int32), _ptr(score, C.c_float), _ptr(amb, C.c_float))
+        if rc != 0:
+            raise RuntimeError(f"osfm_cudasift_match failed ({rc})")
+        return float(ms[0]), float(ms[1]), match, score, amb

@@ -1249,3 +1249,21 @@ def test_reference_side_binding_on_two_devices():
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SHIM_CHECK PASS" in r.stdout, r.stdout
     assert "BUNDLER_CHECK PASS" in r.stderr, r.stderr
+
+
+def test_reference_gpu_matcher_baseline_runs_and_agrees_on_clear_matches():
+    """The reference's own GPU matcher (CudaSift MatchSiftData / FindMaxCorr10, unmodified
+    sources compiled for sm_100 into oracle/_ref/libcudasift_ref.so) is timed beside the product by
+    bench.py.  Here: it runs on this GPU, and where the product accepts a match (clear ratio) its
+    float arg-max names the same candidate."""
+    import oracle
+    if not oracle.have_cudasift():
+        pytest.skip("oracle/_ref/libcudasift_ref.so not built (needs /root/reference)")
+    vs = synth.sift_views(71, 2, 2048, noise="renorm")       # a multiple of 32: its tail handling plays no part
+    mean_ms, min_ms, match, score, amb = oracle.CudaSiftReference().match(vs[1], vs[0], reps=2)
+    assert 0 < min_ms <= mean_ms
+    with matcher(vs) as m:
+        ours = m.twoway_match(KIND_SIFT_U8, 1, 0).matches_1_2
+    ok = ours >= 0
+    assert ok.sum() > 200
+    assert (match[ok] == ours[ok]).mean() > 0.99
