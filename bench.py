@@ -602,34 +602,32 @@ def e2e_single(job, steps):
                      "note": "same, osfm_match_pairs: the dense Matching::Result vectors of every pair"},
            "lists_equal_dense_on_sample": bool(lists_equal_dense)}
     # (c) what the reference's plugin interface does (bundler_matching.cc:51,74-132,162): init() with FLOAT
-    # descriptors in pageable memory (quantised on the device, convert_descriptor), then pairwise_match once per
-    # pair in compute()'s order, each returning its Matching::Result to the host
+    # descriptor records in pageable memory (quantised on the device, convert_descriptor), then pairwise_match
+    # once per pair in compute()'s order, each returning its Matching::Result to the host.  Run natively
+    # (orthosfm_b200/csrc/plugin_loop_bench.cc: the C ABI as csrc/gpu_exhaustive_matching.h drives it).
     try:
-        floats = [(v.astype(np.float32) / 255.0) for v in views_np]
-        fvps = [Viewport(FeatureSet(sift_descriptors=f)) for f in floats]
-        h2d_f = sum(f.nbytes for f in floats)
-        plug = {}
-        for name, window in (("per_pair", 0), ("lookahead", len(my_pairs))):
-            def loop():
-                out = 0
-                for v1, v2 in my_pairs:
-                    out += int((me.pairwise_match(int(v1), int(v2)).matches_1_2 >= 0).sum())
-                return out
-
-            def init_float():
-                me.init(fvps)
-                me.set_lookahead(window)
-            s, nm = timed(loop, init_float, reps=4)
-            plug[name] = {"value": job.my_cmp / s, "ms_per_step": 1e3 * s, "matches": int(nm)}
-        me.set_lookahead(0)
-        plug["h2d_bytes_per_step"] = int(h2d_f)
-        plug["d2h_bytes_per_step"] = d2h_dense
-        plug["note"] = ("ExhaustiveMatching.init (osfm_match_set_view_f32: float descriptors from pageable memory, "
-                        "quantised on the device) + osfm_match_pair for every pair in bundler::Matching::compute's "
-                        "order.  per_pair: every call is its own launch sequence and D2H; lookahead: the first "
-                        "miss matches the following pairs of the reference's enumeration in one batch "
-                        "(osfm_match_set_lookahead) and later calls are served from that result")
-        e2e["plugin"] = plug
+        import tempfile
+        from orthosfm_b200.csrc import build as cuda_build
+        exe = cuda_build.PLUGIN_BENCH
+        with tempfile.NamedTemporaryFile(suffix=".u8") as tf:
+            np.concatenate(views_np).tofile(tf.name)
+            out = subprocess.run([exe, tf.name, str(nv), str(n), "3"], capture_output=True, text=True, timeout=600)
+        if out.returncode != 0:
+            raise RuntimeError(f"plugin_loop_bench rc {out.returncode}: {out.stderr[-300:]}")
+        pb = json.loads(out.stdout.strip().splitlines()[-1])
+        total_look = pb["init_f32_ms"] + pb["loop_lookahead_ms"]
+        e2e["plugin"] = {
+            "value": job.my_cmp / (total_look * 1e-3), "unit": UNIT, "ms_per_step": total_look,
+            "init_f32_ms": pb["init_f32_ms"], "loop_lookahead_ms": pb["loop_lookahead_ms"],
+            "loop_per_pair_ms": pb["loop_per_pair_ms"], "batch_dense_ms": pb["batch_dense_ms"],
+            "loop_vs_batch": pb["loop_lookahead_ms"] / pb["batch_dense_ms"],
+            "h2d_bytes_per_step": pb["h2d_bytes"], "d2h_bytes_per_step": d2h_dense, "matches": pb["matches"],
+            "note": "native C++ (plugin_loop_bench): osfm_match_begin / osfm_match_set_view_f32 per view from pageable "
+                    "Sift::Descriptor records (132-float stride, quantised on the device) / osfm_match_commit = init_f32_ms; "
+                    "then osfm_match_pair for every pair in bundler::Matching::compute's order into std::vector results: "
+                    "loop_lookahead_ms with the look-ahead the C++ binding switches on (the first miss matches the pairs "
+                    "that follow in one batch), loop_per_pair_ms without it (every call its own launch sequence and "
+                    "D2H); batch_dense_ms = one osfm_match_pairs call for the same pairs.  value = init + look-ahead loop"}
     except Exception as ex:  # noqa: BLE001
         e2e["plugin"] = {"error": repr(ex)}
     return e2e, me, lists_host, loff_h, counts, views_np

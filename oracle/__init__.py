@@ -470,6 +470,21 @@ class Reference(_Impl):
                                          C.c_float(ratio), _ptr(counts, C.c_int))
         return counts[:pr.shape[0]].copy()
 
+    def match_pairs_u8_digest(self, views, pairs, ratio: float = 0.8):
+        """Like match_pairs_u8, plus a 64-bit FNV-1a digest of every pair's correspondence list
+        ((i, j) int32 pairs in ascending i): returns (counts, digests)."""
+        views = [_c(v, np.uint8).reshape(-1, 128) for v in views]
+        ptrs = (C.POINTER(C.c_uint8) * len(views))(*[_ptr(v, C.c_uint8) for v in views])
+        sizes = np.array([v.shape[0] for v in views], dtype=np.int32)
+        pr = _c(pairs, np.int32).reshape(-1, 2)
+        counts = np.zeros(max(pr.shape[0], 1), dtype=np.int32)
+        digest = np.zeros(max(pr.shape[0], 1), dtype=np.uint64)
+        self.lib.osfm_ref_match_pairs_u8_digest.restype = C.c_long
+        self.lib.osfm_ref_match_pairs_u8_digest(ptrs, _ptr(sizes, C.c_int), C.c_int(len(views)),
+                                                _ptr(pr, C.c_int), C.c_int(pr.shape[0]), C.c_float(ratio),
+                                                _ptr(counts, C.c_int), _ptr(digest, C.c_ulonglong))
+        return counts[:pr.shape[0]], digest[:pr.shape[0]]
+
     def tracks_compute(self, features, pair_views, offsets, ij):
         """The reference's own Tracks::compute through ref_driver.cc."""
         features = _c(features, np.int32)
@@ -649,3 +664,13 @@ class CudaSiftReference:
         if rc != 0:
             raise RuntimeError(f"osfm_cudasift_match failed ({rc})")
         return float(ms[0]), float(ms[1]), match, score, amb
+
+
+def list_digest(ij: np.ndarray) -> int:
+    """FNV-1a (64 bit) over an (i, j) int32 correspondence list, as osfm_ref_match_pairs_u8_digest."""
+    h = np.uint64(1469598103934665603)
+    prime = np.uint64(1099511628211)
+    with np.errstate(over="ignore"):
+        for b in np.ascontiguousarray(ij, np.int32).view(np.uint8).reshape(-1):
+            h = (h ^ np.uint64(b)) * prime
+    return int(h)

@@ -285,6 +285,53 @@ osfm_ref_match_pairs_u8 (const uint8_t* const* views, const int* sizes,
     return total;
 }
 
+/* Same, returning a digest of every pair's filtered result instead of just its count:
+ * digest[p] = FNV-1a (64 bit) over the int32 pairs (i, matches_1_2[i]) of the surviving entries
+ * in ascending i -- i.e. over the correspondence list bundler_matching.cc:178-192 builds.  Lets a
+ * test hold ALL lists of a large pair set against the reference without moving them. */
+long
+osfm_ref_match_pairs_u8_digest (const uint8_t* const* views, const int* sizes,
+    int num_views, const int* pairs, int npairs, float ratio, int* counts, unsigned long long* digest)
+{
+    std::vector<util::AlignedMemory<unsigned short, 16>> wide(num_views);
+    std::vector<char> used(num_views, 0);
+    for (int p = 0; p < 2 * npairs; ++p)
+        used[pairs[p]] = 1;
+    for (int v = 0; v < num_views; ++v)
+        if (used[v])
+            wide[v] = widen<unsigned short>(views[v], (std::size_t)sizes[v] * 128);
+
+    long total = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+:total)
+    for (int p = 0; p < npairs; ++p)
+    {
+        int const v1 = pairs[2 * p + 0];
+        int const v2 = pairs[2 * p + 1];
+        sfm::Matching::Result r;
+        sfm::Matching::twoway_match(make_opts(128, ratio,
+            std::numeric_limits<float>::max()),
+            wide[v1].data(), sizes[v1], wide[v2].data(), sizes[v2], &r);
+        sfm::Matching::remove_inconsistent_matches(&r);
+        unsigned long long h = 1469598103934665603ull;
+        int c = 0;
+        for (std::size_t i = 0; i < r.matches_1_2.size(); ++i)
+        {
+            if (r.matches_1_2[i] < 0)
+                continue;
+            int const rec[2] = { (int)i, r.matches_1_2[i] };
+            unsigned char const* b = reinterpret_cast<unsigned char const*>(rec);
+            for (int k = 0; k < 8; ++k) { h ^= b[k]; h *= 1099511628211ull; }
+            ++c;
+        }
+        if (counts != nullptr)
+            counts[p] = c;
+        if (digest != nullptr)
+            digest[p] = h;
+        total += c;
+    }
+    return total;
+}
+
 /* ---- ExhaustiveMatching (the MatchingBase plugin) ------------------ */
 
 struct osfm_ref_exhaustive

@@ -28,6 +28,7 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
+        build_tools()
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
@@ -35,7 +36,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env.pop("CC", None)   # the image exports a gcc wrapper that cannot link OpenMP; use the system one
     env.pop("CXX", None)
     subprocess.check_call(cmd, cwd=HERE, env=env)
+    build_tools()
     return SO
+
+
+PLUGIN_BENCH = os.path.join(HERE, "plugin_loop_bench")
+
+
+def build_tools() -> str:
+    """plugin_loop_bench: the reference's plugin call pattern against the C ABI, in C++ (bench.py's
+    e2e.plugin figures)."""
+    src = os.path.join(HERE, "plugin_loop_bench.cc")
+    if os.path.exists(PLUGIN_BENCH) and os.path.getmtime(PLUGIN_BENCH) >= max(os.path.getmtime(src), os.path.getmtime(SO)):
+        return PLUGIN_BENCH
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", src, "-o", PLUGIN_BENCH, "-L" + HERE, "-losfm_match",
+                           "-Wl,-rpath,$ORIGIN"], cwd=HERE)
+    return PLUGIN_BENCH
 
 
 if __name__ == "__main__":

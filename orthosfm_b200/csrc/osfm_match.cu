@@ -490,7 +490,8 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     CU_TRY(m, cudaGetLastError());
     gather_rows_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
                                                               sp.job_xrow.p, sp.list.p, k.pool,
-                                                              sp.xpool.p, sp.xrow_map.p);
+                                                              sp.xpool.p, sp.xrow_map.p,
+                                                              verify && PASS == kPassResolve ? m->d_rowres.p : nullptr);
     CU_TRY(m, cudaGetLastError());
     CU_TRY(m, cudaFuncSetAttribute(scan_kernel<0, PASS, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
     ExactParams ex;
@@ -734,24 +735,26 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         cl.jobs = m->d_jobs.p;
         cl.rev_of = m->d_rev_of.p;
         cl.fwd_rows = fwd_rows;
-        cl.total_rows = rows;
         cl.pool = k.pool;
         cl.oneway = m->d_oneway.p;
         cl.rowres = m->d_rowres.p;
+        cl.norm2 = k.d_norm2.p;
+        cl.viewmax = k.d_viewmax.p;
+        cl.surv_list = m->pass[0].list.p;
+        cl.surv_cnt = m->pass[0].cnt.p;
+        cl.uncert_list = m->d_cand.p;
+        cl.counters = m->d_counters;
         int const fgrid = static_cast<int>((fwd_rows + 255) / 256);
-        int const rgrid = static_cast<int>((rev_rows + 255) / 256);
         cp.total_rows = rows;
         if (k.is_signed) {
             claim_kernel<true><<<fgrid, 256, 0, m->stream>>>(cl);
-            targets_kernel<true><<<rgrid, 256, 0, m->stream>>>(cp, fwd_rows);
         } else {
             claim_kernel<false><<<fgrid, 256, 0, m->stream>>>(cl);
-            targets_kernel<false><<<rgrid, 256, 0, m->stream>>>(cp, fwd_rows);
-            certify_kernel<true><<<m->num_sms * 32, 256, 0, m->stream>>>(cp);
+            certify_kernel<true><<<m->num_sms * 8, 256, 0, m->stream>>>(cp);
             m->stats.kernel_launches++;
         }
         CU_TRY(m, cudaGetLastError());
-        m->stats.kernel_launches += 2;
+        m->stats.kernel_launches++;
         CU_TRY(m, m->phases.mark(m->stream, kPhResolveRev));
         OS_TRY(second_passes(true));
     }

@@ -375,92 +375,103 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
 // goes through the filter pass (one tensor-core product per pair instead of two); the reverse
 // direction is evaluated for the claimed rows alone:
 //   claim_kernel    V[j] = the largest similarity any claimant has with j (clamped at the
-//                   reference's initial 0), kept in the (otherwise unused) rowres slot of j;
-//   targets_kernel  queues the claimed rows like classify_kernel queues survivors: rows with
-//                   the 16-bit norm certificate for the RESOLVE pass in verify mode (a similarity
-//                   above V: some row that is no claimant is nearer, the result is -1 for the
-//                   mutual filter; otherwise V is the row's best and RESOLVE's result is the
-//                   reference's), the others for the EXACT pass / the CUDA-core replay, which
-//                   need no V.
+//                   reference's initial 0), kept in the (otherwise unused) rowres slot of j; the
+//                   first claimant also queues j like classify_kernel queues survivors: rows
+//                   with the 16-bit norm certificate for the RESOLVE pass in verify mode (a
+//                   similarity above V: some row that is no claimant is nearer, the result is -1
+//                   for the mutual filter; otherwise V is the row's best and RESOLVE's result is
+//                   the reference's), the others for certify_kernel / the EXACT pass / the
+//                   CUDA-core replay, which need no V.
 // Rows nobody claims keep the -1 the host wrote beforehand.
 
 struct ClaimParams {
     const ScanJob* jobs;
     const int32_t* rev_of;       // per job: its pair's reverse job (or -1)
     int64_t fwd_rows;            // rows [0, fwd_rows) belong to forward (scanned) jobs
-    int64_t total_rows;
     const uint8_t* pool;
     const int32_t* oneway;
     int2* rowres;                // forward rows: the filter's record; reverse rows: (V, job), preset to -1
+    const int32_t* norm2;        // the norm certificate's inputs (as in ClassifyParams)
+    const int32_t* viewmax;
+    int64_t* surv_list;          // RESOLVE queue of the reverse jobs (certified rows), per job at out_row
+    int* surv_cnt;
+    int64_t* uncert_list;        // claimed rows without certificate, flat
+    unsigned long long* counters;   // [0] uncert_list length, [3] signed rows without certificate, [4] claimed rows
 };
 
+// One thread per forward row.  The FIRST claimant of a row (the atomic maximum returns the preset
+// -1) also queues it; the value the queue entry carries is filled in later, from the slot, once
+// every claim has landed (gather_rows_kernel).
 template <bool SIGNED>
 __global__ void __launch_bounds__(256) claim_kernel(ClaimParams p)
 {
     int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= p.fwd_rows) return;
-    int const mt = p.oneway[g];
-    if (mt < 0) return;
-    int const ji = p.rowres[g].y & kRowJobMask;
-    int const rj = p.rev_of[ji];
-    if (rj < 0) return;
-    ScanJob const job = p.jobs[ji];
-    int s = dot_row<SIGNED>(p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes,
-                            p.pool + (static_cast<int64_t>(job.c_row) + mt) * kRowBytes);
-    s = max(s, 0);               // the reference's best starts at 0 (nearest_neighbor.cc:221-224, 246-249)
-    int2* const slot = p.rowres + p.jobs[rj].out_row + mt;
-    atomicMax(&slot->x, s);
-    slot->y = rj;                // every claimant writes the same value
-}
-
-template <bool SIGNED>
-__global__ void __launch_bounds__(256) targets_kernel(ClassifyParams p, int64_t first_row)
-{
-    int64_t const g = first_row + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     int const lane = threadIdx.x & 31;
-    bool survive = false, wraps = false, doubtful = false;
-    int ji = -1, v1 = 0;
-    int64_t out_row = 0;
-    if (g < p.total_rows) {
-        int2 const rr = p.rowres[g];
-        if (rr.x >= 0) {         // claimed
-            v1 = rr.x;
-            ji = rr.y;
-            ScanJob const job = p.jobs[ji];
-            out_row = job.out_row;
-            int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
-            int64_t const qn2 = p.norm2[job.q_row + static_cast<int>(g - job.out_row)];
-            bool const certified = qn2 * static_cast<int64_t>(p.viewmax[job.c_view]) < limit;
-            // without certificate: signed -> CUDA-core replay; unsigned -> certify_kernel looks at
-            // the few candidates that could take the row to 2^16
-            survive = certified;
-            doubtful = !certified;
+    bool first = false, certified = false;
+    int rj = -1;
+    int64_t target = 0, out_row = 0;
+    if (g < p.fwd_rows) {
+        int const mt = p.oneway[g];
+        if (mt >= 0) {
+            int2 const rr = p.rowres[g];
+            int const ji = rr.y & kRowJobMask;
+            rj = p.rev_of[ji];
+            if (rj >= 0) {
+                ScanJob const job = p.jobs[ji];
+                // The similarity of the claimant with its match IS its row's best, which the filter
+                // recorded exactly if no similarity of the row left the 16-bit range (norm certificate,
+                // or scanned with 32-bit loads and found below 2^16).  Only the few rows that went
+                // through the EXACT pass / the replay need the product computed again.
+                int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
+                int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
+                bool const trusted = flag == kRowWideOk ||
+                    (flag == kRowPacked && static_cast<int64_t>(p.norm2[q_prow]) * static_cast<int64_t>(p.viewmax[job.c_view]) <
+                                               (SIGNED ? (1ll << 30) : (1ll << 32)));
+                int s;
+                if (trusted)
+                    s = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
+                else
+                    s = dot_row<SIGNED>(p.pool + static_cast<int64_t>(q_prow) * kRowBytes,
+                                        p.pool + (static_cast<int64_t>(job.c_row) + mt) * kRowBytes);
+                s = max(s, 0);       // the reference's best starts at 0 (nearest_neighbor.cc:221-224, 246-249)
+                ScanJob const rjob = p.jobs[rj];
+                out_row = rjob.out_row;
+                target = out_row + mt;
+                int2* const slot = p.rowres + target;
+                first = atomicMax(&slot->x, s) < 0;
+                if (first) {
+                    slot->y = rj;
+                    int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+                    int64_t const qn2 = p.norm2[rjob.q_row + mt];
+                    certified = qn2 * static_cast<int64_t>(p.viewmax[rjob.c_view]) < limit;
+                }
+            }
         }
     }
-#pragma unroll
-    for (int which = 0; which < (SIGNED ? 1 : 2); ++which) {
-        bool const mine = which == 0 ? survive : wraps;
-        unsigned const xm = __ballot_sync(0xffffffffu, mine);
-        if (mine) {
-            unsigned const peers = __match_any_sync(xm, ji);
-            int const leader = __ffs(peers) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd((which == 0 ? p.surv_cnt : p.exact_cnt) + ji, __popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            (which == 0 ? p.surv_list : p.exact_list)[out_row + base + __popc(peers & ((1u << lane) - 1u))] =
-                surv_entry(g, v1, which == 0);
-        }
+    // certified rows -> the reverse job's RESOLVE queue, one atomic per job present in the warp
+    bool const queue = first && certified;
+    unsigned const qm = __ballot_sync(0xffffffffu, queue);
+    if (queue) {
+        unsigned const peers = __match_any_sync(qm, rj);
+        int const leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(p.surv_cnt + rj, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(target, 0, true);
     }
+    // without certificate: signed -> CUDA-core replay; unsigned -> certify_kernel<true> looks at
+    // the few candidates that could take the row to 2^16
+    bool const doubtful = first && !certified;
     unsigned const um = __ballot_sync(0xffffffffu, doubtful);
     if (um != 0) {
         unsigned long long ub = 0;
         if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
         ub = __shfl_sync(0xffffffffu, ub, 0);
-        if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
+        if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = target;
     }
-    unsigned const tm = __ballot_sync(0xffffffffu, survive || wraps || doubtful);
+    unsigned const fm = __ballot_sync(0xffffffffu, first);
     if (lane == 0) {
-        if (tm) atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(tm)));   // claimed rows (cumulative)
+        if (fm) atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(fm)));      // claimed rows (cumulative)
         if (SIGNED && um) atomicAdd(p.counters + 3, static_cast<unsigned long long>(__popc(um)));   // unsigned: certify_kernel counts
     }
 }
@@ -590,7 +601,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
                                                            const int64_t* __restrict__ slow_list,
                                                            const uint8_t* __restrict__ pool,
                                                            uint8_t* __restrict__ xpool,
-                                                           int64_t* __restrict__ xrow_map)
+                                                           int64_t* __restrict__ xrow_map,
+                                                           const int2* __restrict__ claimed_v)
 {
     for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
         int const cnt = slow_cnt[j];
@@ -603,7 +615,10 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
             int64_t const src_row = static_cast<int64_t>(job.q_row) + (surv_row(entry) - job.out_row);
             reinterpret_cast<uint4*>(xpool + (static_cast<int64_t>(x0) + s) * kRowBytes)[part] =
                 __ldg(reinterpret_cast<const uint4*>(pool + src_row * kRowBytes) + part);
-            if (part == 0) xrow_map[x0 + s] = entry;
+            // reverse pass: the value a claimed row is held against is final only now
+            if (part == 0)
+                xrow_map[x0 + s] = claimed_v == nullptr ? entry
+                    : surv_entry(surv_row(entry), claimed_v[surv_row(entry)].x, (static_cast<uint64_t>(entry) & kSurvCertified) != 0);
         }
     }
 }

@@ -59,3 +59,11 @@ def golden_cases():
 @pytest.fixture(scope="session")
 def golden_real():
     return np.load(os.path.join(GOLDEN, "real_pair.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_triple():
+    """The three images the reference ships through its own SIFT and ExhaustiveMatching
+    (tests/golden/make_golden.py::real_triple): BASELINE config 1 restated."""
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_triple.npz"))

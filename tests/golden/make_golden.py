@@ -8,6 +8,8 @@ Outputs (committed):
   real_pair.npz    quantised SIFT descriptors of the reference's own test images
                    src/cuda_sift/data/left.pgm / righ.pgm, produced by the reference's
                    sfm::Sift, with the reference ExhaustiveMatching results.
+  real_triple.npz  the same for the three images the reference ships (left / righ / rimg_pts.pgm):
+                   all 3 pairs, BASELINE config 1 restated (3-image set, exhaustive matching).
   cases.npz        seeded synthetic and adversarial descriptor sets with the reference's
                    twoway_match / remove_inconsistent / count results (u8, s8, f32).
 """
@@ -68,6 +70,31 @@ def real_pair():
                         sift_0=q[0], sift_1=q[1], twoway_12=t12, twoway_21=t21,
                         match_12=m12, match_21=m21, lowres_500=np.int32(lowres),
                         float_sample=fl[0][:64], float_sample_q=q[0][:64])
+
+
+def real_triple():
+    """BASELINE config 1 restated: a 3-image set through the reference's own
+    feature extractor and its ExhaustiveMatching, all 3 pairs in bundler::Matching::compute's
+    order (view_1 > view_2).  The images are the three the reference ships
+    (src/cuda_sift/data): the Suzanne renders of the testbench are an external download."""
+    d = "/root/reference/src/cuda_sift/data"
+    fl = [REF.sift_gray8(read_pgm(os.path.join(d, n))) for n in ("left.pgm", "righ.pgm", "rimg_pts.pgm")]
+    print("SIFT descriptors:", [x.shape for x in fl])
+    empty = np.zeros((0, 64), np.float32)
+    ex = REF.exhaustive([(f, empty) for f in fl])
+    q = [ORA.quantize_sift(x) for x in fl]
+    out = {"sift_%d" % v: q[v] for v in range(3)}
+    for v1 in range(1, 3):
+        for v2 in range(v1):
+            m12, m21 = ex.pairwise_match(v1, v2)
+            out[f"match_{v1}{v2}_12"] = m12
+            out[f"match_{v1}{v2}_21"] = m21
+            out[f"lowres_{v1}{v2}"] = np.int32(ex.pairwise_match_lowres(v1, v2, 500))
+            t12, t21 = REF.twoway("u8", q[v1], q[v2], 0.8)
+            f12, f21 = REF.remove_inconsistent(t12, t21)
+            assert np.array_equal(f12, m12) and np.array_equal(f21, m21)
+            print((v1, v2), "consistent:", int((m12 >= 0).sum()), "lowres:", int(out[f"lowres_{v1}{v2}"]))
+    np.savez_compressed(os.path.join(HERE, "real_triple.npz"), **out)
 
 
 def cases():
@@ -143,6 +170,7 @@ def cases():
 
 if __name__ == "__main__":
     real_pair()
+    real_triple()
     cases()
-    for f in ("real_pair.npz", "cases.npz"):
+    for f in ("real_pair.npz", "real_triple.npz", "cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -124,6 +124,29 @@ def test_golden_real_image_pair(golden_real):
         assert_clean(m)
 
 
+def test_golden_three_image_set(golden_triple):
+    """BASELINE config 1 restated: the three images the reference ships, all 3 pairs in
+    bundler::Matching::compute's order, pair by pair (with and without look-ahead) and batched,
+    against the reference's own ExhaustiveMatching results."""
+    g = golden_triple
+    pairs = [(1, 0), (2, 0), (2, 1)]
+    with matcher([g["sift_0"], g["sift_1"], g["sift_2"]]) as m:
+        for window in (0, 8):
+            m.set_lookahead(window)
+            for v1, v2 in pairs:
+                assert m.pairwise_match_lowres(v1, v2, 500) == int(g[f"lowres_{v1}{v2}"])
+                res = m.pairwise_match(v1, v2)
+                assert np.array_equal(res.matches_1_2, g[f"match_{v1}{v2}_12"])
+                assert np.array_equal(res.matches_2_1, g[f"match_{v1}{v2}_21"])
+        m.set_lookahead(0)
+        results, counts = m.match_pairs(pairs)
+        for (v1, v2), r in zip(pairs, results):
+            assert np.array_equal(r.matches_1_2, g[f"match_{v1}{v2}_12"])
+            assert np.array_equal(r.matches_2_1, g[f"match_{v1}{v2}_21"])
+        assert counts.tolist() == [810, 810, 2376]
+        assert_clean(m)
+
+
 def test_quantiser_matches_convert_descriptor(ora, golden_real):
     """set_view_f32 quantises on the device exactly like convert_descriptor."""
     g = golden_real
@@ -568,6 +591,54 @@ def test_baseline_config_2_lists_equal_the_reference():
         got = out[loff[p]:loff[p + 1]]
         assert np.array_equal(got[:, 0], i) and np.array_equal(got[:, 1], o12[i]), (v1, v2)
         assert i.size > 500
+
+
+def _digests_of_lists(out, loff):
+    import oracle
+    return np.array([oracle.list_digest(out[loff[p]:loff[p + 1]]) for p in range(len(loff) - 1)], np.uint64)
+
+
+def test_baseline_config_2_all_630_lists_equal_the_reference():
+    """BASELINE config 2 in full: every one of the 630 correspondence lists against the
+    reference matcher itself (oracle/_ref, OpenMP over the pairs: about a minute of host time on
+    16 cores), compared through per-pair counts and 64-bit digests of the (i, j) lists."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    views = synth.sift_views(2, 36, 8192, noise="renorm")
+    pairs = synth.all_pairs(36)
+    with matcher(views) as m:
+        out = np.empty((630 * 2048, 2), np.int32)
+        loff = m.match_pairs_lists(pairs, out)
+        assert_clean(m)
+    ref = oracle.Reference()
+    ref.use_all_cores()
+    counts, digests = ref.match_pairs_u8_digest(views, pairs, 0.8)
+    assert np.array_equal(np.diff(loff), counts)
+    assert np.array_equal(_digests_of_lists(out, loff), digests)
+    assert counts.min() > 500
+
+
+@pytest.mark.parametrize("nv,n", [(4, 16384), (3, 32768)])
+def test_config_3_and_4_sized_views_lists_equal_the_reference(nv, n):
+    """Views of BASELINE config 3 / 4 size (16 384 / 32 768 descriptors, i.e. MAX_FEATURES of
+    src/matching/matching.h:24): the complete lists of all pairs of a few such views against the
+    reference matcher (counts + digests)."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    views = synth.sift_views(3 if n == 16384 else 4, nv, n, noise="renorm")
+    pairs = synth.all_pairs(nv)
+    with matcher(views) as m:
+        out = np.empty((len(pairs) * n // 4, 2), np.int32)
+        loff = m.match_pairs_lists(pairs, out)
+        assert_clean(m)
+    ref = oracle.Reference()
+    ref.use_all_cores()
+    counts, digests = ref.match_pairs_u8_digest(views, pairs, 0.8)
+    assert np.array_equal(np.diff(loff), counts)
+    assert np.array_equal(_digests_of_lists(out, loff), digests)
+    assert counts.min() > n // 16
 
 
 def test_config_5_single_large_pair(ora):

@@ -54,6 +54,20 @@ def test_oracle_real_image_pair(ora, golden_real):
     assert ora.pairwise_match_lowres(g["sift_1"], g["sift_0"], empty, empty, 500) == int(g["lowres_500"]) == 187
 
 
+def test_oracle_three_image_set(ora, golden_triple):
+    """BASELINE config 1 restated: 3 real images, all 3 pairs, against the reference's results."""
+    g = golden_triple
+    empty = np.zeros((0, 64), np.int8)
+    counts = {}
+    for v1 in range(1, 3):
+        for v2 in range(v1):
+            m12, m21 = ora.pairwise_match(g[f"sift_{v1}"], g[f"sift_{v2}"], empty, empty)
+            assert np.array_equal(m12, g[f"match_{v1}{v2}_12"]) and np.array_equal(m21, g[f"match_{v1}{v2}_21"])
+            assert ora.pairwise_match_lowres(g[f"sift_{v1}"], g[f"sift_{v2}"], empty, empty, 500) == int(g[f"lowres_{v1}{v2}"])
+            counts[(v1, v2)] = int((m12 >= 0).sum())
+    assert counts == {(1, 0): 810, (2, 0): 810, (2, 1): 2376}
+
+
 def test_oracle_quantiser_golden(ora, golden_real):
     g = golden_real
     assert np.array_equal(ora.quantize_sift(g["float_sample"]), g["float_sample_q"])

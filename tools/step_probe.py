@@ -17,5 +17,5 @@ with ExhaustiveMatching() as m:
     for _ in range(steps):
         loff = m.match_pairs_compact(pairs, out)
         st = m.stats()
-        print(f"device {st['last_total_ms']:.3f} ms  filter {st['last_scan_ms']:.3f} ms", flush=True)
+        print(f"device {st['last_total_ms']:.3f} ms  " + "  ".join(f"{k} {v:.3f}" for k, v in st["last_phase_ms"].items()), flush=True)
     print({k: v for k, v in st.items() if "rows" in k or k in ("kernel_launches", "self_check_failures")}, int(loff[-1]))
