@@ -743,6 +743,31 @@ def run_ours(args, cfg, config):
         except Exception as ex:  # noqa: BLE001
             cudasift = {"error": repr(ex)}
 
+    # ---- the float path (Matching::twoway_match<float>, nearest_neighbor.cc:141-210, 272-289): one pair
+    float_path = None
+    if world == 1:
+        try:
+            from orthosfm_b200 import Matching
+            fa = (job.pool[n:2 * n].float() / 255.0).cpu().numpy()
+            fb = (job.pool[:n].float() / 255.0).cpu().numpy()
+            fa /= np.linalg.norm(fa, axis=1, keepdims=True)
+            fb /= np.linalg.norm(fb, axis=1, keepdims=True)
+            opts_f = Matching.Options(128, 0.8, float(np.finfo(np.float32).max))
+            ts = []
+            for _ in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rf = job.m.twoway_match_f32(opts_f, fa, fb)
+                ts.append(time.perf_counter() - t0)
+            s_f = min(ts[1:])
+            float_path = {"pair_ms": 1e3 * s_f, "comparisons_per_s": n * n / s_f,
+                          "matches_1_2": int((rf.matches_1_2 >= 0).sum()),
+                          "note": f"osfm_match_twoway_f32, one pair {n} x {n} x 128 floats, host buffers in and out (H2D "
+                                  f"{2 * n * 512} B inside); CUDA-core kernel, the reference's SSE3 summation order "
+                                  "(bit-identical results, not merely within the tie tolerance)"}
+        except Exception as ex:  # noqa: BLE001
+            float_path = {"error": repr(ex)}
+
     final_stats = job.m.stats()
     # ---- config 3 under an extra key at N = 1 and N = 8, so the strong-scaling curve is like for like
     extra3 = None
@@ -804,6 +829,7 @@ def run_ours(args, cfg, config):
         "both_directions_device_ms": both_ms,
         "cpu_baseline": cpu_base,
         "cudasift_baseline": cudasift,
+        "float_path": float_path,
         "device_ms_per_step": r["device_ms_max"],
         "lists_equal_single_gpu_on_sample": check,
         "matches_equal_reference_on_sample": ref_check,

@@ -409,6 +409,9 @@ typedef struct {
                                     batches: [0] filter pass, [1] classify + certify, [2] RESOLVE / EXACT of
                                     the forward direction, [3] claims + targets, [4] RESOLVE / EXACT of the
                                     claimed rows, [5] mutual filter, [6] list compaction, [7] unused */
+    int64_t reverse_restricted_pairs; /* (pair, kind) jobs whose reverse direction was held against a subset of the
+                                    other view only: the rows whose own best similarity can matter; cumulative */
+    int64_t reverse_candidate_rows;   /* rows in those subsets, cumulative */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
@@ -417,9 +420,11 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
 /* mode 0 = normal; 1 = scan kernel skips the epilogue reduction (MMA+TMA only);
  * 2 = epilogue reads TMEM but does not reduce.  Results are invalid for != 0. */
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
-/* on != 0: the filtered entry points run BOTH directions of every pair through the filter pass
+/* on = 1: the filtered entry points run BOTH directions of every pair through the filter pass
  * (Matching::twoway_match as the reference executes it, matching.h:155-158) instead of one
- * direction plus the claimed rows of the other.  Same results; for A/B tests and timing. */
+ * direction plus the claimed rows of the other.  on = 2: one direction plus the claimed rows, but
+ * those are held against the whole other view instead of the subset of its rows that can matter.
+ * on = 0: the default.  Same results in every mode; for A/B tests and timing. */
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on);
 /* Writes the raw int32 similarity matrix of one (query view, candidate view)
  * SIFT job as computed by the tensor-core kernel: out is n_q x ld ints,

@@ -60,7 +60,8 @@ class Stats(C.Structure):
                 ("self_check_failures", C.c_int64), ("last_scan_ms", C.c_double),
                 ("last_total_ms", C.c_double), ("last_comparisons", C.c_int64),
                 ("exact_rows", C.c_int64), ("last_scan_sm_cycles", C.c_int64), ("last_scan_ns", C.c_int64),
-                ("claimed_rows", C.c_int64), ("last_phase_ms", C.c_double * 8)]
+                ("claimed_rows", C.c_int64), ("last_phase_ms", C.c_double * 8),
+                ("reverse_restricted_pairs", C.c_int64), ("reverse_candidate_rows", C.c_int64)]
 
     PHASES = ("filter", "classify", "resolve_fwd", "claim", "resolve_rev", "mutual", "compact")
 

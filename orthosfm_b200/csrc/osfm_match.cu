@@ -201,6 +201,7 @@ struct osfm_matcher {
     DevBuf<int2> d_rowres;
     DevBuf<int32_t> d_oneway;
     DevBuf<int64_t> d_cand;
+    DevBuf<int64_t> d_cand_rev;          // claimed rows without the norm certificate (reverse pass)
     DevBuf<int4> d_big;
     DevBuf<PairPart> d_parts;
     DevBuf<int32_t> d_dense;
@@ -224,6 +225,16 @@ struct osfm_matcher {
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
     DevBuf<int32_t> d_rev_of;            // per job: the reverse job of its pair (or -1)
+    // restricted candidate sets of the reverse pass (select_candidates_kernel)
+    DevBuf<int32_t> d_tau;
+    DevBuf<ScanJob> d_jobs_rev;
+    DevBuf<int32_t> d_seg_first_rev;
+    DevBuf<uint8_t> d_cand_pool;
+    DevBuf<int32_t> d_cand_map;
+    CUtensorMap cand_tmap;
+    uint8_t* cand_tmap_for = nullptr;
+    size_t cand_tmap_rows = 0;
+    int reverse_mode = 0;                // 0: restricted candidate sets; 2: whole views (A/B switch)
     DevBuf<uint32_t> d_replay_flags;     // bitmap over a batch's rows: already in the replay list
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
     // survivors), [1] EXACT (unsigned rows without the 16-bit norm certificate)
@@ -456,7 +467,7 @@ cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, i
     ex.norm2 = k.d_norm2.p;
     ex.viewmax = k.d_viewmax.p;
     scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
+        k.tmap, k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
         m->d_counters + 6);
     return cudaGetLastError();
 }
@@ -471,9 +482,19 @@ cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int
 // rows without certificate): plan, gather, and that variant of the scan kernel.  Everything is
 // sized on the device; the host never learns how many rows there were until it reads the
 // counters.
+// The reverse RESOLVE pass over restricted candidate sets: its own copy of the job list (reverse
+// jobs redirected to their subsets), one segment per reverse job, the gathered candidate pool.
+struct ReverseSubset {
+    const ScanJob* jobs;
+    const int32_t* seg_first;
+    int nseg;
+    const CUtensorMap* tmap;
+    const int32_t* col_map;
+};
+
 template <int PASS, bool SIGNED>
 int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, int64_t rows, const PostParams& pp,
-                       bool verify) {
+                       bool verify, const ReverseSubset* subset = nullptr) {
     osfm_matcher::SecondPass& sp = m->pass[PASS == kPassResolve ? 0 : 1];
     CU_TRY(m, sp.job_xrow.reserve(static_cast<size_t>(njobs)));
     CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(nseg) + 1));
@@ -484,7 +505,10 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         sp.tmap_for = sp.xpool.p;
         sp.tmap_rows = sp.xpool.cap;
     }
-    plan_rows_kernel<<<1, 1024, 0, m->stream>>>(m->d_jobs.p, m->d_seg_first.p, nseg, sp.cnt.p,
+    if (subset) CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(subset->nseg) + 1));
+    plan_rows_kernel<<<1, 1024, 0, m->stream>>>(subset ? subset->jobs : m->d_jobs.p,
+                                                 subset ? subset->seg_first : m->d_seg_first.p,
+                                                 subset ? subset->nseg : nseg, sp.cnt.p,
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
                                                  PASS == kPassExact ? m->d_counters + 5 : nullptr);
     CU_TRY(m, cudaGetLastError());
@@ -510,6 +534,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     ex.norm2 = nullptr;
     ex.viewmax = nullptr;
     ex.verify = verify ? 1 : 0;
+    ex.col_map = subset ? subset->col_map : nullptr;
     ex.replay_flags = nullptr;
     if (PASS == kPassExact) {
         CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
@@ -523,7 +548,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     scan_kernel<0, PASS, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
-        sp.tmap, k.tmap, sp.xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
+        sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 3;
     if (PASS == kPassExact) {
@@ -535,6 +560,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         PostParams rp = pp;
         rp.slow_list = m->d_cand.p;
         rp.counters = m->d_counters + 8;
+        rp.slow_len = m->d_counters + 8;
         slow_rows_kernel<false><<<m->num_sms * 2, 256, 0, m->stream>>>(rp);
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches += 2;
@@ -567,6 +593,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     std::vector<int32_t> seg_first;   // first job of every (direction, candidate view, c_n) segment
     std::vector<int32_t> job_of(specs.size(), -1);
     int64_t rows = 0, items = 0, fwd_rows = 0;
+    int fwd_jobs = 0;
     bool prev_reverse = false;
     for (size_t oi = 0; oi < order.size(); ++oi) {
         size_t const i = order[oi];
@@ -589,6 +616,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         if (!s.reverse) {
             items += (s.q_n + kItemM - 1) / kItemM;
             fwd_rows = rows;
+            fwd_jobs = static_cast<int>(jobs.size()) + 1;
         }
         jobs.push_back(j);
     }
@@ -676,6 +704,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     cp.exact_cnt = m->pass[1].cnt.p;
     cp.uncert_list = m->d_cand.p;
     cp.counters = m->d_counters;
+    cp.uncert_len = m->d_counters + 0;
     cp.sq_lowe = sq_lowe;
     cp.sq_dist = sq_dist;
 
@@ -688,18 +717,19 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     pp.sq_dist = sq_dist;
     pp.slow_list = m->d_cand.p;
     pp.counters = m->d_counters;
+    pp.slow_len = m->d_counters + 0;
 
     // The rows queued by classify_kernel / targets_kernel: CUDA-core replay of the signed rows
     // without certificate, RESOLVE pass, EXACT pass.
-    auto second_passes = [&](bool verify) -> int {
+    auto second_passes = [&](bool verify, const ReverseSubset* subset) -> int {
         if (k.is_signed) {
             // rows without the norm certificate (adversarial input only): warp-per-row emulation
             slow_rows_kernel<true><<<m->num_sms * 2, 256, 0, m->stream>>>(pp);
             CU_TRY(m, cudaGetLastError());
             m->stats.kernel_launches++;
-            OS_TRY((launch_second_pass<kPassResolve, true>(m, k, njobs, nseg, rows, pp, verify)));
+            OS_TRY((launch_second_pass<kPassResolve, true>(m, k, njobs, nseg, rows, pp, verify, subset)));
         } else {
-            OS_TRY((launch_second_pass<kPassResolve, false>(m, k, njobs, nseg, rows, pp, verify)));
+            OS_TRY((launch_second_pass<kPassResolve, false>(m, k, njobs, nseg, rows, pp, verify, subset)));
             OS_TRY((launch_second_pass<kPassExact, false>(m, k, njobs, nseg, rows, pp, verify)));
         }
         return OSFM_OK;
@@ -719,7 +749,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
             m->stats.kernel_launches++;
         }
         CU_TRY(m, m->phases.mark(m->stream, kPhResolveFwd));
-        OS_TRY(second_passes(false));
+        OS_TRY(second_passes(false, nullptr));
     }
 
     if (have_reverse) {
@@ -730,11 +760,18 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         CU_TRY(m, cudaMemsetAsync(m->d_rowres.p + fwd_rows, 0xff, sizeof(int2) * rev_rows, m->stream));
         for (int i = 0; i < (k.is_signed ? 1 : 2); ++i)
             CU_TRY(m, cudaMemsetAsync(m->pass[i].cnt.p, 0, sizeof(int) * njobs, m->stream));
-        CU_TRY(m, cudaMemsetAsync(m->d_counters, 0, sizeof(unsigned long long), m->stream));  // [0]
+        CU_TRY(m, cudaMemsetAsync(m->d_counters + 11, 0, sizeof(unsigned long long), m->stream));
+        CU_TRY(m, m->d_cand_rev.reserve(static_cast<size_t>(rev_rows)));
+        bool const restricted = m->reverse_mode == 0;
+        if (restricted) {
+            CU_TRY(m, m->d_tau.reserve(static_cast<size_t>(njobs)));
+            CU_TRY(m, cudaMemsetAsync(m->d_tau.p, 0x7f, sizeof(int32_t) * njobs, m->stream));   // "no claim yet"
+        }
+        // Every forward row whose result can be a match sits in one of the second passes' row lists
+        // (the rest was rejected by the filter): claims are made list by list.
         ClaimParams cl;
         cl.jobs = m->d_jobs.p;
         cl.rev_of = m->d_rev_of.p;
-        cl.fwd_rows = fwd_rows;
         cl.pool = k.pool;
         cl.oneway = m->d_oneway.p;
         cl.rowres = m->d_rowres.p;
@@ -742,21 +779,86 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         cl.viewmax = k.d_viewmax.p;
         cl.surv_list = m->pass[0].list.p;
         cl.surv_cnt = m->pass[0].cnt.p;
-        cl.uncert_list = m->d_cand.p;
+        cl.uncert_list = m->d_cand_rev.p;
+        cl.uncert_len = m->d_counters + 11;
         cl.counters = m->d_counters;
-        int const fgrid = static_cast<int>((fwd_rows + 255) / 256);
-        cp.total_rows = rows;
+        cl.smin = restricted ? m->d_tau.p : nullptr;
+        // the lists' lengths are only known on the device; a thread's work is one long chain of
+        // dependent loads, so the grid covers the longest possible list rather than striding
+        int const cgrid = static_cast<int>(std::min<int64_t>((fwd_rows + 255) / 256, static_cast<int64_t>(m->num_sms) * 256));
+        cl.rows = m->pass[0].xrow_map.p;          // RESOLVE pass: the entries carry the rows' best similarity
+        cl.n_int = m->pass[0].d_xmeta + 2;
+        cl.n_ull = nullptr;
+        if (k.is_signed) claim_kernel<true, true><<<cgrid, 256, 0, m->stream>>>(cl);
+        else             claim_kernel<false, true><<<cgrid, 256, 0, m->stream>>>(cl);
         if (k.is_signed) {
-            claim_kernel<true><<<fgrid, 256, 0, m->stream>>>(cl);
+            cl.rows = m->d_cand.p;                // rows replayed on CUDA cores (classify_kernel's flat list)
+            cl.n_int = nullptr;
+            cl.n_ull = m->d_counters + 0;
+            claim_kernel<true, false><<<cgrid, 256, 0, m->stream>>>(cl);
         } else {
-            claim_kernel<false><<<fgrid, 256, 0, m->stream>>>(cl);
-            certify_kernel<true><<<m->num_sms * 8, 256, 0, m->stream>>>(cp);
-            m->stats.kernel_launches++;
+            cl.rows = m->pass[1].xrow_map.p;      // EXACT pass
+            cl.n_int = m->pass[1].d_xmeta + 2;
+            claim_kernel<false, false><<<cgrid, 256, 0, m->stream>>>(cl);
         }
         CU_TRY(m, cudaGetLastError());
-        m->stats.kernel_launches++;
+        m->stats.kernel_launches += 2;
+        cp.total_rows = rows;
+        cp.uncert_list = m->d_cand_rev.p;
+        cp.uncert_len = m->d_counters + 11;
+        pp.slow_list = m->d_cand_rev.p;
+        pp.slow_len = m->d_counters + 11;
+        if (!k.is_signed) {
+            certify_kernel<true><<<m->num_sms * 32, 256, 0, m->stream>>>(cp);
+            CU_TRY(m, cudaGetLastError());
+            m->stats.kernel_launches++;
+        }
+        ReverseSubset subset;
+        if (restricted) {
+            // candidate subsets of the reverse jobs (post_kernels.cuh, select_candidates_kernel)
+            std::vector<int32_t> seg_rev;
+            for (int j = fwd_jobs; j <= njobs; ++j) seg_rev.push_back(j);        // every reverse job alone
+            CU_TRY(m, m->d_seg_first_rev.reserve(seg_rev.size()));
+            CU_TRY(m, cudaMemcpyAsync(m->d_seg_first_rev.p, seg_rev.data(), sizeof(int32_t) * seg_rev.size(),
+                                      cudaMemcpyHostToDevice, m->stream));
+            CU_TRY(m, m->d_jobs_rev.reserve(jobs.size()));
+            CU_TRY(m, cudaMemcpyAsync(m->d_jobs_rev.p, m->d_jobs.p, sizeof(ScanJob) * jobs.size(),
+                                      cudaMemcpyDeviceToDevice, m->stream));
+            CU_TRY(m, m->d_cand_pool.reserve(static_cast<size_t>(fwd_rows + kPadRows) * kRowBytes));
+            CU_TRY(m, m->d_cand_map.reserve(static_cast<size_t>(fwd_rows)));
+            if (m->cand_tmap_for != m->d_cand_pool.p || m->cand_tmap_rows != m->d_cand_pool.cap) {
+                OS_TRY(encode_tmap(m, &m->cand_tmap, m->d_cand_pool.p, static_cast<int64_t>(m->d_cand_pool.cap / kRowBytes)));
+                m->cand_tmap_for = m->d_cand_pool.p;
+                m->cand_tmap_rows = m->d_cand_pool.cap;
+            }
+            SelectParams sel;
+            sel.jobs = m->d_jobs.p;
+            sel.jobs_rev = m->d_jobs_rev.p;
+            sel.rev_of = m->d_rev_of.p;
+            sel.fwd_jobs = fwd_jobs;
+            sel.rowres = m->d_rowres.p;
+            sel.norm2 = k.d_norm2.p;
+            sel.viewmax = k.d_viewmax.p;
+            sel.smin = m->d_tau.p;
+            sel.sq_lowe = sq_lowe;
+            sel.sq_dist = sq_dist;
+            sel.surv_cnt = m->pass[0].cnt.p;
+            sel.pool = k.pool;
+            sel.cand_pool = m->d_cand_pool.p;
+            sel.cand_map = m->d_cand_map.p;
+            sel.counters = m->d_counters;
+            if (k.is_signed) select_candidates_kernel<true><<<fwd_jobs, 1024, 0, m->stream>>>(sel);
+            else             select_candidates_kernel<false><<<fwd_jobs, 1024, 0, m->stream>>>(sel);
+            CU_TRY(m, cudaGetLastError());
+            m->stats.kernel_launches++;
+            subset.jobs = m->d_jobs_rev.p;
+            subset.seg_first = m->d_seg_first_rev.p;
+            subset.nseg = njobs - fwd_jobs;
+            subset.tmap = &m->cand_tmap;
+            subset.col_map = m->d_cand_map.p;
+        }
         CU_TRY(m, m->phases.mark(m->stream, kPhResolveRev));
-        OS_TRY(second_passes(true));
+        OS_TRY(second_passes(true, restricted ? &subset : nullptr));
     }
     CU_TRY(m, m->phases.mark(m->stream, -1));
 
@@ -880,8 +982,10 @@ int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense
 }
 
 int read_counters(osfm_matcher* m) {
-    unsigned long long c[8];
+    unsigned long long c[16];
     CU_TRY(m, cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    m->stats.reverse_candidate_rows = static_cast<int64_t>(c[9]);
+    m->stats.reverse_restricted_pairs = static_cast<int64_t>(c[10]);
     m->stats.exact_rows = static_cast<int64_t>(c[5]);
     m->stats.last_scan_sm_cycles = static_cast<int64_t>(c[6]);
     m->stats.last_scan_ns = static_cast<int64_t>(c[7]);
@@ -1011,8 +1115,8 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     CU_TRY(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU_TRY(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : m->ev) CU_TRY(m, cudaEventCreate(&ev));
-    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 16 * sizeof(unsigned long long)));
-    CU_TRY(m, cudaMemset(m->d_counters, 0, 16 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_counters), 32 * sizeof(unsigned long long)));
+    CU_TRY(m, cudaMemset(m->d_counters, 0, 32 * sizeof(unsigned long long)));
     for (auto& sp : m->pass) {
         CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&sp.d_xmeta), 4 * sizeof(int)));
         CU_TRY(m, cudaMemset(sp.d_xmeta, 0, 4 * sizeof(int)));
@@ -1052,7 +1156,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     reset_kind(m->kind[0], true);
     reset_kind(m->kind[1], true);
     m->d_jobs.release(); m->d_rowres.release(); m->d_oneway.release();
-    m->d_cand.release(); m->d_big.release();
+    m->d_cand.release(); m->d_cand_rev.release(); m->d_big.release();
     m->d_parts.release(); m->d_dense.release(); m->d_counts.release(); m->d_listoff.release(); m->d_list.release();
     m->tr_ints.release(); m->tr_table.release(); m->tr_meta.release(); m->tr_meta32.release();
     m->rs_xy.release(); m->rs_pos.release(); m->rs_samples.release(); m->rs_F.release(); m->rs_cnt.release();
@@ -1066,6 +1170,8 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_ftmp.release();
     m->d_seg_first.release();
     m->d_rev_of.release();
+    m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
+    m->d_cand_pool.release(); m->d_cand_map.release();
     m->d_replay_flags.release();
     for (auto& sp : m->pass) sp.release();
     if (m->d_counters) cudaFree(m->d_counters);
@@ -2643,6 +2749,8 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
         out->slow_rows += p->stats.slow_rows;
         out->exact_rows += p->stats.exact_rows;
         out->claimed_rows += p->stats.claimed_rows;
+        out->reverse_candidate_rows += p->stats.reverse_candidate_rows;
+        out->reverse_restricted_pairs += p->stats.reverse_restricted_pairs;
         out->self_check_failures += p->stats.self_check_failures;
     }
     return OSFM_OK;
@@ -2651,8 +2759,9 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
-    m->both_directions = on != 0;
-    for (osfm_matcher* p : m->peers) p->both_directions = on != 0;
+    m->both_directions = on == 1;
+    m->reverse_mode = on == 2 ? 2 : 0;
+    for (osfm_matcher* p : m->peers) { p->both_directions = m->both_directions; p->reverse_mode = m->reverse_mode; }
     return OSFM_OK;
 }
 

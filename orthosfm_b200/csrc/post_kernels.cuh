@@ -204,6 +204,7 @@ struct PostParams {
     float sq_dist;              // distance_threshold^2     (matching.h:127)
     int64_t* slow_list;         // rows slow_rows_kernel replays
     unsigned long long* counters;  // [0] length of slow_list
+    const unsigned long long* slow_len;   // length of slow_list (normally counters + 0)
 };
 
 // ---------------------------------------------------------------- filter decision
@@ -225,8 +226,9 @@ struct ClassifyParams {
     int* exact_cnt;
     int64_t* uncert_list;        // rows without certificate from the norms alone, flat: signed kind:
                                  // CUDA-core replay; unsigned kind: certify_kernel's input
-    unsigned long long* counters;  // [0] uncert_list length, [1] certified survivors (cumulative),
+    unsigned long long* counters;  // [1] certified survivors (cumulative),
                                    // [3] rows that stay without certificate (cumulative)
+    unsigned long long* uncert_len;   // length of uncert_list
     float sq_lowe, sq_dist;
 };
 
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
     unsigned const wm = __ballot_sync(0xffffffffu, wraps);
     if (um != 0) {
         unsigned long long ub = 0;
-        if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
+        if (lane == 0) ub = atomicAdd(p.uncert_len, static_cast<unsigned long long>(__popc(um)));
         ub = __shfl_sync(0xffffffffu, ub, 0);
         if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = g;
     }
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 template <bool TARGETS>
 __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
 {
-    int64_t const n = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.counters + 0));
+    int64_t const n = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.uncert_len));
     int const lane = threadIdx.x & 31;
     int64_t const nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     unsigned n_exact = 0, n_surv = 0;
@@ -387,7 +389,11 @@ __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
 struct ClaimParams {
     const ScanJob* jobs;
     const int32_t* rev_of;       // per job: its pair's reverse job (or -1)
-    int64_t fwd_rows;            // rows [0, fwd_rows) belong to forward (scanned) jobs
+    // the forward rows whose result may be a match: a second pass's gathered row list (xrow_map,
+    // length *n_int) or the flat list of rows replayed on CUDA cores (length *n_ull)
+    const int64_t* rows;
+    const int* n_int;
+    const unsigned long long* n_ull;
     const uint8_t* pool;
     const int32_t* oneway;
     int2* rowres;                // forward rows: the filter's record; reverse rows: (V, job), preset to -1
@@ -396,83 +402,215 @@ struct ClaimParams {
     int64_t* surv_list;          // RESOLVE queue of the reverse jobs (certified rows), per job at out_row
     int* surv_cnt;
     int64_t* uncert_list;        // claimed rows without certificate, flat
-    unsigned long long* counters;   // [0] uncert_list length, [3] signed rows without certificate, [4] claimed rows
+    unsigned long long* uncert_len;
+    unsigned long long* counters;   // [3] signed rows without certificate, [4] claimed rows
+    int32_t* smin;               // per reverse job: the smallest claimed value (nullptr: not wanted)
 };
 
-// One thread per forward row.  The FIRST claimant of a row (the atomic maximum returns the preset
-// -1) also queues it; the value the queue entry carries is filled in later, from the slot, once
-// every claim has landed (gather_rows_kernel).
+// The largest similarity t <= s for which a best of s and a second best of t still pass the
+// reference's tests (matching.h:138-143); -1 if even a second best of 0 fails.  The tests are
+// monotone in t (the distance falls as t grows, the quotient rises), so a bisection finds it.
 template <bool SIGNED>
+__device__ __forceinline__ int ratio_limit(int s, float sq_lowe, float sq_dist) {
+    int const d1 = ip_to_dist<SIGNED>(s);
+    if (!passes_tests(d1, ip_to_dist<SIGNED>(0), sq_lowe, sq_dist)) return -1;
+    int lo = 0, hi = s;              // passes at lo; find the largest passing value in [lo, hi]
+    while (lo < hi) {
+        int const mid = lo + (hi - lo + 1) / 2;
+        if (passes_tests(d1, ip_to_dist<SIGNED>(mid), sq_lowe, sq_dist)) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// One thread per listed forward row (grid-stride: the list length is only known on the device).
+// TRUSTED: the list is the RESOLVE pass's, whose entries carry the row's best similarity -- which
+// IS the similarity of the row with its match; otherwise (EXACT pass, replay) the product is
+// computed again.  The FIRST claimant of a row (the atomic maximum returns the preset -1) also
+// queues it; the value the queue entry carries is filled in later, from the slot, once every claim
+// has landed (gather_rows_kernel).
+template <bool SIGNED, bool TRUSTED>
 __global__ void __launch_bounds__(256) claim_kernel(ClaimParams p)
 {
-    int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t const n = p.n_int != nullptr ? static_cast<int64_t>(*p.n_int)
+                                         : static_cast<int64_t>(*reinterpret_cast<const volatile unsigned long long*>(p.n_ull));
     int const lane = threadIdx.x & 31;
-    bool first = false, certified = false;
-    int rj = -1;
-    int64_t target = 0, out_row = 0;
-    if (g < p.fwd_rows) {
-        int const mt = p.oneway[g];
-        if (mt >= 0) {
-            int2 const rr = p.rowres[g];
-            int const ji = rr.y & kRowJobMask;
-            rj = p.rev_of[ji];
-            if (rj >= 0) {
-                ScanJob const job = p.jobs[ji];
-                // The similarity of the claimant with its match IS its row's best, which the filter
-                // recorded exactly if no similarity of the row left the 16-bit range (norm certificate,
-                // or scanned with 32-bit loads and found below 2^16).  Only the few rows that went
-                // through the EXACT pass / the replay need the product computed again.
-                int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
-                int const q_prow = job.q_row + static_cast<int>(g - job.out_row);
-                bool const trusted = flag == kRowWideOk ||
-                    (flag == kRowPacked && static_cast<int64_t>(p.norm2[q_prow]) * static_cast<int64_t>(p.viewmax[job.c_view]) <
-                                               (SIGNED ? (1ll << 30) : (1ll << 32)));
-                int s;
-                if (trusted)
-                    s = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
-                else
-                    s = dot_row<SIGNED>(p.pool + static_cast<int64_t>(q_prow) * kRowBytes,
-                                        p.pool + (static_cast<int64_t>(job.c_row) + mt) * kRowBytes);
-                s = max(s, 0);       // the reference's best starts at 0 (nearest_neighbor.cc:221-224, 246-249)
-                ScanJob const rjob = p.jobs[rj];
-                out_row = rjob.out_row;
-                target = out_row + mt;
-                int2* const slot = p.rowres + target;
-                first = atomicMax(&slot->x, s) < 0;
-                if (first) {
-                    slot->y = rj;
-                    int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
-                    int64_t const qn2 = p.norm2[rjob.q_row + mt];
-                    certified = qn2 * static_cast<int64_t>(p.viewmax[rjob.c_view]) < limit;
+    int64_t const stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    // (whole warps leave the loop together: the bound is rounded up to the warp)
+    for (int64_t k0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); k0 < n; k0 += stride) {
+        int64_t const k = k0 + lane;
+        bool first = false, certified = false;
+        int rj = -1, claimed_s = -1;
+        int64_t target = 0, out_row = 0;
+        if (k < n) {
+            int64_t const entry = p.rows[k];
+            int64_t const g = surv_row(entry);
+            int const mt = p.oneway[g];
+            if (mt >= 0) {
+                int const ji = p.rowres[g].y & kRowJobMask;
+                rj = p.rev_of[ji];
+                if (rj >= 0) {
+                    int s;
+                    if (TRUSTED) {
+                        uint32_t const v16 = static_cast<uint32_t>((static_cast<uint64_t>(entry) >> kSurvRowBits) & 0xffffu);
+                        s = SIGNED ? static_cast<int>(static_cast<short>(v16)) : static_cast<int>(v16);
+                    } else {
+                        ScanJob const job = p.jobs[ji];
+                        s = dot_row<SIGNED>(p.pool + (static_cast<int64_t>(job.q_row) + (g - job.out_row)) * kRowBytes,
+                                            p.pool + (static_cast<int64_t>(job.c_row) + mt) * kRowBytes);
+                    }
+                    s = max(s, 0);   // the reference's best starts at 0 (nearest_neighbor.cc:221-224, 246-249)
+                    claimed_s = s;
+                    ScanJob const rjob = p.jobs[rj];
+                    out_row = rjob.out_row;
+                    target = out_row + mt;
+                    int2* const slot = p.rowres + target;
+                    first = atomicMax(&slot->x, s) < 0;
+                    if (first) {
+                        slot->y = rj;
+                        int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+                        int64_t const qn2 = p.norm2[rjob.q_row + mt];
+                        certified = qn2 * static_cast<int64_t>(p.viewmax[rjob.c_view]) < limit;
+                    }
                 }
             }
         }
+        // the smallest claimed value per job: one atomic per job present in the warp (the lists are
+        // ordered by job, so unaggregated atomics would queue up on a handful of addresses)
+        if (p.smin != nullptr) {
+            unsigned const cm = __ballot_sync(0xffffffffu, claimed_s >= 0);
+            if (claimed_s >= 0) {
+                unsigned const peers = __match_any_sync(cm, rj);
+                int const mn = __reduce_min_sync(peers, claimed_s);
+                if (lane == __ffs(peers) - 1) atomicMin(p.smin + rj, mn);
+            }
+        }
+        // certified rows -> the reverse job's RESOLVE queue, one atomic per job present in the warp
+        bool const queue = first && certified;
+        unsigned const qm = __ballot_sync(0xffffffffu, queue);
+        if (queue) {
+            unsigned const peers = __match_any_sync(qm, rj);
+            int const leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.surv_cnt + rj, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(target, 0, true);
+        }
+        // without certificate: signed -> CUDA-core replay; unsigned -> certify_kernel<true> looks at
+        // the few candidates that could take the row to 2^16
+        bool const doubtful = first && !certified;
+        unsigned const um = __ballot_sync(0xffffffffu, doubtful);
+        if (um != 0) {
+            unsigned long long ub = 0;
+            if (lane == 0) ub = atomicAdd(p.uncert_len, static_cast<unsigned long long>(__popc(um)));
+            ub = __shfl_sync(0xffffffffu, ub, 0);
+            if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = target;
+        }
+        unsigned const fm = __ballot_sync(0xffffffffu, first);
+        if (lane == 0) {
+            if (fm) atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(fm)));      // claimed rows (cumulative)
+            if (SIGNED && um) atomicAdd(p.counters + 3, static_cast<unsigned long long>(__popc(um)));   // unsigned: certify_kernel counts
+        }
     }
-    // certified rows -> the reverse job's RESOLVE queue, one atomic per job present in the warp
-    bool const queue = first && certified;
-    unsigned const qm = __ballot_sync(0xffffffffu, queue);
-    if (queue) {
-        unsigned const peers = __match_any_sync(qm, rj);
-        int const leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(p.surv_cnt + rj, __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        p.surv_list[out_row + base + __popc(peers & ((1u << lane) - 1u))] = surv_entry(target, 0, true);
+}
+
+// Restricted candidate sets for the reverse pass.  One CTA per forward job (pair).  The reverse
+// job of the pair holds its claimed rows against the forward job's query rows; of those only the
+// rows whose own best similarity exceeds tau (below) -- or whose record is not exact -- can
+// matter, and the filter pass has that best similarity for every row already.  The kernel compacts
+// them, in order (ties go to the highest index: the order must survive), into the gathered
+// candidate pool at the forward job's own row offset, records the column -> row map, and points the
+// reverse job (in the copy of the job list the reverse RESOLVE pass plans from) at the subset, flagged
+// by a negative c_view.  Pairs where the subset would not pay (more than half of the rows) keep
+// the whole view.
+struct SelectParams {
+    const ScanJob* jobs;
+    ScanJob* jobs_rev;           // copy of jobs; reverse entries are redirected here
+    const int32_t* rev_of;
+    int fwd_jobs;                // jobs [0, fwd_jobs) are forward jobs
+    const int2* rowres;
+    const int32_t* norm2;
+    const int32_t* viewmax;
+    const int32_t* smin;         // per reverse job: the smallest claimed value (claim_kernel)
+    float sq_lowe, sq_dist;
+    const int* surv_cnt;         // claimed rows per reverse job queued for the RESOLVE pass
+    const uint8_t* pool;
+    uint8_t* cand_pool;
+    int32_t* cand_map;
+    unsigned long long* counters;   // [9] candidate rows kept (cumulative), [10] pairs restricted (cumulative)
+};
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(1024) select_candidates_kernel(SelectParams p)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int running;
+    int const ji = blockIdx.x;
+    int const rj = p.rev_of[ji];
+    if (rj < 0 || p.surv_cnt[rj] == 0) return;          // nothing claimed: the reverse job has no work
+    ScanJob const job = p.jobs[ji];
+    // Rows of this view whose own best similarity is at most tau cannot influence what the reverse
+    // pass decides about any row this pair claims: with s the smallest claimed value, they lie below
+    // every claimed value (so they neither beat nor tie one) and at most at the largest second best
+    // that still passes the ratio test beside a best of s -- and beside any larger best, the limit
+    // being monotone in the best (so they cannot turn an accept into a reject).
+    int const sm = p.smin[rj];
+    int const tau = min(ratio_limit<SIGNED>(sm, p.sq_lowe, p.sq_dist), sm - 1);
+    int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+    int64_t const vmax = p.viewmax[job.c_view];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int start = 0; start < job.q_n; start += blockDim.x) {
+        int const r = start + threadIdx.x;
+        bool keep = false;
+        if (r < job.q_n) {
+            int2 const rr = p.rowres[job.out_row + r];
+            int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
+            bool const trusted = flag == kRowWideOk ||
+                (flag == kRowPacked && static_cast<int64_t>(p.norm2[job.q_row + r]) * vmax < limit);
+            int const v1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
+            keep = !trusted || v1 > tau;
+        }
+        unsigned const b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(b);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        int total = 0;
+        if (threadIdx.x == 0)
+            for (int w = 0; w < 32; ++w) total += warp_tot[w];
+        int const run = running;
+        if (keep) p.cand_map[job.out_row + run + before + __popc(b & ((1u << lane) - 1u))] = r;
+        __syncthreads();
+        if (threadIdx.x == 0) running = run + total;
+        __syncthreads();
     }
-    // without certificate: signed -> CUDA-core replay; unsigned -> certify_kernel<true> looks at
-    // the few candidates that could take the row to 2^16
-    bool const doubtful = first && !certified;
-    unsigned const um = __ballot_sync(0xffffffffu, doubtful);
-    if (um != 0) {
-        unsigned long long ub = 0;
-        if (lane == 0) ub = atomicAdd(p.counters + 0, static_cast<unsigned long long>(__popc(um)));
-        ub = __shfl_sync(0xffffffffu, ub, 0);
-        if (doubtful) p.uncert_list[ub + __popc(um & ((1u << lane) - 1u))] = target;
+    int const cnt = running;
+    // not worth it for small views or when most rows stay: the reverse job keeps the whole view
+    if (job.q_n < 1024 || 2 * cnt > job.q_n) return;
+    // gather the kept rows (8 threads move one 128-byte row), then zero rows up to a whole number
+    // of candidate tiles, so that the RESOLVE pass never meets a ragged tile.  A zero row has
+    // similarity 0 with every row, below every claimed value of a restricted job (a claimed value
+    // of 0 gives tau = -1, which keeps every row and so the whole view) and no more than the
+    // reference's initial second best of 0.  padded <= q_n / 2 + 255 <= q_n: inside the job's slots.
+    int const padded = (cnt + kBlockN - 1) / kBlockN * kBlockN;
+    for (int e = threadIdx.x; e < padded * 8; e += blockDim.x) {
+        int const sidx = e >> 3, part = e & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (sidx < cnt) {
+            int const r = p.cand_map[job.out_row + sidx];
+            v = __ldg(reinterpret_cast<const uint4*>(p.pool + (static_cast<int64_t>(job.q_row) + r) * kRowBytes) + part);
+        }
+        reinterpret_cast<uint4*>(p.cand_pool + (job.out_row + sidx) * kRowBytes)[part] = v;
     }
-    unsigned const fm = __ballot_sync(0xffffffffu, first);
-    if (lane == 0) {
-        if (fm) atomicAdd(p.counters + 4, static_cast<unsigned long long>(__popc(fm)));      // claimed rows (cumulative)
-        if (SIGNED && um) atomicAdd(p.counters + 3, static_cast<unsigned long long>(__popc(um)));   // unsigned: certify_kernel counts
+    if (threadIdx.x == 0) {
+        ScanJob rjob = p.jobs[rj];
+        rjob.c_row = static_cast<int32_t>(job.out_row);
+        rjob.c_n = padded;
+        rjob.c_view = -1 - rjob.c_view;
+        p.jobs_rev[rj] = rjob;
+        atomicAdd(p.counters + 9, static_cast<unsigned long long>(cnt));
+        atomicAdd(p.counters + 10, 1ull);
     }
 }
 
@@ -485,7 +623,7 @@ __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
 {
     // The list length is only known on the device (written by a kernel that precedes this
     // launch in stream order); the grid strides over it.
-    int64_t const nslow = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long*>(p.counters + 0));
+    int64_t const nslow = static_cast<int64_t>(*reinterpret_cast<const volatile unsigned long long*>(p.slow_len));
     int const lane = threadIdx.x & 31;
     int64_t const nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < nslow; w += nwarps) {

@@ -158,6 +158,9 @@ struct ExactParams {
     // row's nearest neighbour is not one of its claimants, and the row's result is -1 as far as
     // the mutual filter is concerned.
     int verify;
+    // RESOLVE pass over a restricted candidate set (jobs with c_view < 0 read their candidates from
+    // the second candidate tensor map, a gathered subset of the view): column -> row of the view
+    const int32_t* col_map;
 };
 
 // Sets bit g of a bitmap; true for the caller that set it.  Keeps a row from entering the replay
@@ -385,6 +388,7 @@ __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, 
 template <int MODE, int PASS, bool SIGNED>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+            const __grid_constant__ CUtensorMap tmap_c2,
             const ScanJob* __restrict__ jobs, int total_items_host, uint32_t idesc, int ksteps,
             int32_t* __restrict__ dump, int64_t dump_ld, ExactParams ex, int2* __restrict__ rowres,
             unsigned long long* __restrict__ prof)
@@ -433,6 +437,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     if (warp == kProducerWarp && lane == 0) {
         prefetch_tensormap(&tmap_q);
         prefetch_tensormap(&tmap_c);
+        if (PASS == kPassResolve) prefetch_tensormap(&tmap_c2);
     }
     if (warp == kMmaWarp) {
         tmem_alloc(smem_base + kSmemTmemPtr, kTmemCols);
@@ -471,8 +476,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     mbar_arrive_expect_tx(b_full(s), kBTileBytes);
                     uint32_t const dst = smem_base + kSmemB + s * kBTileBytes;
                     int const row = job.c_row + t * kBlockN;
-                    tma_load_2d(dst, &tmap_c, b_full(s), 0, row);
-                    tma_load_2d(dst + kBTileBytes / 2, &tmap_c, b_full(s), 0, row + kBlockN / 2);
+                    // (RESOLVE: a job flagged by a negative c_view scans a gathered subset of its view)
+                    const CUtensorMap* const tm = (PASS == kPassResolve && job.c_view < 0) ? &tmap_c2 : &tmap_c;
+                    tma_load_2d(dst, tm, b_full(s), 0, row);
+                    tma_load_2d(dst + kBTileBytes / 2, tm, b_full(s), 0, row + kBlockN / 2);
                 }
             }
         }
@@ -861,7 +868,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     int const second = cnt >= 2 ? V0 : v2;
                     bool const ok = passes_tests(ip_to_dist<SIGNED>(V0), ip_to_dist<SIGNED>(second), ex.sq_lowe, ex.sq_dist);
                     // signed: a best of 0 may be the initial value, reached by no candidate: index 0
-                    ex.oneway[surv_row(entry)] = ok ? max(idx, 0) : -1;
+                    int const found = (job.c_view < 0 && idx >= 0) ? ex.col_map[job.c_row + idx] : max(idx, 0);
+                    ex.oneway[surv_row(entry)] = ok ? found : -1;
                     if (cnt == 0 && !(SIGNED && V0 == 0)) atomicAdd(ex.self_check, 1ull);   // the row's best was not found
                 }
             }

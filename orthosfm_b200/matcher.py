@@ -508,7 +508,7 @@ class ExhaustiveMatching:
     def debug_set_both_directions(self, on: bool) -> None:
         """A/B switch: both directions of every pair through the filter pass (as the reference
         executes Matching::twoway_match) instead of one direction + the claimed rows of the other."""
-        self._check(self._L.osfm_match_debug_set_both_directions(self._h, 1 if on else 0))
+        self._check(self._L.osfm_match_debug_set_both_directions(self._h, int(on)))
 
     def debug_dump_similarity(self, kind: int, view_q: int, view_c: int) -> np.ndarray:
         k = 0 if kind == KIND_SIFT_U8 else 1

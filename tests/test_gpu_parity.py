@@ -361,16 +361,19 @@ def test_one_product_per_pair_equals_both_directions(ora, case):
         one = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
         lowres_one = m.pairwise_match_lowres(0, 1, 200)
         claimed = m.stats()["claimed_rows"]
-        m.debug_set_both_directions(True)
+        m.debug_set_both_directions(2)                    # claimed rows against the whole other view
+        whole = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
+        claimed_after_whole = m.stats()["claimed_rows"]
+        m.debug_set_both_directions(1)
         both = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
         lowres_both = m.pairwise_match_lowres(0, 1, 200)
-        assert m.stats()["claimed_rows"] == claimed       # nothing is claimed when both directions are scanned
+        assert m.stats()["claimed_rows"] == claimed_after_whole   # nothing is claimed when both directions are scanned
         assert_clean(m)
     o12, o21 = ora.twoway(kind, a, b, ratio)
     f12, f21 = ora.remove_inconsistent(o12, o21)
-    for r in (one[0], both[0]):
+    for r in (one[0], whole[0], both[0]):
         assert np.array_equal(r.matches_1_2, f12) and np.array_equal(r.matches_2_1, f21)
-    for r in (one[1], both[1]):
+    for r in (one[1], whole[1], both[1]):
         assert np.array_equal(r.matches_1_2, f21) and np.array_equal(r.matches_2_1, f12)
     assert lowres_one == lowres_both
     assert 0 <= claimed <= (o12 >= 0).sum() + (o21 >= 0).sum() + 200   # at most one row per forward match
