@@ -304,10 +304,11 @@ def tracks_compute(features, pair_views, offsets, ij):
 
 
 # ---- tracks.txt / AAA_BBB.txt -------------------------------------------------------------------
-# PARITY UNPINNED: src/matching/matching_io.cpp includes Boost, OpenCV and Eigen headers (through
-# data_structures/track.h), none of which is in this image, so the reference's writer cannot be
-# compiled here; the functions below restate it line by line and the reference holds no golden
-# file for these formats.
+# The functions below restate orthosfm's writer / reader line by line.  Parity is pinned: the
+# reference's own src/matching/matching_io.cpp is compiled, unmodified, into
+# _ref/libmatching_io_ref.so against stand-in third-party headers (oracle/stubs/, class
+# ReferenceTrackIO below); the restatement, the product's osfm_io_* and the committed golden files
+# (tests/golden/tracks_golden.txt, tests/golden/pairwise_golden/) are held against it.
 
 def _g(x) -> str:
     """operator<<(ostream&, float) with the default precision 6 -- printf's %g."""
@@ -674,3 +675,68 @@ def list_digest(ij: np.ndarray) -> int:
         for b in np.ascontiguousarray(ij, np.int32).view(np.uint8).reshape(-1):
             h = (h ^ np.uint64(b)) * prime
     return int(h)
+
+
+_MATCHING_IO_SO = os.path.join(_HERE, "_ref", "libmatching_io_ref.so")
+
+
+def have_ref_io() -> bool:
+    return os.path.exists(_MATCHING_IO_SO)
+
+
+class ReferenceTrackIO:
+    """The reference's own orthosfm::saveTracksToFile / loadTracksFromFile /
+    saveTracksToPairwiseFiles (src/matching/matching_io.cpp:16-140), compiled unmodified
+    (oracle/Makefile, matching_io_driver.cc).  Tracks are lists of
+    (viewID, localFeatureID, globalFeatureID, x, y, r, g, b) as tracks_from_ids builds them."""
+
+    def __init__(self):
+        self.lib = C.CDLL(_MATCHING_IO_SO)
+
+    @staticmethod
+    def _table(tracks):
+        offsets = np.concatenate([[0], np.cumsum([len(t) for t in tracks])]).astype(np.int64)
+        flat = [f for t in tracks for f in t]
+        ids = np.array([[f[0], f[1], f[2]] for f in flat], np.uint32).reshape(-1, 3)
+        xy = np.array([[f[3], f[4]] for f in flat], np.float32).reshape(-1, 2)
+        rgb = np.array([[f[5], f[6], f[7]] for f in flat], np.uint32).reshape(-1, 3)
+        return offsets, np.ascontiguousarray(ids), np.ascontiguousarray(xy), np.ascontiguousarray(rgb)
+
+    def save_tracks(self, path: str, tracks) -> None:
+        off, ids, xy, rgb = self._table(tracks)
+        self._quiet(lambda: self.lib.osfm_refio_save_tracks(
+            path.encode(), C.c_int64(len(tracks)), _ptr(off, C.c_int64), _ptr(ids, C.c_uint32), _ptr(xy, C.c_float),
+            _ptr(rgb, C.c_uint32)))
+
+    def save_pairwise(self, folder: str, tracks, num_views: int) -> None:
+        off, ids, xy, rgb = self._table(tracks)
+        self.lib.osfm_refio_save_pairwise(folder.encode(), C.c_int(num_views), C.c_int64(len(tracks)),
+                                          _ptr(off, C.c_int64), _ptr(ids, C.c_uint32), _ptr(xy, C.c_float),
+                                          _ptr(rgb, C.c_uint32))
+
+    def load_tracks(self, path: str):
+        nt, nf = C.c_int64(0), C.c_int64(0)
+        self.lib.osfm_refio_load_tracks(path.encode(), C.byref(nt), C.byref(nf), None, None, None, None)
+        off = np.zeros(nt.value + 1, np.int64)
+        ids = np.zeros((max(nf.value, 1), 3), np.uint32)
+        xy = np.zeros((max(nf.value, 1), 2), np.float32)
+        rgb = np.zeros((max(nf.value, 1), 3), np.uint32)
+        self.lib.osfm_refio_load_tracks(path.encode(), None, None, _ptr(off, C.c_int64), _ptr(ids, C.c_uint32),
+                                        _ptr(xy, C.c_float), _ptr(rgb, C.c_uint32))
+        return {"offsets": off, "ids": ids[:nf.value], "xy": xy[:nf.value], "rgb": rgb[:nf.value]}
+
+    @staticmethod
+    def _quiet(fn):
+        """saveTracksToFile announces itself on std::cout: keep test output clean."""
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        try:
+            os.dup2(devnull, 1)
+            return fn()
+        finally:
+            C.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)

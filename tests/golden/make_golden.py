@@ -10,6 +10,8 @@ Outputs (committed):
                    sfm::Sift, with the reference ExhaustiveMatching results.
   real_triple.npz  the same for the three images the reference ships (left / righ / rimg_pts.pgm):
                    all 3 pairs, BASELINE config 1 restated (3-image set, exhaustive matching).
+  tracks_golden.txt, pairwise_golden/   the OrthoSfM track files of a seeded track table, written by
+                   the reference's own src/matching/matching_io.cpp (compiled unmodified).
   cases.npz        seeded synthetic and adversarial descriptor sets with the reference's
                    twoway_match / remove_inconsistent / count results (u8, s8, f32).
 """
@@ -97,6 +99,48 @@ def real_triple():
     np.savez_compressed(os.path.join(HERE, "real_triple.npz"), **out)
 
 
+def track_files_case():
+    """Deterministic input of the golden track files (the tests rebuild it): 5 views, tracks of
+    2-5 features, positions and colours."""
+    rng = np.random.default_rng(424242)
+    feats = [40, 55, 33, 61, 48]
+    n = sum(feats)
+    base = np.concatenate([[0], np.cumsum(feats)])
+    ids = np.full(n, -1, np.int32)
+    free = [list(range(base[v], base[v + 1])) for v in range(len(feats))]
+    members = []
+    for _ in range(45):
+        k = int(rng.integers(2, len(feats) + 1))
+        views = sorted(rng.choice(len(feats), k, replace=False).tolist())
+        if any(len(free[v]) == 0 for v in views):
+            continue
+        members.append([free[v].pop(int(rng.integers(len(free[v])))) for v in views])
+    members.sort(key=lambda m: min(m))
+    for t, m in enumerate(members):
+        ids[m] = t
+    pos = ((rng.random((n, 2)) - 0.5) * 0.97).astype(np.float32)
+    pos[3] = (0.25, -0.125)            # values that print short ...
+    pos[7] = (1e-7, 0.49999997)        # ... and in exponent form
+    col = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    return feats, ids, len(members), pos, col, 3000.0
+
+
+def track_files():
+    """tracks.txt and the AAA_BBB.txt pair files as the reference's OWN writer produces them
+    (src/matching/matching_io.cpp:16-50, 97-140, compiled unmodified: oracle/_ref/libmatching_io_ref.so)."""
+    import shutil
+    io = oracle.ReferenceTrackIO()
+    feats, ids, nt, pos, col, width = track_files_case()
+    tracks = oracle.tracks_from_ids(feats, ids, pos, width, col)
+    io.save_tracks(os.path.join(HERE, "tracks_golden.txt"), tracks)
+    folder = os.path.join(HERE, "pairwise_golden")
+    shutil.rmtree(folder, ignore_errors=True)
+    os.makedirs(folder)
+    io.save_pairwise(folder, tracks, len(feats))
+    print("tracks_golden.txt:", os.path.getsize(os.path.join(HERE, "tracks_golden.txt")), "bytes;",
+          len(os.listdir(folder)), "pair files")
+
+
 def cases():
     rng = np.random.default_rng(20261018)
     out = {}
@@ -171,6 +215,7 @@ def cases():
 if __name__ == "__main__":
     real_pair()
     real_triple()
+    track_files()
     cases()
     for f in ("real_pair.npz", "real_triple.npz", "cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -231,3 +231,73 @@ def test_pairwise_track_files_match_the_restated_writer(tmp_path):
     assert sorted(os.listdir(tmp_path)) == sorted(want)
     for name, text in want.items():
         assert open(tmp_path / name).read() == text
+
+
+def _golden_track_case():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_tracks", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    src = open(spec.origin).read()
+    # only the seeded input builder (the module itself loads the compiled reference at import)
+    start = src.index("def track_files_case():")
+    end = src.index("def track_files():")
+    ns = {"np": np}
+    exec(src[start:end], ns)
+    return ns["track_files_case"]()
+
+
+def test_track_files_equal_the_reference_writers_golden_files(tmp_path):
+    """osfm_io_save_tracks / osfm_io_save_pairwise_tracks against files written by the
+    reference's OWN writer (src/matching/matching_io.cpp:16-50, 97-140, compiled unmodified into
+    oracle/_ref/libmatching_io_ref.so; tests/golden/make_golden.py::track_files): same bytes."""
+    import oracle
+    from orthosfm_b200 import io as osio
+    golden = os.path.join(ROOT, "tests", "golden")
+    feats, ids, nt, pos, col, width = _golden_track_case()
+    path = str(tmp_path / "tracks.txt")
+    osio.save_tracks(path, feats, ids, nt, pos, width, col)
+    assert open(path, "rb").read() == open(os.path.join(golden, "tracks_golden.txt"), "rb").read()
+    # the restatement in oracle/ agrees with the reference's file as well
+    want = oracle.tracks_from_ids(feats, ids, pos, width, col)
+    assert oracle.save_tracks_text(want) == open(os.path.join(golden, "tracks_golden.txt")).read()
+    folder = tmp_path / "pairs"
+    folder.mkdir()
+    n = osio.save_pairwise_tracks(str(folder), feats, ids, nt, pos, width)
+    names = sorted(os.listdir(os.path.join(golden, "pairwise_golden")))
+    assert n == len(names) and sorted(os.listdir(folder)) == names
+    for name in names:
+        assert open(folder / name, "rb").read() == open(os.path.join(golden, "pairwise_golden", name), "rb").read(), name
+    # and the reference's file reads back through osfm_io_load_tracks
+    back = osio.load_tracks(os.path.join(golden, "tracks_golden.txt"))
+    flat = [f for t in want for f in t]
+    assert back["ids"].tolist() == [list(f[:3]) for f in flat]
+    assert np.array_equal(back["xy"], np.array([[np.float32("%g" % f[3]), np.float32("%g" % f[4])] for f in flat], np.float32))
+    assert back["rgb"].tolist() == [list(f[5:]) for f in flat]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_track_files_equal_the_compiled_reference_writer(tmp_path, seed):
+    """Random track tables through the reference's own writer and reader (where oracle/_ref was
+    built) and through osfm_io_*: same files, same parsed tables."""
+    import oracle
+    from orthosfm_b200 import io as osio
+    if not oracle.have_ref_io():
+        pytest.skip("oracle/_ref/libmatching_io_ref.so not built (needs /root/reference)")
+    ref = oracle.ReferenceTrackIO()
+    feats, ids, nt, pos, col = _tracks_case(seed)
+    width = [3000.0, 1234.0, 640.0][seed - 1]
+    tracks = oracle.tracks_from_ids(feats, ids, pos, width, col)
+    ours, theirs = str(tmp_path / "ours.txt"), str(tmp_path / "theirs.txt")
+    osio.save_tracks(ours, feats, ids, nt, pos, width, col)
+    ref.save_tracks(theirs, tracks)
+    assert open(ours, "rb").read() == open(theirs, "rb").read()
+    a, b = osio.load_tracks(theirs), ref.load_tracks(ours)
+    for key in ("offsets", "ids", "xy", "rgb"):
+        assert np.array_equal(a[key], b[key]), key
+    fo, ft = tmp_path / "po", tmp_path / "pt"
+    fo.mkdir()
+    ft.mkdir()
+    osio.save_pairwise_tracks(str(fo), feats, ids, nt, pos, width)
+    ref.save_pairwise(str(ft), tracks, len(feats))
+    assert sorted(os.listdir(fo)) == sorted(os.listdir(ft)) and len(os.listdir(fo)) > 0
+    for name in os.listdir(ft):
+        assert open(fo / name, "rb").read() == open(ft / name, "rb").read(), name
