@@ -224,6 +224,7 @@ struct osfm_matcher {
     cudaEvent_t rs_stage_free[2] = {nullptr, nullptr};
     DevBuf<float> d_ftmp;
     DevBuf<int32_t> d_seg_first;
+    DevBuf<int32_t> d_item_job;          // filter pass: the job of every work item
     DevBuf<int32_t> d_rev_of;            // per job: the reverse job of its pair (or -1)
     // restricted candidate sets of the reverse pass (select_candidates_kernel)
     DevBuf<int32_t> d_tau;
@@ -243,6 +244,7 @@ struct osfm_matcher {
         DevBuf<int> cnt;            // rows per job
         DevBuf<int> job_xrow;
         DevBuf<ScanJob> xjobs;
+        DevBuf<int32_t> item_job;
         DevBuf<uint8_t> xpool;      // gathered query rows
         DevBuf<int64_t> xrow_map;
         int* d_xmeta = nullptr;
@@ -250,7 +252,7 @@ struct osfm_matcher {
         uint8_t* tmap_for = nullptr;
         size_t tmap_rows = 0;
         void release() {
-            list.release(); cnt.release(); job_xrow.release(); xjobs.release(); xpool.release(); xrow_map.release();
+            list.release(); cnt.release(); job_xrow.release(); xjobs.release(); item_job.release(); xpool.release(); xrow_map.release();
             if (d_xmeta) cudaFree(d_xmeta);
             d_xmeta = nullptr;
         }
@@ -318,6 +320,18 @@ int cuda_fail(osfm_matcher* m, cudaError_t e, const char* what) {
         int r__ = (call);             \
         if (r__ != OSFM_OK) return r__; \
     } while (0)
+
+// No C++ exception may cross the C ABI (a std::bad_alloc from a vector, say, would terminate the
+// host process): every entry point that does more than read a field runs inside this pair.
+#define OSFM_TRY_BEGIN try {
+#define OSFM_TRY_END(handle, internal_code)                                                             \
+    } catch (const std::bad_alloc&) {                                                                   \
+        return fail((handle), OSFM_ERR_OUT_OF_MEMORY, "out of host memory");                           \
+    } catch (const std::exception& e) {                                                                 \
+        return fail((handle), (internal_code), "unexpected exception: %s", e.what());                  \
+    } catch (...) {                                                                                     \
+        return fail((handle), (internal_code), "unexpected exception");                                \
+    }
 
 // Forgets the views (keeps the staging arena's memory unless release_arena).
 void reset_kind(KindPool& k, bool release_arena) {
@@ -467,7 +481,7 @@ cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, i
     ex.norm2 = k.d_norm2.p;
     ex.viewmax = k.d_viewmax.p;
     scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, k.tmap, m->d_jobs.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
+        k.tmap, k.tmap, k.tmap, m->d_jobs.p, m->d_item_job.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
         m->d_counters + 6);
     return cudaGetLastError();
 }
@@ -506,11 +520,13 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         sp.tmap_rows = sp.xpool.cap;
     }
     if (subset) CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(subset->nseg) + 1));
+    // every segment's rows make ceil(rows / 256) items: at most rows / 256 + one per segment
+    CU_TRY(m, sp.item_job.reserve(static_cast<size_t>(rows / kItemM) + static_cast<size_t>(subset ? subset->nseg : nseg) + 1));
     plan_rows_kernel<<<1, 1024, 0, m->stream>>>(subset ? subset->jobs : m->d_jobs.p,
                                                  subset ? subset->seg_first : m->d_seg_first.p,
                                                  subset ? subset->nseg : nseg, sp.cnt.p,
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
-                                                 PASS == kPassExact ? m->d_counters + 5 : nullptr);
+                                                 PASS == kPassExact ? m->d_counters + 5 : nullptr, sp.item_job.p);
     CU_TRY(m, cudaGetLastError());
     gather_rows_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
                                                               sp.job_xrow.p, sp.list.p, k.pool,
@@ -548,7 +564,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     scan_kernel<0, PASS, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
-        sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
+        sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, sp.item_job.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 3;
     if (PASS == kPassExact) {
@@ -662,6 +678,9 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     float const sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
     float const sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
 
+    CU_TRY(m, m->d_item_job.reserve(static_cast<size_t>(items) + 1));
+    fill_item_job_kernel<<<(njobs + 255) / 256, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_item_job.p);
+    CU_TRY(m, cudaGetLastError());
     CU_TRY(m, m->phases.mark(m->stream, kPhFilter));
     cudaError_t e = cudaSuccess;
     if (items > 0) {
@@ -1089,6 +1108,7 @@ const char* osfm_match_last_error(const osfm_matcher* m) {
 }
 
 int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
+    OSFM_TRY_BEGIN
     if (!out) return OSFM_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     osfm_matcher* m = new (std::nothrow) osfm_matcher();
@@ -1141,6 +1161,7 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     m->kind[1].is_signed = true;  m->kind[1].dim = 64;
     m->kind[1].lowe = m->cfg.surf_lowe_ratio; m->kind[1].dist = m->cfg.surf_distance_threshold;
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 void osfm_match_destroy(osfm_matcher* m) {
@@ -1169,7 +1190,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->rs_stage_ints = 0;
     m->d_ftmp.release();
     m->d_seg_first.release();
-    m->d_rev_of.release();
+    m->d_rev_of.release(); m->d_item_job.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
     m->d_cand_pool.release(); m->d_cand_map.release();
     m->d_replay_flags.release();
@@ -1190,6 +1211,7 @@ void osfm_match_destroy(osfm_matcher* m) {
 }
 
 int osfm_match_create_multi(const osfm_match_config* cfg, const int* devices, int num_devices, osfm_matcher** out) {
+    OSFM_TRY_BEGIN
     if (!out) return OSFM_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if (!devices || num_devices < 1) return OSFM_ERR_INVALID_ARGUMENT;
@@ -1222,6 +1244,7 @@ int osfm_match_create_multi(const osfm_match_config* cfg, const int* devices, in
     }
     CU_TRY(m, cudaSetDevice(m->device));
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_num_devices(const osfm_matcher* m) {
@@ -1296,6 +1319,7 @@ static int replicate_to_peers(osfm_matcher* m) {
 }
 
 static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -1327,6 +1351,7 @@ static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
         m->view_ev_seq.assign(static_cast<size_t>(num_views), 0);
     }
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_begin(osfm_matcher* m, int num_views) { return begin_impl(m, num_views, false); }
@@ -1336,6 +1361,7 @@ int osfm_match_begin_overlapped(osfm_matcher* m, int num_views) { return begin_i
 // Stages one view of one kind at the end of the arena.  All copies are asynchronous on the
 // handle's stream; the source must stay valid until osfm_match_commit() returns.
 static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n, int stride, bool is_float) {
+    OSFM_TRY_BEGIN
     KindPool& k = m->kind[kd];
     if (k.stage_off[view] >= 0 || view < k.last_staged) k.in_order = false;  // re-staged or out of order
     k.n[view] = 0;
@@ -1370,10 +1396,12 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
     k.arena_used += n;
     k.n[view] = n;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_set_view_f32(osfm_matcher* m, int view_id, const float* sift, int n_sift, int sift_stride,
                             const float* surf, int n_surf, int surf_stride) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
@@ -1382,6 +1410,7 @@ int osfm_match_set_view_f32(osfm_matcher* m, int view_id, const float* sift, int
     OS_TRY(stage_view(m, 0, view_id, sift, n_sift, sift_stride, true));
     OS_TRY(stage_view(m, 1, view_id, surf, n_surf, surf_stride, true));
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 static int set_view_q8_locked(osfm_matcher* m, int view_id, const uint8_t* sift, int n_sift,
@@ -1400,15 +1429,18 @@ static int set_view_q8_locked(osfm_matcher* m, int view_id, const uint8_t* sift,
 
 int osfm_match_set_view_q8(osfm_matcher* m, int view_id, const uint8_t* sift, int n_sift,
                            const int8_t* surf, int n_surf) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
     CU_TRY(m, cudaSetDevice(m->device));
     return set_view_q8_locked(m, view_id, sift, n_sift, surf, n_surf);
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const uint8_t* const* sift,
                             const int32_t* n_sift, const int8_t* const* surf, const int32_t* n_surf) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_views outside begin/commit");
@@ -1419,9 +1451,11 @@ int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const ui
         OS_TRY(set_view_q8_locked(m, first_view + i, sift ? sift[i] : nullptr, sift ? n_sift[i] : 0,
                                   surf ? surf[i] : nullptr, surf ? n_surf[i] : 0));
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_commit(osfm_matcher* m) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "commit outside begin/commit");
@@ -1478,9 +1512,11 @@ int osfm_match_commit(osfm_matcher* m) {
     OS_TRY(replicate_to_peers(m));
     m->committed = true;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_wait_staged(osfm_matcher* m) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -1490,6 +1526,7 @@ int osfm_match_wait_staged(osfm_matcher* m) {
     m->copies_in_flight = false;
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_commit_device(osfm_matcher* m, int num_views,
@@ -1497,6 +1534,7 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
                              int64_t sift_pool_rows,
                              const void* surf_pool, const int64_t* surf_row_offset, const int32_t* n_surf,
                              int64_t surf_pool_rows) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -1549,6 +1587,7 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
     OS_TRY(replicate_to_peers(m));
     m->committed = true;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_num_views(const osfm_matcher* m) { return m ? m->num_views : OSFM_ERR_INVALID_ARGUMENT; }
@@ -1576,6 +1615,7 @@ static int build_plans(osfm_matcher* m, const int32_t* pairs, int npairs, int li
 }
 
 int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int npairs) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (require_committed(m) != OSFM_OK) return OSFM_ERR_STATE;
@@ -1585,6 +1625,7 @@ int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int 
     int64_t total = 0;
     for (PairPlan const& p : plans) total += static_cast<int64_t>(p.len12) + p.len21;
     return total;
+    OSFM_TRY_END(m, -6)
 }
 
 static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, OutputMode mode, int only_kind,
@@ -1630,12 +1671,14 @@ static int dense_dispatch(osfm_matcher* m, std::vector<PairPlan>& plans, OutputM
 
 int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* matches, int64_t* offsets,
                      int32_t* n_consistent) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
     return dense_dispatch(m, plans, kFiltered, -1, matches, offsets, n_consistent);
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // The window of pairs that follows (view_1, view_2) in the reference's enumeration
@@ -1653,12 +1696,14 @@ static void lookahead_window(int num_views, int v1, int v2, int limit, std::vect
 static int64_t flat_pair_index(int v1, int v2) { return static_cast<int64_t>(v1) * (v1 - 1) / 2 + v2; }
 
 int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs) {
+    OSFM_TRY_BEGIN
     if (!m || max_pairs < 0) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     m->lookahead = max_pairs;
     m->cache_full.clear();
     m->cache_lowres.clear();
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // Serves osfm_match_pair from the look-ahead cache, filling it first if (view_1, view_2) is not in it.
@@ -1707,6 +1752,7 @@ static int pair_from_lookahead(osfm_matcher* m, int v1, int v2, int32_t* matches
 
 int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id, int32_t* matches_1_2, int* len_1_2,
                     int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -1725,10 +1771,12 @@ int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id, int32_t* matc
     if (len_2_1) *len_2_1 = plans[0].len21;
     if (n_consistent) *n_consistent = cnt;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_id, int32_t* matches_1_2,
                            int32_t* matches_2_1) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -1751,9 +1799,11 @@ int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_
     if (matches_1_2 && p.len12 > 0) memcpy(matches_1_2, buf.data() + offs[0], sizeof(int32_t) * p.len12);
     if (matches_2_1 && p.len21 > 0) memcpy(matches_2_1, buf.data() + offs[1], sizeof(int32_t) * p.len21);
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t num_features, int* n_consistent) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -1787,6 +1837,7 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
     OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, &cnt));
     if (n_consistent) *n_consistent = cnt;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- float path ---------------------------------------------------------------------------
@@ -1794,6 +1845,7 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
 int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2, int dim,
                           float lowe_ratio_threshold, float distance_threshold,
                           int32_t* matches_1_2, int32_t* matches_2_1) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -1832,6 +1884,7 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
     CU_TRY(m, cudaMemcpyAsync(matches_2_1, m->d_oneway.p + n1, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- batched, device-resident, compacted ------------------------------------------------
@@ -2121,6 +2174,7 @@ void osfm_match_two_view_default_options(osfm_two_view_options* o) {
 int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options* opts, const int32_t* pairs,
                                    int npairs, int32_t* match_ij, int64_t capacity_ij, int64_t* list_offset,
                                    int32_t* status, int32_t* count) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -2205,6 +2259,7 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
     }
     list_offset[npairs] = at;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- tracks (bundler::Tracks::compute) -------------------------------------------------------
@@ -2212,6 +2267,7 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
 int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_per_view, const int32_t* pair_views,
                         const int64_t* list_offset, const int32_t* match_ij, int npairs,
                         int32_t* track_of_feature, int32_t* num_tracks, int32_t* num_conflicting) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -2297,6 +2353,7 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
     *num_tracks = small[2];
     if (num_conflicting) *num_conflicting = small[1];
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- RANSAC for the fundamental matrix ------------------------------------------------------------
@@ -2339,6 +2396,7 @@ private:
     struct random_data park_rd_, rd_;
     char* real_ = nullptr;
 #else
+    RandSequence() = default;
     int next() { return std::rand(); }
 #endif
     RandSequence(const RandSequence&) = delete;
@@ -2352,7 +2410,13 @@ static inline void order2(int32_t& a, int32_t& b) {
     a = lo; b = hi;
 }
 
+// RandSequence takes over the process-wide generator while it draws: two handles (or two threads
+// on one) must not do that at the same time.  A thread that calls rand() itself meanwhile is as
+// undefined as it is against the reference's own std::rand() loop.
+static std::mutex g_rand_mutex;
+
 static void draw_samples_for_pairs(int npairs, const int64_t* list_offset, int max_iterations, int32_t* out) {
+    std::lock_guard<std::mutex> rand_lock(g_rand_mutex);
     RandSequence seq;
     for (int p = 0; p < npairs; ++p) {
         // rand() % count without a division per draw (Lemire's fastmod: exact for 32-bit operands)
@@ -2385,6 +2449,7 @@ static void draw_samples_for_pairs(int npairs, const int64_t* list_offset, int m
 }
 
 int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_iterations, int32_t* samples) {
+    OSFM_TRY_BEGIN
     if (npairs < 0 || max_iterations < 0 || (npairs > 0 && (!list_offset || !samples))) return OSFM_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < npairs; ++p) {
         int64_t const count = list_offset[p + 1] - list_offset[p];
@@ -2392,12 +2457,14 @@ int osfm_ransac_draw_samples(int npairs, const int64_t* list_offset, int max_ite
     }
     draw_samples_for_pairs(npairs, list_offset, max_iterations, samples);
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* features_per_view, const float* positions,
                             const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij,
                             int npairs, const int32_t* samples, int max_iterations, double threshold,
                             int32_t* inlier_ij, int64_t* inlier_offset, double* fundamental) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
@@ -2540,6 +2607,7 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
         inlier_offset[p + 1] = inlier_offset[p] + count[p];
     }
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- the whole two-view stage: gates, RANSAC, inlier threshold --------------------------------------
@@ -2555,6 +2623,7 @@ void osfm_match_ransac_default_options(osfm_ransac_options* o) {
 int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, const osfm_ransac_options* ransac,
                         const float* positions, const int32_t* pairs, int npairs, int32_t* match_ij,
                         int64_t capacity_ij, int64_t* list_offset, int32_t* status, int32_t* count) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     if (!ransac || ransac->max_iterations < 0) {
         std::lock_guard<std::mutex> lock(m->mu);
@@ -2605,6 +2674,7 @@ int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, cons
     }
     list_offset[npairs] = at;
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 // ---- on-disk format (MVE prebundle) ------------------------------------------------------------
@@ -2612,6 +2682,7 @@ int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, cons
 int osfm_io_save_prebundle(const char* path, int num_views, const int32_t* features_per_view,
                            const float* positions, const uint8_t* colors, int npairs,
                            const int32_t* pair_views, const int64_t* list_offset, const int32_t* match_ij) {
+    OSFM_TRY_BEGIN
     if (!path || num_views < 0 || npairs < 0 || (num_views > 0 && !features_per_view) ||
         (npairs > 0 && (!pair_views || !list_offset)))
         return OSFM_ERR_INVALID_ARGUMENT;
@@ -2621,6 +2692,7 @@ int osfm_io_save_prebundle(const char* path, int num_views, const int32_t* featu
     }
     return save_prebundle(path, num_views, features_per_view, positions, colors, npairs, pair_views, list_offset,
                           match_ij) == 0 ? OSFM_OK : OSFM_ERR_IO;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 struct osfm_prebundle {
@@ -2629,6 +2701,7 @@ struct osfm_prebundle {
 
 int osfm_io_load_prebundle(const char* path, osfm_prebundle** out, int* num_views, int64_t* num_positions,
                            int64_t* num_colors, int* npairs, int64_t* num_matches) {
+    OSFM_TRY_BEGIN
     if (!path || !out) return OSFM_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     osfm_prebundle* h = new (std::nothrow) osfm_prebundle();
@@ -2642,10 +2715,12 @@ int osfm_io_load_prebundle(const char* path, osfm_prebundle** out, int* num_view
     if (num_matches) *num_matches = h->d.list_offset.back();
     *out = h;
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 int osfm_io_prebundle_get(const osfm_prebundle* h, int32_t* n_positions, int32_t* n_colors, float* positions,
                           uint8_t* colors, int32_t* pair_views, int64_t* list_offset, int32_t* match_ij) {
+    OSFM_TRY_BEGIN
     if (!h) return OSFM_ERR_INVALID_ARGUMENT;
     PrebundleData const& d = h->d;
     auto cp = [](void* dst, const void* src, size_t bytes) { if (dst && bytes) memcpy(dst, src, bytes); };
@@ -2657,6 +2732,7 @@ int osfm_io_prebundle_get(const osfm_prebundle* h, int32_t* n_positions, int32_t
     cp(list_offset, d.list_offset.data(), sizeof(int64_t) * d.list_offset.size());
     cp(match_ij, d.match_ij.data(), sizeof(int32_t) * d.match_ij.size());
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 void osfm_io_prebundle_free(osfm_prebundle* h) { delete h; }
@@ -2680,17 +2756,20 @@ static int track_table_from_ids(int num_views, const int32_t* features_per_view,
 int osfm_io_save_tracks(const char* path, int num_views, const int32_t* features_per_view,
                         const int32_t* track_of_feature, int num_tracks, const float* positions,
                         double image_width, const uint8_t* colors) {
+    OSFM_TRY_BEGIN
     if (!path) return OSFM_ERR_INVALID_ARGUMENT;
     TrackTable t;
     int const rc = track_table_from_ids(num_views, features_per_view, track_of_feature, num_tracks, positions,
                                         image_width, colors, &t);
     if (rc != OSFM_OK) return rc;
     return save_tracks(path, t) == 0 ? OSFM_OK : OSFM_ERR_IO;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 int osfm_io_save_pairwise_tracks(const char* folder, int num_views, const int32_t* features_per_view,
                                  const int32_t* track_of_feature, int num_tracks, const float* positions,
                                  double image_width, int* files_written) {
+    OSFM_TRY_BEGIN
     if (!folder) return OSFM_ERR_INVALID_ARGUMENT;
     TrackTable t;
     int const rc = track_table_from_ids(num_views, features_per_view, track_of_feature, num_tracks, positions,
@@ -2702,6 +2781,7 @@ int osfm_io_save_pairwise_tracks(const char* folder, int num_views, const int32_
     if (n < 0) return OSFM_ERR_IO;
     if (files_written) *files_written = n;
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 struct osfm_track_table {
@@ -2709,6 +2789,7 @@ struct osfm_track_table {
 };
 
 int osfm_io_load_tracks(const char* path, osfm_track_table** out, int64_t* num_tracks, int64_t* num_features) {
+    OSFM_TRY_BEGIN
     if (!path || !out) return OSFM_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     osfm_track_table* h = new (std::nothrow) osfm_track_table();
@@ -2719,10 +2800,12 @@ int osfm_io_load_tracks(const char* path, osfm_track_table** out, int64_t* num_t
     if (num_features) *num_features = static_cast<int64_t>(h->t.features.size());
     *out = h;
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 int osfm_io_track_table_get(const osfm_track_table* h, int64_t* track_offset, uint32_t* ids, float* xy,
                             uint32_t* rgb) {
+    OSFM_TRY_BEGIN
     if (!h) return OSFM_ERR_INVALID_ARGUMENT;
     TrackTable const& t = h->t;
     if (track_offset) memcpy(track_offset, t.offset.data(), sizeof(int64_t) * t.offset.size());
@@ -2733,6 +2816,7 @@ int osfm_io_track_table_get(const osfm_track_table* h, int64_t* track_offset, ui
         if (rgb) { rgb[3 * i] = o.r; rgb[3 * i + 1] = o.g; rgb[3 * i + 2] = o.b; }
     }
     return OSFM_OK;
+    OSFM_TRY_END(nullptr, OSFM_ERR_INTERNAL)
 }
 
 void osfm_io_track_table_free(osfm_track_table* h) { delete h; }
@@ -2757,12 +2841,14 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
 }
 
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     m->both_directions = on == 1;
     m->reverse_mode = on == 2 ? 2 : 0;
     for (osfm_matcher* p : m->peers) { p->both_directions = m->both_directions; p->reverse_mode = m->reverse_mode; }
     return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
@@ -2806,6 +2892,7 @@ int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int 
 }
 
 int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, int64_t* out, int64_t out_words) {
+    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(m->mu);
     OS_TRY(require_committed(m));
@@ -2834,6 +2921,7 @@ int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, in
     }
     cudaFree(d);
     return r;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
 int osfm_match_debug_dump_packed(osfm_matcher* m, int kind, int view_q, int view_c, uint32_t* out, int64_t out_words) {

@@ -649,6 +649,16 @@ __global__ void __launch_bounds__(256) slow_rows_kernel(PostParams p)
     }
 }
 
+// item_job[] of a host-built job list (the filter pass): one thread per job.
+__global__ void __launch_bounds__(256) fill_item_job_kernel(const ScanJob* __restrict__ jobs, int njobs,
+                                                            int32_t* __restrict__ item_job)
+{
+    int const j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    int const first = jobs[j].item_start, last = jobs[j + 1].item_start;
+    for (int it = first; it < last; ++it) item_job[it] = j;
+}
+
 // ---------------------------------------------------------------- exact pass set-up
 
 // Single CTA.  Turns the per-job slow-row counts into the job list of the EXACT scan pass.
@@ -661,7 +671,8 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const ScanJob* __restri
                                                           const int* __restrict__ slow_cnt,
                                                           ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
                                                           int* __restrict__ meta,
-                                                          unsigned long long* __restrict__ rows_total)
+                                                          unsigned long long* __restrict__ rows_total,
+                                                          int32_t* __restrict__ item_job)
 {
     __shared__ int wsum[3][32];
     __shared__ int run[3];
@@ -705,6 +716,7 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const ScanJob* __restri
             x.item_start = pre[1];
             x.c_view = first.c_view;
             xjobs[pre[2]] = x;
+            for (int q = 0; q < val[1]; ++q) item_job[pre[1] + q] = pre[2];
             int at = pre[0];
             for (int j = seg_first[sgi]; j < seg_first[sgi + 1]; ++j) {
                 job_xrow[j] = at;

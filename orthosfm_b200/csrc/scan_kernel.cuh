@@ -8,7 +8,9 @@
 //
 // A *job* is one direction of one image pair: every descriptor of a query set against
 // every descriptor of a candidate view.  A *work item* is a 256-row block of a job's
-// queries.  For each item a persistent CTA
+// queries; item_job[] names every item's job (a walk along the jobs' item prefix sums costs a
+// dependent load per job passed, which for the short jobs of the second passes -- a handful of
+// items each, 148 items between two items of a CTA -- came to more than the item's own work).  For each item a persistent CTA
 //   - TMA-loads the 256 x 128 B query tile once (two 128-row halves, SWIZZLE_128B, K-major),
 //   - streams the candidate view through a ring of 256 x 128 B tiles; each candidate tile
 //     feeds two tcgen05.mma groups (one per query half), which halves the L2 -> SMEM
@@ -389,7 +391,7 @@ template <int MODE, int PASS, bool SIGNED>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
             const __grid_constant__ CUtensorMap tmap_c2,
-            const ScanJob* __restrict__ jobs, int total_items_host, uint32_t idesc, int ksteps,
+            const ScanJob* __restrict__ jobs, const int32_t* __restrict__ item_job, int total_items_host, uint32_t idesc, int ksteps,
             int32_t* __restrict__ dump, int64_t dump_ld, ExactParams ex, int2* __restrict__ rowres,
             unsigned long long* __restrict__ prof)
 {
@@ -454,7 +456,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             int j = 0;
             uint32_t bcnt = 0, ic = 0;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
-                while (it >= jobs[j + 1].item_start) ++j;
+                j = item_job[it];
                 ScanJob const job = jobs[j];
                 int const rb = it - job.item_start;
                 int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
@@ -509,7 +511,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             int j = 0;
             uint32_t bcnt = 0, ic = 0, hc = 0;   // hc: tiles this issuer has issued so far
             for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
-                while (it >= warp_uniform(jobs[j + 1].item_start)) ++j;
+                j = warp_uniform(item_job[it]);
                 int const c_n = warp_uniform(jobs[j].c_n);
                 int const rb = it - warp_uniform(jobs[j].item_start);
                 bool const active = (warp_uniform(jobs[j].q_n) - rb * kItemM > kHalfM) || h == 0;
@@ -578,7 +580,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         int j = 0;
         uint32_t cnt = 0, ic = 0;            // cnt: tiles of this warp's accumulator so far
         for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
-            while (it >= jobs[j + 1].item_start) ++j;
+            j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
             int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
@@ -786,7 +788,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         int j = 0;
         uint32_t cnt_tiles = 0, ic = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
-            while (it >= jobs[j + 1].item_start) ++j;
+            j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
             int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
@@ -884,7 +886,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         int j = 0;
         uint32_t hcnt = 0;                   // tiles this group has processed so far
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            while (it >= jobs[j + 1].item_start) ++j;
+            j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
             int const nh = (job.q_n - rb * kItemM > kHalfM) ? 2 : 1;
