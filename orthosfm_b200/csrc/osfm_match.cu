@@ -738,7 +738,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     pp.counters = m->d_counters;
     pp.slow_len = m->d_counters + 0;
 
-    // The rows queued by classify_kernel / targets_kernel: CUDA-core replay of the signed rows
+    // The rows queued by classify_kernel / claim_kernel: CUDA-core replay of the signed rows
     // without certificate, RESOLVE pass, EXACT pass.
     auto second_passes = [&](bool verify, const ReverseSubset* subset) -> int {
         if (k.is_signed) {

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p)
 // treated like any certified row (rejected, or queued for the RESOLVE pass); otherwise it is
 // queued for the EXACT pass.  Grid-strides over the list, whose length is only known on the
 // device.
-// TARGETS: the rows are claimed rows of a reverse job (targets_kernel): rowres holds (V, job),
+// TARGETS: the rows are claimed rows of a reverse job (claim_kernel): rowres holds (V, job),
 // and a row certified after the fact is queued for the RESOLVE pass whatever its value.
 template <bool TARGETS>
 __global__ void __launch_bounds__(256) certify_kernel(ClassifyParams p)
