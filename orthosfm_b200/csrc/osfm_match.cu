@@ -172,7 +172,7 @@ struct PhaseTimer {
 }  // namespace
 
 struct osfm_matcher {
-    std::mutex mu;
+    std::recursive_mutex mu;     // recursive: osfm_match_two_view holds it across the stages it calls
     std::string err;
     osfm_match_config cfg;
     int device = 0;
@@ -681,6 +681,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     CU_TRY(m, m->d_item_job.reserve(static_cast<size_t>(items) + 1));
     fill_item_job_kernel<<<(njobs + 255) / 256, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_item_job.p);
     CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches++;
     CU_TRY(m, m->phases.mark(m->stream, kPhFilter));
     cudaError_t e = cudaSuccess;
     if (items > 0) {
@@ -1150,11 +1151,24 @@ int osfm_match_create(const osfm_match_config* cfg, osfm_matcher** out) {
     m->encode = reinterpret_cast<EncodeTiledFn>(fn);
 
     // watchdog report buffer in mapped pinned memory
-    CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&m->hang_host), sizeof(HangReport), cudaHostAllocMapped));
-    memset(m->hang_host, 0, sizeof(HangReport));
-    HangReport* dptr = nullptr;
-    CU_TRY(m, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->hang_host, 0));
-    CU_TRY(m, cudaMemcpyToSymbol(g_hang_report, &dptr, sizeof dptr));
+    // One report buffer per device for the life of the process, shared by every handle on that
+    // device (the kernels find it through a per-device symbol): a handle that goes away must not
+    // take the others' watchdog report with it.
+    {
+        static std::mutex hang_mu;
+        static HangReport* per_device[64] = {};
+        std::lock_guard<std::mutex> hang_lock(hang_mu);
+        if (m->device < 64 && per_device[m->device] != nullptr) {
+            m->hang_host = per_device[m->device];
+        } else {
+            CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&m->hang_host), sizeof(HangReport), cudaHostAllocMapped));
+            memset(m->hang_host, 0, sizeof(HangReport));
+            HangReport* dptr = nullptr;
+            CU_TRY(m, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->hang_host, 0));
+            CU_TRY(m, cudaMemcpyToSymbol(g_hang_report, &dptr, sizeof dptr));
+            if (m->device < 64) per_device[m->device] = m->hang_host;
+        }
+    }
 
     m->kind[0].is_signed = false; m->kind[0].dim = 128;
     m->kind[0].lowe = m->cfg.sift_lowe_ratio; m->kind[0].dist = m->cfg.sift_distance_threshold;
@@ -1196,11 +1210,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_replay_flags.release();
     for (auto& sp : m->pass) sp.release();
     if (m->d_counters) cudaFree(m->d_counters);
-    if (m->hang_host) {
-        HangReport* null_ptr = nullptr;
-        cudaMemcpyToSymbol(g_hang_report, &null_ptr, sizeof null_ptr);
-        cudaFreeHost(m->hang_host);
-    }
+    m->hang_host = nullptr;      // per-device, process-lifetime (see osfm_match_create)
     m->phases.release();
     if (m->cache_full.host) cudaFreeHost(m->cache_full.host);
     for (auto& ev : m->ev) if (ev) cudaEventDestroy(ev);
@@ -1263,7 +1273,7 @@ static int replicate_to_peers(osfm_matcher* m) {
         KindPool& k = m->kind[kd];
         size_t const bytes = static_cast<size_t>(k.rows + kPadRows) * kRowBytes;
         for (osfm_matcher* p : m->peers) {
-            std::lock_guard<std::mutex> lock(p->mu);
+            std::lock_guard<std::recursive_mutex> lock(p->mu);
             KindPool& pk = p->kind[kd];
             CU_TRY(p, cudaSetDevice(p->device));
             CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
@@ -1292,7 +1302,7 @@ static int replicate_to_peers(osfm_matcher* m) {
     CU_TRY(m, cudaSetDevice(m->device));
     CU_TRY(m, cudaEventRecord(t1, m->stream));
     for (osfm_matcher* p : m->peers) {
-        std::lock_guard<std::mutex> lock(p->mu);
+        std::lock_guard<std::recursive_mutex> lock(p->mu);
         CU_TRY(p, cudaSetDevice(p->device));
         for (int kd = 0; kd < 2; ++kd) {
             int rc = make_tmap(p, p->kind[kd]);
@@ -1321,7 +1331,7 @@ static int replicate_to_peers(osfm_matcher* m) {
 static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
     CU_TRY(m, cudaSetDevice(m->device));
@@ -1403,7 +1413,7 @@ int osfm_match_set_view_f32(osfm_matcher* m, int view_id, const float* sift, int
                             const float* surf, int n_surf, int surf_stride) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
     OS_TRY(check_view(m, view_id));
     CU_TRY(m, cudaSetDevice(m->device));
@@ -1431,7 +1441,7 @@ int osfm_match_set_view_q8(osfm_matcher* m, int view_id, const uint8_t* sift, in
                            const int8_t* surf, int n_surf) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_view outside begin/commit");
     CU_TRY(m, cudaSetDevice(m->device));
     return set_view_q8_locked(m, view_id, sift, n_sift, surf, n_surf);
@@ -1442,7 +1452,7 @@ int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const ui
                             const int32_t* n_sift, const int8_t* const* surf, const int32_t* n_surf) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "set_views outside begin/commit");
     if (count < 0 || (count > 0 && ((sift && !n_sift) || (surf && !n_surf))))
         return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
@@ -1457,7 +1467,7 @@ int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const ui
 int osfm_match_commit(osfm_matcher* m) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->began || m->committed) return fail(m, OSFM_ERR_STATE, "commit outside begin/commit");
     CU_TRY(m, cudaSetDevice(m->device));
     // Overlapped staging stays lazy only if the arena already is the pool (views staged in
@@ -1518,7 +1528,7 @@ int osfm_match_commit(osfm_matcher* m) {
 int osfm_match_wait_staged(osfm_matcher* m) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     CU_TRY(m, cudaSetDevice(m->device));
     if (m->committed) OS_TRY(ensure_views(m, m->num_views - 1));
@@ -1536,7 +1546,7 @@ int osfm_match_commit_device(osfm_matcher* m, int num_views,
                              int64_t surf_pool_rows) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "num_views must be >= 0");
     CU_TRY(m, cudaSetDevice(m->device));
@@ -1617,7 +1627,7 @@ static int build_plans(osfm_matcher* m, const int32_t* pairs, int npairs, int li
 int64_t osfm_match_pairs_result_size(osfm_matcher* m, const int32_t* pairs, int npairs) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (require_committed(m) != OSFM_OK) return OSFM_ERR_STATE;
     std::vector<PairPlan> plans;
     int r = build_plans(m, pairs, npairs, 0, false, plans);
@@ -1673,7 +1683,7 @@ int osfm_match_pairs(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t*
                      int32_t* n_consistent) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     std::vector<PairPlan> plans;
     OS_TRY(build_plans(m, pairs, npairs, 0, false, plans));
@@ -1698,7 +1708,7 @@ static int64_t flat_pair_index(int v1, int v2) { return static_cast<int64_t>(v1)
 int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs) {
     OSFM_TRY_BEGIN
     if (!m || max_pairs < 0) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     m->lookahead = max_pairs;
     m->cache_full.clear();
     m->cache_lowres.clear();
@@ -1754,7 +1764,7 @@ int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id, int32_t* matc
                     int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     if (m->lookahead > 1 && view_1_id > view_2_id && view_2_id >= 0 && view_1_id < m->num_views)
         return pair_from_lookahead(m, view_1_id, view_2_id, matches_1_2, len_1_2, matches_2_1, len_2_1, n_consistent);
@@ -1778,7 +1788,7 @@ int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_
                            int32_t* matches_2_1) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     if (kind != OSFM_KIND_SIFT_U8 && kind != OSFM_KIND_SURF_S8) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "unknown kind %d", kind);
     OS_TRY(check_view(m, view_1_id));
@@ -1805,7 +1815,7 @@ int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_
 int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t num_features, int* n_consistent) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     if (num_features == 0 || num_features > INT32_MAX) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad num_features");
     if (m->lookahead > 1 && view_1_id > view_2_id && view_2_id >= 0 && view_1_id < m->num_views) {
@@ -1847,7 +1857,7 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
                           int32_t* matches_1_2, int32_t* matches_2_1) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (n1 < 0 || n2 < 0 || dim <= 0 || dim > kFDim || (dim & 3) != 0)
         return fail(m, OSFM_ERR_INVALID_ARGUMENT, "float path needs n >= 0 and dim a multiple of 4 in (0, %d]", kFDim);
@@ -2024,7 +2034,7 @@ static int run_sharded(osfm_matcher* m, std::vector<Shard>& shards, Fn fn) {
             if (shards[d].first == shards[d].last) continue;
             threads.emplace_back([&shards, &fn, d] {
                 Shard& sh = shards[d];
-                std::lock_guard<std::mutex> lock(sh.h->mu);
+                std::lock_guard<std::recursive_mutex> lock(sh.h->mu);
                 sh.rc = fn(sh);
             });
         }
@@ -2146,7 +2156,7 @@ extern "C" {
 int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* d_match_ij,
                                     int64_t capacity_ij, int64_t* list_offset) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (capacity_ij < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative capacity");
     return compact_core(m, pairs, npairs, d_match_ij, capacity_ij, list_offset, nullptr);
 }
@@ -2154,7 +2164,7 @@ int osfm_match_pairs_compact_device(osfm_matcher* m, const int32_t* pairs, int n
 int osfm_match_pairs_compact(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* match_ij,
                              int64_t capacity_ij, int64_t* list_offset) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (capacity_ij < 0) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "negative capacity");
     return compact_to_host(m, pairs, npairs, match_ij, capacity_ij, list_offset, true, 0, nullptr);
 }
@@ -2176,7 +2186,7 @@ int osfm_match_two_view_candidates(osfm_matcher* m, const osfm_two_view_options*
                                    int32_t* status, int32_t* count) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     if (!opts || !list_offset || !status || !count || npairs < 0 || (npairs > 0 && !pairs) || capacity_ij < 0)
         return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad argument");
@@ -2269,7 +2279,7 @@ int osfm_tracks_compute(osfm_matcher* m, int num_views, const int32_t* features_
                         int32_t* track_of_feature, int32_t* num_tracks, int32_t* num_conflicting) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0 || npairs < 0 || (num_views > 0 && !features_per_view) ||
         (npairs > 0 && (!pair_views || !list_offset)) || !num_tracks)
@@ -2466,7 +2476,7 @@ int osfm_ransac_fundamental(osfm_matcher* m, int num_views, const int32_t* featu
                             int32_t* inlier_ij, int64_t* inlier_offset, double* fundamental) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
     if (num_views < 0 || npairs < 0 || max_iterations < 0 || (num_views > 0 && !features_per_view) || !inlier_offset ||
         (npairs > 0 && (!pair_views || !list_offset || !positions || !match_ij || !inlier_ij)))
@@ -2623,10 +2633,12 @@ void osfm_match_ransac_default_options(osfm_ransac_options* o) {
 int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, const osfm_ransac_options* ransac,
                         const float* positions, const int32_t* pairs, int npairs, int32_t* match_ij,
                         int64_t capacity_ij, int64_t* list_offset, int32_t* status, int32_t* count) {
-    OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    OSFM_TRY_BEGIN
+    // the views must not change between the stages: one lock for the whole call
+    std::lock_guard<std::recursive_mutex> whole_call(m->mu);
     if (!ransac || ransac->max_iterations < 0) {
-        std::lock_guard<std::mutex> lock(m->mu);
+        std::lock_guard<std::recursive_mutex> lock(m->mu);
         return fail(m, OSFM_ERR_INVALID_ARGUMENT, "bad RANSAC options");
     }
     // 1. bundler_matching.cc:92-192: pair rules, low-res gate, full match, match-count threshold
@@ -2644,7 +2656,7 @@ int osfm_match_two_view(osfm_matcher* m, const osfm_two_view_options* opts, cons
     if (nok == 0) return OSFM_OK;
     std::vector<int32_t> fpv;
     {
-        std::lock_guard<std::mutex> lock(m->mu);
+        std::lock_guard<std::recursive_mutex> lock(m->mu);
         if (!positions) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "positions required");
         fpv.resize(m->kind[0].n.size());
         for (size_t v = 0; v < fpv.size(); ++v) fpv[v] = m->kind[0].n[v] + m->kind[1].n[v];
@@ -2843,7 +2855,7 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     m->both_directions = on == 1;
     m->reverse_mode = on == 2 ? 2 : 0;
     for (osfm_matcher* p : m->peers) { p->both_directions = m->both_directions; p->reverse_mode = m->reverse_mode; }
@@ -2853,14 +2865,14 @@ int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
 
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {
     if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;   /* 3-5: dump / trace entry points */
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     m->scan_mode = mode;
     return OSFM_OK;
 }
 
 static int debug_dump(osfm_matcher* m, int kind, int view_q, int view_c, int32_t* out, int64_t out_ints, int mode) {
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     CU_TRY(m, cudaSetDevice(m->device));
     OS_TRY(ensure_views(m, m->num_views - 1));
@@ -2894,7 +2906,7 @@ int osfm_match_debug_dump_similarity(osfm_matcher* m, int kind, int view_q, int 
 int osfm_match_debug_trace(osfm_matcher* m, const int32_t* pairs, int npairs, int64_t* out, int64_t out_words) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
     OS_TRY(require_committed(m));
     CU_TRY(m, cudaSetDevice(m->device));
     OS_TRY(ensure_views(m, m->num_views - 1));
