@@ -128,11 +128,12 @@ int osfm_match_commit(osfm_matcher* m);
  * copies run on their own stream and osfm_match_commit returns WITHOUT waiting for them:
  * the buffers handed to osfm_match_set_view_q8 must stay valid and unchanged until the first
  * call that returns results (osfm_match_pairs*, osfm_match_pair*, osfm_match_two_view*) or
- * osfm_match_wait_staged has returned.  A pair list in the reference's order (view_1
- * ascending, bundler_matching.cc:92-93) is then matched in two phases -- the pairs within
- * the first quarter of the views, then the rest -- each starting as soon as its views have
- * arrived, so most of the copy time hides behind the matching of
- * the earlier pairs.  Views must be staged in ascending order (otherwise commit waits, as
+ * osfm_match_wait_staged has returned.  The first batched call then launches its filter pass
+ * in several pieces -- the pairs grouped by the highest view they need, view ranges growing
+ * geometrically -- each piece waiting on the device only for its own views, so the filter works
+ * on the early pairs of a list in the reference's order (view_1 ascending,
+ * bundler_matching.cc:92-93) while the later views are still being copied; nothing else of the
+ * batch is split.  Views must be staged in ascending order (otherwise commit waits, as
  * the plain one does); quantised descriptors only.  Results are the same as with
  * osfm_match_begin. */
 /* osfm_match_set_view_q8 for `count` consecutive views in one call (sift / surf: one pointer

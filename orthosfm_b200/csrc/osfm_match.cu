@@ -470,26 +470,26 @@ int arena_reserve(osfm_matcher* m, KindPool& k, int64_t rows) {
 int ksteps_of(const KindPool& k) { return (k.dim + 31) / 32; }
 
 template <int MODE, bool SIGNED>
-cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
+cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int item_first, int total_items, int32_t* dump, int64_t dump_ld) {
     cudaError_t e = cudaFuncSetAttribute(scan_kernel<MODE, kPassFilter, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kScanSmemBytes);
     if (e != cudaSuccess) return e;
-    int const grid = std::min(m->num_sms, total_items);
+    int const grid = std::min(m->num_sms, total_items - item_first);
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     ExactParams ex;
     memset(&ex, 0, sizeof ex);
     ex.norm2 = k.d_norm2.p;
     ex.viewmax = k.d_viewmax.p;
     scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, k.tmap, m->d_jobs.p, m->d_item_job.p, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
+        k.tmap, k.tmap, k.tmap, m->d_jobs.p, m->d_item_job.p, item_first, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
         m->d_counters + 6);
     return cudaGetLastError();
 }
 
 template <int MODE>
-cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int total_items, int32_t* dump, int64_t dump_ld) {
-    return k.is_signed ? launch_scan_t<MODE, true>(m, k, total_items, dump, dump_ld)
-                       : launch_scan_t<MODE, false>(m, k, total_items, dump, dump_ld);
+cudaError_t launch_scan(osfm_matcher* m, const KindPool& k, int item_first, int total_items, int32_t* dump, int64_t dump_ld) {
+    return k.is_signed ? launch_scan_t<MODE, true>(m, k, item_first, total_items, dump, dump_ld)
+                       : launch_scan_t<MODE, false>(m, k, item_first, total_items, dump, dump_ld);
 }
 
 // A second pass over gathered rows (RESOLVE: the filter's certified survivors; EXACT: unsigned
@@ -564,7 +564,7 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     scan_kernel<0, PASS, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
-        sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, sp.item_job.p, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
+        sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, sp.item_job.p, 0, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 3;
     if (PASS == kPassExact) {
@@ -599,25 +599,55 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     // concurrently running work items then stream the same candidate tiles (L2 locality), and the
     // second passes can merge the rows of all jobs that share a candidate view into full 256-row
     // items.
+    //
+    // Overlapped staging (views still on their way, m->lazy): the forward jobs are grouped into
+    // buckets by the highest view they need, view ranges growing geometrically, and the filter pass
+    // is launched bucket by bucket, each launch waiting (on the device) only for its views: the
+    // filter works on the early pairs of a list in the reference's order while the later views
+    // are being copied, and nothing else of the batch is split.
+    bool const staged = m->lazy && dump == nullptr;
+    std::vector<int> bucket_end;      // exclusive upper view id per bucket
+    if (staged && m->num_views >= 8) {
+        int b = std::max(2, (m->num_views + 5) / 6);
+        while (b < m->num_views) {
+            bucket_end.push_back(b);
+            b = std::max(b + 1, (b * 29 + 19) / 20);      // x 1.45
+        }
+    }
+    bucket_end.push_back(std::max(m->num_views, 1));
+    auto bucket_of = [&](JobSpec const& sp) {
+        if (sp.reverse || bucket_end.size() == 1) return 0;
+        int const v = std::max(sp.q_view, sp.c_view);
+        int b = 0;
+        while (b + 1 < static_cast<int>(bucket_end.size()) && v >= bucket_end[b]) ++b;
+        return b;
+    };
     std::vector<uint32_t> order(specs.size());
     for (size_t i = 0; i < specs.size(); ++i) order[i] = static_cast<uint32_t>(i);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         if (specs[a].reverse != specs[b].reverse) return !specs[a].reverse;
+        int const ba = bucket_of(specs[a]), bb = bucket_of(specs[b]);
+        if (ba != bb) return ba < bb;
         if (specs[a].c_view != specs[b].c_view) return specs[a].c_view < specs[b].c_view;
         return specs[a].c_n < specs[b].c_n;
     });
+    std::vector<int64_t> bucket_items(bucket_end.size(), 0);   // items up to and including each bucket
     std::vector<int32_t> seg_first;   // first job of every (direction, candidate view, c_n) segment
     std::vector<int32_t> job_of(specs.size(), -1);
     int64_t rows = 0, items = 0, fwd_rows = 0;
     int fwd_jobs = 0;
     bool prev_reverse = false;
+    int prev_bucket = 0;
     for (size_t oi = 0; oi < order.size(); ++oi) {
         size_t const i = order[oi];
         JobSpec const& s = specs[i];
         if (s.q_n <= 0 || s.c_n <= 0) continue;
-        if (jobs.empty() || prev_reverse != s.reverse || jobs.back().c_view != s.c_view || jobs.back().c_n != s.c_n)
+        int const bk = bucket_of(s);
+        if (jobs.empty() || prev_reverse != s.reverse || prev_bucket != bk || jobs.back().c_view != s.c_view ||
+            jobs.back().c_n != s.c_n)
             seg_first.push_back(static_cast<int32_t>(jobs.size()));
         prev_reverse = s.reverse;
+        prev_bucket = bk;
         ScanJob j;
         j.q_row = static_cast<int32_t>(k.off[s.q_view]);
         j.q_n = s.q_n;
@@ -631,6 +661,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         rows += s.q_n;
         if (!s.reverse) {
             items += (s.q_n + kItemM - 1) / kItemM;
+            for (size_t b = static_cast<size_t>(bk); b < bucket_items.size(); ++b) bucket_items[b] = items;
             fwd_rows = rows;
             fwd_jobs = static_cast<int>(jobs.size()) + 1;
         }
@@ -684,17 +715,23 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     m->stats.kernel_launches++;
     CU_TRY(m, m->phases.mark(m->stream, kPhFilter));
     cudaError_t e = cudaSuccess;
-    if (items > 0) {
+    int64_t launched = 0;
+    for (size_t b = 0; b < bucket_end.size(); ++b) {
+        // (a lazy commit: the views of this bucket have arrived and have their norms)
+        OS_TRY(ensure_views(m, bucket_end[b] - 1));
+        int const first = static_cast<int>(launched), last = static_cast<int>(bucket_items[b]);
+        if (last <= first) continue;
         switch (dump ? dump_mode : m->scan_mode) {
-            case 1: e = launch_scan<1>(m, k, static_cast<int>(items), nullptr, 0); break;
-            case 2: e = launch_scan<2>(m, k, static_cast<int>(items), m->d_oneway.p, 0); break;
-            case 3: e = launch_scan<3>(m, k, static_cast<int>(items), dump, dump_ld); break;
-            case 4: e = launch_scan<4>(m, k, static_cast<int>(items), dump, dump_ld); break;
-            case 5: e = launch_scan<5>(m, k, static_cast<int>(items), dump, dump_ld); break;
-            default: e = launch_scan<0>(m, k, static_cast<int>(items), nullptr, 0); break;
+            case 1: e = launch_scan<1>(m, k, first, last, nullptr, 0); break;
+            case 2: e = launch_scan<2>(m, k, first, last, m->d_oneway.p, 0); break;
+            case 3: e = launch_scan<3>(m, k, first, last, dump, dump_ld); break;
+            case 4: e = launch_scan<4>(m, k, first, last, dump, dump_ld); break;
+            case 5: e = launch_scan<5>(m, k, first, last, dump, dump_ld); break;
+            default: e = launch_scan<0>(m, k, first, last, nullptr, 0); break;
         }
         if (e != cudaSuccess) return cuda_fail(m, e, "scan_kernel launch");
         m->stats.kernel_launches++;
+        launched = last;
     }
     CU_TRY(m, m->phases.mark(m->stream, kPhClassify));
     m->stats.scan_items += items;
@@ -932,11 +969,7 @@ enum OutputMode { kFiltered = 0, kTwoway = 1 };
 int run_batch(osfm_matcher* m, const std::vector<PairPlan>& plans, int64_t dense_ints, OutputMode mode,
               int only_kind /* -1: both */) {
     int const np = static_cast<int>(plans.size());
-    if (m->lazy) {
-        int max_view = 0;
-        for (PairPlan const& p : plans) max_view = std::max(max_view, std::max(p.v1, p.v2));
-        OS_TRY(ensure_views(m, max_view));
-    }
+    // (a lazy commit is completed by run_jobs, bucket by bucket of its filter pass)
     CU_TRY(m, m->d_dense.reserve(static_cast<size_t>(std::max<int64_t>(dense_ints, 1))));
     CU_TRY(m, m->d_counts.reserve(static_cast<size_t>(np)));
     CU_TRY(m, cudaMemsetAsync(m->d_counts.p, 0, sizeof(int32_t) * np, m->stream));
@@ -1662,7 +1695,7 @@ static int match_pairs_dense(osfm_matcher* m, std::vector<PairPlan>& plans, Outp
             }
         host_base += dense;
         return OSFM_OK;
-    }, m->lazy ? m->num_views : 0);
+    });
     if (r != OSFM_OK) return r;
     if (offsets) offsets[2 * plans.size()] = host_base;
     CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));
@@ -1974,7 +2007,7 @@ static int compact_core(osfm_matcher* m, const int32_t* pairs, int npairs, int32
         // no host round trip here: the next batch is ordered behind this kernel by the stream,
         // and the pageable sources above were staged before cudaMemcpyAsync returned
         return OSFM_OK;
-    }, m->lazy ? m->num_views : 0);
+    });
     if (r != OSFM_OK) return r;
     list_offset[plans.size()] = list_base;
     CU_TRY(m, cudaEventRecord(m->ev[3], m->stream));

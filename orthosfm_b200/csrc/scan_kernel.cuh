@@ -23,6 +23,9 @@
 //     similarity matrix never leaves the SM.
 // Warps 0 and 1 issue the MMAs (one per query half, taking turns), warp 2 drives TMA.
 //
+// A launch covers the work items [item_first, total_items) of the job list (the filter pass of a
+// batch may be cut into several launches that start as the views they need arrive).
+//
 // Three passes share this pipeline and differ in the epilogue (template parameter PASS):
 //
 // FILTER (all rows).  Reads the accumulator with tcgen05.ld ... .pack::16b (two adjacent
@@ -391,7 +394,7 @@ template <int MODE, int PASS, bool SIGNED>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
             const __grid_constant__ CUtensorMap tmap_c2,
-            const ScanJob* __restrict__ jobs, const int32_t* __restrict__ item_job, int total_items_host, uint32_t idesc, int ksteps,
+            const ScanJob* __restrict__ jobs, const int32_t* __restrict__ item_job, int item_first, int total_items_host, uint32_t idesc, int ksteps,
             int32_t* __restrict__ dump, int64_t dump_ld, ExactParams ex, int2* __restrict__ rowres,
             unsigned long long* __restrict__ prof)
 {
@@ -455,7 +458,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         if (lane == 0) {
             int j = 0;
             uint32_t bcnt = 0, ic = 0;
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
+            for (int it = item_first + blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
                 j = item_job[it];
                 ScanJob const job = jobs[j];
                 int const rb = it - job.item_start;
@@ -510,7 +513,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         {
             int j = 0;
             uint32_t bcnt = 0, ic = 0, hc = 0;   // hc: tiles this issuer has issued so far
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
+            for (int it = item_first + blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
                 j = warp_uniform(item_job[it]);
                 int const c_n = warp_uniform(jobs[j].c_n);
                 int const rb = it - warp_uniform(jobs[j].item_start);
@@ -579,7 +582,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
         int j = 0;
         uint32_t cnt = 0, ic = 0;            // cnt: tiles of this warp's accumulator so far
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
+        for (int it = item_first + blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
             j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
@@ -787,7 +790,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
         int j = 0;
         uint32_t cnt_tiles = 0, ic = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
+        for (int it = item_first + blockIdx.x; it < total_items; it += gridDim.x, ++ic) {
             j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
@@ -885,7 +888,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
         int j = 0;
         uint32_t hcnt = 0;                   // tiles this group has processed so far
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        for (int it = item_first + blockIdx.x; it < total_items; it += gridDim.x) {
             j = item_job[it];
             ScanJob const job = jobs[j];
             int const rb = it - job.item_start;
