@@ -110,7 +110,9 @@ int osfm_match_begin(osfm_matcher* m, int num_views);
  * n_sift x 128 floats, row stride sift_stride floats (>= 128; the reference's
  * Sift::Descriptor is 132 floats, sift.h:137-149, so pass &descr[0].data[0] and
  * stride 132).  `surf` is n_surf x 64 floats, stride >= 64 (68 for
- * Surf::Descriptor, surf.h:83-95).  Either may be NULL with n = 0. */
+ * Surf::Descriptor, surf.h:83-95).  Either may be NULL with n = 0.  The floats are read
+ * at osfm_match_commit (by a few host threads at once, through page-locked buffers: a single
+ * pageable copy moves a fifth of what the link can). */
 int osfm_match_set_view_f32(osfm_matcher* m, int view_id,
     const float* sift, int n_sift, int sift_stride,
     const float* surf, int n_surf, int surf_stride);

@@ -10,6 +10,7 @@
 //
 // There is no CPU path in this file: every result comes from the kernels.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstdarg>
 #include <cstdio>
@@ -223,6 +224,19 @@ struct osfm_matcher {
     size_t rs_stage_ints = 0;
     cudaEvent_t rs_stage_free[2] = {nullptr, nullptr};
     DevBuf<float> d_ftmp;
+    // Float descriptors (osfm_match_set_view_f32) are staged at commit, by a few host threads at
+    // once: each copies views into its own page-locked buffers, sends them on and quantises them on
+    // its own stream (a single pageable cudaMemcpy moves about 11 GB/s, a fifth of the link).
+    struct FloatView { int kd; int64_t arena_row; const float* src; int n; int stride; };
+    std::vector<FloatView> float_views;
+    struct FloatLane {
+        cudaStream_t stream = nullptr;
+        float* pinned[2] = {nullptr, nullptr};
+        float* dev[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        size_t cap = 0;            // floats per buffer
+    };
+    std::vector<FloatLane> float_lanes;
     DevBuf<int32_t> d_seg_first;
     DevBuf<int32_t> d_item_job;          // filter pass: the job of every work item
     DevBuf<int32_t> d_rev_of;            // per job: the reverse job of its pair (or -1)
@@ -1236,6 +1250,15 @@ void osfm_match_destroy(osfm_matcher* m) {
     }
     m->rs_stage_ints = 0;
     m->d_ftmp.release();
+    for (auto& ln : m->float_lanes) {
+        for (int b = 0; b < 2; ++b) {
+            if (ln.pinned[b]) cudaFreeHost(ln.pinned[b]);
+            if (ln.dev[b]) cudaFree(ln.dev[b]);
+            if (ln.done[b]) cudaEventDestroy(ln.done[b]);
+        }
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    m->float_lanes.clear();
     m->d_seg_first.release();
     m->d_rev_of.release(); m->d_item_job.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
@@ -1382,6 +1405,7 @@ static int begin_impl(osfm_matcher* m, int num_views, bool overlap) {
     m->committed = false;
     m->cache_full.clear();
     m->cache_lowres.clear();
+    m->float_views.clear();
     m->overlap = overlap;
     m->lazy = false;
     if (overlap) {
@@ -1418,16 +1442,9 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
     if (is_float) {
         if (m->overlap) return fail(m, OSFM_ERR_STATE, "overlapped staging takes quantised descriptors (set_view_q8)");
         if (stride < k.dim) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "stride %d < descriptor length %d", stride, k.dim);
-        size_t const count = static_cast<size_t>(n - 1) * stride + k.dim;
-        if (count > m->d_ftmp.cap) CU_TRY(m, cudaStreamSynchronize(m->stream));  // still read by a kernel
-        CU_TRY(m, m->d_ftmp.reserve(count));
-        CU_TRY(m, cudaMemcpyAsync(m->d_ftmp.p, src, count * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        int64_t const total = static_cast<int64_t>(n) * kRowBytes;
-        int const grid = static_cast<int>((total + 255) / 256);
-        if (k.is_signed) quantize_kernel<true><<<grid, 256, 0, m->stream>>>(m->d_ftmp.p, n, k.dim, stride, d);
-        else             quantize_kernel<false><<<grid, 256, 0, m->stream>>>(m->d_ftmp.p, n, k.dim, stride, d);
-        CU_TRY(m, cudaGetLastError());
-        m->stats.kernel_launches++;
+        // moved at commit (run_float_views); the source stays valid until then
+        m->float_views.push_back({kd, k.arena_used, static_cast<const float*>(src), n, stride});
+        (void)d;
     } else if (k.dim == kRowBytes) {
         CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, cs));
     } else {
@@ -1497,6 +1514,84 @@ int osfm_match_set_views_q8(osfm_matcher* m, int first_view, int count, const ui
     OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
 
+// Stages the float views recorded by osfm_match_set_view_f32: a few host threads, each with two
+// page-locked buffers, two device buffers and a stream of its own: copy a view into page-locked
+// memory, send it, quantise it into its place in the arena (convert_descriptor,
+// exhaustive_matching.cc:18-39, on the device), take the next view while that runs.
+static int run_float_views(osfm_matcher* m) {
+    std::vector<osfm_matcher::FloatView>& views = m->float_views;
+    if (views.empty()) return OSFM_OK;
+    size_t max_floats = 0;
+    for (auto const& v : views)
+        max_floats = std::max(max_floats, static_cast<size_t>(v.n - 1) * v.stride + m->kind[v.kd].dim);
+    unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
+    size_t const lanes = std::min<size_t>(std::min<size_t>(8, std::max(1u, hw / 2)), views.size());
+    CU_TRY(m, cudaStreamSynchronize(m->stream));          // the arena may just have been moved
+    if (m->float_lanes.size() < lanes) m->float_lanes.resize(lanes);
+    for (size_t l = 0; l < lanes; ++l) {
+        osfm_matcher::FloatLane& ln = m->float_lanes[l];
+        if (!ln.stream) CU_TRY(m, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b)
+            if (!ln.done[b]) CU_TRY(m, cudaEventCreateWithFlags(&ln.done[b], cudaEventDisableTiming));
+        if (ln.cap < max_floats) {
+            for (int b = 0; b < 2; ++b) {
+                if (ln.pinned[b]) cudaFreeHost(ln.pinned[b]);
+                if (ln.dev[b]) cudaFree(ln.dev[b]);
+                ln.pinned[b] = nullptr; ln.dev[b] = nullptr;
+            }
+            ln.cap = 0;
+            size_t const want = max_floats + max_floats / 8;
+            for (int b = 0; b < 2; ++b) {
+                CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&ln.pinned[b]), want * sizeof(float), cudaHostAllocDefault));
+                CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&ln.dev[b]), want * sizeof(float)));
+            }
+            ln.cap = want;
+        }
+    }
+    std::atomic<size_t> next(0);
+    std::vector<cudaError_t> err(lanes, cudaSuccess);
+    auto work = [&](size_t l) {
+        osfm_matcher::FloatLane& ln = m->float_lanes[l];
+        cudaError_t e = cudaSetDevice(m->device);
+        bool used[2] = {false, false};
+        int b = 0;
+        for (size_t i = next.fetch_add(1); e == cudaSuccess && i < views.size(); i = next.fetch_add(1), b ^= 1) {
+            osfm_matcher::FloatView const& v = views[i];
+            KindPool const& k = m->kind[v.kd];
+            size_t const count = static_cast<size_t>(v.n - 1) * v.stride + k.dim;
+            if (used[b]) e = cudaEventSynchronize(ln.done[b]);       // this pair of buffers is free again
+            if (e != cudaSuccess) break;
+            memcpy(ln.pinned[b], v.src, count * sizeof(float));
+            e = cudaMemcpyAsync(ln.dev[b], ln.pinned[b], count * sizeof(float), cudaMemcpyHostToDevice, ln.stream);
+            if (e != cudaSuccess) break;
+            uint8_t* const dst = k.arena + static_cast<size_t>(v.arena_row) * kRowBytes;
+            int64_t const total = static_cast<int64_t>(v.n) * kRowBytes;
+            int const grid = static_cast<int>((total + 255) / 256);
+            if (k.is_signed) quantize_kernel<true><<<grid, 256, 0, ln.stream>>>(ln.dev[b], v.n, k.dim, v.stride, dst);
+            else             quantize_kernel<false><<<grid, 256, 0, ln.stream>>>(ln.dev[b], v.n, k.dim, v.stride, dst);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaEventRecord(ln.done[b], ln.stream);
+            used[b] = true;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ln.stream);
+        err[l] = e;
+    };
+    std::vector<std::thread> threads;
+    try {
+        for (size_t l = 1; l < lanes; ++l) threads.emplace_back(work, l);
+    } catch (...) {
+        // fewer threads than planned: the lanes that did start (and this one) drain the queue
+    }
+    work(0);
+    for (std::thread& t : threads) t.join();
+    m->stats.kernel_launches += static_cast<int64_t>(views.size());
+    views.clear();
+    CU_TRY(m, cudaSetDevice(m->device));
+    for (cudaError_t e : err)
+        if (e != cudaSuccess) return cuda_fail(m, e, "staging float descriptors");
+    return OSFM_OK;
+}
+
 int osfm_match_commit(osfm_matcher* m) {
     OSFM_TRY_BEGIN
     if (!m) return OSFM_ERR_INVALID_ARGUMENT;
@@ -1506,6 +1601,7 @@ int osfm_match_commit(osfm_matcher* m) {
     // Overlapped staging stays lazy only if the arena already is the pool (views staged in
     // ascending order); otherwise everything is waited for here, as in the plain commit.
     // (a multi-device matcher broadcasts the complete pool at commit: nothing stays lazy)
+    OS_TRY(run_float_views(m));
     bool const lazy = m->overlap && m->kind[0].in_order && m->kind[1].in_order && m->peers.empty();
     if (m->overlap && !lazy) CU_TRY(m, cudaStreamSynchronize(m->copy_stream));
     for (int kd = 0; kd < 2; ++kd) {
