@@ -182,8 +182,9 @@ int osfm_match_pair(osfm_matcher* m, int view_1_id, int view_2_id,
  * pairwise_match once per pair, in the order i -> (view_1, view_2) of bundler_matching.cc:92-93.
  * With max_pairs > 1, an osfm_match_pair(view_1 > view_2) call whose pair is not cached
  * matches that pair AND the max_pairs - 1 pairs that follow it in this order in one batched pass
- * (dense results kept in pinned host memory, at most 1 GiB); the calls that follow are served
- * from it.  osfm_match_pair_lowres does the same with a window of 16 x max_pairs.  Results are
+ * (sharded over the devices of a multi-device handle; the correspondence lists are kept in pinned
+ * host memory, at most 1 GiB, and a pair's dense vectors are rebuilt from its list); the calls
+ * that follow are served from it.  osfm_match_pair_lowres does the same with a window of 16 x max_pairs.  Results are
  * identical; pairs the caller skips (its low-res gate) were matched for nothing.  0 (default): off.
  * The cache is dropped by osfm_match_begin* / osfm_match_commit_device. */
 int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs);

@@ -288,9 +288,10 @@ struct osfm_matcher {
         int64_t first = -1;               // flat pair index of the first cached pair (-1: empty)
         int count = 0;
         int num_features = 0;             // low-res cache: the feature limit it was computed with
-        std::vector<int64_t> offsets;     // dense cache: 2 * count + 1
+        std::vector<int64_t> offsets;     // full cache: list offsets, count + 1
         std::vector<int32_t> counts;
-        int32_t* host = nullptr;          // dense cache: pinned
+        std::vector<int32_t> lens;        // full cache: lengths of the two dense vectors per pair
+        int32_t* host = nullptr;          // full cache: the (i, j) lists, pinned
         size_t host_cap = 0;              // ints
         void clear() { first = -1; count = 0; }
     } cache_full, cache_lowres;
@@ -1846,12 +1847,19 @@ int osfm_match_set_lookahead(osfm_matcher* m, int max_pairs) {
 }
 
 // Serves osfm_match_pair from the look-ahead cache, filling it first if (view_1, view_2) is not in it.
+static int compact_to_host(osfm_matcher* m, const int32_t* pairs, int npairs, int32_t* match_ij, int64_t capacity_ij,
+                           int64_t* list_offset, bool sift_only, int min_count, int32_t* counts_out);
+
 static int pair_from_lookahead(osfm_matcher* m, int v1, int v2, int32_t* matches_1_2, int* len_1_2,
                                int32_t* matches_2_1, int* len_2_1, int* n_consistent) {
+    // The cache holds the window's correspondence lists ((i, j) pairs in the combined SIFT + SURF
+    // index space, an eighth of the dense vectors' bytes to bring back), computed by the same
+    // sharded call as osfm_match_pairs_compact; a pair's dense Matching::Result is rebuilt from its
+    // list when it is asked for: after the mutual filter the two vectors hold exactly those pairs.
     osfm_matcher::PairCache& c = m->cache_full;
     int64_t const idx = flat_pair_index(v1, v2);
     if (c.first < 0 || idx < c.first || idx >= c.first + c.count) {
-        constexpr int64_t kMaxCacheInts = 1ll << 28;     // 1 GiB of pinned host memory at most
+        constexpr int64_t kMaxCacheEntries = 1ll << 27;     // 1 GiB of pinned host memory at most
         std::vector<int32_t> pairs;
         lookahead_window(m->num_views, v1, v2, m->lookahead, pairs);
         std::vector<PairPlan> plans;
@@ -1859,32 +1867,41 @@ static int pair_from_lookahead(osfm_matcher* m, int v1, int v2, int32_t* matches
         int64_t total = 0;
         size_t keep = 0;
         for (; keep < plans.size(); ++keep) {
-            int64_t const d = static_cast<int64_t>(plans[keep].len12) + plans[keep].len21;
-            if (keep > 0 && total + d > kMaxCacheInts) break;
+            PairPlan const& p = plans[keep];
+            int64_t const d = std::min(p.n1[0], p.n2[0]) + std::min(p.n1[1], p.n2[1]);   // a list cannot be longer
+            if (keep > 0 && total + d > kMaxCacheEntries) break;
             total += d;
         }
         plans.resize(keep);
         c.clear();
-        if (static_cast<size_t>(total) + 1 > c.host_cap) {
+        if (2 * static_cast<size_t>(total) + 2 > c.host_cap) {
             CU_TRY(m, cudaSetDevice(m->device));
             if (c.host) cudaFreeHost(c.host);
             c.host = nullptr; c.host_cap = 0;
-            size_t const want = static_cast<size_t>(total) + static_cast<size_t>(total) / 8 + 1024;
+            size_t const want = 2 * static_cast<size_t>(total) + static_cast<size_t>(total) / 4 + 1024;
             CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&c.host), want * sizeof(int32_t), cudaHostAllocDefault));
             c.host_cap = want;
         }
-        c.offsets.assign(2 * plans.size() + 1, 0);
+        c.offsets.assign(plans.size() + 1, 0);
         c.counts.assign(plans.size(), 0);
-        OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, c.host, c.offsets.data(), c.counts.data()));
+        c.lens.resize(2 * plans.size());
+        for (size_t p = 0; p < plans.size(); ++p) { c.lens[2 * p] = plans[p].len12; c.lens[2 * p + 1] = plans[p].len21; }
+        OS_TRY(compact_to_host(m, pairs.data(), static_cast<int>(plans.size()), c.host, static_cast<int64_t>(c.host_cap / 2),
+                               c.offsets.data(), false, 0, c.counts.data()));
         c.first = idx;
         c.count = static_cast<int>(plans.size());
     }
     size_t const k = static_cast<size_t>(idx - c.first);
-    int64_t const o12 = c.offsets[2 * k], o21 = c.offsets[2 * k + 1], end = c.offsets[2 * k + 2];
-    if (matches_1_2 && o21 > o12) memcpy(matches_1_2, c.host + o12, sizeof(int32_t) * (o21 - o12));
-    if (matches_2_1 && end > o21) memcpy(matches_2_1, c.host + o21, sizeof(int32_t) * (end - o21));
-    if (len_1_2) *len_1_2 = static_cast<int>(o21 - o12);
-    if (len_2_1) *len_2_1 = static_cast<int>(end - o21);
+    int const l12 = c.lens[2 * k], l21 = c.lens[2 * k + 1];
+    if (matches_1_2) std::fill(matches_1_2, matches_1_2 + l12, -1);
+    if (matches_2_1) std::fill(matches_2_1, matches_2_1 + l21, -1);
+    for (int64_t e = c.offsets[k]; e < c.offsets[k + 1]; ++e) {
+        int32_t const i = c.host[2 * e], jj = c.host[2 * e + 1];
+        if (matches_1_2) matches_1_2[i] = jj;
+        if (matches_2_1) matches_2_1[jj] = i;
+    }
+    if (len_1_2) *len_1_2 = l12;
+    if (len_2_1) *len_2_1 = l21;
     if (n_consistent) *n_consistent = c.counts[k];
     return OSFM_OK;
 }
@@ -1959,7 +1976,7 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
             OS_TRY(build_plans(m, pairs.data(), static_cast<int>(pairs.size() / 2), static_cast<int>(num_features), true, plans));
             c.clear();
             c.counts.assign(plans.size(), 0);
-            OS_TRY(match_pairs_dense(m, plans, kFiltered, -1, nullptr, nullptr, c.counts.data()));
+            OS_TRY(dense_dispatch(m, plans, kFiltered, -1, nullptr, nullptr, c.counts.data()));
             c.first = idx;
             c.count = static_cast<int>(plans.size());
             c.num_features = static_cast<int>(num_features);
