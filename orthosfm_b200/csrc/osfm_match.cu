@@ -239,6 +239,7 @@ struct osfm_matcher {
     std::vector<FloatLane> float_lanes;
     DevBuf<int32_t> d_seg_first;
     DevBuf<int32_t> d_item_job;          // filter pass: the job of every work item
+    DevBuf<uint4> d_stash;               // RESOLVE pass: one set-aside packed load per thread (ResolveStash)
     DevBuf<int32_t> d_rev_of;            // per job: the reverse job of its pair (or -1)
     // restricted candidate sets of the reverse pass (select_candidates_kernel)
     DevBuf<int32_t> d_tau;
@@ -566,6 +567,11 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     ex.viewmax = nullptr;
     ex.verify = verify ? 1 : 0;
     ex.col_map = subset ? subset->col_map : nullptr;
+    ex.stash = nullptr;
+    if (PASS == kPassResolve) {
+        CU_TRY(m, m->d_stash.reserve(static_cast<size_t>(m->num_sms) * 8 * kScanThreads));
+        ex.stash = m->d_stash.p;
+    }
     ex.replay_flags = nullptr;
     if (PASS == kPassExact) {
         CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
@@ -1261,7 +1267,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     }
     m->float_lanes.clear();
     m->d_seg_first.release();
-    m->d_rev_of.release(); m->d_item_job.release();
+    m->d_rev_of.release(); m->d_item_job.release(); m->d_stash.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
     m->d_cand_pool.release(); m->d_cand_map.release();
     m->d_replay_flags.release();

@@ -166,6 +166,9 @@ struct ExactParams {
     // RESOLVE pass over a restricted candidate set (jobs with c_view < 0 read their candidates from
     // the second candidate tensor map, a gathered subset of the view): column -> row of the view
     const int32_t* col_map;
+    // RESOLVE pass: 8 x uint4 per thread of the grid, for the one packed load per row and item
+    // that holds the row's best value (ResolveStash)
+    uint4* stash;
 };
 
 // Sets bit g of a bitmap; true for the caller that set it.  Keeps a row from entering the replay
@@ -302,39 +305,91 @@ __device__ __forceinline__ void slots_top2(const uint32_t (&m)[kSlotRegs], int& 
 #endif
 constexpr int kResolveChains = OSFM_RESOLVE_CHAINS;   // dependent chains of the RESOLVE load maximum
 
-// RESOLVE: a group of 16 consecutive columns (eight packed registers) that contains the row's
-// best value V, set aside to be looked at value by value later (see the RESOLVE epilogue).
-struct ResolvePending {
-    uint32_t r[8];
-    int col;            // first column of the group in the candidate view; -1: nothing pending
+// RESOLVE: a packed load (64 columns, 32 registers) that contains the row's best value V is set
+// aside whole, in this thread's slot of a global scratch buffer, to be looked at value by value
+// at the end of the work item.  Setting it aside is eight 16-byte stores: the thread is back at
+// its accumulator in time (finding and keeping the 16-column group in registers, as round 1 did,
+// was ~100 dependent instructions in a divergent region, on 40 % of the tile visits -- more than
+// the slack a tile leaves, so one late warp of the eight stalled the accumulator's hand-back).
+struct ResolveStash {
+    uint4* slot;        // element q of this thread's slot is slot[q * kScanThreads]
+    int col;            // first column of the load in the candidate view; -1: nothing set aside
 };
 
-// Looks at a pending group: counts the columns equal to V, remembers the last one and takes
-// the maximum of the others.  (col < c_n: a masked column of an all-zero row is no column.)
+// Looks at eight packed registers (16 columns from column `col`) value by value: counts the
+// columns equal to V, remembers the last one and takes the maximum of the others.
+// (col < c_n: a masked column of an all-zero row is no column.)
 template <bool SIGNED>
-__device__ __forceinline__ void resolve_flush(ResolvePending& pd, int c_n, int V, int& cnt, int& idx, int& v2) {
-    if (pd.col < 0) return;
+__device__ __forceinline__ void resolve_scan16(const uint32_t (&r)[8], int col, int c_n, int V, int& cnt, int& idx, int& v2) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        int const col = pd.col + 2 * k;
-        int const x0 = plo<SIGNED>(pd.r[k]), x1 = phi<SIGNED>(pd.r[k]);
-        bool const e0 = x0 == V && col < c_n;
-        bool const e1 = x1 == V && col + 1 < c_n;
+        int const c0 = col + 2 * k;
+        int const x0 = plo<SIGNED>(r[k]), x1 = phi<SIGNED>(r[k]);
+        bool const e0 = x0 == V && c0 < c_n;
+        bool const e1 = x1 == V && c0 + 1 < c_n;
         cnt += (e0 ? 1 : 0) + (e1 ? 1 : 0);
-        idx = e1 ? col + 1 : (e0 ? col : idx);
+        idx = e1 ? c0 + 1 : (e0 ? c0 : idx);
         v2 = max(v2, e0 ? 0 : x0);
         v2 = max(v2, e1 ? 0 : x1);
     }
-    pd.col = -1;
+}
+
+// Looks at the load set aside.  Normally exactly one of its four groups of 16 columns holds V:
+// that group is picked with selects (every lane of the warp has its own, so no branch per group)
+// and scanned; the other groups only feed v2.  A lane with V in several groups (duplicates) scans
+// all four.
+template <bool SIGNED>
+__device__ __forceinline__ void resolve_flush(ResolveStash& st, int c_n, int V, int& cnt, int& idx, int& v2) {
+    if (st.col < 0) return;
+    uint32_t r[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint4 const w = st.slot[q * kScanThreads];
+        r[4 * q] = w.x; r[4 * q + 1] = w.y; r[4 * q + 2] = w.z; r[4 * q + 3] = w.w;
+    }
+    int mg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t const a = pmax3<SIGNED>(r[8 * i], r[8 * i + 1], r[8 * i + 2]);
+        uint32_t const b = pmax3<SIGNED>(r[8 * i + 3], r[8 * i + 4], r[8 * i + 5]);
+        uint32_t const g = pmax<SIGNED>(pmax3<SIGNED>(a, b, r[8 * i + 6]), r[8 * i + 7]);
+        mg[i] = max(plo<SIGNED>(g), phi<SIGNED>(g));
+    }
+    int const hits = (mg[0] >= V ? 1 : 0) + (mg[1] >= V ? 1 : 0) + (mg[2] >= V ? 1 : 0) + (mg[3] >= V ? 1 : 0);
+    if (hits == 1) {
+        int const gi = mg[1] >= V ? 1 : (mg[2] >= V ? 2 : (mg[3] >= V ? 3 : 0));
+        uint32_t sel[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t const lo = (gi & 1) ? r[8 + k] : r[k];
+            uint32_t const hi = (gi & 1) ? r[24 + k] : r[16 + k];
+            sel[k] = (gi & 2) ? hi : lo;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v2 = max(v2, i == gi ? 0 : mg[i]);
+        resolve_scan16<SIGNED>(sel, st.col + 16 * gi, c_n, V, cnt, idx, v2);
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            uint32_t grp[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t const lo = (i & 1) ? r[8 + k] : r[k];
+                uint32_t const hi = (i & 1) ? r[24 + k] : r[16 + k];
+                grp[k] = (i & 2) ? hi : lo;
+            }
+            resolve_scan16<SIGNED>(grp, st.col + 16 * i, c_n, V, cnt, idx, v2);
+        }
+    }
+    st.col = -1;
 }
 
 // RESOLVE: one packed load (64 columns starting at column col0 of the candidate view) of a row
-// whose largest similarity V is known.  Groups that cannot contain V only feed v2; a group
-// that does is set aside (columns are visited in ascending order, so flushing the previous
-// pending group first keeps "the last column equal to V" right).
+// whose largest similarity V is known.  A load that cannot contain V only feeds v2; one that does
+// is set aside (columns are visited in ascending order).
 template <bool SIGNED>
-__device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int c_n, int& V, bool& beaten,
-                                             ResolvePending& pd, int& cnt, int& idx, int& v2)
+__device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, int& V, bool& beaten,
+                                             ResolveStash& st, bool& dup, int& v2)
 {
     // the load's maximum as ONE dependent chain (like the filter's fold: a warp that stalls on
     // its own result leaves issue slots to the MMA issuers; a tree would issue back to back)
@@ -362,26 +417,15 @@ __device__ __forceinline__ void resolve_load(const uint32_t (&r)[32], int col0, 
         V = 0x7fffffff;     // nothing reaches this: the row stays on the fast path from here on
         return;
     }
-    // some lane has V in this load: maxima of the four groups of 16 columns
-    uint32_t g[4];
+    // This load holds the row's best value (once per row and item, unless it has duplicates).  An
+    // earlier load still set aside then also holds V: the row has at least two columns equal to
+    // V -- all that the result needs of the earlier one (the second best is V itself, the index
+    // is the LAST column equal to V, which lies in this load or a later one) -- and it is dropped.
+    dup = dup || st.col >= 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t const a = pmax3<SIGNED>(r[8 * i], r[8 * i + 1], r[8 * i + 2]);
-        uint32_t const b = pmax3<SIGNED>(r[8 * i + 3], r[8 * i + 4], r[8 * i + 5]);
-        g[i] = pmax<SIGNED>(pmax3<SIGNED>(a, b, r[8 * i + 6]), r[8 * i + 7]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int const mg = max(plo<SIGNED>(g[i]), phi<SIGNED>(g[i]));
-        if (mg < V) {
-            v2 = max(v2, mg);
-        } else {
-            resolve_flush<SIGNED>(pd, c_n, V, cnt, idx, v2);     // rare: a second hit before the flush
-#pragma unroll
-            for (int k = 0; k < 8; ++k) pd.r[k] = r[8 * i + k];
-            pd.col = col0 + 16 * i;
-        }
-    }
+    for (int q = 0; q < 8; ++q)
+        st.slot[q * kScanThreads] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    st.col = col0;
 }
 
 // MODE 0: normal.  1: epilogue only hands the accumulator back (MMA/TMA ceiling).
@@ -808,7 +852,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             bool beaten = false;    // some similarity exceeds V (legitimate in the reverse pass only)
 
             int cnt = 0, idx = -1, v2 = 0;
-            ResolvePending pd;
+            int cnt_r = 0, idx_r = -1, v2_r = 0;     // what a ragged last tile adds (its columns come last)
+            bool dup = false;                        // V seen in more than one load of this warp
+            ResolveStash pd;
+            pd.slot = ex.stash + static_cast<size_t>(blockIdx.x) * 8 * kScanThreads + threadIdx.x;
             pd.col = -1;
             for (int t = 0; t < ntiles; ++t, ++cnt_tiles) {
                 int const ncols = job.c_n - t * kBlockN;
@@ -817,7 +864,6 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 if (ncols < kBlockN) {
                     // a ragged last tile, apart from the loop proper (see the filter): value by
                     // value over the valid columns
-                    resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
 #pragma unroll 1
                     for (int q4 = 0; q4 < kAccCols / kChunk; ++q4) {
                         int32_t v[32];
@@ -829,9 +875,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                             bool const valid = colq + q < job.c_n;
                             bool const eq = valid && v[q] == V;
                             beaten = beaten || (valid && v[q] > V);
-                            cnt += eq ? 1 : 0;
-                            idx = eq ? colq + q : idx;
-                            v2 = max(v2, (valid && !eq) ? v[q] : 0);
+                            cnt_r += eq ? 1 : 0;
+                            idx_r = eq ? colq + q : idx_r;
+                            v2_r = max(v2_r, (valid && !eq) ? v[q] : 0);
                         }
                     }
                     tc_fence_before_sync();
@@ -848,13 +894,15 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(h));
                 int const col0 = t * kBlockN + c * kAccCols;
-                resolve_load<SIGNED>(ra, col0, job.c_n, V, beaten, pd, cnt, idx, v2);
-                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, job.c_n, V, beaten, pd, cnt, idx, v2);
+                resolve_load<SIGNED>(ra, col0, V, beaten, pd, dup, v2);
+                resolve_load<SIGNED>(rc, col0 + kAccCols / 2, V, beaten, pd, dup, v2);
             }
-            // The group set aside is looked at once, here: a row has one column equal to V unless
-            // it has duplicates, so the value-by-value scan runs once per item for all the rows
-            // of the warp instead of once per hit.
+            // The load set aside is looked at once, here, for all the rows of the warp; then
+            // what the ragged tile found in the columns after it.
             resolve_flush<SIGNED>(pd, job.c_n, V, cnt, idx, v2);
+            cnt += cnt_r + (dup ? 1 : 0);
+            idx = idx_r >= 0 ? idx_r : idx;
+            v2 = max(v2, v2_r);
             int4* const merge = merge_base + (ic & 1) * (kMergeBufBytes / 16) + h * kHalfM + row;
             if (c == 1) *merge = make_int4(cnt, idx, v2, beaten ? 1 : 0);
             named_barrier_sync(1 + h * 4 + quad, 64);
