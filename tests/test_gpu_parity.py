@@ -339,6 +339,8 @@ def _one_product_cases():
     cases.append(("surf", "s8", a, b, 0.7))
     cases.append(("surf-ratio-1", "s8", a, b, 1.0))
     cases.append(("surf-negative", "s8", np.abs(a[:33]), -np.abs(b[:20]), 1.0))   # every similarity <= 0
+    pool = synth.surf_pool(36, 700)
+    cases.append(("surf-large", "s8", synth.surf_view(36, 0, 1600, pool), synth.surf_view(36, 1, 1400, pool), 0.7))
     a = rng.integers(-127, 128, (300, 64), dtype=np.int8)   # arbitrary signed bytes: no norm certificate
     b = rng.integers(-127, 128, (280, 64), dtype=np.int8)
     b[:60] = a[:60]
@@ -361,6 +363,7 @@ def test_one_product_per_pair_equals_both_directions(ora, case):
         one = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
         lowres_one = m.pairwise_match_lowres(0, 1, 200)
         claimed = m.stats()["claimed_rows"]
+        restricted = m.stats()["reverse_restricted_pairs"]
         m.debug_set_both_directions(2)                    # claimed rows against the whole other view
         whole = [m.pairwise_match(0, 1), m.pairwise_match(1, 0)]
         claimed_after_whole = m.stats()["claimed_rows"]
@@ -376,6 +379,8 @@ def test_one_product_per_pair_equals_both_directions(ora, case):
     for r in (one[1], whole[1], both[1]):
         assert np.array_equal(r.matches_1_2, f21) and np.array_equal(r.matches_2_1, f12)
     assert lowres_one == lowres_both
+    if case[0] in ("renorm", "surf-large"):
+        assert restricted == 2, restricted      # both calls held their claimed rows against a subset of the other view
     assert 0 <= claimed <= (o12 >= 0).sum() + (o21 >= 0).sum() + 200   # at most one row per forward match
 
 
@@ -583,6 +588,8 @@ def test_baseline_config_2_lists_equal_the_reference():
         assert_clean(m)
         st = m.stats()
     assert st["exact_rows"] < 64                     # unit-norm data: next to nothing reaches 2^16
+    assert st["reverse_restricted_pairs"] >= 600     # (nearly) every pair's claimed rows met a subset of the other view ...
+    assert st["reverse_candidate_rows"] < 630 * 8192 // 4    # ... a small one
     sample = list(range(0, 630, 53))                 # 12 pairs
     impl = oracle.Reference() if oracle.have_ref() else oracle.Oracle()
     from concurrent.futures import ThreadPoolExecutor      # (ctypes releases the GIL)
