@@ -2187,7 +2187,13 @@ static int run_sharded(osfm_matcher* m, std::vector<Shard>& shards, Fn fn) {
             threads.emplace_back([&shards, &fn, d] {
                 Shard& sh = shards[d];
                 std::lock_guard<std::recursive_mutex> lock(sh.h->mu);
-                sh.rc = fn(sh);
+                try {                       // an exception must not leave a thread
+                    sh.rc = fn(sh);
+                } catch (const std::bad_alloc&) {
+                    sh.rc = fail(sh.h, OSFM_ERR_OUT_OF_MEMORY, "out of host memory");
+                } catch (...) {
+                    sh.rc = fail(sh.h, OSFM_ERR_INTERNAL, "unexpected exception");
+                }
             });
         }
     } catch (...) {
