@@ -416,6 +416,8 @@ typedef struct {
     int64_t reverse_restricted_pairs; /* (pair, kind) jobs whose reverse direction was held against a subset of the
                                     other view only: the rows whose own best similarity can matter; cumulative */
     int64_t reverse_candidate_rows;   /* rows in those subsets, cumulative */
+    int64_t exact_wide_rows;     /* of exact_rows: replayed from CUDA-core inner products spread over the device
+                                    (few rows against large views) instead of by the scan pass; cumulative */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
@@ -430,6 +432,11 @@ int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
  * those are held against the whole other view instead of the subset of its rows that can matter.
  * on = 0: the default.  Same results in every mode; for A/B tests and timing. */
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on);
+/* Rows whose similarities reach 2^16 are replayed exactly.  mode 0 (default): when their inner
+ * products fit a scratch buffer they are computed on CUDA cores across the whole device and
+ * replayed one warp per row; otherwise by the tensor-core scan pass.  mode 1: always the scan
+ * pass.  Same results either way; for A/B tests and timing. */
+int osfm_match_debug_set_exact_path(osfm_matcher* m, int mode);
 /* Writes the raw int32 similarity matrix of one (query view, candidate view)
  * SIFT job as computed by the tensor-core kernel: out is n_q x ld ints,
  * ld = 256 * ceil(n_c / 256). */

@@ -247,11 +247,20 @@ struct osfm_matcher {
     DevBuf<int32_t> d_seg_first_rev;
     DevBuf<uint8_t> d_cand_pool;
     DevBuf<int32_t> d_cand_map;
+    DevBuf<int32_t> d_cand_cnt;                // per forward job: rows kept (-1: the reverse job keeps the whole view)
     CUtensorMap cand_tmap;
     uint8_t* cand_tmap_for = nullptr;
     size_t cand_tmap_rows = 0;
     int reverse_mode = 0;                // 0: restricted candidate sets; 2: whole views (A/B switch)
     DevBuf<uint32_t> d_replay_flags;     // bitmap over a batch's rows: already in the replay list
+    // EXACT rows of very few jobs against large views: inner products on CUDA cores, spread over
+    // the device, then a warp-per-row replay (post_kernels.cuh, exact_dots_kernel)
+    DevBuf<int32_t> d_xw_x, d_xw_xmax;
+    DevBuf<int64_t> d_xw_off, d_xw_moff;
+    DevBuf<int> d_xw_unit;
+    int* d_xw_meta = nullptr;            // [0] path taken, [1] units, [4] work items left to the scan pass
+    int exact_mode = 0;                  // 0: by capacity; 1: always the scan pass (A/B switch)
+    int batch_max_cn = 0;                // largest candidate set of the batch being run
     // scratch of the two second passes over gathered rows: [0] RESOLVE (the filter's certified
     // survivors), [1] EXACT (unsigned rows without the 16-bit norm certificate)
     struct SecondPass {
@@ -544,7 +553,10 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
                                                  PASS == kPassExact ? m->d_counters + 5 : nullptr, sp.item_job.p);
     CU_TRY(m, cudaGetLastError());
-    gather_rows_kernel<<<std::min(std::max(njobs, 1), m->num_sms * 16), 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
+    // few jobs (one pair of two large views): several blocks share a job's list
+    int const gather_x = std::min(std::max(njobs, 1), m->num_sms * 16);
+    dim3 const gather_grid(gather_x, std::max(1, std::min(64, m->num_sms * 4 / gather_x)));
+    gather_rows_kernel<<<gather_grid, 256, 0, m->stream>>>(m->d_jobs.p, njobs, sp.cnt.p,
                                                               sp.job_xrow.p, sp.list.p, k.pool,
                                                               sp.xpool.p, sp.xrow_map.p,
                                                               verify && PASS == kPassResolve ? m->d_rowres.p : nullptr);
@@ -583,6 +595,54 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
         CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
     }
+    if (PASS == kPassExact) {
+        // few rows against large views: every inner product on CUDA cores, spread over the device,
+        // then a warp-per-row replay; the scan pass below then finds no work items.  Decided on the
+        // device (the host does not know how many rows there are) by what fits the scratch buffer.
+        if (!m->d_xw_meta) {
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xw_meta), 8 * sizeof(int)));
+            CU_TRY(m, cudaMemset(m->d_xw_meta, 0, 8 * sizeof(int)));
+        }
+        ExactWideParams xw;
+        xw.x_cap = std::min<int64_t>(int64_t(1) << 26, std::max<int64_t>(int64_t(1) << 20, int64_t(512) * m->batch_max_cn));
+        xw.xm_cap = xw.x_cap / 16;
+        xw.max_jobs = nseg;
+        CU_TRY(m, m->d_xw_x.reserve(static_cast<size_t>(xw.x_cap)));
+        CU_TRY(m, m->d_xw_xmax.reserve(static_cast<size_t>(xw.xm_cap)));
+        CU_TRY(m, m->d_xw_off.reserve(static_cast<size_t>(nseg) + 1));
+        CU_TRY(m, m->d_xw_moff.reserve(static_cast<size_t>(nseg) + 1));
+        CU_TRY(m, m->d_xw_unit.reserve(static_cast<size_t>(nseg) + 1));
+        xw.xjobs = sp.xjobs.p;
+        xw.xmeta = sp.d_xmeta;
+        xw.xpool = sp.xpool.p;
+        xw.pool = k.pool;
+        xw.xrow_map = sp.xrow_map.p;
+        xw.x_off = m->d_xw_off.p;
+        xw.xm_off = m->d_xw_moff.p;
+        xw.unit_first = m->d_xw_unit.p;
+        xw.meta = m->d_xw_meta;
+        xw.x = m->d_xw_x.p;
+        xw.xmax = m->d_xw_xmax.p;
+        xw.mode = m->exact_mode;
+        xw.oneway = pp.oneway;
+        xw.sq_lowe = pp.sq_lowe;
+        xw.sq_dist = pp.sq_dist;
+        xw.big_list = m->d_big.p;
+        xw.big_count = m->d_counters + 12;
+        xw.replay_list = m->d_cand.p;
+        xw.replay_count = m->d_counters + 8;
+        xw.replay_flags = m->d_replay_flags.p;
+        xw.self_check = m->d_counters + 2;
+        xw.wide_rows = m->d_counters + 13;
+        exact_wide_plan_kernel<<<1, 32, 0, m->stream>>>(xw);
+        CU_TRY(m, cudaGetLastError());
+        exact_dots_kernel<<<m->num_sms * 4, kWideColBlock, 0, m->stream>>>(xw);
+        CU_TRY(m, cudaGetLastError());
+        exact_replay_kernel<<<m->num_sms, 256, 0, m->stream>>>(xw);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches += 3;
+        ex.total_items_dev = m->d_xw_meta + 4;
+    }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);
     scan_kernel<0, PASS, SIGNED><<<m->num_sms, kScanThreads, kScanSmemBytes, m->stream>>>(
         sp.tmap, k.tmap, subset ? *subset->tmap : k.tmap, sp.xjobs.p, sp.item_job.p, 0, 0, idesc, ksteps_of(k), nullptr, 0, ex, nullptr, nullptr);
@@ -614,6 +674,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
              std::vector<int64_t>& out_row, int32_t* dump = nullptr, int64_t dump_ld = 0, int dump_mode = 3) {
     KindPool& k = m->kind[kind_id];
     out_row.assign(specs.size(), -1);
+    m->batch_max_cn = 0;
     std::vector<ScanJob> jobs;
     jobs.reserve(specs.size() + 1);
     // Forward jobs first, then the reverse jobs; each group ordered by candidate view:
@@ -674,6 +735,7 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         j.q_n = s.q_n;
         j.c_row = static_cast<int32_t>(k.off[s.c_view]);
         j.c_n = s.c_n;
+        m->batch_max_cn = std::max(m->batch_max_cn, s.c_n);
         j.out_row = rows;
         j.item_start = static_cast<int32_t>(items);   // reverse jobs: no items in the filter pass
         j.c_view = s.c_view;
@@ -924,11 +986,18 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
             sel.pool = k.pool;
             sel.cand_pool = m->d_cand_pool.p;
             sel.cand_map = m->d_cand_map.p;
+            CU_TRY(m, m->d_cand_cnt.reserve(static_cast<size_t>(fwd_jobs)));
+            CU_TRY(m, cudaMemsetAsync(m->d_cand_cnt.p, 0xff, sizeof(int32_t) * fwd_jobs, m->stream));   // "whole view"
+            sel.cand_cnt = m->d_cand_cnt.p;
             sel.counters = m->d_counters;
             if (k.is_signed) select_candidates_kernel<true><<<fwd_jobs, 1024, 0, m->stream>>>(sel);
             else             select_candidates_kernel<false><<<fwd_jobs, 1024, 0, m->stream>>>(sel);
             CU_TRY(m, cudaGetLastError());
-            m->stats.kernel_launches++;
+            dim3 const cgrid2(fwd_jobs, std::max(1, std::min(64, m->num_sms * 4 / fwd_jobs)));
+            gather_candidates_kernel<<<cgrid2, 256, 0, m->stream>>>(m->d_jobs.p, m->d_cand_cnt.p, m->d_cand_map.p, k.pool,
+                                                                   m->d_cand_pool.p);
+            CU_TRY(m, cudaGetLastError());
+            m->stats.kernel_launches += 2;
             subset.jobs = m->d_jobs_rev.p;
             subset.seg_first = m->d_seg_first_rev.p;
             subset.nseg = njobs - fwd_jobs;
@@ -1061,6 +1130,7 @@ int read_counters(osfm_matcher* m) {
     m->stats.reverse_candidate_rows = static_cast<int64_t>(c[9]);
     m->stats.reverse_restricted_pairs = static_cast<int64_t>(c[10]);
     m->stats.exact_rows = static_cast<int64_t>(c[5]);
+    m->stats.exact_wide_rows = static_cast<int64_t>(c[13]);
     m->stats.last_scan_sm_cycles = static_cast<int64_t>(c[6]);
     m->stats.last_scan_ns = static_cast<int64_t>(c[7]);
     m->stats.candidate_rows = static_cast<int64_t>(c[1]);
@@ -1269,7 +1339,10 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_seg_first.release();
     m->d_rev_of.release(); m->d_item_job.release(); m->d_stash.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
-    m->d_cand_pool.release(); m->d_cand_map.release();
+    m->d_cand_pool.release(); m->d_cand_map.release(); m->d_cand_cnt.release();
+    m->d_xw_x.release(); m->d_xw_xmax.release(); m->d_xw_off.release(); m->d_xw_moff.release(); m->d_xw_unit.release();
+    if (m->d_xw_meta) cudaFree(m->d_xw_meta);
+    m->d_xw_meta = nullptr;
     m->d_replay_flags.release();
     for (auto& sp : m->pass) sp.release();
     if (m->d_counters) cudaFree(m->d_counters);
@@ -3002,6 +3075,7 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
         out->candidate_rows += p->stats.candidate_rows;
         out->slow_rows += p->stats.slow_rows;
         out->exact_rows += p->stats.exact_rows;
+        out->exact_wide_rows += p->stats.exact_wide_rows;
         out->claimed_rows += p->stats.claimed_rows;
         out->reverse_candidate_rows += p->stats.reverse_candidate_rows;
         out->reverse_restricted_pairs += p->stats.reverse_restricted_pairs;
@@ -3019,6 +3093,14 @@ int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
     for (osfm_matcher* p : m->peers) { p->both_directions = m->both_directions; p->reverse_mode = m->reverse_mode; }
     return OSFM_OK;
     OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
+}
+
+int osfm_match_debug_set_exact_path(osfm_matcher* m, int mode) {
+    if (!m || mode < 0 || mode > 1) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
+    m->exact_mode = mode;
+    for (osfm_matcher* p : m->peers) p->exact_mode = mode;
+    return OSFM_OK;
 }
 
 int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode) {

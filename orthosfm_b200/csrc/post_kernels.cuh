@@ -513,6 +513,44 @@ __global__ void __launch_bounds__(256) claim_kernel(ClaimParams p)
     }
 }
 
+// Ordered compaction over a CTA of 1024 threads, each holding kRowsPerThread consecutive rows:
+// given the number of rows a thread keeps, returns the rank of its first kept row among all rows
+// kept so far and advances the running total (the same in every thread).  Two barriers a round.
+constexpr int kRowsPerThread = 8;
+struct BlockRank {
+    int warp_tot[32];
+    int warp_pre[32];
+    int total;
+};
+__device__ __forceinline__ int block_rank(int my_count, int& running, BlockRank& sm)
+{
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = my_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int const t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int const t = sm.warp_tot[lane];
+        int inc2 = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int const u = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += u;
+        }
+        sm.warp_pre[lane] = running + inc2 - t;
+        if (lane == 31) sm.total = running + inc2;
+    }
+    __syncthreads();
+    // (the next round writes warp_pre / total only after its first barrier: these reads are safe)
+    int const rank = sm.warp_pre[warp] + incl - my_count;
+    running = sm.total;
+    return rank;
+}
+
 // Restricted candidate sets for the reverse pass.  One CTA per forward job (pair).  The reverse
 // job of the pair holds its claimed rows against the forward job's query rows; of those only the
 // rows whose own best similarity exceeds tau (below) -- or whose record is not exact -- can
@@ -536,14 +574,14 @@ struct SelectParams {
     const uint8_t* pool;
     uint8_t* cand_pool;
     int32_t* cand_map;
+    int32_t* cand_cnt;           // per forward job: rows kept if the pair is restricted (preset to -1)
     unsigned long long* counters;   // [9] candidate rows kept (cumulative), [10] pairs restricted (cumulative)
 };
 
 template <bool SIGNED>
 __global__ void __launch_bounds__(1024) select_candidates_kernel(SelectParams p)
 {
-    __shared__ int warp_tot[32];
-    __shared__ int running;
+    __shared__ BlockRank sm;
     int const ji = blockIdx.x;
     int const rj = p.rev_of[ji];
     if (rj < 0 || p.surv_cnt[rj] == 0) return;          // nothing claimed: the reverse job has no work
@@ -553,64 +591,70 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(SelectParams p)
     // every claimed value (so they neither beat nor tie one) and at most at the largest second best
     // that still passes the ratio test beside a best of s -- and beside any larger best, the limit
     // being monotone in the best (so they cannot turn an accept into a reject).
-    int const sm = p.smin[rj];
-    int const tau = min(ratio_limit<SIGNED>(sm, p.sq_lowe, p.sq_dist), sm - 1);
+    int const sm_claim = p.smin[rj];
+    int const tau = min(ratio_limit<SIGNED>(sm_claim, p.sq_lowe, p.sq_dist), sm_claim - 1);
     int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
     int64_t const vmax = p.viewmax[job.c_view];
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (int start = 0; start < job.q_n; start += blockDim.x) {
-        int const r = start + threadIdx.x;
-        bool keep = false;
-        if (r < job.q_n) {
-            int2 const rr = p.rowres[job.out_row + r];
-            int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
-            bool const trusted = flag == kRowWideOk ||
-                (flag == kRowPacked && static_cast<int64_t>(p.norm2[job.q_row + r]) * vmax < limit);
-            int const v1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
-            keep = !trusted || v1 > tau;
+    int running = 0;
+    for (int start = 0; start < job.q_n; start += blockDim.x * kRowsPerThread) {
+        int const r0 = start + threadIdx.x * kRowsPerThread;
+        unsigned keep = 0;
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k) {
+            int const r = r0 + k;
+            if (r < job.q_n) {
+                int2 const rr = p.rowres[job.out_row + r];
+                int const flag = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
+                bool const trusted = flag == kRowWideOk ||
+                    (flag == kRowPacked && static_cast<int64_t>(p.norm2[job.q_row + r]) * vmax < limit);
+                int const v1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
+                if (!trusted || v1 > tau) keep |= 1u << k;
+            }
         }
-        unsigned const b = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(b);
-        __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += warp_tot[w];
-        int total = 0;
-        if (threadIdx.x == 0)
-            for (int w = 0; w < 32; ++w) total += warp_tot[w];
-        int const run = running;
-        if (keep) p.cand_map[job.out_row + run + before + __popc(b & ((1u << lane) - 1u))] = r;
-        __syncthreads();
-        if (threadIdx.x == 0) running = run + total;
-        __syncthreads();
+        int rank = block_rank(__popc(keep), running, sm);
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k)
+            if ((keep >> k) & 1u) p.cand_map[job.out_row + rank++] = r0 + k;
     }
     int const cnt = running;
     // not worth it for small views or when most rows stay: the reverse job keeps the whole view
     if (job.q_n < 1024 || 2 * cnt > job.q_n) return;
-    // gather the kept rows (8 threads move one 128-byte row), then zero rows up to a whole number
-    // of candidate tiles, so that the RESOLVE pass never meets a ragged tile.  A zero row has
-    // similarity 0 with every row, below every claimed value of a restricted job (a claimed value
-    // of 0 gives tau = -1, which keeps every row and so the whole view) and no more than the
-    // reference's initial second best of 0.  padded <= q_n / 2 + 255 <= q_n: inside the job's slots.
+    if (threadIdx.x == 0) {
+        // gather_candidates_kernel copies the rows; padded <= q_n / 2 + 255 <= q_n: inside the job's slots
+        ScanJob rjob = p.jobs[rj];
+        rjob.c_row = static_cast<int32_t>(job.out_row);
+        rjob.c_n = (cnt + kBlockN - 1) / kBlockN * kBlockN;
+        rjob.c_view = -1 - rjob.c_view;
+        p.jobs_rev[rj] = rjob;
+        p.cand_cnt[ji] = cnt;
+        atomicAdd(p.counters + 9, static_cast<unsigned long long>(cnt));
+        atomicAdd(p.counters + 10, 1ull);
+    }
+}
+
+// The rows select_candidates_kernel kept (8 threads move one 128-byte row), then zero rows up to a
+// whole number of candidate tiles, so that the RESOLVE pass never meets a ragged tile.  A zero row
+// has similarity 0 with every row, below every claimed value of a restricted job (a claimed value
+// of 0 gives tau = -1, which keeps every row and so the whole view) and no more than the
+// reference's initial second best of 0.  blockIdx.x: forward job; blockIdx.y: slices of its rows.
+__global__ void __launch_bounds__(256) gather_candidates_kernel(const ScanJob* __restrict__ jobs,
+                                                                 const int32_t* __restrict__ cand_cnt,
+                                                                 const int32_t* __restrict__ cand_map,
+                                                                 const uint8_t* __restrict__ pool,
+                                                                 uint8_t* __restrict__ cand_pool)
+{
+    int const cnt = cand_cnt[blockIdx.x];
+    if (cnt < 0) return;
+    ScanJob const job = jobs[blockIdx.x];
     int const padded = (cnt + kBlockN - 1) / kBlockN * kBlockN;
-    for (int e = threadIdx.x; e < padded * 8; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < padded * 8; e += gridDim.y * blockDim.x) {
         int const sidx = e >> 3, part = e & 7;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (sidx < cnt) {
-            int const r = p.cand_map[job.out_row + sidx];
-            v = __ldg(reinterpret_cast<const uint4*>(p.pool + (static_cast<int64_t>(job.q_row) + r) * kRowBytes) + part);
+            int const r = cand_map[job.out_row + sidx];
+            v = __ldg(reinterpret_cast<const uint4*>(pool + (static_cast<int64_t>(job.q_row) + r) * kRowBytes) + part);
         }
-        reinterpret_cast<uint4*>(p.cand_pool + (job.out_row + sidx) * kRowBytes)[part] = v;
-    }
-    if (threadIdx.x == 0) {
-        ScanJob rjob = p.jobs[rj];
-        rjob.c_row = static_cast<int32_t>(job.out_row);
-        rjob.c_n = padded;
-        rjob.c_view = -1 - rjob.c_view;
-        p.jobs_rev[rj] = rjob;
-        atomicAdd(p.counters + 9, static_cast<unsigned long long>(cnt));
-        atomicAdd(p.counters + 10, 1ull);
+        reinterpret_cast<uint4*>(cand_pool + (job.out_row + sidx) * kRowBytes)[part] = v;
     }
 }
 
@@ -759,7 +803,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
         if (cnt == 0) continue;
         ScanJob const job = jobs[j];
         int const x0 = job_xrow[j];
-        for (int e = threadIdx.x; e < cnt * 8; e += blockDim.x) {
+        // blockIdx.y: slices of one job's list (a single pair of large views has few jobs)
+        for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < cnt * 8; e += gridDim.y * blockDim.x) {
             int const s = e >> 3, part = e & 7;
             int64_t const entry = slow_list[job.out_row + s];
             int64_t const src_row = static_cast<int64_t>(job.q_row) + (surv_row(entry) - job.out_row);
@@ -769,6 +814,204 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
             if (part == 0)
                 xrow_map[x0 + s] = claimed_v == nullptr ? entry
                     : surv_entry(surv_row(entry), claimed_v[surv_row(entry)].x, (static_cast<uint64_t>(entry) & kSurvCertified) != 0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exact pass, few rows
+
+// The EXACT scan pass walks a row group's candidate tiles one after the other, which for a
+// handful of rows against a very large view (one pair of 200 000 x 200 000) is one CTA working
+// through hundreds of tiles while the others idle.  When the rows' inner products fit the scratch
+// buffer they are computed here instead, spread over the whole device -- exact_dots_kernel: every
+// inner product of every gathered row (dp4a), plus the largest one per block of 256 columns --
+// and exact_replay_kernel then replays the reference's sequential scan (nearest_neighbor.cc:87-100)
+// one warp per row, skipping the column blocks (and, inside a block, the groups of 32 columns) that
+// hold nothing at or above the row's current second best.  A skipped stretch cannot change the
+// state, and every value that is looked at goes through the same ref_scan_step() and big-candidate
+// bookkeeping as in the scan pass, so both paths give the same rows the same results.
+constexpr int kWideRowBatch = 32;      // gathered rows one CTA holds in shared memory
+constexpr int kWideColBlock = 256;     // columns per block: one per thread
+
+struct ExactWideParams {
+    const ScanJob* xjobs;          // plan_rows_kernel's gathered jobs (rows in xpool, candidates in pool)
+    const int* xmeta;              // plan_rows_kernel: [0] work items, [1] gathered jobs, [2] gathered rows
+    const uint8_t* xpool;
+    const uint8_t* pool;
+    const int64_t* xrow_map;
+    int64_t* x_off;                // per gathered job: offset of its inner products / block maxima
+    int64_t* xm_off;
+    int* unit_first;               // per gathered job: its first (row batch, column block) unit
+    int* meta;                     // [0] 1: this path is taken, [1] units, [4] work items left to the scan pass
+    int32_t* x;
+    int32_t* xmax;
+    int64_t x_cap, xm_cap;
+    int mode;                      // 0: by capacity, 1: always the scan pass
+    int max_jobs;
+    // results, as in the scan pass
+    int32_t* oneway;
+    float sq_lowe, sq_dist;
+    int4* big_list;
+    unsigned long long* big_count;
+    int64_t* replay_list;
+    unsigned long long* replay_count;
+    uint32_t* replay_flags;
+    unsigned long long* self_check;
+    unsigned long long* wide_rows;   // rows that took this path (cumulative)
+};
+
+// One thread: sizes the scratch layout and decides which path the rows take.
+__global__ void exact_wide_plan_kernel(ExactWideParams p)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int const nx = p.xmeta[1];
+    bool ok = p.mode == 0 && nx > 0 && nx <= p.max_jobs;
+    int64_t xo = 0, mo = 0, units = 0;
+    for (int s = 0; ok && s < nx; ++s) {
+        ScanJob const xj = p.xjobs[s];
+        int64_t const ncb = (xj.c_n + kWideColBlock - 1) / kWideColBlock;
+        p.x_off[s] = xo;
+        p.xm_off[s] = mo;
+        p.unit_first[s] = static_cast<int>(units);
+        xo += static_cast<int64_t>(xj.q_n) * xj.c_n;
+        mo += static_cast<int64_t>(xj.q_n) * ncb;
+        units += static_cast<int64_t>((xj.q_n + kWideRowBatch - 1) / kWideRowBatch) * ncb;
+        ok = xo <= p.x_cap && mo <= p.xm_cap && units < (1ll << 30);
+    }
+    if (ok) p.unit_first[nx] = static_cast<int>(units);
+    p.meta[0] = ok ? 1 : 0;
+    p.meta[1] = ok ? static_cast<int>(units) : 0;
+    p.meta[4] = ok ? 0 : p.xmeta[0];
+    if (ok) atomicAdd(p.wide_rows, static_cast<unsigned long long>(p.xmeta[2]));
+}
+
+// largest s with first[s] <= v (first[] ascending, first[0] = 0, n >= 1)
+__device__ __forceinline__ int last_not_above(const int* first, int n, int v) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int const mid = (lo + hi + 1) >> 1;
+        if (first[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kWideColBlock) exact_dots_kernel(ExactWideParams p)
+{
+    if (p.meta[0] == 0) return;
+    __shared__ uint4 rows[kWideRowBatch][8];
+    __shared__ int wmax[kWideRowBatch][kWideColBlock / 32];
+    int const nx = p.xmeta[1], units = p.meta[1];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int const s = last_not_above(p.unit_first, nx, u);
+        ScanJob const xj = p.xjobs[s];
+        int const ncb = (xj.c_n + kWideColBlock - 1) / kWideColBlock;
+        int const rb = (u - p.unit_first[s]) / ncb, cb = (u - p.unit_first[s]) % ncb;
+        int const r0 = rb * kWideRowBatch;
+        int const nr = min(kWideRowBatch, xj.q_n - r0);
+        __syncthreads();                       // the previous unit's rows are no longer read
+        {
+            int const r = threadIdx.x >> 3, part = threadIdx.x & 7;      // 256 threads: 32 rows x 8 parts
+            if (r < nr)
+                rows[r][part] = __ldg(reinterpret_cast<const uint4*>(p.xpool + (static_cast<int64_t>(xj.q_row) + r0 + r) * kRowBytes) + part);
+        }
+        int const col = cb * kWideColBlock + threadIdx.x;
+        bool const live = col < xj.c_n;
+        uint4 c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            c[k] = live ? __ldg(reinterpret_cast<const uint4*>(p.pool + (static_cast<int64_t>(xj.c_row) + col) * kRowBytes) + k)
+                        : make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        int32_t* const xr = p.x + p.x_off[s] + static_cast<int64_t>(r0) * xj.c_n + col;
+        for (int r = 0; r < nr; ++r) {
+            unsigned acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint4 const q = rows[r][k];
+                acc = __dp4a(q.x, c[k].x, acc);
+                acc = __dp4a(q.y, c[k].y, acc);
+                acc = __dp4a(q.z, c[k].z, acc);
+                acc = __dp4a(q.w, c[k].w, acc);
+            }
+            int const v = live ? static_cast<int>(acc) : INT_MIN;
+            if (live) xr[static_cast<int64_t>(r) * xj.c_n] = v;
+            int const m = __reduce_max_sync(0xffffffffu, v);
+            if (lane == 0) wmax[r][warp] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            int m = INT_MIN;
+#pragma unroll
+            for (int w = 0; w < kWideColBlock / 32; ++w) m = max(m, wmax[threadIdx.x][w]);
+            p.xmax[p.xm_off[s] + static_cast<int64_t>(r0 + threadIdx.x) * ncb + cb] = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) exact_replay_kernel(ExactWideParams p)
+{
+    if (p.meta[0] == 0) return;
+    int const nx = p.xmeta[1], total_rows = p.xmeta[2];
+    int const lane = threadIdx.x & 31;
+    int const nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total_rows; w += nwarps) {
+        // the gathered job of row w: xjobs[].out_row ascends, xjobs[nx] is the end marker
+        int lo = 0, hi = nx - 1;
+        while (lo < hi) {
+            int const mid = (lo + hi + 1) >> 1;
+            if (p.xjobs[mid].out_row <= w) lo = mid; else hi = mid - 1;
+        }
+        ScanJob const xj = p.xjobs[lo];
+        int const r = w - static_cast<int>(xj.out_row);
+        int const ncb = (xj.c_n + kWideColBlock - 1) / kWideColBlock;
+        const int32_t* const xr = p.x + p.x_off[lo] + static_cast<int64_t>(r) * xj.c_n;
+        const int32_t* const xm = p.xmax + p.xm_off[lo] + static_cast<int64_t>(r) * ncb;
+        int64_t const entry = p.xrow_map[w];
+        int64_t const g = surv_row(entry);
+
+        int b1 = 0, b2 = 0, i1 = 0, nbig = 0;     // warp-uniform (nearest_neighbor.cc:246-249)
+        for (int cb0 = 0; cb0 < ncb; cb0 += 32) {
+            int const mx = cb0 + lane < ncb ? xm[cb0 + lane] : INT_MIN;
+            if (!__any_sync(0xffffffffu, mx >= b2)) continue;      // nothing in 32 blocks can enter
+            int const nb = min(32, ncb - cb0);
+            for (int l = 0; l < nb; ++l) {
+                // against the second best as it is now (a wrapped store can lower it)
+                if (__shfl_sync(0xffffffffu, mx, l) < b2) continue;
+                int const col0 = (cb0 + l) * kWideColBlock;
+                int x[kWideColBlock / 32];
+#pragma unroll
+                for (int q = 0; q < kWideColBlock / 32; ++q) {
+                    int const col = col0 + q * 32 + lane;
+                    x[q] = col < xj.c_n ? xr[col] : INT_MIN;
+                }
+#pragma unroll
+                for (int q = 0; q < kWideColBlock / 32; ++q) {
+                    if (!__any_sync(0xffffffffu, x[q] >= b2)) continue;
+                    for (int t = 0; t < 32; ++t) {
+                        int const v = __shfl_sync(0xffffffffu, x[q], t);
+                        if (v >= b2) {
+                            int const col = col0 + q * 32 + t;
+                            if (v >= 65536) {
+                                if (nbig < kMaxBigPerRow && lane == 0)
+                                    p.big_list[atomicAdd(p.big_count, 1ull)] =
+                                        make_int4(static_cast<int>(g), static_cast<int>(g >> 32), col, v);
+                                ++nbig;
+                            }
+                            ref_scan_step<false>(v, col, b1, b2, i1);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            bool const ok = passes_tests(ip_to_dist<false>(b1), ip_to_dist<false>(b2), p.sq_lowe, p.sq_dist);
+            p.oneway[g] = ok ? i1 : -1;
+            if (nbig > kMaxBigPerRow && mark_once(p.replay_flags, g))   // cannot be certified by verify_big_kernel
+                p.replay_list[atomicAdd(p.replay_count, 1ull)] = g;
+            if ((static_cast<uint64_t>(entry) & kSurvCertified) != 0 &&
+                (b1 & 0xffff) != static_cast<int>((static_cast<uint64_t>(entry) >> kSurvRowBits) & 0xffffu))
+                atomicAdd(p.self_check, 1ull);
         }
     }
 }
@@ -857,38 +1100,29 @@ __global__ void __launch_bounds__(256) copy_twoway_kernel(const PairPart* __rest
 // One CTA per pair part: the surviving (i, j) of matches_1_2 in ascending i -- the
 // order in which the reference builds its correspondence list
 // (src/mve/sfm/bundler_matching.cc:178-192) -- written to list[list_offset[pair] ...].
-// Ranks inside a warp come from a ballot, warp totals from a shared-memory scan.
+// Each thread holds eight consecutive rows; ranks come from block_rank().
 __global__ void __launch_bounds__(1024) compact_kernel(const PairPart* __restrict__ parts,
                                                        const int32_t* __restrict__ dense,
                                                        const int64_t* __restrict__ list_offset,
                                                        int2* __restrict__ list)
 {
-    __shared__ int warp_tot[32];
-    __shared__ int running;
+    __shared__ BlockRank sm;
     PairPart const pp = parts[blockIdx.x];
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t const base = list_offset[pp.pair];
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (int start = 0; start < pp.n1; start += blockDim.x) {
-        int const i = start + threadIdx.x;
-        int const m = i < pp.n1 ? dense[pp.out12 + i] : -1;
-        unsigned const b = __ballot_sync(0xffffffffu, m >= 0);
-        if (lane == 0) warp_tot[warp] = __popc(b);
-        __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += warp_tot[w];
-        int total = 0;
-        if (threadIdx.x == 0)
-            for (int w = 0; w < 32; ++w) total += warp_tot[w];
-        int const run = running;
-        if (m >= 0) {
-            int const rank = run + before + __popc(b & ((1u << lane) - 1u));
-            list[base + rank] = make_int2(i, m);
+    int running = 0;
+    for (int start = 0; start < pp.n1; start += blockDim.x * kRowsPerThread) {
+        int const i0 = start + threadIdx.x * kRowsPerThread;
+        int mt[kRowsPerThread];
+        int kept = 0;
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k) {
+            mt[k] = i0 + k < pp.n1 ? dense[pp.out12 + i0 + k] : -1;
+            kept += mt[k] >= 0;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) running = run + total;
-        __syncthreads();
+        int rank = block_rank(kept, running, sm);
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k)
+            if (mt[k] >= 0) list[base + rank++] = make_int2(i0 + k, mt[k]);
     }
 }
 

@@ -510,6 +510,11 @@ class ExhaustiveMatching:
         executes Matching::twoway_match) instead of one direction + the claimed rows of the other."""
         self._check(self._L.osfm_match_debug_set_both_directions(self._h, int(on)))
 
+    def debug_set_exact_path(self, mode: int) -> None:
+        """A/B switch for the rows that reach 2^16: 0 = CUDA-core inner products + warp-per-row
+        replay when they fit the scratch buffer, 1 = always the tensor-core scan pass."""
+        self._check(self._L.osfm_match_debug_set_exact_path(self._h, mode))
+
     def debug_dump_similarity(self, kind: int, view_q: int, view_c: int) -> np.ndarray:
         k = 0 if kind == KIND_SIFT_U8 else 1
         nq = self._sizes[view_q][k]

@@ -267,6 +267,42 @@ def test_mixed_certified_wrapping_and_doubtful_rows(ora):
     assert 0 < st["exact_rows"] < 400, st           # ... but only on the rows that reach 2^16
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_exact_rows_both_paths(ora, mode):
+    """The rows that reach 2^16 are replayed either from CUDA-core inner products spread over the
+    device (mode 0: they fit the scratch buffer) or by the tensor-core scan pass (mode 1): same
+    results on inflated norms, on arbitrary bytes (every 16-bit lane wraps, the verify / replay
+    route) and through the batched entry point with its reverse pass."""
+    vs = synth.sift_views(20, 2, 2000, noise="renorm")
+    a, b = vs[0].copy(), vs[1].copy()
+    rng = np.random.default_rng(3)
+    hot = rng.choice(2000, 60, replace=False)
+    a[hot[:30]] = np.minimum(a[hot[:30]].astype(np.int32) + 3, 255).astype(np.uint8)
+    b[hot[30:]] = np.minimum(b[hot[30:]].astype(np.int32) + 3, 255).astype(np.uint8)
+    b[hot[:10]] = a[hot[:10]]
+    c = rng.integers(0, 256, (333, 128), dtype=np.uint8)
+    d = rng.integers(0, 256, (517, 128), dtype=np.uint8)
+    d[:100] = c[:100]
+    lsb = synth.sift_views(32, 2, 900)                    # norms drift: many rows reach 2^16
+    sets = [a, b, c, d, lsb[0][:700], lsb[1]]
+    with matcher(sets) as m:
+        m.debug_set_exact_path(mode)
+        for i, j in [(0, 1), (2, 3), (4, 5), (3, 0)]:
+            tw = m.twoway_match(KIND_SIFT_U8, i, j)
+            res = m.pairwise_match(i, j)
+            o12, o21 = ora.twoway("u8", sets[i], sets[j], 0.8)
+            assert np.array_equal(tw.matches_1_2, o12) and np.array_equal(tw.matches_2_1, o21), (i, j)
+            f12, f21 = ora.remove_inconsistent(o12, o21)
+            assert np.array_equal(res.matches_1_2, f12) and np.array_equal(res.matches_2_1, f21), (i, j)
+        assert_clean(m)
+        st = m.stats()
+    assert st["exact_rows"] > 100, st
+    if mode == 0:     # (the lsb pair's rows exceed the scratch buffer sized for views this small)
+        assert 100 < st["exact_wide_rows"] <= st["exact_rows"], st
+    else:
+        assert st["exact_wide_rows"] == 0, st
+
+
 def test_surf_degenerate_rows(ora):
     """Signed kind: rows whose best similarity is negative (index stays 0), exactly zero, and
     duplicates; ragged sizes."""
@@ -670,6 +706,7 @@ def test_config_5_single_large_pair(ora):
     st = m.stats()
     m.close()
     assert st["self_check_failures"] == 0
+    assert st["exact_wide_rows"] == st["exact_rows"] > 0     # a few rows against 200 000: spread over the device
     assert a.shape[0] > 10000 and np.all(np.diff(a[:, 0]) > 0)
     # swapping the views transposes the list
     bs = b[np.argsort(b[:, 1], kind="stable")]
