@@ -547,11 +547,59 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     if (subset) CU_TRY(m, sp.xjobs.reserve(static_cast<size_t>(subset->nseg) + 1));
     // every segment's rows make ceil(rows / 256) items: at most rows / 256 + one per segment
     CU_TRY(m, sp.item_job.reserve(static_cast<size_t>(rows / kItemM) + static_cast<size_t>(subset ? subset->nseg : nseg) + 1));
+    ExactWideParams xw;
+    memset(&xw, 0, sizeof xw);
+    if (PASS == kPassExact) {
+        CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
+        size_t const flag_words = static_cast<size_t>(rows / 32 + 1);
+        CU_TRY(m, m->d_replay_flags.reserve(flag_words));
+        CU_TRY(m, cudaMemsetAsync(m->d_replay_flags.p, 0, flag_words * sizeof(uint32_t), m->stream));
+        CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
+        CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
+        // Few rows against large views: every inner product on CUDA cores, spread over the device,
+        // then a warp-per-row replay; the scan pass then finds no work items.  Decided on the device
+        // (the host does not know how many rows there are, plan_rows_kernel's tail does) by what
+        // fits the scratch buffer.
+        if (!m->d_xw_meta) {
+            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xw_meta), 8 * sizeof(int)));
+            CU_TRY(m, cudaMemset(m->d_xw_meta, 0, 8 * sizeof(int)));
+        }
+        xw.x_cap = std::min<int64_t>(int64_t(1) << 26, std::max<int64_t>(int64_t(1) << 20, int64_t(512) * m->batch_max_cn));
+        xw.xm_cap = xw.x_cap / 16;
+        xw.max_jobs = std::min(nseg, 64);      // the layout is sized by one thread; many candidate views: scan pass
+        CU_TRY(m, m->d_xw_x.reserve(static_cast<size_t>(xw.x_cap)));
+        CU_TRY(m, m->d_xw_xmax.reserve(static_cast<size_t>(xw.xm_cap)));
+        CU_TRY(m, m->d_xw_off.reserve(static_cast<size_t>(nseg) + 1));
+        CU_TRY(m, m->d_xw_moff.reserve(static_cast<size_t>(nseg) + 1));
+        CU_TRY(m, m->d_xw_unit.reserve(static_cast<size_t>(nseg) + 1));
+        xw.xjobs = sp.xjobs.p;
+        xw.xmeta = sp.d_xmeta;
+        xw.xpool = sp.xpool.p;
+        xw.pool = k.pool;
+        xw.xrow_map = sp.xrow_map.p;
+        xw.x_off = m->d_xw_off.p;
+        xw.xm_off = m->d_xw_moff.p;
+        xw.unit_first = m->d_xw_unit.p;
+        xw.meta = m->d_xw_meta;
+        xw.x = m->d_xw_x.p;
+        xw.xmax = m->d_xw_xmax.p;
+        xw.mode = m->exact_mode;
+        xw.oneway = pp.oneway;
+        xw.sq_lowe = pp.sq_lowe;
+        xw.sq_dist = pp.sq_dist;
+        xw.big_list = m->d_big.p;
+        xw.big_count = m->d_counters + 12;
+        xw.replay_list = m->d_cand.p;
+        xw.replay_count = m->d_counters + 8;
+        xw.replay_flags = m->d_replay_flags.p;
+        xw.self_check = m->d_counters + 2;
+        xw.wide_rows = m->d_counters + 13;
+    }
     plan_rows_kernel<<<1, 1024, 0, m->stream>>>(subset ? subset->jobs : m->d_jobs.p,
                                                  subset ? subset->seg_first : m->d_seg_first.p,
                                                  subset ? subset->nseg : nseg, sp.cnt.p,
                                                  sp.xjobs.p, sp.job_xrow.p, sp.d_xmeta,
-                                                 PASS == kPassExact ? m->d_counters + 5 : nullptr, sp.item_job.p);
+                                                 PASS == kPassExact ? m->d_counters + 5 : nullptr, sp.item_job.p, xw);
     CU_TRY(m, cudaGetLastError());
     // few jobs (one pair of two large views): several blocks share a job's list
     int const gather_x = std::min(std::max(njobs, 1), m->num_sms * 16);
@@ -586,61 +634,15 @@ int launch_second_pass(osfm_matcher* m, const KindPool& k, int njobs, int nseg, 
     }
     ex.replay_flags = nullptr;
     if (PASS == kPassExact) {
-        CU_TRY(m, m->d_big.reserve(static_cast<size_t>(rows) * kMaxBigPerRow));
         ex.big_list = m->d_big.p;
-        size_t const flag_words = static_cast<size_t>(rows / 32 + 1);
-        CU_TRY(m, m->d_replay_flags.reserve(flag_words));
-        CU_TRY(m, cudaMemsetAsync(m->d_replay_flags.p, 0, flag_words * sizeof(uint32_t), m->stream));
         ex.replay_flags = m->d_replay_flags.p;
-        CU_TRY(m, cudaMemsetAsync(m->d_counters + 8, 0, sizeof(unsigned long long), m->stream));
-        CU_TRY(m, cudaMemsetAsync(m->d_counters + 12, 0, sizeof(unsigned long long), m->stream));
     }
     if (PASS == kPassExact) {
-        // few rows against large views: every inner product on CUDA cores, spread over the device,
-        // then a warp-per-row replay; the scan pass below then finds no work items.  Decided on the
-        // device (the host does not know how many rows there are) by what fits the scratch buffer.
-        if (!m->d_xw_meta) {
-            CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_xw_meta), 8 * sizeof(int)));
-            CU_TRY(m, cudaMemset(m->d_xw_meta, 0, 8 * sizeof(int)));
-        }
-        ExactWideParams xw;
-        xw.x_cap = std::min<int64_t>(int64_t(1) << 26, std::max<int64_t>(int64_t(1) << 20, int64_t(512) * m->batch_max_cn));
-        xw.xm_cap = xw.x_cap / 16;
-        xw.max_jobs = nseg;
-        CU_TRY(m, m->d_xw_x.reserve(static_cast<size_t>(xw.x_cap)));
-        CU_TRY(m, m->d_xw_xmax.reserve(static_cast<size_t>(xw.xm_cap)));
-        CU_TRY(m, m->d_xw_off.reserve(static_cast<size_t>(nseg) + 1));
-        CU_TRY(m, m->d_xw_moff.reserve(static_cast<size_t>(nseg) + 1));
-        CU_TRY(m, m->d_xw_unit.reserve(static_cast<size_t>(nseg) + 1));
-        xw.xjobs = sp.xjobs.p;
-        xw.xmeta = sp.d_xmeta;
-        xw.xpool = sp.xpool.p;
-        xw.pool = k.pool;
-        xw.xrow_map = sp.xrow_map.p;
-        xw.x_off = m->d_xw_off.p;
-        xw.xm_off = m->d_xw_moff.p;
-        xw.unit_first = m->d_xw_unit.p;
-        xw.meta = m->d_xw_meta;
-        xw.x = m->d_xw_x.p;
-        xw.xmax = m->d_xw_xmax.p;
-        xw.mode = m->exact_mode;
-        xw.oneway = pp.oneway;
-        xw.sq_lowe = pp.sq_lowe;
-        xw.sq_dist = pp.sq_dist;
-        xw.big_list = m->d_big.p;
-        xw.big_count = m->d_counters + 12;
-        xw.replay_list = m->d_cand.p;
-        xw.replay_count = m->d_counters + 8;
-        xw.replay_flags = m->d_replay_flags.p;
-        xw.self_check = m->d_counters + 2;
-        xw.wide_rows = m->d_counters + 13;
-        exact_wide_plan_kernel<<<1, 32, 0, m->stream>>>(xw);
-        CU_TRY(m, cudaGetLastError());
         exact_dots_kernel<<<m->num_sms * 4, kWideColBlock, 0, m->stream>>>(xw);
         CU_TRY(m, cudaGetLastError());
         exact_replay_kernel<<<m->num_sms, 256, 0, m->stream>>>(xw);
         CU_TRY(m, cudaGetLastError());
-        m->stats.kernel_launches += 3;
+        m->stats.kernel_launches += 2;
         ex.total_items_dev = m->d_xw_meta + 4;
     }
     uint32_t const idesc = make_idesc_i8(kHalfM, kBlockN, SIGNED ? 1 : 0, SIGNED ? 1 : 0);

@@ -703,6 +703,72 @@ __global__ void __launch_bounds__(256) fill_item_job_kernel(const ScanJob* __res
     for (int it = first; it < last; ++it) item_job[it] = j;
 }
 
+// ---------------------------------------------------------------- exact pass, few rows
+
+// The EXACT scan pass walks a row group's candidate tiles one after the other, which for a
+// handful of rows against a very large view (one pair of 200 000 x 200 000) is one CTA working
+// through hundreds of tiles while the others idle.  When the rows' inner products fit the scratch
+// buffer they are computed here instead, spread over the whole device -- exact_dots_kernel: every
+// inner product of every gathered row (dp4a), plus the largest one per block of 256 columns --
+// and exact_replay_kernel then replays the reference's sequential scan (nearest_neighbor.cc:87-100)
+// one warp per row, skipping the column blocks (and, inside a block, the groups of 32 columns) that
+// hold nothing at or above the row's current second best.  A skipped stretch cannot change the
+// state, and every value that is looked at goes through the same ref_scan_step() and big-candidate
+// bookkeeping as in the scan pass, so both paths give the same rows the same results.
+constexpr int kWideRowBatch = 32;      // gathered rows one CTA holds in shared memory
+constexpr int kWideColBlock = 256;     // columns per block: one per thread
+
+struct ExactWideParams {
+    const ScanJob* xjobs;          // plan_rows_kernel's gathered jobs (rows in xpool, candidates in pool)
+    const int* xmeta;              // plan_rows_kernel: [0] work items, [1] gathered jobs, [2] gathered rows
+    const uint8_t* xpool;
+    const uint8_t* pool;
+    const int64_t* xrow_map;
+    int64_t* x_off;                // per gathered job: offset of its inner products / block maxima
+    int64_t* xm_off;
+    int* unit_first;               // per gathered job: its first (row batch, column block) unit
+    int* meta;                     // [0] 1: this path is taken, [1] units, [4] work items left to the scan pass
+    int32_t* x;
+    int32_t* xmax;
+    int64_t x_cap, xm_cap;
+    int mode;                      // 0: by capacity, 1: always the scan pass
+    int max_jobs;
+    // results, as in the scan pass
+    int32_t* oneway;
+    float sq_lowe, sq_dist;
+    int4* big_list;
+    unsigned long long* big_count;
+    int64_t* replay_list;
+    unsigned long long* replay_count;
+    uint32_t* replay_flags;
+    unsigned long long* self_check;
+    unsigned long long* wide_rows;   // rows that took this path (cumulative)
+};
+
+// One thread (the tail of plan_rows_kernel): sizes the scratch layout and decides which path the
+// rows take.
+__device__ __forceinline__ void exact_wide_plan(ExactWideParams const& p, const ScanJob* xjobs, int items, int nx, int rows)
+{
+    bool ok = p.mode == 0 && nx > 0 && nx <= p.max_jobs;
+    int64_t xo = 0, mo = 0, units = 0;
+    for (int s = 0; ok && s < nx; ++s) {
+        ScanJob const xj = xjobs[s];
+        int64_t const ncb = (xj.c_n + kWideColBlock - 1) / kWideColBlock;
+        p.x_off[s] = xo;
+        p.xm_off[s] = mo;
+        p.unit_first[s] = static_cast<int>(units);
+        xo += static_cast<int64_t>(xj.q_n) * xj.c_n;
+        mo += static_cast<int64_t>(xj.q_n) * ncb;
+        units += static_cast<int64_t>((xj.q_n + kWideRowBatch - 1) / kWideRowBatch) * ncb;
+        ok = xo <= p.x_cap && mo <= p.xm_cap && units < (1ll << 30);
+    }
+    if (ok) p.unit_first[nx] = static_cast<int>(units);
+    p.meta[0] = ok ? 1 : 0;
+    p.meta[1] = ok ? static_cast<int>(units) : 0;
+    p.meta[4] = ok ? 0 : items;
+    if (ok) atomicAdd(p.wide_rows, static_cast<unsigned long long>(rows));
+}
+
 // ---------------------------------------------------------------- exact pass set-up
 
 // Single CTA.  Turns the per-job slow-row counts into the job list of the EXACT scan pass.
@@ -716,7 +782,8 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const ScanJob* __restri
                                                           ScanJob* __restrict__ xjobs, int* __restrict__ job_xrow,
                                                           int* __restrict__ meta,
                                                           unsigned long long* __restrict__ rows_total,
-                                                          int32_t* __restrict__ item_job)
+                                                          int32_t* __restrict__ item_job,
+                                                          ExactWideParams wide)
 {
     __shared__ int wsum[3][32];
     __shared__ int run[3];
@@ -784,6 +851,7 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const ScanJob* __restri
         meta[1] = run[2];
         meta[2] = run[0];
         if (run[0] > 0 && rows_total != nullptr) atomicAdd(rows_total, static_cast<unsigned long long>(run[0]));   // cumulative
+        if (wide.meta != nullptr) exact_wide_plan(wide, xjobs, run[1], run[2], run[0]);      // EXACT pass: which way do the rows go?
     }
 }
 
@@ -818,72 +886,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const ScanJob* __restr
     }
 }
 
-// ---------------------------------------------------------------- exact pass, few rows
-
-// The EXACT scan pass walks a row group's candidate tiles one after the other, which for a
-// handful of rows against a very large view (one pair of 200 000 x 200 000) is one CTA working
-// through hundreds of tiles while the others idle.  When the rows' inner products fit the scratch
-// buffer they are computed here instead, spread over the whole device -- exact_dots_kernel: every
-// inner product of every gathered row (dp4a), plus the largest one per block of 256 columns --
-// and exact_replay_kernel then replays the reference's sequential scan (nearest_neighbor.cc:87-100)
-// one warp per row, skipping the column blocks (and, inside a block, the groups of 32 columns) that
-// hold nothing at or above the row's current second best.  A skipped stretch cannot change the
-// state, and every value that is looked at goes through the same ref_scan_step() and big-candidate
-// bookkeeping as in the scan pass, so both paths give the same rows the same results.
-constexpr int kWideRowBatch = 32;      // gathered rows one CTA holds in shared memory
-constexpr int kWideColBlock = 256;     // columns per block: one per thread
-
-struct ExactWideParams {
-    const ScanJob* xjobs;          // plan_rows_kernel's gathered jobs (rows in xpool, candidates in pool)
-    const int* xmeta;              // plan_rows_kernel: [0] work items, [1] gathered jobs, [2] gathered rows
-    const uint8_t* xpool;
-    const uint8_t* pool;
-    const int64_t* xrow_map;
-    int64_t* x_off;                // per gathered job: offset of its inner products / block maxima
-    int64_t* xm_off;
-    int* unit_first;               // per gathered job: its first (row batch, column block) unit
-    int* meta;                     // [0] 1: this path is taken, [1] units, [4] work items left to the scan pass
-    int32_t* x;
-    int32_t* xmax;
-    int64_t x_cap, xm_cap;
-    int mode;                      // 0: by capacity, 1: always the scan pass
-    int max_jobs;
-    // results, as in the scan pass
-    int32_t* oneway;
-    float sq_lowe, sq_dist;
-    int4* big_list;
-    unsigned long long* big_count;
-    int64_t* replay_list;
-    unsigned long long* replay_count;
-    uint32_t* replay_flags;
-    unsigned long long* self_check;
-    unsigned long long* wide_rows;   // rows that took this path (cumulative)
-};
-
-// One thread: sizes the scratch layout and decides which path the rows take.
-__global__ void exact_wide_plan_kernel(ExactWideParams p)
-{
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int const nx = p.xmeta[1];
-    bool ok = p.mode == 0 && nx > 0 && nx <= p.max_jobs;
-    int64_t xo = 0, mo = 0, units = 0;
-    for (int s = 0; ok && s < nx; ++s) {
-        ScanJob const xj = p.xjobs[s];
-        int64_t const ncb = (xj.c_n + kWideColBlock - 1) / kWideColBlock;
-        p.x_off[s] = xo;
-        p.xm_off[s] = mo;
-        p.unit_first[s] = static_cast<int>(units);
-        xo += static_cast<int64_t>(xj.q_n) * xj.c_n;
-        mo += static_cast<int64_t>(xj.q_n) * ncb;
-        units += static_cast<int64_t>((xj.q_n + kWideRowBatch - 1) / kWideRowBatch) * ncb;
-        ok = xo <= p.x_cap && mo <= p.xm_cap && units < (1ll << 30);
-    }
-    if (ok) p.unit_first[nx] = static_cast<int>(units);
-    p.meta[0] = ok ? 1 : 0;
-    p.meta[1] = ok ? static_cast<int>(units) : 0;
-    p.meta[4] = ok ? 0 : p.xmeta[0];
-    if (ok) atomicAdd(p.wide_rows, static_cast<unsigned long long>(p.xmeta[2]));
-}
+// ---------------------------------------------------------------- exact pass, few rows (kernels)
 
 // largest s with first[s] <= v (first[] ascending, first[0] = 0, n >= 1)
 __device__ __forceinline__ int last_not_above(const int* first, int n, int v) {
