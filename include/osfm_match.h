@@ -418,6 +418,8 @@ typedef struct {
     int64_t reverse_candidate_rows;   /* rows in those subsets, cumulative */
     int64_t exact_wide_rows;     /* of exact_rows: replayed from CUDA-core inner products spread over the device
                                     (few rows against large views) instead of by the scan pass; cumulative */
+    int64_t float_filter_rows;   /* float path: rows that went through the tensor-core filter first, cumulative */
+    int64_t float_exact_rows;    /* ... of which the filter could not decide (evaluated by the exact kernel) */
 } osfm_match_stats;
 
 int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out);
@@ -432,6 +434,17 @@ int osfm_match_debug_set_scan_mode(osfm_matcher* m, int mode);
  * those are held against the whole other view instead of the subset of its rows that can matter.
  * on = 0: the default.  Same results in every mode; for A/B tests and timing. */
 int osfm_match_debug_set_both_directions(osfm_matcher* m, int on);
+/* Float path (osfm_match_twoway_f32).  mode 0 (default): pairs of at least 2^20 comparisons go
+ * through the tensor-core filter (tf32 hi/lo split, fp32 accumulate) and only the rows it cannot
+ * decide within its error bound through the exact CUDA-core kernel; smaller pairs through the exact
+ * kernel alone.  mode 1: the exact kernel alone.  mode 2: always the filter first.  The match
+ * vectors are the same in every mode. */
+int osfm_match_debug_set_float_path(osfm_matcher* m, int mode);
+/* The filter's view of one pair: per row of set_1 (then of set_2) its largest and second largest
+ * similarity as the tensor cores computed them and the index of the largest.  s1 / s2 / j1:
+ * n1 + n2 entries each. */
+int osfm_match_debug_float_filter(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2, int dim,
+    float* s1, float* s2, int32_t* j1);
 /* Rows whose similarities reach 2^16 are replayed exactly.  mode 0 (default): when their inner
  * products fit a scratch buffer they are computed on CUDA cores across the whole device and
  * replayed one warp per row; otherwise by the tensor-core scan pass.  mode 1: always the scan

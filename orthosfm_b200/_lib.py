@@ -32,7 +32,7 @@ EXPORTS = [
     "osfm_ransac_draw_samples", "osfm_ransac_fundamental", "osfm_match_two_view",
     "osfm_match_ransac_default_options",
     "osfm_match_get_stats", "osfm_match_debug_set_scan_mode", "osfm_match_debug_dump_similarity", "osfm_match_debug_dump_packed", "osfm_match_debug_trace",
-    "osfm_match_debug_set_both_directions", "osfm_match_debug_set_exact_path", "osfm_match_set_lookahead",
+    "osfm_match_debug_set_both_directions", "osfm_match_debug_set_exact_path", "osfm_match_debug_set_float_path", "osfm_match_debug_float_filter", "osfm_match_set_lookahead",
     "osfm_match_create_multi", "osfm_match_num_devices",
 ]
 
@@ -62,7 +62,7 @@ class Stats(C.Structure):
                 ("exact_rows", C.c_int64), ("last_scan_sm_cycles", C.c_int64), ("last_scan_ns", C.c_int64),
                 ("claimed_rows", C.c_int64), ("last_phase_ms", C.c_double * 8),
                 ("reverse_restricted_pairs", C.c_int64), ("reverse_candidate_rows", C.c_int64),
-                ("exact_wide_rows", C.c_int64)]
+                ("exact_wide_rows", C.c_int64), ("float_filter_rows", C.c_int64), ("float_exact_rows", C.c_int64)]
 
     PHASES = ("filter", "classify", "resolve_fwd", "claim", "resolve_rev", "mutual", "compact")
 
@@ -153,6 +153,8 @@ def load() -> C.CDLL:
     L.osfm_match_debug_set_scan_mode.argtypes = [vp, C.c_int]
     L.osfm_match_debug_set_both_directions.argtypes = [vp, C.c_int]
     L.osfm_match_debug_set_exact_path.argtypes = [vp, C.c_int]
+    L.osfm_match_debug_set_float_path.argtypes = [vp, C.c_int]
+    L.osfm_match_debug_float_filter.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, f32p, f32p, i32p]
     L.osfm_match_set_lookahead.argtypes = [vp, C.c_int]
     L.osfm_match_debug_dump_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.osfm_match_debug_trace.argtypes = [vp, i32p, C.c_int, i64p, C.c_int64]

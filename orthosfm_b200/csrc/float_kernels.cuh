@@ -40,9 +40,13 @@ struct FloatRowState {
 
 // set_q: n_q x 128 floats, set_c: n_c x 128 floats (both zero-padded beyond the descriptor
 // length).  out[i] = index of the match of query i in set_c, or -1.
+// row_list (may be null): only the query rows row_list[0 .. *list_count) are evaluated -- the rows
+// the tensor-core filter could not decide (float_tc_kernels.cuh); the grid covers n_q rows and the
+// CTAs beyond the list leave at once.
 __global__ void __launch_bounds__(kFloatThreads)
 float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __restrict__ set_c, int n_c,
-                    float sq_lowe, float sq_dist, int32_t* __restrict__ out)
+                    float sq_lowe, float sq_dist, int32_t* __restrict__ out,
+                    const int32_t* __restrict__ row_list, const int* __restrict__ list_count)
 {
     extern __shared__ float4 fsmem4[];
     float* const As = reinterpret_cast<float*>(fsmem4);
@@ -52,12 +56,15 @@ float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __res
     int const tx = threadIdx.x & 15;   // column block: candidates tx*4 .. tx*4+3 of a tile
     int const ty = threadIdx.x >> 4;   // row block: queries ty*4 .. ty*4+3
     int const row0 = blockIdx.x * kFM;
+    int const n_rows = row_list != nullptr ? min(*list_count, n_q) : n_q;
+    if (row0 >= n_rows) return;
+    auto query_row = [&](int r) { return row_list != nullptr ? row_list[row0 + r] : row0 + r; };
 
     // query tile (rows past the end are zero)
     for (int e = threadIdx.x; e < kFM * (kFDim / 4); e += kFloatThreads) {
         int const r = e / (kFDim / 4), c4 = e % (kFDim / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < n_q) v = __ldg(reinterpret_cast<const float4*>(set_q + static_cast<int64_t>(row0 + r) * kFDim) + c4);
+        if (row0 + r < n_rows) v = __ldg(reinterpret_cast<const float4*>(set_q + static_cast<int64_t>(query_row(r)) * kFDim) + c4);
         *reinterpret_cast<float4*>(As + r * kFPitch + c4 * 4) = v;
     }
 
@@ -140,7 +147,7 @@ float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __res
                 second = fmaxf(second, o.b1);
             }
         }
-        if (row0 + r < n_q) {
+        if (row0 + r < n_rows) {
             // std::max(0.0f, 2.0f - 2.0f * ip) (:287-288), mul and sub separately rounded
             float d1 = __fsub_rn(2.0f, __fmul_rn(2.0f, best.b1));
             float d2 = __fsub_rn(2.0f, __fmul_rn(2.0f, second));
@@ -148,7 +155,7 @@ float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __res
             d2 = 0.0f < d2 ? d2 : 0.0f;
             bool ok = !(d1 > sq_dist);                       // matching.h:138
             if (ok && __fdiv_rn(d1, d2) > sq_lowe) ok = false;   // :140-143, NaN accepts
-            out[row0 + r] = ok ? best.i1 : -1;
+            out[query_row(r)] = ok ? best.i1 : -1;
         }
     }
 }

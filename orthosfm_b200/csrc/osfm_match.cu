@@ -30,6 +30,7 @@
 
 #include "../../include/osfm_match.h"
 #include "float_kernels.cuh"
+#include "float_tc_kernels.cuh"
 #include "io_formats.cuh"
 #include "post_kernels.cuh"
 #include "ransac_kernels.cuh"
@@ -224,6 +225,13 @@ struct osfm_matcher {
     size_t rs_stage_ints = 0;
     cudaEvent_t rs_stage_free[2] = {nullptr, nullptr};
     DevBuf<float> d_ftmp;
+    // float path, tensor-core filter (float_tc_kernels.cuh): hi / lo parts, norms, the filter's row records,
+    // the rows left to the exact kernel
+    DevBuf<float> d_fsplit, d_fnorm;
+    DevBuf<FloatTopRow> d_ftop;
+    DevBuf<int32_t> d_flist;
+    int* d_fmeta = nullptr;              // [0], [1]: rows left per direction; [2], [3]: largest norm per set (float bits)
+    int float_mode = 0;                  // 0: by size; 1: exact kernel only; 2: always filter first
     // Float descriptors (osfm_match_set_view_f32) are staged at commit, by a few host threads at
     // once: each copies views into its own page-locked buffers, sends them on and quantises them on
     // its own stream (a single pageable cudaMemcpy moves about 11 GB/s, a fifth of the link).
@@ -382,6 +390,20 @@ int encode_tmap(osfm_matcher* m, CUtensorMap* map, void* base, int64_t rows_with
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(m, OSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return OSFM_OK;
+}
+
+// Float matrix of rows_with_pad x 128 floats (512-byte rows): boxes of 128 bytes x 128 rows, i.e.
+// one 32-float chunk of 128 descriptors, laid out like the 8-bit tiles (SWIZZLE_128B).
+int encode_tmap_f32(osfm_matcher* m, CUtensorMap* map, void* base, int64_t rows_with_pad) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kFDim * 4), static_cast<cuuint64_t>(rows_with_pad)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(kFDim * 4)};
+    cuuint32_t box[2] = {128u, static_cast<cuuint32_t>(kFtM)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(m, OSFM_ERR_CUDA, "cuTensorMapEncodeTiled (float) failed (%d)", (int)r);
     return OSFM_OK;
 }
 
@@ -1342,6 +1364,9 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_rev_of.release(); m->d_item_job.release(); m->d_stash.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
     m->d_cand_pool.release(); m->d_cand_map.release(); m->d_cand_cnt.release();
+    m->d_fsplit.release(); m->d_fnorm.release(); m->d_ftop.release(); m->d_flist.release();
+    if (m->d_fmeta) cudaFree(m->d_fmeta);
+    m->d_fmeta = nullptr;
     m->d_xw_x.release(); m->d_xw_xmax.release(); m->d_xw_off.release(); m->d_xw_moff.release(); m->d_xw_unit.release();
     if (m->d_xw_meta) cudaFree(m->d_xw_meta);
     m->d_xw_meta = nullptr;
@@ -2079,6 +2104,43 @@ int osfm_match_pair_lowres(osfm_matcher* m, int view_1_id, int view_2_id, size_t
 
 // ---- float path ---------------------------------------------------------------------------
 
+// The tensor-core filter of the float path (float_tc_kernels.cuh) for one pair: d1 / d2 are the
+// zero-padded n x 128 float sets on the device.  Afterwards (in stream order) m->d_oneway holds the
+// result of every row the filter decided, m->d_flist / m->d_fmeta the rows it left, per direction.
+static int float_filter(osfm_matcher* m, const float* d1, int n1, const float* d2, int n2, float sq_lowe, float sq_dist) {
+    int const n1p = (n1 + kFtN - 1) / kFtN * kFtN, n2p = (n2 + kFtN - 1) / kFtN * kFtN;
+    size_t const f1 = static_cast<size_t>(n1p) * kFDim, f2 = static_cast<size_t>(n2p) * kFDim;
+    CU_TRY(m, m->d_fsplit.reserve(2 * (f1 + f2)));
+    CU_TRY(m, m->d_fnorm.reserve(static_cast<size_t>(n1) + n2));
+    CU_TRY(m, m->d_ftop.reserve(static_cast<size_t>(n1) + n2));
+    CU_TRY(m, m->d_flist.reserve(static_cast<size_t>(n1) + n2));
+    if (!m->d_fmeta) CU_TRY(m, cudaMalloc(reinterpret_cast<void**>(&m->d_fmeta), 4 * sizeof(int)));
+    CU_TRY(m, cudaMemsetAsync(m->d_fmeta, 0, 4 * sizeof(int), m->stream));
+    float* const hi1 = m->d_fsplit.p;
+    float* const lo1 = hi1 + f1;
+    float* const hi2 = lo1 + f1;
+    float* const lo2 = hi2 + f2;
+    float_split_kernel<<<(n1p * 32 + 255) / 256, 256, 0, m->stream>>>(d1, n1, n1p, hi1, lo1, m->d_fnorm.p, m->d_fmeta + 2);
+    float_split_kernel<<<(n2p * 32 + 255) / 256, 256, 0, m->stream>>>(d2, n2, n2p, hi2, lo2, m->d_fnorm.p + n1, m->d_fmeta + 3);
+    CU_TRY(m, cudaGetLastError());
+    CUtensorMap t_hi1, t_lo1, t_hi2, t_lo2;
+    OS_TRY(encode_tmap_f32(m, &t_hi1, hi1, n1p));
+    OS_TRY(encode_tmap_f32(m, &t_lo1, lo1, n1p));
+    OS_TRY(encode_tmap_f32(m, &t_hi2, hi2, n2p));
+    OS_TRY(encode_tmap_f32(m, &t_lo2, lo2, n2p));
+    CU_TRY(m, cudaFuncSetAttribute(float_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
+    int const items = (n1 + kFtM - 1) / kFtM + (n2 + kFtM - 1) / kFtM;
+    float_filter_kernel<<<std::min(m->num_sms, items), kFtThreads, kFtSmemBytes, m->stream>>>(
+        t_hi1, t_lo1, t_hi2, t_lo2, n1, n2, m->d_ftop.p);
+    CU_TRY(m, cudaGetLastError());
+    float_decide_kernel<<<(n1 + n2 + 255) / 256, 256, 0, m->stream>>>(
+        m->d_ftop.p, m->d_fnorm.p, m->d_fnorm.p + n1, m->d_fmeta + 2, n1, n2, sq_lowe, sq_dist,
+        m->d_oneway.p, m->d_flist.p, m->d_fmeta);
+    CU_TRY(m, cudaGetLastError());
+    m->stats.kernel_launches += 4;
+    return OSFM_OK;
+}
+
 int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2, int dim,
                           float lowe_ratio_threshold, float distance_threshold,
                           int32_t* matches_1_2, int32_t* matches_2_1) {
@@ -2111,15 +2173,65 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
     CU_TRY(m, cudaFuncSetAttribute(float_oneway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFloatSmemBytes));
     float const sq_lowe = lowe_ratio_threshold * lowe_ratio_threshold;    // MATH_POW2 in float
     float const sq_dist = distance_threshold * distance_threshold;
+    // Large pairs: the tensor-core filter decides nearly every row; the exact kernel then sees only
+    // the rows on its list.  Small pairs: the exact kernel alone.
+    bool const filter_first = m->float_mode == 2 ||
+        (m->float_mode == 0 && static_cast<int64_t>(n1) * n2 >= (int64_t(1) << 20));
+    const int32_t* list1 = nullptr;
+    const int32_t* list2 = nullptr;
+    const int* cnt1 = nullptr;
+    const int* cnt2 = nullptr;
+    if (filter_first) {
+        OS_TRY(float_filter(m, d1, n1, d2, n2, sq_lowe, sq_dist));
+        list1 = m->d_flist.p;
+        list2 = m->d_flist.p + n1;
+        cnt1 = m->d_fmeta;
+        cnt2 = m->d_fmeta + 1;
+    }
     float_oneway_kernel<<<(n1 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
-        d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p);
+        d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p, list1, cnt1);
     float_oneway_kernel<<<(n2 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
-        d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1);
+        d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1, list2, cnt2);
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 2;
     CU_TRY(m, cudaMemcpyAsync(matches_1_2, m->d_oneway.p, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaMemcpyAsync(matches_2_1, m->d_oneway.p + n1, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, m->stream));
+    int left[2] = {0, 0};
+    if (filter_first) CU_TRY(m, cudaMemcpyAsync(left, m->d_fmeta, sizeof left, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaStreamSynchronize(m->stream));
+    if (filter_first) {
+        m->stats.float_filter_rows += static_cast<int64_t>(n1) + n2;
+        m->stats.float_exact_rows += static_cast<int64_t>(left[0]) + left[1];
+    }
+    return OSFM_OK;
+    OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
+}
+
+int osfm_match_debug_float_filter(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2, int dim,
+                                  float* s1, float* s2, int32_t* j1) {
+    OSFM_TRY_BEGIN
+    if (!m) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
+    if (!m->stream) return fail(m, OSFM_ERR_STATE, "handle was not created successfully");
+    if (n1 <= 0 || n2 <= 0 || dim <= 0 || dim > kFDim || (dim & 3) != 0 || !set_1 || !set_2 || !s1 || !s2 || !j1)
+        return fail(m, OSFM_ERR_INVALID_ARGUMENT, "float filter dump needs two non-empty sets, dim a multiple of 4 in (0, %d]", kFDim);
+    CU_TRY(m, cudaSetDevice(m->device));
+    size_t const f1 = static_cast<size_t>(n1) * kFDim, f2 = static_cast<size_t>(n2) * kFDim;
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    CU_TRY(m, m->d_ftmp.reserve(f1 + f2));
+    CU_TRY(m, m->d_oneway.reserve(static_cast<size_t>(n1) + n2));
+    float* const d1 = m->d_ftmp.p;
+    float* const d2 = m->d_ftmp.p + f1;
+    if (dim < kFDim) CU_TRY(m, cudaMemsetAsync(m->d_ftmp.p, 0, (f1 + f2) * sizeof(float), m->stream));
+    CU_TRY(m, cudaMemcpy2DAsync(d1, kFDim * sizeof(float), set_1, dim * sizeof(float), dim * sizeof(float), n1,
+                                cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpy2DAsync(d2, kFDim * sizeof(float), set_2, dim * sizeof(float), dim * sizeof(float), n2,
+                                cudaMemcpyHostToDevice, m->stream));
+    OS_TRY(float_filter(m, d1, n1, d2, n2, 0.64f, INFINITY));
+    std::vector<FloatTopRow> top(static_cast<size_t>(n1) + n2);
+    CU_TRY(m, cudaMemcpyAsync(top.data(), m->d_ftop.p, sizeof(FloatTopRow) * top.size(), cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    for (size_t i = 0; i < top.size(); ++i) { s1[i] = top[i].s1; s2[i] = top[i].s2; j1[i] = top[i].j1; }
     return OSFM_OK;
     OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
 }
@@ -3078,6 +3190,8 @@ int osfm_match_get_stats(const osfm_matcher* m, osfm_match_stats* out) {
         out->slow_rows += p->stats.slow_rows;
         out->exact_rows += p->stats.exact_rows;
         out->exact_wide_rows += p->stats.exact_wide_rows;
+        out->float_filter_rows += p->stats.float_filter_rows;
+        out->float_exact_rows += p->stats.float_exact_rows;
         out->claimed_rows += p->stats.claimed_rows;
         out->reverse_candidate_rows += p->stats.reverse_candidate_rows;
         out->reverse_restricted_pairs += p->stats.reverse_restricted_pairs;
@@ -3095,6 +3209,13 @@ int osfm_match_debug_set_both_directions(osfm_matcher* m, int on) {
     for (osfm_matcher* p : m->peers) { p->both_directions = m->both_directions; p->reverse_mode = m->reverse_mode; }
     return OSFM_OK;
     OSFM_TRY_END(m, OSFM_ERR_INTERNAL)
+}
+
+int osfm_match_debug_set_float_path(osfm_matcher* m, int mode) {
+    if (!m || mode < 0 || mode > 2) return OSFM_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> lock(m->mu);
+    m->float_mode = mode;
+    return OSFM_OK;
 }
 
 int osfm_match_debug_set_exact_path(osfm_matcher* m, int mode) {

@@ -321,6 +321,23 @@ class ExhaustiveMatching:
             m12.ctypes.data_as(i32p), m21.ctypes.data_as(i32p)))
         return Matching.Result(m12[:a.shape[0]].copy(), m21[:b.shape[0]].copy())
 
+    def debug_set_float_path(self, mode: int) -> None:
+        """Float path: 0 = tensor-core filter first for large pairs, 1 = exact kernel only,
+        2 = always the filter first.  Same match vectors in every mode."""
+        self._check(self._L.osfm_match_debug_set_float_path(self._h, mode))
+
+    def debug_float_filter(self, set_1, set_2, dim: int = 128):
+        """What the float path's tensor-core filter sees: (s1, s2, j1), each n1 + n2 long."""
+        a = np.ascontiguousarray(set_1, np.float32).reshape(-1, dim)
+        b = np.ascontiguousarray(set_2, np.float32).reshape(-1, dim)
+        n = a.shape[0] + b.shape[0]
+        s1, s2, j1 = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int32)
+        f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        self._check(self._L.osfm_match_debug_float_filter(
+            self._h, _ptr(a), a.shape[0], _ptr(b), b.shape[0], dim,
+            s1.ctypes.data_as(f32p), s2.ctypes.data_as(f32p), j1.ctypes.data_as(i32p)))
+        return s1, s2, j1
+
     # -- batched ------------------------------------------------------------------------------
     def match_pairs(self, pairs, out: Optional[np.ndarray] = None) -> tuple:
         """All pairs in one pass.  Returns (results, n_consistent): a list of

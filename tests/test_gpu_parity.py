@@ -504,6 +504,89 @@ def test_float_path_is_bit_identical_to_reference_order(ora, n1, n2, dim, ratio,
         assert (o12 >= 0).sum() > 10
 
 
+@pytest.mark.parametrize("n1,n2,dim,ratio,dist", [(1, 1, 128, 0.8, None), (300, 500, 128, 0.8, None),
+                                                  (777, 65, 128, 0.9, 0.5), (200, 1000, 64, 0.7, None),
+                                                  (1500, 1500, 128, 0.8, None), (64, 129, 64, 1.0, 0.05),
+                                                  (2500, 2100, 128, 0.8, None), (257, 3000, 128, 0.8, 0.3)])
+def test_float_path_filter_first_gives_the_same_vectors(ora, n1, n2, dim, ratio, dist):
+    """The tensor-core filter (tf32 hi/lo split) decides the rows whose outcome is clear within its
+    error bound and leaves the rest to the exact kernel: the vectors stay the reference's bit for
+    bit -- near duplicates, exact duplicates (ties, d = 0), signed 64-d input, ragged tiles."""
+    rng = np.random.default_rng(n1 * 7 + n2)
+    signed = dim == 64
+    a = rng.standard_normal((n1, dim)) if signed else np.abs(rng.standard_normal((n1, dim)))
+    b = rng.standard_normal((n2, dim)) if signed else np.abs(rng.standard_normal((n2, dim)))
+    a, b = _unit(a), _unit(b)
+    k = min(n1, n2) // 3
+    b[:k] = _unit(a[:k] + 0.02 * rng.standard_normal((k, dim)))
+    if k > 4:
+        b[k:k + 2] = a[:2]
+    thr = 3.402823466e+38 if dist is None else dist
+    with ExhaustiveMatching() as m:
+        m.debug_set_float_path(2)
+        r = m.twoway_match_f32(Matching.Options(dim, ratio, thr), a, b)
+        st = m.stats()
+        m.debug_set_float_path(1)
+        r1 = m.twoway_match_f32(Matching.Options(dim, ratio, thr), a, b)
+    o12, o21 = ora.twoway("f32", a, b, ratio, dist=thr, sse3_order=True)
+    assert np.array_equal(r.matches_1_2, o12) and np.array_equal(r.matches_2_1, o21)
+    assert np.array_equal(r1.matches_1_2, o12) and np.array_equal(r1.matches_2_1, o21)
+    assert st["float_filter_rows"] == n1 + n2
+    if n1 >= 1500 and not signed:       # the filter decides nearly everything
+        assert st["float_exact_rows"] < 0.05 * (n1 + n2), st
+
+
+def test_float_path_filter_unusual_input(ora):
+    """Rows that are not unit vectors (the bound scales with the norms), zero rows, a huge row and
+    non-finite values (everything goes to the exact kernel): same vectors as the exact path."""
+    rng = np.random.default_rng(77)
+    a = np.abs(rng.standard_normal((1100, 128))).astype(np.float32) * rng.uniform(0.01, 30.0, (1100, 1)).astype(np.float32)
+    b = np.abs(rng.standard_normal((1300, 128))).astype(np.float32) * rng.uniform(0.01, 30.0, (1300, 1)).astype(np.float32)
+    b[:300] = a[:300] * np.float32(1.5)
+    a[5] = 0
+    b[7] = 0
+    opts = Matching.Options(128, 0.8, 3.402823466e+38)
+    with ExhaustiveMatching() as m:
+        for variant in range(3):
+            aa, bb = a.copy(), b.copy()
+            if variant == 1:
+                aa[11, 3] = 1e30
+            if variant == 2:
+                bb[13, 5] = np.inf
+                aa[17, 1] = np.nan
+            m.debug_set_float_path(1)
+            want = m.twoway_match_f32(opts, aa, bb)
+            m.debug_set_float_path(2)
+            got = m.twoway_match_f32(opts, aa, bb)
+            assert np.array_equal(got.matches_1_2, want.matches_1_2), variant
+            assert np.array_equal(got.matches_2_1, want.matches_2_1), variant
+            if variant == 0:
+                o12, o21 = ora.twoway("f32", aa, bb, 0.8, dist=3.402823466e+38, sse3_order=True)
+                assert np.array_equal(got.matches_1_2, o12) and np.array_equal(got.matches_2_1, o21)
+
+
+def test_float_filter_error_is_far_below_the_bound():
+    """The similarities the tensor cores produce from the tf32 hi/lo split against float64: the
+    decision rule allows 6e-5 |a| |b|; what is seen must be a small fraction of it."""
+    rng = np.random.default_rng(5)
+    a = _unit(np.abs(rng.standard_normal((700, 128))))
+    b = _unit(np.abs(rng.standard_normal((900, 128))))
+    b[:200] = _unit(a[:200] + 0.01 * rng.standard_normal((200, 128)))
+    a[300:] *= np.float32(7.0)                      # the error scales with the norms
+    with ExhaustiveMatching() as m:
+        s1, s2, j1 = m.debug_float_filter(a, b)
+    S = a.astype(np.float64) @ b.astype(np.float64).T
+    na, nb = np.linalg.norm(a.astype(np.float64), axis=1), np.linalg.norm(b.astype(np.float64), axis=1)
+    for top1, top2, idx, M, nq, ncmax in ((s1[:700], s2[:700], j1[:700], S, na, nb.max()),
+                                          (s1[700:], s2[700:], j1[700:], S.T, nb, na.max())):
+        srt = np.sort(M, axis=1)
+        err1 = np.abs(top1 - srt[:, -1]) / (nq * ncmax)
+        err2 = np.abs(top2 - srt[:, -2]) / (nq * ncmax)
+        assert err1.max() < 3e-6 and err2.max() < 3e-6, (err1.max(), err2.max())
+        picked = M[np.arange(M.shape[0]), idx]
+        assert (np.abs(picked - srt[:, -1]) / (nq * ncmax)).max() < 3e-6
+
+
 def test_float_path_empty_sets():
     a = _unit(np.abs(np.random.default_rng(0).standard_normal((5, 128))))
     with ExhaustiveMatching() as m:
