@@ -753,18 +753,33 @@ def run_ours(args, cfg, config):
             fa /= np.linalg.norm(fa, axis=1, keepdims=True)
             fb /= np.linalg.norm(fb, axis=1, keepdims=True)
             opts_f = Matching.Options(128, 0.8, float(np.finfo(np.float32).max))
-            ts = []
-            for _ in range(4):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                rf = job.m.twoway_match_f32(opts_f, fa, fb)
-                ts.append(time.perf_counter() - t0)
-            s_f = min(ts[1:])
+
+            def time_float(mode):
+                job.m.debug_set_float_path(mode)
+                ts = []
+                for _ in range(4):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    res = job.m.twoway_match_f32(opts_f, fa, fb)
+                    ts.append(time.perf_counter() - t0)
+                return min(ts[1:]), res
+            st0 = job.m.stats()
+            s_f, rf = time_float(0)
+            st1 = job.m.stats()
+            s_x, rx = time_float(1)
+            job.m.debug_set_float_path(0)
             float_path = {"pair_ms": 1e3 * s_f, "comparisons_per_s": n * n / s_f,
                           "matches_1_2": int((rf.matches_1_2 >= 0).sum()),
-                          "note": f"osfm_match_twoway_f32, one pair {n} x {n} x 128 floats, host buffers in and out (H2D "
-                                  f"{2 * n * 512} B inside); CUDA-core kernel, the reference's SSE3 summation order "
-                                  "(bit-identical results, not merely within the tie tolerance)"}
+                          "rows_left_to_the_exact_kernel": (st1["float_exact_rows"] - st0["float_exact_rows"]) // 4,
+                          "rows": 2 * n,
+                          "exact_kernel_only_pair_ms": 1e3 * s_x,
+                          "same_vectors_as_exact_kernel_only": bool(np.array_equal(rf.matches_1_2, rx.matches_1_2)
+                                                                    and np.array_equal(rf.matches_2_1, rx.matches_2_1)),
+                          "note": f"osfm_match_twoway_f32, one pair {n} x {n} x 128 floats, pageable host buffers in and out "
+                                  f"(H2D {2 * n * 512} B inside); tensor-core filter (tcgen05 kind::tf32 on a hi/lo split, three "
+                                  "products, fp32 accumulate) + the exact CUDA-core kernel (the reference's SSE3 summation "
+                                  "order) on the rows the filter cannot decide within its error bound: bit-identical "
+                                  "results, not merely within the tie tolerance"}
         except Exception as ex:  # noqa: BLE001
             float_path = {"error": repr(ex)}
 

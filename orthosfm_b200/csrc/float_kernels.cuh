@@ -38,15 +38,33 @@ struct FloatRowState {
     int i1, pad;
 };
 
+// A row's final state -> its entry of the match vector.
+__device__ __forceinline__ int float_row_result(float b1, float b2, int i1, float sq_lowe, float sq_dist)
+{
+    // std::max(0.0f, 2.0f - 2.0f * ip) (nearest_neighbor.cc:287-288), mul and sub separately rounded
+    float d1 = __fsub_rn(2.0f, __fmul_rn(2.0f, b1));
+    float d2 = __fsub_rn(2.0f, __fmul_rn(2.0f, b2));
+    d1 = 0.0f < d1 ? d1 : 0.0f;
+    d2 = 0.0f < d2 ? d2 : 0.0f;
+    bool ok = !(d1 > sq_dist);                           // matching.h:138
+    if (ok && __fdiv_rn(d1, d2) > sq_lowe) ok = false;   // :140-143, NaN accepts
+    return ok ? i1 : -1;
+}
+
 // set_q: n_q x 128 floats, set_c: n_c x 128 floats (both zero-padded beyond the descriptor
 // length).  out[i] = index of the match of query i in set_c, or -1.
 // row_list (may be null): only the query rows row_list[0 .. *list_count) are evaluated -- the rows
 // the tensor-core filter could not decide (float_tc_kernels.cuh); the grid covers n_q rows and the
-// CTAs beyond the list leave at once.
+// CTAs beyond the list leave at once.  A short list would leave the device to a handful of CTAs
+// walking all candidates, so in that mode blockIdx.y slices the candidate tiles: every CTA writes
+// its rows' states for its slice to parts[list position * gridDim.y + slice], and
+// float_finish_kernel merges the slices (row states merge in any order, see above) and applies the
+// tests.
 __global__ void __launch_bounds__(kFloatThreads)
 float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __restrict__ set_c, int n_c,
                     float sq_lowe, float sq_dist, int32_t* __restrict__ out,
-                    const int32_t* __restrict__ row_list, const int* __restrict__ list_count)
+                    const int32_t* __restrict__ row_list, const int* __restrict__ list_count,
+                    FloatRowState* __restrict__ parts)
 {
     extern __shared__ float4 fsmem4[];
     float* const As = reinterpret_cast<float*>(fsmem4);
@@ -73,7 +91,10 @@ float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __res
 #pragma unroll
     for (int r = 0; r < 4; ++r) { b1[r] = 0.0f; b2[r] = 0.0f; i1[r] = 0; }   // nearest_neighbor.cc:276-279
 
-    for (int col0 = 0; col0 < n_c; col0 += kFN) {
+    int const tiles = (n_c + kFN - 1) / kFN;
+    int const tile_lo = parts != nullptr ? static_cast<int>(static_cast<int64_t>(tiles) * blockIdx.y / gridDim.y) : 0;
+    int const tile_hi = parts != nullptr ? static_cast<int>(static_cast<int64_t>(tiles) * (blockIdx.y + 1) / gridDim.y) : tiles;
+    for (int col0 = tile_lo * kFN; col0 < tile_hi * kFN; col0 += kFN) {
         __syncthreads();   // previous tile fully consumed (and the query tile is visible)
         for (int e = threadIdx.x; e < kFN * (kFDim / 4); e += kFloatThreads) {
             int const r = e / (kFDim / 4), c4 = e % (kFDim / 4);
@@ -148,16 +169,37 @@ float_oneway_kernel(const float* __restrict__ set_q, int n_q, const float* __res
             }
         }
         if (row0 + r < n_rows) {
-            // std::max(0.0f, 2.0f - 2.0f * ip) (:287-288), mul and sub separately rounded
-            float d1 = __fsub_rn(2.0f, __fmul_rn(2.0f, best.b1));
-            float d2 = __fsub_rn(2.0f, __fmul_rn(2.0f, second));
-            d1 = 0.0f < d1 ? d1 : 0.0f;
-            d2 = 0.0f < d2 ? d2 : 0.0f;
-            bool ok = !(d1 > sq_dist);                       // matching.h:138
-            if (ok && __fdiv_rn(d1, d2) > sq_lowe) ok = false;   // :140-143, NaN accepts
-            out[query_row(r)] = ok ? best.i1 : -1;
+            if (parts != nullptr) {
+                best.b2 = second;
+                parts[static_cast<int64_t>(row0 + r) * gridDim.y + blockIdx.y] = best;
+            } else {
+                out[query_row(r)] = float_row_result(best.b1, second, best.i1, sq_lowe, sq_dist);
+            }
         }
     }
+}
+
+// The candidate slices of the listed rows (float_oneway_kernel with parts): one thread per row.
+__global__ void __launch_bounds__(256) float_finish_kernel(const FloatRowState* __restrict__ parts, int slices,
+                                                           const int32_t* __restrict__ row_list,
+                                                           const int* __restrict__ list_count, int n_q,
+                                                           float sq_lowe, float sq_dist, int32_t* __restrict__ out)
+{
+    int const k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(*list_count, n_q)) return;
+    FloatRowState best = parts[static_cast<int64_t>(k) * slices];
+    float second = best.b2;
+    for (int t = 1; t < slices; ++t) {
+        FloatRowState const o = parts[static_cast<int64_t>(k) * slices + t];
+        second = fmaxf(second, o.b2);
+        if (o.b1 > best.b1 || (o.b1 == best.b1 && o.i1 > best.i1)) {
+            second = fmaxf(second, best.b1);
+            best.b1 = o.b1; best.i1 = o.i1;
+        } else {
+            second = fmaxf(second, o.b1);
+        }
+    }
+    out[row_list[k]] = float_row_result(best.b1, second, best.i1, sq_lowe, sq_dist);
 }
 
 }  // namespace osfm

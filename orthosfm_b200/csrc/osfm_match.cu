@@ -230,6 +230,7 @@ struct osfm_matcher {
     DevBuf<float> d_fsplit, d_fnorm;
     DevBuf<FloatTopRow> d_ftop;
     DevBuf<int32_t> d_flist;
+    DevBuf<FloatRowState> d_fparts;      // listed rows x candidate slices (float_oneway_kernel / float_finish_kernel)
     int* d_fmeta = nullptr;              // [0], [1]: rows left per direction; [2], [3]: largest norm per set (float bits)
     int float_mode = 0;                  // 0: by size; 1: exact kernel only; 2: always filter first
     // Float descriptors (osfm_match_set_view_f32) are staged at commit, by a few host threads at
@@ -1364,7 +1365,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_rev_of.release(); m->d_item_job.release(); m->d_stash.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
     m->d_cand_pool.release(); m->d_cand_map.release(); m->d_cand_cnt.release();
-    m->d_fsplit.release(); m->d_fnorm.release(); m->d_ftop.release(); m->d_flist.release();
+    m->d_fsplit.release(); m->d_fnorm.release(); m->d_ftop.release(); m->d_flist.release(); m->d_fparts.release();
     if (m->d_fmeta) cudaFree(m->d_fmeta);
     m->d_fmeta = nullptr;
     m->d_xw_x.release(); m->d_xw_xmax.release(); m->d_xw_off.release(); m->d_xw_moff.release(); m->d_xw_unit.release();
@@ -2188,10 +2189,26 @@ int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const flo
         cnt1 = m->d_fmeta;
         cnt2 = m->d_fmeta + 1;
     }
-    float_oneway_kernel<<<(n1 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
-        d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p, list1, cnt1);
-    float_oneway_kernel<<<(n2 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
-        d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1, list2, cnt2);
+    if (filter_first) {
+        // the listed rows: candidate tiles sliced over blockIdx.y, merged by float_finish_kernel
+        int const s1n = std::min(64, std::max(1, ((n2 + kFN - 1) / kFN) / 4));
+        int const s2n = std::min(64, std::max(1, ((n1 + kFN - 1) / kFN) / 4));
+        CU_TRY(m, m->d_fparts.reserve(static_cast<size_t>(n1) * s1n + static_cast<size_t>(n2) * s2n));
+        FloatRowState* const p1 = m->d_fparts.p;
+        FloatRowState* const p2 = p1 + static_cast<size_t>(n1) * s1n;
+        float_oneway_kernel<<<dim3((n1 + kFM - 1) / kFM, s1n), kFloatThreads, kFloatSmemBytes, m->stream>>>(
+            d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p, list1, cnt1, p1);
+        float_oneway_kernel<<<dim3((n2 + kFM - 1) / kFM, s2n), kFloatThreads, kFloatSmemBytes, m->stream>>>(
+            d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1, list2, cnt2, p2);
+        float_finish_kernel<<<(n1 + 255) / 256, 256, 0, m->stream>>>(p1, s1n, list1, cnt1, n1, sq_lowe, sq_dist, m->d_oneway.p);
+        float_finish_kernel<<<(n2 + 255) / 256, 256, 0, m->stream>>>(p2, s2n, list2, cnt2, n2, sq_lowe, sq_dist, m->d_oneway.p + n1);
+        m->stats.kernel_launches += 2;
+    } else {
+        float_oneway_kernel<<<(n1 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
+            d1, n1, d2, n2, sq_lowe, sq_dist, m->d_oneway.p, nullptr, nullptr, nullptr);
+        float_oneway_kernel<<<(n2 + kFM - 1) / kFM, kFloatThreads, kFloatSmemBytes, m->stream>>>(
+            d2, n2, d1, n1, sq_lowe, sq_dist, m->d_oneway.p + n1, nullptr, nullptr, nullptr);
+    }
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches += 2;
     CU_TRY(m, cudaMemcpyAsync(matches_1_2, m->d_oneway.p, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, m->stream));
