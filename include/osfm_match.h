@@ -200,8 +200,11 @@ int osfm_match_pair_twoway(osfm_matcher* m, int kind, int view_1_id, int view_2_
  * which the reference compiles out of ExhaustiveMatching (DISCRETIZE_DESCRIPTORS 1) but
  * keeps as a static template.  Stateless with respect to the staged views: set_1 is
  * n1 x dim floats, set_2 n2 x dim floats (host pointers, densely packed, dim a multiple of
- * 4 and <= 128).  Inner products are formed in the summation order of the reference's SSE3
- * build, so the results are bit-identical to it, not merely within its tie tolerance.
+ * 4 and <= 128).  Large pairs first go through a tensor-core filter (tf32 hi/lo split, fp32
+ * accumulate) that decides every row whose outcome is clear within its error bound; the other
+ * rows -- and small pairs altogether -- are evaluated with inner products formed in the
+ * summation order of the reference's SSE3 build, so the results are bit-identical to it, not
+ * merely within its tie tolerance.
  * matches_1_2 receives n1 ints, matches_2_1 n2 ints (no mutual filter). */
 int osfm_match_twoway_f32(osfm_matcher* m, const float* set_1, int n1, const float* set_2, int n2,
     int dim, float lowe_ratio_threshold, float distance_threshold,
