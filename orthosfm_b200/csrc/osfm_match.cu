@@ -948,9 +948,13 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         cl.uncert_len = m->d_counters + 11;
         cl.counters = m->d_counters;
         cl.smin = restricted ? m->d_tau.p : nullptr;
-        // the lists' lengths are only known on the device; a thread's work is one long chain of
-        // dependent loads, so the grid covers the longest possible list rather than striding
-        int const cgrid = static_cast<int>(std::min<int64_t>((fwd_rows + 255) / 256, static_cast<int64_t>(m->num_sms) * 256));
+        // The lists' lengths are only known on the device.  A thread's work is one long chain of
+        // dependent loads, so the grid is sized to cover the list without striding where that is
+        // cheap: a quarter of the forward rows is more than the filter lets through on any
+        // descriptor set worth matching (a longer list is strided over), and every block beyond the
+        // list costs ~0.6 ns of launch time.
+        int const cgrid = static_cast<int>(std::min<int64_t>((fwd_rows + 1023) / 1024 + 1, static_cast<int64_t>(m->num_sms) * 256));
+        int const cgrid_rare = std::min(cgrid, m->num_sms * 8);       // lists that are normally (nearly) empty
         cl.rows = m->pass[0].xrow_map.p;          // RESOLVE pass: the entries carry the rows' best similarity
         cl.n_int = m->pass[0].d_xmeta + 2;
         cl.n_ull = nullptr;
@@ -960,11 +964,11 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
             cl.rows = m->d_cand.p;                // rows replayed on CUDA cores (classify_kernel's flat list)
             cl.n_int = nullptr;
             cl.n_ull = m->d_counters + 0;
-            claim_kernel<true, false><<<cgrid, 256, 0, m->stream>>>(cl);
+            claim_kernel<true, false><<<cgrid_rare, 256, 0, m->stream>>>(cl);
         } else {
             cl.rows = m->pass[1].xrow_map.p;      // EXACT pass
             cl.n_int = m->pass[1].d_xmeta + 2;
-            claim_kernel<false, false><<<cgrid, 256, 0, m->stream>>>(cl);
+            claim_kernel<false, false><<<cgrid_rare, 256, 0, m->stream>>>(cl);
         }
         CU_TRY(m, cudaGetLastError());
         m->stats.kernel_launches += 2;

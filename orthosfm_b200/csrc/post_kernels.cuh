@@ -464,12 +464,15 @@ __global__ void __launch_bounds__(256) claim_kernel(ClaimParams p)
                     out_row = rjob.out_row;
                     target = out_row + mt;
                     int2* const slot = p.rowres + target;
+                    // (the certificate's inputs are loaded before the atomic: one round trip less
+                    // in a thread that is a chain of dependent memory operations as it is)
+                    int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
+                    int64_t const qn2 = p.norm2[rjob.q_row + mt];
+                    int64_t const vm = p.viewmax[rjob.c_view];
                     first = atomicMax(&slot->x, s) < 0;
                     if (first) {
                         slot->y = rj;
-                        int64_t const limit = SIGNED ? (1ll << 30) : (1ll << 32);
-                        int64_t const qn2 = p.norm2[rjob.q_row + mt];
-                        certified = qn2 * static_cast<int64_t>(p.viewmax[rjob.c_view]) < limit;
+                        certified = qn2 * vm < limit;
                     }
                 }
             }
