@@ -486,6 +486,20 @@ class Reference(_Impl):
                                                 _ptr(counts, C.c_int), _ptr(digest, C.c_ulonglong))
         return counts[:pr.shape[0]], digest[:pr.shape[0]]
 
+    def match_large_pair_u8(self, set_1, set_2, ratio: float = 0.8):
+        """One large pair on all cores (the reference's oneway_match on chunks of the query rows,
+        then remove_inconsistent_matches): returns (count, digest, m12, m21)."""
+        a = _c(set_1, np.uint8).reshape(-1, 128)
+        b = _c(set_2, np.uint8).reshape(-1, 128)
+        m12 = np.full(max(a.shape[0], 1), -7, dtype=np.int32)
+        m21 = np.full(max(b.shape[0], 1), -7, dtype=np.int32)
+        digest = C.c_ulonglong(0)
+        f = self.lib.osfm_ref_match_large_pair_u8
+        f.restype = C.c_long
+        n = f(_ptr(a, C.c_uint8), C.c_int(a.shape[0]), _ptr(b, C.c_uint8), C.c_int(b.shape[0]), C.c_float(ratio),
+              _ptr(m12, C.c_int), _ptr(m21, C.c_int), C.byref(digest))
+        return int(n), int(digest.value), m12[:a.shape[0]], m21[:b.shape[0]]
+
     def tracks_compute(self, features, pair_views, offsets, ij):
         """The reference's own Tracks::compute through ref_driver.cc."""
         features = _c(features, np.int32)

@@ -210,6 +210,55 @@ osfm_ref_twoway_f32 (const float* set_1, int n1, const float* set_2, int n2,
     copy_out(r.matches_2_1, m21);
 }
 
+/* One LARGE pair on all cores: the reference's own Matching::oneway_match (matching.h:114-146)
+ * called on chunks of the query rows of each direction -- a query's scan of the other set does not
+ * depend on the other queries (matching.h:128-145), so twoway_match (matching.h:148-159) is the
+ * concatenation of the chunks' results -- then remove_inconsistent_matches.  Returns the number of
+ * consistent matches; m12 / m21 receive the filtered vectors, *digest the FNV-1a digest of the
+ * correspondence list as osfm_ref_match_pairs_u8_digest computes it. */
+long
+osfm_ref_match_large_pair_u8 (const uint8_t* set_1, int n1, const uint8_t* set_2, int n2,
+    float ratio, int* m12, int* m21, unsigned long long* digest)
+{
+    auto a = widen<unsigned short>(set_1, (std::size_t)n1 * 128);
+    auto b = widen<unsigned short>(set_2, (std::size_t)n2 * 128);
+    sfm::Matching::Options const opts = make_opts(128, ratio, std::numeric_limits<float>::max());
+    sfm::Matching::Result r;
+    r.matches_1_2.assign(n1, -1);
+    r.matches_2_1.assign(n2, -1);
+    int const chunk = 512;
+    int const c1 = (n1 + chunk - 1) / chunk, c2 = (n2 + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic)
+    for (int c = 0; c < c1 + c2; ++c)
+    {
+        bool const fwd = c < c1;
+        int const row0 = (fwd ? c : c - c1) * chunk;
+        int const rows = std::min(chunk, (fwd ? n1 : n2) - row0);
+        std::vector<int> part;
+        if (fwd)
+            sfm::Matching::oneway_match(opts, a.data() + (std::size_t)row0 * 128, rows, b.data(), n2, &part);
+        else
+            sfm::Matching::oneway_match(opts, b.data() + (std::size_t)row0 * 128, rows, a.data(), n1, &part);
+        std::copy(part.begin(), part.end(), (fwd ? r.matches_1_2 : r.matches_2_1).begin() + row0);
+    }
+    sfm::Matching::remove_inconsistent_matches(&r);
+    unsigned long long h = 1469598103934665603ull;
+    long c = 0;
+    for (std::size_t i = 0; i < r.matches_1_2.size(); ++i)
+    {
+        if (r.matches_1_2[i] < 0)
+            continue;
+        int const rec[2] = { (int)i, r.matches_1_2[i] };
+        unsigned char const* bytes = reinterpret_cast<unsigned char const*>(rec);
+        for (int k = 0; k < 8; ++k) { h ^= bytes[k]; h *= 1099511628211ull; }
+        ++c;
+    }
+    if (m12 != nullptr) copy_out(r.matches_1_2, m12);
+    if (m21 != nullptr) copy_out(r.matches_2_1, m21);
+    if (digest != nullptr) *digest = h;
+    return c;
+}
+
 /* ---- filters ------------------------------------------------------ */
 
 void

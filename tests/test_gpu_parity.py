@@ -804,6 +804,40 @@ def test_config_5_single_large_pair(ora):
         assert got.get(int(r), -1) == (o if (o >= 0 and back == r) else -1), r
 
 
+def test_config_5_full_list_equals_the_reference():
+    """BASELINE config 5 in full: the whole correspondence list of the 200 000 x 200 000 pair
+    against the reference matcher itself (oracle/_ref: its oneway_match on chunks of the query rows
+    over all host cores, 8 x 10^10 executed comparisons: under a minute on 16 cores), by count and
+    64-bit digest."""
+    import os
+    import torch
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    if len(os.sched_getaffinity(0)) < 8:
+        pytest.skip("fewer than 8 host cores: the reference would take minutes")
+    n = 200000
+    dev = torch.device("cuda", 0)
+    pool = synth.torch_sift_views(5, 2, n, dev, noise="renorm")
+    v0, v1 = pool[:n].cpu().numpy(), pool[n:2 * n].cpu().numpy()
+    pool = torch.cat([pool, torch.zeros((256, 128), dtype=torch.uint8, device=dev)])
+    m = ExhaustiveMatching(device=0)
+    m.init_device_pool(pool, np.array([0, n], np.int64), np.array([n, n], np.int32))
+    out = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    loff = m.match_pairs_compact(np.array([[1, 0]], np.int32), out)
+    got = out[:int(loff[1])].cpu().numpy()
+    st = m.stats()
+    m.close()
+    assert st["self_check_failures"] == 0
+    ref = oracle.Reference()
+    ref.use_all_cores()
+    count, digest, m12, _ = ref.match_large_pair_u8(v1, v0, 0.8)
+    assert got.shape[0] == count
+    assert oracle.list_digest(got) == digest
+    rows = np.flatnonzero(m12 >= 0)
+    assert np.array_equal(got[:, 0], rows) and np.array_equal(got[:, 1], m12[rows])
+
+
 def test_more_rows_than_one_batch(ora):
     """40 views x 16384, all 780 pairs: 25.6 M job rows, i.e. more than the 16 M rows one batch
     of scratch memory holds; lists of pairs from every batch against the oracle (sampled rows),

@@ -336,3 +336,22 @@ def test_fundamental_on_non_finite_and_extreme_input_equals_reference():
         F2 = hc.fundamental(m[:, :2], m[:, 2:])
         F3, _ = hc.fundamental_staged(m[:, :2], m[:, 2:])
         assert np.array_equal(F1, F2, equal_nan=True) and np.array_equal(F1, F3, equal_nan=True), (t, kind)
+
+
+def test_reference_large_pair_entry_equals_the_pairwise_entry():
+    """osfm_ref_match_large_pair_u8 (the reference's oneway_match on chunks of the query rows, over
+    OpenMP threads) against osfm_ref_match_pairs_u8_digest (its twoway_match on the whole sets):
+    same count, digest and vectors, with set sizes that are no multiple of the chunk."""
+    import oracle
+    from orthosfm_b200 import synth
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = oracle.Reference()
+    v = synth.sift_views(41, 2, 1400, noise="renorm")
+    a, b = v[0][:1333], v[1][:1100]
+    counts, digests = ref.match_pairs_u8_digest([a, b], np.array([[0, 1]], np.int32), 0.8)
+    count, digest, m12, m21 = ref.match_large_pair_u8(a, b, 0.8)
+    assert count == counts[0] > 50 and digest == digests[0]
+    t12, t21 = ref.twoway("u8", a, b, 0.8)
+    f12, f21 = ref.remove_inconsistent(t12, t21)
+    assert np.array_equal(m12, f12) and np.array_equal(m21, f21)
