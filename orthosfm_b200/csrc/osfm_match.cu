@@ -1537,6 +1537,8 @@ int osfm_match_begin(osfm_matcher* m, int num_views) { return begin_impl(m, num_
 
 int osfm_match_begin_overlapped(osfm_matcher* m, int num_views) { return begin_impl(m, num_views, true); }
 
+constexpr int kFloatChunkRows = 2048;      // rows of a float view one staging step (run_float_views) moves
+
 // Stages one view of one kind at the end of the arena.  All copies are asynchronous on the
 // handle's stream; the source must stay valid until osfm_match_commit() returns.
 static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n, int stride, bool is_float) {
@@ -1555,7 +1557,11 @@ static int stage_view(osfm_matcher* m, int kd, int view, const void* src, int n,
         if (m->overlap) return fail(m, OSFM_ERR_STATE, "overlapped staging takes quantised descriptors (set_view_q8)");
         if (stride < k.dim) return fail(m, OSFM_ERR_INVALID_ARGUMENT, "stride %d < descriptor length %d", stride, k.dim);
         // moved at commit (run_float_views); the source stays valid until then
-        m->float_views.push_back({kd, k.arena_used, static_cast<const float*>(src), n, stride});
+        // (in chunks of rows: the first transfer starts after a fraction of a view has been copied
+        // into page-locked memory, and the lanes' buffers stay small)
+        for (int r0 = 0; r0 < n; r0 += kFloatChunkRows)
+            m->float_views.push_back({kd, k.arena_used + r0, static_cast<const float*>(src) + static_cast<size_t>(r0) * stride,
+                                      std::min(kFloatChunkRows, n - r0), stride});
         (void)d;
     } else if (k.dim == kRowBytes) {
         CU_TRY(m, cudaMemcpyAsync(d, src, static_cast<size_t>(n) * kRowBytes, cudaMemcpyHostToDevice, cs));
@@ -1637,7 +1643,7 @@ static int run_float_views(osfm_matcher* m) {
     for (auto const& v : views)
         max_floats = std::max(max_floats, static_cast<size_t>(v.n - 1) * v.stride + m->kind[v.kd].dim);
     unsigned const hw = std::max(1u, std::thread::hardware_concurrency());
-    size_t const lanes = std::min<size_t>(std::min<size_t>(8, std::max(1u, hw / 2)), views.size());
+    size_t const lanes = std::min<size_t>(std::min<size_t>(12, std::max(1u, hw * 3 / 4)), views.size());
     CU_TRY(m, cudaStreamSynchronize(m->stream));          // the arena may just have been moved
     if (m->float_lanes.size() < lanes) m->float_lanes.resize(lanes);
     for (size_t l = 0; l < lanes; ++l) {
