@@ -201,6 +201,12 @@ struct osfm_matcher {
 
     DevBuf<ScanJob> d_jobs;
     DevBuf<int2> d_rowres;
+    // few work items (one pair of large views): the filter pass runs on column segments of the jobs
+    // (run_jobs), its records land in d_rowres_part and merge_split_kernel folds them
+    DevBuf<ScanJob> d_fjobs;
+    DevBuf<int2> d_rowres_part;
+    const ScanJob* filter_jobs = nullptr;      // what launch_scan_t hands to the kernel (null: d_jobs / d_rowres)
+    int2* filter_rowres = nullptr;
     DevBuf<int32_t> d_oneway;
     DevBuf<int64_t> d_cand;
     DevBuf<int64_t> d_cand_rev;          // claimed rows without the norm certificate (reverse pass)
@@ -529,7 +535,8 @@ cudaError_t launch_scan_t(osfm_matcher* m, const KindPool& k, int item_first, in
     ex.norm2 = k.d_norm2.p;
     ex.viewmax = k.d_viewmax.p;
     scan_kernel<MODE, kPassFilter, SIGNED><<<grid, kScanThreads, kScanSmemBytes, m->stream>>>(
-        k.tmap, k.tmap, k.tmap, m->d_jobs.p, m->d_item_job.p, item_first, total_items, idesc, ksteps_of(k), dump, dump_ld, ex, m->d_rowres.p,
+        k.tmap, k.tmap, k.tmap, m->filter_jobs ? m->filter_jobs : m->d_jobs.p, m->d_item_job.p, item_first, total_items, idesc,
+        ksteps_of(k), dump, dump_ld, ex, m->filter_rowres ? m->filter_rowres : m->d_rowres.p,
         m->d_counters + 6);
     return cudaGetLastError();
 }
@@ -817,8 +824,63 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
     float const sq_lowe = k.lowe * k.lowe;  // MATH_POW2 in float (matching.h:126)
     float const sq_dist = k.dist * k.dist;  // FLT_MAX^2 = +inf: never rejects (matching.h:127)
 
-    CU_TRY(m, m->d_item_job.reserve(static_cast<size_t>(items) + 1));
-    fill_item_job_kernel<<<(njobs + 255) / 256, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_item_job.p);
+    // A batch with few work items (one pair of two large views: 782 items for 200 000 rows, 5.3 waves
+    // of 148 CTAs rounded up to 6) is cut along the candidates as well: every forward job becomes
+    // `split` jobs over consecutive column segments, the filter's (best, bound on the second best)
+    // records of the segments are folded afterwards (merge_split_kernel; the fold is the one the
+    // filter's own epilogue applies to its column halves), and everything downstream sees the
+    // records of whole jobs.  `split` minimises waves x tiles per item.
+    int split = 1;
+    if (!staged && dump == nullptr && m->scan_mode == 0 && fwd_jobs > 0 && items < 8ll * m->num_sms) {
+        int max_tiles = 0;
+        for (int j = 0; j < fwd_jobs; ++j) max_tiles = std::max(max_tiles, (jobs[j].c_n + kBlockN - 1) / kBlockN);
+        int64_t best = (items + m->num_sms - 1) / m->num_sms * max_tiles;
+        for (int sp = 2; sp <= 16 && max_tiles / sp >= 8; ++sp) {
+            // (+ 1 tile per item: the query tile's load and the item's tail are not free)
+            int64_t const cost = (items * sp + m->num_sms - 1) / m->num_sms * ((max_tiles + sp - 1) / sp + 1);
+            if (cost < best) { best = cost; split = sp; }
+        }
+        if (static_cast<int64_t>(fwd_jobs) * split > kRowJobMask || items * split > INT32_MAX) split = 1;
+    }
+    int64_t filter_items = items;
+    if (split > 1) {
+        std::vector<ScanJob> fjobs;
+        fjobs.reserve(static_cast<size_t>(fwd_jobs) * split + 1);
+        int64_t fitems = 0;
+        for (int sgm = 0; sgm < split; ++sgm)
+            for (int j = 0; j < fwd_jobs; ++j) {
+                ScanJob f = jobs[j];
+                int const tiles = (f.c_n + kBlockN - 1) / kBlockN;
+                int const t0 = static_cast<int>(static_cast<int64_t>(tiles) * sgm / split);
+                int const t1 = static_cast<int>(static_cast<int64_t>(tiles) * (sgm + 1) / split);
+                f.c_row = jobs[j].c_row + t0 * kBlockN;
+                f.c_n = std::min(jobs[j].c_n, t1 * kBlockN) - t0 * kBlockN;      // 0: a view with fewer tiles than segments
+                f.out_row = static_cast<int64_t>(sgm) * fwd_rows + jobs[j].out_row;
+                f.item_start = static_cast<int32_t>(fitems);
+                if (f.c_n > 0) fitems += (f.q_n + kItemM - 1) / kItemM;
+                fjobs.push_back(f);
+            }
+        ScanJob fs;
+        memset(&fs, 0, sizeof fs);
+        fs.out_row = static_cast<int64_t>(split) * fwd_rows;
+        fs.item_start = static_cast<int32_t>(fitems);
+        fjobs.push_back(fs);
+        filter_items = fitems;
+        CU_TRY(m, m->d_fjobs.reserve(fjobs.size()));
+        CU_TRY(m, cudaMemcpyAsync(m->d_fjobs.p, fjobs.data(), sizeof(ScanJob) * fjobs.size(), cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(m, m->d_rowres_part.reserve(static_cast<size_t>(split) * fwd_rows));
+        // (a segment without columns writes nothing: its records must read as "nothing seen", y = -1)
+        CU_TRY(m, cudaMemsetAsync(m->d_rowres_part.p, 0xff, sizeof(int2) * static_cast<size_t>(split) * fwd_rows, m->stream));
+        CU_TRY(m, m->d_item_job.reserve(static_cast<size_t>(fitems) + 1));
+        fill_item_job_kernel<<<(static_cast<int>(fjobs.size()) - 1 + 255) / 256, 256, 0, m->stream>>>(
+            m->d_fjobs.p, static_cast<int>(fjobs.size()) - 1, m->d_item_job.p);
+        m->filter_jobs = m->d_fjobs.p;
+        m->filter_rowres = m->d_rowres_part.p;
+        bucket_items.back() = fitems;
+    } else {
+        CU_TRY(m, m->d_item_job.reserve(static_cast<size_t>(items) + 1));
+        fill_item_job_kernel<<<(njobs + 255) / 256, 256, 0, m->stream>>>(m->d_jobs.p, njobs, m->d_item_job.p);
+    }
     CU_TRY(m, cudaGetLastError());
     m->stats.kernel_launches++;
     CU_TRY(m, m->phases.mark(m->stream, kPhFilter));
@@ -841,8 +903,17 @@ int run_jobs(osfm_matcher* m, int kind_id, const std::vector<JobSpec>& specs,
         m->stats.kernel_launches++;
         launched = last;
     }
+    m->filter_jobs = nullptr;
+    m->filter_rowres = nullptr;
+    if (split > 1) {
+        int const mgrid = static_cast<int>((fwd_rows + 255) / 256);
+        if (k.is_signed) merge_split_kernel<true><<<mgrid, 256, 0, m->stream>>>(m->d_rowres_part.p, split, fwd_rows, fwd_jobs, m->d_rowres.p);
+        else             merge_split_kernel<false><<<mgrid, 256, 0, m->stream>>>(m->d_rowres_part.p, split, fwd_rows, fwd_jobs, m->d_rowres.p);
+        CU_TRY(m, cudaGetLastError());
+        m->stats.kernel_launches++;
+    }
     CU_TRY(m, m->phases.mark(m->stream, kPhClassify));
-    m->stats.scan_items += items;
+    m->stats.scan_items += filter_items;
     if (dump) { CU_TRY(m, m->phases.mark(m->stream, -1)); return OSFM_OK; }   // debug dumps produce no results
     if (m->scan_mode != 0) {
         // timing modes: the filter wrote no row records, so nothing downstream may look at them;
@@ -1369,6 +1440,7 @@ void osfm_match_destroy(osfm_matcher* m) {
     m->d_rev_of.release(); m->d_item_job.release(); m->d_stash.release();
     m->d_tau.release(); m->d_jobs_rev.release(); m->d_seg_first_rev.release();
     m->d_cand_pool.release(); m->d_cand_map.release(); m->d_cand_cnt.release();
+    m->d_fjobs.release(); m->d_rowres_part.release();
     m->d_fsplit.release(); m->d_fnorm.release(); m->d_ftop.release(); m->d_flist.release(); m->d_fparts.release();
     if (m->d_fmeta) cudaFree(m->d_fmeta);
     m->d_fmeta = nullptr;

@@ -207,6 +207,40 @@ struct PostParams {
     const unsigned long long* slow_len;   // length of slow_list (normally counters + 0)
 };
 
+// ---------------------------------------------------------------- filter pass cut along the candidates
+
+// The filter pass of a batch with few work items runs on `split` column segments per job (run_jobs in
+// osfm_match.cu): part[s * rows + g] is segment s's record of row g, its job field counting the
+// segment jobs (s * jobs + j).  The fold is the one the filter's epilogue applies to its two column
+// halves: best = the larger best, bound on the second best = the largest of the smaller best and
+// the two bounds.  All segments of a row were scanned the same way (the choice depends on the
+// row and the candidate view only); a row that wraps in one segment wraps.  One thread per row.
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) merge_split_kernel(const int2* __restrict__ part, int split, int64_t rows, int jobs,
+                                                          int2* __restrict__ rowres)
+{
+    int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= rows) return;
+    int v1 = 0, v2 = 0, flag = 0, job = 0;
+    bool any = false;
+    for (int s = 0; s < split; ++s) {
+        int2 const rr = part[static_cast<int64_t>(s) * rows + g];
+        if (rr.y == -1) continue;      // a segment without columns (a small view in the batch) wrote nothing
+        int const a1 = SIGNED ? static_cast<int>(static_cast<short>(rr.x & 0xffff)) : (rr.x & 0xffff);
+        int const a2 = SIGNED ? (rr.x >> 16) : static_cast<int>(static_cast<uint32_t>(rr.x) >> 16);
+        int const f = static_cast<int>(static_cast<uint32_t>(rr.y) >> kRowFlagShift);
+        if (!any) {
+            v1 = a1; v2 = a2; flag = f; job = (rr.y & kRowJobMask) % jobs;
+            any = true;
+        } else {
+            v2 = max(max(min(v1, a1), v2), a2);
+            v1 = max(v1, a1);
+            flag = max(flag, f);
+        }
+    }
+    rowres[g] = pack_rowres(v1, v2, job, flag);
+}
+
 // ---------------------------------------------------------------- filter decision
 
 struct ClassifyParams {
